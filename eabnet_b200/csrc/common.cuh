@@ -1,0 +1,170 @@
+// Shared device/host helpers for the eabnet_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace eab {
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing: every launcher returns 0/1 and leaves a message for eab_last_error()
+// ---------------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int  fail(const std::string& msg);                       // sets the message, returns 1
+int  check_cuda(cudaError_t e, const char* what);        // 0 if ok
+void count_launch(int n = 1);                            // per-thread launch counter
+int  launch_count();
+void reset_launch_count();
+
+#define EAB_CUDA(x)                                                   \
+    do {                                                              \
+        if (eab::check_cuda((x), #x)) return 1;                       \
+    } while (0)
+#define EAB_TRY(x)                                                    \
+    do {                                                              \
+        if ((x) != 0) return 1;                                       \
+    } while (0)
+#define EAB_LAUNCH_CHECK(name)                                        \
+    do {                                                              \
+        eab::count_launch();                                          \
+        if (eab::check_cuda(cudaGetLastError(), name)) return 1;      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// On-load activation transform.  Every activation tensor is stored RAW (exactly what its producing
+// conv wrote) next to per-(b,c) double sums {sum, sumsq}; whoever reads it applies
+//     v = x ; [PReLU if prelu==1] ; v = v*s + h ; [PReLU if prelu==2]
+// with (s,h) from the statistics (InstanceNorm: biased variance, eps inside the sqrt, affine;
+// EaBNet.py:684-686), from precomputed per-channel arrays (BatchNorm eval, EaBNet.py:678-681), or identity.
+// 2-D blocks are conv -> norm -> PReLU (prelu==2); TCM branches are PReLU -> norm (prelu==1).
+// ---------------------------------------------------------------------------------------------------
+struct Xform {
+    const double* stats;   // affine==1: [B][C][2] running sums of the (pre-PReLU'd if prelu==1) values
+    const float* scale;    // affine==1: gamma[C];  affine==2: precomputed scale[C]
+    const float* shift;    // affine==1: beta[C];   affine==2: precomputed shift[C]
+    const float* alpha;    // PReLU slopes [C] (prelu != 0)
+    float inv_count;       // 1 / (#elements per (b,c)) for affine==1
+    int affine;            // 0 none, 1 instance statistics, 2 precomputed
+    int prelu;             // 0 none, 1 before the affine, 2 after it
+};
+
+static inline Xform xform_identity() {
+    Xform x;
+    x.stats = nullptr; x.scale = nullptr; x.shift = nullptr; x.alpha = nullptr;
+    x.inv_count = 0.f; x.affine = 0; x.prelu = 0;
+    return x;
+}
+
+#ifdef __CUDACC__
+// coefficients for channel c of batch b (called once per CTA per channel, not per element)
+__device__ __forceinline__ void xform_coeffs(const Xform& xf, int b, int C, int c, float& s, float& h, float& a) {
+    s = 1.f; h = 0.f; a = 1.f;
+    if (xf.affine == 1) {
+        const double* st = xf.stats + ((size_t)b * C + c) * 2;
+        double mean = st[0] * (double)xf.inv_count;
+        double var = st[1] * (double)xf.inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        double rstd = rsqrt(var + 1e-5);
+        double g = (double)xf.scale[c];
+        s = (float)(g * rstd);
+        h = (float)((double)xf.shift[c] - mean * g * rstd);
+    } else if (xf.affine == 2) {
+        s = xf.scale[c];
+        h = xf.shift[c];
+    }
+    if (xf.prelu) a = xf.alpha[c];
+}
+
+__device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
+
+__device__ __forceinline__ float xform_apply(float x, float s, float h, float a, int prelu) {
+    if (prelu == 1) x = prelu_f(x, a);
+    x = fmaf(x, s, h);
+    if (prelu == 2) x = prelu_f(x, a);
+    return x;
+}
+
+// accurate-enough logistic / tanh on the SFU path (abs error ~1e-7; ex2.approx + rcp)
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) {
+    // 1 - 2/(1+e^{2x}); saturates cleanly for |x| large (e^{2x} -> inf or 0)
+    return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int n = valid ? 16 : 0;                                  // src-size 0 => the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// launch descriptors shared between model.cu and the kernel translation units
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxTaps = 16;
+constexpr int kMaxCin = 1024;
+
+struct ConvSrc {
+    const float* x;      // [B][T][Fin][C] raw
+    int C;
+    Xform xf;
+};
+
+// One "virtual" stride-1-output convolution over rows (t, e):  fi = e*in_stride + df[tap],
+// frame = t - dt[tap], fo = e*out_stride + out_off.  A Conv2d with stride (1,2) is one launch
+// (in_stride 2, out_stride 1); a ConvTranspose2d with stride (1,2) is two launches, one per output parity
+// (in_stride 1, out_stride 2, out_off = parity, df = -i) -- no zero stuffing.
+struct ConvArgs {
+    ConvSrc src[2];
+    int nsrc;
+    int B, T, Fin;
+    int E;                       // rows per frame in this launch
+    int in_stride, out_stride, out_off, Fout;
+    int ntaps;
+    int dt[kMaxTaps], df[kMaxTaps];
+    const float* W;              // packed [ntaps][Cin_total][N]
+    const float* bias;           // [N] or null
+    int Cout, N, gate_off;       // N = padded column count (multiple of 64); gate_off>0 => gated
+    int relu;                    // ReLU on the output (w_dnn hidden layer)
+    float* out;                  // [B][T][Fout][Cout]
+    const float* resid;          // optional, same layout as out (TCM residual)
+    double* stats[2];            // optional [B][Cout][2] accumulators
+    const float* stat_alpha[2];  // if set, statistics are taken of PReLU(out, alpha) (TCM convention)
+    int nstats;
+};
+int launch_conv(const ConvArgs& a, cudaStream_t st);
+
+struct CombineArgs {
+    ConvSrc src[3];
+    int nsrc;
+    int B, P, C;                 // P = positions per batch item (T*F)
+    float* out;
+};
+int launch_combine(const CombineArgs& a, cudaStream_t st);
+
+struct LstmArgs {
+    ConvSrc src;                 // [B][T][F][E] ; xf applied on load
+    int layer_norm;              // LayerNorm(E) after the transform (bf_map.norm, EaBNet.py:598,608)
+    const float* ln_g; const float* ln_b;
+    const float* Wx;             // packed [E][64][4]
+    const float* Wh;             // packed [64][64][4]
+    const float* bias;           // packed [64][4]  (b_ih + b_hh)
+    int B, T, F, E;
+    float* out;                  // [B][T][F][64]
+};
+int launch_lstm(const LstmArgs& a, cudaStream_t st);
+
+struct BeamArgs {
+    const float* w;              // [B][T][F][NW]  (NW = 2M mimo, 2 miso), channel = m*2 + ri
+    const float* inpt;           // [B][T][F][M][2]
+    int B, T, F, M, miso;
+    float* out;                  // mimo [B][2][T][F];  miso [B][2][T]
+};
+int launch_beam(const BeamArgs& a, cudaStream_t st);
+
+int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st);
+int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st);
+
+}  // namespace eab

@@ -1,0 +1,969 @@
+// Model plan, parameter table, weight packing and the C ABI (include/eabnet_b200.h).
+//
+// The architecture walk below restates EaBNet.__init__/forward (EaBNet.py:9-125 and the sub-modules at
+// :157-624) as a list of layer descriptors that (a) declare the reference state_dict entries in the reference's
+// registration order, (b) pack them into the kernels' layouts, and (c) launch the kernels.  Activations are
+// channels-last [B,T,F,C] fp32 and are stored RAW next to their (sum, sumsq) statistics; normalisation and
+// PReLU are applied by the consumer while it stages its operand (see common.cuh Xform).
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/eabnet_b200.h"
+#include "common.cuh"
+
+namespace eab {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static thread_local int g_launches = 0;
+void set_error(const std::string& m) { g_err = m; }
+int fail(const std::string& m) { g_err = m; return 1; }
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 1;
+}
+void count_launch(int n) { g_launches += n; }
+int launch_count() { return g_launches; }
+void reset_launch_count() { g_launches = 0; }
+
+namespace {
+
+inline int ceil64(int x) { return (x + 63) / 64 * 64; }
+inline int pad_n(int x) { int n = ceil64(x); return n == 192 ? 256 : n; }
+
+struct Param {
+    std::string name;
+    int ndim = 0;
+    int64_t shape[4] = {1, 1, 1, 1};
+    int kind = 0;
+    int fan_in = 1;
+    std::vector<float> host;
+    bool set = false;
+    int64_t numel() const { int64_t n = 1; for (int i = 0; i < ndim; ++i) n *= shape[i]; return n; }
+};
+
+// norm (optional) + PReLU following a conv (2-D: conv -> norm -> PReLU; TCM: PReLU -> norm)
+struct NormAct {
+    bool has_norm = false;
+    int C = 0;
+    int gamma = -1, beta = -1, mean = -1, var = -1, alpha = -1;   // param indices
+    size_t off_scale = 0, off_shift = 0, off_alpha = 0;           // floats into the device blob
+};
+
+struct ConvLayer {
+    int w = -1, b = -1;                 // param indices
+    int cin = 0, cout = 0, kt = 1, kf = 1;
+    bool deconv = false, gated = false;
+    bool perm_ri = false;               // first layer: reference channel ri*M+m  ->  memory order m*2+ri
+    int M = 0;
+    int N = 0, gate_off = 0;
+    // packed variants: conv -> 1, deconv -> 2 (output parity)
+    int nvar = 1;
+    int ntaps[2] = {0, 0};
+    int dt[2][kMaxTaps], df[2][kMaxTaps];
+    size_t off_w[2] = {0, 0}, off_b = 0;
+    NormAct na;
+};
+
+struct UnetModule {
+    ConvLayer in_conv;
+    std::vector<ConvLayer> enco, deco;
+};
+
+struct TcmLayer {
+    int dilation = 1;
+    int w_in = -1, w_left = -1, w_right = -1, w_out = -1;
+    NormAct na_left, na_right, na_out;
+    size_t off_in = 0, off_dil = 0, off_out = 0;
+    int dt[kMaxTaps];
+};
+
+struct Act {                 // an activation tensor as seen by a consumer
+    float* data = nullptr;
+    int F = 0, C = 0;
+    Xform xf = xform_identity();
+};
+
+struct Tap { Act act; int B = 0, T = 0; };
+
+}  // namespace
+}  // namespace eab
+
+using namespace eab;
+
+struct eab_model {
+    eab_config cfg;
+    std::vector<Param> params;
+    std::unordered_map<std::string, int> index;
+
+    // architecture
+    std::vector<UnetModule> en_mod, de_mod;         // U2 variants
+    std::vector<ConvLayer> en_plain, de_plain;      // U-Net variants (and the U2 last convs at the back)
+    ConvLayer en_last, de_last;
+    std::vector<TcmLayer> tcms;                     // q*p
+    int Fb = 0;                                     // bottleneck F
+    std::vector<int> Fchain;                        // encoder F sizes: F0 (input) .. F5
+    // head
+    int rnn[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};
+    int dnn_w[2] = {-1, -1}, dnn_b[2] = {-1, -1}, ln_g = -1, ln_b = -1, cnn_w = -1, cnn_b = -1;
+    size_t off_rnn[2][3] = {{0, 0, 0}, {0, 0, 0}}, off_dnn_w[2] = {0, 0}, off_dnn_b[2] = {0, 0}, off_ln_g = 0,
+           off_ln_b = 0, off_cnn_w = 0, off_cnn_b = 0;
+    int dnn_N[2] = {0, 0}, cnn_N = 0;
+
+    // device state
+    float* blob = nullptr;
+    size_t blob_floats = 0;
+    bool dirty = true;
+    int last_launches = 0;
+    std::map<std::string, Tap> taps;
+    void* scratch = nullptr;      // eab_enhance_host
+    size_t scratch_bytes = 0;
+};
+
+namespace eab {
+namespace {
+
+// ================================================================================================ declare
+struct Builder {
+    eab_model* m;
+    int add(const std::string& name, std::initializer_list<int64_t> shape, int kind, int fan_in) {
+        Param p;
+        p.name = name;
+        p.ndim = (int)shape.size();
+        int i = 0;
+        for (auto s : shape) p.shape[i++] = s;
+        p.kind = kind;
+        p.fan_in = fan_in;
+        m->index[name] = (int)m->params.size();
+        m->params.push_back(p);
+        return (int)m->params.size() - 1;
+    }
+    void norm(const std::string& pfx, int C, NormAct& na) {
+        na.has_norm = true;
+        na.C = C;
+        na.gamma = add(pfx + ".norm.weight", {C}, EAB_P_NORM_G, C);
+        na.beta = add(pfx + ".norm.bias", {C}, EAB_P_NORM_B, C);
+        if (m->cfg.norm_type == 1) {
+            na.mean = add(pfx + ".norm.running_mean", {C}, EAB_P_BN_MEAN, C);
+            na.var = add(pfx + ".norm.running_var", {C}, EAB_P_BN_VAR, C);
+            add(pfx + ".norm.num_batches_tracked", {}, EAB_P_BN_COUNT, 1);
+        }
+    }
+    // Sequential(gated (de)conv, [norm], PReLU)   (EaBNet.py:185-189, 214-231, 267-271, 351-358)
+    ConvLayer gated(const std::string& pfx, int cin, int cout, int kt, int kf, bool deconv, bool with_norm) {
+        ConvLayer L;
+        L.cin = cin; L.cout = cout; L.kt = kt; L.kf = kf; L.deconv = deconv; L.gated = true;
+        const std::string sub = kt > 1 ? (deconv ? ".0.conv.0" : ".0.conv.1") : ".0.conv";
+        const int fan = (deconv ? 2 * cout : cin) * kt * kf;      // torch: weight.size(1) * receptive field
+        if (deconv) L.w = add(pfx + sub + ".weight", {cin, 2 * cout, kt, kf}, EAB_P_CONV_W, fan);
+        else        L.w = add(pfx + sub + ".weight", {2 * cout, cin, kt, kf}, EAB_P_CONV_W, fan);
+        L.b = add(pfx + sub + ".bias", {2 * cout}, EAB_P_CONV_B, fan);
+        L.na.C = cout;
+        if (with_norm) {
+            norm(pfx + ".1", cout, L.na);
+            L.na.alpha = add(pfx + ".2.weight", {cout}, EAB_P_PRELU, cout);
+        } else {
+            L.na.alpha = add(pfx + ".1.weight", {cout}, EAB_P_PRELU, cout);
+        }
+        return L;
+    }
+    // Conv2dunit / Deconv2dunit (EaBNet.py:391-431)
+    ConvLayer unit(const std::string& pfx, int cin, int cout, int kt, int kf, bool deconv) {
+        ConvLayer L;
+        L.cin = cin; L.cout = cout; L.kt = kt; L.kf = kf; L.deconv = deconv; L.gated = false;
+        const int fan = (deconv ? cout : cin) * kt * kf;
+        if (deconv) L.w = add(pfx + ".0.weight", {cin, cout, kt, kf}, EAB_P_CONV_W, fan);
+        else        L.w = add(pfx + ".0.weight", {cout, cin, kt, kf}, EAB_P_CONV_W, fan);
+        L.b = add(pfx + ".0.bias", {cout}, EAB_P_CONV_B, fan);
+        norm(pfx + ".1", cout, L.na);
+        L.na.alpha = add(pfx + ".2.weight", {cout}, EAB_P_PRELU, cout);
+        return L;
+    }
+    UnetModule module(const std::string& pfx, int cin, int kt, int kf, int scale, bool deconv) {
+        const eab_config& c = m->cfg;
+        UnetModule U;
+        U.in_conv = gated(pfx + ".in_conv", cin, c.c, kt, kf, deconv, true);
+        for (int i = 0; i < scale; ++i)
+            U.enco.push_back(unit(pfx + ".enco." + std::to_string(i) + ".conv", c.c, c.c, c.k2_t, c.k2_f, false));
+        for (int i = 0; i < scale; ++i) {
+            const int cin_d = (i == 0 || c.intra_connect == 1) ? c.c : 2 * c.c;
+            U.deco.push_back(unit(pfx + ".deco." + std::to_string(i) + ".deconv", cin_d, c.c, c.k2_t, c.k2_f, true));
+        }
+        return U;
+    }
+};
+
+int conv_out_f(int Fin, int kf) { return Fin < kf ? -1 : (Fin - kf) / 2 + 1; }
+int deconv_out_f(int Fin, int kf) { return 2 * (Fin - 1) + kf; }
+
+int build(eab_model* m) {
+    const eab_config& c = m->cfg;
+    if (c.c < 1 || c.c > 128) return fail("c must be in 1..128");
+    if (c.embed_dim < 1 || c.embed_dim > 128) return fail("embed_dim must be in 1..128");
+    if (c.M < 1 || c.M > 64) return fail("M must be in 1..64");
+    if (c.kd1 < 1 || c.kd1 > kMaxTaps) return fail("kd1 must be in 1..16");
+    if (c.k1_t < 1 || c.k1_t > 2 || c.k2_t < 1 || c.k2_t > 2) return fail("temporal kernel sizes above 2 are not supported");
+    if (c.k1_t * c.k1_f > kMaxTaps || c.k2_t * c.k2_f > kMaxTaps || c.k1_f < 1 || c.k2_f < 1) return fail("kernel too large");
+    if (c.cd1 < 1 || c.cd1 > 128) return fail("cd1 must be in 1..128");
+    if (c.p < 1 || c.q < 1 || c.q > 3) return fail("p >= 1 and 1 <= q <= 3 required");
+    if (c.norm_type != 0 && c.norm_type != 1)
+        return fail("norm_type 'cLN' cannot be constructed in the reference either (EaBNet.py:689,691)");
+    Builder bd{m};
+    // encoder F chain
+    m->Fchain.clear();
+    m->Fchain.push_back(c.n_freq);
+    {
+        int F = conv_out_f(c.n_freq, 5);
+        m->Fchain.push_back(F);
+        for (int i = 0; i < 4; ++i) { F = F > 0 ? conv_out_f(F, c.k1_f) : -1; m->Fchain.push_back(F); }
+        if (F < 1) return fail("n_freq too small for the five stride-2 encoder stages");
+        m->Fb = F;
+    }
+    if (c.d_feat != 64 * m->Fb)
+        return fail("d_feat must equal 64 * bottleneck_F (the reference fails at run time otherwise, EaBNet.py:100,549)");
+    if (c.is_u2) {
+        m->en_mod.push_back(bd.module("en.meta_unet_list.0", 2 * c.M, 2, 5, 4, false));
+        for (int i = 1; i < 4; ++i)
+            m->en_mod.push_back(bd.module("en.meta_unet_list." + std::to_string(i), c.c, c.k1_t, c.k1_f, 4 - i, false));
+        m->en_mod[0].in_conv.perm_ri = true;
+        m->en_mod[0].in_conv.M = c.M;
+        m->en_last = bd.gated("en.last_conv", c.c, 64, c.k1_t, c.k1_f, false, true);
+        m->de_mod.push_back(bd.module("de.meta_unet_list.0", 128, c.k1_t, c.k1_f, 1, true));
+        for (int i = 1; i < 4; ++i)
+            m->de_mod.push_back(bd.module("de.meta_unet_list." + std::to_string(i), 2 * c.c, c.k1_t, c.k1_f, i + 1, true));
+        m->de_last = bd.gated("de.last_conv", 2 * c.c, c.embed_dim, 2, 5, true, true);
+    } else {
+        m->en_plain.push_back(bd.gated("en.unet_list.0", 2 * c.M, c.c, 2, 5, false, true));
+        m->en_plain[0].perm_ri = true;
+        m->en_plain[0].M = c.M;
+        m->en_plain.push_back(bd.gated("en.unet_list.1", c.c, c.c, c.k1_t, c.k1_f, false, false));
+        m->en_plain.push_back(bd.gated("en.unet_list.2", c.c, c.c, c.k1_t, c.k1_f, false, false));
+        m->en_plain.push_back(bd.gated("en.unet_list.3", c.c, c.c, c.k1_t, c.k1_f, false, true));
+        m->en_plain.push_back(bd.gated("en.unet_list.4", c.c, 64, c.k1_t, c.k1_f, false, true));
+        m->de_plain.push_back(bd.gated("de.unet_list.0", 128, c.c, c.k1_t, c.k1_f, true, true));
+        for (int i = 1; i < 4; ++i)
+            m->de_plain.push_back(bd.gated("de.unet_list." + std::to_string(i), 2 * c.c, c.c, c.k1_t, c.k1_f, true, true));
+        m->de_plain.push_back(bd.gated("de.unet_list.4", 2 * c.c, c.embed_dim, 2, 5, true, true));
+    }
+    // head (EaBNet.py:75-81, 581-598)
+    if (c.topo_type == 0 && c.bf_type == 0) {
+        const int H = 64;
+        for (int r = 0; r < 2; ++r) {
+            const std::string p = std::string("bf_map.rnn") + (r ? "2" : "1");
+            const int cin = r ? H : c.embed_dim;
+            m->rnn[r][0] = bd.add(p + ".weight_ih_l0", {4 * H, cin}, EAB_P_LSTM, H);
+            m->rnn[r][1] = bd.add(p + ".weight_hh_l0", {4 * H, H}, EAB_P_LSTM, H);
+            m->rnn[r][2] = bd.add(p + ".bias_ih_l0", {4 * H}, EAB_P_LSTM, H);
+            m->rnn[r][3] = bd.add(p + ".bias_hh_l0", {4 * H}, EAB_P_LSTM, H);
+        }
+        m->dnn_w[0] = bd.add("bf_map.w_dnn.0.weight", {H, H}, EAB_P_LIN_W, H);
+        m->dnn_b[0] = bd.add("bf_map.w_dnn.0.bias", {H}, EAB_P_LIN_B, H);
+        m->dnn_w[1] = bd.add("bf_map.w_dnn.2.weight", {2 * c.M, H}, EAB_P_LIN_W, H);
+        m->dnn_b[1] = bd.add("bf_map.w_dnn.2.bias", {2 * c.M}, EAB_P_LIN_B, H);
+        m->ln_g = bd.add("bf_map.norm.weight", {c.embed_dim}, EAB_P_NORM_G, c.embed_dim);
+        m->ln_b = bd.add("bf_map.norm.bias", {c.embed_dim}, EAB_P_NORM_B, c.embed_dim);
+    } else {
+        const int n = c.topo_type == 0 ? 2 * c.M : 2;
+        m->cnn_w = bd.add("bf_map.weight", {n, c.embed_dim, 1, 1}, EAB_P_CONV_W, c.embed_dim);
+        m->cnn_b = bd.add("bf_map.bias", {n}, EAB_P_CONV_B, c.embed_dim);
+    }
+    // squeezed TCMs (EaBNet.py:83-86, 506-571)
+    for (int g = 0; g < c.q; ++g)
+        for (int i = 0; i < c.p; ++i) {
+            if (i > 24) return fail("p too large (dilation 2^i overflows)");
+            TcmLayer t;
+            t.dilation = 1 << i;
+            const std::string p = "stcns." + std::to_string(g) + ".tcm_list." + std::to_string(i);
+            t.w_in = bd.add(p + ".in_conv.weight", {c.cd1, c.d_feat, 1}, EAB_P_CONV_W, c.d_feat);
+            t.na_left.C = t.na_right.C = t.na_out.C = c.cd1;
+            t.na_left.alpha = bd.add(p + ".left_conv.0.weight", {c.cd1}, EAB_P_PRELU, c.cd1);
+            bd.norm(p + ".left_conv.1", c.cd1, t.na_left);
+            t.w_left = bd.add(p + ".left_conv.3.weight", {c.cd1, c.cd1, c.kd1}, EAB_P_CONV_W, c.cd1 * c.kd1);
+            t.na_right.alpha = bd.add(p + ".right_conv.0.weight", {c.cd1}, EAB_P_PRELU, c.cd1);
+            bd.norm(p + ".right_conv.1", c.cd1, t.na_right);
+            t.w_right = bd.add(p + ".right_conv.3.weight", {c.cd1, c.cd1, c.kd1}, EAB_P_CONV_W, c.cd1 * c.kd1);
+            t.na_out.alpha = bd.add(p + ".out_conv.0.weight", {c.cd1}, EAB_P_PRELU, c.cd1);
+            bd.norm(p + ".out_conv.1", c.cd1, t.na_out);
+            t.w_out = bd.add(p + ".out_conv.2.weight", {c.d_feat, c.cd1, 1}, EAB_P_CONV_W, c.cd1);
+            const int span = (c.kd1 - 1) * t.dilation;
+            if (!c.is_causal && (span & 1)) return fail("non-causal TCM needs an even (kd1-1)*dilation");
+            const int pad_left = c.is_causal ? span : span / 2;
+            for (int k = 0; k < c.kd1; ++k) t.dt[k] = pad_left - k * t.dilation;
+            m->tcms.push_back(t);
+        }
+    return 0;
+}
+
+// ================================================================================================ pack
+struct Packer {
+    eab_model* m;
+    std::vector<float> blob;
+    size_t alloc(size_t n) {
+        size_t off = (blob.size() + 63) / 64 * 64;
+        blob.resize(off + n, 0.f);
+        return off;
+    }
+    const std::vector<float>& P(int i) const { return m->params[i].host; }
+
+    void normact(NormAct& na) {
+        const int C = na.C;
+        if (na.has_norm) {
+            na.off_scale = alloc(C);
+            na.off_shift = alloc(C);
+            for (int c = 0; c < C; ++c) {
+                if (m->cfg.norm_type == 1) {          // BatchNorm eval: fold running statistics
+                    const double s = (double)P(na.gamma)[c] / sqrt((double)P(na.var)[c] + 1e-5);
+                    blob[na.off_scale + c] = (float)s;
+                    blob[na.off_shift + c] = (float)((double)P(na.beta)[c] - (double)P(na.mean)[c] * s);
+                } else {
+                    blob[na.off_scale + c] = P(na.gamma)[c];
+                    blob[na.off_shift + c] = P(na.beta)[c];
+                }
+            }
+        }
+        na.off_alpha = alloc(C);
+        for (int c = 0; c < C; ++c) blob[na.off_alpha + c] = P(na.alpha)[c];
+    }
+
+    void conv(ConvLayer& L) {
+        const int cout_t = L.gated ? 2 * L.cout : L.cout;
+        L.N = L.gated ? 2 * ceil64(L.cout) : pad_n(L.cout);
+        L.gate_off = L.gated ? ceil64(L.cout) : 0;
+        auto col_of = [&](int n_orig) { return (L.gated && n_orig >= L.cout) ? L.gate_off + (n_orig - L.cout) : n_orig; };
+        auto cin_of = [&](int cin_ref) {          // reference input channel -> memory channel
+            if (!L.perm_ri) return cin_ref;
+            const int ri = cin_ref / L.M, mic = cin_ref - ri * L.M;
+            return mic * 2 + ri;
+        };
+        const std::vector<float>& W = P(L.w);
+        L.nvar = L.deconv ? 2 : 1;
+        for (int v = 0; v < L.nvar; ++v) {
+            int nt = 0;
+            std::vector<int> kj, kk;
+            for (int j = 0; j < L.kt; ++j)
+                for (int k = 0; k < L.kf; ++k) {
+                    if (L.deconv) {
+                        if ((k & 1) != v) continue;
+                        L.dt[v][nt] = j;                  // transposed conv + chomp: tap j reads frame t - j
+                        L.df[v][nt] = -(k / 2);           // fo = 2e + v, fi = e - (k - v)/2
+                    } else {
+                        L.dt[v][nt] = L.kt - 1 - j;       // top padding kt-1: tap j reads frame t - (kt-1-j)
+                        L.df[v][nt] = k;                  // fi = 2 fo + k
+                    }
+                    kj.push_back(j); kk.push_back(k);
+                    ++nt;
+                }
+            L.ntaps[v] = nt;
+            L.off_w[v] = alloc((size_t)(nt > 0 ? nt : 1) * L.cin * L.N);
+            for (int tp = 0; tp < nt; ++tp)
+                for (int ci = 0; ci < L.cin; ++ci)
+                    for (int n = 0; n < cout_t; ++n) {
+                        const size_t src = L.deconv
+                            ? (((size_t)ci * cout_t + n) * L.kt + kj[tp]) * L.kf + kk[tp]
+                            : (((size_t)n * L.cin + ci) * L.kt + kj[tp]) * L.kf + kk[tp];
+                        blob[L.off_w[v] + ((size_t)tp * L.cin + cin_of(ci)) * L.N + col_of(n)] = W[src];
+                    }
+        }
+        L.off_b = alloc(L.N);
+        for (int n = 0; n < cout_t; ++n) blob[L.off_b + col_of(n)] = P(L.b)[n];
+        normact(L.na);
+    }
+
+    void tcm(TcmLayer& t) {
+        const eab_config& c = m->cfg;
+        const int Fb = m->Fb, cd = c.cd1, df = c.d_feat, kd = c.kd1;
+        const int Nin = pad_n(cd);
+        // 1x1 squeeze: reference channel cc*Fb + f  ->  memory channel f*64 + cc
+        t.off_in = alloc((size_t)df * Nin);
+        for (int n = 0; n < cd; ++n)
+            for (int cr = 0; cr < df; ++cr) {
+                const int cc = cr / Fb, f = cr - cc * Fb;
+                blob[t.off_in + (size_t)(f * 64 + cc) * Nin + n] = P(t.w_in)[(size_t)n * df + cr];
+            }
+        // dilated pair as one gated conv over K = [left-branch channels | right-branch channels]
+        const int Nd = 2 * ceil64(cd), goff = ceil64(cd);
+        t.off_dil = alloc((size_t)kd * 2 * cd * Nd);
+        for (int k = 0; k < kd; ++k)
+            for (int ci = 0; ci < cd; ++ci)
+                for (int n = 0; n < cd; ++n) {
+                    blob[t.off_dil + ((size_t)k * 2 * cd + ci) * Nd + n] = P(t.w_left)[((size_t)n * cd + ci) * kd + k];
+                    blob[t.off_dil + ((size_t)k * 2 * cd + cd + ci) * Nd + goff + n] = P(t.w_right)[((size_t)n * cd + ci) * kd + k];
+                }
+        // 1x1 expand: output reference channel cc*Fb + f -> column f*64 + cc
+        t.off_out = alloc((size_t)cd * df);
+        for (int nr = 0; nr < df; ++nr) {
+            const int cc = nr / Fb, f = nr - cc * Fb;
+            for (int ci = 0; ci < cd; ++ci) blob[t.off_out + (size_t)ci * df + (f * 64 + cc)] = P(t.w_out)[(size_t)nr * cd + ci];
+        }
+        normact(t.na_left);
+        normact(t.na_right);
+        normact(t.na_out);
+    }
+
+    size_t linear(int w, int b, int nout, int nin, int* N, size_t* off_b) {
+        *N = pad_n(nout);
+        const size_t off = alloc((size_t)nin * *N);
+        for (int n = 0; n < nout; ++n)
+            for (int k = 0; k < nin; ++k) blob[off + (size_t)k * *N + n] = P(w)[(size_t)n * nin + k];
+        *off_b = alloc(*N);
+        for (int n = 0; n < nout; ++n) blob[*off_b + n] = P(b)[n];
+        return off;
+    }
+
+    void head() {
+        const eab_config& c = m->cfg;
+        if (m->rnn[0][0] >= 0) {
+            const int H = 64;
+            for (int r = 0; r < 2; ++r) {
+                const int E = r ? H : c.embed_dim;
+                m->off_rnn[r][0] = alloc((size_t)E * H * 4);
+                m->off_rnn[r][1] = alloc((size_t)H * H * 4);
+                m->off_rnn[r][2] = alloc((size_t)H * 4);
+                for (int g = 0; g < 4; ++g)
+                    for (int j = 0; j < H; ++j) {
+                        for (int k = 0; k < E; ++k)
+                            blob[m->off_rnn[r][0] + ((size_t)k * H + j) * 4 + g] = P(m->rnn[r][0])[(size_t)(g * H + j) * E + k];
+                        for (int k = 0; k < H; ++k)
+                            blob[m->off_rnn[r][1] + ((size_t)k * H + j) * 4 + g] = P(m->rnn[r][1])[(size_t)(g * H + j) * H + k];
+                        blob[m->off_rnn[r][2] + (size_t)j * 4 + g] = P(m->rnn[r][2])[g * H + j] + P(m->rnn[r][3])[g * H + j];
+                    }
+            }
+            m->off_dnn_w[0] = linear(m->dnn_w[0], m->dnn_b[0], H, H, &m->dnn_N[0], &m->off_dnn_b[0]);
+            m->off_dnn_w[1] = linear(m->dnn_w[1], m->dnn_b[1], 2 * c.M, H, &m->dnn_N[1], &m->off_dnn_b[1]);
+            m->off_ln_g = alloc(c.embed_dim);
+            m->off_ln_b = alloc(c.embed_dim);
+            for (int i = 0; i < c.embed_dim; ++i) {
+                blob[m->off_ln_g + i] = P(m->ln_g)[i];
+                blob[m->off_ln_b + i] = P(m->ln_b)[i];
+            }
+        } else {
+            const int n = c.topo_type == 0 ? 2 * c.M : 2;
+            m->off_cnn_w = linear(m->cnn_w, m->cnn_b, n, c.embed_dim, &m->cnn_N, &m->off_cnn_b);
+        }
+    }
+};
+
+int commit(eab_model* m, cudaStream_t st) {
+    for (const Param& p : m->params)
+        if (!p.set && p.kind != EAB_P_BN_COUNT) return fail("parameter not set: " + p.name);
+    Packer pk{m};
+    for (auto& U : m->en_mod) { pk.conv(U.in_conv); for (auto& L : U.enco) pk.conv(L); for (auto& L : U.deco) pk.conv(L); }
+    for (auto& U : m->de_mod) { pk.conv(U.in_conv); for (auto& L : U.enco) pk.conv(L); for (auto& L : U.deco) pk.conv(L); }
+    if (m->cfg.is_u2) { pk.conv(m->en_last); pk.conv(m->de_last); }
+    for (auto& L : m->en_plain) pk.conv(L);
+    for (auto& L : m->de_plain) pk.conv(L);
+    for (auto& t : m->tcms) pk.tcm(t);
+    pk.head();
+    if (m->blob && m->blob_floats < pk.blob.size()) { cudaFree(m->blob); m->blob = nullptr; }
+    if (!m->blob) {
+        EAB_CUDA(cudaMalloc(&m->blob, pk.blob.size() * sizeof(float)));
+        m->blob_floats = pk.blob.size();
+    }
+    EAB_CUDA(cudaMemcpyAsync(m->blob, pk.blob.data(), pk.blob.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    EAB_CUDA(cudaStreamSynchronize(st));        // the staging vector dies with this scope
+    m->dirty = false;
+    return 0;
+}
+
+// ================================================================================================ run
+struct Ctx {
+    eab_model* m;
+    bool dry;                 // size planning only: no launches, no dereference
+    char* base;
+    size_t stats_off = 0, stats_cap = 0;      // [0, stats_cap): zeroed once per forward
+    size_t act_off = 0;
+    int B, T;
+    cudaStream_t st;
+
+    float* alloc_act(size_t floats) {
+        const size_t bytes = (floats * sizeof(float) + 255) / 256 * 256;
+        float* p = reinterpret_cast<float*>(base + act_off);
+        act_off += bytes;
+        return p;
+    }
+    double* alloc_stats(int C) {
+        const size_t bytes = ((size_t)B * C * 2 * sizeof(double) + 255) / 256 * 256;
+        double* p = reinterpret_cast<double*>(base + stats_off);
+        stats_off += bytes;
+        return p;
+    }
+    const float* W(size_t off) const { return m->blob + off; }
+};
+
+// the Xform a consumer uses for the output of a conv followed by NormAct (2-D convention: norm -> PReLU)
+Xform xf_after(Ctx& cx, const NormAct& na, double* stats, int count, int prelu_pos) {
+    Xform x = xform_identity();
+    if (na.has_norm) {
+        if (cx.m->cfg.norm_type == 0) { x.affine = 1; x.stats = stats; x.inv_count = 1.f / (float)count; }
+        else x.affine = 2;
+        x.scale = cx.W(na.off_scale);
+        x.shift = cx.W(na.off_shift);
+    }
+    x.alpha = cx.W(na.off_alpha);
+    x.prelu = prelu_pos;
+    return x;
+}
+
+// one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
+int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out) {
+    const int Fin = srcs[0].F;
+    int cin = 0;
+    for (int i = 0; i < nsrc; ++i) {
+        if (srcs[i].F != Fin) return fail("skip connection width mismatch (the reference's torch.cat would raise too)");
+        cin += srcs[i].C;
+    }
+    if (cin != L.cin) return fail("internal: channel mismatch in conv layer");
+    const int Fout = L.deconv ? deconv_out_f(Fin, L.kf) : conv_out_f(Fin, L.kf);
+    if (Fout < 1) return fail("frequency axis too short for this layer");
+    out->F = Fout;
+    out->C = L.cout;
+    out->data = cx.alloc_act((size_t)cx.B * cx.T * Fout * L.cout);
+    const bool in_stats = L.na.has_norm && cx.m->cfg.norm_type == 0;
+    double* stats = in_stats ? cx.alloc_stats(L.cout) : nullptr;
+    out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
+    if (cx.dry) return 0;
+    for (int v = 0; v < L.nvar; ++v) {
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.nsrc = nsrc;
+        for (int i = 0; i < nsrc; ++i) { a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf; }
+        a.B = cx.B; a.T = cx.T; a.Fin = Fin; a.Fout = Fout;
+        if (L.deconv) { a.in_stride = 1; a.out_stride = 2; a.out_off = v; a.E = (Fout - v + 1) / 2; }
+        else          { a.in_stride = 2; a.out_stride = 1; a.out_off = 0; a.E = Fout; }
+        a.ntaps = L.ntaps[v];
+        for (int i = 0; i < a.ntaps; ++i) { a.dt[i] = L.dt[v][i]; a.df[i] = L.df[v][i]; }
+        if (a.ntaps == 0) return fail("transposed conv with kf == 1 is not supported");
+        a.W = cx.W(L.off_w[v]);
+        a.bias = cx.W(L.off_b);
+        a.Cout = L.cout; a.N = L.N; a.gate_off = L.gate_off;
+        a.out = out->data;
+        if (stats) { a.nstats = 1; a.stats[0] = stats; }
+        EAB_TRY(launch_conv(a, cx.st));
+    }
+    return 0;
+}
+
+int run_combine(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
+    out->F = srcs[0].F;
+    out->C = srcs[0].C;
+    out->xf = xform_identity();
+    out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * out->C);
+    if (cx.dry) return 0;
+    CombineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nsrc = nsrc;
+    for (int i = 0; i < nsrc; ++i) {
+        if (srcs[i].F != out->F || srcs[i].C != out->C) return fail("internal: combine shape mismatch");
+        a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf;
+    }
+    a.B = cx.B; a.P = cx.T * out->F; a.C = out->C; a.out = out->data;
+    return launch_combine(a, cx.st);
+}
+
+// En_unet_module.forward (EaBNet.py:372-388)
+int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out) {
+    Act x0;
+    EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0));
+    Act y = x0;
+    std::vector<Act> keep;
+    for (size_t i = 0; i < U.enco.size(); ++i) {
+        Act z;
+        EAB_TRY(run_conv2d(cx, U.enco[i], &y, 1, &z));
+        keep.push_back(z);
+        y = z;
+    }
+    for (size_t i = 0; i < U.deco.size(); ++i) {
+        Act z;
+        if (i == 0) {
+            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z));
+        } else {
+            Act pair[2] = {y, keep[keep.size() - 1 - i]};
+            if (cx.m->cfg.intra_connect == 0) {
+                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z));
+            } else {
+                Act sum;
+                EAB_TRY(run_combine(cx, pair, 2, &sum));
+                EAB_TRY(run_conv2d(cx, U.deco[i], &sum, 1, &z));
+            }
+        }
+        y = z;
+    }
+    Act pair[2] = {x0, y};
+    return run_combine(cx, pair, 2, out);
+}
+
+// 1x1 "conv" over positions with optional bias / relu / residual / statistics (used by TCMs and the head)
+int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const float* bias, int Cout, int N, int gate_off,
+                  int ntaps, const int* dt, int relu, const float* resid, int nstats, double** stats,
+                  const float** stat_alpha, Act* out) {
+    out->F = srcs[0].F;
+    out->C = Cout;
+    out->xf = xform_identity();
+    out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * Cout);
+    if (cx.dry) return 0;
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nsrc = nsrc;
+    for (int i = 0; i < nsrc; ++i) { a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf; }
+    a.B = cx.B; a.T = cx.T; a.Fin = srcs[0].F; a.Fout = srcs[0].F; a.E = srcs[0].F;
+    a.in_stride = 1; a.out_stride = 1; a.out_off = 0;
+    a.ntaps = ntaps;
+    for (int i = 0; i < ntaps; ++i) { a.dt[i] = dt ? dt[i] : 0; a.df[i] = 0; }
+    a.W = W; a.bias = bias; a.Cout = Cout; a.N = N; a.gate_off = gate_off; a.relu = relu;
+    a.out = out->data; a.resid = resid;
+    a.nstats = nstats;
+    for (int i = 0; i < nstats; ++i) { a.stats[i] = stats[i]; a.stat_alpha[i] = stat_alpha[i]; }
+    return launch_conv(a, cx.st);
+}
+
+// SqueezedTCM.forward (EaBNet.py:572-578) on the channels-last residual stream x [B,T,1,d_feat]
+int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
+    const eab_config& c = cx.m->cfg;
+    const bool in_stats = c.norm_type == 0;
+    // squeeze 1x1; statistics of PReLU_left(y) and PReLU_right(y) for the two branch norms
+    double* st_lr[2] = {in_stats ? cx.alloc_stats(c.cd1) : nullptr, in_stats ? cx.alloc_stats(c.cd1) : nullptr};
+    const float* al_lr[2] = {cx.W(t.na_left.off_alpha), cx.W(t.na_right.off_alpha)};
+    Act y;
+    EAB_TRY(run_pointwise(cx, &x, 1, cx.W(t.off_in), nullptr, c.cd1, pad_n(c.cd1), 0, 1, nullptr, 0, nullptr,
+                          in_stats ? 2 : 0, st_lr, al_lr, &y));
+    // both dilated branches as one gated conv: value = left branch, gate = right branch (sigmoid)
+    Act br[2] = {y, y};
+    br[0].xf = xf_after(cx, t.na_left, st_lr[0], cx.T, 1);
+    br[1].xf = xf_after(cx, t.na_right, st_lr[1], cx.T, 1);
+    double* st_o[1] = {in_stats ? cx.alloc_stats(c.cd1) : nullptr};
+    const float* al_o[1] = {cx.W(t.na_out.off_alpha)};
+    Act z;
+    EAB_TRY(run_pointwise(cx, br, 2, cx.W(t.off_dil), nullptr, c.cd1, 2 * ceil64(c.cd1), ceil64(c.cd1), c.kd1, t.dt, 0,
+                          nullptr, in_stats ? 1 : 0, st_o, al_o, &z));
+    // expand 1x1 + residual
+    z.xf = xf_after(cx, t.na_out, st_o[0], cx.T, 1);
+    return run_pointwise(cx, &z, 1, cx.W(t.off_out), nullptr, c.d_feat, c.d_feat, 0, 1, nullptr, 0, x.data, 0, nullptr,
+                         nullptr, out);
+}
+
+void tap(Ctx& cx, const char* name, const Act& a) {
+    if (cx.dry) return;
+    Tap t;
+    t.act = a; t.B = cx.B; t.T = cx.T;
+    cx.m->taps[name] = t;
+}
+
+int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
+    eab_model* m = cx.m;
+    const eab_config& c = m->cfg;
+    Act x;
+    x.data = const_cast<float*>(inpt);
+    x.F = c.n_freq;
+    x.C = 2 * c.M;
+    std::vector<Act> skips;
+    // ---------------- encoder (EaBNet.py:190-197 / :234-239)
+    if (c.is_u2) {
+        for (size_t i = 0; i < m->en_mod.size(); ++i) {
+            Act y;
+            EAB_TRY(run_module(cx, m->en_mod[i], &x, 1, &y));
+            skips.push_back(y);
+            tap(cx, ("en." + std::to_string(i)).c_str(), y);
+            x = y;
+        }
+        Act y;
+        EAB_TRY(run_conv2d(cx, m->en_last, &x, 1, &y));
+        skips.push_back(y);
+        tap(cx, "en.4", y);
+        x = y;
+    } else {
+        for (size_t i = 0; i < m->en_plain.size(); ++i) {
+            Act y;
+            EAB_TRY(run_conv2d(cx, m->en_plain[i], &x, 1, &y));
+            skips.push_back(y);
+            tap(cx, ("en." + std::to_string(i)).c_str(), y);
+            x = y;
+        }
+    }
+    if (x.F != m->Fb || x.C != 64) return fail("internal: bottleneck shape");
+    // ---------------- squeezed TCM stack (EaBNet.py:99-106); channel order f*64+c is kept both ways
+    Act r;                                            // residual stream [B,T,1,d_feat], finalised
+    EAB_TRY(run_combine(cx, &x, 1, &r));
+    r.F = 1;
+    r.C = c.d_feat;
+    std::vector<Act> group_out;
+    size_t ti = 0;
+    for (int g = 0; g < c.q; ++g) {
+        for (int i = 0; i < c.p; ++i) {
+            Act nx;
+            EAB_TRY(run_tcm(cx, m->tcms[ti++], r, &nx));
+            r = nx;
+        }
+        group_out.push_back(r);
+    }
+    Act acc;
+    if (c.q == 1) acc = group_out[0];
+    else EAB_TRY(run_combine(cx, group_out.data(), c.q, &acc));
+    acc.F = m->Fb;
+    acc.C = 64;
+    tap(cx, "tcm", acc);
+    // ---------------- decoder (EaBNet.py:273-279 / :324-328)
+    x = acc;
+    Act emb;
+    if (c.is_u2) {
+        for (size_t i = 0; i < m->de_mod.size(); ++i) {
+            Act pair[2] = {x, skips[skips.size() - 1 - i]};
+            Act y;
+            EAB_TRY(run_module(cx, m->de_mod[i], pair, 2, &y));
+            tap(cx, ("de." + std::to_string(i)).c_str(), y);
+            x = y;
+        }
+        Act pair[2] = {x, skips[0]};
+        EAB_TRY(run_conv2d(cx, m->de_last, pair, 2, &emb));
+    } else {
+        for (size_t i = 0; i < m->de_plain.size(); ++i) {
+            Act pair[2] = {x, skips[skips.size() - 1 - i]};
+            Act y;
+            EAB_TRY(run_conv2d(cx, m->de_plain[i], pair, 2, &y));
+            if (i + 1 < m->de_plain.size()) tap(cx, ("de." + std::to_string(i)).c_str(), y);
+            x = y;
+        }
+        emb = x;
+    }
+    if (emb.F != c.n_freq) return fail("decoder output width differs from the input width (the reference would fail in filter-and-sum)");
+    tap(cx, "embed", emb);
+    // ---------------- beam-weight head + filter-and-sum (EaBNet.py:108-125, 600-614)
+    Act w;
+    if (c.topo_type == 0 && c.bf_type == 0) {
+        Act h[2];
+        for (int l = 0; l < 2; ++l) {
+            h[l].F = c.n_freq; h[l].C = 64; h[l].xf = xform_identity();
+            h[l].data = cx.alloc_act((size_t)cx.B * cx.T * c.n_freq * 64);
+            if (!cx.dry) {
+                LstmArgs a;
+                memset(&a, 0, sizeof(a));
+                const Act& src = l ? h[0] : emb;
+                a.src.x = src.data; a.src.C = src.C; a.src.xf = src.xf;
+                a.layer_norm = l == 0;
+                a.ln_g = cx.W(m->off_ln_g); a.ln_b = cx.W(m->off_ln_b);
+                a.Wx = cx.W(m->off_rnn[l][0]); a.Wh = cx.W(m->off_rnn[l][1]); a.bias = cx.W(m->off_rnn[l][2]);
+                a.B = cx.B; a.T = cx.T; a.F = c.n_freq; a.E = src.C;
+                a.out = h[l].data;
+                EAB_TRY(launch_lstm(a, cx.st));
+            }
+            tap(cx, l ? "h2" : "h1", h[l]);
+        }
+        Act u;
+        EAB_TRY(run_pointwise(cx, &h[1], 1, cx.W(m->off_dnn_w[0]), cx.W(m->off_dnn_b[0]), 64, m->dnn_N[0], 0, 1, nullptr, 1,
+                              nullptr, 0, nullptr, nullptr, &u));
+        EAB_TRY(run_pointwise(cx, &u, 1, cx.W(m->off_dnn_w[1]), cx.W(m->off_dnn_b[1]), 2 * c.M, m->dnn_N[1], 0, 1, nullptr, 0,
+                              nullptr, 0, nullptr, nullptr, &w));
+    } else {
+        const int n = c.topo_type == 0 ? 2 * c.M : 2;
+        EAB_TRY(run_pointwise(cx, &emb, 1, cx.W(m->off_cnn_w), cx.W(m->off_cnn_b), n, m->cnn_N, 0, 1, nullptr, 0, nullptr, 0,
+                              nullptr, nullptr, &w));
+    }
+    tap(cx, "w", w);
+    if (!cx.dry) {
+        BeamArgs a;
+        a.w = w.data; a.inpt = inpt; a.B = cx.B; a.T = cx.T; a.F = c.n_freq; a.M = c.M; a.miso = c.topo_type == 1;
+        a.out = out_dev;
+        EAB_TRY(launch_beam(a, cx.st));
+    }
+    return 0;
+}
+
+int plan(eab_model* m, int B, int T, size_t* stats_bytes, size_t* total_bytes) {
+    Ctx cx;
+    cx.m = m; cx.dry = true; cx.base = nullptr; cx.B = B; cx.T = T; cx.st = nullptr;
+    EAB_TRY(run_forward(cx, nullptr, nullptr));
+    *stats_bytes = cx.stats_off;
+    *total_bytes = cx.stats_off + cx.act_off;
+    return 0;
+}
+
+int forward(eab_model* m, const float* inpt, float* out, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (B < 1 || T < 1) return fail("forward: B and T must be positive");
+    if (m->cfg.norm_type == 0 && T < 2)
+        return fail("InstanceNorm1d needs more than one frame (the reference raises too)");
+    if (m->dirty) return fail("parameters not committed: call eab_commit_params first");
+    size_t sb = 0, tb = 0;
+    EAB_TRY(plan(m, B, T, &sb, &tb));
+    if (ws_bytes < tb) return fail("workspace too small: need " + std::to_string(tb) + " bytes");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail("workspace must be 256-byte aligned");
+    m->taps.clear();
+    if (sb) EAB_CUDA(cudaMemsetAsync(ws, 0, sb, st));
+    Ctx cx;
+    cx.m = m; cx.dry = false; cx.base = static_cast<char*>(ws); cx.B = B; cx.T = T; cx.st = st;
+    cx.stats_off = 0; cx.stats_cap = sb; cx.act_off = sb;
+    return run_forward(cx, inpt, out);
+}
+
+}  // namespace
+}  // namespace eab
+
+// =================================================================================================== C ABI
+extern "C" {
+
+int eab_create(const eab_config* cfg, eab_model** out) {
+    if (!cfg || !out) return fail("eab_create: null argument");
+    std::unique_ptr<eab_model> m(new eab_model());
+    m->cfg = *cfg;
+    if (m->cfg.n_freq <= 0) m->cfg.n_freq = 161;
+    if (build(m.get())) return 1;
+    *out = m.release();
+    return 0;
+}
+
+void eab_destroy(eab_model* m) {
+    if (!m) return;
+    if (m->blob) cudaFree(m->blob);
+    if (m->scratch) cudaFree(m->scratch);
+    delete m;
+}
+
+int eab_param_count(const eab_model* m) { return m ? (int)m->params.size() : 0; }
+
+int eab_param_info(const eab_model* m, int i, const char** name, int* ndim, int64_t shape[4], int* kind, int* fan_in) {
+    if (!m || i < 0 || i >= (int)m->params.size()) return fail("eab_param_info: index out of range");
+    const Param& p = m->params[i];
+    if (name) *name = p.name.c_str();
+    if (ndim) *ndim = p.ndim;
+    if (shape) for (int k = 0; k < 4; ++k) shape[k] = p.shape[k];
+    if (kind) *kind = p.kind;
+    if (fan_in) *fan_in = p.fan_in;
+    return 0;
+}
+
+int eab_set_param(eab_model* m, const char* name, const float* host, int64_t numel) {
+    if (!m || !name) return fail("eab_set_param: null argument");
+    auto it = m->index.find(name);
+    if (it == m->index.end()) return fail(std::string("unexpected key in state_dict: ") + name);
+    Param& p = m->params[it->second];
+    if (p.kind == EAB_P_BN_COUNT) { p.set = true; return 0; }
+    if (numel != p.numel()) return fail(std::string("size mismatch for ") + name);
+    if (!host) return fail("eab_set_param: null data");
+    p.host.assign(host, host + numel);
+    p.set = true;
+    m->dirty = true;
+    return 0;
+}
+
+int eab_commit_params(eab_model* m, void* stream) {
+    if (!m) return fail("null model");
+    return commit(m, static_cast<cudaStream_t>(stream));
+}
+
+size_t eab_workspace_bytes(const eab_model* m, int B, int T) {
+    size_t sb = 0, tb = 0;
+    if (!m || B < 1 || T < 1) return 0;
+    if (plan(const_cast<eab_model*>(m), B, T, &sb, &tb)) return 0;
+    return tb;
+}
+
+int eab_forward(eab_model* m, const float* inpt, float* out, int B, int T, void* ws, size_t ws_bytes, void* stream) {
+    if (!m || !inpt || !out || !ws) return fail("eab_forward: null argument");
+    reset_launch_count();
+    const int rc = forward(m, inpt, out, B, T, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    m->last_launches = launch_count();
+    return rc;
+}
+
+int eab_stft(const float* wave, float* spec, int B, int M, int L, void* stream) {
+    if (!wave || !spec) return fail("eab_stft: null argument");
+    return launch_stft(wave, spec, B, M, L, static_cast<cudaStream_t>(stream));
+}
+
+int eab_istft(const float* spec, float* wave, int B, int T, void* stream) {
+    if (!spec || !wave) return fail("eab_istft: null argument");
+    return launch_istft(spec, wave, B, T, static_cast<cudaStream_t>(stream));
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t eab_enhance_workspace_bytes(const eab_model* m, int B, int L) {
+    if (!m || B < 1 || L < 161) return 0;
+    const int T = 1 + L / 160;
+    const size_t fw = eab_workspace_bytes(m, B, T);
+    if (!fw) return 0;
+    const size_t spec = align256((size_t)B * T * m->cfg.n_freq * m->cfg.M * 2 * sizeof(float));
+    const size_t outp = align256((size_t)B * 2 * T * m->cfg.n_freq * sizeof(float));
+    return spec + outp + fw;
+}
+
+int eab_enhance(eab_model* m, const float* wave, float* enhanced, int B, int L, void* ws, size_t ws_bytes, void* stream) {
+    if (!m || !wave || !enhanced || !ws) return fail("eab_enhance: null argument");
+    if (m->cfg.topo_type == 1) return fail("eab_enhance: the 'miso' topology returns [B,2,T], which has no iSTFT");
+    if (m->cfg.n_freq != 161) return fail("eab_enhance: the 320-point STFT gives 161 bins");
+    if (L < 161) return fail("eab_enhance: need at least 161 samples");
+    const size_t need = eab_enhance_workspace_bytes(m, B, L);
+    if (!need) return 1;
+    if (ws_bytes < need) return fail("workspace too small: need " + std::to_string(need) + " bytes");
+    const int T = 1 + L / 160;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* p = static_cast<char*>(ws);
+    float* spec = reinterpret_cast<float*>(p);
+    p += align256((size_t)B * T * 161 * m->cfg.M * 2 * sizeof(float));
+    float* outp = reinterpret_cast<float*>(p);
+    p += align256((size_t)B * 2 * T * 161 * sizeof(float));
+    reset_launch_count();
+    int rc = launch_stft(wave, spec, B, m->cfg.M, L, st);
+    if (!rc) rc = forward(m, spec, outp, B, T, p, ws_bytes - (size_t)(p - static_cast<char*>(ws)), st);
+    if (!rc) rc = launch_istft(outp, enhanced, B, T, st);
+    m->last_launches = launch_count();
+    return rc;
+}
+
+int eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host, int B, int L, void* stream) {
+    if (!m || !wave_host || !enhanced_host) return fail("eab_enhance_host: null argument");
+    const size_t need = eab_enhance_workspace_bytes(m, B, L);
+    if (!need) return fail("eab_enhance_host: bad shape");
+    const size_t in_b = align256((size_t)B * m->cfg.M * L * sizeof(float));
+    const size_t out_b = align256((size_t)B * 160 * (L / 160) * sizeof(float));
+    const size_t total = in_b + out_b + need;
+    if (m->scratch_bytes < total) {
+        if (m->scratch) cudaFree(m->scratch);
+        m->scratch = nullptr;
+        m->scratch_bytes = 0;
+        EAB_CUDA(cudaMalloc(&m->scratch, total));
+        m->scratch_bytes = total;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* p = static_cast<char*>(m->scratch);
+    float* din = reinterpret_cast<float*>(p);
+    float* dout = reinterpret_cast<float*>(p + in_b);
+    EAB_CUDA(cudaMemcpyAsync(din, wave_host, (size_t)B * m->cfg.M * L * sizeof(float), cudaMemcpyHostToDevice, st));
+    EAB_TRY(eab_enhance(m, din, dout, B, L, p + in_b + out_b, need, stream));
+    EAB_CUDA(cudaMemcpyAsync(enhanced_host, dout, (size_t)B * 160 * (L / 160) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    EAB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int eab_last_launch_count(const eab_model* m) { return m ? m->last_launches : 0; }
+
+int64_t eab_debug_tap(eab_model* m, const char* name, float* dst, int64_t capacity, void* stream) {
+    if (!m || !name || !dst) { fail("eab_debug_tap: null argument"); return -1; }
+    auto it = m->taps.find(name);
+    if (it == m->taps.end()) { fail(std::string("no such tap: ") + name); return -1; }
+    const Tap& t = it->second;
+    const int64_t n = (int64_t)t.B * t.T * t.act.F * t.act.C;
+    if (n > capacity) { fail("eab_debug_tap: destination too small"); return -1; }
+    CombineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nsrc = 1;
+    a.src[0].x = t.act.data; a.src[0].C = t.act.C; a.src[0].xf = t.act.xf;
+    a.B = t.B; a.P = t.T * t.act.F; a.C = t.act.C; a.out = dst;
+    if (launch_combine(a, static_cast<cudaStream_t>(stream))) return -1;
+    return n;
+}
+
+const char* eab_last_error(void) { return g_err.c_str(); }
+
+const char* eab_build_info(void) {
+#define EAB_STR2(x) #x
+#define EAB_STR(x) EAB_STR2(x)
+    return "sm_100a;" __DATE__ ";nvcc " EAB_STR(__CUDACC_VER_MAJOR__) "." EAB_STR(__CUDACC_VER_MINOR__);
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+// 320/160 STFT with square-root compression, and the matching iSTFT, as windowed real-DFT matrix products in
+// fp32 (the compression amplifies operand rounding, so no reduced-precision operands here: SURVEY.md 7.2).
+//
+//   forward (test.py:32-43):  frame g[n] = x_reflect[160 t + n - 160] * hann[n],  X[f] = sum_n g[n] e^{-i th n f}
+//       folded with the even/odd symmetry of cos/sin about n = 160 (halves the multiply-adds):
+//         Re X[f] =  sum_{k=0..160} Ev[k] cos(th k f),   Ev[k] = g[k] + g[320-k]  (Ev[0]=g[0], Ev[160]=g[160])
+//         Im X[f] = -sum_{k=1..159} Od[k] sin(th k f),   Od[k] = g[k] - g[320-k]
+//       then z * |z|^{-1/2}   ( == |z|^0.5 * (cos, sin)(atan2(im, re)) ).
+//   inverse (enhance.py:59-61): s[n] = (P[n] - Q[n]) / 320, s[320-n] = (P[n] + Q[n]) / 320 for n <= 160 with
+//         P[n] = sum_f a_f Yr[f] cos(th n f) (a_0 = a_160 = 1, else 2),  Q[n] = sum_{f=1..159} 2 Yi[f] sin(th n f)
+//       windowed overlap-add of the two frames covering each output sample, divided by the squared-window
+//       envelope, with the 160-sample centre padding trimmed  -> 160 (T-1) samples.
+//
+// Both directions use the same "column GEMM": a thread owns one output column (322 of them) and RB = 24 rows
+// (frames x mics, or frames) as register accumulators; the A operand sits in shared memory [k][RB], the
+// twiddle table (built in double on the host) streams from L2.
+#include <math.h>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace eab {
+
+namespace {
+
+constexpr int NFFT = 320, HOP = 160, NF = 161;
+constexpr int NCOL = 2 * NF;          // 322 output columns
+constexpr int LDT = 352;              // padded table row
+constexpr int RB = 24;                // accumulator rows per thread
+constexpr int THREADS = 352;          // 11 warps, one column per thread
+
+struct Tables {
+    float* fwd = nullptr;    // [161][352]: col<161: cos(th k col); col>=161: -sin(th k (col-161))
+    float* inv = nullptr;    // [161][352]: col<161: a_f cos(th f n)/320 ; col>=161: 2 sin(th f n)/320 (f in 1..159)
+    float* win = nullptr;    // [320] periodic hann
+    float* ienv = nullptr;   // [160] 1 / (w[n]^2 + w[n+160]^2)
+};
+Tables g_tab[64];
+std::mutex g_tab_mu;
+
+int get_tables(Tables** out) {
+    int dev = 0;
+    EAB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail("stft: device index out of range");
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    Tables& t = g_tab[dev];
+    if (!t.fwd) {
+        std::vector<float> fwd((size_t)NF * LDT, 0.f), inv((size_t)NF * LDT, 0.f), win(NFFT), ienv(HOP);
+        const double th = 2.0 * M_PI / NFFT;
+        for (int k = 0; k < NF; ++k)
+            for (int f = 0; f < NF; ++f) {
+                const int kf = (k * f) % NFFT;             // exact argument reduction
+                const double c = cos(th * kf), s = sin(th * kf);
+                fwd[(size_t)k * LDT + f] = (float)c;
+                fwd[(size_t)k * LDT + NF + f] = (k == 0 || k == 160) ? 0.f : (float)(-s);
+                // inverse: row = frequency k, column = sample f
+                const double af = (k == 0 || k == 160) ? 1.0 : 2.0;
+                inv[(size_t)k * LDT + f] = (float)(af * c / NFFT);
+                inv[(size_t)k * LDT + NF + f] = (k == 0 || k == 160) ? 0.f : (float)(2.0 * s / NFFT);
+            }
+        std::vector<double> w(NFFT);
+        for (int n = 0; n < NFFT; ++n) {
+            w[n] = 0.5 - 0.5 * cos(th * n);
+            win[n] = (float)w[n];
+        }
+        for (int n = 0; n < HOP; ++n) {
+            const double e = (double)win[n] * win[n] + (double)win[n + HOP] * win[n + HOP];
+            ienv[n] = (float)(1.0 / e);
+        }
+        EAB_CUDA(cudaMalloc(&t.fwd, fwd.size() * 4));
+        EAB_CUDA(cudaMalloc(&t.inv, inv.size() * 4));
+        EAB_CUDA(cudaMalloc(&t.win, win.size() * 4));
+        EAB_CUDA(cudaMalloc(&t.ienv, ienv.size() * 4));
+        EAB_CUDA(cudaMemcpy(t.fwd, fwd.data(), fwd.size() * 4, cudaMemcpyHostToDevice));
+        EAB_CUDA(cudaMemcpy(t.inv, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+        EAB_CUDA(cudaMemcpy(t.win, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
+        EAB_CUDA(cudaMemcpy(t.ienv, ienv.data(), ienv.size() * 4, cudaMemcpyHostToDevice));
+    }
+    *out = &t;
+    return 0;
+}
+
+// acc[r] = sum_k A[k][r] * tab[k][col]   (A in shared memory, 16-byte aligned rows of RB floats)
+__device__ __forceinline__ void column_gemm(const float* __restrict__ A, const float* __restrict__ tab, int col,
+                                            float (&acc)[RB]) {
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < NF; ++k) {
+        const float tv = __ldg(tab + (size_t)k * LDT + col);
+        const float4* a4 = reinterpret_cast<const float4*>(A + k * RB);
+#pragma unroll
+        for (int u = 0; u < RB / 4; ++u) {
+            const float4 v = a4[u];
+            acc[4 * u + 0] = fmaf(v.x, tv, acc[4 * u + 0]);
+            acc[4 * u + 1] = fmaf(v.y, tv, acc[4 * u + 1]);
+            acc[4 * u + 2] = fmaf(v.z, tv, acc[4 * u + 2]);
+            acc[4 * u + 3] = fmaf(v.w, tv, acc[4 * u + 3]);
+        }
+    }
+}
+
+constexpr int FR = 8;    // frames per CTA in the forward transform
+
+// grid (ceil(T/FR), B).  Rows = (frame r, mic m) pairs, processed RB at a time.
+__global__ void __launch_bounds__(THREADS) stft_kernel(const float* __restrict__ wave, float* __restrict__ spec,
+                                                       const float* __restrict__ tab, const float* __restrict__ win,
+                                                       int B, int M, int L, int T) {
+    extern __shared__ __align__(16) float dsm[];
+    float* Aev = dsm;                                   // [NF][RB]
+    float* Aod = Aev + NF * RB;                         // [NF][RB]
+    float2* Xs = reinterpret_cast<float2*>(Aod + NF * RB);   // [RB][NF]
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FR;
+    const int nrows = FR * M;
+    const int col = threadIdx.x;
+    for (int rb0 = 0; rb0 < nrows; rb0 += RB) {
+        // ---- build the folded, windowed frames
+        for (int i = threadIdx.x; i < RB * NF; i += THREADS) {
+            const int r = i / NF, k = i - r * NF;
+            const int row = rb0 + r;
+            float ev = 0.f, od = 0.f;
+            const int fr = row / M, m = row - fr * M;
+            const int t = t0 + fr;
+            if (row < nrows && t < T) {
+                const float* x = wave + ((size_t)b * M + m) * L;
+                auto sample = [&](int n) -> float {
+                    int j = HOP * t + n - HOP;            // centre padding = 160, reflect (test.py:35)
+                    if (j < 0) j = -j;
+                    if (j >= L) j = 2 * (L - 1) - j;
+                    return __ldg(x + j) * __ldg(win + n);
+                };
+                const float g0 = sample(k);
+                if (k == 0 || k == HOP) {
+                    ev = g0;
+                } else {
+                    const float g1 = sample(NFFT - k);
+                    ev = g0 + g1;
+                    od = g0 - g1;
+                }
+            }
+            Aev[k * RB + r] = ev;
+            Aod[k * RB + r] = od;
+        }
+        __syncthreads();
+        // ---- 161 real + 161 imaginary columns
+        if (col < NCOL) {
+            float acc[RB];
+            column_gemm(col < NF ? Aev : Aod, tab, col, acc);
+            const int f = col < NF ? col : col - NF;
+            float* xs = reinterpret_cast<float*>(Xs);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) xs[(r * NF + f) * 2 + (col < NF ? 0 : 1)] = acc[r];
+        }
+        __syncthreads();
+        // ---- compression z |z|^{-1/2} and store to [B,T,F,M,2]
+        for (int i = threadIdx.x; i < RB * NF; i += THREADS) {
+            const int r = i / NF, f = i - r * NF;
+            const int row = rb0 + r;
+            const int fr = row / M, m = row - fr * M;
+            const int t = t0 + fr;
+            if (row < nrows && t < T) {
+                float2 z = Xs[r * NF + f];
+                const float mag = sqrtf(z.x * z.x + z.y * z.y);
+                const float sc = mag > 0.f ? rsqrtf(mag) : 0.f;
+                z.x *= sc;
+                z.y *= sc;
+                reinterpret_cast<float2*>(spec)[(((size_t)b * T + t) * NF + f) * M + m] = z;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int IFR = RB;          // frames per CTA in the inverse transform -> IFR-1 output hops
+
+// grid (ceil((T-1)/(IFR-1)), B)
+__global__ void __launch_bounds__(THREADS) istft_kernel(const float* __restrict__ spec, float* __restrict__ wave,
+                                                        const float* __restrict__ tab, const float* __restrict__ win,
+                                                        const float* __restrict__ ienv, int B, int T) {
+    extern __shared__ __align__(16) float dsm[];
+    float* Are = dsm;                    // [NF][RB]
+    float* Aim = Are + NF * RB;          // [NF][RB]
+    float* PQ = Aim + NF * RB;           // [frame][col]: P[n] (col<161), Q[n] (col>=161)
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * (IFR - 1);
+    const size_t plane = (size_t)T * NF;
+    const float* yr = spec + (size_t)b * 2 * plane;
+    const float* yi = yr + plane;
+    for (int i = threadIdx.x; i < RB * NF; i += THREADS) {
+        const int r = i / NF, f = i - r * NF;
+        const int t = t0 + r;
+        float re = 0.f, im = 0.f;
+        if (t < T) {
+            re = __ldg(yr + (size_t)t * NF + f);
+            im = __ldg(yi + (size_t)t * NF + f);
+        }
+        Are[f * RB + r] = re;
+        Aim[f * RB + r] = im;
+    }
+    __syncthreads();
+    const int col = threadIdx.x;
+    if (col < NCOL) {
+        float acc[RB];
+        column_gemm(col < NF ? Are : Aim, tab, col, acc);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) PQ[r * NCOL + col] = acc[r];
+    }
+    __syncthreads();
+    const size_t out_len = (size_t)HOP * (T - 1);
+    for (int i = threadIdx.x; i < (IFR - 1) * HOP; i += THREADS) {
+        const int u = i / HOP, n = i - u * HOP;
+        const int ta = t0 + u;              // earlier frame contributes its second half, sample n + 160
+        if (ta + 1 > T - 1) continue;
+        const float* Pa = PQ + u * NCOL;
+        const float* Pb = PQ + (u + 1) * NCOL;
+        const float sa = Pa[HOP - n] + Pa[NF + HOP - n];          // s_a[n+160] * 320 / 320 (scale in table)
+        const float sb = Pb[n] - Pb[NF + n];                      // s_b[n]
+        const float v = (__ldg(win + n + HOP) * sa + __ldg(win + n) * sb) * __ldg(ienv + n);
+        wave[(size_t)b * out_len + (size_t)ta * HOP + n] = v;
+    }
+}
+
+constexpr size_t kSmemBytes = (size_t)(2 * NF * RB + RB * NCOL) * sizeof(float);   // both kernels
+
+}  // namespace
+
+int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st) {
+    if (L < HOP + 1) return fail("stft: need at least 161 samples (reflect padding of 160)");
+    if (B <= 0 || M <= 0) return fail("stft: bad shape");
+    Tables* t;
+    EAB_TRY(get_tables(&t));
+    const int T = 1 + L / HOP;
+    static bool configured = false;
+    if (!configured) {
+        EAB_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        EAB_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        configured = true;
+    }
+    stft_kernel<<<dim3((T + FR - 1) / FR, B), THREADS, kSmemBytes, st>>>(wave, spec, t->fwd, t->win, B, M, L, T);
+    EAB_LAUNCH_CHECK("stft_kernel");
+    return 0;
+}
+
+int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st) {
+    if (T < 2) return fail("istft: need at least 2 frames");
+    Tables* t;
+    EAB_TRY(get_tables(&t));
+    static bool configured = false;
+    if (!configured) {
+        EAB_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        EAB_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        configured = true;
+    }
+    istft_kernel<<<dim3((T - 1 + IFR - 2) / (IFR - 1), B), THREADS, kSmemBytes, st>>>(spec, wave, t->inv, t->win, t->ienv, B, T);
+    EAB_LAUNCH_CHECK("istft_kernel");
+    return 0;
+}
+
+}  // namespace eab

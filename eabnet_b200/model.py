@@ -1,0 +1,249 @@
+"""Drop-in `EaBNet(nn.Module)`: the reference's constructor, attributes, state_dict and forward contract
+(EaBNet.py:9-125) over the hand-written sm_100a kernels in libeabnet_b200.so.
+
+The module holds ordinary nn.Parameters under exactly the reference's names (so `load_state_dict`, `.to()`,
+`.state_dict()`, DDP wrapping ... behave), and a native handle that owns the packed copies the kernels read.
+Packed weights are refreshed whenever a parameter's version counter or storage changes.  Inference only:
+the kernels have no backward, and `forward` raises if autograd is recording on any input/parameter.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_BF = {"lstm": 0, "cnn": 1}
+_TOPO = {"mimo": 0, "miso": 1}
+_INTRA = {"cat": 0, "add": 1}
+_NORM = {"IN": 0, "BN": 1}
+N_FREQ = 161
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+class _Native:
+    """Owns an eab_model* and frees it with the module."""
+
+    def __init__(self, cfg: _lib.EabConfig):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        _lib.check(self.lib.eab_create(C.byref(cfg), C.byref(self.h)), "eab_create")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.eab_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def param_table(self) -> List[Tuple[str, Tuple[int, ...], int, int]]:
+        out = []
+        name, ndim, kind, fan = C.c_char_p(), C.c_int(), C.c_int(), C.c_int()
+        shape = (C.c_int64 * 4)()
+        for i in range(self.lib.eab_param_count(self.h)):
+            _lib.check(self.lib.eab_param_info(self.h, i, C.byref(name), C.byref(ndim), C.byref(shape),
+                                               C.byref(kind), C.byref(fan)))
+            out.append((name.value.decode(), tuple(int(shape[k]) for k in range(ndim.value)), kind.value, fan.value))
+        return out
+
+
+class EaBNet(nn.Module):
+    def __init__(self, k1: tuple = (2, 3), k2: tuple = (1, 3), c: int = 64, M: int = 9, embed_dim: int = 64,
+                 kd1: int = 5, cd1: int = 64, d_feat: int = 256, p: int = 6, q: int = 3, is_causal: bool = True,
+                 is_u2: bool = True, bf_type: str = "lstm", topo_type: str = "mimo", intra_connect: str = "cat",
+                 norm_type: str = "IN"):
+        super().__init__()
+        self.k1, self.k2, self.c, self.M, self.embed_dim = tuple(k1), tuple(k2), c, M, embed_dim
+        self.kd1, self.cd1, self.d_feat, self.p, self.q = kd1, cd1, d_feat, p, q
+        self.is_causal, self.is_u2, self.bf_type = is_causal, is_u2, bf_type
+        self.intra_connect, self.topo_type, self.norm_type = intra_connect, topo_type, norm_type
+        if norm_type == "cLN":
+            # the reference raises a TypeError here as well (NormSwitch passes a string as num_features)
+            raise TypeError("norm_type 'cLN' cannot be constructed (EaBNet.py:689,691)")
+        for val, table, what in ((bf_type, _BF, "bf_type"), (topo_type, _TOPO, "topo_type"),
+                                 (intra_connect, _INTRA, "intra_connect"), (norm_type, _NORM, "norm_type")):
+            if val not in table:
+                raise ValueError("unknown %s %r" % (what, val))
+        cfg = _lib.EabConfig(self.k1[0], self.k1[1], self.k2[0], self.k2[1], c, M, embed_dim, kd1, cd1, d_feat, p, q,
+                             int(bool(is_causal)), int(bool(is_u2)), _BF[bf_type], _TOPO[topo_type],
+                             _INTRA[intra_connect], _NORM[norm_type], N_FREQ)
+        object.__setattr__(self, "_native", _Native(cfg))
+        object.__setattr__(self, "_table", self._native.param_table())
+        object.__setattr__(self, "_packed_key", None)
+        object.__setattr__(self, "_ws", None)
+        object.__setattr__(self, "_pack_device", None)
+        for name, shape, kind, fan in self._table:
+            self._register(name, self._init_tensor(shape, kind, fan), is_buffer=kind in (8, 9, 10))
+
+    # ---------------------------------------------------------------- parameter tree
+    @staticmethod
+    def _init_tensor(shape, kind, fan) -> torch.Tensor:
+        """torch's default initialisers for the layer kinds the reference uses."""
+        if kind == 10:
+            return torch.tensor(0, dtype=torch.long)
+        t = torch.empty(shape, dtype=torch.float32)
+        bound = 1.0 / math.sqrt(max(fan, 1))
+        if kind in (0, 1, 5, 6, 7):
+            t.uniform_(-bound, bound)           # kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), +) ; LSTM 1/sqrt(H)
+        elif kind in (2, 9):
+            t.fill_(1.0)
+        elif kind in (3, 8):
+            t.zero_()
+        elif kind == 4:
+            t.fill_(0.25)
+        return t
+
+    def _register(self, dotted: str, value: torch.Tensor, is_buffer: bool) -> None:
+        parts = dotted.split(".")
+        mod: nn.Module = self
+        for part in parts[:-1]:
+            if part not in mod._modules:
+                mod.add_module(part, nn.Module())
+            mod = mod._modules[part]
+        if is_buffer:
+            mod.register_buffer(parts[-1], value)
+        else:
+            mod.register_parameter(parts[-1], nn.Parameter(value))
+
+    def _tensor_of(self, dotted: str) -> torch.Tensor:
+        mod: nn.Module = self
+        parts = dotted.split(".")
+        for part in parts[:-1]:
+            mod = mod._modules[part]
+        t = mod._parameters.get(parts[-1])
+        return t if t is not None else mod._buffers[parts[-1]]
+
+    # ---------------------------------------------------------------- packing
+    def _sync_params(self, device: torch.device) -> None:
+        tensors = [self._tensor_of(n) for n, _, _, _ in self._table]
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if key == self._packed_key:
+            return
+        lib, h = self._native.lib, self._native.h
+        keep = []
+        for (name, shape, kind, _), t in zip(self._table, tensors):
+            if kind == 10:
+                _lib.check(lib.eab_set_param(h, name.encode(), None, 0))
+                continue
+            if t.dtype != torch.float32:
+                raise TypeError("eabnet_b200 computes in fp32; parameter %s is %s" % (name, t.dtype))
+            ht = t.detach().to("cpu").contiguous()
+            keep.append(ht)
+            _lib.check(lib.eab_set_param(h, name.encode(), _ptr(ht), ht.numel()), name)
+        with torch.cuda.device(device):
+            _lib.check(lib.eab_commit_params(h, torch.cuda.current_stream(device).cuda_stream), "commit")
+        object.__setattr__(self, "_packed_key", key)
+        object.__setattr__(self, "_pack_device", device)
+
+    def _workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        ws = self._ws
+        if ws is None or ws.device != device or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            object.__setattr__(self, "_ws", ws)
+        return ws
+
+    def _check_input(self, x: torch.Tensor, what: str) -> None:
+        if not x.is_cuda:
+            raise RuntimeError("eabnet_b200 runs on CUDA (sm_100a) only; %s is on %s - there is no CPU fallback"
+                               % (what, x.device))
+        if x.dtype != torch.float32:
+            raise TypeError("%s must be float32" % what)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("eabnet_b200 is an inference path (no backward kernels): call it under "
+                               "torch.no_grad() / torch.inference_mode()")
+        if self.norm_type == "BN" and self.training:
+            raise RuntimeError("norm_type='BN' is supported in eval() mode only (running statistics)")
+
+    # ---------------------------------------------------------------- the reference contract
+    def forward(self, inpt: torch.Tensor) -> torch.Tensor:
+        """inpt [B,T,F,M,2] (or [B,T,F,2] for M = 1) -> [B,2,T,F]   (EaBNet.py:88-125)."""
+        if inpt.ndim == 4:
+            inpt = inpt.unsqueeze(-2)
+        if inpt.ndim != 5 or inpt.shape[-1] != 2:
+            raise ValueError("expected [B,T,F,M,2], got %s" % (tuple(inpt.shape),))
+        self._check_input(inpt, "inpt")
+        B, T, Fq, M, _ = inpt.shape
+        if Fq != N_FREQ or M != self.M:
+            raise RuntimeError("expected F=%d and M=%d, got F=%d, M=%d" % (N_FREQ, self.M, Fq, M))
+        dev = inpt.device
+        x = inpt.contiguous()
+        with torch.cuda.device(dev):
+            self._sync_params(dev)
+            lib, h = self._native.lib, self._native.h
+            nbytes = lib.eab_workspace_bytes(h, B, T)
+            if nbytes == 0:
+                _lib.check(1, "eab_workspace_bytes")
+            ws = self._workspace(nbytes, dev)
+            out = torch.empty((B, 2, T) if self.topo_type == "miso" else (B, 2, T, Fq), dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.eab_forward(h, _ptr(x), _ptr(out), B, T, _ptr(ws), ws.numel(), stream), "eab_forward")
+        return out
+
+    # ---------------------------------------------------------------- wave-to-wave (test.py:178-190)
+    def enhance(self, wave: torch.Tensor) -> torch.Tensor:
+        """wave [B,M,L] on the GPU -> enhanced [B,160*(L//160)]: STFT+compression, forward, iSTFT in one call."""
+        self._check_input(wave, "wave")
+        B, M, L = wave.shape
+        if M != self.M:
+            raise RuntimeError("expected %d microphones, got %d" % (self.M, M))
+        dev = wave.device
+        x = wave.contiguous()
+        with torch.cuda.device(dev):
+            self._sync_params(dev)
+            lib, h = self._native.lib, self._native.h
+            nbytes = lib.eab_enhance_workspace_bytes(h, B, L)
+            if nbytes == 0:
+                _lib.check(1, "eab_enhance_workspace_bytes")
+            ws = self._workspace(nbytes, dev)
+            out = torch.empty((B, 160 * (L // 160)), dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.eab_enhance(h, _ptr(x), _ptr(out), B, L, _ptr(ws), ws.numel(), stream), "eab_enhance")
+        return out
+
+    def enhance_host(self, wave: torch.Tensor, out: torch.Tensor | None = None,
+                     device: torch.device | str = "cuda") -> torch.Tensor:
+        """HOST wave [B,M,L] (ideally pinned) -> HOST enhanced wave; copies both ways inside the call."""
+        if wave.is_cuda or wave.dtype != torch.float32:
+            raise TypeError("enhance_host takes a float32 CPU tensor")
+        B, M, L = wave.shape
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        x = wave.contiguous()
+        if out is None:
+            out = torch.empty((B, 160 * (L // 160)), dtype=torch.float32, pin_memory=True)
+        with torch.cuda.device(dev):
+            self._sync_params(dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._native.lib.eab_enhance_host(self._native.h, _ptr(x), _ptr(out), B, L, stream),
+                       "eab_enhance_host")
+        return out
+
+    # ---------------------------------------------------------------- introspection for tests / bench
+    def last_launch_count(self) -> int:
+        return int(self._native.lib.eab_last_launch_count(self._native.h))
+
+    def debug_tap(self, name: str, shape: Tuple[int, ...]) -> torch.Tensor:
+        """Named intermediate of the last forward (normalised + activated), channels-last [B,T,F',C']."""
+        dev = self._pack_device
+        dst = torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            n = self._native.lib.eab_debug_tap(self._native.h, name.encode(), _ptr(dst), dst.numel(),
+                                               torch.cuda.current_stream(dev).cuda_stream)
+        if n != dst.numel():
+            raise RuntimeError("debug_tap(%s): got %d elements, expected %d (%s)" % (
+                name, n, dst.numel(), (self._native.lib.eab_last_error() or b"").decode()))
+        return dst
+
+
+def numParams(net: nn.Module) -> int:
+    """EaBNet.py:653-659."""
+    return sum(int(p.numel()) for p in net.parameters() if p.requires_grad)

@@ -1,0 +1,117 @@
+/*
+ * eabnet_b200 -- C ABI of the B200-native EaBNet inference hot path.
+ *
+ * The reference (Ezreal11/EaBNet) is pure Python/PyTorch and has no FFI of its own; the boundary it exposes
+ * for this path is the Python class `EaBNet(nn.Module)` (EaBNet.py:9-125).  Every entry point below names
+ * the reference interface it stands in for.  Signatures use plain pointers and sizes only (no torch types);
+ * "dev" pointers are CUDA device pointers on the current device, `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  All functions return 0 on success, non-zero on failure with a
+ * message available from eab_last_error() (the Python host layer turns that into RuntimeError -- the
+ * reference reports errors as Python exceptions only).  There is no CPU fallback.
+ *
+ * Tensor layouts are the reference's own at the boundary:
+ *     inpt  [B, T, F, M, 2] fp32   (EaBNet.forward argument, EaBNet.py:90)
+ *     out   [B, 2, T, F]    fp32   (EaBNet.forward result,   EaBNet.py:91);  [B, 2, T] for topo_type "miso"
+ *     wave  [B, M, L]       fp32   (prepare_data argument,   test.py:20,32)
+ *     enhanced wave [B, 160*(L/160)] fp32 (torch.istft result, enhance.py:61-62)
+ */
+#ifndef EABNET_B200_H_
+#define EABNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define EAB_API __attribute__((visibility("default")))
+#else
+#define EAB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Constructor arguments of EaBNet.__init__ (EaBNet.py:10-27), same meaning, enums for the strings. */
+typedef struct eab_config {
+    int k1_t, k1_f;      /* k1 = (2,3)  kernel of the gated 2-D convs                       */
+    int k2_t, k2_f;      /* k2 = (1,3)  kernel inside the inner U-Nets                      */
+    int c;               /* 64          channels of the 2-D convs                           */
+    int M;               /* 9           microphones                                        */
+    int embed_dim;       /* 64                                                             */
+    int kd1;             /* 5           dilated kernel size in the squeezed TCM             */
+    int cd1;             /* 64          squeezed channels                                  */
+    int d_feat;          /* 256         TCM feature channels (= 64 * bottleneck F)          */
+    int p, q;            /* 6, 3        TCMs per group, groups                              */
+    int is_causal;       /* 1                                                              */
+    int is_u2;           /* 1                                                              */
+    int bf_type;         /* 0 "lstm", 1 "cnn"                                               */
+    int topo_type;       /* 0 "mimo", 1 "miso"                                              */
+    int intra_connect;   /* 0 "cat",  1 "add"                                               */
+    int norm_type;       /* 0 "IN",   1 "BN" (eval-mode running statistics)                 */
+    int n_freq;          /* 161         F of the input spectrum (fft_num/2+1, test.py:26)   */
+} eab_config;
+
+typedef struct eab_model eab_model;
+
+/* kinds reported by eab_param_info (used by the host layer to pick torch's default initialiser) */
+enum { EAB_P_CONV_W = 0, EAB_P_CONV_B = 1, EAB_P_NORM_G = 2, EAB_P_NORM_B = 3, EAB_P_PRELU = 4,
+       EAB_P_LSTM = 5, EAB_P_LIN_W = 6, EAB_P_LIN_B = 7, EAB_P_BN_MEAN = 8, EAB_P_BN_VAR = 9,
+       EAB_P_BN_COUNT = 10 };
+
+/* EaBNet.__init__ (EaBNet.py:50-86).  Pure host work: no CUDA call is made until parameters are
+ * committed, so this (and the parameter table below) is usable on a machine without a GPU. */
+EAB_API int  eab_create(const eab_config* cfg, eab_model** out);
+EAB_API void eab_destroy(eab_model* m);
+
+/* nn.Module.state_dict() key/shape table (498 entries for the default config), in the
+ * reference's registration order.  `shape` receives up to 4 extents, `fan_in` the torch fan-in of the owning
+ * layer (for default initialisation). */
+EAB_API int  eab_param_count(const eab_model* m);
+EAB_API int  eab_param_info(const eab_model* m, int index, const char** name, int* ndim, int64_t shape[4],
+                    int* kind, int* fan_in);
+
+/* nn.Module.load_state_dict (enhance.py:22, test.py:165): hand over one fp32 tensor in its reference layout
+ * from HOST memory; eab_commit_params packs everything into the kernels' layouts and uploads it (one blob).
+ * BN "num_batches_tracked" is accepted and ignored. */
+EAB_API int  eab_set_param(eab_model* m, const char* name, const float* host_data, int64_t numel);
+EAB_API int  eab_commit_params(eab_model* m, void* stream);
+
+/* Scratch needed by eab_forward / eab_enhance for a given batch and frame count (caller allocates; the
+ * reference relies on torch's caching allocator, SURVEY.md section 8b "Ownership"). */
+EAB_API size_t eab_workspace_bytes(const eab_model* m, int B, int T);
+
+/* EaBNet.forward (EaBNet.py:88-125).  inpt is not modified. */
+EAB_API int  eab_forward(eab_model* m, const float* inpt_dev, float* out_dev, int B, int T,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* prepare_data's noisy branch (test.py:32-43 == train_distributed.py:80-91): STFT 320/160 hann,
+ * center/reflect, + square-root magnitude compression.  T = 1 + L/160.  spec_dev [B,T,161,M,2]. */
+EAB_API int  eab_stft(const float* wave_dev, float* spec_dev, int B, int M, int L, void* stream);
+
+/* torch.istft call of enhance.py:59-61 / test.py:189-190 on a [B,2,T,161] spectrum -> [B,160*(T-1)]. */
+EAB_API int  eab_istft(const float* spec_dev, float* wave_dev, int B, int T, void* stream);
+
+/* The whole test.py:178-190 sequence on device buffers: wave [B,M,L] -> enhanced [B,160*(L/160)].
+ * Workspace must be at least eab_enhance_workspace_bytes(m,B,L). */
+EAB_API size_t eab_enhance_workspace_bytes(const eab_model* m, int B, int L);
+EAB_API int  eab_enhance(eab_model* m, const float* wave_dev, float* enhanced_dev, int B, int L,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Same with HOST buffers (the call enhance.py makes end to end: H2D, compute, D2H all inside; the library
+ * keeps its own device scratch).  Synchronises the stream before returning. */
+EAB_API int  eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host, int B, int L, void* stream);
+
+/* Introspection used by tests and bench: number of kernels launched by the last forward/enhance call, and a
+ * copy of a named intermediate of the last eab_forward ("en.0".."en.4", "tcm", "de.0".."de.3", "embed",
+ * "h1", "h2", "w") with its normalisation/activation applied, channels-last [B,T,F',C'].  Returns the
+ * number of floats written (<= capacity) or -1. */
+EAB_API int     eab_last_launch_count(const eab_model* m);
+EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, int64_t capacity, void* stream);
+
+EAB_API const char* eab_last_error(void);
+EAB_API const char* eab_build_info(void);   /* "sm_100a;<date>;<nvcc>" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EABNET_B200_H_ */

@@ -148,6 +148,12 @@ def unet_module(sd: SD, pfx: str, x: Tensor, k_in, scale: int, deconv: bool, cfg
     return x0 + y
 
 
+def _tap(taps, name: str, x: Tensor) -> None:
+    """record a channels-last copy [B,T,F,C] of an intermediate (debug aid for the stage-wise GPU tests)"""
+    if taps is not None:
+        taps[name] = x.permute(0, 2, 3, 1).contiguous() if x.dim() == 4 else x
+
+
 def encoder(sd: SD, x: Tensor, cfg: dict) -> Tuple[Tensor, List[Tensor]]:
     """U2Net_Encoder (EaBNet.py:157-197) or UNet_Encoder (:199-239)."""
     skips = []
@@ -165,16 +171,19 @@ def encoder(sd: SD, x: Tensor, cfg: dict) -> Tuple[Tensor, List[Tensor]]:
     return x, skips
 
 
-def decoder(sd: SD, x: Tensor, skips: List[Tensor], cfg: dict) -> Tensor:
+def decoder(sd: SD, x: Tensor, skips: List[Tensor], cfg: dict, taps=None) -> Tensor:
     """U2Net_Decoder (EaBNet.py:241-279) or UNet_Decoder (:282-328)."""
     if cfg["is_u2"]:
         for i in range(4):
             x = unet_module(sd, "de.meta_unet_list.%d" % i, torch.cat((x, skips[-(i + 1)]), dim=1),
                             cfg["k1"], i + 1, True, cfg)
+            _tap(taps, "de.%d" % i, x)
         return _gated_block(sd, "de.last_conv", torch.cat((x, skips[0]), dim=1), (2, 5), cfg, True)
     for i in range(5):
         k = (2, 5) if i == 4 else cfg["k1"]
         x = _gated_block(sd, "de.unet_list.%d" % i, torch.cat((x, skips[-(i + 1)]), dim=1), k, cfg, True)
+        if i < 4:
+            _tap(taps, "de.%d" % i, x)
     return x
 
 
@@ -224,7 +233,7 @@ def lstm_layer(x: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor
     return torch.stack(out, dim=1)
 
 
-def lstm_head(sd: SD, emb: Tensor, cfg: dict) -> Tensor:
+def lstm_head(sd: SD, emb: Tensor, cfg: dict, taps=None) -> Tensor:
     """LSTM_BF (EaBNet.py:581-614): emb [B, C, T, F] -> beam weights [B, T, F, M, 2]."""
     B, C, T, Fq = emb.shape
     x = F.layer_norm(emb.permute(0, 3, 2, 1), (C,), sd["bf_map.norm.weight"], sd["bf_map.norm.bias"], 1e-5)
@@ -232,6 +241,8 @@ def lstm_head(sd: SD, emb: Tensor, cfg: dict) -> Tensor:
     for r in ("rnn1", "rnn2"):
         x = lstm_layer(x, *(sd["bf_map.%s.%s_l0" % (r, n)] for n in
                             ("weight_ih", "weight_hh", "bias_ih", "bias_hh")))
+        if taps is not None:
+            taps["h1" if r == "rnn1" else "h2"] = x.view(B, Fq, T, -1).transpose(1, 2).contiguous()
     x = x.view(B, Fq, T, -1).transpose(1, 2)
     x = torch.relu(F.linear(x, sd["bf_map.w_dnn.0.weight"], sd["bf_map.w_dnn.0.bias"]))
     x = F.linear(x, sd["bf_map.w_dnn.2.weight"], sd["bf_map.w_dnn.2.bias"])
@@ -244,26 +255,32 @@ def filter_and_sum(w: Tensor, inpt: Tensor) -> Tensor:
     return torch.stack(((wr * xr - wi * xi).sum(-1), (wr * xi + wi * xr).sum(-1)), dim=1)
 
 
-def network_embedding(sd: SD, inpt: Tensor, cfg: dict) -> Tensor:
+def network_embedding(sd: SD, inpt: Tensor, cfg: dict, taps=None) -> Tensor:
     """inpt [B,T,F,M,2] -> decoder output [B, embed_dim, T, F]  (EaBNet.py:95-107)."""
     B, T, Fq, M, _ = inpt.shape
     x = inpt.transpose(-2, -1).reshape(B, T, Fq, 2 * M).permute(0, 3, 1, 2)           # channel = ri*M + m
     x, skips = encoder(sd, x, cfg)
+    for i, s in enumerate(skips):
+        _tap(taps, "en.%d" % i, s)
     x = tcm_stack(sd, x, cfg)
-    return decoder(sd, x, skips, cfg)
+    _tap(taps, "tcm", x)
+    emb = decoder(sd, x, skips, cfg, taps)
+    _tap(taps, "embed", emb)
+    return emb
 
 
 @torch.no_grad()
-def forward(sd: SD, inpt: Tensor, cfg: dict | None = None) -> Tensor:
-    """EaBNet.forward (EaBNet.py:88-125).  inpt [B,T,F,M,2] or [B,T,F,2]; returns [B,2,T,F] ([B,2,T] miso)."""
+def forward(sd: SD, inpt: Tensor, cfg: dict | None = None, taps=None) -> Tensor:
+    """EaBNet.forward (EaBNet.py:88-125).  inpt [B,T,F,M,2] or [B,T,F,2]; returns [B,2,T,F] ([B,2,T] miso).
+    `taps`, if a dict, receives channels-last copies of the main intermediates."""
     cfg = make_cfg() if cfg is None else cfg
     if inpt.dim() == 4:
         inpt = inpt.unsqueeze(-2)
     B, T, Fq, M, _ = inpt.shape
-    emb = network_embedding(sd, inpt, cfg)
+    emb = network_embedding(sd, inpt, cfg, taps)
     if cfg["topo_type"] == "mimo":
         if cfg["bf_type"] == "lstm":
-            w = lstm_head(sd, emb, cfg)
+            w = lstm_head(sd, emb, cfg, taps)
         else:
             w = F.conv2d(emb, sd["bf_map.weight"], sd["bf_map.bias"])
             w = w.view(B, M, -1, T, Fq).permute(0, 3, 4, 1, 2)
