@@ -16,6 +16,15 @@ void count_launch(int n = 1);                            // per-thread launch co
 int  launch_count();
 void reset_launch_count();
 
+// Optional per-launch timing (CUDA events on the launching stream), switched on by eab_profile_enable; used by
+// bench.py for the live roofline of the dominant kernel.  `flops` / `bytes` are ALGORITHMIC figures of the launch.
+struct ProfScope {
+    ProfScope(const char* category, double flops, double bytes, cudaStream_t st);
+    ~ProfScope();
+    void* rec;
+    cudaStream_t st;
+};
+
 #define EAB_CUDA(x)                                                   \
     do {                                                              \
         if (eab::check_cuda((x), #x)) return 1;                       \
@@ -128,6 +137,7 @@ struct ConvArgs {
     const float* bias;           // [N] or null
     int Cout, N, gate_off;       // N = padded column count (multiple of 64); gate_off>0 => gated
     int relu;                    // ReLU on the output (w_dnn hidden layer)
+    float algo_frac;             // share of the dense K x N product that is algorithmic work (profiling only)
     float* out;                  // [B][T][Fout][Cout]
     const float* resid;          // optional, same layout as out (TCM residual)
     double* stats[2];            // optional [B][Cout][2] accumulators

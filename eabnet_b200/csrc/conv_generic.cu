@@ -312,6 +312,11 @@ int launch_inst(const ConvArgs& a, cudaStream_t st) {
     }
     const int rows = a.T * a.E;
     dim3 grid((rows + TM - 1) / TM, a.B);
+    const double pos = (double)a.B * rows;
+    const int ncol = a.Cout * (GATED ? 2 : 1);
+    ProfScope ps("conv_generic", 2.0 * pos * a.ntaps * Ctot * ncol * a.algo_frac,
+                 4.0 * (pos * a.in_stride * Ctot / (a.out_stride > 1 ? 2.0 : 1.0) + pos * a.Cout * (a.resid ? 2 : 1) +
+                        (double)a.ntaps * Ctot * ncol), st);
     conv_generic_kernel<NV, RPT, GATED><<<grid, NTHREADS, smem, st>>>(a);
     EAB_LAUNCH_CHECK("conv_generic_kernel");
     return 0;

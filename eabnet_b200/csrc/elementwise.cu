@@ -106,12 +106,16 @@ int launch_combine(const CombineArgs& a, cudaStream_t st) {
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
     const size_t smem = (size_t)a.nsrc * 3 * a.C * sizeof(float);
+    ProfScope ps("combine", (double)a.nsrc * a.B * per_b, 4.0 * (a.nsrc + 1) * a.B * per_b, st);
     combine_kernel<<<dim3(blocks, a.B), 256, smem, st>>>(a);
     EAB_LAUNCH_CHECK("combine_kernel");
     return 0;
 }
 
 int launch_beam(const BeamArgs& a, cudaStream_t st) {
+    const double npos = (double)a.B * a.T * a.F;
+    const int nw = a.miso ? 2 : 2 * a.M;
+    ProfScope ps("beam", 4.0 * nw * npos, 4.0 * npos * (nw + 2.0 * a.M + 2), st);
     if (a.miso) {
         const size_t warps = (size_t)a.B * a.T;
         beam_miso_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a);

@@ -210,6 +210,7 @@ int launch_inst(const LstmArgs& a, cudaStream_t st) {
         configured = true;
     }
     const int NQ = a.B * a.F;
+    ProfScope ps("lstm", 2.0 * NQ * a.T * (E + H) * 4.0 * H, 4.0 * NQ * a.T * (E + H), st);
     lstm_kernel<SPT, E><<<(NQ + S - 1) / S, 256, smem, st>>>(a);
     EAB_LAUNCH_CHECK("lstm_kernel");
     return 0;

@@ -6,6 +6,7 @@
 // channels-last [B,T,F,C] fp32 and are stored RAW next to their (sum, sumsq) statistics; normalisation and
 // PReLU are applied by the consumer while it stages its operand (see common.cuh Xform).
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <map>
@@ -30,6 +31,37 @@ int check_cuda(cudaError_t e, const char* what) {
     return 1;
 }
 void count_launch(int n) { g_launches += n; }
+
+// ------------------------------------------------------------------------------------------------ profiler
+struct ProfRec { const char* cat; double flops, bytes; cudaEvent_t a, b; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        cudaEvent_t e;
+        if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
+        cudaEventCreate(&e);
+        return e;
+    }
+    void clear() {
+        for (auto& r : recs) { pool.push_back(r.a); pool.push_back(r.b); }
+        recs.clear();
+    }
+};
+static thread_local Profiler g_prof;
+
+ProfScope::ProfScope(const char* category, double flops, double bytes, cudaStream_t s) : rec(nullptr), st(s) {
+    if (!g_prof.on) return;
+    ProfRec r{category, flops, bytes, g_prof.get(), g_prof.get()};
+    cudaEventRecord(r.a, st);
+    g_prof.recs.push_back(r);
+    rec = reinterpret_cast<void*>(g_prof.recs.size());      // index + 1
+}
+ProfScope::~ProfScope() {
+    if (!rec) return;
+    cudaEventRecord(g_prof.recs[reinterpret_cast<size_t>(rec) - 1].b, st);
+}
 int launch_count() { return g_launches; }
 void reset_launch_count() { g_launches = 0; }
 
@@ -543,6 +575,7 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out)
         a.W = cx.W(L.off_w[v]);
         a.bias = cx.W(L.off_b);
         a.Cout = L.cout; a.N = L.N; a.gate_off = L.gate_off;
+        a.algo_frac = 1.f;
         a.out = out->data;
         if (stats) { a.nstats = 1; a.stats[0] = stats; }
         EAB_TRY(launch_conv(a, cx.st));
@@ -617,6 +650,7 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
     a.ntaps = ntaps;
     for (int i = 0; i < ntaps; ++i) { a.dt[i] = dt ? dt[i] : 0; a.df[i] = 0; }
     a.W = W; a.bias = bias; a.Cout = Cout; a.N = N; a.gate_off = gate_off; a.relu = relu;
+    a.algo_frac = (nsrc == 2 && gate_off > 0) ? 0.5f : 1.f;      // merged TCM branches: block-diagonal weights
     a.out = out->data; a.resid = resid;
     a.nstats = nstats;
     for (int i = 0; i < nstats; ++i) { a.stats[i] = stats[i]; a.stat_alpha[i] = stat_alpha[i]; }
@@ -956,6 +990,41 @@ int64_t eab_debug_tap(eab_model* m, const char* name, float* dst, int64_t capaci
     a.B = t.B; a.P = t.T * t.act.F; a.C = t.act.C; a.out = dst;
     if (launch_combine(a, static_cast<cudaStream_t>(stream))) return -1;
     return n;
+}
+
+int eab_profile_enable(eab_model* m, int on) {
+    (void)m;
+    g_prof.clear();
+    g_prof.on = on != 0;
+    return 0;
+}
+
+int64_t eab_profile_summary(eab_model* m, char* buf, int64_t cap) {
+    (void)m;
+    if (!buf || cap < 2) { fail("eab_profile_summary: bad buffer"); return -1; }
+    if (check_cuda(cudaDeviceSynchronize(), "profile sync")) return -1;
+    struct Agg { int n = 0; double ms = 0, flops = 0, bytes = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : g_prof.recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+        Agg& a = agg[r.cat];
+        a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    }
+    std::string js = "[";
+    bool first = true;
+    for (auto& kv : agg) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s{\"kernel\":\"%s\",\"launches\":%d,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}",
+                 first ? "" : ",", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+        js += tmp;
+        first = false;
+    }
+    js += "]";
+    g_prof.clear();
+    if ((int64_t)js.size() + 1 > cap) { fail("eab_profile_summary: buffer too small"); return -1; }
+    memcpy(buf, js.c_str(), js.size() + 1);
+    return (int64_t)js.size();
 }
 
 const char* eab_last_error(void) { return g_err.c_str(); }

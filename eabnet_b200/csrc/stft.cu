@@ -238,6 +238,7 @@ int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_
         EAB_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         configured = true;
     }
+    ProfScope ps("stft", 2.0 * NF * NCOL * (double)B * M * T, 4.0 * ((double)B * M * L + (double)B * T * NF * M * 2), st);
     stft_kernel<<<dim3((T + FR - 1) / FR, B), THREADS, kSmemBytes, st>>>(wave, spec, t->fwd, t->win, B, M, L, T);
     EAB_LAUNCH_CHECK("stft_kernel");
     return 0;
@@ -253,6 +254,7 @@ int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st) 
         EAB_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         configured = true;
     }
+    ProfScope ps("istft", 2.0 * NF * NCOL * (double)B * T, 4.0 * ((double)B * 2 * T * NF + (double)B * HOP * (T - 1)), st);
     istft_kernel<<<dim3((T - 1 + IFR - 2) / (IFR - 1), B), THREADS, kSmemBytes, st>>>(spec, wave, t->inv, t->win, t->ienv, B, T);
     EAB_LAUNCH_CHECK("istft_kernel");
     return 0;

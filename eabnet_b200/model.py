@@ -231,6 +231,19 @@ class EaBNet(nn.Module):
     def last_launch_count(self) -> int:
         return int(self._native.lib.eab_last_launch_count(self._native.h))
 
+    def profile(self, on: bool) -> None:
+        """switch per-launch CUDA-event timing on/off for this thread's launches"""
+        _lib.check(self._native.lib.eab_profile_enable(self._native.h, int(bool(on))))
+
+    def profile_summary(self) -> list:
+        """[{kernel, launches, ms, flops, bytes}] since the last call (synchronises the device)"""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        n = self._native.lib.eab_profile_summary(self._native.h, buf, len(buf))
+        if n < 0:
+            _lib.check(1, "eab_profile_summary")
+        return json.loads(buf.value.decode())
+
     def debug_tap(self, name: str, shape: Tuple[int, ...]) -> torch.Tensor:
         """Named intermediate of the last forward (normalised + activated), channels-last [B,T,F',C']."""
         dev = self._pack_device

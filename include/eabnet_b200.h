@@ -108,6 +108,12 @@ EAB_API int  eab_enhance_host(eab_model* m, const float* wave_host, float* enhan
 EAB_API int     eab_last_launch_count(const eab_model* m);
 EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, int64_t capacity, void* stream);
 
+/* Per-launch CUDA-event timing of the calling thread's launches, aggregated per kernel family; the summary is a
+ * JSON array [{"kernel","launches","ms","flops","bytes"}] with ALGORITHMIC flops/bytes, written to
+ * `buf` (returns its length, or -1).  Reading the summary synchronises the device and clears the records. */
+EAB_API int     eab_profile_enable(eab_model* m, int on);
+EAB_API int64_t eab_profile_summary(eab_model* m, char* buf, int64_t capacity);
+
 EAB_API const char* eab_last_error(void);
 EAB_API const char* eab_build_info(void);   /* "sm_100a;<date>;<nvcc>" */
 

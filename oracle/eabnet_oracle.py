@@ -217,7 +217,21 @@ def tcm_stack(sd: SD, x: Tensor, cfg: dict) -> Tensor:
 
 
 def lstm_layer(x: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor) -> Tensor:
-    """nn.LSTM(batch_first, 1 layer, zero initial state), gate order i,f,g,o, restated step by step."""
+    """nn.LSTM(batch_first, 1 layer, zero initial state) through torch's own fused CPU primitive - the same call
+    the reference makes (EaBNet.py:610-611), so the CPU baseline is not handicapped by a Python time loop.
+    tests/test_oracle_golden.py checks it against the step-by-step restatement below."""
+    H = w_hh.shape[1]
+    rnn = torch.nn.LSTM(input_size=w_ih.shape[1], hidden_size=H, batch_first=True).to(x.dtype)
+    with torch.no_grad():
+        rnn.weight_ih_l0.copy_(w_ih)
+        rnn.weight_hh_l0.copy_(w_hh)
+        rnn.bias_ih_l0.copy_(b_ih)
+        rnn.bias_hh_l0.copy_(b_hh)
+        return rnn(x)[0]
+
+
+def lstm_layer_stepwise(x: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor) -> Tensor:
+    """The recurrence written out: gate order i,f,g,o, both biases added, h0 = c0 = 0."""
     N, T, _ = x.shape
     H = w_hh.shape[1]
     gx = x @ w_ih.t() + (b_ih + b_hh)

@@ -62,3 +62,14 @@ def test_si_sdr_definition():
     s = rng.randn(1000)
     assert O.si_sdr(s, 3.0 * s + 1e-3 * rng.randn(1000)) > 50
     assert abs(O.si_sdr(s, s + rng.randn(1000))) < 1.5
+
+
+def test_lstm_fused_equals_stepwise_restatement():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(7, 33, 64, generator=g)
+    w = [torch.randn(256, 64, generator=g) * 0.125, torch.randn(256, 64, generator=g) * 0.125,
+         torch.randn(256, generator=g) * 0.1, torch.randn(256, generator=g) * 0.1]
+    assert (O.lstm_layer(x, *w) - O.lstm_layer_stepwise(x, *w)).abs().max() <= 2e-6
+    xd = x.double()
+    wd = [t.double() for t in w]
+    assert (O.lstm_layer(xd, *wd) - O.lstm_layer_stepwise(xd, *wd)).abs().max() <= 1e-12
