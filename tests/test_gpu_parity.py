@@ -85,8 +85,11 @@ def test_forward_matches_oracle(over, B, L):
     net, sd = _net(cfg, seed=2)
     wave, _ = O.make_wave(B, cfg["M"], L, seed=21)
     spec = O.stft_compress(wave)
-    taps = {}
+    taps, taps64 = {}, {}
     ref = O.forward(sd, spec, cfg, taps)
+    # conditioning of the case itself: the oracle in fp64 vs fp32 (InstanceNorm over a handful of frames is
+    # ill-conditioned for very short inputs); the kernels may deviate by a few times that, never by more
+    ref64 = O.forward({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}, spec.double(), cfg, taps64)
     with torch.no_grad():
         x = spec.cuda()
         if cfg["M"] == 1:
@@ -96,9 +99,11 @@ def test_forward_matches_oracle(over, B, L):
     scale = max(1.0, float(ref.abs().max()))
     for name, r in taps.items():
         got = net.debug_tap(name, tuple(r.shape)).cpu()
-        assert (got - r).abs().max() <= 5e-4 * max(1.0, float(r.abs().max())), name
-    err = float((out - ref).abs().max())
-    assert err <= TIGHT * scale and err <= TOL * scale, err
+        cond = float((r.double() - taps64[name]).abs().max())
+        assert (got.double() - taps64[name]).abs().max() <= max(5e-4 * max(1.0, float(r.abs().max())), 8 * cond), name
+    err = float((out.double() - ref64).abs().max())
+    cond = float((ref.double() - ref64).abs().max())
+    assert err <= max(TIGHT * scale, 8 * cond) and err <= TOL * scale, (err, cond)
 
 
 def test_enhance_wave_to_wave_and_si_sdr():
