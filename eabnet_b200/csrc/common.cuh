@@ -146,6 +146,36 @@ struct ConvArgs {
 };
 int launch_conv(const ConvArgs& a, cudaStream_t st);
 
+// tcgen05 implicit-GEMM variant of ConvArgs (conv_umma.cu).  Weights come as 128B-swizzled K-major images
+// [ntaps][nslab][N rows][32 k] already rounded to TF32 (hi) plus the rounding residual (lo) for 3xTF32.
+struct UmmaConvArgs {
+    ConvSrc src[2];
+    int nsrc;
+    int B, T, Fin, E;
+    int in_stride, out_stride, out_off, Fout;
+    int ntaps;
+    int dt[kMaxTaps], df[kMaxTaps];
+    int wide, kwidth;            // first-layer mode: a tap is a window of kwidth contiguous floats (kf positions x C)
+    int nslab;                   // 32-element K slabs per tap
+    int ncoef;                   // total input channels (transform coefficients held in shared memory)
+    int npass;                   // 1: TF32, 3: 3xTF32 (hi*hi + lo*hi + hi*lo)
+    const float* Whi;
+    const float* Wlo;
+    const float* bias;           // [N] (value | gate) or null
+    int Cout, N, gate_off;       // plain: N == Cout; gated: N == 2*Cout, gate_off == Cout
+    int relu;
+    float algo_frac;
+    float* out;
+    int out_ld, out_coff;        // output row stride (channels) and channel offset
+    const float* resid;          // optional, addressed like out
+    double* stats[2];
+    const float* stat_alpha[2];
+    int nstats;
+    int tiles_per_b;             // ceil(T*E / 128)
+};
+bool umma_conv_supported(const UmmaConvArgs& a);
+int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st);
+
 struct CombineArgs {
     ConvSrc src[3];
     int nsrc;

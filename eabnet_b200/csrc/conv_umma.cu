@@ -1,0 +1,546 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a -- the hot-path kernel of the 2-D conv family
+// (gated / plain Conv2d and ConvTranspose2d with stride (1,2), EaBNet.py:391-490) and of every other
+// conv-shaped layer whose channel counts fit (TCM 1x1 / dilated convs, w_dnn).
+//
+// GEMM view: rows = output positions (t,e) of one batch item, K = taps x input channels, N = output channels
+// (value | gate halves side by side).  One CTA (320 threads) walks a contiguous range of 128-row tiles:
+//
+//   warps 0-3  A producers : gather the tap's input rows from HBM/L2 (channels-last, 128 B per row per K slab),
+//                            apply the producer layer's norm + PReLU (Xform), round to TF32 (or split hi/lo for
+//                            3xTF32), store into the 128B-swizzled K-major stage, fence.proxy.async, arrive.
+//   warp 4     MMA issuer  : one elected lane issues 4 x tcgen05.mma.kind::tf32 (M128 x N x K8) per stage,
+//                            tcgen05.commit frees the stage; a second commit per tile publishes the accumulator.
+//   warp 5     B loader    : cp.async.bulk of the pre-swizzled, pre-rounded weight image (N x 128 B) per stage.
+//   warps 6-9  epilogue    : tcgen05.ld accumulator rows from TMEM (double-buffered, so the next tile's MMAs
+//                            overlap), bias + gate + ReLU, stage in smem, coalesced 128-bit stores (+ residual),
+//                            per-(b,c) sum / sum-of-squares of the tile -> fp64 atomics (InstanceNorm statistics).
+//
+// The channel concat of a skip connection is two K slabs; a transposed conv is two launches (output parity);
+// the causal halo and the ragged last tile are literal zero rows.  npass = 3 runs every K slab three times
+// (A_hi B_hi + A_lo B_hi + A_hi B_lo) for fp32-grade accuracy where single-pass TF32 is not enough.
+#include "common.cuh"
+
+namespace eab {
+
+namespace {
+
+constexpr int TM = 128;             // rows per tile (UMMA M)
+constexpr int KC = 32;              // tf32 elements per K slab = one 128-byte swizzle row
+constexpr int NPROD = 256;          // producer threads (8 warps)
+constexpr int RPP = TM * 8 / NPROD;  // rows per producer thread per K slab
+constexpr int NEPI = 128;           // epilogue threads
+constexpr int NTHREADS = NPROD + 64 + NEPI;
+constexpr int A_STAGE_BYTES = TM * 128;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > SPIN_LIMIT) __trap();        // a protocol bug must fault, never hang the GPU
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B stacked along M/N (SBO = 1024 B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+    return d;
+}
+
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                    // D format F32
+    d |= 2u << 7;                    // A format TF32
+    d |= 2u << 10;                   // B format TF32
+    d |= (uint32_t)(N >> 3) << 17;   // N / 8
+    d |= (uint32_t)(TM >> 4) << 24;  // M / 16
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct Smem {
+    // offsets (bytes) into the 1024-aligned dynamic shared memory
+    int a_off, b_off, stg_off, rowoff_off, coef_off, bar_off, total;
+    int nstages, b_stage_bytes, stg_ld;
+};
+
+__host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef) {
+    Smem s;
+    s.b_stage_bytes = N * 128;
+    s.stg_ld = Cout + 4;
+    const int stage = A_STAGE_BYTES + s.b_stage_bytes;
+    const int fixed = TM * s.stg_ld * 4 + TM * 8 + 3 * ncoef * 4 + 256;
+    int ns = (227 * 1024 - 1024 - fixed) / stage;
+    if (ns > 6) ns = 6;
+    s.nstages = ns;
+    s.a_off = 0;
+    s.b_off = ns * A_STAGE_BYTES;
+    s.stg_off = s.b_off + ns * s.b_stage_bytes;
+    s.rowoff_off = s.stg_off + TM * s.stg_ld * 4;
+    s.coef_off = s.rowoff_off + TM * 8;
+    s.bar_off = (s.coef_off + 3 * ncoef * 4 + 15) / 16 * 16;
+    s.total = s.bar_off + 256 + 1024;          // + slack for the 1024-byte alignment of the base
+    return s;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef);
+    uint8_t* As = smem + sp.a_off;
+    uint8_t* Bs = smem + sp.b_off;
+    float* stg = reinterpret_cast<float*>(smem + sp.stg_off);
+    long long* rowoff = reinterpret_cast<long long*>(smem + sp.rowoff_off);
+    float* coef = reinterpret_cast<float*>(smem + sp.coef_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
+    uint64_t* full = bars;                      // [nstages]  A stored (128 arrivals) + B bytes landed
+    uint64_t* empty = bars + 8;                 // [nstages]  MMAs that read the stage have completed
+    uint64_t* acc_full = bars + 16;             // [2]        accumulator complete
+    uint64_t* acc_empty = bars + 18;            // [2]        accumulator drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int NS = sp.nstages;
+    const uint32_t tmem_cols = a.N <= 64 ? 128u : (a.N <= 128 ? 256u : 512u);      // two accumulators
+
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], NPROD + 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
+        fence_barrier_init();
+    }
+    if (warp == NPROD / 32) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // contiguous tile range of this CTA
+    const long long ntiles = (long long)a.B * a.tiles_per_b;
+    const long long tile_begin = ntiles * blockIdx.x / gridDim.x;
+    const long long tile_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+    const int rows_per_b = a.T * a.E;
+    const int chunks_per_pass_unit = a.ntaps * a.nslab;       // (tap, slab) pairs
+    const int nchunks = chunks_per_pass_unit * a.npass;
+
+    if (warp < NPROD / 32) {
+        // =========================================================================== A producers
+        // Software-pipelined over the flattened (tile, unit) stream: the global loads of unit g+PF are in flight
+        // while unit g is transformed and stored, across tile boundaries.
+        const int c4 = tid & 7;                 // 16-byte chunk inside the 128-byte slab row
+        const int rbase = tid >> 3;             // rows rbase + 32 i, i < 4
+        const int upt = chunks_per_pass_unit;   // units per tile
+        const long long total_units = (tile_end - tile_begin) * upt;
+
+        // ---- load-side cursor (runs PF units ahead of the store side)
+        long long l_tile = tile_begin;
+        int l_unit = 0, l_b = 0;
+        int rt[RPP], re[RPP];
+        bool rv[RPP];
+        auto decode_tile = [&](long long tile) {
+            l_b = (int)(tile / a.tiles_per_b);
+            const int row0 = (int)(tile - (long long)l_b * a.tiles_per_b) * TM;
+#pragma unroll
+            for (int i = 0; i < RPP; ++i) {
+                const int r = row0 + rbase + 32 * i;
+                rv[i] = r < rows_per_b;
+                rt[i] = r / a.E;
+                re[i] = r - rt[i] * a.E;
+            }
+        };
+        auto issue_loads = [&](float4 (&v)[RPP], uint32_t& mask) {
+            const int tap = l_unit / a.nslab;
+            const int slab = l_unit - tap * a.nslab;
+            const int dtv = a.dt[tap], dfv = a.df[tap];
+            int s = 0, c0 = slab * KC;
+            if (!a.wide && c0 >= a.src[0].C) { s = 1; c0 -= a.src[0].C; }
+            const float* __restrict__ xsrc = a.src[s].x;
+            const int C = a.src[s].C;
+            const int cc = c0 + c4 * 4;
+            mask = 0;
+#pragma unroll
+            for (int i = 0; i < RPP; ++i) {
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int tt = rt[i] - dtv;
+                const int fi = re[i] * a.in_stride + dfv;
+                if (rv[i] && tt >= 0 && tt < a.T && fi >= 0 && fi < a.Fin) {
+                    const float* p = xsrc + (((size_t)l_b * a.T + tt) * a.Fin + fi) * C + cc;
+                    if (!a.wide) {
+                        v[i] = __ldg(reinterpret_cast<const float4*>(p));
+                    } else {                     // first layer: window of kwidth floats, 8-byte aligned only
+                        if (cc + 1 < a.kwidth) { const float2 q = __ldg(reinterpret_cast<const float2*>(p)); v[i].x = q.x; v[i].y = q.y; }
+                        if (cc + 3 < a.kwidth) { const float2 q = __ldg(reinterpret_cast<const float2*>(p) + 1); v[i].z = q.x; v[i].w = q.y; }
+                    }
+                    mask |= 1u << i;
+                }
+            }
+            if (++l_unit == upt) {
+                l_unit = 0;
+                if (++l_tile < tile_end) decode_tile(l_tile);
+            }
+        };
+
+        // ---- store-side state
+        int cur_b = -1;
+        int stage = 0;
+        uint32_t phase = 0;
+        int s_unit = 0;
+        long long s_tile = tile_begin;
+        auto consume = [&](float4 (&v)[RPP], uint32_t mask) {
+            if (s_unit == 0) {
+                const int b = (int)(s_tile / a.tiles_per_b);
+                if (b != cur_b) {
+                    named_bar_sync(1, NPROD);   // nobody still reads the previous coefficients
+                    for (int i = tid; i < a.ncoef; i += NPROD) {
+                        const int s = i < a.src[0].C ? 0 : 1;
+                        const int c = s ? i - a.src[0].C : i;
+                        float cs, ch, ca;
+                        xform_coeffs(a.src[s].xf, b, a.src[s].C, c, cs, ch, ca);
+                        coef[i] = cs;
+                        coef[a.ncoef + i] = ch;
+                        coef[2 * a.ncoef + i] = ca;
+                    }
+                    named_bar_sync(1, NPROD);
+                    cur_b = b;
+                }
+            }
+            const int tap = s_unit / a.nslab;
+            const int slab = s_unit - tap * a.nslab;
+            int s = 0, c0 = slab * KC, soff = 0;
+            if (!a.wide && c0 >= a.src[0].C) { s = 1; c0 -= a.src[0].C; soff = a.src[0].C; }
+            const int prelu = a.src[s].xf.prelu;
+            const bool ident = a.wide || (a.src[s].xf.affine == 0 && prelu == 0);
+            if (!ident) {
+                const int ci = soff + c0 + c4 * 4;
+                float cs[4], ch[4], ca[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { cs[q] = coef[ci + q]; ch[q] = coef[a.ncoef + ci + q]; ca[q] = coef[2 * a.ncoef + ci + q]; }
+#pragma unroll
+                for (int i = 0; i < RPP; ++i) {
+                    if (mask & (1u << i)) {
+                        v[i].x = xform_apply(v[i].x, cs[0], ch[0], ca[0], prelu);
+                        v[i].y = xform_apply(v[i].y, cs[1], ch[1], ca[1], prelu);
+                        v[i].z = xform_apply(v[i].z, cs[2], ch[2], ca[2], prelu);
+                        v[i].w = xform_apply(v[i].w, cs[3], ch[3], ca[3], prelu);
+                    }
+                }
+            }
+            for (int pass = 0; pass < a.npass; ++pass) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* A = As + stage * A_STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < RPP; ++i) {
+                    const int r = rbase + 32 * i;
+                    float4 o;
+                    const float hx = to_tf32(v[i].x), hy = to_tf32(v[i].y), hz = to_tf32(v[i].z), hw = to_tf32(v[i].w);
+                    if (pass == 1) {             // residual of the TF32 rounding, itself rounded to TF32
+                        o = make_float4(to_tf32(v[i].x - hx), to_tf32(v[i].y - hy), to_tf32(v[i].z - hz), to_tf32(v[i].w - hw));
+                    } else {
+                        o = make_float4(hx, hy, hz, hw);
+                    }
+                    *reinterpret_cast<float4*>(A + r * 128 + ((c4 ^ (r & 7)) << 4)) = o;
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[stage]);
+                if (++stage == NS) { stage = 0; phase ^= 1; }
+            }
+            if (++s_unit == upt) { s_unit = 0; ++s_tile; }
+        };
+
+        float4 v0[RPP], v1[RPP], v2[RPP];
+        uint32_t m0 = 0, m1 = 0, m2 = 0;
+        decode_tile(l_tile);
+        long long issued = 0;
+        if (issued < total_units) { issue_loads(v0, m0); ++issued; }
+        if (issued < total_units) { issue_loads(v1, m1); ++issued; }
+        for (long long g = 0; g < total_units; g += 3) {
+            if (issued < total_units) { issue_loads(v2, m2); ++issued; }
+            consume(v0, m0);
+            if (g + 1 >= total_units) break;
+            if (issued < total_units) { issue_loads(v0, m0); ++issued; }
+            consume(v1, m1);
+            if (g + 2 >= total_units) break;
+            if (issued < total_units) { issue_loads(v1, m1); ++issued; }
+            consume(v2, m2);
+        }
+    } else if (warp == NPROD / 32) {
+        // =========================================================================== MMA issuer
+        const uint32_t idesc = make_idesc(a.N);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = tile_begin; tile < tile_end; ++tile) {
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.N);
+            for (int ch = 0; ch < nchunks; ++ch) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(As + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(Bs + stage * sp.b_stage_bytes);
+#pragma unroll
+                    for (int k = 0; k < KC / 8; ++k) {
+                        const uint64_t ad = make_desc(a_addr + k * 32);
+                        const uint64_t bd = make_desc(b_addr + k * 32);
+                        umma_tf32(d_tmem, ad, bd, idesc, (ch | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);                         // stage reusable once these MMAs retire
+                    if (ch == nchunks - 1) umma_commit(&acc_full[acc]);   // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == NS) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp == NPROD / 32 + 1) {
+        // =========================================================================== B (weight) loader
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)sp.b_stage_bytes;
+        for (long long tile = tile_begin; tile < tile_end; ++tile) {
+            for (int unit = 0; unit < chunks_per_pass_unit; ++unit) {
+                for (int pass = 0; pass < a.npass; ++pass) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (lane == 0) {
+                        const float* img = (pass == 2 ? a.Wlo : a.Whi) + (size_t)unit * a.N * KC;
+                        mbar_arrive_expect_tx(&full[stage], bytes);
+                        bulk_copy_g2s(Bs + stage * sp.b_stage_bytes, img, bytes, &full[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // =========================================================================== epilogue (last 4 warps)
+        const int et = tid - (NPROD + 64);      // 0..127
+        const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;       // accumulator row == tile row
+        const bool gated = a.gate_off > 0;
+        const int ld = sp.stg_ld;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = tile_begin; tile < tile_end; ++tile) {
+            const int b = (int)(tile / a.tiles_per_b);
+            const int row0 = (int)(tile - (long long)b * a.tiles_per_b) * TM;
+            const int nvalid = min(TM, rows_per_b - row0);
+            {
+                const int r = row0 + row;
+                long long off = -1;
+                if (r < rows_per_b) {
+                    const int t = r / a.E, e = r - t * a.E;
+                    off = ((((long long)b * a.T + t) * a.Fout) + (e * a.out_stride + a.out_off)) * a.out_ld + a.out_coff;
+                }
+                rowoff[row] = off;
+            }
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.N);
+            for (int c0 = 0; c0 < a.Cout; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (a.bias) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + c0 + i);
+                }
+                if (gated) {
+                    float g[16];
+                    tmem_ld16(taddr + a.gate_off + c0, g);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float gg = g[i] + (a.bias ? __ldg(a.bias + a.gate_off + c0 + i) : 0.f);
+                        v[i] *= sigmoid_f(gg);
+                    }
+                }
+                if (a.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(stg + row * ld + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);       // the MMA warp may start overwriting this accumulator
+            named_bar_sync(2, NEPI);            // staging tile + row offsets complete
+            // ---- coalesced stores (+ residual): Cout/4 threads per row
+            const int tpr = a.Cout >> 2;
+            const int rows_per_it = NEPI / tpr;
+            const int cq = (et % tpr) * 4;
+            for (int r = et / tpr; r < nvalid; r += rows_per_it) {
+                float4 o = *reinterpret_cast<const float4*>(stg + r * ld + cq);
+                const long long off = rowoff[r];
+                if (a.resid) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + off + cq));
+                    o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+                    if (a.nstats) *reinterpret_cast<float4*>(stg + r * ld + cq) = o;
+                }
+                *reinterpret_cast<float4*>(a.out + off + cq) = o;
+            }
+            // ---- per-channel statistics of the tile (valid rows only)
+            if (a.nstats) {
+                if (a.resid) named_bar_sync(2, NEPI);
+                const int nsc = a.nstats * a.Cout;
+                for (int i = et; i < nsc * 2; i += NEPI) {
+                    const int half = i / nsc;
+                    const int sc = i - half * nsc;
+                    const int s = sc / a.Cout, c = sc - s * a.Cout;
+                    const float al = a.stat_alpha[s] ? __ldg(a.stat_alpha[s] + c) : 1.f;
+                    const bool pre = a.stat_alpha[s] != nullptr;
+                    float sum = 0.f, sq = 0.f;
+                    const int r_lo = half * (TM / 2), r_hi = min(nvalid, r_lo + TM / 2);
+                    for (int r = r_lo; r < r_hi; ++r) {
+                        float u = stg[r * ld + c];
+                        if (pre) u = prelu_f(u, al);
+                        sum += u;
+                        sq += u * u;
+                    }
+                    if (r_hi > r_lo) {
+                        double* dst = a.stats[s] + ((size_t)b * a.Cout + c) * 2;
+                        atomicAdd(dst, (double)sum);
+                        atomicAdd(dst + 1, (double)sq);
+                    }
+                }
+            }
+            named_bar_sync(2, NEPI);            // staging free for the next tile
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NPROD / 32) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+bool umma_conv_supported(const UmmaConvArgs& a) {
+    if (a.N % 16 != 0 || a.N < 16 || a.N > 256) return false;
+    if (a.Cout != 16 && a.Cout != 32 && a.Cout != 64 && a.Cout != 128) return false;
+    if (a.gate_off > 0 && (a.gate_off != a.Cout || a.N != 2 * a.Cout)) return false;
+    if (a.gate_off == 0 && a.N != a.Cout) return false;
+    if (a.ntaps < 1 || a.ntaps > kMaxTaps) return false;
+    if (a.wide) {
+        if (a.nsrc != 1 || (a.src[0].C & 1) || (a.kwidth & 1)) return false;
+        if (a.src[0].xf.affine != 0 || a.src[0].xf.prelu != 0) return false;     // wide mode reads raw input only
+    } else {
+        for (int i = 0; i < a.nsrc; ++i)
+            if (a.src[i].C % KC != 0) return false;
+    }
+    if (a.out_ld % 4 != 0 || a.out_coff % 4 != 0) return false;
+    return true;
+}
+
+int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
+    if (!umma_conv_supported(a)) return fail("conv_umma: unsupported shape");
+    if (a.B <= 0 || a.T <= 0 || a.E <= 0) return 0;
+    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef);
+    if (sp.nstages < 2) return fail("conv_umma: not enough shared memory for two stages");
+    static int configured = 0;
+    if (sp.total > configured) {
+        EAB_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        configured = sp.total;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        EAB_CUDA(cudaGetDevice(&dev));
+        EAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long ntiles = (long long)a.B * a.tiles_per_b;
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    const double pos = (double)a.B * a.T * a.E;
+    double kreal = 0;
+    for (int i = 0; i < a.nsrc; ++i) kreal += a.src[i].C;
+    if (a.wide) kreal = a.kwidth;
+    ProfScope ps("conv_umma", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
+                 4.0 * (pos * a.in_stride * kreal / (a.out_stride > 1 ? 2.0 : 1.0) / (a.wide ? (double)a.kwidth / a.src[0].C / 2.0 : 1.0) +
+                        pos * a.Cout * (a.resid ? 2 : 1) + (double)a.ntaps * kreal * a.N),
+                 st);
+    conv_umma_kernel<<<grid, NTHREADS, sp.total, st>>>(a);
+    EAB_LAUNCH_CHECK("conv_umma_kernel");
+    return 0;
+}
+
+}  // namespace eab

@@ -101,6 +101,13 @@ struct ConvLayer {
     int ntaps[2] = {0, 0};
     int dt[2][kMaxTaps], df[2][kMaxTaps];
     size_t off_w[2] = {0, 0}, off_b = 0;
+    // tcgen05 path: swizzled TF32 weight images (hi / lo), per variant
+    bool umma_ok = false, wide = false;
+    int zone = 0;                       // 0 encoder, 1 decoder (precision policy)
+    int u_nslab = 0, u_kwidth = 0, u_N = 0, u_gate_off = 0;
+    int u_ntaps[2] = {0, 0};
+    int u_dt[2][kMaxTaps], u_df[2][kMaxTaps];
+    size_t off_whi[2] = {0, 0}, off_wlo[2] = {0, 0}, off_ub = 0;
     NormAct na;
 };
 
@@ -157,6 +164,10 @@ struct eab_model {
     std::map<std::string, Tap> taps;
     void* scratch = nullptr;      // eab_enhance_host
     size_t scratch_bytes = 0;
+    // options (eab_set_option)
+    int opt_umma = 1;             // tcgen05 path for eligible layers
+    int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
+    int opt_dec_passes = 1;       // single-pass TF32 in the decoder
 };
 
 namespace eab {
@@ -232,6 +243,18 @@ struct Builder {
     }
 };
 
+inline float tf32_rna(float x) {           // cvt.rna.tf32.f32 on the host (ties away from zero, 10-bit mantissa)
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+// element (n, k) of a [N][32] K-major tile with the 128-byte swizzle the tensor core expects
+inline size_t sw128_index(int n, int k) { return (size_t)n * 32 + (size_t)((((k >> 2) ^ (n & 7)) << 2) | (k & 3)); }
+
 int conv_out_f(int Fin, int kf) { return Fin < kf ? -1 : (Fin - kf) / 2 + 1; }
 int deconv_out_f(int Fin, int kf) { return 2 * (Fin - 1) + kf; }
 
@@ -271,6 +294,8 @@ int build(eab_model* m) {
         for (int i = 1; i < 4; ++i)
             m->de_mod.push_back(bd.module("de.meta_unet_list." + std::to_string(i), 2 * c.c, c.k1_t, c.k1_f, i + 1, true));
         m->de_last = bd.gated("de.last_conv", 2 * c.c, c.embed_dim, 2, 5, true, true);
+        for (auto& U : m->de_mod) { U.in_conv.zone = 1; for (auto& L : U.enco) L.zone = 1; for (auto& L : U.deco) L.zone = 1; }
+        m->de_last.zone = 1;
     } else {
         m->en_plain.push_back(bd.gated("en.unet_list.0", 2 * c.M, c.c, 2, 5, false, true));
         m->en_plain[0].perm_ri = true;
@@ -283,6 +308,7 @@ int build(eab_model* m) {
         for (int i = 1; i < 4; ++i)
             m->de_plain.push_back(bd.gated("de.unet_list." + std::to_string(i), 2 * c.c, c.c, c.k1_t, c.k1_f, true, true));
         m->de_plain.push_back(bd.gated("de.unet_list.4", 2 * c.c, c.embed_dim, 2, 5, true, true));
+        for (auto& L : m->de_plain) L.zone = 1;
     }
     // head (EaBNet.py:75-81, 581-598)
     if (c.topo_type == 0 && c.bf_type == 0) {
@@ -405,7 +431,83 @@ struct Packer {
         }
         L.off_b = alloc(L.N);
         for (int n = 0; n < cout_t; ++n) blob[L.off_b + col_of(n)] = P(L.b)[n];
+        pack_umma(L, W);
         normact(L.na);
+    }
+
+    // tcgen05 weight images: [variant][tap][slab][N rows][32 k], 128B-swizzled, hi = tf32(w), lo = tf32(w - hi)
+    void pack_umma(ConvLayer& L, const std::vector<float>& W) {
+        const int co = L.cout;
+        L.umma_ok = false;
+        if (co != 16 && co != 32 && co != 64 && co != 128) return;
+        if (L.gated && co > 128) return;
+        L.wide = L.perm_ri;
+        if (!L.wide && (L.cin % 32 != 0)) return;
+        if (L.wide && L.deconv) return;
+        const int cout_t = L.gated ? 2 * co : co;
+        L.u_N = cout_t;
+        L.u_gate_off = L.gated ? co : 0;
+        L.u_kwidth = L.wide ? L.kf * L.cin : 0;
+        L.u_nslab = L.wide ? (L.u_kwidth + 31) / 32 : L.cin / 32;
+        auto cin_mem = [&](int cin_ref) {
+            if (!L.perm_ri) return cin_ref;
+            const int ri = cin_ref / L.M, mic = cin_ref - ri * L.M;
+            return mic * 2 + ri;
+        };
+        for (int v = 0; v < L.nvar; ++v) {
+            // taps: wide mode has one tap per temporal tap (window over kf positions); otherwise as the generic path
+            std::vector<int> tj, tk;
+            int nt = 0;
+            if (L.wide) {
+                for (int j = 0; j < L.kt; ++j) { L.u_dt[v][nt] = L.kt - 1 - j; L.u_df[v][nt] = 0; tj.push_back(j); tk.push_back(0); ++nt; }
+            } else {
+                nt = L.ntaps[v];
+                int q = 0;
+                for (int j = 0; j < L.kt; ++j)
+                    for (int k = 0; k < L.kf; ++k) {
+                        if (L.deconv && (k & 1) != v) continue;
+                        L.u_dt[v][q] = L.dt[v][q]; L.u_df[v][q] = L.df[v][q];
+                        tj.push_back(j); tk.push_back(k);
+                        ++q;
+                    }
+            }
+            L.u_ntaps[v] = nt;
+            if (nt == 0) return;
+            const size_t img = (size_t)nt * L.u_nslab * cout_t * 32;
+            L.off_whi[v] = alloc(img);
+            L.off_wlo[v] = alloc(img);
+            // dense [tap][kk][n] first (kk = K index inside the tap in MEMORY order), then swizzle per slab
+            const int kper = L.u_nslab * 32;
+            std::vector<float> dense((size_t)nt * kper * cout_t, 0.f);
+            for (int tp = 0; tp < nt; ++tp)
+                for (int ci = 0; ci < L.cin; ++ci)
+                    for (int n = 0; n < cout_t; ++n) {
+                        if (L.wide) {
+                            for (int k = 0; k < L.kf; ++k) {
+                                const size_t src = (((size_t)n * L.cin + ci) * L.kt + tj[tp]) * L.kf + k;
+                                dense[((size_t)tp * kper + (size_t)k * L.cin + cin_mem(ci)) * cout_t + n] = W[src];
+                            }
+                        } else {
+                            const size_t src = L.deconv ? (((size_t)ci * cout_t + n) * L.kt + tj[tp]) * L.kf + tk[tp]
+                                                        : (((size_t)n * L.cin + ci) * L.kt + tj[tp]) * L.kf + tk[tp];
+                            dense[((size_t)tp * kper + ci) * cout_t + n] = W[src];
+                        }
+                    }
+            for (int tp = 0; tp < nt; ++tp)
+                for (int sl = 0; sl < L.u_nslab; ++sl) {
+                    const size_t base = ((size_t)tp * L.u_nslab + sl) * cout_t * 32;
+                    for (int n = 0; n < cout_t; ++n)
+                        for (int k = 0; k < 32; ++k) {
+                            const float w = dense[((size_t)tp * kper + sl * 32 + k) * cout_t + n];
+                            const float hi = tf32_rna(w);
+                            blob[L.off_whi[v] + base + sw128_index(n, k)] = hi;
+                            blob[L.off_wlo[v] + base + sw128_index(n, k)] = tf32_rna(w - hi);
+                        }
+                }
+        }
+        L.off_ub = alloc(cout_t);
+        for (int n = 0; n < cout_t; ++n) blob[L.off_ub + n] = P(L.b)[n];
+        L.umma_ok = true;
     }
 
     void tcm(TcmLayer& t) {
@@ -562,6 +664,28 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out)
     out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
     if (cx.dry) return 0;
     for (int v = 0; v < L.nvar; ++v) {
+        if (cx.m->opt_umma && L.umma_ok) {
+            UmmaConvArgs u;
+            memset(&u, 0, sizeof(u));
+            u.nsrc = nsrc;
+            for (int i = 0; i < nsrc; ++i) { u.src[i].x = srcs[i].data; u.src[i].C = srcs[i].C; u.src[i].xf = srcs[i].xf; }
+            u.B = cx.B; u.T = cx.T; u.Fin = Fin; u.Fout = Fout;
+            if (L.deconv) { u.in_stride = 1; u.out_stride = 2; u.out_off = v; u.E = (Fout - v + 1) / 2; }
+            else          { u.in_stride = 2; u.out_stride = 1; u.out_off = 0; u.E = Fout; }
+            u.ntaps = L.u_ntaps[v];
+            for (int i = 0; i < u.ntaps; ++i) { u.dt[i] = L.u_dt[v][i]; u.df[i] = L.u_df[v][i]; }
+            u.wide = L.wide; u.kwidth = L.u_kwidth; u.nslab = L.u_nslab; u.ncoef = cin;
+            u.npass = L.zone == 0 ? cx.m->opt_enc_passes : cx.m->opt_dec_passes;
+            u.Whi = cx.W(L.off_whi[v]); u.Wlo = cx.W(L.off_wlo[v]); u.bias = cx.W(L.off_ub);
+            u.Cout = L.cout; u.N = L.u_N; u.gate_off = L.u_gate_off; u.algo_frac = 1.f;
+            u.out = out->data; u.out_ld = L.cout; u.out_coff = 0;
+            if (stats) { u.nstats = 1; u.stats[0] = stats; }
+            u.tiles_per_b = (cx.T * u.E + 127) / 128;
+            if (umma_conv_supported(u)) {
+                EAB_TRY(launch_conv_umma(u, cx.st));
+                continue;
+            }
+        }
         ConvArgs a;
         memset(&a, 0, sizeof(a));
         a.nsrc = nsrc;
@@ -990,6 +1114,16 @@ int64_t eab_debug_tap(eab_model* m, const char* name, float* dst, int64_t capaci
     a.B = t.B; a.P = t.T * t.act.F; a.C = t.act.C; a.out = dst;
     if (launch_combine(a, static_cast<cudaStream_t>(stream))) return -1;
     return n;
+}
+
+int eab_set_option(eab_model* m, const char* name, int value) {
+    if (!m || !name) return fail("eab_set_option: null argument");
+    const std::string n(name);
+    if (n == "umma") m->opt_umma = value != 0;
+    else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
+    else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
+    else return fail("eab_set_option: unknown option or bad value: " + n);
+    return 0;
 }
 
 int eab_profile_enable(eab_model* m, int on) {

@@ -231,6 +231,10 @@ class EaBNet(nn.Module):
     def last_launch_count(self) -> int:
         return int(self._native.lib.eab_last_launch_count(self._native.h))
 
+    def set_option(self, name: str, value: int) -> None:
+        """kernel-selection / precision knobs of the native path (see include/eabnet_b200.h: eab_set_option)"""
+        _lib.check(self._native.lib.eab_set_option(self._native.h, name.encode(), int(value)), "eab_set_option")
+
     def profile(self, on: bool) -> None:
         """switch per-launch CUDA-event timing on/off for this thread's launches"""
         _lib.check(self._native.lib.eab_profile_enable(self._native.h, int(bool(on))))

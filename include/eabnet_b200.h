@@ -108,6 +108,12 @@ EAB_API int  eab_enhance_host(eab_model* m, const float* wave_host, float* enhan
 EAB_API int     eab_last_launch_count(const eab_model* m);
 EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, int64_t capacity, void* stream);
 
+/* Precision / kernel-selection knobs of the sm_100a path (defaults in parentheses):
+ *   "umma" (1)        tcgen05 implicit-GEMM kernel for every eligible conv layer; 0 = fp32 CUDA-core kernel only
+ *   "enc_passes" (3)  1 = single-pass TF32, 3 = 3xTF32 split (fp32-grade) in the encoder convs
+ *   "dec_passes" (1)  same for the decoder convs */
+EAB_API int     eab_set_option(eab_model* m, const char* name, int value);
+
 /* Per-launch CUDA-event timing of the calling thread's launches, aggregated per kernel family; the summary is a
  * JSON array [{"kernel","launches","ms","flops","bytes"}] with ALGORITHMIC flops/bytes, written to
  * `buf` (returns its length, or -1).  Reading the summary synchronises the device and clears the records. */

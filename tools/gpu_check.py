@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--B", type=int, default=2)
     ap.add_argument("--L", type=int, default=3200)
     ap.add_argument("--variant", default="B")
+    ap.add_argument("--opt", action="append", default=[], help="name=value for EaBNet.set_option")
     a = ap.parse_args()
     cfg = O.make_cfg(**ast.literal_eval(a.cfg))
     sd = O.make_weights(cfg, 0, a.variant)
@@ -32,6 +33,9 @@ def main():
     net = E.EaBNet(**cfg).eval()
     net.load_state_dict(sd, strict=True)
     net.to(dev)
+    for o in a.opt:
+        k, v = o.split("=")
+        net.set_option(k, int(v))
 
     spec_ref = O.stft_compress(wave)
     spec = E.stft_compress(wave.to(dev))
