@@ -130,15 +130,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// round-to-nearest (ties away) to the 10-bit TF32 mantissa: add half an ulp of the kept part, clear the rest.
+// (cvt.rna.tf32.f32 compiles to a ~5-instruction sequence on sm_100a; activations here are finite.)
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 struct Smem {
     // offsets (bytes) into the 1024-aligned dynamic shared memory
-    int a_off, b_off, stg_off, rowoff_off, coef_off, bar_off, total;
+    int a_off, b_off, stg_off, rowoff_off, coef_off, bias_off, bar_off, total;
     int nstages, b_stage_bytes, stg_ld;
 };
 
@@ -147,7 +145,7 @@ __host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef) {
     s.b_stage_bytes = N * 128;
     s.stg_ld = Cout + 4;
     const int stage = A_STAGE_BYTES + s.b_stage_bytes;
-    const int fixed = TM * s.stg_ld * 4 + TM * 8 + 3 * ncoef * 4 + 256;
+    const int fixed = TM * s.stg_ld * 4 + TM * 8 + 3 * ncoef * 4 + N * 4 + 256 + 64;
     int ns = (227 * 1024 - 1024 - fixed) / stage;
     if (ns > 6) ns = 6;
     s.nstages = ns;
@@ -156,20 +154,25 @@ __host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef) {
     s.stg_off = s.b_off + ns * s.b_stage_bytes;
     s.rowoff_off = s.stg_off + TM * s.stg_ld * 4;
     s.coef_off = s.rowoff_off + TM * 8;
-    s.bar_off = (s.coef_off + 3 * ncoef * 4 + 15) / 16 * 16;
+    s.bias_off = (s.coef_off + 3 * ncoef * 4 + 15) / 16 * 16;
+    s.bar_off = s.bias_off + N * 4;
     s.total = s.bar_off + 256 + 1024;          // + slack for the 1024-byte alignment of the base
     return s;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // align to 1024 B (128B-swizzle atom) by OFFSETTING the __shared__ array: a round trip through uintptr_t would
+    // demote every later access to generic ST.E / LD.E
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const Smem sp = smem_plan(a.N, a.Cout, a.ncoef);
     uint8_t* As = smem + sp.a_off;
     uint8_t* Bs = smem + sp.b_off;
     float* stg = reinterpret_cast<float*>(smem + sp.stg_off);
     long long* rowoff = reinterpret_cast<long long*>(smem + sp.rowoff_off);
     float* coef = reinterpret_cast<float*>(smem + sp.coef_off);
+    float* sbias = reinterpret_cast<float*>(smem + sp.bias_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
     uint64_t* full = bars;                      // [nstages]  A stored (128 arrivals) + B bytes landed
     uint64_t* empty = bars + 8;                 // [nstages]  MMAs that read the stage have completed
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         fence_barrier_init();
     }
     if (warp == NPROD / 32) tmem_alloc(tmem_slot, tmem_cols);
+    for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -204,47 +208,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
 
     if (warp < NPROD / 32) {
         // =========================================================================== A producers
-        // Software-pipelined over the flattened (tile, unit) stream: the global loads of unit g+PF are in flight
-        // while unit g is transformed and stored, across tile boundaries.
+        // Software-pipelined over the flattened (tile, unit) stream: the global loads of units g+1, g+2 are in
+        // flight while unit g is transformed and stored, across tile boundaries.  The inner loop is kept free of
+        // divisions and 64-bit index arithmetic (it was issue-bound on exactly that): per-tile row coordinates,
+        // incremental (tap, slab) counters, 32-bit element offsets from a per-batch base pointer.
         const int c4 = tid & 7;                 // 16-byte chunk inside the 128-byte slab row
-        const int rbase = tid >> 3;             // rows rbase + 32 i, i < 4
+        const int rbase = tid >> 3;             // rows rbase + 32 i, i < RPP
         const int upt = chunks_per_pass_unit;   // units per tile
         const long long total_units = (tile_end - tile_begin) * upt;
+        const int nslab0 = WIDE ? a.nslab : a.src[0].C / KC;
+        const int C0 = a.src[0].C, C1 = a.nsrc > 1 ? a.src[1].C : 0;
+        const uint32_t st_off = (uint32_t)(rbase * 128 + ((c4 ^ (rbase & 7)) << 4));   // same swizzle for rows +32 i
 
-        // ---- load-side cursor (runs PF units ahead of the store side)
+        // ---- load-side cursor
         long long l_tile = tile_begin;
-        int l_unit = 0, l_b = 0;
-        int rt[RPP], re[RPP];
-        bool rv[RPP];
+        int l_tap = 0, l_slab = 0;
+        const float* xb0 = nullptr;
+        const float* xb1 = nullptr;
+        int rt[RPP], rf[RPP];                   // frame index and e * in_stride of this thread's rows (big negative if ragged)
         auto decode_tile = [&](long long tile) {
-            l_b = (int)(tile / a.tiles_per_b);
-            const int row0 = (int)(tile - (long long)l_b * a.tiles_per_b) * TM;
+            const int b = (int)(tile / a.tiles_per_b);
+            const int row0 = (int)(tile - (long long)b * a.tiles_per_b) * TM;
+            xb0 = a.src[0].x + (size_t)b * a.T * a.Fin * C0;
+            xb1 = a.nsrc > 1 ? a.src[1].x + (size_t)b * a.T * a.Fin * C1 : nullptr;
 #pragma unroll
             for (int i = 0; i < RPP; ++i) {
                 const int r = row0 + rbase + 32 * i;
-                rv[i] = r < rows_per_b;
-                rt[i] = r / a.E;
-                re[i] = r - rt[i] * a.E;
+                const int t = r / a.E;
+                rt[i] = r < rows_per_b ? t : -(1 << 28);
+                rf[i] = (r - t * a.E) * a.in_stride;
             }
         };
         auto issue_loads = [&](float4 (&v)[RPP], uint32_t& mask) {
-            const int tap = l_unit / a.nslab;
-            const int slab = l_unit - tap * a.nslab;
-            const int dtv = a.dt[tap], dfv = a.df[tap];
-            int s = 0, c0 = slab * KC;
-            if (!a.wide && c0 >= a.src[0].C) { s = 1; c0 -= a.src[0].C; }
-            const float* __restrict__ xsrc = a.src[s].x;
-            const int C = a.src[s].C;
-            const int cc = c0 + c4 * 4;
+            const int dtv = a.dt[l_tap], dfv = a.df[l_tap];
+            const bool second = l_slab >= nslab0;
+            const float* __restrict__ xb = second ? xb1 : xb0;
+            const int C = second ? C1 : C0;
+            const int cc = (second ? l_slab - nslab0 : l_slab) * KC + c4 * 4;
             mask = 0;
 #pragma unroll
             for (int i = 0; i < RPP; ++i) {
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int tt = rt[i] - dtv;
-                const int fi = re[i] * a.in_stride + dfv;
-                if (rv[i] && tt >= 0 && tt < a.T && fi >= 0 && fi < a.Fin) {
-                    const float* p = xsrc + (((size_t)l_b * a.T + tt) * a.Fin + fi) * C + cc;
-                    if (!a.wide) {
+                const int fi = rf[i] + dfv;
+                if ((unsigned)tt < (unsigned)a.T && (unsigned)fi < (unsigned)a.Fin) {
+                    const float* p = xb + (uint32_t)((tt * a.Fin + fi) * C + cc);
+                    if (!WIDE) {
                         v[i] = __ldg(reinterpret_cast<const float4*>(p));
                     } else {                     // first layer: window of kwidth floats, 8-byte aligned only
                         if (cc + 1 < a.kwidth) { const float2 q = __ldg(reinterpret_cast<const float2*>(p)); v[i].x = q.x; v[i].y = q.y; }
@@ -253,9 +262,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                     mask |= 1u << i;
                 }
             }
-            if (++l_unit == upt) {
-                l_unit = 0;
-                if (++l_tile < tile_end) decode_tile(l_tile);
+            if (++l_slab == a.nslab) {
+                l_slab = 0;
+                if (++l_tap == a.ntaps) {
+                    l_tap = 0;
+                    if (++l_tile < tile_end) decode_tile(l_tile);
+                }
             }
         };
 
@@ -263,67 +275,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         int cur_b = -1;
         int stage = 0;
         uint32_t phase = 0;
-        int s_unit = 0;
+        int s_tap = 0, s_slab = 0;
         long long s_tile = tile_begin;
+        const int mode0 = WIDE ? 0 : (a.src[0].xf.affine == 0 && a.src[0].xf.prelu == 0 ? 0 : (a.src[0].xf.prelu == 1 ? 2 : 1));
+        const int mode1 = a.nsrc > 1 ? (a.src[1].xf.affine == 0 && a.src[1].xf.prelu == 0 ? 0 : (a.src[1].xf.prelu == 1 ? 2 : 1)) : 0;
         auto consume = [&](float4 (&v)[RPP], uint32_t mask) {
-            if (s_unit == 0) {
+            if ((s_tap | s_slab) == 0) {
                 const int b = (int)(s_tile / a.tiles_per_b);
                 if (b != cur_b) {
                     named_bar_sync(1, NPROD);   // nobody still reads the previous coefficients
                     for (int i = tid; i < a.ncoef; i += NPROD) {
-                        const int s = i < a.src[0].C ? 0 : 1;
-                        const int c = s ? i - a.src[0].C : i;
+                        const int s = i < C0 ? 0 : 1;
+                        const int c = s ? i - C0 : i;
                         float cs, ch, ca;
                         xform_coeffs(a.src[s].xf, b, a.src[s].C, c, cs, ch, ca);
                         coef[i] = cs;
                         coef[a.ncoef + i] = ch;
-                        coef[2 * a.ncoef + i] = ca;
+                        coef[2 * a.ncoef + i] = a.src[s].xf.prelu ? ca : 1.f;   // slope 1 == no PReLU
                     }
                     named_bar_sync(1, NPROD);
                     cur_b = b;
                 }
             }
-            const int tap = s_unit / a.nslab;
-            const int slab = s_unit - tap * a.nslab;
-            int s = 0, c0 = slab * KC, soff = 0;
-            if (!a.wide && c0 >= a.src[0].C) { s = 1; c0 -= a.src[0].C; soff = a.src[0].C; }
-            const int prelu = a.src[s].xf.prelu;
-            const bool ident = a.wide || (a.src[s].xf.affine == 0 && prelu == 0);
-            if (!ident) {
-                const int ci = soff + c0 + c4 * 4;
-                float cs[4], ch[4], ca[4];
+            const bool second = s_slab >= nslab0;
+            const int mode = second ? mode1 : mode0;
+            if (mode != 0) {
+                const int ci = s_slab * KC + c4 * 4;            // slabs of source 1 follow those of source 0
+                const float4 cs = *reinterpret_cast<const float4*>(coef + ci);
+                const float4 ch = *reinterpret_cast<const float4*>(coef + a.ncoef + ci);
+                const float4 ca = *reinterpret_cast<const float4*>(coef + 2 * a.ncoef + ci);
+                const uint32_t tmask = mask == (1u << RPP) - 1 ? 0xFFFFFFFFu : mask;   // interior tiles: no per-row test
+                if (mode == 1) {                 // norm -> PReLU (2-D blocks)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { cs[q] = coef[ci + q]; ch[q] = coef[a.ncoef + ci + q]; ca[q] = coef[2 * a.ncoef + ci + q]; }
+                    for (int i = 0; i < RPP; ++i) {
+                        if (tmask & (1u << i)) {
+                            float x;
+                            x = fmaf(v[i].x, cs.x, ch.x); v[i].x = fmaxf(x, 0.f) + ca.x * fminf(x, 0.f);
+                            x = fmaf(v[i].y, cs.y, ch.y); v[i].y = fmaxf(x, 0.f) + ca.y * fminf(x, 0.f);
+                            x = fmaf(v[i].z, cs.z, ch.z); v[i].z = fmaxf(x, 0.f) + ca.z * fminf(x, 0.f);
+                            x = fmaf(v[i].w, cs.w, ch.w); v[i].w = fmaxf(x, 0.f) + ca.w * fminf(x, 0.f);
+                        }
+                    }
+                } else {                         // PReLU -> norm (TCM branches)
 #pragma unroll
-                for (int i = 0; i < RPP; ++i) {
-                    if (mask & (1u << i)) {
-                        v[i].x = xform_apply(v[i].x, cs[0], ch[0], ca[0], prelu);
-                        v[i].y = xform_apply(v[i].y, cs[1], ch[1], ca[1], prelu);
-                        v[i].z = xform_apply(v[i].z, cs[2], ch[2], ca[2], prelu);
-                        v[i].w = xform_apply(v[i].w, cs[3], ch[3], ca[3], prelu);
+                    for (int i = 0; i < RPP; ++i) {
+                        if (tmask & (1u << i)) {
+                            v[i].x = fmaf(fmaxf(v[i].x, 0.f) + ca.x * fminf(v[i].x, 0.f), cs.x, ch.x);
+                            v[i].y = fmaf(fmaxf(v[i].y, 0.f) + ca.y * fminf(v[i].y, 0.f), cs.y, ch.y);
+                            v[i].z = fmaf(fmaxf(v[i].z, 0.f) + ca.z * fminf(v[i].z, 0.f), cs.z, ch.z);
+                            v[i].w = fmaf(fmaxf(v[i].w, 0.f) + ca.w * fminf(v[i].w, 0.f), cs.w, ch.w);
+                        }
                     }
                 }
             }
+            float4 hi[RPP];
+#pragma unroll
+            for (int i = 0; i < RPP; ++i) hi[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
             for (int pass = 0; pass < a.npass; ++pass) {
                 mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* A = As + stage * A_STAGE_BYTES;
+                uint8_t* A = As + stage * A_STAGE_BYTES + st_off;
+                if (pass == 1) {                 // residual of the TF32 rounding, itself rounded to TF32
 #pragma unroll
-                for (int i = 0; i < RPP; ++i) {
-                    const int r = rbase + 32 * i;
-                    float4 o;
-                    const float hx = to_tf32(v[i].x), hy = to_tf32(v[i].y), hz = to_tf32(v[i].z), hw = to_tf32(v[i].w);
-                    if (pass == 1) {             // residual of the TF32 rounding, itself rounded to TF32
-                        o = make_float4(to_tf32(v[i].x - hx), to_tf32(v[i].y - hy), to_tf32(v[i].z - hz), to_tf32(v[i].w - hw));
-                    } else {
-                        o = make_float4(hx, hy, hz, hw);
-                    }
-                    *reinterpret_cast<float4*>(A + r * 128 + ((c4 ^ (r & 7)) << 4)) = o;
+                    for (int i = 0; i < RPP; ++i)
+                        *reinterpret_cast<float4*>(A + i * 4096) = make_float4(to_tf32(v[i].x - hi[i].x), to_tf32(v[i].y - hi[i].y),
+                                                                               to_tf32(v[i].z - hi[i].z), to_tf32(v[i].w - hi[i].w));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < RPP; ++i) *reinterpret_cast<float4*>(A + i * 4096) = hi[i];
                 }
                 fence_proxy_async();
                 mbar_arrive(&full[stage]);
                 if (++stage == NS) { stage = 0; phase ^= 1; }
             }
-            if (++s_unit == upt) { s_unit = 0; ++s_tile; }
+            if (++s_slab == a.nslab) {
+                s_slab = 0;
+                if (++s_tap == a.ntaps) { s_tap = 0; ++s_tile; }
+            }
         };
 
         float4 v0[RPP], v1[RPP], v2[RPP];
@@ -420,17 +447,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             for (int c0 = 0; c0 < a.Cout; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
-                if (a.bias) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + c0 + i);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 bq = *reinterpret_cast<const float4*>(sbias + c0 + 4 * i);
+                    v[4 * i] += bq.x; v[4 * i + 1] += bq.y; v[4 * i + 2] += bq.z; v[4 * i + 3] += bq.w;
                 }
                 if (gated) {
                     float g[16];
                     tmem_ld16(taddr + a.gate_off + c0, g);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float gg = g[i] + (a.bias ? __ldg(a.bias + a.gate_off + c0 + i) : 0.f);
-                        v[i] *= sigmoid_f(gg);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 bq = *reinterpret_cast<const float4*>(sbias + a.gate_off + c0 + 4 * i);
+                        v[4 * i] *= sigmoid_f(g[4 * i] + bq.x);
+                        v[4 * i + 1] *= sigmoid_f(g[4 * i + 1] + bq.y);
+                        v[4 * i + 2] *= sigmoid_f(g[4 * i + 2] + bq.z);
+                        v[4 * i + 3] *= sigmoid_f(g[4 * i + 3] + bq.w);
                     }
                 }
                 if (a.relu) {
@@ -519,7 +550,8 @@ int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
     if (sp.nstages < 2) return fail("conv_umma: not enough shared memory for two stages");
     static int configured = 0;
     if (sp.total > configured) {
-        EAB_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        EAB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        EAB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
         configured = sp.total;
     }
     static int sms = 0;
@@ -538,7 +570,8 @@ int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
                  4.0 * (pos * a.in_stride * kreal / (a.out_stride > 1 ? 2.0 : 1.0) / (a.wide ? (double)a.kwidth / a.src[0].C / 2.0 : 1.0) +
                         pos * a.Cout * (a.resid ? 2 : 1) + (double)a.ntaps * kreal * a.N),
                  st);
-    conv_umma_kernel<<<grid, NTHREADS, sp.total, st>>>(a);
+    if (a.wide) conv_umma_kernel<true><<<grid, NTHREADS, sp.total, st>>>(a);
+    else conv_umma_kernel<false><<<grid, NTHREADS, sp.total, st>>>(a);
     EAB_LAUNCH_CHECK("conv_umma_kernel");
     return 0;
 }
