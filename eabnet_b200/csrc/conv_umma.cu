@@ -18,6 +18,8 @@
 // The channel concat of a skip connection is two K slabs; a transposed conv is two launches (output parity);
 // the causal halo and the ragged last tile are literal zero rows.  npass = 3 runs every K slab three times
 // (A_hi B_hi + A_lo B_hi + A_hi B_lo) for fp32-grade accuracy where single-pass TF32 is not enough.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace eab {
@@ -25,7 +27,7 @@ namespace eab {
 namespace {
 
 constexpr int TM = 128;             // rows per tile (UMMA M)
-constexpr int KC = 32;              // tf32 elements per K slab = one 128-byte swizzle row
+constexpr int KC = 64;              // fp16 elements per K slab = one 128-byte swizzle row
 constexpr int NPROD = 256;          // producer threads (8 warps)
 constexpr int RPP = TM * 8 / NPROD;  // rows per producer thread per K slab
 constexpr int NEPI = 128;           // epilogue threads
@@ -95,22 +97,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     return d;
 }
 
-// kind::tf32, fp32 accumulate, both operands K-major, M = 128
+// kind::f16 (fp16 operands, same 10-bit mantissa as TF32 at half the bytes and twice the rate), fp32 accumulate,
+// both operands K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(int N) {
     uint32_t d = 0;
     d |= 1u << 4;                    // D format F32
-    d |= 2u << 7;                    // A format TF32
-    d |= 2u << 10;                   // B format TF32
+    d |= 0u << 7;                    // A format F16
+    d |= 0u << 10;                   // B format F16
     d |= (uint32_t)(N >> 3) << 17;   // N / 8
     d |= (uint32_t)(TM >> 4) << 24;  // M / 16
     return d;
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -130,9 +133,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// round-to-nearest (ties away) to the 10-bit TF32 mantissa: add half an ulp of the kept part, clear the rest.
-// (cvt.rna.tf32.f32 compiles to a ~5-instruction sequence on sm_100a; activations here are finite.)
-__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+// 8 floats -> 8 fp16 (round to nearest even), and the fp16-rounded residual for the 3-pass split
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_lo_h2(float a, float b, uint32_t hi) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    return pack_h2(a - f.x, b - f.y);
+}
 
 struct Smem {
     // offsets (bytes) into the 1024-aligned dynamic shared memory
@@ -239,25 +248,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 rf[i] = (r - t * a.E) * a.in_stride;
             }
         };
-        auto issue_loads = [&](float4 (&v)[RPP], uint32_t& mask) {
+        auto issue_loads = [&](float4 (&v)[2 * RPP], uint32_t& mask) {
             const int dtv = a.dt[l_tap], dfv = a.df[l_tap];
             const bool second = l_slab >= nslab0;
             const float* __restrict__ xb = second ? xb1 : xb0;
             const int C = second ? C1 : C0;
-            const int cc = (second ? l_slab - nslab0 : l_slab) * KC + c4 * 4;
+            const int cc = (second ? l_slab - nslab0 : l_slab) * KC + c4 * 8;      // 8 channels = one 16-byte fp16 chunk
             mask = 0;
 #pragma unroll
             for (int i = 0; i < RPP; ++i) {
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int tt = rt[i] - dtv;
                 const int fi = rf[i] + dfv;
                 if ((unsigned)tt < (unsigned)a.T && (unsigned)fi < (unsigned)a.Fin) {
                     const float* p = xb + (uint32_t)((tt * a.Fin + fi) * C + cc);
                     if (!WIDE) {
-                        v[i] = __ldg(reinterpret_cast<const float4*>(p));
+                        v[2 * i] = __ldg(reinterpret_cast<const float4*>(p));
+                        v[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
                     } else {                     // first layer: window of kwidth floats, 8-byte aligned only
-                        if (cc + 1 < a.kwidth) { const float2 q = __ldg(reinterpret_cast<const float2*>(p)); v[i].x = q.x; v[i].y = q.y; }
-                        if (cc + 3 < a.kwidth) { const float2 q = __ldg(reinterpret_cast<const float2*>(p) + 1); v[i].z = q.x; v[i].w = q.y; }
+                        const float2* p2 = reinterpret_cast<const float2*>(p);
+                        if (cc + 1 < a.kwidth) { const float2 q = __ldg(p2); v[2 * i].x = q.x; v[2 * i].y = q.y; }
+                        if (cc + 3 < a.kwidth) { const float2 q = __ldg(p2 + 1); v[2 * i].z = q.x; v[2 * i].w = q.y; }
+                        if (cc + 5 < a.kwidth) { const float2 q = __ldg(p2 + 2); v[2 * i + 1].x = q.x; v[2 * i + 1].y = q.y; }
+                        if (cc + 7 < a.kwidth) { const float2 q = __ldg(p2 + 3); v[2 * i + 1].z = q.x; v[2 * i + 1].w = q.y; }
                     }
                     mask |= 1u << i;
                 }
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         long long s_tile = tile_begin;
         const int mode0 = WIDE ? 0 : (a.src[0].xf.affine == 0 && a.src[0].xf.prelu == 0 ? 0 : (a.src[0].xf.prelu == 1 ? 2 : 1));
         const int mode1 = a.nsrc > 1 ? (a.src[1].xf.affine == 0 && a.src[1].xf.prelu == 0 ? 0 : (a.src[1].xf.prelu == 1 ? 2 : 1)) : 0;
-        auto consume = [&](float4 (&v)[RPP], uint32_t mask) {
+        auto consume = [&](float4 (&v)[2 * RPP], uint32_t mask) {
             if ((s_tap | s_slab) == 0) {
                 const int b = (int)(s_tile / a.tiles_per_b);
                 if (b != cur_b) {
@@ -300,48 +314,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             const bool second = s_slab >= nslab0;
             const int mode = second ? mode1 : mode0;
             if (mode != 0) {
-                const int ci = s_slab * KC + c4 * 4;            // slabs of source 1 follow those of source 0
-                const float4 cs = *reinterpret_cast<const float4*>(coef + ci);
-                const float4 ch = *reinterpret_cast<const float4*>(coef + a.ncoef + ci);
-                const float4 ca = *reinterpret_cast<const float4*>(coef + 2 * a.ncoef + ci);
+                const int ci = s_slab * KC + c4 * 8;            // slabs of source 1 follow those of source 0
                 const uint32_t tmask = mask == (1u << RPP) - 1 ? 0xFFFFFFFFu : mask;   // interior tiles: no per-row test
-                if (mode == 1) {                 // norm -> PReLU (2-D blocks)
 #pragma unroll
-                    for (int i = 0; i < RPP; ++i) {
-                        if (tmask & (1u << i)) {
-                            float x;
-                            x = fmaf(v[i].x, cs.x, ch.x); v[i].x = fmaxf(x, 0.f) + ca.x * fminf(x, 0.f);
-                            x = fmaf(v[i].y, cs.y, ch.y); v[i].y = fmaxf(x, 0.f) + ca.y * fminf(x, 0.f);
-                            x = fmaf(v[i].z, cs.z, ch.z); v[i].z = fmaxf(x, 0.f) + ca.z * fminf(x, 0.f);
-                            x = fmaf(v[i].w, cs.w, ch.w); v[i].w = fmaxf(x, 0.f) + ca.w * fminf(x, 0.f);
+                for (int h = 0; h < 2; ++h) {
+                    const float4 cs = *reinterpret_cast<const float4*>(coef + ci + 4 * h);
+                    const float4 ch = *reinterpret_cast<const float4*>(coef + a.ncoef + ci + 4 * h);
+                    const float4 ca = *reinterpret_cast<const float4*>(coef + 2 * a.ncoef + ci + 4 * h);
+                    if (mode == 1) {             // norm -> PReLU (2-D blocks)
+#pragma unroll
+                        for (int i = 0; i < RPP; ++i) {
+                            if (tmask & (1u << i)) {
+                                float4& q = v[2 * i + h];
+                                float x;
+                                x = fmaf(q.x, cs.x, ch.x); q.x = fmaxf(x, 0.f) + ca.x * fminf(x, 0.f);
+                                x = fmaf(q.y, cs.y, ch.y); q.y = fmaxf(x, 0.f) + ca.y * fminf(x, 0.f);
+                                x = fmaf(q.z, cs.z, ch.z); q.z = fmaxf(x, 0.f) + ca.z * fminf(x, 0.f);
+                                x = fmaf(q.w, cs.w, ch.w); q.w = fmaxf(x, 0.f) + ca.w * fminf(x, 0.f);
+                            }
                         }
-                    }
-                } else {                         // PReLU -> norm (TCM branches)
+                    } else {                     // PReLU -> norm (TCM branches)
 #pragma unroll
-                    for (int i = 0; i < RPP; ++i) {
-                        if (tmask & (1u << i)) {
-                            v[i].x = fmaf(fmaxf(v[i].x, 0.f) + ca.x * fminf(v[i].x, 0.f), cs.x, ch.x);
-                            v[i].y = fmaf(fmaxf(v[i].y, 0.f) + ca.y * fminf(v[i].y, 0.f), cs.y, ch.y);
-                            v[i].z = fmaf(fmaxf(v[i].z, 0.f) + ca.z * fminf(v[i].z, 0.f), cs.z, ch.z);
-                            v[i].w = fmaf(fmaxf(v[i].w, 0.f) + ca.w * fminf(v[i].w, 0.f), cs.w, ch.w);
+                        for (int i = 0; i < RPP; ++i) {
+                            if (tmask & (1u << i)) {
+                                float4& q = v[2 * i + h];
+                                q.x = fmaf(fmaxf(q.x, 0.f) + ca.x * fminf(q.x, 0.f), cs.x, ch.x);
+                                q.y = fmaf(fmaxf(q.y, 0.f) + ca.y * fminf(q.y, 0.f), cs.y, ch.y);
+                                q.z = fmaf(fmaxf(q.z, 0.f) + ca.z * fminf(q.z, 0.f), cs.z, ch.z);
+                                q.w = fmaf(fmaxf(q.w, 0.f) + ca.w * fminf(q.w, 0.f), cs.w, ch.w);
+                            }
                         }
                     }
                 }
             }
-            float4 hi[RPP];
+            uint4 hi[RPP];
 #pragma unroll
-            for (int i = 0; i < RPP; ++i) hi[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
+            for (int i = 0; i < RPP; ++i)
+                hi[i] = make_uint4(pack_h2(v[2 * i].x, v[2 * i].y), pack_h2(v[2 * i].z, v[2 * i].w),
+                                   pack_h2(v[2 * i + 1].x, v[2 * i + 1].y), pack_h2(v[2 * i + 1].z, v[2 * i + 1].w));
             for (int pass = 0; pass < a.npass; ++pass) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* A = As + stage * A_STAGE_BYTES + st_off;
-                if (pass == 1) {                 // residual of the TF32 rounding, itself rounded to TF32
+                if (pass == 1) {                 // residual of the fp16 rounding, itself rounded to fp16
 #pragma unroll
                     for (int i = 0; i < RPP; ++i)
-                        *reinterpret_cast<float4*>(A + i * 4096) = make_float4(to_tf32(v[i].x - hi[i].x), to_tf32(v[i].y - hi[i].y),
-                                                                               to_tf32(v[i].z - hi[i].z), to_tf32(v[i].w - hi[i].w));
+                        *reinterpret_cast<uint4*>(A + i * 4096) =
+                            make_uint4(pack_lo_h2(v[2 * i].x, v[2 * i].y, hi[i].x), pack_lo_h2(v[2 * i].z, v[2 * i].w, hi[i].y),
+                                       pack_lo_h2(v[2 * i + 1].x, v[2 * i + 1].y, hi[i].z), pack_lo_h2(v[2 * i + 1].z, v[2 * i + 1].w, hi[i].w));
                 } else {
 #pragma unroll
-                    for (int i = 0; i < RPP; ++i) *reinterpret_cast<float4*>(A + i * 4096) = hi[i];
+                    for (int i = 0; i < RPP; ++i) *reinterpret_cast<uint4*>(A + i * 4096) = hi[i];
                 }
                 fence_proxy_async();
                 mbar_arrive(&full[stage]);
@@ -353,21 +375,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             }
         };
 
-        float4 v0[RPP], v1[RPP], v2[RPP];
-        uint32_t m0 = 0, m1 = 0, m2 = 0;
+        float4 v0[2 * RPP], v1[2 * RPP];
+        uint32_t m0 = 0, m1 = 0;
         decode_tile(l_tile);
         long long issued = 0;
         if (issued < total_units) { issue_loads(v0, m0); ++issued; }
-        if (issued < total_units) { issue_loads(v1, m1); ++issued; }
-        for (long long g = 0; g < total_units; g += 3) {
-            if (issued < total_units) { issue_loads(v2, m2); ++issued; }
+        for (long long g = 0; g < total_units; g += 2) {
+            if (issued < total_units) { issue_loads(v1, m1); ++issued; }
             consume(v0, m0);
             if (g + 1 >= total_units) break;
             if (issued < total_units) { issue_loads(v0, m0); ++issued; }
             consume(v1, m1);
-            if (g + 2 >= total_units) break;
-            if (issued < total_units) { issue_loads(v1, m1); ++issued; }
-            consume(v2, m2);
         }
     } else if (warp == NPROD / 32) {
         // =========================================================================== MMA issuer
@@ -387,10 +405,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                     const uint32_t a_addr = smem_u32(As + stage * A_STAGE_BYTES);
                     const uint32_t b_addr = smem_u32(Bs + stage * sp.b_stage_bytes);
 #pragma unroll
-                    for (int k = 0; k < KC / 8; ++k) {
+                    for (int k = 0; k < KC / 16; ++k) {
                         const uint64_t ad = make_desc(a_addr + k * 32);
                         const uint64_t bd = make_desc(b_addr + k * 32);
-                        umma_tf32(d_tmem, ad, bd, idesc, (ch | k) ? 1u : 0u);
+                        umma_f16(d_tmem, ad, bd, idesc, (ch | k) ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);                         // stage reusable once these MMAs retire
                     if (ch == nchunks - 1) umma_commit(&acc_full[acc]);   // accumulator complete
@@ -410,7 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 for (int pass = 0; pass < a.npass; ++pass) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (lane == 0) {
-                        const float* img = (pass == 2 ? a.Wlo : a.Whi) + (size_t)unit * a.N * KC;
+                        const float* img = (pass == 2 ? a.Wlo : a.Whi) + (size_t)unit * a.N * 32;     // N rows x 128 B
                         mbar_arrive_expect_tx(&full[stage], bytes);
                         bulk_copy_g2s(Bs + stage * sp.b_stage_bytes, img, bytes, &full[stage]);
                     }
@@ -537,7 +555,7 @@ bool umma_conv_supported(const UmmaConvArgs& a) {
         if (a.src[0].xf.affine != 0 || a.src[0].xf.prelu != 0) return false;     // wide mode reads raw input only
     } else {
         for (int i = 0; i < a.nsrc; ++i)
-            if (a.src[i].C % KC != 0) return false;
+            if (a.src[i].C % KC != 0) return false;      // whole 64-channel fp16 slabs
     }
     if (a.out_ld % 4 != 0 || a.out_coff % 4 != 0) return false;
     return true;

@@ -15,6 +15,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "../../include/eabnet_b200.h"
 #include "common.cuh"
 
@@ -243,17 +245,8 @@ struct Builder {
     }
 };
 
-inline float tf32_rna(float x) {           // cvt.rna.tf32.f32 on the host (ties away from zero, 10-bit mantissa)
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7F800000u) == 0x7F800000u) return x;
-    u = (u + 0x1000u) & 0xFFFFE000u;
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
-}
-// element (n, k) of a [N][32] K-major tile with the 128-byte swizzle the tensor core expects
-inline size_t sw128_index(int n, int k) { return (size_t)n * 32 + (size_t)((((k >> 2) ^ (n & 7)) << 2) | (k & 3)); }
+// element (n, k) of a [N][64] fp16 K-major tile with the 128-byte swizzle the tensor core expects (index in halves)
+inline size_t sw128_index_h(int n, int k) { return (size_t)n * 64 + (size_t)((((k >> 3) ^ (n & 7)) << 3) | (k & 7)); }
 
 int conv_out_f(int Fin, int kf) { return Fin < kf ? -1 : (Fin - kf) / 2 + 1; }
 int deconv_out_f(int Fin, int kf) { return 2 * (Fin - 1) + kf; }
@@ -442,13 +435,13 @@ struct Packer {
         if (co != 16 && co != 32 && co != 64 && co != 128) return;
         if (L.gated && co > 128) return;
         L.wide = L.perm_ri;
-        if (!L.wide && (L.cin % 32 != 0)) return;
+        if (!L.wide && (L.cin % 64 != 0)) return;
         if (L.wide && L.deconv) return;
         const int cout_t = L.gated ? 2 * co : co;
         L.u_N = cout_t;
         L.u_gate_off = L.gated ? co : 0;
         L.u_kwidth = L.wide ? L.kf * L.cin : 0;
-        L.u_nslab = L.wide ? (L.u_kwidth + 31) / 32 : L.cin / 32;
+        L.u_nslab = L.wide ? (L.u_kwidth + 63) / 64 : L.cin / 64;
         auto cin_mem = [&](int cin_ref) {
             if (!L.perm_ri) return cin_ref;
             const int ri = cin_ref / L.M, mic = cin_ref - ri * L.M;
@@ -473,11 +466,11 @@ struct Packer {
             }
             L.u_ntaps[v] = nt;
             if (nt == 0) return;
-            const size_t img = (size_t)nt * L.u_nslab * cout_t * 32;
+            const size_t img = (size_t)nt * L.u_nslab * cout_t * 32;      // floats: N rows x 128 B per (tap, slab)
             L.off_whi[v] = alloc(img);
             L.off_wlo[v] = alloc(img);
             // dense [tap][kk][n] first (kk = K index inside the tap in MEMORY order), then swizzle per slab
-            const int kper = L.u_nslab * 32;
+            const int kper = L.u_nslab * 64;
             std::vector<float> dense((size_t)nt * kper * cout_t, 0.f);
             for (int tp = 0; tp < nt; ++tp)
                 for (int ci = 0; ci < L.cin; ++ci)
@@ -493,15 +486,17 @@ struct Packer {
                             dense[((size_t)tp * kper + ci) * cout_t + n] = W[src];
                         }
                     }
+            __half* img_hi = reinterpret_cast<__half*>(blob.data() + L.off_whi[v]);
+            __half* img_lo = reinterpret_cast<__half*>(blob.data() + L.off_wlo[v]);
             for (int tp = 0; tp < nt; ++tp)
                 for (int sl = 0; sl < L.u_nslab; ++sl) {
-                    const size_t base = ((size_t)tp * L.u_nslab + sl) * cout_t * 32;
+                    const size_t base = ((size_t)tp * L.u_nslab + sl) * cout_t * 64;       // in halves
                     for (int n = 0; n < cout_t; ++n)
-                        for (int k = 0; k < 32; ++k) {
-                            const float w = dense[((size_t)tp * kper + sl * 32 + k) * cout_t + n];
-                            const float hi = tf32_rna(w);
-                            blob[L.off_whi[v] + base + sw128_index(n, k)] = hi;
-                            blob[L.off_wlo[v] + base + sw128_index(n, k)] = tf32_rna(w - hi);
+                        for (int k = 0; k < 64; ++k) {
+                            const float w = dense[((size_t)tp * kper + sl * 64 + k) * cout_t + n];
+                            const __half hi = __float2half_rn(w);
+                            img_hi[base + sw128_index_h(n, k)] = hi;
+                            img_lo[base + sw128_index_h(n, k)] = __float2half_rn(w - __half2float(hi));
                         }
                 }
         }
