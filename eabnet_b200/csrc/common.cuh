@@ -197,7 +197,8 @@ struct LstmArgs {
 int launch_lstm(const LstmArgs& a, cudaStream_t st);
 
 struct BeamArgs {
-    const float* w;              // [B][T][F][NW]  (NW = 2M mimo, 2 miso), channel = m*2 + ri
+    const float* w;              // [B][T][F][w_ld]: first 2M (mimo) / 2 (miso) channels used, channel = m*2 + ri
+    int w_ld;
     const float* inpt;           // [B][T][F][M][2]
     int B, T, F, M, miso;
     float* out;                  // mimo [B][2][T][F];  miso [B][2][T]

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) beam_mimo_kernel(const BeamArgs a) {
     const size_t n = (size_t)a.B * a.T * a.F;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float2* w = reinterpret_cast<const float2*>(a.w) + i * a.M;
+    const float2* w = reinterpret_cast<const float2*>(a.w + i * a.w_ld);
     const float2* x = reinterpret_cast<const float2*>(a.inpt) + i * a.M;
     float yr = 0.f, yi = 0.f;
     for (int m = 0; m < a.M; ++m) {
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) beam_miso_kernel(const BeamArgs a) {
     const size_t row = (size_t)warp * a.F;
     float yr = 0.f, yi = 0.f;
     for (int f = lane; f < a.F; f += 32) {
-        const float2 wv = __ldg(reinterpret_cast<const float2*>(a.w) + row + f);
+        const float2 wv = __ldg(reinterpret_cast<const float2*>(a.w + (row + f) * a.w_ld));
         const float2 xv = __ldg(reinterpret_cast<const float2*>(a.inpt) + (row + f) * a.M);
         yr += wv.x * xv.x - wv.y * xv.y;
         yi += wv.x * xv.y + wv.y * xv.x;

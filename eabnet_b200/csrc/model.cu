@@ -118,8 +118,20 @@ struct UnetModule {
     std::vector<ConvLayer> enco, deco;
 };
 
+// weight images of one pointwise / dilated GEMM on the tcgen05 path (columns split in chunks of <= 128)
+struct UmmaW {
+    bool ok = false;
+    int ntaps = 1, nslab = 0, gate_off = 0;
+    int nsplit = 1, ncol = 0;            // columns (N) per split
+    int cout = 0;                        // stored channels per split
+    int ld = 0;                          // row stride of the output tensor (channels)
+    size_t off_hi[4] = {0, 0, 0, 0}, off_lo[4] = {0, 0, 0, 0}, off_bias[4] = {0, 0, 0, 0};
+    bool has_bias = false;
+};
+
 struct TcmLayer {
     int dilation = 1;
+    UmmaW u_in, u_dil, u_out;
     int w_in = -1, w_left = -1, w_right = -1, w_out = -1;
     NormAct na_left, na_right, na_out;
     size_t off_in = 0, off_dil = 0, off_out = 0;
@@ -157,6 +169,7 @@ struct eab_model {
     size_t off_rnn[2][3] = {{0, 0, 0}, {0, 0, 0}}, off_dnn_w[2] = {0, 0}, off_dnn_b[2] = {0, 0}, off_ln_g = 0,
            off_ln_b = 0, off_cnn_w = 0, off_cnn_b = 0;
     int dnn_N[2] = {0, 0}, cnn_N = 0;
+    UmmaW u_dnn[2], u_cnn;
 
     // device state
     float* blob = nullptr;
@@ -531,9 +544,61 @@ struct Packer {
             const int cc = nr / Fb, f = nr - cc * Fb;
             for (int ci = 0; ci < cd; ++ci) blob[t.off_out + (size_t)ci * df + (f * 64 + cc)] = P(t.w_out)[(size_t)nr * cd + ci];
         }
+        t.u_in = umma_images(t.off_in, 1, df, Nin, cd, false, 0, nullptr);
+        t.u_dil = umma_images(t.off_dil, kd, 2 * cd, Nd, 2 * cd, true, goff, nullptr);
+        t.u_out = umma_images(t.off_out, 1, cd, df, df, false, 0, nullptr);
         normact(t.na_left);
         normact(t.na_right);
         normact(t.na_out);
+    }
+
+    // Build fp16 hi/lo images from a dense [ntaps][K][ldn] fp32 matrix that already sits in the blob at `off`
+    // (the layout of the CUDA-core path).  Columns [0, ncols) are used; gated => value|gate halves of `cout` each
+    // located at columns [0,cout) and [gate_col, gate_col+cout) of the dense matrix.
+    UmmaW umma_images(size_t off, int ntaps, int K, int ldn, int ncols, bool gated, int gate_col, const float* bias) {
+        UmmaW u;
+        if (K % 64 != 0) return u;
+        const int cout = gated ? ncols / 2 : ncols;
+        int padded = cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : (cout + 127) / 128 * 128;
+        if (gated && padded != cout) return u;
+        if (gated && cout > 128) return u;
+        u.ntaps = ntaps;
+        u.nslab = K / 64;
+        u.gate_off = gated ? cout : 0;
+        u.nsplit = (!gated && padded > 128) ? padded / 128 : 1;
+        if (u.nsplit > 4) return u;
+        u.cout = padded / u.nsplit;
+        u.ncol = gated ? 2 * cout : u.cout;
+        u.ld = padded;
+        u.has_bias = bias != nullptr;
+        for (int sp = 0; sp < u.nsplit; ++sp) {
+            const size_t img = (size_t)ntaps * u.nslab * u.ncol * 32;
+            u.off_hi[sp] = alloc(img);
+            u.off_lo[sp] = alloc(img);
+            u.off_bias[sp] = alloc(u.ncol);
+            __half* hi = reinterpret_cast<__half*>(blob.data() + u.off_hi[sp]);
+            __half* lo = reinterpret_cast<__half*>(blob.data() + u.off_lo[sp]);
+            for (int n = 0; n < u.ncol; ++n) {
+                // column of the dense matrix feeding image row n
+                int col;
+                if (gated) col = n < cout ? n : gate_col + (n - cout);
+                else col = sp * u.cout + n;
+                const bool real = gated ? true : col < ncols;
+                blob[u.off_bias[sp] + n] = (bias && real) ? bias[col] : 0.f;
+                for (int tp = 0; tp < ntaps; ++tp)
+                    for (int sl = 0; sl < u.nslab; ++sl) {
+                        const size_t base = ((size_t)tp * u.nslab + sl) * u.ncol * 64;
+                        for (int k = 0; k < 64; ++k) {
+                            const float w = real ? blob[off + ((size_t)tp * K + sl * 64 + k) * ldn + col] : 0.f;
+                            const __half h = __float2half_rn(w);
+                            hi[base + sw128_index_h(n, k)] = h;
+                            lo[base + sw128_index_h(n, k)] = __float2half_rn(w - __half2float(h));
+                        }
+                    }
+            }
+        }
+        u.ok = true;
+        return u;
     }
 
     size_t linear(int w, int b, int nout, int nin, int* N, size_t* off_b) {
@@ -566,6 +631,12 @@ struct Packer {
             }
             m->off_dnn_w[0] = linear(m->dnn_w[0], m->dnn_b[0], H, H, &m->dnn_N[0], &m->off_dnn_b[0]);
             m->off_dnn_w[1] = linear(m->dnn_w[1], m->dnn_b[1], 2 * c.M, H, &m->dnn_N[1], &m->off_dnn_b[1]);
+            {
+                std::vector<float> b0(blob.begin() + m->off_dnn_b[0], blob.begin() + m->off_dnn_b[0] + m->dnn_N[0]);
+                std::vector<float> b1(blob.begin() + m->off_dnn_b[1], blob.begin() + m->off_dnn_b[1] + m->dnn_N[1]);
+                m->u_dnn[0] = umma_images(m->off_dnn_w[0], 1, H, m->dnn_N[0], H, false, 0, b0.data());
+                m->u_dnn[1] = umma_images(m->off_dnn_w[1], 1, H, m->dnn_N[1], 2 * c.M, false, 0, b1.data());
+            }
             m->off_ln_g = alloc(c.embed_dim);
             m->off_ln_b = alloc(c.embed_dim);
             for (int i = 0; i < c.embed_dim; ++i) {
@@ -575,6 +646,10 @@ struct Packer {
         } else {
             const int n = c.topo_type == 0 ? 2 * c.M : 2;
             m->off_cnn_w = linear(m->cnn_w, m->cnn_b, n, c.embed_dim, &m->cnn_N, &m->off_cnn_b);
+            {
+                std::vector<float> b0(blob.begin() + m->off_cnn_b, blob.begin() + m->off_cnn_b + m->cnn_N);
+                m->u_cnn = umma_images(m->off_cnn_w, 1, c.embed_dim, m->cnn_N, n, false, 0, b0.data());
+            }
         }
     }
 };
@@ -754,12 +829,40 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
 // 1x1 "conv" over positions with optional bias / relu / residual / statistics (used by TCMs and the head)
 int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const float* bias, int Cout, int N, int gate_off,
                   int ntaps, const int* dt, int relu, const float* resid, int nstats, double** stats,
-                  const float** stat_alpha, Act* out) {
+                  const float** stat_alpha, Act* out, const UmmaW* uw = nullptr) {
+    const bool use_umma = uw && uw->ok && cx.m->opt_umma && (resid == nullptr || uw->ld == Cout);
     out->F = srcs[0].F;
-    out->C = Cout;
+    out->C = use_umma ? uw->ld : Cout;          // the tcgen05 path may pad the channel count (e.g. 18 -> 32, zeros)
     out->xf = xform_identity();
-    out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * Cout);
+    out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * out->C);
     if (cx.dry) return 0;
+    if (use_umma) {
+        for (int sp = 0; sp < uw->nsplit; ++sp) {
+            UmmaConvArgs u;
+            memset(&u, 0, sizeof(u));
+            u.nsrc = nsrc;
+            int cin = 0;
+            for (int i = 0; i < nsrc; ++i) { u.src[i].x = srcs[i].data; u.src[i].C = srcs[i].C; u.src[i].xf = srcs[i].xf; cin += srcs[i].C; }
+            u.B = cx.B; u.T = cx.T; u.Fin = srcs[0].F; u.Fout = srcs[0].F; u.E = srcs[0].F;
+            u.in_stride = 1; u.out_stride = 1; u.out_off = 0;
+            u.ntaps = uw->ntaps;
+            for (int i = 0; i < u.ntaps; ++i) { u.dt[i] = dt ? dt[i] : 0; u.df[i] = 0; }
+            u.wide = 0; u.kwidth = 0; u.nslab = uw->nslab; u.ncoef = cin;
+            u.npass = 3;                        // these layers are < 5 % of the FLOPs: keep them fp32-grade
+            u.Whi = cx.W(uw->off_hi[sp]); u.Wlo = cx.W(uw->off_lo[sp]);
+            u.bias = uw->has_bias ? cx.W(uw->off_bias[sp]) : nullptr;
+            u.Cout = uw->cout; u.N = uw->ncol; u.gate_off = uw->gate_off; u.relu = relu;
+            u.algo_frac = (nsrc == 2 && gate_off > 0) ? 0.5f : 1.f;
+            u.out = out->data; u.out_ld = uw->ld; u.out_coff = sp * uw->cout;
+            u.resid = resid;
+            u.nstats = nstats;
+            for (int i = 0; i < nstats; ++i) { u.stats[i] = stats[i]; u.stat_alpha[i] = stat_alpha[i]; }
+            u.tiles_per_b = (cx.T * u.E + 127) / 128;
+            if (!umma_conv_supported(u)) return fail("internal: pointwise layer rejected by the tcgen05 path");
+            EAB_TRY(launch_conv_umma(u, cx.st));
+        }
+        return 0;
+    }
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.nsrc = nsrc;
@@ -785,7 +888,7 @@ int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
     const float* al_lr[2] = {cx.W(t.na_left.off_alpha), cx.W(t.na_right.off_alpha)};
     Act y;
     EAB_TRY(run_pointwise(cx, &x, 1, cx.W(t.off_in), nullptr, c.cd1, pad_n(c.cd1), 0, 1, nullptr, 0, nullptr,
-                          in_stats ? 2 : 0, st_lr, al_lr, &y));
+                          in_stats ? 2 : 0, st_lr, al_lr, &y, &t.u_in));
     // both dilated branches as one gated conv: value = left branch, gate = right branch (sigmoid)
     Act br[2] = {y, y};
     br[0].xf = xf_after(cx, t.na_left, st_lr[0], cx.T, 1);
@@ -794,11 +897,11 @@ int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
     const float* al_o[1] = {cx.W(t.na_out.off_alpha)};
     Act z;
     EAB_TRY(run_pointwise(cx, br, 2, cx.W(t.off_dil), nullptr, c.cd1, 2 * ceil64(c.cd1), ceil64(c.cd1), c.kd1, t.dt, 0,
-                          nullptr, in_stats ? 1 : 0, st_o, al_o, &z));
+                          nullptr, in_stats ? 1 : 0, st_o, al_o, &z, &t.u_dil));
     // expand 1x1 + residual
     z.xf = xf_after(cx, t.na_out, st_o[0], cx.T, 1);
     return run_pointwise(cx, &z, 1, cx.W(t.off_out), nullptr, c.d_feat, c.d_feat, 0, 1, nullptr, 0, x.data, 0, nullptr,
-                         nullptr, out);
+                         nullptr, out, &t.u_out);
 }
 
 void tap(Ctx& cx, const char* name, const Act& a) {
@@ -909,18 +1012,18 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
         }
         Act u;
         EAB_TRY(run_pointwise(cx, &h[1], 1, cx.W(m->off_dnn_w[0]), cx.W(m->off_dnn_b[0]), 64, m->dnn_N[0], 0, 1, nullptr, 1,
-                              nullptr, 0, nullptr, nullptr, &u));
+                              nullptr, 0, nullptr, nullptr, &u, &m->u_dnn[0]));
         EAB_TRY(run_pointwise(cx, &u, 1, cx.W(m->off_dnn_w[1]), cx.W(m->off_dnn_b[1]), 2 * c.M, m->dnn_N[1], 0, 1, nullptr, 0,
-                              nullptr, 0, nullptr, nullptr, &w));
+                              nullptr, 0, nullptr, nullptr, &w, &m->u_dnn[1]));
     } else {
         const int n = c.topo_type == 0 ? 2 * c.M : 2;
         EAB_TRY(run_pointwise(cx, &emb, 1, cx.W(m->off_cnn_w), cx.W(m->off_cnn_b), n, m->cnn_N, 0, 1, nullptr, 0, nullptr, 0,
-                              nullptr, nullptr, &w));
+                              nullptr, nullptr, &w, &m->u_cnn));
     }
     tap(cx, "w", w);
     if (!cx.dry) {
         BeamArgs a;
-        a.w = w.data; a.inpt = inpt; a.B = cx.B; a.T = cx.T; a.F = c.n_freq; a.M = c.M; a.miso = c.topo_type == 1;
+        a.w = w.data; a.w_ld = w.C; a.inpt = inpt; a.B = cx.B; a.T = cx.T; a.F = c.n_freq; a.M = c.M; a.miso = c.topo_type == 1;
         a.out = out_dev;
         EAB_TRY(launch_beam(a, cx.st));
     }
@@ -965,6 +1068,9 @@ int eab_create(const eab_config* cfg, eab_model** out) {
     m->cfg = *cfg;
     if (m->cfg.n_freq <= 0) m->cfg.n_freq = 161;
     if (build(m.get())) return 1;
+    // the 1x1-conv heads feed decoder round-off straight into the beam weights (no recurrent smoothing, and "miso"
+    // sums 161 bins): keep their decoder fp32-grade as well
+    if (!(m->cfg.topo_type == 0 && m->cfg.bf_type == 0)) m->opt_dec_passes = 3;
     *out = m.release();
     return 0;
 }

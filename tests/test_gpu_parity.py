@@ -13,7 +13,8 @@ from oracle import eabnet_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3          # north_star bar on the [B,2,T,F] output
-TIGHT = 1e-4        # what the fp32 path is expected to meet (relative to max(1, |out|max))
+TIGHT = 4e-4        # default precision policy (3-pass fp16 encoder/TCM/head, single-pass fp16 decoder): typ. 1e-4
+EXACT = 2e-5        # every tensor-core layer in 3-pass mode (fp32-grade), and the CUDA-core-only path
 
 
 def _net(cfg, variant="B", seed=0):
@@ -100,10 +101,25 @@ def test_forward_matches_oracle(over, B, L):
     for name, r in taps.items():
         got = net.debug_tap(name, tuple(r.shape)).cpu()
         cond = float((r.double() - taps64[name]).abs().max())
-        assert (got.double() - taps64[name]).abs().max() <= max(5e-4 * max(1.0, float(r.abs().max())), 8 * cond), name
+        assert (got.double() - taps64[name]).abs().max() <= max(5e-3 * max(1.0, float(r.abs().max())), 8 * cond), name
     err = float((out.double() - ref64).abs().max())
     cond = float((ref.double() - ref64).abs().max())
     assert err <= max(TIGHT * scale, 8 * cond) and err <= TOL * scale, (err, cond)
+
+
+@pytest.mark.parametrize("opts", [{"enc_passes": 3, "dec_passes": 3}, {"umma": 0}])
+def test_forward_fp32_grade_modes(opts):
+    """all-3-pass tensor-core mode and the CUDA-core-only kernels are both fp32-grade against the oracle"""
+    cfg = O.make_cfg()
+    net, sd = _net(cfg, seed=8)
+    for k, v in opts.items():
+        net.set_option(k, v)
+    wave, _ = O.make_wave(2, 9, 6400, seed=23)
+    spec = O.stft_compress(wave)
+    ref = O.forward(sd, spec, cfg)
+    with torch.no_grad():
+        out = net(spec.cuda()).cpu()
+    assert (out - ref).abs().max() <= EXACT * max(1.0, float(ref.abs().max()))
 
 
 def test_enhance_wave_to_wave_and_si_sdr():
@@ -117,7 +133,7 @@ def test_enhance_wave_to_wave_and_si_sdr():
         got = net.enhance(wave.cuda()).cpu()
     host = net.enhance_host(wave.pin_memory())
     assert got.shape == ref.shape == (1, 64000)
-    assert (got - ref).abs().max() <= 1e-4 and torch.equal(host, got)
+    assert (got - ref).abs().max() <= 1e-4 and (host - got).abs().max() <= 1e-6
     s = clean[0, :64000].numpy()
     assert abs(O.si_sdr(s, got[0].numpy()) - O.si_sdr(s, ref[0].numpy())) <= 0.05
 
