@@ -200,10 +200,8 @@ def main():
         clocks = sampler.stop()
         assert torch.isfinite(y).all()
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    from eabnet_b200.shard import max_over_ranks
+    ms, ms_e2e = max_over_ranks([ms, ms_e2e], dev)
     audio_s = world * B * args.seconds
     value = audio_s / (ms * 1e-3)
     e2e = audio_s / (ms_e2e * 1e-3)
