@@ -190,11 +190,14 @@ struct LstmArgs {
     const float* ln_g; const float* ln_b;
     const float* Wx;             // packed [E][64][4]
     const float* Wh;             // packed [64][64][4]
-    const float* bias;           // packed [64][4]  (b_ih + b_hh)
+    const float* bias;           // packed [64][4]  (b_ih + b_hh)  (CUDA-core kernel) / [256] in image row order (tcgen05)
+    const float* Wimg;           // tcgen05 kernel: fp16 images [hi|lo][x|h][256 rows][64 k], 128B-swizzled (or null)
     int B, T, F, E;
     float* out;                  // [B][T][F][64]
 };
 int launch_lstm(const LstmArgs& a, cudaStream_t st);
+bool lstm_umma_supported(const LstmArgs& a);
+int launch_lstm_umma(const LstmArgs& a, cudaStream_t st);
 
 struct BeamArgs {
     const float* w;              // [B][T][F][w_ld]: first 2M (mimo) / 2 (miso) channels used, channel = m*2 + ri

@@ -1,0 +1,268 @@
+// nn.LSTM(64 -> 64) layer of LSTM_BF (EaBNet.py:591-592, 610-611) on the tensor cores (sm_100a), fp32-grade.
+//
+// One CTA owns 128 (b,f) sequences for all T steps.  Per step the gate pre-activations
+//     G[128 x 256] = [x_t | h_{t-1}] (K = 128)  x  [W_ih ; W_hh]^T
+// are three tcgen05.mma.kind::f16 passes (hi*hi + lo*hi + hi*lo of an fp16 split, i.e. ~22 mantissa bits) into a
+// 256-column TMEM accumulator.  The weight images (128 KB) stay resident in shared memory for the whole sequence,
+// the cell state lives in registers, and h_t goes straight back into the swizzled A operand of step t+1.
+//
+//   warps 0-7   cell warps  : two threads per sequence (32 hidden units each): tcgen05.ld gates, bias, sigmoid/tanh,
+//                             c/h update, h_t -> HBM (fp32) and -> A operand (fp16 hi/lo), arrive
+//   warps 8-11  x producers : one thread per sequence: prefetch x_{t+1} (256 B) from HBM a step ahead, apply the
+//                             decoder's norm + PReLU and the head's LayerNorm (thread-local over the 64 channels),
+//                             split to fp16 hi/lo, store to the A operand once MMA(t) has released it, arrive
+//   warp 12     MMA issuer  : waits for both operand halves, issues 24 MMAs (M128 x N256 x K16), commits
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace eab {
+
+namespace {
+
+using namespace umma;
+
+constexpr int H = 64;
+constexpr int ROWS = 128;
+constexpr int NCELL = 256, NXP = 128, NTHREADS = NCELL + NXP + 32;
+constexpr int SLAB_BYTES = ROWS * 128;                 // one 64-wide fp16 K slab of the A operand
+constexpr int A_BYTES = 4 * SLAB_BYTES;                // [hi|lo][x|h]
+constexpr int B_SLAB_BYTES = 256 * 128;                // one K slab of the weight image (256 gate rows)
+constexpr int B_BYTES = 4 * B_SLAB_BYTES;              // [hi|lo][x|h]
+constexpr int MISC_FLOATS = 256 + 2 * 3 * 64 + 2 * 64; // bias, transform coefficients (2 batch items), LayerNorm
+constexpr int SMEM_BYTES = A_BYTES + B_BYTES + MISC_FLOATS * 4 + 64 + 1024;
+
+__device__ __forceinline__ uint8_t* a_slab(uint8_t* A, int hl, int slab) { return A + (hl * 2 + slab) * SLAB_BYTES; }
+
+__global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* As = smem;
+    uint8_t* Bs = smem + A_BYTES;
+    float* sbias = reinterpret_cast<float*>(smem + A_BYTES + B_BYTES);
+    float* coef = sbias + 256;                  // [2][3][64]
+    float* lng = coef + 2 * 3 * 64;
+    float* lnb = lng + 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lnb + 64);
+    uint64_t* a_ready = bars;                   // operand of the next step complete (cells: h, producers: x)
+    uint64_t* acc_full = bars + 1;              // gates of the current step complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int NQ = a.B * a.F;
+    const int q0 = blockIdx.x * ROWS;
+    const int b0 = q0 / a.F;
+
+    if (tid == 0) {
+        mbar_init(a_ready, NCELL + NXP);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 12) tmem_alloc(tmem_slot, 256);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.Wimg);
+        uint4* dst = reinterpret_cast<uint4*>(Bs);
+        for (int i = tid; i < B_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
+        uint4* az = reinterpret_cast<uint4*>(As);
+        for (int i = tid; i < A_BYTES / 16; i += NTHREADS) az[i] = make_uint4(0, 0, 0, 0);      // h_{-1} = 0
+        for (int i = tid; i < 256; i += NTHREADS) sbias[i] = __ldg(a.bias + i);
+        for (int i = tid; i < 2 * 64; i += NTHREADS) {
+            const int bb = i >> 6, c = i & 63;
+            float cs = 1.f, ch = 0.f, ca = 1.f;
+            if (b0 + bb < a.B) xform_coeffs(a.src.xf, b0 + bb, 64, c, cs, ch, ca);
+            coef[(bb * 3 + 0) * 64 + c] = cs;
+            coef[(bb * 3 + 1) * 64 + c] = ch;
+            coef[(bb * 3 + 2) * 64 + c] = a.src.xf.prelu ? ca : 1.f;
+        }
+        for (int i = tid; i < 64; i += NTHREADS) {
+            lng[i] = a.layer_norm ? __ldg(a.ln_g + i) : 1.f;
+            lnb[i] = a.layer_norm ? __ldg(a.ln_b + i) : 0.f;
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ======================================================================= cell warps
+        const int quad = warp & 3;
+        const int half = warp >> 2;
+        const int row = quad * 32 + lane;
+        const int q = q0 + row;
+        const bool valid = q < NQ;
+        const int bq = valid ? q / a.F : 0;
+        const int fq = valid ? q - bq * a.F : 0;
+        float* outp = a.out + (((size_t)bq * a.T) * a.F + fq) * H + half * 32;
+        const size_t ostep = (size_t)a.F * H;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
+        uint8_t* hrow_hi = a_slab(As, 0, 1) + row * 128;
+        uint8_t* hrow_lo = a_slab(As, 1, 1) + row * 128;
+        float c[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) c[i] = 0.f;
+        mbar_arrive(a_ready);                   // h_{-1} = 0 is in place
+        for (int t = 0; t < a.T; ++t) {
+            mbar_wait(acc_full, (uint32_t)(t & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {       // 8 hidden units at a time
+                uint32_t gi[8], gf[8], gg[8], go[8];
+                tmem_ld8_nowait(taddr + 0 * 32 + u * 8, gi);
+                tmem_ld8_nowait(taddr + 1 * 32 + u * 8, gf);
+                tmem_ld8_nowait(taddr + 2 * 32 + u * 8, gg);
+                tmem_ld8_nowait(taddr + 3 * 32 + u * 8, go);
+                tmem_wait_ld();
+                float hv[8];
+                const float* bi = sbias + half * 128 + u * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float xi = __uint_as_float(gi[e]) + bi[e];
+                    const float xf = __uint_as_float(gf[e]) + bi[32 + e];
+                    const float xg = __uint_as_float(gg[e]) + bi[64 + e];
+                    const float xo = __uint_as_float(go[e]) + bi[96 + e];
+                    const float cn = sigmoid_f(xf) * c[u * 8 + e] + sigmoid_f(xi) * tanh_f(xg);
+                    c[u * 8 + e] = cn;
+                    hv[e] = sigmoid_f(xo) * tanh_f(cn);
+                }
+                if (valid) {
+                    float4* o4 = reinterpret_cast<float4*>(outp + (size_t)t * ostep + u * 8);
+                    o4[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                    o4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                }
+                uint4 hi, lo;
+                hi.x = pack_h2(hv[0], hv[1]); hi.y = pack_h2(hv[2], hv[3]); hi.z = pack_h2(hv[4], hv[5]); hi.w = pack_h2(hv[6], hv[7]);
+                lo.x = pack_lo_h2(hv[0], hv[1], hi.x); lo.y = pack_lo_h2(hv[2], hv[3], hi.y);
+                lo.z = pack_lo_h2(hv[4], hv[5], hi.z); lo.w = pack_lo_h2(hv[6], hv[7], hi.w);
+                const int chunk = ((half * 4 + u) ^ (row & 7)) << 4;
+                *reinterpret_cast<uint4*>(hrow_hi + chunk) = hi;
+                *reinterpret_cast<uint4*>(hrow_lo + chunk) = lo;
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            if (t + 1 < a.T) mbar_arrive(a_ready);
+        }
+    } else if (warp < 12) {
+        // ======================================================================= x producers (one thread per row)
+        const int row = tid - NCELL;
+        const int q = q0 + row;
+        const bool valid = q < NQ;
+        const int bq = valid ? q / a.F : 0;
+        const int fq = valid ? q - bq * a.F : 0;
+        const float* xp = a.src.x + (((size_t)bq * a.T) * a.F + fq) * H;
+        const size_t xstep = (size_t)a.F * H;
+        const float* cf = coef + (valid ? bq - b0 : 0) * 3 * 64;
+        const int mode = (a.src.xf.affine == 0 && a.src.xf.prelu == 0) ? 0 : (a.src.xf.prelu == 1 ? 2 : 1);
+        uint8_t* xrow_hi = a_slab(As, 0, 0) + row * 128;
+        uint8_t* xrow_lo = a_slab(As, 1, 0) + row * 128;
+        float4 xr[16];
+        auto load = [&](int t) {
+            if (valid) {
+                const float4* p = reinterpret_cast<const float4*>(xp + (size_t)t * xstep);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) xr[i] = __ldg(p + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto publish = [&]() {
+            float* x = reinterpret_cast<float*>(xr);
+            if (valid && mode != 0) {
+#pragma unroll
+                for (int k = 0; k < 64; ++k) {
+                    const float s = cf[k], h = cf[64 + k], al = cf[128 + k];
+                    float v = x[k];
+                    if (mode == 1) { v = fmaf(v, s, h); v = fmaxf(v, 0.f) + al * fminf(v, 0.f); }
+                    else { v = fmaxf(v, 0.f) + al * fminf(v, 0.f); v = fmaf(v, s, h); }
+                    x[k] = v;
+                }
+            }
+            if (valid && a.layer_norm) {
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 64; ++k) sum += x[k];
+                const float mean = sum * (1.f / 64.f);
+                float sq = 0.f;
+#pragma unroll
+                for (int k = 0; k < 64; ++k) { const float d = x[k] - mean; sq += d * d; }
+                const float rstd = rsqrtf(sq * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+                for (int k = 0; k < 64; ++k) x[k] = (x[k] - mean) * rstd * lng[k] + lnb[k];
+            }
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const float* v = x + ch * 8;
+                uint4 hi, lo;
+                hi.x = pack_h2(v[0], v[1]); hi.y = pack_h2(v[2], v[3]); hi.z = pack_h2(v[4], v[5]); hi.w = pack_h2(v[6], v[7]);
+                lo.x = pack_lo_h2(v[0], v[1], hi.x); lo.y = pack_lo_h2(v[2], v[3], hi.y);
+                lo.z = pack_lo_h2(v[4], v[5], hi.z); lo.w = pack_lo_h2(v[6], v[7], hi.w);
+                const int off = (ch ^ (row & 7)) << 4;
+                *reinterpret_cast<uint4*>(xrow_hi + off) = hi;
+                *reinterpret_cast<uint4*>(xrow_lo + off) = lo;
+            }
+            fence_proxy_async();
+        };
+        load(0);
+        publish();
+        mbar_arrive(a_ready);
+        for (int t = 0; t < a.T; ++t) {
+            if (t + 1 < a.T) load(t + 1);       // in flight while the tensor core and the cell warps work on step t
+            mbar_wait(acc_full, (uint32_t)(t & 1));      // MMA(t) has consumed x_t
+            if (t + 1 < a.T) {
+                publish();
+                mbar_arrive(a_ready);
+            }
+        }
+    } else {
+        // ======================================================================= MMA issuer
+        const uint32_t idesc = make_idesc(256);
+        for (int t = 0; t < a.T; ++t) {
+            mbar_wait(a_ready, (uint32_t)(t & 1));
+            tc_fence_after();
+            if (lane == 0) {
+                // pass 0: A_hi B_hi, pass 1: A_lo B_hi, pass 2: A_hi B_lo
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const int ahl = pass == 1 ? 1 : 0;
+                    const int bhl = pass == 2 ? 1 : 0;
+#pragma unroll
+                    for (int slab = 0; slab < 2; ++slab) {
+                        const uint32_t aa = smem_u32(a_slab(As, ahl, slab));
+                        const uint32_t bb = smem_u32(Bs + (bhl * 2 + slab) * B_SLAB_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem_base, make_desc(aa + k * 32), make_desc(bb + k * 32), idesc, (pass | slab | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace
+
+bool lstm_umma_supported(const LstmArgs& a) { return a.E == 64 && a.F >= ROWS && a.Wimg != nullptr; }
+
+int launch_lstm_umma(const LstmArgs& a, cudaStream_t st) {
+    if (!lstm_umma_supported(a)) return fail("lstm_umma: unsupported shape");
+    static bool configured = false;
+    if (!configured) {
+        EAB_CUDA(cudaFuncSetAttribute(lstm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int NQ = a.B * a.F;
+    ProfScope ps("lstm_umma", 2.0 * NQ * a.T * (64 + H) * 4.0 * H, 4.0 * NQ * a.T * (64 + H), st);
+    lstm_umma_kernel<<<(NQ + ROWS - 1) / ROWS, NTHREADS, SMEM_BYTES, st>>>(a);
+    EAB_LAUNCH_CHECK("lstm_umma_kernel");
+    return 0;
+}
+
+}  // namespace eab

@@ -170,6 +170,8 @@ struct eab_model {
            off_ln_b = 0, off_cnn_w = 0, off_cnn_b = 0;
     int dnn_N[2] = {0, 0}, cnn_N = 0;
     UmmaW u_dnn[2], u_cnn;
+    size_t off_rnn_img[2] = {0, 0}, off_rnn_ubias[2] = {0, 0};
+    bool rnn_umma_ok = false;
 
     // device state
     float* blob = nullptr;
@@ -629,6 +631,29 @@ struct Packer {
                         blob[m->off_rnn[r][2] + (size_t)j * 4 + g] = P(m->rnn[r][2])[g * H + j] + P(m->rnn[r][3])[g * H + j];
                     }
             }
+            // tcgen05 LSTM: image row n = half*128 + gate*32 + jj  <->  torch row gate*64 + (half*32 + jj);
+            // K slab 0 = W_ih (input channels), slab 1 = W_hh
+            m->rnn_umma_ok = c.embed_dim == 64;
+            if (m->rnn_umma_ok) {
+                for (int r = 0; r < 2; ++r) {
+                    m->off_rnn_img[r] = alloc((size_t)4 * 256 * 32);
+                    m->off_rnn_ubias[r] = alloc(256);
+                    __half* img = reinterpret_cast<__half*>(blob.data() + m->off_rnn_img[r]);
+                    for (int n = 0; n < 256; ++n) {
+                        const int half_ = n >> 7, g = (n >> 5) & 3, jj = n & 31;
+                        const int row = g * H + half_ * 32 + jj;
+                        blob[m->off_rnn_ubias[r] + n] = P(m->rnn[r][2])[row] + P(m->rnn[r][3])[row];
+                        for (int slab = 0; slab < 2; ++slab)
+                            for (int k = 0; k < 64; ++k) {
+                                const float w = P(m->rnn[r][slab])[(size_t)row * 64 + k];
+                                const __half hi = __float2half_rn(w);
+                                const __half lo = __float2half_rn(w - __half2float(hi));
+                                img[((size_t)(0 * 2 + slab) * 256) * 64 + sw128_index_h(n, k)] = hi;
+                                img[((size_t)(1 * 2 + slab) * 256) * 64 + sw128_index_h(n, k)] = lo;
+                            }
+                    }
+                }
+            }
             m->off_dnn_w[0] = linear(m->dnn_w[0], m->dnn_b[0], H, H, &m->dnn_N[0], &m->off_dnn_b[0]);
             m->off_dnn_w[1] = linear(m->dnn_w[1], m->dnn_b[1], 2 * c.M, H, &m->dnn_N[1], &m->off_dnn_b[1]);
             {
@@ -1006,6 +1031,16 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
                 a.Wx = cx.W(m->off_rnn[l][0]); a.Wh = cx.W(m->off_rnn[l][1]); a.bias = cx.W(m->off_rnn[l][2]);
                 a.B = cx.B; a.T = cx.T; a.F = c.n_freq; a.E = src.C;
                 a.out = h[l].data;
+                if (m->opt_umma && m->rnn_umma_ok) {
+                    LstmArgs u = a;
+                    u.Wimg = cx.W(m->off_rnn_img[l]);
+                    u.bias = cx.W(m->off_rnn_ubias[l]);
+                    if (lstm_umma_supported(u)) {
+                        EAB_TRY(launch_lstm_umma(u, cx.st));
+                        tap(cx, l ? "h2" : "h1", h[l]);
+                        continue;
+                    }
+                }
                 EAB_TRY(launch_lstm(a, cx.st));
             }
             tap(cx, l ? "h2" : "h1", h[l]);
