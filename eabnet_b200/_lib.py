@@ -35,6 +35,7 @@ SYMBOLS = {
     "eab_last_launch_count": (C.c_int, [_P]),
     "eab_debug_tap": (C.c_int64, [_P, C.c_char_p, _F, C.c_int64, _P]),
     "eab_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "eab_debug_counters": (C.c_int, [_P, C.POINTER(C.c_uint64 * 16)]),
     "eab_profile_enable": (C.c_int, [_P, C.c_int]),
     "eab_profile_summary": (C.c_int64, [_P, C.c_char_p, C.c_int64]),
     "eab_last_error": (C.c_char_p, []),

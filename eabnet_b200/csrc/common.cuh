@@ -172,9 +172,44 @@ struct UmmaConvArgs {
     const float* stat_alpha[2];
     int nstats;
     int tiles_per_b;             // ceil(T*E / 128)
+    unsigned long long* dbg;     // optional [16] cycle counters of CTA 0 (diagnostics), else null
 };
 bool umma_conv_supported(const UmmaConvArgs& a);
 int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st);
+
+// "Stage once, shift by descriptor" variant (conv_plane.cu): GEMM rows are (t, e') with a padded pitch P >= E rows per
+// frame; the transformed fp16 input of a tile (+ halo) is staged ONCE per tile as 1-2 column planes with the same
+// pitch, and every tap is the same shared-memory plane viewed through a row-shifted UMMA descriptor.
+struct PlaneConvArgs {
+    ConvSrc src[2];
+    int nsrc;
+    int B, T, Fin;
+    int E, P;                    // valid rows per frame / padded pitch
+    int nplanes;                 // 1, or 2 for stride-2 convs (even / odd input columns)
+    int plane_cols[2];           // real columns per plane (the rest up to P are zero)
+    int col_stride, col_off[2];  // fi = col * col_stride + col_off[plane]
+    int ntaps;
+    int tap_plane[kMaxTaps], tap_shift[kMaxTaps];   // A rows of a tap = plane rows + tap_shift
+    int back, fwd;               // halo rows before / after the 128 tile rows
+    int out_stride, out_off, Fout;
+    int nslab, ncoef, npass;
+    const float* Whi;
+    const float* Wlo;
+    const float* bias;
+    int Cout, N, gate_off, relu;
+    float algo_frac;
+    float* out;
+    int out_ld, out_coff;
+    const float* resid;
+    double* stats[2];
+    const float* stat_alpha[2];
+    int nstats;
+    int tiles_per_b;             // ceil(T*P / 128)
+    unsigned int p_magic;        // floor(2^32 / P) + 1  (division by P in the producers)
+    int nbuf;                    // plane double-buffering (1 or 2), chosen by the launcher from the smem budget
+};
+bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
+int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);
 
 struct CombineArgs {
     ConvSrc src[3];

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -185,6 +186,10 @@ struct eab_model {
     int opt_umma = 1;             // tcgen05 path for eligible layers
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
+    int opt_plane = 1;            // "stage once, shift by descriptor" kernel for multi-tap layers
+    int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
+    int umma_launch_idx = 0;
+    unsigned long long* dbg_buf = nullptr;
 };
 
 namespace eab {
@@ -740,6 +745,57 @@ Xform xf_after(Ctx& cx, const NormAct& na, double* stats, int count, int prelu_p
     return x;
 }
 
+// Re-express a per-tap gather launch as a "stage once" launch (conv_plane.cu); false if the shape does not qualify.
+bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p) {
+    if (u.wide) return false;
+    memset(p, 0, sizeof(*p));
+    p->nsrc = u.nsrc;
+    for (int i = 0; i < u.nsrc; ++i) p->src[i] = u.src[i];
+    p->B = u.B; p->T = u.T; p->Fin = u.Fin; p->E = u.E;
+    int min_df = 0, max_df = 0;
+    for (int i = 0; i < u.ntaps; ++i) { min_df = std::min(min_df, u.df[i]); max_df = std::max(max_df, u.df[i]); }
+    if (u.in_stride == 2) {
+        if (min_df < 0) return false;
+        p->nplanes = 2;
+        p->plane_cols[0] = (u.Fin + 1) / 2; p->plane_cols[1] = u.Fin / 2;
+        p->col_stride = 2; p->col_off[0] = 0; p->col_off[1] = 1;
+        p->P = std::max(u.E + max_df / 2, p->plane_cols[0]);
+    } else if (u.in_stride == 1) {
+        if (max_df > 0) return false;
+        p->nplanes = 1;
+        p->plane_cols[0] = u.Fin; p->plane_cols[1] = 0;
+        p->col_stride = 1; p->col_off[0] = 0; p->col_off[1] = 0;
+        p->P = std::max(u.E, u.Fin - min_df);          // the pad columns [Fin, P) absorb the negative column offsets
+    } else {
+        return false;
+    }
+    p->ntaps = u.ntaps;
+    int back = 0, fwd = 0;
+    for (int i = 0; i < u.ntaps; ++i) {
+        p->tap_plane[i] = u.in_stride == 2 ? (u.df[i] & 1) : 0;
+        p->tap_shift[i] = -u.dt[i] * p->P + (u.in_stride == 2 ? (u.df[i] >> 1) : u.df[i]);
+        back = std::max(back, -p->tap_shift[i]);
+        fwd = std::max(fwd, p->tap_shift[i]);
+    }
+    p->back = back; p->fwd = fwd;
+    p->out_stride = u.out_stride; p->out_off = u.out_off; p->Fout = u.Fout;
+    p->nslab = u.nslab; p->ncoef = u.ncoef; p->npass = u.npass;
+    p->Whi = u.Whi; p->Wlo = u.Wlo; p->bias = u.bias;
+    p->Cout = u.Cout; p->N = u.N; p->gate_off = u.gate_off; p->relu = u.relu; p->algo_frac = u.algo_frac;
+    p->out = u.out; p->out_ld = u.out_ld; p->out_coff = u.out_coff; p->resid = u.resid;
+    p->nstats = u.nstats;
+    for (int i = 0; i < 2; ++i) { p->stats[i] = u.stats[i]; p->stat_alpha[i] = u.stat_alpha[i]; }
+    p->tiles_per_b = (int)(((long long)u.T * p->P + 127) / 128);
+    p->nbuf = 1;
+    return plane_conv_supported(*p);
+}
+
+int launch_tensor_conv(eab_model* m, const UmmaConvArgs& u, cudaStream_t st) {
+    PlaneConvArgs p;
+    if (m->opt_plane && u.ntaps > 1 && to_plane_args(u, &p)) return launch_conv_plane(p, st);
+    return launch_conv_umma(u, st);
+}
+
 // one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
 int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out) {
     const int Fin = srcs[0].F;
@@ -777,7 +833,8 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out)
             if (stats) { u.nstats = 1; u.stats[0] = stats; }
             u.tiles_per_b = (cx.T * u.E + 127) / 128;
             if (umma_conv_supported(u)) {
-                EAB_TRY(launch_conv_umma(u, cx.st));
+                if (cx.m->umma_launch_idx++ == cx.m->opt_dbg_launch && cx.m->dbg_buf) u.dbg = cx.m->dbg_buf;
+                EAB_TRY(launch_tensor_conv(cx.m, u, cx.st));
                 continue;
             }
         }
@@ -884,7 +941,7 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
             for (int i = 0; i < nstats; ++i) { u.stats[i] = stats[i]; u.stat_alpha[i] = stat_alpha[i]; }
             u.tiles_per_b = (cx.T * u.E + 127) / 128;
             if (!umma_conv_supported(u)) return fail("internal: pointwise layer rejected by the tcgen05 path");
-            EAB_TRY(launch_conv_umma(u, cx.st));
+            EAB_TRY(launch_tensor_conv(cx.m, u, cx.st));
         }
         return 0;
     }
@@ -1084,6 +1141,7 @@ int forward(eab_model* m, const float* inpt, float* out, int B, int T, void* ws,
     if (ws_bytes < tb) return fail("workspace too small: need " + std::to_string(tb) + " bytes");
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail("workspace must be 256-byte aligned");
     m->taps.clear();
+    m->umma_launch_idx = 0;
     if (sb) EAB_CUDA(cudaMemsetAsync(ws, 0, sb, st));
     Ctx cx;
     cx.m = m; cx.dry = false; cx.base = static_cast<char*>(ws); cx.B = B; cx.T = T; cx.st = st;
@@ -1256,9 +1314,22 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     if (!m || !name) return fail("eab_set_option: null argument");
     const std::string n(name);
     if (n == "umma") m->opt_umma = value != 0;
+    else if (n == "plane") m->opt_plane = value != 0;
     else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
     else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
+    else if (n == "dbg_launch") {
+        m->opt_dbg_launch = value;
+        if (!m->dbg_buf) { if (check_cuda(cudaMalloc(&m->dbg_buf, 16 * sizeof(unsigned long long)), "dbg alloc")) return 1; }
+        cudaMemset(m->dbg_buf, 0, 16 * sizeof(unsigned long long));
+    }
     else return fail("eab_set_option: unknown option or bad value: " + n);
+    return 0;
+}
+
+int eab_debug_counters(eab_model* m, unsigned long long* out16) {
+    if (!m || !out16 || !m->dbg_buf) return fail("eab_debug_counters: not enabled");
+    EAB_CUDA(cudaDeviceSynchronize());
+    EAB_CUDA(cudaMemcpy(out16, m->dbg_buf, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 

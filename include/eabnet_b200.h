@@ -113,6 +113,8 @@ EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, in
  *   "enc_passes" (3)  1 = single-pass TF32, 3 = 3xTF32 split (fp32-grade) in the encoder convs
  *   "dec_passes" (1)  same for the decoder convs */
 EAB_API int     eab_set_option(eab_model* m, const char* name, int value);
+/* diagnostics: cycle counters of CTA 0 of the tcgen05 conv launch selected with option "dbg_launch" */
+EAB_API int     eab_debug_counters(eab_model* m, unsigned long long* out16);
 
 /* Per-launch CUDA-event timing of the calling thread's launches, aggregated per kernel family; the summary is a
  * JSON array [{"kernel","launches","ms","flops","bytes"}] with ALGORITHMIC flops/bytes, written to
