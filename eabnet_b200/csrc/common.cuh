@@ -207,6 +207,7 @@ struct PlaneConvArgs {
     int tiles_per_b;             // ceil(T*P / 128)
     unsigned int p_magic;        // floor(2^32 / P) + 1  (division by P in the producers)
     int nbuf;                    // plane double-buffering (1 or 2), chosen by the launcher from the smem budget
+    unsigned long long* dbg;     // optional [16] cycle counters of CTA 0 (diagnostics)
 };
 bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
 int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);

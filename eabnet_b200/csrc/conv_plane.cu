@@ -33,7 +33,6 @@ constexpr int NPROD = 512;
 constexpr int NEPI = 128;
 constexpr int NTHREADS = NPROD + 64 + NEPI;
 constexpr int NSB = 3;               // weight ring stages
-constexpr int ITEMS = 2;             // 16-byte output chunks per producer thread per batch (2 LDG.128 each)
 
 struct Plan {
     int R;                           // staged rows per plane = 128 + back + fwd
@@ -115,8 +114,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
         const int C0 = a.src[0].C, C1 = a.nsrc > 1 ? a.src[1].C : 0;
         const int nslab0 = C0 / KC;
         const int R = pl.R;
-        const int rows_total = a.nplanes * a.nslab * R;            // (plane, slab, row) triples per buffer
-        const int c8 = tid & 7;                                    // 16-byte output chunk = 8 channels
+        const int nps = a.nplanes * a.nslab;
+        const int items_total = nps * R * 2;                       // work item = half a plane row: 32 channels
         const int mode0 = (a.src[0].xf.affine == 0 && a.src[0].xf.prelu == 0) ? 0 : (a.src[0].xf.prelu == 1 ? 2 : 1);
         const int mode1 = a.nsrc > 1 ? ((a.src[1].xf.affine == 0 && a.src[1].xf.prelu == 0) ? 0 : (a.src[1].xf.prelu == 1 ? 2 : 1)) : 0;
         // frames are shifted by `kf` so that the row coordinate fed to the magic division is never negative
@@ -124,7 +123,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
         int cur_b = -1;
         int buf = 0;
         uint32_t bphase = 0;
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+        long long t_wait = 0, t_issue = 0, t_xform = 0, t_store = 0, t_items = 0, t_fence = 0;
+        const long long t_start = dbg_on ? clock64() : 0;
+        int rot = 0;                                               // rotates the item -> thread map so that the ragged
+        for (int tile = tile_begin; tile < tile_end; ++tile) {     // last batch lands on a different warp every tile
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
             if (b != cur_b) {
@@ -143,60 +146,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
             }
             const float* xb0 = a.src[0].x + (size_t)b * a.T * a.Fin * C0;
             const float* xb1 = a.nsrc > 1 ? a.src[1].x + (size_t)b * a.T * a.Fin * C1 : nullptr;
+            const long long w0 = dbg_on ? clock64() : 0;
             mbar_wait(&plane_empty[buf], bphase ^ 1);
+            if (dbg_on) t_wait += clock64() - w0;
             uint8_t* pbuf = planes + buf * pl.buf_bytes;
             const int rho0 = row0 - a.back + kf * a.P;             // >= 0
-            // each thread walks (plane, slab, row) triples  rid = tid/8 + (NPROD/8) * n,  ITEMS at a time
-            for (int rid0 = tid >> 3; rid0 < rows_total; rid0 += ITEMS * (NPROD / 8)) {
-                float4 v[ITEMS][2];
-                int dst[ITEMS];                                    // byte offset in the buffer (hi copy), -1 = none
-                int cidx[ITEMS], md[ITEMS];
-                bool ok[ITEMS];
+            int vt = tid + rot;
+            if (vt >= NPROD) vt -= NPROD;
+            rot += 97;
+            if (rot >= NPROD) rot -= NPROD;
+            const long long i0 = dbg_on ? clock64() : 0;
+            for (int item = vt; item < items_total; item += NPROD) {
+                const long long j0 = dbg_on ? clock64() : 0;
+                const int hf = item & 1;                           // which 32-channel half of the 64-channel slab row
+                const int rid = item >> 1;
+                const int ps = rid / R;                            // plane * nslab + slab   (one division per 32 channels)
+                const int lam = rid - ps * R;
+                const int plane = ps / a.nslab;
+                const int slab = ps - plane * a.nslab;
+                const int rho = rho0 + lam;
+                const int tq = a.P == 1 ? rho : (int)__umulhi((unsigned)rho, a.p_magic);
+                const int col = rho - tq * a.P;
+                const int t = tq - kf;
+                uint8_t* drow = pbuf + (ps * npb) * pl.plane_bytes + lam * 128;
+                const int sw = lam & 7;
+                float4 v[8];
+                const bool ok = t >= 0 && t < a.T && col < a.plane_cols[plane];
+                const bool second = slab >= nslab0;
+                if (ok) {
+                    const int fi = col * a.col_stride + a.col_off[plane];
+                    const float* xb = second ? xb1 : xb0;
+                    const int C = second ? C1 : C0;
+                    const int cc = (second ? slab - nslab0 : slab) * KC + hf * 32;
+                    const float4* p = reinterpret_cast<const float4*>(xb + (uint32_t)((t * a.Fin + fi) * C + cc));
 #pragma unroll
-                for (int it = 0; it < ITEMS; ++it) {
-                    const int rid = rid0 + it * (NPROD / 8);
-                    v[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    dst[it] = -1;
-                    ok[it] = false;
-                    cidx[it] = 0;
-                    md[it] = 0;
-                    if (rid < rows_total) {
-                        const int ps = rid / R;                    // plane * nslab + slab
-                        const int lam = rid - ps * R;
-                        const int plane = ps / a.nslab;
-                        const int slab = ps - plane * a.nslab;
-                        dst[it] = (ps * npb) * pl.plane_bytes + lam * 128 + ((c8 ^ (lam & 7)) << 4);
-                        const int rho = rho0 + lam;
-                        const int tq = a.P == 1 ? rho : (int)__umulhi((unsigned)rho, a.p_magic);
-                        const int col = rho - tq * a.P;
-                        const int t = tq - kf;
-                        if (t >= 0 && t < a.T && col < a.plane_cols[plane]) {
-                            const int fi = col * a.col_stride + a.col_off[plane];
-                            const bool second = slab >= nslab0;
-                            const float* xb = second ? xb1 : xb0;
-                            const int C = second ? C1 : C0;
-                            const int cc = (second ? slab - nslab0 : slab) * KC + c8 * 8;
-                            const float4* p = reinterpret_cast<const float4*>(xb + (uint32_t)((t * a.Fin + fi) * C + cc));
-                            v[it][0] = __ldg(p);
-                            v[it][1] = __ldg(p + 1);
-                            ok[it] = true;
-                            cidx[it] = slab * KC + c8 * 8;
-                            md[it] = second ? mode1 : mode0;
-                        }
-                    }
-                }
+                    for (int j = 0; j < 8; ++j) v[j] = __ldg(p + j);
+                    if (dbg_on) t_issue += clock64() - j0;
+                    const int md = second ? mode1 : mode0;
+                    if (md != 0) {
+                        const float* cb = coef + slab * KC + hf * 32;
 #pragma unroll
-                for (int it = 0; it < ITEMS; ++it) {
-                    if (dst[it] < 0) continue;
-                    if (ok[it] && md[it] != 0) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float4 cs = *reinterpret_cast<const float4*>(coef + cidx[it] + 4 * h);
-                            const float4 ch = *reinterpret_cast<const float4*>(coef + a.ncoef + cidx[it] + 4 * h);
-                            const float4 ca = *reinterpret_cast<const float4*>(coef + 2 * a.ncoef + cidx[it] + 4 * h);
-                            float4& q = v[it][h];
-                            if (md[it] == 1) {
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 cs = *reinterpret_cast<const float4*>(cb + 4 * j);
+                            const float4 ch = *reinterpret_cast<const float4*>(cb + a.ncoef + 4 * j);
+                            const float4 ca = *reinterpret_cast<const float4*>(cb + 2 * a.ncoef + 4 * j);
+                            float4& q = v[j];
+                            if (md == 1) {
                                 float x;
                                 x = fmaf(q.x, cs.x, ch.x); q.x = fmaxf(x, 0.f) + ca.x * fminf(x, 0.f);
                                 x = fmaf(q.y, cs.y, ch.y); q.y = fmaxf(x, 0.f) + ca.y * fminf(x, 0.f);
@@ -210,31 +205,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
                             }
                         }
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const long long j2 = dbg_on ? clock64() : 0;
+                if (dbg_on) t_xform += j2 - j0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {                      // four 16-byte fp16 chunks of this half row
+                    const float4 lo4 = v[2 * c], hi4 = v[2 * c + 1];
                     uint4 hi;
-                    hi.x = pack_h2(v[it][0].x, v[it][0].y); hi.y = pack_h2(v[it][0].z, v[it][0].w);
-                    hi.z = pack_h2(v[it][1].x, v[it][1].y); hi.w = pack_h2(v[it][1].z, v[it][1].w);
-                    *reinterpret_cast<uint4*>(pbuf + dst[it]) = hi;
+                    hi.x = pack_h2(lo4.x, lo4.y); hi.y = pack_h2(lo4.z, lo4.w);
+                    hi.z = pack_h2(hi4.x, hi4.y); hi.w = pack_h2(hi4.z, hi4.w);
+                    const int off = ((hf * 4 + c) ^ sw) << 4;
+                    *reinterpret_cast<uint4*>(drow + off) = hi;
                     if (npb == 2) {
                         uint4 lo;
-                        lo.x = pack_lo_h2(v[it][0].x, v[it][0].y, hi.x); lo.y = pack_lo_h2(v[it][0].z, v[it][0].w, hi.y);
-                        lo.z = pack_lo_h2(v[it][1].x, v[it][1].y, hi.z); lo.w = pack_lo_h2(v[it][1].z, v[it][1].w, hi.w);
-                        *reinterpret_cast<uint4*>(pbuf + dst[it] + pl.plane_bytes) = lo;
+                        lo.x = pack_lo_h2(lo4.x, lo4.y, hi.x); lo.y = pack_lo_h2(lo4.z, lo4.w, hi.y);
+                        lo.z = pack_lo_h2(hi4.x, hi4.y, hi.z); lo.w = pack_lo_h2(hi4.z, hi4.w, hi.w);
+                        *reinterpret_cast<uint4*>(drow + pl.plane_bytes + off) = lo;
                     }
                 }
+                if (dbg_on) t_store += clock64() - j2;
             }
+            const long long i1 = dbg_on ? clock64() : 0;
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&plane_full[buf]);
+            if (dbg_on) { t_items += i1 - i0; t_fence += clock64() - i1; }
             if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
+        if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wait; a.dbg[2] = tile_end - tile_begin; a.dbg[3] = items_total; a.dbg[13] = t_issue; a.dbg[14] = t_xform; a.dbg[15] = t_store; a.dbg[12] = t_items; a.dbg[11] = t_fence; }
     } else if (warp == NPROD / 32) {
         // =========================================================================== MMA issuer
         const uint32_t idesc = make_idesc(a.N);
         int buf = 0, stage = 0, acc = 0;
         uint32_t bphase = 0, sphase = 0, aphase = 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        long long t_wacc = 0, t_wplane = 0, t_wb = 0;
+        const long long t_start = dbg_on ? clock64() : 0;
         for (int tile = tile_begin; tile < tile_end; ++tile) {
+            long long w0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_empty[acc], aphase ^ 1);
+            long long w1 = dbg_on ? clock64() : 0;
             mbar_wait(&plane_full[buf], bphase);
+            if (dbg_on) { t_wacc += w1 - w0; t_wplane += clock64() - w1; }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.N);
             const uint32_t pbase = smem_u32(planes + buf * pl.buf_bytes);
@@ -244,7 +259,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
                 for (int slab = 0; slab < a.nslab; ++slab) {
                     const uint32_t a_hi = pbase + (uint32_t)(((a.tap_plane[tap] * a.nslab + slab) * npb) * pl.plane_bytes + arow * 128);
                     for (int pass = 0; pass < a.npass; ++pass, ++unit) {
+                        w0 = dbg_on ? clock64() : 0;
                         mbar_wait(&b_full[stage], sphase);
+                        if (dbg_on) t_wb += clock64() - w0;
                         tc_fence_after();
                         if (lane == 0) {
                             const uint32_t a_addr = a_hi + (pass == 1 ? (uint32_t)pl.plane_bytes : 0u);
@@ -266,6 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
             if (++acc == 2) { acc = 0; aphase ^= 1; }
             if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
+        if (dbg_on) { a.dbg[4] = clock64() - t_start; a.dbg[5] = t_wacc; a.dbg[6] = t_wplane; a.dbg[7] = t_wb; }
     } else if (warp == NPROD / 32 + 1) {
         // =========================================================================== B (weight) loader
         int stage = 0;
@@ -294,9 +312,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
         const int ld = pl.stg_ld;
         int acc = 0;
         uint32_t aphase = 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && et == 0;
+        long long t_wfull = 0, t_tmem = 0, t_store = 0, t_stats = 0;
+        const long long t_start = dbg_on ? clock64() : 0;
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
+            bool row_valid;
             {
                 const int r = row0 + row;
                 long long off = -1;
@@ -306,8 +328,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
                     if (e < a.E) off = ((((long long)b * a.T + t) * a.Fout) + (e * a.out_stride + a.out_off)) * a.out_ld + a.out_coff;
                 }
                 rowoff[row] = off;
+                row_valid = off >= 0;
             }
+            const long long e0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_full[acc], aphase);
+            const long long e1 = dbg_on ? clock64() : 0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.N);
             for (int c0 = 0; c0 < a.Cout; c0 += 16) {
@@ -334,6 +359,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
+                if (!row_valid) {                // dummy / ragged rows contribute exact zeros to the statistics
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     *reinterpret_cast<float4*>(stg + row * ld + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -341,20 +370,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
             named_bar_sync(2, NEPI);
-            const int tpr = a.Cout >> 2;
-            const int rows_per_it = NEPI / tpr;
-            const int cq = (et % tpr) * 4;
-            for (int r = et / tpr; r < TM; r += rows_per_it) {
-                const long long off = rowoff[r];
-                if (off < 0) continue;
-                float4 o = *reinterpret_cast<const float4*>(stg + r * ld + cq);
-                if (a.resid) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + off + cq));
-                    o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-                    if (a.nstats) *reinterpret_cast<float4*>(stg + r * ld + cq) = o;
+            const long long e2 = dbg_on ? clock64() : 0;
+            if (!a.resid) {
+                // one bulk shared -> global copy per valid row (Cout * 4 bytes), issued by the row's own thread
+                fence_proxy_async();
+                if (row_valid)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.out + rowoff[row]),
+                                 "r"(smem_u32(stg + row * ld)), "r"((uint32_t)(a.Cout * 4))
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            } else {
+                const int tpr = a.Cout >> 2;
+                const int rows_per_it = NEPI / tpr;
+                const int cq = (et % tpr) * 4;
+                for (int r0 = et / tpr; r0 < TM; r0 += 4 * rows_per_it) {
+                    long long off[4];
+                    float4 o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = r0 + j * rows_per_it;
+                        off[j] = r < TM ? rowoff[r] : -1;
+                        o[j] = r < TM ? *reinterpret_cast<const float4*>(stg + r * ld + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (off[j] < 0) continue;
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + off[j] + cq));
+                        o[j].x += q.x; o[j].y += q.y; o[j].z += q.z; o[j].w += q.w;
+                        if (a.nstats) *reinterpret_cast<float4*>(stg + (r0 + j * rows_per_it) * ld + cq) = o[j];
+                        *reinterpret_cast<float4*>(a.out + off[j] + cq) = o[j];
+                    }
                 }
-                *reinterpret_cast<float4*>(a.out + off + cq) = o;
             }
+            const long long e3 = dbg_on ? clock64() : 0;
             if (a.nstats) {
                 if (a.resid) named_bar_sync(2, NEPI);
                 const int nsc = a.nstats * a.Cout;
@@ -364,24 +412,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
                     const int s = sc / a.Cout, c = sc - s * a.Cout;
                     const bool pre = a.stat_alpha[s] != nullptr;
                     const float al = pre ? __ldg(a.stat_alpha[s] + c) : 1.f;
-                    float sum = 0.f, sq = 0.f;
-                    const int r_lo = half * (TM / 2);
-#pragma unroll 4
-                    for (int r = r_lo; r < r_lo + TM / 2; ++r) {
-                        if (rowoff[r] < 0) continue;
-                        float u = stg[r * ld + c];
-                        if (pre) u = prelu_f(u, al);
-                        sum += u;
-                        sq += u * u;
+                    const float* col = stg + (half * (TM / 2)) * ld + c;
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                    for (int r = 0; r < TM / 2; r += 2) {      // invalid rows were staged as zeros
+                        float u0 = col[r * ld], u1 = col[(r + 1) * ld];
+                        u0 = fmaxf(u0, 0.f) + al * fminf(u0, 0.f);      // al == 1 when the statistics are of the raw value
+                        u1 = fmaxf(u1, 0.f) + al * fminf(u1, 0.f);
+                        s0 += u0; q0 = fmaf(u0, u0, q0);
+                        s1 += u1; q1 = fmaf(u1, u1, q1);
                     }
                     double* dstp = a.stats[s] + ((size_t)b * a.Cout + c) * 2;
-                    atomicAdd(dstp, (double)sum);
-                    atomicAdd(dstp + 1, (double)sq);
+                    atomicAdd(dstp, (double)(s0 + s1));
+                    atomicAdd(dstp + 1, (double)(q0 + q1));
                 }
             }
+            if (!a.resid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             named_bar_sync(2, NEPI);
+            if (dbg_on) { const long long e4 = clock64(); t_wfull += e1 - e0; t_tmem += e2 - e1; t_store += e3 - e2; t_stats += e4 - e3; }
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
+        if (dbg_on) { a.dbg[8] = clock64() - t_start; a.dbg[9] = t_wfull; a.dbg[10] = t_tmem; a.dbg[11] = t_store; a.dbg[12] = t_stats; }
     }
 
     tc_fence_before();

@@ -39,6 +39,7 @@ void count_launch(int n) { g_launches += n; }
 struct ProfRec { const char* cat; double flops, bytes; cudaEvent_t a, b; };
 struct Profiler {
     bool on = false;
+    bool detail = false;
     std::vector<ProfRec> recs;
     std::vector<cudaEvent_t> pool;
     cudaEvent_t get() {
@@ -792,7 +793,7 @@ bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p) {
 
 int launch_tensor_conv(eab_model* m, const UmmaConvArgs& u, cudaStream_t st) {
     PlaneConvArgs p;
-    if (m->opt_plane && u.ntaps > 1 && to_plane_args(u, &p)) return launch_conv_plane(p, st);
+    if (m->opt_plane && u.ntaps > 1 && to_plane_args(u, &p)) { p.dbg = u.dbg; return launch_conv_plane(p, st); }
     return launch_conv_umma(u, st);
 }
 
@@ -1337,6 +1338,7 @@ int eab_profile_enable(eab_model* m, int on) {
     (void)m;
     g_prof.clear();
     g_prof.on = on != 0;
+    g_prof.detail = on == 2;          // 2: one summary entry per launch instead of per kernel family
     return 0;
 }
 
@@ -1346,10 +1348,13 @@ int64_t eab_profile_summary(eab_model* m, char* buf, int64_t cap) {
     if (check_cuda(cudaDeviceSynchronize(), "profile sync")) return -1;
     struct Agg { int n = 0; double ms = 0, flops = 0, bytes = 0; };
     std::map<std::string, Agg> agg;
+    int seq = 0;
     for (auto& r : g_prof.recs) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
-        Agg& a = agg[r.cat];
+        char key[64];
+        if (g_prof.detail) snprintf(key, sizeof(key), "%04d:%s", seq++, r.cat); else snprintf(key, sizeof(key), "%s", r.cat);
+        Agg& a = agg[key];
         a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
     }
     std::string js = "[";

@@ -235,14 +235,14 @@ class EaBNet(nn.Module):
         """kernel-selection / precision knobs of the native path (see include/eabnet_b200.h: eab_set_option)"""
         _lib.check(self._native.lib.eab_set_option(self._native.h, name.encode(), int(value)), "eab_set_option")
 
-    def profile(self, on: bool) -> None:
-        """switch per-launch CUDA-event timing on/off for this thread's launches"""
-        _lib.check(self._native.lib.eab_profile_enable(self._native.h, int(bool(on))))
+    def profile(self, on) -> None:
+        """switch per-launch CUDA-event timing on/off for this thread's launches (2 = one entry per launch)"""
+        _lib.check(self._native.lib.eab_profile_enable(self._native.h, int(on)))
 
     def profile_summary(self) -> list:
         """[{kernel, launches, ms, flops, bytes}] since the last call (synchronises the device)"""
         import json
-        buf = C.create_string_buffer(1 << 16)
+        buf = C.create_string_buffer(1 << 18)
         n = self._native.lib.eab_profile_summary(self._native.h, buf, len(buf))
         if n < 0:
             _lib.check(1, "eab_profile_summary")
