@@ -793,6 +793,7 @@ bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p) {
 
 int launch_tensor_conv(eab_model* m, const UmmaConvArgs& u, cudaStream_t st) {
     PlaneConvArgs p;
+    // single-tap layers gain nothing from staging planes (measured: 22.6 vs 22.2 ms per step): keep the gather kernel
     if (m->opt_plane && u.ntaps > 1 && to_plane_args(u, &p)) { p.dbg = u.dbg; return launch_conv_plane(p, st); }
     return launch_conv_umma(u, st);
 }
