@@ -167,12 +167,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    sampler.start()                      # nvidia-smi needs ~1 s to produce its first sample: start before the warm-up
     with torch.no_grad():
         for _ in range(args.warmup):
             net.enhance(wave)
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler.rows.clear()             # keep only samples taken from here on (timed regions)
         # ---- device-resident throughput
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
