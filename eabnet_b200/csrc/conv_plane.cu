@@ -124,12 +124,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
         int buf = 0;
         uint32_t bphase = 0;
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-        long long t_wait = 0, t_issue = 0, t_xform = 0, t_store = 0, t_items = 0, t_fence = 0;
+        long long t_wait = 0, t_items = 0, t_fence = 0, t_pref = 0;
         const long long t_start = dbg_on ? clock64() : 0;
-        int rot = 0;                                               // rotates the item -> thread map so that the ragged
-        for (int tile = tile_begin; tile < tile_end; ++tile) {     // last batch lands on a different warp every tile
+        // item -> (plane/slab, row, half) decode + global loads; returns false for an out-of-range item
+        struct Item { int ps, lam, hf, slab; bool ok, second; };
+        auto decode_and_load = [&](int item, int tile, float4 (&v)[8], Item& it) {
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
+            it.hf = item & 1;
+            const int rid = item >> 1;
+            it.ps = rid / R;
+            it.lam = rid - it.ps * R;
+            const int plane = it.ps / a.nslab;
+            it.slab = it.ps - plane * a.nslab;
+            const int rho = row0 - a.back + kf * a.P + it.lam;     // >= 0
+            const int tq = a.P == 1 ? rho : (int)__umulhi((unsigned)rho, a.p_magic);
+            const int col = rho - tq * a.P;
+            const int t = tq - kf;
+            it.ok = t >= 0 && t < a.T && col < a.plane_cols[plane];
+            it.second = it.slab >= nslab0;
+            if (it.ok) {
+                const int fi = col * a.col_stride + a.col_off[plane];
+                const int C = it.second ? C1 : C0;
+                const float* xb = (it.second ? a.src[1].x : a.src[0].x) + (size_t)b * a.T * a.Fin * C;
+                const int cc = (it.second ? it.slab - nslab0 : it.slab) * KC + it.hf * 32;
+                const float4* p = reinterpret_cast<const float4*>(xb + (uint32_t)((t * a.Fin + fi) * C + cc));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldg(p + j);
+            }
+        };
+        auto rot_of = [&](int tile) { return (int)(((unsigned)(tile - tile_begin) * 97u) % (unsigned)NPROD); };
+        auto first_item = [&](int tile) { int vt = tid + rot_of(tile); return vt >= NPROD ? vt - NPROD : vt; };
+
+        float4 v[8];
+        Item cur;
+        cur.ok = false; cur.ps = 0; cur.lam = 0; cur.hf = 0; cur.slab = 0; cur.second = false;
+        bool have = false;                                         // v / cur hold the prefetched first item of `tile`
+        if (tile_begin < tile_end && first_item(tile_begin) < items_total) { decode_and_load(first_item(tile_begin), tile_begin, v, cur); have = true; }
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            const int b = tile / a.tiles_per_b;
             if (b != cur_b) {
                 named_bar_sync(1, NPROD);
                 for (int i = tid; i < a.ncoef; i += NPROD) {
@@ -144,47 +177,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
                 named_bar_sync(1, NPROD);
                 cur_b = b;
             }
-            const float* xb0 = a.src[0].x + (size_t)b * a.T * a.Fin * C0;
-            const float* xb1 = a.nsrc > 1 ? a.src[1].x + (size_t)b * a.T * a.Fin * C1 : nullptr;
             const long long w0 = dbg_on ? clock64() : 0;
             mbar_wait(&plane_empty[buf], bphase ^ 1);
             if (dbg_on) t_wait += clock64() - w0;
             uint8_t* pbuf = planes + buf * pl.buf_bytes;
-            const int rho0 = row0 - a.back + kf * a.P;             // >= 0
-            int vt = tid + rot;
-            if (vt >= NPROD) vt -= NPROD;
-            rot += 97;
-            if (rot >= NPROD) rot -= NPROD;
             const long long i0 = dbg_on ? clock64() : 0;
-            for (int item = vt; item < items_total; item += NPROD) {
-                const long long j0 = dbg_on ? clock64() : 0;
-                const int hf = item & 1;                           // which 32-channel half of the 64-channel slab row
-                const int rid = item >> 1;
-                const int ps = rid / R;                            // plane * nslab + slab   (one division per 32 channels)
-                const int lam = rid - ps * R;
-                const int plane = ps / a.nslab;
-                const int slab = ps - plane * a.nslab;
-                const int rho = rho0 + lam;
-                const int tq = a.P == 1 ? rho : (int)__umulhi((unsigned)rho, a.p_magic);
-                const int col = rho - tq * a.P;
-                const int t = tq - kf;
-                uint8_t* drow = pbuf + (ps * npb) * pl.plane_bytes + lam * 128;
-                const int sw = lam & 7;
-                float4 v[8];
-                const bool ok = t >= 0 && t < a.T && col < a.plane_cols[plane];
-                const bool second = slab >= nslab0;
-                if (ok) {
-                    const int fi = col * a.col_stride + a.col_off[plane];
-                    const float* xb = second ? xb1 : xb0;
-                    const int C = second ? C1 : C0;
-                    const int cc = (second ? slab - nslab0 : slab) * KC + hf * 32;
-                    const float4* p = reinterpret_cast<const float4*>(xb + (uint32_t)((t * a.Fin + fi) * C + cc));
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __ldg(p + j);
-                    if (dbg_on) t_issue += clock64() - j0;
-                    const int md = second ? mode1 : mode0;
+            for (int item = first_item(tile); item < items_total; item += NPROD) {
+                if (!have) decode_and_load(item, tile, v, cur);
+                have = false;
+                uint8_t* drow = pbuf + (cur.ps * npb) * pl.plane_bytes + cur.lam * 128;
+                const int sw = cur.lam & 7;
+                if (cur.ok) {
+                    const int md = cur.second ? mode1 : mode0;
                     if (md != 0) {
-                        const float* cb = coef + slab * KC + hf * 32;
+                        const float* cb = coef + cur.slab * KC + cur.hf * 32;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 cs = *reinterpret_cast<const float4*>(cb + 4 * j);
@@ -209,15 +215,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                const long long j2 = dbg_on ? clock64() : 0;
-                if (dbg_on) t_xform += j2 - j0;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {                      // four 16-byte fp16 chunks of this half row
                     const float4 lo4 = v[2 * c], hi4 = v[2 * c + 1];
                     uint4 hi;
                     hi.x = pack_h2(lo4.x, lo4.y); hi.y = pack_h2(lo4.z, lo4.w);
                     hi.z = pack_h2(hi4.x, hi4.y); hi.w = pack_h2(hi4.z, hi4.w);
-                    const int off = ((hf * 4 + c) ^ sw) << 4;
+                    const int off = ((cur.hf * 4 + c) ^ sw) << 4;
                     *reinterpret_cast<uint4*>(drow + off) = hi;
                     if (npb == 2) {
                         uint4 lo;
@@ -226,16 +230,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
                         *reinterpret_cast<uint4*>(drow + pl.plane_bytes + off) = lo;
                     }
                 }
-                if (dbg_on) t_store += clock64() - j2;
             }
+            // the next tile's first item: loads go out BEFORE the proxy fence, so their latency and the fence overlap
             const long long i1 = dbg_on ? clock64() : 0;
+            if (tile + 1 < tile_end && first_item(tile + 1) < items_total) { decode_and_load(first_item(tile + 1), tile + 1, v, cur); have = true; }
+            const long long i2 = dbg_on ? clock64() : 0;
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&plane_full[buf]);
-            if (dbg_on) { t_items += i1 - i0; t_fence += clock64() - i1; }
+            if (dbg_on) { t_items += i1 - i0; t_pref += i2 - i1; t_fence += clock64() - i2; }
             if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
-        if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wait; a.dbg[2] = tile_end - tile_begin; a.dbg[3] = items_total; a.dbg[13] = t_issue; a.dbg[14] = t_xform; a.dbg[15] = t_store; a.dbg[12] = t_items; a.dbg[11] = t_fence; }
+        if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wait; a.dbg[2] = tile_end - tile_begin; a.dbg[3] = items_total; a.dbg[13] = t_items; a.dbg[14] = t_fence; a.dbg[15] = t_pref; }
     } else if (warp == NPROD / 32) {
         // =========================================================================== MMA issuer
         const uint32_t idesc = make_idesc(a.N);

@@ -6,7 +6,7 @@
 namespace eab {
 namespace umma {
 
-constexpr uint32_t SPIN_LIMIT = 1u << 28;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;     // x the ~10 ms suspend hint: far beyond any legitimate wait
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -19,16 +19,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Blocks in hardware: the suspend-time hint lets the warp sleep until the phase completes (or the hint expires)
+// instead of spinning - spinning waiters otherwise steal issue slots from the warps that do the work.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0, spins = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)
             : "memory");
         if (done) break;
         if (++spins > SPIN_LIMIT) __trap();        // a protocol bug must fault, never hang the GPU
