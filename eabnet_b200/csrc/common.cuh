@@ -230,6 +230,7 @@ struct LstmArgs {
     const float* Wimg;           // tcgen05 kernel: fp16 images [hi|lo][x|h][256 rows][64 k], 128B-swizzled (or null)
     int B, T, F, E;
     float* out;                  // [B][T][F][64]
+    unsigned long long* dbg;     // optional cycle counters (diagnostics)
 };
 int launch_lstm(const LstmArgs& a, cudaStream_t st);
 bool lstm_umma_supported(const LstmArgs& a);

@@ -23,7 +23,14 @@ using namespace umma;
 
 constexpr int H = 64;
 constexpr int ROWS = 128;
-constexpr int NCELL = 256, NXP = 128, NTHREADS = NCELL + NXP + 32;
+
+__device__ __forceinline__ float ex2(float x) {          // one SFU op, ~2 ulp
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr int NCELL = 512, NXP = 128, NTHREADS = NCELL + NXP + 32;      // 16 cell warps, 4 x-producer warps, 1 MMA warp
+constexpr int MMA_WARP = (NCELL + NXP) / 32;
 constexpr int SLAB_BYTES = ROWS * 128;                 // one 64-wide fp16 K slab of the A operand
 constexpr int A_BYTES = 4 * SLAB_BYTES;                // [hi|lo][x|h]
 constexpr int B_SLAB_BYTES = 256 * 128;                // one K slab of the weight image (256 gate rows)
@@ -44,8 +51,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
     float* lnb = lng + 64;
     uint64_t* bars = reinterpret_cast<uint64_t*>(lnb + 64);
     uint64_t* a_ready = bars;                   // operand of the next step complete (cells: h, producers: x)
-    uint64_t* acc_full = bars + 1;              // gates of the current step complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    uint64_t* acc_full = bars + 1;              // [2] gate columns [0,128) / [128,256) of the current step complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -56,17 +63,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
 
     if (tid == 0) {
         mbar_init(a_ready, NCELL + NXP);
-        mbar_init(acc_full, 1);
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
         fence_barrier_init();
     }
-    if (warp == 12) tmem_alloc(tmem_slot, 256);
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 256);
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.Wimg);
         uint4* dst = reinterpret_cast<uint4*>(Bs);
         for (int i = tid; i < B_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
         uint4* az = reinterpret_cast<uint4*>(As);
         for (int i = tid; i < A_BYTES / 16; i += NTHREADS) az[i] = make_uint4(0, 0, 0, 0);      // h_{-1} = 0
-        for (int i = tid; i < 256; i += NTHREADS) sbias[i] = __ldg(a.bias + i);
+        for (int i = tid; i < 256; i += NTHREADS)       // image row order: quarter*64 + gate*16 + jj; gate 2 (g) feeds tanh
+            sbias[i] = __ldg(a.bias + i) * (((i >> 4) & 3) == 2 ? -2.f : -1.f) * 1.4426950408889634f;
         for (int i = tid; i < 2 * 64; i += NTHREADS) {
             const int bb = i >> 6, c = i & 63;
             float cs = 1.f, ch = 0.f, ca = 1.f;
@@ -86,46 +95,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < NCELL / 32) {
         // ======================================================================= cell warps
-        const int quad = warp & 3;
-        const int half = warp >> 2;
+        // thread = (sequence row, quarter of the hidden units): 16 units, gate columns quarter*64 + gate*16 + jj
+        const int quad = warp & 3;              // TMEM lane quadrant
+        const int qtr = warp >> 2;              // which 16 hidden units
         const int row = quad * 32 + lane;
         const int q = q0 + row;
         const bool valid = q < NQ;
         const int bq = valid ? q / a.F : 0;
         const int fq = valid ? q - bq * a.F : 0;
-        float* outp = a.out + (((size_t)bq * a.T) * a.F + fq) * H + half * 32;
+        float* outp = a.out + (((size_t)bq * a.T) * a.F + fq) * H + qtr * 16;
         const size_t ostep = (size_t)a.F * H;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qtr * 64);
         uint8_t* hrow_hi = a_slab(As, 0, 1) + row * 128;
         uint8_t* hrow_lo = a_slab(As, 1, 1) + row * 128;
-        float c[32];
+        float c[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) c[i] = 0.f;
+        for (int i = 0; i < 16; ++i) c[i] = 0.f;
         mbar_arrive(a_ready);                   // h_{-1} = 0 is in place
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+        long long t_wait = 0, t_cell = 0, t_fence = 0;
+        const long long t_start = dbg_on ? clock64() : 0;
+        constexpr float L2E = 1.4426950408889634f;
         for (int t = 0; t < a.T; ++t) {
-            mbar_wait(acc_full, (uint32_t)(t & 1));
+            const long long c0 = dbg_on ? clock64() : 0;
+            mbar_wait(&acc_full[qtr >> 1], (uint32_t)(t & 1));      // only this thread's half of the gate columns
+            const long long c1 = dbg_on ? clock64() : 0;
             tc_fence_after();
+            uint4 hst_hi[2], hst_lo[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {       // 8 hidden units at a time
+            for (int u = 0; u < 2; ++u) {       // 8 hidden units at a time
                 uint32_t gi[8], gf[8], gg[8], go[8];
-                tmem_ld8_nowait(taddr + 0 * 32 + u * 8, gi);
-                tmem_ld8_nowait(taddr + 1 * 32 + u * 8, gf);
-                tmem_ld8_nowait(taddr + 2 * 32 + u * 8, gg);
-                tmem_ld8_nowait(taddr + 3 * 32 + u * 8, go);
+                tmem_ld8_nowait(taddr + 0 * 16 + u * 8, gi);
+                tmem_ld8_nowait(taddr + 1 * 16 + u * 8, gf);
+                tmem_ld8_nowait(taddr + 2 * 16 + u * 8, gg);
+                tmem_ld8_nowait(taddr + 3 * 16 + u * 8, go);
                 tmem_wait_ld();
                 float hv[8];
-                const float* bi = sbias + half * 128 + u * 8;
+                const float* bi = sbias + qtr * 64 + u * 8;     // biases pre-scaled by -log2(e) (i,f,o) / -2 log2(e) (g)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float xi = __uint_as_float(gi[e]) + bi[e];
-                    const float xf = __uint_as_float(gf[e]) + bi[32 + e];
-                    const float xg = __uint_as_float(gg[e]) + bi[64 + e];
-                    const float xo = __uint_as_float(go[e]) + bi[96 + e];
-                    const float cn = sigmoid_f(xf) * c[u * 8 + e] + sigmoid_f(xi) * tanh_f(xg);
+                    // 7 SFU ops per unit instead of 10: the sigmoid / tanh quotients share their reciprocals
+                    //   c' = sig(f) c + sig(i) tanh(g) = [c (1+Ei)(1+Eg) + (1-Eg)(1+Ef)] / [(1+Ei)(1+Ef)(1+Eg)]
+                    //   h  = sig(o) tanh(c')          = (1-Ec) / [(1+Eo)(1+Ec)]
+                    // with Ei = e^-i, Ef = e^-f, Eg = e^-2g, Ec = e^-2c', Eo = e^-o.  The exponents are clamped from above
+                    // only (2^40: the functions are saturated to < 1e-12 there and the triple product stays < 2^127).
+                    const float Ei = ex2(fminf(fmaf(__uint_as_float(gi[e]), -L2E, bi[e]), 40.f));
+                    const float Ef = ex2(fminf(fmaf(__uint_as_float(gf[e]), -L2E, bi[16 + e]), 40.f));
+                    const float Eg = ex2(fminf(fmaf(__uint_as_float(gg[e]), -2.f * L2E, bi[32 + e]), 40.f));
+                    const float Eo = ex2(fminf(fmaf(__uint_as_float(go[e]), -L2E, bi[48 + e]), 40.f));
+                    const float A = 1.f + Ei, Bf = 1.f + Ef, G = 1.f + Eg;
+                    const float AG = A * G;
+                    const float cn = __fdividef(fmaf(c[u * 8 + e], AG, (1.f - Eg) * Bf), AG * Bf);
                     c[u * 8 + e] = cn;
-                    hv[e] = sigmoid_f(xo) * tanh_f(cn);
+                    const float Ec = ex2(fminf(cn * (-2.f * L2E), 40.f));
+                    hv[e] = __fdividef(1.f - Ec, (1.f + Eo) * (1.f + Ec));
                 }
                 if (valid) {
                     float4* o4 = reinterpret_cast<float4*>(outp + (size_t)t * ostep + u * 8);
@@ -136,15 +161,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                 hi.x = pack_h2(hv[0], hv[1]); hi.y = pack_h2(hv[2], hv[3]); hi.z = pack_h2(hv[4], hv[5]); hi.w = pack_h2(hv[6], hv[7]);
                 lo.x = pack_lo_h2(hv[0], hv[1], hi.x); lo.y = pack_lo_h2(hv[2], hv[3], hi.y);
                 lo.z = pack_lo_h2(hv[4], hv[5], hi.z); lo.w = pack_lo_h2(hv[6], hv[7], hi.w);
-                const int chunk = ((half * 4 + u) ^ (row & 7)) << 4;
-                *reinterpret_cast<uint4*>(hrow_hi + chunk) = hi;
-                *reinterpret_cast<uint4*>(hrow_lo + chunk) = lo;
+                hst_hi[u] = hi;
+                hst_lo[u] = lo;
             }
+            // h_t overwrites the operand that the second half's MMAs may still be reading: wait for them, then publish
+            mbar_wait(&acc_full[1], (uint32_t)(t & 1));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int chunk = ((qtr * 2 + u) ^ (row & 7)) << 4;
+                *reinterpret_cast<uint4*>(hrow_hi + chunk) = hst_hi[u];
+                *reinterpret_cast<uint4*>(hrow_lo + chunk) = hst_lo[u];
+            }
+            const long long c2 = dbg_on ? clock64() : 0;
             tc_fence_before();
             fence_proxy_async();
             if (t + 1 < a.T) mbar_arrive(a_ready);
+            if (dbg_on) { t_wait += c1 - c0; t_cell += c2 - c1; t_fence += clock64() - c2; }
         }
-    } else if (warp < 12) {
+        if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wait; a.dbg[2] = t_cell; a.dbg[3] = t_fence; a.dbg[4] = a.T; }
+    } else if (warp < MMA_WARP) {
         // ======================================================================= x producers (one thread per row)
         const int row = tid - NCELL;
         const int q = q0 + row;
@@ -210,7 +245,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         mbar_arrive(a_ready);
         for (int t = 0; t < a.T; ++t) {
             if (t + 1 < a.T) load(t + 1);       // in flight while the tensor core and the cell warps work on step t
-            mbar_wait(acc_full, (uint32_t)(t & 1));      // MMA(t) has consumed x_t
+            mbar_wait(&acc_full[1], (uint32_t)(t & 1));  // every MMA of step t has consumed x_t
             if (t + 1 < a.T) {
                 publish();
                 mbar_arrive(a_ready);
@@ -218,33 +253,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         }
     } else {
         // ======================================================================= MMA issuer
-        const uint32_t idesc = make_idesc(256);
+        const uint32_t idesc = make_idesc(128);
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        long long t_wait = 0;
         for (int t = 0; t < a.T; ++t) {
+            const long long c0 = dbg_on ? clock64() : 0;
             mbar_wait(a_ready, (uint32_t)(t & 1));
+            if (dbg_on) t_wait += clock64() - c0;
             tc_fence_after();
             if (lane == 0) {
-                // pass 0: A_hi B_hi, pass 1: A_lo B_hi, pass 2: A_hi B_lo
+                // two column halves (N = 128 each), committed separately so that half of the cell warps start early;
+                // per half: pass 0: A_hi B_hi, pass 1: A_lo B_hi, pass 2: A_hi B_lo
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const int ahl = pass == 1 ? 1 : 0;
-                    const int bhl = pass == 2 ? 1 : 0;
+                for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-                    for (int slab = 0; slab < 2; ++slab) {
-                        const uint32_t aa = smem_u32(a_slab(As, ahl, slab));
-                        const uint32_t bb = smem_u32(Bs + (bhl * 2 + slab) * B_SLAB_BYTES);
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const int ahl = pass == 1 ? 1 : 0;
+                        const int bhl = pass == 2 ? 1 : 0;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(tmem_base, make_desc(aa + k * 32), make_desc(bb + k * 32), idesc, (pass | slab | k) ? 1u : 0u);
+                        for (int slab = 0; slab < 2; ++slab) {
+                            const uint32_t aa = smem_u32(a_slab(As, ahl, slab));
+                            const uint32_t bb = smem_u32(Bs + (bhl * 2 + slab) * B_SLAB_BYTES + hf * 128 * 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16(tmem_base + hf * 128, make_desc(aa + k * 32), make_desc(bb + k * 32), idesc, (pass | slab | k) ? 1u : 0u);
+                        }
                     }
+                    umma_commit(&acc_full[hf]);
                 }
-                umma_commit(acc_full);
             }
             __syncwarp();
         }
+        if (dbg_on) a.dbg[5] = t_wait;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem_base, 256);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace

@@ -637,7 +637,7 @@ struct Packer {
                         blob[m->off_rnn[r][2] + (size_t)j * 4 + g] = P(m->rnn[r][2])[g * H + j] + P(m->rnn[r][3])[g * H + j];
                     }
             }
-            // tcgen05 LSTM: image row n = half*128 + gate*32 + jj  <->  torch row gate*64 + (half*32 + jj);
+            // tcgen05 LSTM: image row n = quarter*64 + gate*16 + jj  <->  torch row gate*64 + (quarter*16 + jj);
             // K slab 0 = W_ih (input channels), slab 1 = W_hh
             m->rnn_umma_ok = c.embed_dim == 64;
             if (m->rnn_umma_ok) {
@@ -646,8 +646,8 @@ struct Packer {
                     m->off_rnn_ubias[r] = alloc(256);
                     __half* img = reinterpret_cast<__half*>(blob.data() + m->off_rnn_img[r]);
                     for (int n = 0; n < 256; ++n) {
-                        const int half_ = n >> 7, g = (n >> 5) & 3, jj = n & 31;
-                        const int row = g * H + half_ * 32 + jj;
+                        const int qtr_ = n >> 6, g = (n >> 4) & 3, jj = n & 15;
+                        const int row = g * H + qtr_ * 16 + jj;
                         blob[m->off_rnn_ubias[r] + n] = P(m->rnn[r][2])[row] + P(m->rnn[r][3])[row];
                         for (int slab = 0; slab < 2; ++slab)
                             for (int k = 0; k < 64; ++k) {
@@ -1092,6 +1092,7 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
                 a.out = h[l].data;
                 if (m->opt_umma && m->rnn_umma_ok) {
                     LstmArgs u = a;
+                    if (m->opt_dbg_launch == -100 - l && m->dbg_buf) u.dbg = m->dbg_buf;
                     u.Wimg = cx.W(m->off_rnn_img[l]);
                     u.bias = cx.W(m->off_rnn_ubias[l]);
                     if (lstm_umma_supported(u)) {
