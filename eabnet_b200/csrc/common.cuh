@@ -208,9 +208,18 @@ struct PlaneConvArgs {
     unsigned int p_magic;        // floor(2^32 / P) + 1  (division by P in the producers)
     int nbuf;                    // plane double-buffering (1 or 2), chosen by the launcher from the smem budget
     unsigned long long* dbg;     // optional [16] cycle counters of CTA 0 (diagnostics)
+    // "staged" variant (conv_tma_kernel): the planes were written to HBM by stage_kernel as fp16 images
+    // np[(plane * nslab + slab) * npb + hl] : [B][np_rows][64] halves, row = np_front + t*P + col, 128B-swizzled by row & 7
+    const void* np[16];
+    int np_rows, np_front;
 };
 bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
 int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);
+// staged variant: geometry helpers + the two launches (stage = normalise + fp16 + layout, conv = TMA-fed GEMM)
+int staged_rows(const PlaneConvArgs& a, int* front);    // rows per batch item of a staged plane array (multiple of 8)
+bool staged_conv_supported(const PlaneConvArgs& a);
+int launch_stage(const PlaneConvArgs& a, cudaStream_t st);
+int launch_conv_staged(PlaneConvArgs a, cudaStream_t st);
 
 struct CombineArgs {
     ConvSrc src[3];

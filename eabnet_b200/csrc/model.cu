@@ -187,7 +187,8 @@ struct eab_model {
     int opt_umma = 1;             // tcgen05 path for eligible layers
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
-    int opt_plane = 1;            // "stage once, shift by descriptor" kernel for multi-tap layers
+    int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
+    int opt_plane = 1;            // "stage once, shift by descriptor" kernel with fused producers (fallback)
     int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
     int umma_launch_idx = 0;
     unsigned long long* dbg_buf = nullptr;
@@ -747,7 +748,7 @@ Xform xf_after(Ctx& cx, const NormAct& na, double* stats, int count, int prelu_p
 }
 
 // Re-express a per-tap gather launch as a "stage once" launch (conv_plane.cu); false if the shape does not qualify.
-bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p) {
+bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p, int force_P = 0) {
     if (u.wide) return false;
     memset(p, 0, sizeof(*p));
     p->nsrc = u.nsrc;
@@ -760,13 +761,13 @@ bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p) {
         p->nplanes = 2;
         p->plane_cols[0] = (u.Fin + 1) / 2; p->plane_cols[1] = u.Fin / 2;
         p->col_stride = 2; p->col_off[0] = 0; p->col_off[1] = 1;
-        p->P = std::max(u.E + max_df / 2, p->plane_cols[0]);
+        p->P = std::max(std::max(u.E + max_df / 2, p->plane_cols[0]), force_P);
     } else if (u.in_stride == 1) {
         if (max_df > 0) return false;
         p->nplanes = 1;
         p->plane_cols[0] = u.Fin; p->plane_cols[1] = 0;
         p->col_stride = 1; p->col_off[0] = 0; p->col_off[1] = 0;
-        p->P = std::max(u.E, u.Fin - min_df);          // the pad columns [Fin, P) absorb the negative column offsets
+        p->P = std::max(std::max(u.E, u.Fin - min_df), force_P);      // the pad columns [Fin, P) absorb the negative column offsets
     } else {
         return false;
     }
@@ -798,6 +799,51 @@ int launch_tensor_conv(eab_model* m, const UmmaConvArgs& u, cudaStream_t st) {
     return launch_conv_umma(u, st);
 }
 
+// Launch the 1-4 tensor-core variants of one layer (output parities of a transposed conv, column splits of a wide
+// 1x1) that read the same inputs.  Preferred path: stage the normalised fp16 planes ONCE (stage_kernel) and run the
+// TMA-fed GEMM per variant; otherwise the fused-producer kernels.  Also runs in planning mode (allocations only).
+int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
+    eab_model* m = cx.m;
+    if (m->opt_staged && !us[0].wide && n <= 4) {
+        PlaneConvArgs p[4];
+        bool ok = true;
+        int P = 0;
+        for (int i = 0; i < n; ++i) { ok = ok && to_plane_args(us[i], &p[i]); if (ok) P = std::max(P, p[i].P); }
+        if (ok)
+            for (int i = 0; i < n; ++i)
+                if (p[i].P != P) ok = ok && to_plane_args(us[i], &p[i], P);
+        if (ok)
+            for (int i = 1; i < n; ++i)
+                ok = ok && p[i].nplanes == p[0].nplanes && p[i].plane_cols[0] == p[0].plane_cols[0] &&
+                     p[i].plane_cols[1] == p[0].plane_cols[1] && p[i].nslab == p[0].nslab && p[i].npass == p[0].npass &&
+                     p[i].tiles_per_b == p[0].tiles_per_b;
+        if (ok) {
+            PlaneConvArgs ps = p[0];
+            for (int i = 1; i < n; ++i) { ps.back = std::max(ps.back, p[i].back); ps.fwd = std::max(ps.fwd, p[i].fwd); }
+            ok = staged_conv_supported(ps);
+            for (int i = 0; i < n; ++i) ok = ok && staged_conv_supported(p[i]);
+            if (ok) {
+                int front = 0;
+                const int rows = staged_rows(ps, &front);
+                const int nimg = ps.nplanes * ps.nslab * (ps.npass == 3 ? 2 : 1);
+                ps.np_rows = rows; ps.np_front = front;
+                for (int k = 0; k < nimg; ++k) ps.np[k] = cx.alloc_act((size_t)cx.B * rows * 32);     // 128 B per row
+                if (cx.dry) return 0;
+                EAB_TRY(launch_stage(ps, cx.st));
+                for (int i = 0; i < n; ++i) {
+                    p[i].np_rows = rows; p[i].np_front = front;
+                    for (int k = 0; k < nimg; ++k) p[i].np[k] = ps.np[k];
+                    EAB_TRY(launch_conv_staged(p[i], cx.st));
+                }
+                return 0;
+            }
+        }
+    }
+    if (cx.dry) return 0;
+    for (int i = 0; i < n; ++i) EAB_TRY(launch_tensor_conv(m, us[i], cx.st));
+    return 0;
+}
+
 // one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
 int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out) {
     const int Fin = srcs[0].F;
@@ -815,10 +861,11 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out)
     const bool in_stats = L.na.has_norm && cx.m->cfg.norm_type == 0;
     double* stats = in_stats ? cx.alloc_stats(L.cout) : nullptr;
     out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
-    if (cx.dry) return 0;
-    for (int v = 0; v < L.nvar; ++v) {
-        if (cx.m->opt_umma && L.umma_ok) {
-            UmmaConvArgs u;
+    if (cx.m->opt_umma && L.umma_ok) {
+        UmmaConvArgs us[2];
+        bool all_ok = true;
+        for (int v = 0; v < L.nvar; ++v) {
+            UmmaConvArgs& u = us[v];
             memset(&u, 0, sizeof(u));
             u.nsrc = nsrc;
             for (int i = 0; i < nsrc; ++i) { u.src[i].x = srcs[i].data; u.src[i].C = srcs[i].C; u.src[i].xf = srcs[i].xf; }
@@ -834,12 +881,12 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out)
             u.out = out->data; u.out_ld = L.cout; u.out_coff = 0;
             if (stats) { u.nstats = 1; u.stats[0] = stats; }
             u.tiles_per_b = (cx.T * u.E + 127) / 128;
-            if (umma_conv_supported(u)) {
-                if (cx.m->umma_launch_idx++ == cx.m->opt_dbg_launch && cx.m->dbg_buf) u.dbg = cx.m->dbg_buf;
-                EAB_TRY(launch_tensor_conv(cx.m, u, cx.st));
-                continue;
-            }
+            all_ok = all_ok && umma_conv_supported(u);
         }
+        if (all_ok) return run_tensor_convs(cx, us, L.nvar);
+    }
+    if (cx.dry) return 0;
+    for (int v = 0; v < L.nvar; ++v) {
         ConvArgs a;
         memset(&a, 0, sizeof(a));
         a.nsrc = nsrc;
@@ -919,10 +966,10 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
     out->C = use_umma ? uw->ld : Cout;          // the tcgen05 path may pad the channel count (e.g. 18 -> 32, zeros)
     out->xf = xform_identity();
     out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * out->C);
-    if (cx.dry) return 0;
     if (use_umma) {
+        UmmaConvArgs us[4];
         for (int sp = 0; sp < uw->nsplit; ++sp) {
-            UmmaConvArgs u;
+            UmmaConvArgs& u = us[sp];
             memset(&u, 0, sizeof(u));
             u.nsrc = nsrc;
             int cin = 0;
@@ -943,10 +990,10 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
             for (int i = 0; i < nstats; ++i) { u.stats[i] = stats[i]; u.stat_alpha[i] = stat_alpha[i]; }
             u.tiles_per_b = (cx.T * u.E + 127) / 128;
             if (!umma_conv_supported(u)) return fail("internal: pointwise layer rejected by the tcgen05 path");
-            EAB_TRY(launch_tensor_conv(cx.m, u, cx.st));
         }
-        return 0;
+        return run_tensor_convs(cx, us, uw->nsplit);
     }
+    if (cx.dry) return 0;
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.nsrc = nsrc;
@@ -1318,6 +1365,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     const std::string n(name);
     if (n == "umma") m->opt_umma = value != 0;
     else if (n == "plane") m->opt_plane = value != 0;
+    else if (n == "staged") m->opt_staged = value != 0;
     else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
     else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
     else if (n == "dbg_launch") {
