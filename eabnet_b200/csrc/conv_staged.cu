@@ -193,13 +193,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         const uint32_t idesc = make_idesc(a.N);
         int buf = 0, stage = 0, acc = 0;
         uint32_t bphase = 0, sphase = 0, aphase = 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        long long t_wacc = 0, t_wplane = 0, t_wb = 0;
+        const long long t_start = dbg_on ? clock64() : 0;
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
             const int rs = a.np_front + row0 - a.back;
             const int lead = rs & 7;                             // rows between the copy start and the tile's first plane row
+            const long long w0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_empty[acc], aphase ^ 1);
+            const long long w1 = dbg_on ? clock64() : 0;
             mbar_wait(&plane_full[buf], bphase);
+            if (dbg_on) { t_wacc += w1 - w0; t_wplane += clock64() - w1; }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.N);
             const uint32_t pbase = smem_u32(planes + buf * pl.buf_bytes);
@@ -209,7 +215,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                 for (int slab = 0; slab < a.nslab; ++slab) {
                     const uint32_t a_hi = pbase + (uint32_t)(((a.tap_plane[tap] * a.nslab + slab) * npb) * pl.plane_bytes + arow * 128);
                     for (int pass = 0; pass < a.npass; ++pass, ++unit) {
+                        const long long w2 = dbg_on ? clock64() : 0;
                         mbar_wait(&b_full[stage], sphase);
+                        if (dbg_on) t_wb += clock64() - w2;
                         tc_fence_after();
                         if (lane == 0) {
                             const uint32_t a_addr = a_hi + (pass == 1 ? (uint32_t)pl.plane_bytes : 0u);
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             if (++acc == 2) { acc = 0; aphase ^= 1; }
             if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
+        if (dbg_on) { a.dbg[4] = clock64() - t_start; a.dbg[5] = t_wacc; a.dbg[6] = t_wplane; a.dbg[7] = t_wb; a.dbg[2] = tile_end - tile_begin; a.dbg[0] = clock64() - t_start; }
     } else if (warp == 2) {
         // =========================================================================== B (weight) loader
         int stage = 0;
@@ -259,12 +268,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         const bool gated = a.gate_off > 0;
         const int ld = pl.stg_ld;
         const int cper = a.Cout >> 1;           // channels per half (multiple of 8)
+        const bool need_stage = a.resid != nullptr || a.nstats > 0;     // smem staging only for the residual / statistics passes
         int acc = 0;
         uint32_t aphase = 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && et == 0;
+        long long t_wfull = 0, t_tmem = 0, t_store = 0, t_stats = 0;
+        const long long t_start = dbg_on ? clock64() : 0;
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
             bool row_valid;
+            long long my_off;
             {
                 const int r = row0 + row;
                 long long off = -1;
@@ -275,8 +289,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                 }
                 if (chalf == 0) rowoff[row] = off;
                 row_valid = off >= 0;
+                my_off = off;
             }
+            const long long e0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_full[acc], aphase);
+            const long long e1 = dbg_on ? clock64() : 0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.N);
             for (int c0 = chalf * cper; c0 < (chalf + 1) * cper; c0 += 8) {
@@ -301,24 +318,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
-                if (!row_valid) {               // dummy / ragged rows contribute exact zeros to the statistics
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                if (!a.resid && row_valid) {    // full 32-byte sectors straight from registers: no smem round trip, no proxy fence
+                    float4* o4 = reinterpret_cast<float4*>(a.out + my_off + c0);
+                    o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    o4[1] = make_float4(v[4], v[5], v[6], v[7]);
                 }
-                *reinterpret_cast<float4*>(stg + row * ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(stg + row * ld + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                if (need_stage) {
+                    if (!row_valid) {           // dummy / ragged rows contribute exact zeros to the statistics
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                    }
+                    *reinterpret_cast<float4*>(stg + row * ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(stg + row * ld + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
             named_bar_sync(2, NEPI);            // staging tile + row offsets complete
+            const long long e2 = dbg_on ? clock64() : 0;
             if (!a.resid) {
-                // one bulk shared -> global copy per valid row (Cout * 4 bytes)
-                fence_proxy_async();
-                if (chalf == 0 && row_valid)
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.out + rowoff[row]),
-                                 "r"(smem_u32(stg + row * ld)), "r"((uint32_t)(a.Cout * 4))
-                                 : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                // rows were already stored from registers
             } else {
                 const int tpr = a.Cout >> 2;
                 const int rows_per_it = NEPI / tpr;
@@ -333,6 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                     *reinterpret_cast<float4*>(a.out + off + cq) = o;
                 }
             }
+            const long long e3 = dbg_on ? clock64() : 0;
             if (a.nstats) {
                 if (a.resid) named_bar_sync(2, NEPI);
                 // (statistic, channel) x row-quarter per thread: branch-free column sums over the staged tile
@@ -358,10 +378,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                     atomicAdd(dstp + 1, (double)(q0 + q1));
                 }
             }
-            if (!a.resid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             named_bar_sync(2, NEPI);            // staging free for the next tile
+            if (dbg_on) { const long long e4 = clock64(); t_wfull += e1 - e0; t_tmem += e2 - e1; t_store += e3 - e2; t_stats += e4 - e3; }
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
+        if (dbg_on) { a.dbg[8] = clock64() - t_start; a.dbg[9] = t_wfull; a.dbg[10] = t_tmem; a.dbg[11] = t_store; a.dbg[12] = t_stats; }
     }
 
     tc_fence_before();

@@ -831,6 +831,7 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
                 if (cx.dry) return 0;
                 EAB_TRY(launch_stage(ps, cx.st));
                 for (int i = 0; i < n; ++i) {
+                    if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) p[i].dbg = m->dbg_buf;
                     p[i].np_rows = rows; p[i].np_front = front;
                     for (int k = 0; k < nimg; ++k) p[i].np[k] = ps.np[k];
                     EAB_TRY(launch_conv_staged(p[i], cx.st));

@@ -18,8 +18,6 @@ with torch.no_grad():
         net._native.lib.eab_debug_counters(net._native.h, C.byref(buf))
         d = dict(zip(names, list(buf)))
         n = max(d["tiles"], 1)
-        raw = list(buf)
-        print("   producer per tile: items-loop %.0f  prefetch-issue %.0f  fence+arrive %.0f" % (raw[13] / n, raw[15] / n, raw[14] / n))
         print("launch", idx, "tiles", d["tiles"], "rows/buf", d["rows_total"], "| per tile: total %.0f | prod busy %.0f wait %.0f | mma wait acc %.0f plane %.0f b %.0f | epi wait %.0f tmem %.0f store %.0f stats %.0f" % (
             d["prod_total"] / n, (d["prod_total"] - d["prod_wait_empty"]) / n, d["prod_wait_empty"] / n, d["mma_wait_acc"] / n,
             d["mma_wait_plane"] / n, d["mma_wait_b"] / n, d["epi_wait_full"] / n, d["epi_tmem"] / n, d["epi_store"] / n, d["epi_stats"] / n))
