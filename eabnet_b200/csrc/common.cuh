@@ -64,6 +64,27 @@ static inline Xform xform_identity() {
     return x;
 }
 
+// Programmatic dependent launch: every kernel is launched with the stream-serialisation attribute, calls pdl_trigger()
+// first (its successor may be scheduled onto SMs as they free up and run its data-independent prologue) and pdl_wait()
+// before it reads anything its predecessor wrote or writes anything at all.
+extern bool g_use_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 // coefficients for channel c of batch b (called once per CTA per channel, not per element)
 __device__ __forceinline__ void xform_coeffs(const Xform& xf, int b, int C, int c, float& s, float& h, float& a) {

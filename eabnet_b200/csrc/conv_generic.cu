@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_generic_kernel(const ConvArgs a
     float* Bs = As + 2 * KC * TM;                // [2][KC][N]
     float* coef = Bs + 2 * KC * N;               // [3][Ctot]
 
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     const int rows_per_b = a.T * a.E;
@@ -317,7 +319,7 @@ int launch_inst(const ConvArgs& a, cudaStream_t st) {
     ProfScope ps("conv_generic", 2.0 * pos * a.ntaps * Ctot * ncol * a.algo_frac,
                  4.0 * (pos * a.in_stride * Ctot / (a.out_stride > 1 ? 2.0 : 1.0) + pos * a.Cout * (a.resid ? 2 : 1) +
                         (double)a.ntaps * Ctot * ncol), st);
-    conv_generic_kernel<NV, RPT, GATED><<<grid, NTHREADS, smem, st>>>(a);
+    EAB_CUDA(launch_k(conv_generic_kernel<NV, RPT, GATED>, grid, dim3(NTHREADS), smem, st, a));
     EAB_LAUNCH_CHECK("conv_generic_kernel");
     return 0;
 }

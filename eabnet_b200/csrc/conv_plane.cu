@@ -96,8 +96,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
         for (int i = 0; i < NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         fence_barrier_init();
     }
+    pdl_trigger();
     if (warp == NPROD / 32) tmem_alloc(tmem_slot, tmem_cols);
     for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+    pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -498,7 +500,7 @@ int launch_conv_plane(PlaneConvArgs a, cudaStream_t st) {
     for (int i = 0; i < a.nsrc; ++i) kreal += a.src[i].C;
     ProfScope ps("conv_plane", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
                  4.0 * ((double)a.B * a.T * a.Fin * kreal + pos * a.Cout * (a.resid ? 2 : 1) + (double)a.ntaps * kreal * a.N), st);
-    conv_plane_kernel<<<grid, NTHREADS, pl.total, st>>>(a);
+    EAB_CUDA(launch_k(conv_plane_kernel, dim3(grid), dim3(NTHREADS), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_plane_kernel");
     return 0;
 }

@@ -38,6 +38,8 @@ inline int ceil8(int x) { return (x + 7) & ~7; }
 // grid (row blocks, nplanes*nslab, B), 256 threads: 8 threads per plane row (8 channels = one 16-byte fp16 chunk each)
 __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
     __shared__ float coef[3 * 64];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.z;
     const int ps = blockIdx.y;
     const int plane = ps / a.nslab;
@@ -154,8 +156,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
         fence_barrier_init();
     }
+    pdl_trigger();
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+    pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -421,7 +425,7 @@ int launch_stage(const PlaneConvArgs& a_in, cudaStream_t st) {
     for (int i = 0; i < a.nsrc; ++i) cin += a.src[i].C;
     const double elems = (double)a.B * a.T * a.Fin * cin;
     ProfScope ps("stage", 4.0 * elems, elems * 4.0 + (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1), st);
-    stage_kernel<<<grid, 256, 0, st>>>(a);
+    EAB_CUDA(launch_k(stage_kernel, grid, dim3(256), (size_t)0, st, a));
     EAB_LAUNCH_CHECK("stage_kernel");
     return 0;
 }
@@ -452,7 +456,7 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
                  (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1) + 4.0 * pos * a.Cout * (a.resid ? 2 : 1) +
                      4.0 * a.ntaps * kreal * a.N,
                  st);
-    conv_tma_kernel<<<grid, NTHREADS, pl.total, st>>>(a);
+    EAB_CUDA(launch_k(conv_tma_kernel, dim3(grid), dim3(NTHREADS), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_tma_kernel");
     return 0;
 }

@@ -94,8 +94,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
         fence_barrier_init();
     }
+    pdl_trigger();
     if (warp == NPROD / 32) tmem_alloc(tmem_slot, tmem_cols);
     for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+    pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -482,8 +484,8 @@ int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
                  4.0 * (pos * a.in_stride * kreal / (a.out_stride > 1 ? 2.0 : 1.0) / (a.wide ? (double)a.kwidth / a.src[0].C / 2.0 : 1.0) +
                         pos * a.Cout * (a.resid ? 2 : 1) + (double)a.ntaps * kreal * a.N),
                  st);
-    if (a.wide) conv_umma_kernel<true><<<grid, NTHREADS, sp.total, st>>>(a);
-    else conv_umma_kernel<false><<<grid, NTHREADS, sp.total, st>>>(a);
+    if (a.wide) EAB_CUDA(launch_k(conv_umma_kernel<true>, dim3(grid), dim3(NTHREADS), (size_t)sp.total, st, a));
+    else EAB_CUDA(launch_k(conv_umma_kernel<false>, dim3(grid), dim3(NTHREADS), (size_t)sp.total, st, a));
     EAB_LAUNCH_CHECK("conv_umma_kernel");
     return 0;
 }

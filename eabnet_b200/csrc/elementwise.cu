@@ -9,6 +9,8 @@ namespace {
 // out[b,p,c] = sum_s xform_s(src_s[b,p,c]);  grid (chunks, B); 128-bit accesses when C % 4 == 0
 __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
     extern __shared__ float coef[];                  // [nsrc][3][C]
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     const int C = a.C;
     for (int i = threadIdx.x; i < a.nsrc * C; i += blockDim.x) {
@@ -52,6 +54,8 @@ __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
 
 // mimo: y[b,:,t,f] = sum_m w[b,t,f,m] * x[b,t,f,m]  (complex);  one thread per (b,t,f)
 __global__ void __launch_bounds__(256) beam_mimo_kernel(const BeamArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const size_t n = (size_t)a.B * a.T * a.F;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -72,6 +76,8 @@ __global__ void __launch_bounds__(256) beam_mimo_kernel(const BeamArgs a) {
 // miso: the reference multiplies by mic 0 and then sums its last axis, which is F (EaBNet.py:123-124),
 // so the result is [B,2,T].  One warp per (b,t).
 __global__ void __launch_bounds__(256) beam_miso_kernel(const BeamArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.B * a.T) return;
@@ -107,7 +113,7 @@ int launch_combine(const CombineArgs& a, cudaStream_t st) {
     if (blocks > 148 * 8) blocks = 148 * 8;
     const size_t smem = (size_t)a.nsrc * 3 * a.C * sizeof(float);
     ProfScope ps("combine", (double)a.nsrc * a.B * per_b, 4.0 * (a.nsrc + 1) * a.B * per_b, st);
-    combine_kernel<<<dim3(blocks, a.B), 256, smem, st>>>(a);
+    EAB_CUDA(launch_k(combine_kernel, dim3(blocks, a.B), dim3(256), smem, st, a));
     EAB_LAUNCH_CHECK("combine_kernel");
     return 0;
 }
@@ -118,11 +124,11 @@ int launch_beam(const BeamArgs& a, cudaStream_t st) {
     ProfScope ps("beam", 4.0 * nw * npos, 4.0 * npos * (nw + 2.0 * a.M + 2), st);
     if (a.miso) {
         const size_t warps = (size_t)a.B * a.T;
-        beam_miso_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a);
+        EAB_CUDA(launch_k(beam_miso_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), (size_t)0, st, a));
         EAB_LAUNCH_CHECK("beam_miso_kernel");
     } else {
         const size_t n = (size_t)a.B * a.T * a.F;
-        beam_mimo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+        EAB_CUDA(launch_k(beam_mimo_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, st, a));
         EAB_LAUNCH_CHECK("beam_mimo_kernel");
     }
     return 0;

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const LstmArgs a) {
     float* lng = coef + 2 * 3 * E;                          // [E]
     float* lnb = lng + E;                                   // [E]
 
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int j = tid & 63;
     const int sg = tid >> 6;
@@ -211,7 +213,7 @@ int launch_inst(const LstmArgs& a, cudaStream_t st) {
     }
     const int NQ = a.B * a.F;
     ProfScope ps("lstm", 2.0 * NQ * a.T * (E + H) * 4.0 * H, 4.0 * NQ * a.T * (E + H), st);
-    lstm_kernel<SPT, E><<<(NQ + S - 1) / S, 256, smem, st>>>(a);
+    EAB_CUDA(launch_k(lstm_kernel<SPT, E>, dim3((NQ + S - 1) / S), dim3(256), smem, st, a));
     EAB_LAUNCH_CHECK("lstm_kernel");
     return 0;
 }

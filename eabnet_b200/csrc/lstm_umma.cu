@@ -67,11 +67,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         mbar_init(&acc_full[1], 1);
         fence_barrier_init();
     }
+    pdl_trigger();
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 256);
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.Wimg);
         uint4* dst = reinterpret_cast<uint4*>(Bs);
-        for (int i = tid; i < B_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < B_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);     // static weights: before the wait
+        pdl_wait();
         uint4* az = reinterpret_cast<uint4*>(As);
         for (int i = tid; i < A_BYTES / 16; i += NTHREADS) az[i] = make_uint4(0, 0, 0, 0);      // h_{-1} = 0
         for (int i = tid; i < 256; i += NTHREADS)       // image row order: quarter*64 + gate*16 + jj; gate 2 (g) feeds tanh
@@ -304,7 +306,7 @@ int launch_lstm_umma(const LstmArgs& a, cudaStream_t st) {
     }
     const int NQ = a.B * a.F;
     ProfScope ps("lstm_umma", 2.0 * NQ * a.T * (64 + H) * 4.0 * H, 4.0 * NQ * a.T * (64 + H), st);
-    lstm_umma_kernel<<<(NQ + ROWS - 1) / ROWS, NTHREADS, SMEM_BYTES, st>>>(a);
+    EAB_CUDA(launch_k(lstm_umma_kernel, dim3((NQ + ROWS - 1) / ROWS), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a));
     EAB_LAUNCH_CHECK("lstm_umma_kernel");
     return 0;
 }

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(THREADS) stft_kernel(const float* __restrict__
                                                        const float* __restrict__ tab, const float* __restrict__ win,
                                                        int B, int M, int L, int T) {
     extern __shared__ __align__(16) float dsm[];
+    pdl_trigger();
+    pdl_wait();
     float* Aev = dsm;                                   // [NF][RB]
     float* Aod = Aev + NF * RB;                         // [NF][RB]
     float2* Xs = reinterpret_cast<float2*>(Aod + NF * RB);   // [RB][NF]
@@ -180,6 +182,8 @@ __global__ void __launch_bounds__(THREADS) istft_kernel(const float* __restrict_
                                                         const float* __restrict__ tab, const float* __restrict__ win,
                                                         const float* __restrict__ ienv, int B, int T) {
     extern __shared__ __align__(16) float dsm[];
+    pdl_trigger();
+    pdl_wait();
     float* Are = dsm;                    // [NF][RB]
     float* Aim = Are + NF * RB;          // [NF][RB]
     float* PQ = Aim + NF * RB;           // [frame][col]: P[n] (col<161), Q[n] (col>=161)
@@ -239,7 +243,7 @@ int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_
         configured = true;
     }
     ProfScope ps("stft", 2.0 * NF * NCOL * (double)B * M * T, 4.0 * ((double)B * M * L + (double)B * T * NF * M * 2), st);
-    stft_kernel<<<dim3((T + FR - 1) / FR, B), THREADS, kSmemBytes, st>>>(wave, spec, t->fwd, t->win, B, M, L, T);
+    EAB_CUDA(launch_k(stft_kernel, dim3((T + FR - 1) / FR, B), dim3(THREADS), kSmemBytes, st, wave, spec, (const float*)t->fwd, (const float*)t->win, B, M, L, T));
     EAB_LAUNCH_CHECK("stft_kernel");
     return 0;
 }
@@ -255,7 +259,7 @@ int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st) 
         configured = true;
     }
     ProfScope ps("istft", 2.0 * NF * NCOL * (double)B * T, 4.0 * ((double)B * 2 * T * NF + (double)B * HOP * (T - 1)), st);
-    istft_kernel<<<dim3((T - 1 + IFR - 2) / (IFR - 1), B), THREADS, kSmemBytes, st>>>(spec, wave, t->inv, t->win, t->ienv, B, T);
+    EAB_CUDA(launch_k(istft_kernel, dim3((T - 1 + IFR - 2) / (IFR - 1), B), dim3(THREADS), kSmemBytes, st, spec, wave, (const float*)t->inv, (const float*)t->win, (const float*)t->ienv, B, T));
     EAB_LAUNCH_CHECK("istft_kernel");
     return 0;
 }
