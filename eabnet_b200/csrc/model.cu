@@ -719,12 +719,18 @@ struct Ctx {
     int B, T;
     cudaStream_t st;
 
+    size_t act_peak = 0;
     float* alloc_act(size_t floats) {
         const size_t bytes = (floats * sizeof(float) + 255) / 256 * 256;
         float* p = reinterpret_cast<float*>(base + act_off);
         act_off += bytes;
+        if (act_off > act_peak) act_peak = act_off;
         return p;
     }
+    // scoped reuse: everything allocated after mark() is dead at release() (single stream => later kernels that
+    // overwrite the region are ordered after the kernels that read it)
+    size_t mark() const { return act_off; }
+    void release(size_t m) { act_off = m; }
     double* alloc_stats(int C) {
         const size_t bytes = ((size_t)B * C * 2 * sizeof(double) + 255) / 256 * 256;
         double* p = reinterpret_cast<double*>(base + stats_off);
@@ -828,7 +834,9 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
                 const int rows = staged_rows(ps, &front);
                 const int nimg = ps.nplanes * ps.nslab * (ps.npass == 3 ? 2 : 1);
                 ps.np_rows = rows; ps.np_front = front;
+                const size_t scratch = cx.mark();           // the staged planes die with this layer
                 for (int k = 0; k < nimg; ++k) ps.np[k] = cx.alloc_act((size_t)cx.B * rows * 32);     // 128 B per row
+                cx.release(scratch);
                 if (cx.dry) return 0;
                 EAB_TRY(launch_stage(ps, cx.st));
                 for (int i = 0; i < n; ++i) {
@@ -910,11 +918,17 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out)
     return 0;
 }
 
+int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out);
 int run_combine(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
     out->F = srcs[0].F;
     out->C = srcs[0].C;
     out->xf = xform_identity();
     out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * out->C);
+    return run_combine_into(cx, srcs, nsrc, out);
+}
+
+// same, into an Act whose buffer (F, C, data) the caller has already allocated
+int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
     if (cx.dry) return 0;
     CombineArgs a;
     memset(&a, 0, sizeof(a));
@@ -928,7 +942,17 @@ int run_combine(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
 }
 
 // En_unet_module.forward (EaBNet.py:372-388)
+int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out);
 int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out) {
+    // the module output is allocated first; everything else (in_conv output, inner U-Net maps) is scoped scratch
+    const int Fin = srcs[0].F;
+    const int Fw = U.in_conv.deconv ? deconv_out_f(Fin, U.in_conv.kf) : conv_out_f(Fin, U.in_conv.kf);
+    if (Fw < 1) return fail("frequency axis too short for this layer");
+    out->F = Fw;
+    out->C = U.in_conv.cout;
+    out->xf = xform_identity();
+    out->data = cx.alloc_act((size_t)cx.B * cx.T * Fw * out->C);
+    const size_t scope = cx.mark();
     Act x0;
     EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0));
     Act y = x0;
@@ -956,18 +980,22 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
         y = z;
     }
     Act pair[2] = {x0, y};
-    return run_combine(cx, pair, 2, out);
+    EAB_TRY(run_combine_into(cx, pair, 2, out));
+    cx.release(scope);
+    return 0;
 }
 
 // 1x1 "conv" over positions with optional bias / relu / residual / statistics (used by TCMs and the head)
 int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const float* bias, int Cout, int N, int gate_off,
                   int ntaps, const int* dt, int relu, const float* resid, int nstats, double** stats,
-                  const float** stat_alpha, Act* out, const UmmaW* uw = nullptr) {
+                  const float** stat_alpha, Act* out, const UmmaW* uw = nullptr, bool preallocated = false) {
     const bool use_umma = uw && uw->ok && cx.m->opt_umma && (resid == nullptr || uw->ld == Cout);
-    out->F = srcs[0].F;
-    out->C = use_umma ? uw->ld : Cout;          // the tcgen05 path may pad the channel count (e.g. 18 -> 32, zeros)
-    out->xf = xform_identity();
-    out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * out->C);
+    if (!preallocated) {
+        out->F = srcs[0].F;
+        out->C = use_umma ? uw->ld : Cout;      // the tcgen05 path may pad the channel count (e.g. 18 -> 32, zeros)
+        out->xf = xform_identity();
+        out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * out->C);
+    }
     if (use_umma) {
         UmmaConvArgs us[4];
         for (int sp = 0; sp < uw->nsplit; ++sp) {
@@ -1016,6 +1044,10 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
 int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
     const eab_config& c = cx.m->cfg;
     const bool in_stats = c.norm_type == 0;
+    // the residual-stream output first, the squeezed intermediates are scoped scratch
+    out->F = x.F; out->C = c.d_feat; out->xf = xform_identity();
+    out->data = cx.alloc_act((size_t)cx.B * cx.T * x.F * c.d_feat);
+    const size_t scope = cx.mark();
     // squeeze 1x1; statistics of PReLU_left(y) and PReLU_right(y) for the two branch norms
     double* st_lr[2] = {in_stats ? cx.alloc_stats(c.cd1) : nullptr, in_stats ? cx.alloc_stats(c.cd1) : nullptr};
     const float* al_lr[2] = {cx.W(t.na_left.off_alpha), cx.W(t.na_right.off_alpha)};
@@ -1033,8 +1065,10 @@ int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
                           nullptr, in_stats ? 1 : 0, st_o, al_o, &z, &t.u_dil));
     // expand 1x1 + residual
     z.xf = xf_after(cx, t.na_out, st_o[0], cx.T, 1);
-    return run_pointwise(cx, &z, 1, cx.W(t.off_out), nullptr, c.d_feat, c.d_feat, 0, 1, nullptr, 0, x.data, 0, nullptr,
-                         nullptr, out, &t.u_out);
+    EAB_TRY(run_pointwise(cx, &z, 1, cx.W(t.off_out), nullptr, c.d_feat, c.d_feat, 0, 1, nullptr, 0, x.data, 0, nullptr,
+                          nullptr, out, &t.u_out, /*preallocated=*/true));
+    cx.release(scope);
+    return 0;
 }
 
 void tap(Ctx& cx, const char* name, const Act& a) {
@@ -1179,7 +1213,7 @@ int plan(eab_model* m, int B, int T, size_t* stats_bytes, size_t* total_bytes) {
     cx.m = m; cx.dry = true; cx.base = nullptr; cx.B = B; cx.T = T; cx.st = nullptr;
     EAB_TRY(run_forward(cx, nullptr, nullptr));
     *stats_bytes = cx.stats_off;
-    *total_bytes = cx.stats_off + cx.act_off;
+    *total_bytes = cx.stats_off + cx.act_peak;
     return 0;
 }
 
@@ -1197,7 +1231,7 @@ int forward(eab_model* m, const float* inpt, float* out, int B, int T, void* ws,
     if (sb) EAB_CUDA(cudaMemsetAsync(ws, 0, sb, st));
     Ctx cx;
     cx.m = m; cx.dry = false; cx.base = static_cast<char*>(ws); cx.B = B; cx.T = T; cx.st = st;
-    cx.stats_off = 0; cx.stats_cap = sb; cx.act_off = sb;
+    cx.stats_off = 0; cx.stats_cap = sb; cx.act_off = sb; cx.act_peak = sb;
     return run_forward(cx, inpt, out);
 }
 
