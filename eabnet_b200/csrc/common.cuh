@@ -140,6 +140,10 @@ struct ConvSrc {
     const float* x;      // [B][T][Fin][C] raw
     int C;
     Xform xf;
+    // optional second addend: value = xf(x) + xf2(x2)  (the residual sum that closes every En_unet_module,
+    // EaBNet.py:386).  Honoured by stage_kernel and combine_kernel only; every other kernel requires x2 == null.
+    const float* x2;
+    Xform xf2;
 };
 
 // One "virtual" stride-1-output convolution over rows (t, e):  fi = e*in_stride + df[tap],

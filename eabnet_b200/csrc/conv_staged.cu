@@ -37,7 +37,7 @@ inline int ceil8(int x) { return (x + 7) & ~7; }
 // ------------------------------------------------------------------------------------------------ stage kernel
 // grid (row blocks, nplanes*nslab, B), 256 threads: 8 threads per plane row (8 channels = one 16-byte fp16 chunk each)
 __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
-    __shared__ float coef[3 * 64];
+    __shared__ float coef[6 * 64];
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.z;
@@ -54,9 +54,16 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
         coef[threadIdx.x] = cs;
         coef[64 + threadIdx.x] = ch;
         coef[128 + threadIdx.x] = src.xf.prelu ? ca : 1.f;
+        if (src.x2) {
+            xform_coeffs(src.xf2, b, src.C, cbase + threadIdx.x, cs, ch, ca);
+            coef[192 + threadIdx.x] = cs;
+            coef[256 + threadIdx.x] = ch;
+            coef[320 + threadIdx.x] = src.xf2.prelu ? ca : 1.f;
+        }
     }
     __syncthreads();
     const int mode = (src.xf.affine == 0 && src.xf.prelu == 0) ? 0 : (src.xf.prelu == 1 ? 2 : 1);
+    const int mode2 = (src.xf2.affine == 0 && src.xf2.prelu == 0) ? 0 : (src.xf2.prelu == 1 ? 2 : 1);
     const int npb = a.npass == 3 ? 2 : 1;
     const int c8 = threadIdx.x & 7;
     const int rho = blockIdx.x * 32 + (threadIdx.x >> 3);
@@ -81,6 +88,21 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
                 }
                 v0 = make_float4(x[0], x[1], x[2], x[3]);
                 v1 = make_float4(x[4], x[5], x[6], x[7]);
+            }
+            if (src.x2) {                        // + the second addend of a module's residual sum
+                const float4* p2 = reinterpret_cast<const float4*>(src.x2 + ((((size_t)b * a.T + t) * a.Fin + fi) * src.C + cbase + c8 * 8));
+                const float4 w0 = __ldg(p2), w1 = __ldg(p2 + 1);
+                float x[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                if (mode2 != 0) {
+                    const float* cs = coef + 192 + c8 * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (mode2 == 1) { const float z = fmaf(x[i], cs[i], cs[64 + i]); x[i] = fmaxf(z, 0.f) + cs[128 + i] * fminf(z, 0.f); }
+                        else x[i] = fmaf(fmaxf(x[i], 0.f) + cs[128 + i] * fminf(x[i], 0.f), cs[i], cs[64 + i]);
+                    }
+                }
+                v0.x += x[0]; v0.y += x[1]; v0.z += x[2]; v0.w += x[3];
+                v1.x += x[4]; v1.y += x[5]; v1.z += x[6]; v1.w += x[7];
             }
         }
     }

@@ -145,7 +145,14 @@ struct Act {                 // an activation tensor as seen by a consumer
     float* data = nullptr;
     int F = 0, C = 0;
     Xform xf = xform_identity();
+    // lazy residual sum: value = xf(data) + xf2(data2) when data2 != null (never materialised on the staged path)
+    float* data2 = nullptr;
+    Xform xf2 = xform_identity();
 };
+
+inline void set_src(ConvSrc& s, const Act& a) {
+    s.x = a.data; s.C = a.C; s.xf = a.xf; s.x2 = a.data2; s.xf2 = a.xf2;
+}
 
 struct Tap { Act act; int B = 0, T = 0; };
 
@@ -189,6 +196,7 @@ struct eab_model {
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
+    int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
     int opt_plane = 1;            // "stage once, shift by descriptor" kernel with fused producers (fallback)
     int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
     int umma_launch_idx = 0;
@@ -849,13 +857,21 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
             }
         }
     }
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < us[i].nsrc; ++k)
+            if (us[i].src[k].x2) return fail("internal: lazy residual sum reached a kernel that cannot read it");
     if (cx.dry) return 0;
     for (int i = 0; i < n; ++i) EAB_TRY(launch_tensor_conv(m, us[i], cx.st));
     return 0;
 }
 
 // one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
-int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out) {
+int materialize(Ctx& cx, Act* a);
+int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* out, float* prealloc = nullptr) {
+    Act srcs[2];
+    for (int i = 0; i < nsrc; ++i) srcs[i] = srcs_in[i];
+    if (!(cx.m->opt_umma && L.umma_ok && cx.m->opt_staged))
+        for (int i = 0; i < nsrc; ++i) EAB_TRY(materialize(cx, &srcs[i]));       // only the staged path reads lazy sums
     const int Fin = srcs[0].F;
     int cin = 0;
     for (int i = 0; i < nsrc; ++i) {
@@ -867,7 +883,8 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out)
     if (Fout < 1) return fail("frequency axis too short for this layer");
     out->F = Fout;
     out->C = L.cout;
-    out->data = cx.alloc_act((size_t)cx.B * cx.T * Fout * L.cout);
+    out->data2 = nullptr;
+    out->data = prealloc ? prealloc : cx.alloc_act((size_t)cx.B * cx.T * Fout * L.cout);
     const bool in_stats = L.na.has_norm && cx.m->cfg.norm_type == 0;
     double* stats = in_stats ? cx.alloc_stats(L.cout) : nullptr;
     out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
@@ -878,7 +895,7 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs, int nsrc, Act* out)
             UmmaConvArgs& u = us[v];
             memset(&u, 0, sizeof(u));
             u.nsrc = nsrc;
-            for (int i = 0; i < nsrc; ++i) { u.src[i].x = srcs[i].data; u.src[i].C = srcs[i].C; u.src[i].xf = srcs[i].xf; }
+            for (int i = 0; i < nsrc; ++i) set_src(u.src[i], srcs[i]);
             u.B = cx.B; u.T = cx.T; u.Fin = Fin; u.Fout = Fout;
             if (L.deconv) { u.in_stride = 1; u.out_stride = 2; u.out_off = v; u.E = (Fout - v + 1) / 2; }
             else          { u.in_stride = 2; u.out_stride = 1; u.out_off = 0; u.E = Fout; }
@@ -932,13 +949,26 @@ int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
     if (cx.dry) return 0;
     CombineArgs a;
     memset(&a, 0, sizeof(a));
-    a.nsrc = nsrc;
+    int n = 0;
     for (int i = 0; i < nsrc; ++i) {
         if (srcs[i].F != out->F || srcs[i].C != out->C) return fail("internal: combine shape mismatch");
-        a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf;
+        if (n + (srcs[i].data2 ? 2 : 1) > 3) return fail("internal: too many addends in combine");
+        a.src[n].x = srcs[i].data; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf; ++n;
+        if (srcs[i].data2) { a.src[n].x = srcs[i].data2; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf2; ++n; }
     }
+    a.nsrc = n;
     a.B = cx.B; a.P = cx.T * out->F; a.C = out->C; a.out = out->data;
     return launch_combine(a, cx.st);
+}
+
+// materialise a lazy residual sum (only needed in front of kernels that cannot read one)
+int materialize(Ctx& cx, Act* a) {
+    if (!a->data2) return 0;
+    Act src = *a;
+    Act dst;
+    EAB_TRY(run_combine(cx, &src, 1, &dst));
+    *a = dst;
+    return 0;
 }
 
 // En_unet_module.forward (EaBNet.py:372-388)
@@ -951,10 +981,18 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
     out->F = Fw;
     out->C = U.in_conv.cout;
     out->xf = xform_identity();
-    out->data = cx.alloc_act((size_t)cx.B * cx.T * Fw * out->C);
+    // lazy mode: the module result x0 + y is never written; its two addends (in_conv output, last inner deconv output)
+    // outlive the module instead and every consumer's stage kernel sums them while staging
+    const bool lazy = cx.m->opt_lazy && cx.m->opt_umma && cx.m->opt_staged && U.in_conv.umma_ok && !U.deco.empty() &&
+                      U.deco.back().umma_ok;
+    const size_t nel = (size_t)cx.B * cx.T * Fw * out->C;
+    float* buf_x0 = nullptr;
+    float* buf_y = nullptr;
+    if (lazy) { buf_x0 = cx.alloc_act(nel); buf_y = cx.alloc_act(nel); out->data = nullptr; }
+    else out->data = cx.alloc_act(nel);
     const size_t scope = cx.mark();
     Act x0;
-    EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0));
+    EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0, buf_x0));
     Act y = x0;
     std::vector<Act> keep;
     for (size_t i = 0; i < U.enco.size(); ++i) {
@@ -965,22 +1003,28 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
     }
     for (size_t i = 0; i < U.deco.size(); ++i) {
         Act z;
+        float* pre = (lazy && i + 1 == U.deco.size()) ? buf_y : nullptr;
         if (i == 0) {
-            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z));
+            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z, pre));
         } else {
             Act pair[2] = {y, keep[keep.size() - 1 - i]};
             if (cx.m->cfg.intra_connect == 0) {
-                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z));
+                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z, pre));
             } else {
                 Act sum;
                 EAB_TRY(run_combine(cx, pair, 2, &sum));
-                EAB_TRY(run_conv2d(cx, U.deco[i], &sum, 1, &z));
+                EAB_TRY(run_conv2d(cx, U.deco[i], &sum, 1, &z, pre));
             }
         }
         y = z;
     }
-    Act pair[2] = {x0, y};
-    EAB_TRY(run_combine_into(cx, pair, 2, out));
+    if (lazy) {
+        out->data = x0.data; out->xf = x0.xf;
+        out->data2 = y.data; out->xf2 = y.xf;
+    } else {
+        Act pair[2] = {x0, y};
+        EAB_TRY(run_combine_into(cx, pair, 2, out));
+    }
     cx.release(scope);
     return 0;
 }
@@ -1003,7 +1047,7 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
             memset(&u, 0, sizeof(u));
             u.nsrc = nsrc;
             int cin = 0;
-            for (int i = 0; i < nsrc; ++i) { u.src[i].x = srcs[i].data; u.src[i].C = srcs[i].C; u.src[i].xf = srcs[i].xf; cin += srcs[i].C; }
+            for (int i = 0; i < nsrc; ++i) { set_src(u.src[i], srcs[i]); cin += srcs[i].C; }
             u.B = cx.B; u.T = cx.T; u.Fin = srcs[0].F; u.Fout = srcs[0].F; u.E = srcs[0].F;
             u.in_stride = 1; u.out_stride = 1; u.out_off = 0;
             u.ntaps = uw->ntaps;
@@ -1391,6 +1435,7 @@ int64_t eab_debug_tap(eab_model* m, const char* name, float* dst, int64_t capaci
     memset(&a, 0, sizeof(a));
     a.nsrc = 1;
     a.src[0].x = t.act.data; a.src[0].C = t.act.C; a.src[0].xf = t.act.xf;
+    if (t.act.data2) { a.nsrc = 2; a.src[1].x = t.act.data2; a.src[1].C = t.act.C; a.src[1].xf = t.act.xf2; }
     a.B = t.B; a.P = t.T * t.act.F; a.C = t.act.C; a.out = dst;
     if (launch_combine(a, static_cast<cudaStream_t>(stream))) return -1;
     return n;
@@ -1403,6 +1448,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "plane") m->opt_plane = value != 0;
     else if (n == "pdl") g_use_pdl = value != 0;
     else if (n == "staged") m->opt_staged = value != 0;
+    else if (n == "lazy") m->opt_lazy = value != 0;
     else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
     else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
     else if (n == "dbg_launch") {
