@@ -32,6 +32,11 @@ SYMBOLS = {
     "eab_enhance_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "eab_enhance": (C.c_int, [_P, _F, _F, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "eab_enhance_host": (C.c_int, [_P, _F, _F, C.c_int, C.c_int, _P]),
+    "eab_enhance_host_batches": (C.c_int, [_P, C.POINTER(_F), C.POINTER(_F), C.c_int, C.c_int, C.c_int, _P]),
+    "eab_stream_state_bytes": (C.c_size_t, [_P, C.c_int]),
+    "eab_stream_reset": (C.c_int, [_P, _P, C.c_size_t, C.c_int, _P]),
+    "eab_stream_step": (C.c_int, [_P, _P, C.c_size_t, _F, _F, C.c_int, _P]),
+    "eab_stream_step_spec": (C.c_int, [_P, _P, C.c_size_t, _F, _F, C.c_int, _P]),
     "eab_last_launch_count": (C.c_int, [_P]),
     "eab_debug_tap": (C.c_int64, [_P, C.c_char_p, _F, C.c_int64, _P]),
     "eab_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

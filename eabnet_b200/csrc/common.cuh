@@ -144,7 +144,17 @@ struct ConvSrc {
     // EaBNet.py:386).  Honoured by stage_kernel and combine_kernel only; every other kernel requires x2 == null.
     const float* x2;
     Xform xf2;
+    int RT;              // streaming only: frames in this tensor's ring (see StreamPos); 0 = offline [B][T][...]
 };
+
+// Frame-by-frame ("streaming", BASELINE configs[2]) addressing.  Offline, a tensor holds frames 0..T-1 of every batch
+// item.  In a streaming launch (step != null) exactly ONE new frame is computed per stream (T == 1); its absolute index
+// n = *step is read on the device (so a whole step is CUDA-graph capturable), every activation is a ring of RT frames
+// per stream with frame n in slot n % RT, and a causal tap that reaches d frames back reads slot (n - d) % RT, or
+// zeros when n - d < 0 (the literal zero padding of the offline path: EaBNet.py:449, :480, :557).
+#ifdef __CUDACC__
+__device__ __forceinline__ int ring_slot(int n, int RT) { return RT <= 1 ? 0 : n % RT; }
+#endif
 
 // One "virtual" stride-1-output convolution over rows (t, e):  fi = e*in_stride + df[tap],
 // frame = t - dt[tap], fo = e*out_stride + out_off.  A Conv2d with stride (1,2) is one launch
@@ -168,6 +178,8 @@ struct ConvArgs {
     double* stats[2];            // optional [B][Cout][2] accumulators
     const float* stat_alpha[2];  // if set, statistics are taken of PReLU(out, alpha) (TCM convention)
     int nstats;
+    const int* step;             // streaming: device pointer to the absolute frame index (null = offline)
+    int out_RT, resid_RT;        // streaming: ring sizes of out / resid
 };
 int launch_conv(const ConvArgs& a, cudaStream_t st);
 
@@ -251,6 +263,8 @@ struct CombineArgs {
     int nsrc;
     int B, P, C;                 // P = positions per batch item (T*F)
     float* out;
+    const int* step;             // streaming (see ConvArgs): P = F, sources / out are rings
+    int out_RT;
 };
 int launch_combine(const CombineArgs& a, cudaStream_t st);
 
@@ -265,6 +279,10 @@ struct LstmArgs {
     int B, T, F, E;
     float* out;                  // [B][T][F][64]
     unsigned long long* dbg;     // optional cycle counters (diagnostics)
+    // streaming (CUDA-core kernel only): T == 1, carried state [B*F][64] read before / written after the step
+    const int* step;
+    float* h_state; float* c_state;
+    int out_RT;
 };
 int launch_lstm(const LstmArgs& a, cudaStream_t st);
 bool lstm_umma_supported(const LstmArgs& a);
@@ -276,10 +294,18 @@ struct BeamArgs {
     const float* inpt;           // [B][T][F][M][2]
     int B, T, F, M, miso;
     float* out;                  // mimo [B][2][T][F];  miso [B][2][T]
+    const int* step;             // streaming: w / inpt are rings of w_RT / inpt_RT frames, T == 1
+    int w_RT, inpt_RT;
 };
 int launch_beam(const BeamArgs& a, cudaStream_t st);
 
 int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st);
 int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st);
+// streaming front/back end (stft.cu): one hop in -> spectrum frame *step into a ring; spectrum frame -> one hop out
+// (delayed by one hop: overlap-add needs the next frame), carried state in prev_hop [S][M][160] / tail [S][160]
+int launch_stft_frame(const float* hop, float* prev_hop, float* spec_ring, int spec_RT, const int* step, int S, int M,
+                      cudaStream_t st);
+int launch_istft_frame(const float* frame, float* tail, float* hop_out, const int* step, int S, cudaStream_t st);
+int launch_step_advance(int* step, cudaStream_t st);
 
 }  // namespace eab

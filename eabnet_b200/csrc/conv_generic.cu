@@ -33,8 +33,11 @@ __global__ void __launch_bounds__(NTHREADS) conv_generic_kernel(const ConvArgs a
     pdl_trigger();
     pdl_wait();
     const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    const int rows_per_b = a.T * a.E;
+    // streaming: rows of all streams share one row space (r = stream * E + e, one frame each); offline: rows (t, e) of item b
+    const bool streaming = a.step != nullptr;
+    const int step = streaming ? *a.step : 0;
+    const int b = streaming ? 0 : blockIdx.y;
+    const int rows_per_b = streaming ? a.B * a.E : a.T * a.E;
     const int row0 = blockIdx.x * TM;
     const int C0 = a.src[0].C;
     const int C1 = a.nsrc > 1 ? a.src[1].C : 0;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_generic_kernel(const ConvArgs a
     for (int i = 0; i < NLD; ++i) {
         const int r = row0 + (tid >> 3) + 32 * i;
         lvalid[i] = r < rows_per_b;
-        lt[i] = r / a.E;
+        lt[i] = r / a.E;                          // streaming: the stream index
         le[i] = r - lt[i] * a.E;
     }
 
@@ -100,10 +103,20 @@ __global__ void __launch_bounds__(NTHREADS) conv_generic_kernel(const ConvArgs a
 #pragma unroll
         for (int i = 0; i < NLD; ++i) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int tt = lt[i] - dtv;
             const int fi = le[i] * a.in_stride + dfv;
-            if (lvalid[i] && tt >= 0 && tt < a.T && fi >= 0 && fi < a.Fin && c < C) {
-                const float* p = src.x + (((size_t)b * a.T + tt) * a.Fin + fi) * C + c;
+            size_t frame;                         // index of the source frame in units of [Fin][C]
+            bool tok;
+            if (streaming) {
+                const int n = step - dtv;
+                tok = n >= 0 && n <= step;
+                frame = (size_t)lt[i] * src.RT + ring_slot(n, src.RT);
+            } else {
+                const int tt = lt[i] - dtv;
+                tok = tt >= 0 && tt < a.T;
+                frame = (size_t)b * a.T + tt;
+            }
+            if (lvalid[i] && tok && fi >= 0 && fi < a.Fin && c < C) {
+                const float* p = src.x + (frame * a.Fin + fi) * C + c;
                 float x[4] = {0.f, 0.f, 0.f, 0.f};
                 if (vec) {
                     const float4 q = __ldg(reinterpret_cast<const float4*>(p));
@@ -214,10 +227,12 @@ __global__ void __launch_bounds__(NTHREADS) conv_generic_kernel(const ConvArgs a
     for (int r = 0; r < RPT; ++r) {
         const int row = row0 + rg * RPT + r;
         if (row >= rows_per_b) continue;
-        const int t = row / a.E;
+        const int t = row / a.E;                  // streaming: the stream index
         const int e = row - t * a.E;
         const int fo = e * a.out_stride + a.out_off;
-        const size_t obase = (((size_t)b * a.T + t) * a.Fout + fo) * a.Cout;
+        const size_t oframe = streaming ? (size_t)t * a.out_RT + ring_slot(step, a.out_RT) : (size_t)b * a.T + t;
+        const size_t obase = (oframe * a.Fout + fo) * a.Cout;
+        const size_t rbase = streaming ? (((size_t)t * a.resid_RT + ring_slot(step, a.resid_RT)) * a.Fout + fo) * a.Cout : obase;
 #pragma unroll
         for (int v = 0; v < NVV_MAX; ++v) {
             const int col = v * 64 + cg * 4;
@@ -239,7 +254,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_generic_kernel(const ConvArgs a
             if (a.resid) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (col + q < a.Cout) o[q] += __ldg(a.resid + obase + col + q);
+                    if (col + q < a.Cout) o[q] += __ldg(a.resid + rbase + col + q);
             }
             if (vec_out) {
                 *reinterpret_cast<float4*>(a.out + obase + col) = make_float4(o[0], o[1], o[2], o[3]);
@@ -312,9 +327,10 @@ int launch_inst(const ConvArgs& a, cudaStream_t st) {
                                       (int)smem));
         configured = smem;
     }
-    const int rows = a.T * a.E;
-    dim3 grid((rows + TM - 1) / TM, a.B);
-    const double pos = (double)a.B * rows;
+    const bool streaming = a.step != nullptr;
+    const int rows = streaming ? a.B * a.E : a.T * a.E;
+    dim3 grid((rows + TM - 1) / TM, streaming ? 1 : a.B);
+    const double pos = streaming ? (double)rows : (double)a.B * rows;
     const int ncol = a.Cout * (GATED ? 2 : 1);
     ProfScope ps("conv_generic", 2.0 * pos * a.ntaps * Ctot * ncol * a.algo_frac,
                  4.0 * (pos * a.in_stride * Ctot / (a.out_stride > 1 ? 2.0 : 1.0) + pos * a.Cout * (a.resid ? 2 : 1) +
@@ -333,6 +349,16 @@ int launch_conv(const ConvArgs& a, cudaStream_t st) {
     if (a.N != 64 && a.N != 128 && a.N != 256) return fail("conv: unsupported output channel count (max 128 gated / 256 plain)");
     if (a.gate_off > 0 && a.gate_off * 2 != a.N) return fail("conv: bad gate offset");
     if (a.B <= 0 || a.T <= 0 || a.E <= 0) return 0;
+    if (a.step) {
+        if (a.T != 1 || a.nstats != 0) return fail("conv: a streaming launch computes one frame and takes no statistics");
+        for (int i = 0; i < a.nsrc; ++i) {
+            if (a.src[i].xf.affine == 1) return fail("conv: streaming needs static normalisation (norm_type 'BN')");
+            int back = 0;
+            for (int k = 0; k < a.ntaps; ++k) { if (a.dt[k] < 0) return fail("conv: streaming needs causal taps"); back = a.dt[k] > back ? a.dt[k] : back; }
+            if (a.src[i].RT < back + 1) return fail("conv: source ring shorter than the receptive field");
+        }
+        if (a.out_RT < 1 || (a.resid && a.resid_RT < 1)) return fail("conv: bad output ring");
+    }
     const bool g = a.gate_off > 0;
     switch (a.N / 64) {
         case 1: return g ? fail("conv: gated layer needs N >= 128") : launch_inst<1, 8, false>(a, st);

@@ -23,14 +23,18 @@ __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
     }
     __syncthreads();
     const size_t per_b = (size_t)a.P * C;
-    const size_t base = (size_t)b * per_b;
+    const int step = a.step ? *a.step : 0;
+    const size_t base = a.step ? ((size_t)b * a.out_RT + ring_slot(step, a.out_RT)) * per_b : (size_t)b * per_b;
+    size_t sbase[3];
+    for (int s = 0; s < a.nsrc; ++s)
+        sbase[s] = a.step ? ((size_t)b * a.src[s].RT + ring_slot(step, a.src[s].RT)) * per_b : (size_t)b * per_b;
     if ((C & 3) == 0) {
         const size_t n4 = per_b / 4;
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
             const int c = (int)((i * 4) % C);
             float o[4] = {0.f, 0.f, 0.f, 0.f};
             for (int s = 0; s < a.nsrc; ++s) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(a.src[s].x + base) + i);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(a.src[s].x + sbase[s]) + i);
                 const float x[4] = {v.x, v.y, v.z, v.w};
                 const int pr = a.src[s].xf.prelu;
 #pragma unroll
@@ -45,7 +49,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
             const int c = (int)(i % C);
             float o = 0.f;
             for (int s = 0; s < a.nsrc; ++s)
-                o += xform_apply(__ldg(a.src[s].x + base + i), coef[(s * 3 + 0) * C + c], coef[(s * 3 + 1) * C + c],
+                o += xform_apply(__ldg(a.src[s].x + sbase[s] + i), coef[(s * 3 + 0) * C + c], coef[(s * 3 + 1) * C + c],
                                  coef[(s * 3 + 2) * C + c], a.src[s].xf.prelu);
             a.out[base + i] = o;
         }
@@ -59,8 +63,15 @@ __global__ void __launch_bounds__(256) beam_mimo_kernel(const BeamArgs a) {
     const size_t n = (size_t)a.B * a.T * a.F;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float2* w = reinterpret_cast<const float2*>(a.w + i * a.w_ld);
-    const float2* x = reinterpret_cast<const float2*>(a.inpt) + i * a.M;
+    size_t iw = i, ix = i;
+    if (a.step) {                                   // T == 1: i = stream * F + f, operands are rings
+        const int step = *a.step;
+        const size_t s = i / a.F, f = i - s * a.F;
+        iw = (s * a.w_RT + ring_slot(step, a.w_RT)) * a.F + f;
+        ix = (s * a.inpt_RT + ring_slot(step, a.inpt_RT)) * a.F + f;
+    }
+    const float2* w = reinterpret_cast<const float2*>(a.w + iw * a.w_ld);
+    const float2* x = reinterpret_cast<const float2*>(a.inpt) + ix * a.M;
     float yr = 0.f, yi = 0.f;
     for (int m = 0; m < a.M; ++m) {
         const float2 wv = __ldg(w + m), xv = __ldg(x + m);
@@ -81,11 +92,16 @@ __global__ void __launch_bounds__(256) beam_miso_kernel(const BeamArgs a) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.B * a.T) return;
-    const size_t row = (size_t)warp * a.F;
+    size_t row = (size_t)warp * a.F, rowx = row;
+    if (a.step) {
+        const int step = *a.step;
+        row = ((size_t)warp * a.w_RT + ring_slot(step, a.w_RT)) * a.F;
+        rowx = ((size_t)warp * a.inpt_RT + ring_slot(step, a.inpt_RT)) * a.F;
+    }
     float yr = 0.f, yi = 0.f;
     for (int f = lane; f < a.F; f += 32) {
         const float2 wv = __ldg(reinterpret_cast<const float2*>(a.w + (row + f) * a.w_ld));
-        const float2 xv = __ldg(reinterpret_cast<const float2*>(a.inpt) + (row + f) * a.M);
+        const float2 xv = __ldg(reinterpret_cast<const float2*>(a.inpt) + (rowx + f) * a.M);
         yr += wv.x * xv.x - wv.y * xv.y;
         yi += wv.x * xv.y + wv.y * xv.x;
     }

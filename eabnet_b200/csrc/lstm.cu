@@ -61,6 +61,12 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const LstmArgs a) {
         for (int i = tid; i < H * 4 * SP; i += 256) hbuf[i] = 0.f;
         for (int i = tid; i < E * 4 * SP; i += 256) xin[i] = 0.f;
     }
+    const bool streaming = a.step != nullptr;
+    const int step = streaming ? *a.step : 0;
+    const int src_slot = streaming ? ring_slot(step, a.src.RT) : 0;
+    const int src_T = streaming ? a.src.RT : a.T;        // frames per batch item in the source / output tensors
+    const int out_T = streaming ? a.out_RT : a.T;
+    const int out_slot = streaming ? ring_slot(step, a.out_RT) : 0;
 
     // loader role: 4 threads per sequence, EPT consecutive channels each
     const int ls = tid >> 2;
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const LstmArgs a) {
     const bool lactive = ls < S && lq < NQ;
     const int lb = lactive ? lq / a.F : 0;
     const int lf = lactive ? lq - lb * a.F : 0;
-    const float* lsrc = a.src.x + (((size_t)lb * a.T) * a.F + lf) * E + part * EPT;
+    const float* lsrc = a.src.x + (((size_t)lb * src_T + src_slot) * a.F + lf) * E + part * EPT;
     const size_t step_stride = (size_t)a.F * E;
     const float* lcoef = coef + (lactive ? (lb - b0) : 0) * 3 * E;
     const int lsg = ls / SPT, lss = ls - lsg * SPT;
@@ -133,11 +139,21 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const LstmArgs a) {
         oval[s] = q < NQ;
         const int bq = oval[s] ? q / a.F : 0;
         const int fq = oval[s] ? q - bq * a.F : 0;
-        obase[s] = (((size_t)bq * a.T) * a.F + fq) * H + j;
+        obase[s] = (((size_t)bq * out_T + out_slot) * a.F + fq) * H + j;
     }
     const size_t ostep = (size_t)a.F * H;
 
     __syncthreads();
+    if (streaming && step > 0) {                 // carried state (zero at the first frame, like the offline path)
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const int q = q0 + sg * SPT + s;
+            if (oval[s]) {
+                cst[s] = a.c_state[(size_t)q * H + j];
+                hbuf[(j * 4 + sg) * SP + s] = a.h_state[(size_t)q * H + j];
+            }
+        }
+    }
     prefetch(0);
     publish();
     __syncthreads();
@@ -199,6 +215,16 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const LstmArgs a) {
         if (t + 1 < a.T) publish();
         __syncthreads();
     }
+    if (streaming) {
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const int q = q0 + sg * SPT + s;
+            if (oval[s]) {
+                a.c_state[(size_t)q * H + j] = cst[s];
+                a.h_state[(size_t)q * H + j] = hbuf[(j * 4 + sg) * SP + s];
+            }
+        }
+    }
 }
 
 template <int SPT, int E>
@@ -249,6 +275,8 @@ int launch_e(const LstmArgs& a, cudaStream_t st) {
 
 int launch_lstm(const LstmArgs& a, cudaStream_t st) {
     if (a.F < 8) return fail("lstm: F < 8 is not supported");
+    if (a.step && (a.T != 1 || !a.h_state || !a.c_state || a.src.RT < 1 || a.out_RT < 1 || a.src.xf.affine == 1))
+        return fail("lstm: bad streaming launch");
     switch (a.E) {
         case 32: return launch_e<32>(a, st);
         case 64: return launch_e<64>(a, st);

@@ -148,10 +148,11 @@ struct Act {                 // an activation tensor as seen by a consumer
     // lazy residual sum: value = xf(data) + xf2(data2) when data2 != null (never materialised on the staged path)
     float* data2 = nullptr;
     Xform xf2 = xform_identity();
+    int RT = 0;              // streaming: frames in this tensor's ring (0 = offline)
 };
 
 inline void set_src(ConvSrc& s, const Act& a) {
-    s.x = a.data; s.C = a.C; s.xf = a.xf; s.x2 = a.data2; s.xf2 = a.xf2;
+    s.x = a.data; s.C = a.C; s.xf = a.xf; s.x2 = a.data2; s.xf2 = a.xf2; s.RT = a.RT;
 }
 
 struct Tap { Act act; int B = 0, T = 0; };
@@ -189,8 +190,10 @@ struct eab_model {
     bool dirty = true;
     int last_launches = 0;
     std::map<std::string, Tap> taps;
-    void* scratch = nullptr;      // eab_enhance_host
+    void* scratch = nullptr;      // eab_enhance_host / eab_enhance_host_batches
     size_t scratch_bytes = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host front door
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // options (eab_set_option)
     int opt_umma = 1;             // tcgen05 path for eligible layers
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
@@ -727,8 +730,19 @@ struct Ctx {
     int B, T;
     cudaStream_t st;
 
+    // streaming (eab_stream_step): T == 1, every activation is a persistent ring of `last_RT` frames in the caller's
+    // state blob (same allocation order every step => same addresses), nothing is reused, tensor-core kernels are off
+    bool streaming = false;
+    const int* step = nullptr;
+    int next_RT = 0;          // ring size of the next allocation (0 = the default of 2: current + previous frame)
+    int last_RT = 0;          // ring size of the last allocation (0 offline)
+    bool tensor_ok() const { return m->opt_umma && !streaming; }
+
     size_t act_peak = 0;
     float* alloc_act(size_t floats) {
+        last_RT = streaming ? (next_RT ? next_RT : 2) : 0;
+        next_RT = 0;
+        if (streaming) floats *= last_RT;
         const size_t bytes = (floats * sizeof(float) + 255) / 256 * 256;
         float* p = reinterpret_cast<float*>(base + act_off);
         act_off += bytes;
@@ -738,7 +752,7 @@ struct Ctx {
     // scoped reuse: everything allocated after mark() is dead at release() (single stream => later kernels that
     // overwrite the region are ordered after the kernels that read it)
     size_t mark() const { return act_off; }
-    void release(size_t m) { act_off = m; }
+    void release(size_t m) { if (!streaming) act_off = m; }
     double* alloc_stats(int C) {
         const size_t bytes = ((size_t)B * C * 2 * sizeof(double) + 255) / 256 * 256;
         double* p = reinterpret_cast<double*>(base + stats_off);
@@ -870,7 +884,7 @@ int materialize(Ctx& cx, Act* a);
 int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* out, float* prealloc = nullptr) {
     Act srcs[2];
     for (int i = 0; i < nsrc; ++i) srcs[i] = srcs_in[i];
-    if (!(cx.m->opt_umma && L.umma_ok && cx.m->opt_staged))
+    if (!(cx.tensor_ok() && L.umma_ok && cx.m->opt_staged))
         for (int i = 0; i < nsrc; ++i) EAB_TRY(materialize(cx, &srcs[i]));       // only the staged path reads lazy sums
     const int Fin = srcs[0].F;
     int cin = 0;
@@ -885,10 +899,11 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
     out->C = L.cout;
     out->data2 = nullptr;
     out->data = prealloc ? prealloc : cx.alloc_act((size_t)cx.B * cx.T * Fout * L.cout);
+    out->RT = prealloc ? 0 : cx.last_RT;
     const bool in_stats = L.na.has_norm && cx.m->cfg.norm_type == 0;
     double* stats = in_stats ? cx.alloc_stats(L.cout) : nullptr;
     out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
-    if (cx.m->opt_umma && L.umma_ok) {
+    if (cx.tensor_ok() && L.umma_ok) {
         UmmaConvArgs us[2];
         bool all_ok = true;
         for (int v = 0; v < L.nvar; ++v) {
@@ -917,7 +932,8 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
         ConvArgs a;
         memset(&a, 0, sizeof(a));
         a.nsrc = nsrc;
-        for (int i = 0; i < nsrc; ++i) { a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf; }
+        for (int i = 0; i < nsrc; ++i) { a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf; a.src[i].RT = srcs[i].RT; }
+        a.step = cx.step; a.out_RT = out->RT;
         a.B = cx.B; a.T = cx.T; a.Fin = Fin; a.Fout = Fout;
         if (L.deconv) { a.in_stride = 1; a.out_stride = 2; a.out_off = v; a.E = (Fout - v + 1) / 2; }
         else          { a.in_stride = 2; a.out_stride = 1; a.out_off = 0; a.E = Fout; }
@@ -941,6 +957,7 @@ int run_combine(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
     out->C = srcs[0].C;
     out->xf = xform_identity();
     out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * out->C);
+    out->RT = cx.last_RT;
     return run_combine_into(cx, srcs, nsrc, out);
 }
 
@@ -953,11 +970,12 @@ int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
     for (int i = 0; i < nsrc; ++i) {
         if (srcs[i].F != out->F || srcs[i].C != out->C) return fail("internal: combine shape mismatch");
         if (n + (srcs[i].data2 ? 2 : 1) > 3) return fail("internal: too many addends in combine");
-        a.src[n].x = srcs[i].data; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf; ++n;
-        if (srcs[i].data2) { a.src[n].x = srcs[i].data2; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf2; ++n; }
+        a.src[n].x = srcs[i].data; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf; a.src[n].RT = srcs[i].RT; ++n;
+        if (srcs[i].data2) { a.src[n].x = srcs[i].data2; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf2; a.src[n].RT = srcs[i].RT; ++n; }
     }
     a.nsrc = n;
     a.B = cx.B; a.P = cx.T * out->F; a.C = out->C; a.out = out->data;
+    a.step = cx.step; a.out_RT = out->RT;
     return launch_combine(a, cx.st);
 }
 
@@ -983,13 +1001,13 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
     out->xf = xform_identity();
     // lazy mode: the module result x0 + y is never written; its two addends (in_conv output, last inner deconv output)
     // outlive the module instead and every consumer's stage kernel sums them while staging
-    const bool lazy = cx.m->opt_lazy && cx.m->opt_umma && cx.m->opt_staged && U.in_conv.umma_ok && !U.deco.empty() &&
+    const bool lazy = cx.m->opt_lazy && cx.tensor_ok() && cx.m->opt_staged && U.in_conv.umma_ok && !U.deco.empty() &&
                       U.deco.back().umma_ok;
     const size_t nel = (size_t)cx.B * cx.T * Fw * out->C;
     float* buf_x0 = nullptr;
     float* buf_y = nullptr;
     if (lazy) { buf_x0 = cx.alloc_act(nel); buf_y = cx.alloc_act(nel); out->data = nullptr; }
-    else out->data = cx.alloc_act(nel);
+    else { out->data = cx.alloc_act(nel); out->RT = cx.last_RT; }
     const size_t scope = cx.mark();
     Act x0;
     EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0, buf_x0));
@@ -1032,13 +1050,14 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
 // 1x1 "conv" over positions with optional bias / relu / residual / statistics (used by TCMs and the head)
 int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const float* bias, int Cout, int N, int gate_off,
                   int ntaps, const int* dt, int relu, const float* resid, int nstats, double** stats,
-                  const float** stat_alpha, Act* out, const UmmaW* uw = nullptr, bool preallocated = false) {
-    const bool use_umma = uw && uw->ok && cx.m->opt_umma && (resid == nullptr || uw->ld == Cout);
+                  const float** stat_alpha, Act* out, const UmmaW* uw = nullptr, bool preallocated = false, int resid_RT = 0) {
+    const bool use_umma = uw && uw->ok && cx.tensor_ok() && (resid == nullptr || uw->ld == Cout);
     if (!preallocated) {
         out->F = srcs[0].F;
         out->C = use_umma ? uw->ld : Cout;      // the tcgen05 path may pad the channel count (e.g. 18 -> 32, zeros)
         out->xf = xform_identity();
         out->data = cx.alloc_act((size_t)cx.B * cx.T * out->F * out->C);
+        out->RT = cx.last_RT;
     }
     if (use_umma) {
         UmmaConvArgs us[4];
@@ -1071,7 +1090,8 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.nsrc = nsrc;
-    for (int i = 0; i < nsrc; ++i) { a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf; }
+    for (int i = 0; i < nsrc; ++i) { a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf; a.src[i].RT = srcs[i].RT; }
+    a.step = cx.step; a.out_RT = out->RT; a.resid_RT = resid_RT;
     a.B = cx.B; a.T = cx.T; a.Fin = srcs[0].F; a.Fout = srcs[0].F; a.E = srcs[0].F;
     a.in_stride = 1; a.out_stride = 1; a.out_off = 0;
     a.ntaps = ntaps;
@@ -1091,7 +1111,13 @@ int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
     // the residual-stream output first, the squeezed intermediates are scoped scratch
     out->F = x.F; out->C = c.d_feat; out->xf = xform_identity();
     out->data = cx.alloc_act((size_t)cx.B * cx.T * x.F * c.d_feat);
+    out->RT = cx.last_RT;
     const size_t scope = cx.mark();
+    if (cx.streaming) {                        // the dilated taps reach (kd1-1)*d frames back into the squeezed tensor
+        int back = 0;
+        for (int i = 0; i < c.kd1; ++i) back = std::max(back, t.dt[i]);
+        cx.next_RT = back + 1;
+    }
     // squeeze 1x1; statistics of PReLU_left(y) and PReLU_right(y) for the two branch norms
     double* st_lr[2] = {in_stats ? cx.alloc_stats(c.cd1) : nullptr, in_stats ? cx.alloc_stats(c.cd1) : nullptr};
     const float* al_lr[2] = {cx.W(t.na_left.off_alpha), cx.W(t.na_right.off_alpha)};
@@ -1110,13 +1136,13 @@ int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
     // expand 1x1 + residual
     z.xf = xf_after(cx, t.na_out, st_o[0], cx.T, 1);
     EAB_TRY(run_pointwise(cx, &z, 1, cx.W(t.off_out), nullptr, c.d_feat, c.d_feat, 0, 1, nullptr, 0, x.data, 0, nullptr,
-                          nullptr, out, &t.u_out, /*preallocated=*/true));
+                          nullptr, out, &t.u_out, /*preallocated=*/true, x.RT));
     cx.release(scope);
     return 0;
 }
 
 void tap(Ctx& cx, const char* name, const Act& a) {
-    if (cx.dry) return;
+    if (cx.dry || cx.streaming) return;
     Tap t;
     t.act = a; t.B = cx.B; t.T = cx.T;
     cx.m->taps[name] = t;
@@ -1129,6 +1155,8 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
     x.data = const_cast<float*>(inpt);
     x.F = c.n_freq;
     x.C = 2 * c.M;
+    x.RT = cx.streaming ? 2 : 0;          // streaming: inpt is the [S][2][F][M][2] spectrum ring of the stream state
+    const int inpt_RT = x.RT;
     std::vector<Act> skips;
     // ---------------- encoder (EaBNet.py:190-197 / :234-239)
     if (c.is_u2) {
@@ -1159,6 +1187,7 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
     EAB_TRY(run_combine(cx, &x, 1, &r));
     r.F = 1;
     r.C = c.d_feat;
+    r.xf = xform_identity();
     std::vector<Act> group_out;
     size_t ti = 0;
     for (int g = 0; g < c.q; ++g) {
@@ -1207,17 +1236,22 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
         for (int l = 0; l < 2; ++l) {
             h[l].F = c.n_freq; h[l].C = 64; h[l].xf = xform_identity();
             h[l].data = cx.alloc_act((size_t)cx.B * cx.T * c.n_freq * 64);
+            h[l].RT = cx.last_RT;
+            float* hc_state[2] = {nullptr, nullptr};
+            if (cx.streaming)
+                for (int k = 0; k < 2; ++k) { cx.next_RT = 1; hc_state[k] = cx.alloc_act((size_t)cx.B * c.n_freq * 64); }
             if (!cx.dry) {
                 LstmArgs a;
                 memset(&a, 0, sizeof(a));
                 const Act& src = l ? h[0] : emb;
-                a.src.x = src.data; a.src.C = src.C; a.src.xf = src.xf;
+                a.src.x = src.data; a.src.C = src.C; a.src.xf = src.xf; a.src.RT = src.RT;
+                a.step = cx.step; a.h_state = hc_state[0]; a.c_state = hc_state[1]; a.out_RT = h[l].RT;
                 a.layer_norm = l == 0;
                 a.ln_g = cx.W(m->off_ln_g); a.ln_b = cx.W(m->off_ln_b);
                 a.Wx = cx.W(m->off_rnn[l][0]); a.Wh = cx.W(m->off_rnn[l][1]); a.bias = cx.W(m->off_rnn[l][2]);
                 a.B = cx.B; a.T = cx.T; a.F = c.n_freq; a.E = src.C;
                 a.out = h[l].data;
-                if (m->opt_umma && m->rnn_umma_ok) {
+                if (cx.tensor_ok() && m->rnn_umma_ok) {
                     LstmArgs u = a;
                     if (m->opt_dbg_launch == -100 - l && m->dbg_buf) u.dbg = m->dbg_buf;
                     u.Wimg = cx.W(m->off_rnn_img[l]);
@@ -1245,6 +1279,8 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
     tap(cx, "w", w);
     if (!cx.dry) {
         BeamArgs a;
+        memset(&a, 0, sizeof(a));
+        a.step = cx.step; a.w_RT = w.RT; a.inpt_RT = inpt_RT;
         a.w = w.data; a.w_ld = w.C; a.inpt = inpt; a.B = cx.B; a.T = cx.T; a.F = c.n_freq; a.M = c.M; a.miso = c.topo_type == 1;
         a.out = out_dev;
         EAB_TRY(launch_beam(a, cx.st));
@@ -1259,6 +1295,41 @@ int plan(eab_model* m, int B, int T, size_t* stats_bytes, size_t* total_bytes) {
     *stats_bytes = cx.stats_off;
     *total_bytes = cx.stats_off + cx.act_peak;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- streaming
+// State blob layout (device, caller-owned): [0,256) absolute frame counter | carried hop [S][M][160] | iSTFT tail
+// [S][160] | spectrum ring [S][2][F][M][2] | output frame [S][2][F] | activation rings + LSTM state (run_forward order)
+struct StreamLayout {
+    size_t off_prev, off_tail, off_spec, off_out, off_act, total;
+};
+inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+
+int stream_layout(eab_model* m, int S, StreamLayout* L) {
+    const eab_config& c = m->cfg;
+    if (S < 1) return fail("stream: need at least one stream");
+    if (c.norm_type != 1) return fail("streaming needs norm_type='BN': InstanceNorm statistics span the whole utterance (EaBNet.py:684-686)");
+    if (!c.is_causal) return fail("streaming needs is_causal=True");
+    size_t o = 256;
+    L->off_prev = o; o += up256((size_t)S * c.M * 160 * sizeof(float));
+    L->off_tail = o; o += up256((size_t)S * 160 * sizeof(float));
+    L->off_spec = o; o += up256((size_t)S * 2 * c.n_freq * c.M * 2 * sizeof(float));
+    L->off_out = o;  o += up256((size_t)S * 2 * c.n_freq * sizeof(float));
+    L->off_act = o;
+    Ctx cx;
+    cx.m = m; cx.dry = true; cx.base = nullptr; cx.B = S; cx.T = 1; cx.st = nullptr; cx.streaming = true;
+    EAB_TRY(run_forward(cx, nullptr, nullptr));
+    if (cx.stats_off != 0) return fail("internal: streaming plan allocated statistics");
+    L->total = o + cx.act_peak;
+    return 0;
+}
+
+int stream_forward(eab_model* m, char* state, const StreamLayout& L, int S, cudaStream_t st) {
+    if (m->dirty) return fail("parameters not committed: call eab_commit_params first");
+    Ctx cx;
+    cx.m = m; cx.dry = false; cx.base = state + L.off_act; cx.B = S; cx.T = 1; cx.st = st;
+    cx.streaming = true; cx.step = reinterpret_cast<const int*>(state);
+    return run_forward(cx, reinterpret_cast<const float*>(state + L.off_spec), reinterpret_cast<float*>(state + L.off_out));
 }
 
 int forward(eab_model* m, const float* inpt, float* out, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -1302,6 +1373,11 @@ void eab_destroy(eab_model* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
     if (m->scratch) cudaFree(m->scratch);
+    if (m->s_in) {
+        cudaStreamDestroy(m->s_in);
+        cudaStreamDestroy(m->s_out);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_comp[i]); cudaEventDestroy(m->ev_out[i]); }
+    }
     delete m;
 }
 
@@ -1397,13 +1473,21 @@ int eab_enhance(eab_model* m, const float* wave, float* enhanced, int B, int L, 
     return rc;
 }
 
-int eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host, int B, int L, void* stream) {
-    if (!m || !wave_host || !enhanced_host) return fail("eab_enhance_host: null argument");
+// Host front door.  Batch i+1 is uploaded (copy stream) and batch i-1 downloaded (second copy stream) while batch i
+// computes on the caller's stream: two device input slots, two output slots, one workspace.
+int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float* const* enhanced_host, int n_batches,
+                             int B, int L, void* stream) {
+    if (!m || !waves_host || !enhanced_host) return fail("eab_enhance_host_batches: null argument");
+    if (n_batches < 1) return 0;
+    for (int i = 0; i < n_batches; ++i)
+        if (!waves_host[i] || !enhanced_host[i]) return fail("eab_enhance_host_batches: null batch pointer");
     const size_t need = eab_enhance_workspace_bytes(m, B, L);
-    if (!need) return fail("eab_enhance_host: bad shape");
-    const size_t in_b = align256((size_t)B * m->cfg.M * L * sizeof(float));
-    const size_t out_b = align256((size_t)B * 160 * (L / 160) * sizeof(float));
-    const size_t total = in_b + out_b + need;
+    if (!need) return fail("eab_enhance_host_batches: bad shape");
+    const int nslot = n_batches > 1 ? 2 : 1;
+    const size_t in_bytes = (size_t)B * m->cfg.M * L * sizeof(float);
+    const size_t out_bytes = (size_t)B * 160 * (L / 160) * sizeof(float);
+    const size_t in_b = align256(in_bytes), out_b = align256(out_bytes);
+    const size_t total = nslot * (in_b + out_b) + need;
     if (m->scratch_bytes < total) {
         if (m->scratch) cudaFree(m->scratch);
         m->scratch = nullptr;
@@ -1411,14 +1495,116 @@ int eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host,
         EAB_CUDA(cudaMalloc(&m->scratch, total));
         m->scratch_bytes = total;
     }
+    if (!m->s_in) {
+        EAB_CUDA(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
+        EAB_CUDA(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            EAB_CUDA(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
+            EAB_CUDA(cudaEventCreateWithFlags(&m->ev_comp[i], cudaEventDisableTiming));
+            EAB_CUDA(cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming));
+        }
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* p = static_cast<char*>(m->scratch);
-    float* din = reinterpret_cast<float*>(p);
-    float* dout = reinterpret_cast<float*>(p + in_b);
-    EAB_CUDA(cudaMemcpyAsync(din, wave_host, (size_t)B * m->cfg.M * L * sizeof(float), cudaMemcpyHostToDevice, st));
-    EAB_TRY(eab_enhance(m, din, dout, B, L, p + in_b + out_b, need, stream));
-    EAB_CUDA(cudaMemcpyAsync(enhanced_host, dout, (size_t)B * 160 * (L / 160) * sizeof(float), cudaMemcpyDeviceToHost, st));
+    float* din[2] = {reinterpret_cast<float*>(p), reinterpret_cast<float*>(p + (nslot - 1) * in_b)};
+    float* dout[2] = {reinterpret_cast<float*>(p + nslot * in_b), reinterpret_cast<float*>(p + nslot * in_b + (nslot - 1) * out_b)};
+    char* ws = p + nslot * (in_b + out_b);
+    // the copy streams start after everything already queued on the caller's stream (scratch may still be in use)
+    EAB_CUDA(cudaEventRecord(m->ev_comp[0], st));
+    EAB_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_comp[0], 0));
+    int launches = 0;
+    for (int i = 0; i < n_batches; ++i) {
+        const int s = i & 1;
+        if (i >= 2) EAB_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_comp[s], 0));          // batch i-2 has consumed this input slot
+        EAB_CUDA(cudaMemcpyAsync(din[s], waves_host[i], in_bytes, cudaMemcpyHostToDevice, m->s_in));
+        EAB_CUDA(cudaEventRecord(m->ev_in[s], m->s_in));
+        EAB_CUDA(cudaStreamWaitEvent(st, m->ev_in[s], 0));
+        if (i >= 2) EAB_CUDA(cudaStreamWaitEvent(st, m->ev_out[s], 0));                // batch i-2 has left this output slot
+        EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, stream));
+        launches += m->last_launches;
+        EAB_CUDA(cudaEventRecord(m->ev_comp[s], st));
+        EAB_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_comp[s], 0));
+        EAB_CUDA(cudaMemcpyAsync(enhanced_host[i], dout[s], out_bytes, cudaMemcpyDeviceToHost, m->s_out));
+        EAB_CUDA(cudaEventRecord(m->ev_out[s], m->s_out));
+    }
+    m->last_launches = launches;
+    EAB_CUDA(cudaStreamSynchronize(m->s_out));
     EAB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host, int B, int L, void* stream) {
+    if (!m || !wave_host || !enhanced_host) return fail("eab_enhance_host: null argument");
+    return eab_enhance_host_batches(m, &wave_host, &enhanced_host, 1, B, L, stream);
+}
+
+size_t eab_stream_state_bytes(const eab_model* m, int n_streams) {
+    StreamLayout L;
+    if (!m || stream_layout(const_cast<eab_model*>(m), n_streams, &L)) return 0;
+    return L.total;
+}
+
+static int stream_check(eab_model* m, void* state, size_t state_bytes, int S, StreamLayout* L) {
+    if (!m || !state) return fail("eab_stream: null argument");
+    EAB_TRY(stream_layout(m, S, L));
+    if (state_bytes < L->total) return fail("stream state too small: need " + std::to_string(L->total) + " bytes");
+    if ((reinterpret_cast<uintptr_t>(state) & 255) != 0) return fail("stream state must be 256-byte aligned");
+    return 0;
+}
+
+int eab_stream_reset(eab_model* m, void* state, size_t state_bytes, int n_streams, void* stream) {
+    StreamLayout L;
+    EAB_TRY(stream_check(m, state, state_bytes, n_streams, &L));
+    EAB_CUDA(cudaMemsetAsync(state, 0, L.total, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int eab_stream_step_spec(eab_model* m, void* state, size_t state_bytes, const float* frame, float* out_frame, int n_streams,
+                         void* stream) {
+    StreamLayout L;
+    EAB_TRY(stream_check(m, state, state_bytes, n_streams, &L));
+    if (!frame || !out_frame) return fail("eab_stream_step_spec: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* p = static_cast<char*>(state);
+    const eab_config& c = m->cfg;
+    reset_launch_count();
+    {   // new spectrum frame -> slot (*step % 2) of the spectrum ring
+        CombineArgs a;
+        memset(&a, 0, sizeof(a));
+        a.nsrc = 1;
+        a.src[0].x = frame; a.src[0].C = 2 * c.M; a.src[0].xf = xform_identity(); a.src[0].RT = 1;
+        a.B = n_streams; a.P = c.n_freq; a.C = 2 * c.M;
+        a.out = reinterpret_cast<float*>(p + L.off_spec); a.out_RT = 2;
+        a.step = reinterpret_cast<const int*>(p);
+        EAB_TRY(launch_combine(a, st));
+    }
+    EAB_TRY(stream_forward(m, p, L, n_streams, st));
+    const size_t out_bytes = (size_t)n_streams * (c.topo_type == 1 ? 2 : 2 * c.n_freq) * sizeof(float);
+    EAB_CUDA(cudaMemcpyAsync(out_frame, p + L.off_out, out_bytes, cudaMemcpyDeviceToDevice, st));
+    EAB_TRY(launch_step_advance(reinterpret_cast<int*>(p), st));
+    m->last_launches = launch_count();
+    return 0;
+}
+
+int eab_stream_step(eab_model* m, void* state, size_t state_bytes, const float* hop, float* enhanced_hop, int n_streams,
+                    void* stream) {
+    StreamLayout L;
+    EAB_TRY(stream_check(m, state, state_bytes, n_streams, &L));
+    if (!hop || !enhanced_hop) return fail("eab_stream_step: null argument");
+    const eab_config& c = m->cfg;
+    if (c.topo_type == 1) return fail("eab_stream_step: the 'miso' topology returns [B,2,T], which has no iSTFT");
+    if (c.n_freq != 161) return fail("eab_stream_step: the 320-point STFT gives 161 bins");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* p = static_cast<char*>(state);
+    int* step = reinterpret_cast<int*>(p);
+    reset_launch_count();
+    EAB_TRY(launch_stft_frame(hop, reinterpret_cast<float*>(p + L.off_prev), reinterpret_cast<float*>(p + L.off_spec), 2, step,
+                              n_streams, c.M, st));
+    EAB_TRY(stream_forward(m, p, L, n_streams, st));
+    EAB_TRY(launch_istft_frame(reinterpret_cast<const float*>(p + L.off_out), reinterpret_cast<float*>(p + L.off_tail),
+                               enhanced_hop, step, n_streams, st));
+    EAB_TRY(launch_step_advance(step, st));
+    m->last_launches = launch_count();
     return 0;
 }
 

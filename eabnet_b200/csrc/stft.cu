@@ -226,7 +226,136 @@ __global__ void __launch_bounds__(THREADS) istft_kernel(const float* __restrict_
     }
 }
 
-constexpr size_t kSmemBytes = (size_t)(2 * NF * RB + RB * NCOL) * sizeof(float);   // both kernels
+constexpr size_t kSmemBytes = (size_t)(2 * NF * RB + RB * NCOL) * sizeof(float);   // all four kernels
+
+// ------------------------------------------------------------------------------------------------ streaming
+// Frame n of the centred STFT covers samples [160 n - 160, 160 n + 160): the previous hop (carried) and the new one.
+// Frame 0's first half is the reflection of hop 0 (sample 160 - k at position k; position 0 is multiplied by
+// hann[0] = 0, so the one sample that would come from hop 1 never matters).  grid (ceil(S / SG)), rows = (stream, mic).
+__global__ void __launch_bounds__(THREADS) stft_frame_kernel(const float* __restrict__ hop, float* __restrict__ prev,
+                                                             float* __restrict__ spec, int spec_RT,
+                                                             const int* __restrict__ step_p, const float* __restrict__ tab,
+                                                             const float* __restrict__ win, int S, int M, int SG) {
+    extern __shared__ __align__(16) float dsm[];
+    float* Aev = dsm;
+    float* Aod = Aev + NF * RB;
+    float2* Xs = reinterpret_cast<float2*>(Aod + NF * RB);
+    pdl_trigger();
+    pdl_wait();
+    const int step = *step_p;
+    const int s0 = blockIdx.x * SG;
+    const int nrows = SG * M;
+    const int col = threadIdx.x;
+    for (int i = threadIdx.x; i < RB * NF; i += THREADS) {
+        const int r = i / NF, k = i - r * NF;
+        float ev = 0.f, od = 0.f;
+        const int sl = r / M, m = r - sl * M;
+        if (r < nrows && s0 + sl < S) {
+            const float* cur = hop + ((size_t)(s0 + sl) * M + m) * HOP;
+            const float* pv = prev + ((size_t)(s0 + sl) * M + m) * HOP;
+            auto sample = [&](int n) -> float {
+                float x;
+                if (n >= HOP) x = __ldg(cur + n - HOP);
+                else if (step > 0) x = pv[n];
+                else x = n == 0 ? 0.f : __ldg(cur + HOP - n);
+                return x * __ldg(win + n);
+            };
+            const float g0 = sample(k);
+            if (k == 0 || k == HOP) {
+                ev = g0;
+            } else {
+                const float g1 = sample(NFFT - k);
+                ev = g0 + g1;
+                od = g0 - g1;
+            }
+        }
+        Aev[k * RB + r] = ev;
+        Aod[k * RB + r] = od;
+    }
+    __syncthreads();
+    // the carried hop: every read of `prev` above is complete
+    for (int i = threadIdx.x; i < nrows * HOP; i += THREADS) {
+        const int r = i / HOP, n = i - r * HOP;
+        const int sl = r / M, m = r - sl * M;
+        if (s0 + sl < S) {
+            const size_t o = ((size_t)(s0 + sl) * M + m) * HOP + n;
+            prev[o] = __ldg(hop + o);
+        }
+    }
+    if (col < NCOL) {
+        float acc[RB];
+        column_gemm(col < NF ? Aev : Aod, tab, col, acc);
+        const int f = col < NF ? col : col - NF;
+        float* xs = reinterpret_cast<float*>(Xs);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) xs[(r * NF + f) * 2 + (col < NF ? 0 : 1)] = acc[r];
+    }
+    __syncthreads();
+    const int slot = ring_slot(step, spec_RT);
+    for (int i = threadIdx.x; i < RB * NF; i += THREADS) {
+        const int r = i / NF, f = i - r * NF;
+        const int sl = r / M, m = r - sl * M;
+        if (r < nrows && s0 + sl < S) {
+            float2 z = Xs[r * NF + f];
+            const float mag = sqrtf(z.x * z.x + z.y * z.y);
+            const float sc = mag > 0.f ? rsqrtf(mag) : 0.f;
+            z.x *= sc;
+            z.y *= sc;
+            reinterpret_cast<float2*>(spec)[(((size_t)(s0 + sl) * spec_RT + slot) * NF + f) * M + m] = z;
+        }
+    }
+}
+
+// Spectrum frame n [S][2][161] -> windowed inverse DFT; output hop n-1 = (second half of frame n-1, carried in `tail`,
+// + first half of frame n) / envelope.  The first call (n == 0) emits zeros.  grid (ceil(S / RB)), rows = streams.
+__global__ void __launch_bounds__(THREADS) istft_frame_kernel(const float* __restrict__ frame, float* __restrict__ tail,
+                                                              float* __restrict__ hop_out, const int* __restrict__ step_p,
+                                                              const float* __restrict__ tab, const float* __restrict__ win,
+                                                              const float* __restrict__ ienv, int S) {
+    extern __shared__ __align__(16) float dsm[];
+    float* Are = dsm;
+    float* Aim = Are + NF * RB;
+    float* PQ = Aim + NF * RB;
+    pdl_trigger();
+    pdl_wait();
+    const int step = *step_p;
+    const int s0 = blockIdx.x * RB;
+    for (int i = threadIdx.x; i < RB * NF; i += THREADS) {
+        const int r = i / NF, f = i - r * NF;
+        float re = 0.f, im = 0.f;
+        if (s0 + r < S) {
+            re = __ldg(frame + ((size_t)(s0 + r) * 2 + 0) * NF + f);
+            im = __ldg(frame + ((size_t)(s0 + r) * 2 + 1) * NF + f);
+        }
+        Are[f * RB + r] = re;
+        Aim[f * RB + r] = im;
+    }
+    __syncthreads();
+    const int col = threadIdx.x;
+    if (col < NCOL) {
+        float acc[RB];
+        column_gemm(col < NF ? Are : Aim, tab, col, acc);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) PQ[r * NCOL + col] = acc[r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RB * HOP; i += THREADS) {
+        const int r = i / HOP, n = i - r * HOP;
+        if (s0 + r >= S) continue;
+        const float* P = PQ + r * NCOL;
+        const float first = P[n] - P[NF + n];                       // s[n]
+        const float second = P[HOP - n] + P[NF + HOP - n];          // s[n + 160]
+        const size_t o = (size_t)(s0 + r) * HOP + n;
+        hop_out[o] = step > 0 ? (tail[o] + __ldg(win + n) * first) * __ldg(ienv + n) : 0.f;
+        tail[o] = __ldg(win + n + HOP) * second;
+    }
+}
+
+__global__ void step_advance_kernel(int* step) {
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x == 0) *step += 1;
+}
 
 }  // namespace
 
@@ -245,6 +374,48 @@ int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_
     ProfScope ps("stft", 2.0 * NF * NCOL * (double)B * M * T, 4.0 * ((double)B * M * L + (double)B * T * NF * M * 2), st);
     EAB_CUDA(launch_k(stft_kernel, dim3((T + FR - 1) / FR, B), dim3(THREADS), kSmemBytes, st, wave, spec, (const float*)t->fwd, (const float*)t->win, B, M, L, T));
     EAB_LAUNCH_CHECK("stft_kernel");
+    return 0;
+}
+
+static int configure_smem() {
+    static bool configured = false;
+    if (!configured) {
+        EAB_CUDA(cudaFuncSetAttribute(stft_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        EAB_CUDA(cudaFuncSetAttribute(istft_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        configured = true;
+    }
+    return 0;
+}
+
+int launch_stft_frame(const float* hop, float* prev_hop, float* spec_ring, int spec_RT, const int* step, int S, int M,
+                      cudaStream_t st) {
+    if (S <= 0 || M <= 0 || M > RB) return fail("stft_frame: bad shape (at most 24 microphones)");
+    Tables* t;
+    EAB_TRY(get_tables(&t));
+    EAB_TRY(configure_smem());
+    const int SG = RB / M;
+    ProfScope ps("stft_frame", 2.0 * NF * NCOL * (double)S * M, 4.0 * ((double)S * M * HOP * 3 + (double)S * NF * M * 2), st);
+    EAB_CUDA(launch_k(stft_frame_kernel, dim3((S + SG - 1) / SG), dim3(THREADS), kSmemBytes, st, hop, prev_hop, spec_ring,
+                      spec_RT, step, (const float*)t->fwd, (const float*)t->win, S, M, SG));
+    EAB_LAUNCH_CHECK("stft_frame_kernel");
+    return 0;
+}
+
+int launch_istft_frame(const float* frame, float* tail, float* hop_out, const int* step, int S, cudaStream_t st) {
+    if (S <= 0) return fail("istft_frame: bad shape");
+    Tables* t;
+    EAB_TRY(get_tables(&t));
+    EAB_TRY(configure_smem());
+    ProfScope ps("istft_frame", 2.0 * NF * NCOL * (double)S, 4.0 * ((double)S * 2 * NF + (double)S * HOP * 3), st);
+    EAB_CUDA(launch_k(istft_frame_kernel, dim3((S + RB - 1) / RB), dim3(THREADS), kSmemBytes, st, frame, tail, hop_out, step,
+                      (const float*)t->inv, (const float*)t->win, (const float*)t->ienv, S));
+    EAB_LAUNCH_CHECK("istft_frame_kernel");
+    return 0;
+}
+
+int launch_step_advance(int* step, cudaStream_t st) {
+    EAB_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(32), (size_t)0, st, step));
+    EAB_LAUNCH_CHECK("step_advance_kernel");
     return 0;
 }
 

@@ -227,6 +227,34 @@ class EaBNet(nn.Module):
                        "eab_enhance_host")
         return out
 
+    def enhance_host_batches(self, waves, outs=None, device: torch.device | str = "cuda"):
+        """A list of HOST batches [B,M,L] (same shape, ideally pinned) -> list of HOST enhanced batches.  Uploads,
+        compute and downloads of consecutive batches overlap (eab_enhance_host_batches)."""
+        if not waves:
+            return []
+        B, M, L = waves[0].shape
+        for w in waves:
+            if w.is_cuda or w.dtype != torch.float32 or tuple(w.shape) != (B, M, L) or not w.is_contiguous():
+                raise TypeError("enhance_host_batches takes contiguous float32 CPU tensors of one shape")
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if outs is None:
+            outs = [torch.empty((B, 160 * (L // 160)), dtype=torch.float32, pin_memory=True) for _ in waves]
+        n = len(waves)
+        wp = (C.c_void_p * n)(*[_ptr(w) for w in waves])
+        op = (C.c_void_p * n)(*[_ptr(o) for o in outs])
+        with torch.cuda.device(dev):
+            self._sync_params(dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._native.lib.eab_enhance_host_batches(self._native.h, wp, op, n, B, L, stream),
+                       "eab_enhance_host_batches")
+        return outs
+
+    def stream(self, n_streams: int, device: torch.device | str | None = None) -> "EaBNetStream":
+        """Carried-state, frame-by-frame inference for `n_streams` concurrent causal streams (eab_stream_*)."""
+        return EaBNetStream(self, n_streams, device)
+
     # ---------------------------------------------------------------- introspection for tests / bench
     def last_launch_count(self) -> int:
         return int(self._native.lib.eab_last_launch_count(self._native.h))
@@ -259,6 +287,80 @@ class EaBNet(nn.Module):
             raise RuntimeError("debug_tap(%s): got %d elements, expected %d (%s)" % (
                 name, n, dst.numel(), (self._native.lib.eab_last_error() or b"").decode()))
         return dst
+
+
+class EaBNetStream:
+    """`n_streams` concurrent causal streams stepped one 10 ms hop at a time (BASELINE configs[2]).
+
+    step(hop [S,M,160])            -> enhanced hop [S,160], delayed by one hop (overlap-add needs the next frame)
+    step_spec(frame [S,F,M,2])     -> [S,2,F], the column EaBNet.forward would produce for this frame
+    Frame n of the result equals frame n of the offline forward on the whole signal (is_causal=True, norm_type='BN').
+    With graph=True the whole step (stft frame, ~270 layer kernels, istft frame) is captured once into a CUDA graph
+    and replayed: the frame counter lives in device memory, so the captured launches never change."""
+
+    def __init__(self, net: EaBNet, n_streams: int, device=None, graph: bool = False):
+        dev = torch.device(device) if device is not None else next(net.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("eabnet_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.net, self.S, self.dev, self.use_graph = net, int(n_streams), dev, graph
+        lib, h = net._native.lib, net._native.h
+        nbytes = lib.eab_stream_state_bytes(h, self.S)
+        if nbytes == 0:
+            _lib.check(1, "eab_stream_state_bytes")
+        self.state = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._graph = None
+        self._hop_in = self._hop_out = None
+        self.reset()
+
+    def reset(self) -> None:
+        with torch.cuda.device(self.dev):
+            self.net._sync_params(self.dev)
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            _lib.check(self.net._native.lib.eab_stream_reset(self.net._native.h, _ptr(self.state), self.state.numel(),
+                                                             self.S, st), "eab_stream_reset")
+
+    def _launch(self, hop: torch.Tensor, out: torch.Tensor) -> None:
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        _lib.check(self.net._native.lib.eab_stream_step(self.net._native.h, _ptr(self.state), self.state.numel(),
+                                                        _ptr(hop), _ptr(out), self.S, st), "eab_stream_step")
+
+    def step(self, hop: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        if tuple(hop.shape) != (self.S, self.net.M, 160) or hop.dtype != torch.float32 or hop.device != self.dev:
+            raise ValueError("expected a float32 [%d,%d,160] tensor on %s" % (self.S, self.net.M, self.dev))
+        hop = hop.contiguous()
+        if out is None:
+            out = torch.empty((self.S, 160), dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            if not self.use_graph:
+                self._launch(hop, out)
+                return out
+            if self._graph is None:
+                self._hop_in, self._hop_out = torch.empty_like(hop), torch.empty_like(out)
+                self.net._sync_params(self.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch(self._hop_in, self._hop_out)
+                self._graph = g
+            self._hop_in.copy_(hop, non_blocking=True)
+            self._graph.replay()
+            out.copy_(self._hop_out, non_blocking=True)
+        return out
+
+    def step_spec(self, frame: torch.Tensor) -> torch.Tensor:
+        net = self.net
+        if frame.ndim == 3:
+            frame = frame.unsqueeze(-2)
+        if tuple(frame.shape) != (self.S, N_FREQ, net.M, 2) or frame.dtype != torch.float32 or frame.device != self.dev:
+            raise ValueError("expected a float32 [%d,%d,%d,2] tensor on %s" % (self.S, N_FREQ, net.M, self.dev))
+        frame = frame.contiguous()
+        out = torch.empty((self.S, 2) if net.topo_type == "miso" else (self.S, 2, N_FREQ), dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            _lib.check(net._native.lib.eab_stream_step_spec(net._native.h, _ptr(self.state), self.state.numel(),
+                                                            _ptr(frame), _ptr(out), self.S, st), "eab_stream_step_spec")
+        return out
 
 
 def numParams(net: nn.Module) -> int:

@@ -101,6 +101,31 @@ EAB_API int  eab_enhance(eab_model* m, const float* wave_dev, float* enhanced_de
  * keeps its own device scratch).  Synchronises the stream before returning. */
 EAB_API int  eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host, int B, int L, void* stream);
 
+/* Dataset-scale form of the same call (enhance.py's loop over files; BASELINE configs[3]): n_batches batches of B
+ * utterances, waves_host[i] -> [B,M,L], enhanced_host[i] -> [B,160*(L/160)], HOST (ideally pinned) buffers.  The
+ * upload of batch i+1 and the download of batch i-1 run on the library's own copy streams while batch i computes on
+ * `stream` (double-buffered device slots).  Synchronises before returning. */
+EAB_API int  eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float* const* enhanced_host,
+                              int n_batches, int B, int L, void* stream);
+
+/* Causal frame-by-frame inference with carried state (BASELINE configs[2]; the reference has no streaming entry point --
+ * the semantics are those of EaBNet.forward restricted to is_causal=True (EaBNet.py:46-48): frame n of the output
+ * depends on input frames <= n only, so n_streams concurrent streams stepped one 10 ms hop at a time reproduce the
+ * offline result frame for frame).  Needs norm_type "BN" (InstanceNorm statistics span the whole utterance).
+ * The caller owns the state blob (device memory, 256-byte aligned, eab_stream_state_bytes(m, n_streams) bytes): conv
+ * history rings, TCM dilation rings, LSTM (h, c), the previous hop and the overlap-add tail.  One step launches
+ * kernels only (the frame counter lives in the state and is read on the device): it can be captured in a CUDA graph.
+ *   eab_stream_step      hop_dev [S][M][160] new samples -> enhanced_hop_dev [S][160], delayed by ONE hop (overlap-add
+ *                        needs the next frame): call k returns samples [160(k-1), 160k) of torch.istft's output
+ *                        (enhance.py:59-62); the first call returns zeros.
+ *   eab_stream_step_spec frame_dev [S][F][M][2] (one column of prepare_data's output) -> out_frame_dev [S][2][F]. */
+EAB_API size_t eab_stream_state_bytes(const eab_model* m, int n_streams);
+EAB_API int  eab_stream_reset(eab_model* m, void* state_dev, size_t state_bytes, int n_streams, void* stream);
+EAB_API int  eab_stream_step(eab_model* m, void* state_dev, size_t state_bytes, const float* hop_dev,
+                     float* enhanced_hop_dev, int n_streams, void* stream);
+EAB_API int  eab_stream_step_spec(eab_model* m, void* state_dev, size_t state_bytes, const float* frame_dev,
+                          float* out_frame_dev, int n_streams, void* stream);
+
 /* Introspection used by tests and bench: number of kernels launched by the last forward/enhance call, and a
  * copy of a named intermediate of the last eab_forward ("en.0".."en.4", "tcm", "de.0".."de.3", "embed",
  * "h1", "h2", "w") with its normalisation/activation applied, channels-last [B,T,F',C'].  Returns the

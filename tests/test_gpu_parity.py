@@ -138,6 +138,18 @@ def test_enhance_wave_to_wave_and_si_sdr():
     assert abs(O.si_sdr(s, got[0].numpy()) - O.si_sdr(s, ref[0].numpy())) <= 0.05
 
 
+def test_enhance_host_batches_matches_single_calls():
+    """dataset-scale front door: 5 host batches through the double-buffered pipeline == 5 single device calls"""
+    cfg = O.make_cfg()
+    net, _ = _net(cfg, seed=2)
+    waves = [O.make_wave(2, 9, 4800, seed=40 + i)[0].pin_memory() for i in range(5)]
+    outs = net.enhance_host_batches(waves)
+    assert len(outs) == 5
+    with torch.no_grad():
+        for w, o in zip(waves, outs):
+            assert (net.enhance(w.cuda()).cpu() - o).abs().max() <= 1e-5
+
+
 def test_input_not_modified_and_repeatable():
     cfg = O.make_cfg()
     net, _ = _net(cfg)
