@@ -299,6 +299,28 @@ struct BeamArgs {
 };
 int launch_beam(const BeamArgs& a, cudaStream_t st);
 
+// streaming TCM stack in one launch (tcm_stream.cu); descriptors live in the stream state blob (device memory)
+struct TcmStreamDesc {
+    // offsets in floats into the model's weight blob (so a re-upload of the weights never invalidates a state)
+    long long W_in, W_dil, W_out;                        // fp32 CUDA-core layouts: [256][64], [kd][128][128], [64][256]
+    long long sL, hL, aL, sR, hR, aR, sO, hO, aO;        // folded BatchNorm scale / shift and PReLU slope per branch
+    long long ring_off;                                  // floats from act_base: history ring [S][RT][64] of the squeezed tensor
+    int RT;
+    int dt[8];
+    int pad_[5];
+};
+struct TcmStreamArgs {
+    const TcmStreamDesc* desc;
+    const float* blob;
+    int ntcm, p, kd, S;
+    const int* step;
+    float* act_base;
+    const float* x;  int x_RT;                           // [S][x_RT][256] residual stream entering the stack
+    float* out;      int out_RT;                         // [S][out_RT][256] sum of the group outputs
+};
+bool tcm_stream_supported(int cd1, int d_feat, int kd1);
+int launch_tcm_stream(const TcmStreamArgs& a, cudaStream_t st);
+
 int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st);
 int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st);
 // streaming front/back end (stft.cu): one hop in -> spectrum frame *step into a ring; spectrum frame -> one hop out

@@ -199,6 +199,7 @@ struct eab_model {
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
+    int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
     int opt_plane = 1;            // "stage once, shift by descriptor" kernel with fused producers (fallback)
     int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
@@ -737,6 +738,8 @@ struct Ctx {
     int next_RT = 0;          // ring size of the next allocation (0 = the default of 2: current + previous frame)
     int last_RT = 0;          // ring size of the last allocation (0 offline)
     bool tensor_ok() const { return m->opt_umma && !streaming; }
+    std::vector<TcmStreamDesc>* tcm_desc = nullptr;     // planning pass of eab_stream_reset: receives the descriptors
+    const TcmStreamDesc* tcm_desc_dev = nullptr;        // step: the table inside the state blob
 
     size_t act_peak = 0;
     float* alloc_act(size_t floats) {
@@ -1188,6 +1191,39 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
     r.F = 1;
     r.C = c.d_feat;
     r.xf = xform_identity();
+    Act acc;
+    if (cx.streaming && tcm_stream_supported(c.cd1, c.d_feat, c.kd1) && c.norm_type == 1 && m->opt_stream_tcm) {
+        // one launch for the whole stack (tcm_stream.cu): per-TCM history rings of the squeezed tensor + the group sum
+        std::vector<TcmStreamDesc> descs;
+        for (const TcmLayer& t : m->tcms) {
+            TcmStreamDesc d;
+            memset(&d, 0, sizeof(d));
+            int back = 0;
+            for (int i = 0; i < c.kd1; ++i) { d.dt[i] = t.dt[i]; back = std::max(back, t.dt[i]); }
+            cx.next_RT = back + 1;
+            float* ring = cx.alloc_act((size_t)cx.B * c.cd1);
+            d.RT = cx.last_RT;
+            d.ring_off = (long long)((reinterpret_cast<char*>(ring) - cx.base) / (ptrdiff_t)sizeof(float));
+            d.W_in = (long long)t.off_in; d.W_dil = (long long)t.off_dil; d.W_out = (long long)t.off_out;
+            d.sL = (long long)t.na_left.off_scale; d.hL = (long long)t.na_left.off_shift; d.aL = (long long)t.na_left.off_alpha;
+            d.sR = (long long)t.na_right.off_scale; d.hR = (long long)t.na_right.off_shift; d.aR = (long long)t.na_right.off_alpha;
+            d.sO = (long long)t.na_out.off_scale; d.hO = (long long)t.na_out.off_shift; d.aO = (long long)t.na_out.off_alpha;
+            descs.push_back(d);
+        }
+        acc.F = 1; acc.C = c.d_feat; acc.xf = xform_identity();
+        acc.data = cx.alloc_act((size_t)cx.B * c.d_feat);
+        acc.RT = cx.last_RT;
+        if (cx.tcm_desc) *cx.tcm_desc = descs;
+        if (!cx.dry) {
+            TcmStreamArgs a;
+            memset(&a, 0, sizeof(a));
+            a.desc = cx.tcm_desc_dev; a.blob = m->blob;
+            a.ntcm = (int)m->tcms.size(); a.p = c.p; a.kd = c.kd1; a.S = cx.B;
+            a.step = cx.step; a.act_base = reinterpret_cast<float*>(cx.base);
+            a.x = r.data; a.x_RT = r.RT; a.out = acc.data; a.out_RT = acc.RT;
+            EAB_TRY(launch_tcm_stream(a, cx.st));
+        }
+    } else {
     std::vector<Act> group_out;
     size_t ti = 0;
     for (int g = 0; g < c.q; ++g) {
@@ -1198,9 +1234,9 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
         }
         group_out.push_back(r);
     }
-    Act acc;
     if (c.q == 1) acc = group_out[0];
     else EAB_TRY(run_combine(cx, group_out.data(), c.q, &acc));
+    }
     acc.F = m->Fb;
     acc.C = 64;
     tap(cx, "tcm", acc);
@@ -1301,7 +1337,8 @@ int plan(eab_model* m, int B, int T, size_t* stats_bytes, size_t* total_bytes) {
 // State blob layout (device, caller-owned): [0,256) absolute frame counter | carried hop [S][M][160] | iSTFT tail
 // [S][160] | spectrum ring [S][2][F][M][2] | output frame [S][2][F] | activation rings + LSTM state (run_forward order)
 struct StreamLayout {
-    size_t off_prev, off_tail, off_spec, off_out, off_act, total;
+    size_t off_desc, off_prev, off_tail, off_spec, off_out, off_act, total;
+    std::vector<TcmStreamDesc> descs;
 };
 inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -1311,6 +1348,7 @@ int stream_layout(eab_model* m, int S, StreamLayout* L) {
     if (c.norm_type != 1) return fail("streaming needs norm_type='BN': InstanceNorm statistics span the whole utterance (EaBNet.py:684-686)");
     if (!c.is_causal) return fail("streaming needs is_causal=True");
     size_t o = 256;
+    L->off_desc = o; o += up256(m->tcms.size() * sizeof(TcmStreamDesc));
     L->off_prev = o; o += up256((size_t)S * c.M * 160 * sizeof(float));
     L->off_tail = o; o += up256((size_t)S * 160 * sizeof(float));
     L->off_spec = o; o += up256((size_t)S * 2 * c.n_freq * c.M * 2 * sizeof(float));
@@ -1318,6 +1356,7 @@ int stream_layout(eab_model* m, int S, StreamLayout* L) {
     L->off_act = o;
     Ctx cx;
     cx.m = m; cx.dry = true; cx.base = nullptr; cx.B = S; cx.T = 1; cx.st = nullptr; cx.streaming = true;
+    cx.tcm_desc = &L->descs;
     EAB_TRY(run_forward(cx, nullptr, nullptr));
     if (cx.stats_off != 0) return fail("internal: streaming plan allocated statistics");
     L->total = o + cx.act_peak;
@@ -1329,6 +1368,7 @@ int stream_forward(eab_model* m, char* state, const StreamLayout& L, int S, cuda
     Ctx cx;
     cx.m = m; cx.dry = false; cx.base = state + L.off_act; cx.B = S; cx.T = 1; cx.st = st;
     cx.streaming = true; cx.step = reinterpret_cast<const int*>(state);
+    cx.tcm_desc_dev = reinterpret_cast<const TcmStreamDesc*>(state + L.off_desc);
     return run_forward(cx, reinterpret_cast<const float*>(state + L.off_spec), reinterpret_cast<float*>(state + L.off_out));
 }
 
@@ -1555,7 +1595,13 @@ static int stream_check(eab_model* m, void* state, size_t state_bytes, int S, St
 int eab_stream_reset(eab_model* m, void* state, size_t state_bytes, int n_streams, void* stream) {
     StreamLayout L;
     EAB_TRY(stream_check(m, state, state_bytes, n_streams, &L));
-    EAB_CUDA(cudaMemsetAsync(state, 0, L.total, static_cast<cudaStream_t>(stream)));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    EAB_CUDA(cudaMemsetAsync(state, 0, L.total, st));
+    if (!L.descs.empty()) {
+        EAB_CUDA(cudaMemcpyAsync(static_cast<char*>(state) + L.off_desc, L.descs.data(), L.descs.size() * sizeof(TcmStreamDesc),
+                                 cudaMemcpyHostToDevice, st));
+        EAB_CUDA(cudaStreamSynchronize(st));       // the descriptor vector dies with this scope
+    }
     return 0;
 }
 
@@ -1635,6 +1681,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "pdl") g_use_pdl = value != 0;
     else if (n == "staged") m->opt_staged = value != 0;
     else if (n == "lazy") m->opt_lazy = value != 0;
+    else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
     else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
     else if (n == "dbg_launch") {

@@ -1,0 +1,160 @@
+// Streaming form of the whole squeezed-TCM stack (EaBNet.py:99-106, 506-578): ONE launch per frame step.
+//
+// Offline, a TCM is three GEMM launches over 38 464 rows.  In a streaming step every stream contributes a single row,
+// so the q*p = 18 TCMs are 54 matrix-vector products per stream that depend on each other: launch latency, not
+// arithmetic, is the cost (measured: 54 launches x ~0.1 ms of the 7.3 ms step).  Streams are independent, so a CTA
+// keeps SPC streams' residual vector x[256] in shared memory and walks all TCMs itself:
+//     y = W_in x                       (256 -> 64, no bias)            -> written to this TCM's history ring
+//     zL = sum_k W_L,k  nL(y[n - dt_k]),  zR = sum_k W_R,k nR(y[n - dt_k])   (n* = PReLU -> BatchNorm, zeros for n - dt < 0)
+//     x += W_out nO(zL * sigmoid(zR))  (64 -> 256)
+// and accumulates the group outputs (x after every p-th TCM).  Weights stream from L2 (fp32, the CUDA-core layouts).
+#include "common.cuh"
+
+namespace eab {
+
+namespace {
+
+constexpr int SPC = 2;          // streams per CTA
+constexpr int CD = 64;          // squeezed channels
+constexpr int DF = 256;         // feature channels
+constexpr int NT = 256;
+
+__device__ __forceinline__ float prelu_norm(float v, float a, float s, float h) {
+    v = v > 0.f ? v : a * v;
+    return fmaf(v, s, h);
+}
+
+__global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
+    __shared__ float xs[SPC][DF];
+    __shared__ float accs[SPC][DF];
+    __shared__ float ys[SPC][CD];
+    __shared__ float red[4][SPC][CD];
+    __shared__ float u[2][8][SPC][CD];        // [branch][tap][stream][channel] normalised dilated-conv inputs
+    __shared__ float zred[2][SPC][2 * CD];
+    __shared__ float uo[SPC][CD];
+    pdl_trigger();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int step = *a.step;
+    const int s0 = blockIdx.x * SPC;
+    const int xslot = ring_slot(step, a.x_RT);
+    for (int i = tid; i < SPC * DF; i += NT) {
+        const int s = i / DF, j = i - s * DF;
+        xs[s][j] = s0 + s < a.S ? a.x[((size_t)(s0 + s) * a.x_RT + xslot) * DF + j] : 0.f;
+        accs[s][j] = 0.f;
+    }
+    __syncthreads();
+    for (int l = 0; l < a.ntcm; ++l) {
+        const TcmStreamDesc& d = a.desc[l];
+        // ---------------------------------------------------------------- squeeze 1x1
+        {
+            const int n = tid & 63, kg = tid >> 6;
+            float p[SPC];
+#pragma unroll
+            for (int s = 0; s < SPC; ++s) p[s] = 0.f;
+            const float* w = a.blob + d.W_in + (size_t)(kg * 64) * CD + n;
+#pragma unroll 16
+            for (int k = 0; k < 64; ++k) {
+                const float wv = __ldg(w + (size_t)k * CD);
+#pragma unroll
+                for (int s = 0; s < SPC; ++s) p[s] = fmaf(xs[s][kg * 64 + k], wv, p[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < SPC; ++s) red[kg][s][n] = p[s];
+        }
+        __syncthreads();
+        float* ring = a.act_base + d.ring_off;
+        if (tid < SPC * CD) {
+            const int s = tid >> 6, n = tid & 63;
+            const float y = red[0][s][n] + red[1][s][n] + red[2][s][n] + red[3][s][n];
+            ys[s][n] = y;
+            if (s0 + s < a.S) ring[((size_t)(s0 + s) * d.RT + ring_slot(step, d.RT)) * CD + n] = y;
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- normalised taps of both branches
+        for (int i = tid; i < a.kd * SPC * CD; i += NT) {
+            const int tap = i / (SPC * CD);
+            const int r = i - tap * (SPC * CD);
+            const int s = r >> 6, c = r & 63;
+            const int n = step - d.dt[tap];
+            float vl = 0.f, vr = 0.f;
+            if (n >= 0 && s0 + s < a.S) {
+                const float v = d.dt[tap] == 0 ? ys[s][c] : ring[((size_t)(s0 + s) * d.RT + ring_slot(n, d.RT)) * CD + c];
+                vl = prelu_norm(v, __ldg(a.blob + d.aL + c), __ldg(a.blob + d.sL + c), __ldg(a.blob + d.hL + c));
+                vr = prelu_norm(v, __ldg(a.blob + d.aR + c), __ldg(a.blob + d.sR + c), __ldg(a.blob + d.hR + c));
+            }
+            u[0][tap][s][c] = vl;
+            u[1][tap][s][c] = vr;
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- dilated convs (block-diagonal packed weights)
+        {
+            const int col = tid & 127;                 // 0..63 left outputs, 64..127 right outputs
+            const int br = col >> 6;
+            const int half = tid >> 7;                 // channel half of the K range
+            float p[SPC];
+#pragma unroll
+            for (int s = 0; s < SPC; ++s) p[s] = 0.f;
+            for (int tap = 0; tap < a.kd; ++tap) {
+                const float* w = a.blob + d.W_dil + ((size_t)tap * 2 * CD + br * CD + half * 32) * (2 * CD) + col;
+#pragma unroll 16
+                for (int c = 0; c < 32; ++c) {
+                    const float wv = __ldg(w + (size_t)c * (2 * CD));
+#pragma unroll
+                    for (int s = 0; s < SPC; ++s) p[s] = fmaf(u[br][tap][s][half * 32 + c], wv, p[s]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SPC; ++s) zred[half][s][col] = p[s];
+        }
+        __syncthreads();
+        if (tid < SPC * CD) {
+            const int s = tid >> 6, n = tid & 63;
+            const float zl = zred[0][s][n] + zred[1][s][n];
+            const float zr = zred[0][s][CD + n] + zred[1][s][CD + n];
+            const float z = zl * sigmoid_f(zr);
+            uo[s][n] = prelu_norm(z, __ldg(a.blob + d.aO + n), __ldg(a.blob + d.sO + n), __ldg(a.blob + d.hO + n));
+        }
+        __syncthreads();
+        // ---------------------------------------------------------------- expand 1x1 + residual
+        {
+            float p[SPC];
+#pragma unroll
+            for (int s = 0; s < SPC; ++s) p[s] = xs[s][tid];
+            const float* w = a.blob + d.W_out + tid;
+#pragma unroll 16
+            for (int c = 0; c < CD; ++c) {
+                const float wv = __ldg(w + (size_t)c * DF);
+#pragma unroll
+                for (int s = 0; s < SPC; ++s) p[s] = fmaf(uo[s][c], wv, p[s]);
+            }
+            // xs[.][tid] is read and written by this thread only; uo / zred are next written two barriers from here
+#pragma unroll
+            for (int s = 0; s < SPC; ++s) {
+                xs[s][tid] = p[s];
+                if ((l + 1) % a.p == 0) accs[s][tid] += p[s];
+            }
+        }
+        __syncthreads();
+    }
+    const int oslot = ring_slot(step, a.out_RT);
+    for (int i = tid; i < SPC * DF; i += NT) {
+        const int s = i / DF, j = i - s * DF;
+        if (s0 + s < a.S) a.out[((size_t)(s0 + s) * a.out_RT + oslot) * DF + j] = accs[s][j];
+    }
+}
+
+}  // namespace
+
+bool tcm_stream_supported(int cd1, int d_feat, int kd1) { return cd1 == CD && d_feat == DF && kd1 >= 1 && kd1 <= 8; }
+
+int launch_tcm_stream(const TcmStreamArgs& a, cudaStream_t st) {
+    if (a.S < 1 || a.ntcm < 1 || a.p < 1) return fail("tcm_stream: bad arguments");
+    double macs = (double)a.ntcm * (DF * CD + 2.0 * a.kd * CD * CD + CD * DF);
+    ProfScope ps("tcm_stream", 2.0 * macs * a.S, 4.0 * macs * ((a.S + SPC - 1) / SPC), st);
+    EAB_CUDA(launch_k(tcm_stream_kernel, dim3((a.S + SPC - 1) / SPC), dim3(NT), (size_t)0, st, a));
+    EAB_LAUNCH_CHECK("tcm_stream_kernel");
+    return 0;
+}
+
+}  // namespace eab
