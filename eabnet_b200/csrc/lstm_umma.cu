@@ -1,17 +1,21 @@
 // nn.LSTM(64 -> 64) layer of LSTM_BF (EaBNet.py:591-592, 610-611) on the tensor cores (sm_100a), fp32-grade.
 //
 // One CTA owns 128 (b,f) sequences for all T steps.  Per step the gate pre-activations
-//     G[128 x 256] = [x_t | h_{t-1}] (K = 128)  x  [W_ih ; W_hh]^T
-// are three tcgen05.mma.kind::f16 passes (hi*hi + lo*hi + hi*lo of an fp16 split, i.e. ~22 mantissa bits) into a
+//     G[128 x 256] = x_t W_ih^T + h_{t-1} W_hh^T      (K = 64 + 64)
+// are three tcgen05.mma.kind::f16 passes each (hi*hi + lo*hi + hi*lo of an fp16 split, i.e. ~22 mantissa bits) into a
 // 256-column TMEM accumulator.  The weight images (128 KB) stay resident in shared memory for the whole sequence,
 // the cell state lives in registers, and h_t goes straight back into the swizzled A operand of step t+1.
+// Only the recurrent half sits on the T-serial chain: the accumulator is double-buffered (2 x 256 TMEM columns) and the
+// input projection of step t+1 is issued right behind the recurrent MMAs of step t, so it executes while the cell warps
+// work on step t.  Gate columns are ordered so that BOTH column halves hold 8 hidden units of every cell thread: all 16
+// cell warps start on the first half while the tensor core finishes the second.
 //
-//   warps 0-7   cell warps  : two threads per sequence (32 hidden units each): tcgen05.ld gates, bias, sigmoid/tanh,
+//   warps 0-15  cell warps  : four threads per sequence (16 hidden units each): tcgen05.ld gates, bias, sigmoid/tanh,
 //                             c/h update, h_t -> HBM (fp32) and -> A operand (fp16 hi/lo), arrive
-//   warps 8-11  x producers : one thread per sequence: prefetch x_{t+1} (256 B) from HBM a step ahead, apply the
-//                             decoder's norm + PReLU and the head's LayerNorm (thread-local over the 64 channels),
-//                             split to fp16 hi/lo, store to the A operand once MMA(t) has released it, arrive
-//   warp 12     MMA issuer  : waits for both operand halves, issues 24 MMAs (M128 x N256 x K16), commits
+//   warps 16-19 x producers : one thread per sequence: prefetch x from HBM two steps ahead, apply the decoder's norm +
+//                             PReLU and the head's LayerNorm (thread-local over the 64 channels), split to fp16 hi/lo,
+//                             store to the A operand once the input-projection MMAs have released it, arrive
+//   warp 20     MMA issuer  : h-part of step t (24 MMAs M128 x N128 x K16, two commits), then x-part of step t+1
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -23,14 +27,25 @@ using namespace umma;
 
 constexpr int H = 64;
 constexpr int ROWS = 128;
+#ifdef EAB_LSTM_SUSPEND
+#define MBW mbar_wait
+#else
+#define MBW mbar_wait_spin
+#endif
 
 __device__ __forceinline__ float ex2(float x) {          // one SFU op, ~2 ulp
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-constexpr int NCELL = 512, NXP = 128, NTHREADS = NCELL + NXP + 32;      // 16 cell warps, 4 x-producer warps, 1 MMA warp
-constexpr int MMA_WARP = (NCELL + NXP) / 32;
+// 96 of the 128 MMA rows carry sequences: 10 304 sequences (64 x 161) then make 108 CTAs - one wave over 148 SMs with
+// 25 % less cell work per CTA than 81 CTAs of 128 (the step time is the cell phase, not the tensor pipe).  A warp may
+// only touch TMEM lanes 32 (warp % 4) ... + 32, so warps 0-15 with warp % 4 == 3 would own the empty lane quadrant:
+// they are x producers instead, next to warps 16-17.
+constexpr int RPC = 96;                                 // sequences per CTA
+constexpr int NCELL = 4 * RPC, NXP = 2 * RPC;           // 12 cell warps (4 threads per row), 6 producer warps (2 per row)
+constexpr int MMA_WARP = 18;
+constexpr int NTHREADS = 19 * 32;
 constexpr int SLAB_BYTES = ROWS * 128;                 // one 64-wide fp16 K slab of the A operand
 constexpr int A_BYTES = 4 * SLAB_BYTES;                // [hi|lo][x|h]
 constexpr int B_SLAB_BYTES = 256 * 128;                // one K slab of the weight image (256 gate rows)
@@ -50,25 +65,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
     float* lng = coef + 2 * 3 * 64;
     float* lnb = lng + 64;
     uint64_t* bars = reinterpret_cast<uint64_t*>(lnb + 64);
-    uint64_t* a_ready = bars;                   // operand of the next step complete (cells: h, producers: x)
+    uint64_t* h_ready = bars;                   // h_{t-1} is in the A operand (all cell threads)
     uint64_t* acc_full = bars + 1;              // [2] gate columns [0,128) / [128,256) of the current step complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* x_ready = bars + 3;               // x_t is in the A operand (all producer threads)
+    uint64_t* x_free = bars + 4;                // the input-projection MMAs have consumed the x operand
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int NQ = a.B * a.F;
-    const int q0 = blockIdx.x * ROWS;
+    const int q0 = blockIdx.x * RPC;
     const int b0 = q0 / a.F;
 
     if (tid == 0) {
-        mbar_init(a_ready, NCELL + NXP);
+        mbar_init(h_ready, NCELL);
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
+        mbar_init(x_ready, NXP);
+        mbar_init(x_free, 1);
         fence_barrier_init();
     }
     pdl_trigger();
-    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 256);
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.Wimg);
         uint4* dst = reinterpret_cast<uint4*>(Bs);
@@ -76,8 +95,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         pdl_wait();
         uint4* az = reinterpret_cast<uint4*>(As);
         for (int i = tid; i < A_BYTES / 16; i += NTHREADS) az[i] = make_uint4(0, 0, 0, 0);      // h_{-1} = 0
-        for (int i = tid; i < 256; i += NTHREADS)       // image row order: quarter*64 + gate*16 + jj; gate 2 (g) feeds tanh
-            sbias[i] = __ldg(a.bias + i) * (((i >> 4) & 3) == 2 ? -2.f : -1.f) * 1.4426950408889634f;
+        for (int i = tid; i < 256; i += NTHREADS)       // image row order: half*128 + quarter*32 + gate*8 + j; gate 2 (g) feeds tanh
+            sbias[i] = __ldg(a.bias + i) * (((i >> 3) & 3) == 2 ? -2.f : -1.f) * 1.4426950408889634f;
         for (int i = tid; i < 2 * 64; i += NTHREADS) {
             const int bb = i >> 6, c = i & 63;
             float cs = 1.f, ch = 0.f, ca = 1.f;
@@ -97,9 +116,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < NCELL / 32) {
+    if (warp < 16 && (warp & 3) != 3) {
         // ======================================================================= cell warps
-        // thread = (sequence row, quarter of the hidden units): 16 units, gate columns quarter*64 + gate*16 + jj
+        // thread = (sequence row, quarter of the hidden units): units quarter*16 + u*8 + e, gate columns
+        // u*128 + quarter*32 + gate*8 + e of accumulator buffer t & 1
         const int quad = warp & 3;              // TMEM lane quadrant
         const int qtr = warp >> 2;              // which 16 hidden units
         const int row = quad * 32 + lane;
@@ -109,33 +129,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         const int fq = valid ? q - bq * a.F : 0;
         float* outp = a.out + (((size_t)bq * a.T) * a.F + fq) * H + qtr * 16;
         const size_t ostep = (size_t)a.F * H;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qtr * 64);
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qtr * 32);
         uint8_t* hrow_hi = a_slab(As, 0, 1) + row * 128;
         uint8_t* hrow_lo = a_slab(As, 1, 1) + row * 128;
         float c[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) c[i] = 0.f;
-        mbar_arrive(a_ready);                   // h_{-1} = 0 is in place
+        mbar_arrive(h_ready);                   // h_{-1} = 0 is in place
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-        long long t_wait = 0, t_cell = 0, t_fence = 0;
+        long long t_wait = 0, t_cell = 0, t_fence = 0, t_w1 = 0;
         const long long t_start = dbg_on ? clock64() : 0;
         constexpr float L2E = 1.4426950408889634f;
         for (int t = 0; t < a.T; ++t) {
             const long long c0 = dbg_on ? clock64() : 0;
-            mbar_wait(&acc_full[qtr >> 1], (uint32_t)(t & 1));      // only this thread's half of the gate columns
-            const long long c1 = dbg_on ? clock64() : 0;
-            tc_fence_after();
+            long long c1 = 0;
+            const uint32_t taddr = taddr0 + (uint32_t)((t & 1) * 256);
             uint4 hst_hi[2], hst_lo[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {       // 8 hidden units at a time
+            for (int u = 0; u < 2; ++u) {       // 8 hidden units at a time: column half u
+                const long long w0 = dbg_on ? clock64() : 0;
+                MBW(&acc_full[u], (uint32_t)(t & 1));
+                if (dbg_on) { if (u == 0) c1 = clock64(); else t_w1 += clock64() - w0; }
+                tc_fence_after();
                 uint32_t gi[8], gf[8], gg[8], go[8];
-                tmem_ld8_nowait(taddr + 0 * 16 + u * 8, gi);
-                tmem_ld8_nowait(taddr + 1 * 16 + u * 8, gf);
-                tmem_ld8_nowait(taddr + 2 * 16 + u * 8, gg);
-                tmem_ld8_nowait(taddr + 3 * 16 + u * 8, go);
+                tmem_ld8_nowait(taddr + u * 128 + 0, gi);
+                tmem_ld8_nowait(taddr + u * 128 + 8, gf);
+                tmem_ld8_nowait(taddr + u * 128 + 16, gg);
+                tmem_ld8_nowait(taddr + u * 128 + 24, go);
                 tmem_wait_ld();
                 float hv[8];
-                const float* bi = sbias + qtr * 64 + u * 8;     // biases pre-scaled by -log2(e) (i,f,o) / -2 log2(e) (g)
+                const float* bi = sbias + u * 128 + qtr * 32;   // biases pre-scaled by -log2(e) (i,f,o) / -2 log2(e) (g)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     // 7 SFU ops per unit instead of 10: the sigmoid / tanh quotients share their reciprocals
@@ -144,9 +167,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                     // with Ei = e^-i, Ef = e^-f, Eg = e^-2g, Ec = e^-2c', Eo = e^-o.  The exponents are clamped from above
                     // only (2^40: the functions are saturated to < 1e-12 there and the triple product stays < 2^127).
                     const float Ei = ex2(fminf(fmaf(__uint_as_float(gi[e]), -L2E, bi[e]), 40.f));
-                    const float Ef = ex2(fminf(fmaf(__uint_as_float(gf[e]), -L2E, bi[16 + e]), 40.f));
-                    const float Eg = ex2(fminf(fmaf(__uint_as_float(gg[e]), -2.f * L2E, bi[32 + e]), 40.f));
-                    const float Eo = ex2(fminf(fmaf(__uint_as_float(go[e]), -L2E, bi[48 + e]), 40.f));
+                    const float Ef = ex2(fminf(fmaf(__uint_as_float(gf[e]), -L2E, bi[8 + e]), 40.f));
+                    const float Eg = ex2(fminf(fmaf(__uint_as_float(gg[e]), -2.f * L2E, bi[16 + e]), 40.f));
+                    const float Eo = ex2(fminf(fmaf(__uint_as_float(go[e]), -L2E, bi[24 + e]), 40.f));
                     const float A = 1.f + Ei, Bf = 1.f + Ef, G = 1.f + Eg;
                     const float AG = A * G;
                     const float cn = __fdividef(fmaf(c[u * 8 + e], AG, (1.f - Eg) * Bf), AG * Bf);
@@ -166,8 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                 hst_hi[u] = hi;
                 hst_lo[u] = lo;
             }
-            // h_t overwrites the operand that the second half's MMAs may still be reading: wait for them, then publish
-            mbar_wait(&acc_full[1], (uint32_t)(t & 1));
+            // h_t overwrites the operand the recurrent MMAs of this step read: both halves have completed (waited above)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int chunk = ((qtr * 2 + u) ^ (row & 7)) << 4;
@@ -177,39 +199,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
             const long long c2 = dbg_on ? clock64() : 0;
             tc_fence_before();
             fence_proxy_async();
-            if (t + 1 < a.T) mbar_arrive(a_ready);
+            if (t + 1 < a.T) mbar_arrive(h_ready);
             if (dbg_on) { t_wait += c1 - c0; t_cell += c2 - c1; t_fence += clock64() - c2; }
         }
-        if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wait; a.dbg[2] = t_cell; a.dbg[3] = t_fence; a.dbg[4] = a.T; }
+        if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wait; a.dbg[2] = t_cell; a.dbg[3] = t_fence; a.dbg[4] = a.T; a.dbg[6] = t_w1; }
     } else if (warp < MMA_WARP) {
-        // ======================================================================= x producers (one thread per row)
-        const int row = tid - NCELL;
+        // ======================================================================= x producers (two threads per row)
+        const int pidx = warp < 16 ? (warp >> 2) : warp - 12;       // 0..5
+        const int row = pidx * 16 + (lane >> 1);
+        const int half = lane & 1;                                   // channels half*32 .. +32
         const int q = q0 + row;
         const bool valid = q < NQ;
         const int bq = valid ? q / a.F : 0;
         const int fq = valid ? q - bq * a.F : 0;
-        const float* xp = a.src.x + (((size_t)bq * a.T) * a.F + fq) * H;
+        const float* xp = a.src.x + (((size_t)bq * a.T) * a.F + fq) * H + half * 32;
         const size_t xstep = (size_t)a.F * H;
-        const float* cf = coef + (valid ? bq - b0 : 0) * 3 * 64;
+        const float* cf = coef + (valid ? bq - b0 : 0) * 3 * 64 + half * 32;
+        const float* lg = lng + half * 32;
+        const float* lb = lnb + half * 32;
         const int mode = (a.src.xf.affine == 0 && a.src.xf.prelu == 0) ? 0 : (a.src.xf.prelu == 1 ? 2 : 1);
         uint8_t* xrow_hi = a_slab(As, 0, 0) + row * 128;
         uint8_t* xrow_lo = a_slab(As, 1, 0) + row * 128;
-        float4 xr[16];
+        float4 xr[8];
         auto load = [&](int t) {
             if (valid) {
                 const float4* p = reinterpret_cast<const float4*>(xp + (size_t)t * xstep);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) xr[i] = __ldg(p + i);
+                for (int i = 0; i < 8; ++i) xr[i] = __ldg(p + i);
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 8; ++i) xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         auto publish = [&]() {
             float* x = reinterpret_cast<float*>(xr);
             if (valid && mode != 0) {
 #pragma unroll
-                for (int k = 0; k < 64; ++k) {
+                for (int k = 0; k < 32; ++k) {
                     const float s = cf[k], h = cf[64 + k], al = cf[128 + k];
                     float v = x[k];
                     if (mode == 1) { v = fmaf(v, s, h); v = fmaxf(v, 0.f) + al * fminf(v, 0.f); }
@@ -217,26 +243,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                     x[k] = v;
                 }
             }
-            if (valid && a.layer_norm) {
+            if (a.layer_norm) {                  // uniform branch: every lane takes part in the pair shuffles
                 float sum = 0.f;
 #pragma unroll
-                for (int k = 0; k < 64; ++k) sum += x[k];
+                for (int k = 0; k < 32; ++k) sum += x[k];
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 const float mean = sum * (1.f / 64.f);
                 float sq = 0.f;
 #pragma unroll
-                for (int k = 0; k < 64; ++k) { const float d = x[k] - mean; sq += d * d; }
+                for (int k = 0; k < 32; ++k) { const float d = x[k] - mean; sq += d * d; }
+                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
                 const float rstd = rsqrtf(sq * (1.f / 64.f) + 1e-5f);
+                if (valid) {
 #pragma unroll
-                for (int k = 0; k < 64; ++k) x[k] = (x[k] - mean) * rstd * lng[k] + lnb[k];
+                    for (int k = 0; k < 32; ++k) x[k] = (x[k] - mean) * rstd * lg[k] + lb[k];
+                }
             }
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                const float* v = x + ch * 8;
+            for (int i = 0; i < 4; ++i) {
+                const float* v = x + i * 8;
                 uint4 hi, lo;
                 hi.x = pack_h2(v[0], v[1]); hi.y = pack_h2(v[2], v[3]); hi.z = pack_h2(v[4], v[5]); hi.w = pack_h2(v[6], v[7]);
                 lo.x = pack_lo_h2(v[0], v[1], hi.x); lo.y = pack_lo_h2(v[2], v[3], hi.y);
                 lo.z = pack_lo_h2(v[4], v[5], hi.z); lo.w = pack_lo_h2(v[6], v[7], hi.w);
-                const int off = (ch ^ (row & 7)) << 4;
+                const int off = ((half * 4 + i) ^ (row & 7)) << 4;
                 *reinterpret_cast<uint4*>(xrow_hi + off) = hi;
                 *reinterpret_cast<uint4*>(xrow_lo + off) = lo;
             }
@@ -244,58 +274,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         };
         load(0);
         publish();
-        mbar_arrive(a_ready);
-        for (int t = 0; t < a.T; ++t) {
-            if (t + 1 < a.T) load(t + 1);       // in flight while the tensor core and the cell warps work on step t
-            mbar_wait(&acc_full[1], (uint32_t)(t & 1));  // every MMA of step t has consumed x_t
-            if (t + 1 < a.T) {
-                publish();
-                mbar_arrive(a_ready);
-            }
+        mbar_arrive(x_ready);
+        if (a.T > 1) load(1);
+        for (int t = 1; t < a.T; ++t) {
+            MBW(x_free, (uint32_t)((t - 1) & 1));        // the input-projection MMAs of step t-1 have consumed x_{t-1}
+            publish();                                   // x_t
+            mbar_arrive(x_ready);
+            if (t + 1 < a.T) load(t + 1);                // in flight for a whole step
         }
     } else {
         // ======================================================================= MMA issuer
         const uint32_t idesc = make_idesc(128);
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
-        long long t_wait = 0;
+        long long t_wait = 0, t_wx = 0;
+        // one K = 64 operand slab (x: slab 0, h: slab 1) against the matching weight slab, both column halves,
+        // three passes per half: A_hi B_hi, A_lo B_hi, A_hi B_lo
+        auto issue = [&](int slab, int buf, bool fresh, bool commit_halves) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const int ahl = pass == 1 ? 1 : 0;
+                    const int bhl = pass == 2 ? 1 : 0;
+                    const uint32_t aa = smem_u32(a_slab(As, ahl, slab));
+                    const uint32_t bb = smem_u32(Bs + (bhl * 2 + slab) * B_SLAB_BYTES + hf * 128 * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(tmem_base + buf * 256 + hf * 128, make_desc(aa + k * 32), make_desc(bb + k * 32), idesc,
+                                 (!fresh || (pass | k)) ? 1u : 0u);
+                }
+                if (commit_halves) umma_commit(&acc_full[hf]);
+            }
+        };
+        MBW(x_ready, 0u);
+        tc_fence_after();
+        if (lane == 0) { issue(0, 0, true, false); umma_commit(x_free); }
+        __syncwarp();
         for (int t = 0; t < a.T; ++t) {
             const long long c0 = dbg_on ? clock64() : 0;
-            mbar_wait(a_ready, (uint32_t)(t & 1));
+            MBW(h_ready, (uint32_t)(t & 1));
             if (dbg_on) t_wait += clock64() - c0;
             tc_fence_after();
-            if (lane == 0) {
-                // two column halves (N = 128 each), committed separately so that half of the cell warps start early;
-                // per half: pass 0: A_hi B_hi, pass 1: A_lo B_hi, pass 2: A_hi B_lo
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const int ahl = pass == 1 ? 1 : 0;
-                        const int bhl = pass == 2 ? 1 : 0;
-#pragma unroll
-                        for (int slab = 0; slab < 2; ++slab) {
-                            const uint32_t aa = smem_u32(a_slab(As, ahl, slab));
-                            const uint32_t bb = smem_u32(Bs + (bhl * 2 + slab) * B_SLAB_BYTES + hf * 128 * 128);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_f16(tmem_base + hf * 128, make_desc(aa + k * 32), make_desc(bb + k * 32), idesc, (pass | slab | k) ? 1u : 0u);
-                        }
-                    }
-                    umma_commit(&acc_full[hf]);
-                }
-            }
+            if (lane == 0) issue(1, t & 1, false, true);             // recurrent half: the only MMAs on the serial chain
             __syncwarp();
+            if (t + 1 < a.T) {
+                const long long c2 = dbg_on ? clock64() : 0;
+                MBW(x_ready, (uint32_t)((t + 1) & 1));
+                if (dbg_on) t_wx += clock64() - c2;
+                tc_fence_after();
+                if (lane == 0) { issue(0, (t + 1) & 1, true, false); umma_commit(x_free); }   // runs under the cell phase of step t
+                __syncwarp();
+            }
         }
-        if (dbg_on) a.dbg[5] = t_wait;
+        if (dbg_on) { a.dbg[5] = t_wait; a.dbg[7] = t_wx; }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 256);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
 
-bool lstm_umma_supported(const LstmArgs& a) { return a.E == 64 && a.F >= ROWS && a.Wimg != nullptr; }
+bool lstm_umma_supported(const LstmArgs& a) { return a.E == 64 && a.F >= RPC && a.Wimg != nullptr; }
 
 int launch_lstm_umma(const LstmArgs& a, cudaStream_t st) {
     if (!lstm_umma_supported(a)) return fail("lstm_umma: unsupported shape");
@@ -306,7 +346,7 @@ int launch_lstm_umma(const LstmArgs& a, cudaStream_t st) {
     }
     const int NQ = a.B * a.F;
     ProfScope ps("lstm_umma", 2.0 * NQ * a.T * (64 + H) * 4.0 * H, 4.0 * NQ * a.T * (64 + H), st);
-    EAB_CUDA(launch_k(lstm_umma_kernel, dim3((NQ + ROWS - 1) / ROWS), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a));
+    EAB_CUDA(launch_k(lstm_umma_kernel, dim3((NQ + RPC - 1) / RPC), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a));
     EAB_LAUNCH_CHECK("lstm_umma_kernel");
     return 0;
 }

@@ -651,7 +651,7 @@ struct Packer {
                         blob[m->off_rnn[r][2] + (size_t)j * 4 + g] = P(m->rnn[r][2])[g * H + j] + P(m->rnn[r][3])[g * H + j];
                     }
             }
-            // tcgen05 LSTM: image row n = quarter*64 + gate*16 + jj  <->  torch row gate*64 + (quarter*16 + jj);
+            // tcgen05 LSTM: image row n = half*128 + quarter*32 + gate*8 + j  <->  torch row gate*64 + (quarter*16 + half*8 + j);
             // K slab 0 = W_ih (input channels), slab 1 = W_hh
             m->rnn_umma_ok = c.embed_dim == 64;
             if (m->rnn_umma_ok) {
@@ -660,8 +660,8 @@ struct Packer {
                     m->off_rnn_ubias[r] = alloc(256);
                     __half* img = reinterpret_cast<__half*>(blob.data() + m->off_rnn_img[r]);
                     for (int n = 0; n < 256; ++n) {
-                        const int qtr_ = n >> 6, g = (n >> 4) & 3, jj = n & 15;
-                        const int row = g * H + qtr_ * 16 + jj;
+                        const int hf_ = n >> 7, qtr_ = (n >> 5) & 3, g = (n >> 3) & 3, jj = n & 7;
+                        const int row = g * H + qtr_ * 16 + hf_ * 8 + jj;
                         blob[m->off_rnn_ubias[r] + n] = P(m->rnn[r][2])[row] + P(m->rnn[r][3])[row];
                         for (int slab = 0; slab < 2; ++slab)
                             for (int k = 0; k < 64; ++k) {
