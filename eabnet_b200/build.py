@@ -19,6 +19,7 @@ LIB = os.path.join(HERE, "libeabnet_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+NVCC_FLAGS += os.environ.get("EAB_NVCC_EXTRA", "").split()      # diagnostics builds (e.g. -DEAB_LSTM_EXPERIMENT)
 
 
 def _nvcc() -> str:

@@ -283,6 +283,7 @@ struct LstmArgs {
     const int* step;
     float* h_state; float* c_state;
     int out_RT;
+    int exp_flags;               // diagnostics builds only
 };
 int launch_lstm(const LstmArgs& a, cudaStream_t st);
 bool lstm_umma_supported(const LstmArgs& a);

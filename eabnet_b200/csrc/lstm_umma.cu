@@ -38,6 +38,11 @@ __device__ __forceinline__ float ex2(float x) {          // one SFU op, ~2 ulp
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#ifdef EAB_LSTM_EXPERIMENT
+#define EXP_FLAG(bit) ((a.exp_flags & (bit)) != 0)
+#else
+#define EXP_FLAG(bit) false
+#endif
 // 96 of the 128 MMA rows carry sequences: 10 304 sequences (64 x 161) then make 108 CTAs - one wave over 148 SMs with
 // 25 % less cell work per CTA than 81 CTAs of 128 (the step time is the cell phase, not the tensor pipe).  A warp may
 // only touch TMEM lanes 32 (warp % 4) ... + 32, so warps 0-15 with warp % 4 == 3 would own the empty lane quadrant:
@@ -51,7 +56,8 @@ constexpr int A_BYTES = 4 * SLAB_BYTES;                // [hi|lo][x|h]
 constexpr int B_SLAB_BYTES = 256 * 128;                // one K slab of the weight image (256 gate rows)
 constexpr int B_BYTES = 4 * B_SLAB_BYTES;              // [hi|lo][x|h]
 constexpr int MISC_FLOATS = 256 + 2 * 3 * 64 + 2 * 64; // bias, transform coefficients (2 batch items), LayerNorm
-constexpr int SMEM_BYTES = A_BYTES + B_BYTES + MISC_FLOATS * 4 + 64 + 1024;
+constexpr int HS_BYTES = RPC * 256;                    // fp32 staging of h_t for the coalesced copy-out (16-byte chunks, XOR-swizzled)
+constexpr int SMEM_BYTES = A_BYTES + B_BYTES + HS_BYTES + MISC_FLOATS * 4 + 64 + 1024;
 
 __device__ __forceinline__ uint8_t* a_slab(uint8_t* A, int hl, int slab) { return A + (hl * 2 + slab) * SLAB_BYTES; }
 
@@ -60,7 +66,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* As = smem;
     uint8_t* Bs = smem + A_BYTES;
-    float* sbias = reinterpret_cast<float*>(smem + A_BYTES + B_BYTES);
+    uint8_t* Hs = smem + A_BYTES + B_BYTES;
+    float* sbias = reinterpret_cast<float*>(smem + A_BYTES + B_BYTES + HS_BYTES);
     float* coef = sbias + 256;                  // [2][3][64]
     float* lng = coef + 2 * 3 * 64;
     float* lnb = lng + 64;
@@ -69,7 +76,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
     uint64_t* acc_full = bars + 1;              // [2] gate columns [0,128) / [128,256) of the current step complete
     uint64_t* x_ready = bars + 3;               // x_t is in the A operand (all producer threads)
     uint64_t* x_free = bars + 4;                // the input-projection MMAs have consumed the x operand
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* hs_free = bars + 5;               // the producers have copied the staged h_t out to HBM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -84,6 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         mbar_init(&acc_full[1], 1);
         mbar_init(x_ready, NXP);
         mbar_init(x_free, 1);
+        mbar_init(hs_free, NXP);
         fence_barrier_init();
     }
     pdl_trigger();
@@ -127,8 +136,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         const bool valid = q < NQ;
         const int bq = valid ? q / a.F : 0;
         const int fq = valid ? q - bq * a.F : 0;
-        float* outp = a.out + (((size_t)bq * a.T) * a.F + fq) * H + qtr * 16;
-        const size_t ostep = (size_t)a.F * H;
+        uint8_t* hs_row = Hs + row * 256;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qtr * 32);
         uint8_t* hrow_hi = a_slab(As, 0, 1) + row * 128;
         uint8_t* hrow_lo = a_slab(As, 1, 1) + row * 128;
@@ -166,6 +174,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                     //   h  = sig(o) tanh(c')          = (1-Ec) / [(1+Eo)(1+Ec)]
                     // with Ei = e^-i, Ef = e^-f, Eg = e^-2g, Ec = e^-2c', Eo = e^-o.  The exponents are clamped from above
                     // only (2^40: the functions are saturated to < 1e-12 there and the triple product stays < 2^127).
+                    if (EXP_FLAG(2)) {          // experiment: no SFU work at all
+                        const float cn = fmaf(c[u * 8 + e], __uint_as_float(gf[e]), __uint_as_float(gi[e]) * __uint_as_float(gg[e])) * 0.25f;
+                        c[u * 8 + e] = cn;
+                        hv[e] = cn * __uint_as_float(go[e]) * 0.01f;
+                        continue;
+                    }
                     const float Ei = ex2(fminf(fmaf(__uint_as_float(gi[e]), -L2E, bi[e]), 40.f));
                     const float Ef = ex2(fminf(fmaf(__uint_as_float(gf[e]), -L2E, bi[8 + e]), 40.f));
                     const float Eg = ex2(fminf(fmaf(__uint_as_float(gg[e]), -2.f * L2E, bi[16 + e]), 40.f));
@@ -177,10 +191,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                     const float Ec = ex2(fminf(cn * (-2.f * L2E), 40.f));
                     hv[e] = __fdividef(1.f - Ec, (1.f + Eo) * (1.f + Ec));
                 }
-                if (valid) {
-                    float4* o4 = reinterpret_cast<float4*>(outp + (size_t)t * ostep + u * 8);
-                    o4[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                    o4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                {   // fp32 copy for HBM: chunk c of a row lives at (c ^ (row & 7)) * 16 (conflict-free both ways)
+                    if (u == 0 && t > 0) MBW(hs_free, (uint32_t)((t - 1) & 1));    // h_{t-1} has left the staging tile
+                    const int c0 = qtr * 4 + u * 2;
+                    *reinterpret_cast<float4*>(hs_row + (((c0 + 0) ^ (row & 7)) << 4)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                    *reinterpret_cast<float4*>(hs_row + (((c0 + 1) ^ (row & 7)) << 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
                 }
                 uint4 hi, lo;
                 hi.x = pack_h2(hv[0], hv[1]); hi.y = pack_h2(hv[2], hv[3]); hi.z = pack_h2(hv[4], hv[5]); hi.w = pack_h2(hv[6], hv[7]);
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
             const long long c2 = dbg_on ? clock64() : 0;
             tc_fence_before();
             fence_proxy_async();
-            if (t + 1 < a.T) mbar_arrive(h_ready);
+            mbar_arrive(h_ready);               // h_t: operand for step t+1 and staged for the copy-out
             if (dbg_on) { t_wait += c1 - c0; t_cell += c2 - c1; t_fence += clock64() - c2; }
         }
         if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wait; a.dbg[2] = t_cell; a.dbg[3] = t_fence; a.dbg[4] = a.T; a.dbg[6] = t_w1; }
@@ -220,6 +235,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         const int mode = (a.src.xf.affine == 0 && a.src.xf.prelu == 0) ? 0 : (a.src.xf.prelu == 1 ? 2 : 1);
         uint8_t* xrow_hi = a_slab(As, 0, 0) + row * 128;
         uint8_t* xrow_lo = a_slab(As, 1, 0) + row * 128;
+        // copy-out role: 16-byte chunk g = i*NXP + ptid of the staged h tile (row = g >> 4), 512 contiguous bytes per warp
+        const int ptid = pidx * 32 + lane;
+        // a CTA straddles at most two batch items: row q lives at q*H floats, plus (T-1)*F*H per batch item before it
+        const long long jump = (long long)(a.T - 1) * a.F * H;
+        const int q_next_b = (b0 + 1) * a.F;
+        const size_t ostep = (size_t)a.F * H;
+        auto copy_out = [&](int t) {            // h_t: staged by the cell warps, phase t+1 of h_ready
+            MBW(h_ready, (uint32_t)((t + 1) & 1));
+            float* base = a.out + (long long)b0 * jump + (size_t)t * ostep;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int g = i * NXP + ptid;
+                const int r = g >> 4, ch = g & 15;
+                const int qq = q0 + r;
+                const float4 v = *reinterpret_cast<const float4*>(Hs + r * 256 + ((ch ^ (r & 7)) << 4));
+                if (qq < NQ && !EXP_FLAG(1))
+                    *reinterpret_cast<float4*>(base + (long long)qq * H + ch * 4 + (qq >= q_next_b ? jump : 0)) = v;
+            }
+            mbar_arrive(hs_free);
+        };
         float4 xr[8];
         auto load = [&](int t) {
             if (valid) {
@@ -281,7 +316,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
             publish();                                   // x_t
             mbar_arrive(x_ready);
             if (t + 1 < a.T) load(t + 1);                // in flight for a whole step
+            copy_out(t - 1);
         }
+        copy_out(a.T - 1);
     } else {
         // ======================================================================= MMA issuer
         const uint32_t idesc = make_idesc(128);

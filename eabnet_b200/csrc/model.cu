@@ -199,6 +199,7 @@ struct eab_model {
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
+    int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
     int opt_plane = 1;            // "stage once, shift by descriptor" kernel with fused producers (fallback)
@@ -1290,6 +1291,7 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
                 if (cx.tensor_ok() && m->rnn_umma_ok) {
                     LstmArgs u = a;
                     if (m->opt_dbg_launch == -100 - l && m->dbg_buf) u.dbg = m->dbg_buf;
+                    u.exp_flags = m->opt_lstm_exp;
                     u.Wimg = cx.W(m->off_rnn_img[l]);
                     u.bias = cx.W(m->off_rnn_ubias[l]);
                     if (lstm_umma_supported(u)) {
@@ -1682,6 +1684,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "staged") m->opt_staged = value != 0;
     else if (n == "lazy") m->opt_lazy = value != 0;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
+    else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
     else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
     else if (n == "dbg_launch") {
