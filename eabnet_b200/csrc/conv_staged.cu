@@ -29,8 +29,9 @@ using namespace umma;
 constexpr int TM = 128;
 constexpr int KC = 64;
 constexpr int NSB = 3;                          // weight ring stages
-constexpr int NEPI = 256;                       // 8 epilogue warps
-constexpr int NTHREADS = 128 + NEPI;            // warp 0 plane copies, 1 MMA, 2 weight loader, 3 idle, 4-11 epilogue
+constexpr int NEPI = 256;                       // 8 epilogue warps per group
+constexpr int NGRP = 1;                         // epilogue groups (2 = alternate tiles between two groups: measured no gain, costs a plane buffer)
+constexpr int NTHREADS = 128 + NGRP * NEPI;     // warp 0 plane copies, 1 MMA, 2 weight loader, 3 idle, 4-11 / 12-19 epilogue
 
 inline int ceil8(int x) { return (x + 7) & ~7; }
 
@@ -140,8 +141,8 @@ __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
     p.stg_ld = a.Cout + 4;
     p.b_off = a.nbuf * p.buf_bytes;
     p.stg_off = p.b_off + NSB * p.b_stage_bytes;
-    p.rowoff_off = p.stg_off + TM * p.stg_ld * 4;
-    p.bias_off = p.rowoff_off + TM * 8;
+    p.rowoff_off = p.stg_off + NGRP * TM * p.stg_ld * 4;
+    p.bias_off = p.rowoff_off + NGRP * TM * 8;
     p.bar_off = p.bias_off + a.N * 4;
     p.total = p.bar_off + 256 + 1024;
     return p;
@@ -287,24 +288,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         }
     } else if (warp >= 4) {
         // =========================================================================== epilogue (8 warps)
-        const int et = tid - 128;               // 0..255
+        const int grp = (warp - 4) >> 3;        // epilogue group = TMEM accumulator it drains
+        const int et = (tid - 128) & (NEPI - 1);        // 0..255 within the group
+        stg += grp * TM * pl.stg_ld;
+        rowoff += grp * TM;
         const int quad = warp & 3;              // TMEM lane quadrant (warp % 4)
-        const int chalf = (warp - 4) >> 2;      // which half of the output channels this warp converts
+        const int chalf = ((warp - 4) >> 2) & 1;        // which half of the output channels this warp converts
         const int row = quad * 32 + lane;
         const bool gated = a.gate_off > 0;
         const int ld = pl.stg_ld;
         const int cper = a.Cout >> 1;           // channels per half (multiple of 8)
-        const bool need_stage = a.resid != nullptr || a.nstats > 0;     // smem staging only for the residual / statistics passes
-        int acc = 0;
+        int acc = grp;                          // NGRP == 2: fixed per group; NGRP == 1: alternates
         uint32_t aphase = 0;
-        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && et == 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && et == 0 && grp == 0;
         long long t_wfull = 0, t_tmem = 0, t_store = 0, t_stats = 0;
         const long long t_start = dbg_on ? clock64() : 0;
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
+        for (int tile = tile_begin + grp; tile < tile_end; tile += NGRP) {
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
-            bool row_valid;
-            long long my_off;
             {
                 const int r = row0 + row;
                 long long off = -1;
@@ -314,14 +315,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                     if (e < a.E) off = ((((long long)b * a.T + t) * a.Fout) + (e * a.out_stride + a.out_off)) * a.out_ld + a.out_coff;
                 }
                 if (chalf == 0) rowoff[row] = off;
-                row_valid = off >= 0;
-                my_off = off;
             }
             const long long e0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_full[acc], aphase);
             const long long e1 = dbg_on ? clock64() : 0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.N);
+            // ---- phase 1: TMEM -> bias / gate / ReLU -> fp32 staging tile (thread = row; 16-byte stores, conflict-free)
             for (int c0 = chalf * cper; c0 < (chalf + 1) * cper; c0 += 8) {
                 uint32_t rv[8], rg[8];
                 tmem_ld8_nowait(taddr + c0, rv);
@@ -344,69 +344,92 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
-                if (!a.resid && row_valid) {    // full 32-byte sectors straight from registers: no smem round trip, no proxy fence
-                    float4* o4 = reinterpret_cast<float4*>(a.out + my_off + c0);
-                    o4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    o4[1] = make_float4(v[4], v[5], v[6], v[7]);
-                }
-                if (need_stage) {
-                    if (!row_valid) {           // dummy / ragged rows contribute exact zeros to the statistics
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                    }
-                    *reinterpret_cast<float4*>(stg + row * ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(stg + row * ld + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                }
+                *reinterpret_cast<float4*>(stg + row * ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(stg + row * ld + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
-            named_bar_sync(2, NEPI);            // staging tile + row offsets complete
+            named_bar_sync(2 + grp, NEPI);            // staging tile + row offsets complete
             const long long e2 = dbg_on ? clock64() : 0;
-            if (!a.resid) {
-                // rows were already stored from registers
-            } else {
-                const int tpr = a.Cout >> 2;
-                const int rows_per_it = NEPI / tpr;
-                const int cq = (et % tpr) * 4;
-                for (int r = et / tpr; r < TM; r += rows_per_it) {
-                    const long long off = rowoff[r];
-                    if (off < 0) continue;
-                    float4 o = *reinterpret_cast<const float4*>(stg + r * ld + cq);
+            // ---- phase 2: coalesced copy-out (a warp writes 512 contiguous bytes per instruction), residual add, and the
+            //      per-channel statistics of exactly what was stored.  16-byte chunk g = i*NEPI + et: row g / tpr, and the
+            //      channel quad cq = 4 (g % tpr) is the SAME for every i when tpr divides NEPI (Cout 16/32/64/128).
+            const int tpr = a.Cout >> 2;        // 16-byte chunks per row
+            const int cq = (et % tpr) * 4;
+            const int rows_per_it = NEPI / tpr;
+            float ssum[2][4], ssq[2][4];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { ssum[s][j] = 0.f; ssq[s][j] = 0.f; }
+            float al[2][4];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) al[s][j] = (s < a.nstats && a.stat_alpha[s]) ? __ldg(a.stat_alpha[s] + cq + j) : 1.f;
+            for (int r = et / tpr; r < TM; r += rows_per_it) {
+                const long long off = rowoff[r];
+                if (off < 0) continue;          // dummy / ragged rows: not stored, not counted
+                float4 o = *reinterpret_cast<const float4*>(stg + r * ld + cq);
+                if (a.resid) {
                     const float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + off + cq));
                     o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-                    if (a.nstats) *reinterpret_cast<float4*>(stg + r * ld + cq) = o;
-                    *reinterpret_cast<float4*>(a.out + off + cq) = o;
+                }
+                *reinterpret_cast<float4*>(a.out + off + cq) = o;
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (s >= a.nstats) continue;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float u = fmaxf(ov[j], 0.f) + al[s][j] * fminf(ov[j], 0.f);
+                        ssum[s][j] += u;
+                        ssq[s][j] = fmaf(u, u, ssq[s][j]);
+                    }
                 }
             }
             const long long e3 = dbg_on ? clock64() : 0;
             if (a.nstats) {
-                if (a.resid) named_bar_sync(2, NEPI);
-                // (statistic, channel) x row-quarter per thread: branch-free column sums over the staged tile
-                const int nsc = a.nstats * a.Cout;
-                for (int i = et; i < nsc * 4; i += NEPI) {
-                    const int qr = i / nsc;
-                    const int sc = i - qr * nsc;
-                    const int s = sc / a.Cout, c = sc - s * a.Cout;
-                    const bool pre = a.stat_alpha[s] != nullptr;
-                    const float al = pre ? __ldg(a.stat_alpha[s] + c) : 1.f;
-                    const float* col = stg + (qr * (TM / 4)) * ld + c;
-                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
-                    for (int r = 0; r < TM / 4; r += 2) {
-                        float u0 = col[r * ld], u1 = col[(r + 1) * ld];
-                        u0 = fmaxf(u0, 0.f) + al * fminf(u0, 0.f);
-                        u1 = fmaxf(u1, 0.f) + al * fminf(u1, 0.f);
-                        s0 += u0; q0 = fmaf(u0, u0, q0);
-                        s1 += u1; q1 = fmaf(u1, u1, q1);
+                // threads with equal et % tpr hold partial sums of the same channels: fold across the warp (lane strides
+                // of tpr), then across the 8 warps through the (now dead) staging tile, then one fp64 atomic per value
+                named_bar_sync(2 + grp, NEPI);        // every thread has finished reading the staging tile
+                for (int s = 0; s < a.nstats; ++s)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float x = ssum[s][j], y = ssq[s][j];
+                        for (int o = tpr; o < 32; o <<= 1) {
+                            x += __shfl_xor_sync(0xffffffffu, x, o);
+                            y += __shfl_xor_sync(0xffffffffu, y, o);
+                        }
+                        ssum[s][j] = x; ssq[s][j] = y;
                     }
+                const int wv = et >> 5;
+                const int nlead = tpr < 32 ? tpr : 32;             // lanes holding distinct channel quads
+                if (lane < nlead) {
+                    for (int s = 0; s < a.nstats; ++s)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            // red[warp][s][channel][2]
+                            float* rp = stg + (((wv * 2 + s) * a.Cout) + cq + j) * 2;
+                            rp[0] = ssum[s][j]; rp[1] = ssq[s][j];
+                        }
+                }
+                named_bar_sync(2 + grp, NEPI);
+                const int nsc = a.nstats * a.Cout;
+                for (int i = et; i < nsc; i += NEPI) {
+                    const int s = i / a.Cout, c = i - s * a.Cout;
+                    float x = 0.f, y = 0.f;
+#pragma unroll
+                    for (int w = 0; w < NEPI / 32; ++w) { x += stg[(((w * 2 + s) * a.Cout) + c) * 2]; y += stg[(((w * 2 + s) * a.Cout) + c) * 2 + 1]; }
                     double* dstp = a.stats[s] + ((size_t)b * a.Cout + c) * 2;
-                    atomicAdd(dstp, (double)(s0 + s1));
-                    atomicAdd(dstp + 1, (double)(q0 + q1));
+                    atomicAdd(dstp, (double)x);
+                    atomicAdd(dstp + 1, (double)y);
                 }
             }
-            named_bar_sync(2, NEPI);            // staging free for the next tile
+            named_bar_sync(2 + grp, NEPI);            // staging free for the next tile
             if (dbg_on) { const long long e4 = clock64(); t_wfull += e1 - e0; t_tmem += e2 - e1; t_store += e3 - e2; t_stats += e4 - e3; }
-            if (++acc == 2) { acc = 0; aphase ^= 1; }
+            if (NGRP == 2) aphase ^= 1;
+            else if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         if (dbg_on) { a.dbg[8] = clock64() - t_start; a.dbg[9] = t_wfull; a.dbg[10] = t_tmem; a.dbg[11] = t_store; a.dbg[12] = t_stats; }
     }
@@ -435,7 +458,7 @@ int staged_rows(const PlaneConvArgs& a, int* front) {
 bool staged_conv_supported(const PlaneConvArgs& a_in) {
     if (!plane_conv_supported(a_in)) return false;
     PlaneConvArgs a = a_in;
-    if (a.Cout < 16 || a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1) > 16) return false;
+    if ((a.Cout != 16 && a.Cout != 32 && a.Cout != 64 && a.Cout != 128) || a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1) > 16) return false;
     return choose_nbuf(a) > 0;
 }
 
