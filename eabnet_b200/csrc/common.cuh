@@ -322,6 +322,21 @@ struct TcmStreamArgs {
 bool tcm_stream_supported(int cd1, int d_feat, int kd1);
 int launch_tcm_stream(const TcmStreamArgs& a, cudaStream_t st);
 
+// fused w_dnn (Linear-ReLU-Linear) + filter-and-sum (head_fused.cu); weights are the fp16 hi/lo images of the tcgen05 path
+struct HeadArgs {
+    const float* h;              // [rows][64] second LSTM layer output, rows = B*T*F
+    const float* inpt;           // [rows][M][2]
+    float* out;                  // [B][2][T][F]
+    float* w_out;                // optional [rows][w_ld] copy of the beam weights (debug tap), else null
+    int w_ld;
+    long long rows;
+    int T, F, M;
+    const void *W1hi, *W1lo, *W2hi, *W2lo;      // [64][64] and [32][64] K-major 128B-swizzled fp16 images
+    const float *b1, *b2;        // [64], [32]
+};
+bool head_fused_supported(const HeadArgs& a);
+int launch_head_fused(const HeadArgs& a, cudaStream_t st);
+
 int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st);
 int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st);
 // streaming front/back end (stft.cu): one hop in -> spectrum frame *step into a ring; spectrum frame -> one hop out

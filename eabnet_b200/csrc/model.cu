@@ -199,6 +199,8 @@ struct eab_model {
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
+    int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
+    int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
@@ -1304,6 +1306,25 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
             }
             tap(cx, l ? "h2" : "h1", h[l]);
         }
+        // fused w_dnn + filter-and-sum (head_fused.cu): one read of h2, nothing else touches HBM
+        if (cx.tensor_ok() && m->opt_fused_head && m->u_dnn[0].ok && m->u_dnn[1].ok && m->u_dnn[0].nsplit == 1 &&
+            m->u_dnn[1].nsplit == 1 && m->u_dnn[0].ncol == 64 && m->u_dnn[1].ncol == 32 && h[1].xf.affine == 0 &&
+            h[1].xf.prelu == 0 && c.M <= 16) {
+            float* wtap = nullptr;
+            if (m->opt_head_w_tap) wtap = cx.alloc_act((size_t)cx.B * cx.T * c.n_freq * 32);
+            if (!cx.dry) {
+                HeadArgs a;
+                memset(&a, 0, sizeof(a));
+                a.h = h[1].data; a.inpt = inpt; a.out = out_dev; a.w_out = wtap; a.w_ld = 32;
+                a.rows = (long long)cx.B * cx.T * c.n_freq; a.T = cx.T; a.F = c.n_freq; a.M = c.M;
+                a.W1hi = cx.W(m->u_dnn[0].off_hi[0]); a.W1lo = cx.W(m->u_dnn[0].off_lo[0]);
+                a.W2hi = cx.W(m->u_dnn[1].off_hi[0]); a.W2lo = cx.W(m->u_dnn[1].off_lo[0]);
+                a.b1 = cx.W(m->u_dnn[0].off_bias[0]); a.b2 = cx.W(m->u_dnn[1].off_bias[0]);
+                EAB_TRY(launch_head_fused(a, cx.st));
+                if (wtap) { Act wa; wa.data = wtap; wa.F = c.n_freq; wa.C = 32; tap(cx, "w", wa); }
+            }
+            return 0;
+        }
         Act u;
         EAB_TRY(run_pointwise(cx, &h[1], 1, cx.W(m->off_dnn_w[0]), cx.W(m->off_dnn_b[0]), 64, m->dnn_N[0], 0, 1, nullptr, 1,
                               nullptr, 0, nullptr, nullptr, &u, &m->u_dnn[0]));
@@ -1685,6 +1706,8 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "lazy") m->opt_lazy = value != 0;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
+    else if (n == "fused_head") m->opt_fused_head = value != 0;
+    else if (n == "head_w_tap") m->opt_head_w_tap = value != 0;
     else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
     else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
     else if (n == "dbg_launch") {

@@ -84,6 +84,7 @@ def test_stft_istft_round_trip_full_size():
 def test_forward_matches_oracle(over, B, L):
     cfg = O.make_cfg(**over)
     net, sd = _net(cfg, seed=2)
+    net.set_option("head_w_tap", 1)                 # the fused head kernel writes the beam weights only on request
     wave, _ = O.make_wave(B, cfg["M"], L, seed=21)
     spec = O.stft_compress(wave)
     taps, taps64 = {}, {}
@@ -107,7 +108,7 @@ def test_forward_matches_oracle(over, B, L):
     assert err <= max(TIGHT * scale, 8 * cond) and err <= TOL * scale, (err, cond)
 
 
-@pytest.mark.parametrize("opts", [{"enc_passes": 3, "dec_passes": 3}, {"umma": 0}])
+@pytest.mark.parametrize("opts", [{"enc_passes": 3, "dec_passes": 3}, {"umma": 0}, {"fused_head": 0, "enc_passes": 3, "dec_passes": 3}])
 def test_forward_fp32_grade_modes(opts):
     """all-3-pass tensor-core mode and the CUDA-core-only kernels are both fp32-grade against the oracle"""
     cfg = O.make_cfg()
