@@ -151,6 +151,47 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def stream_latency(args, dev):
+    """BASELINE configs[2]: `streams` concurrent causal streams, one 10 ms hop (160 samples x 9 mics) per step with
+    carried conv / TCM / LSTM state (norm_type='BN': InstanceNorm spans the utterance), through eab_stream_step replayed
+    from a CUDA graph.  Host-to-host: pinned hop in, enhanced hop back, wall clock per step."""
+    import torch
+    from eabnet_b200 import EaBNet
+    from eabnet_b200.model import EaBNetStream
+    S, N = args.streams, args.stream_steps
+    torch.manual_seed(7)
+    net = EaBNet(norm_type="BN").eval().to(dev)
+    ses = EaBNetStream(net, S, dev, graph=True)
+    hop_host = (0.1 * torch.randn(S, 9, 160)).pin_memory()
+    out_host = torch.empty(S, 160).pin_memory()
+    hop = torch.empty(S, 9, 160, device=dev)
+    out = torch.empty(S, 160, device=dev)
+    for _ in range(20):
+        ses.step(hop, out)
+    torch.cuda.synchronize(dev)
+    wall, devms = [], []
+    for _ in range(N):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        hop.copy_(hop_host, non_blocking=True)
+        e0.record()
+        ses.step(hop, out)
+        e1.record()
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        devms.append(e0.elapsed_time(e1))
+    wall.sort()
+    devms.sort()
+    assert torch.isfinite(out_host).all()
+    return {"workload": "causal streaming, %d concurrent 9-mic streams, one 10 ms hop per step, carried state, BN "
+                        "(BASELINE configs[2])" % S,
+            "streams": S, "steps": N, "hop_ms": 10.0, "p50_ms": wall[N // 2], "p99_ms": wall[min(N - 1, int(N * 0.99))],
+            "device_p50_ms": devms[N // 2], "launches_per_step": net.last_launch_count(), "cuda_graph": True,
+            "timing": "wall clock per step: pinned H2D of the hop + step + D2H of the enhanced hop + sync",
+            "realtime_factor": S * 10.0 / wall[N // 2]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,6 +202,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=6.0)
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample: utterances per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=256, help="concurrent causal streams of the latency measurement")
+    ap.add_argument("--stream-steps", type=int, default=1000, help="timed 10 ms hops of the latency measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
 
@@ -242,6 +285,8 @@ def main():
         clocks = sampler.stop()
         assert torch.isfinite(y).all()
 
+    latency = stream_latency(args, dev) if args.stream_steps > 0 else None
+
     from eabnet_b200.shard import max_over_ranks
     ms, ms_e2e = max_over_ranks([ms, ms_e2e], dev)
     audio_s = world * B * args.seconds
@@ -284,6 +329,8 @@ def main():
                         "single_batch_call_ms": ms_e2e_single},
                 "gpu_launches": launches * args.steps,
                 "roofline": roof, "clocks": clocks, "kernels": prof}
+        if latency is not None:
+            line["latency"] = latency
         if world == 1 and not args.no_cpu_baseline:
             val, med, cores, sample = cpu_reference_throughput(args.ref_batch, args.seconds, 3, 1)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
