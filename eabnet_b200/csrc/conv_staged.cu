@@ -34,6 +34,7 @@ constexpr int NGRP = 1;                         // epilogue groups (2 = alternat
 constexpr int NTHREADS = 128 + NGRP * NEPI;     // warp 0 plane copies, 1 MMA, 2 weight loader, 3 idle, 4-11 / 12-19 epilogue
 
 inline int ceil8(int x) { return (x + 7) & ~7; }
+constexpr int STAGE_RB = 8;                     // 32-row blocks per stage CTA
 
 // ------------------------------------------------------------------------------------------------ stage kernel
 // grid (row blocks, nplanes*nslab, B), 256 threads: 8 threads per plane row (8 channels = one 16-byte fp16 chunk each)
@@ -67,58 +68,66 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
     const int mode2 = (src.xf2.affine == 0 && src.xf2.prelu == 0) ? 0 : (src.xf2.prelu == 1 ? 2 : 1);
     const int npb = a.npass == 3 ? 2 : 1;
     const int c8 = threadIdx.x & 7;
-    const int rho = blockIdx.x * 32 + (threadIdx.x >> 3);
-    if (rho >= a.np_rows) return;
-    const int r = rho - a.np_front;
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (r >= 0 && r < a.T * a.P) {
-        const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
-        const int col = r - t * a.P;
-        if (col < a.plane_cols[plane]) {
-            const int fi = col * a.col_stride + a.col_off[plane];
-            const float4* p = reinterpret_cast<const float4*>(src.x + ((((size_t)b * a.T + t) * a.Fin + fi) * src.C + cbase + c8 * 8));
-            v0 = __ldg(p);
-            v1 = __ldg(p + 1);
-            if (mode != 0) {
-                const float* cs = coef + c8 * 8;
-                float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (mode == 1) { const float z = fmaf(x[i], cs[i], cs[64 + i]); x[i] = fmaxf(z, 0.f) + cs[128 + i] * fminf(z, 0.f); }
-                    else x[i] = fmaf(fmaxf(x[i], 0.f) + cs[128 + i] * fminf(x[i], 0.f), cs[i], cs[64 + i]);
+    uint8_t* dst_hi = static_cast<uint8_t*>(const_cast<void*>(a.np[ps * npb]));
+    uint8_t* dst_lo = npb == 2 ? static_cast<uint8_t*>(const_cast<void*>(a.np[ps * npb + 1])) : nullptr;
+    const float* cs1 = coef + c8 * 8;
+    const float* cs2 = coef + 192 + c8 * 8;
+    // STAGE_RB row blocks of 32 rows per CTA: the (double precision) coefficient set-up above is paid once per 256 rows
+#pragma unroll 2
+    for (int it = 0; it < STAGE_RB; ++it) {
+        const int rho = (blockIdx.x * STAGE_RB + it) * 32 + (threadIdx.x >> 3);
+        if (rho >= a.np_rows) break;
+        const int r = rho - a.np_front;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (r >= 0 && r < a.T * a.P) {
+            const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
+            const int col = r - t * a.P;
+            if (col < a.plane_cols[plane]) {
+                const int fi = col * a.col_stride + a.col_off[plane];
+                const size_t eoff = (((size_t)b * a.T + t) * a.Fin + fi) * src.C + cbase + c8 * 8;
+                const float4* p = reinterpret_cast<const float4*>(src.x + eoff);
+                v0 = __ldg(p);
+                v1 = __ldg(p + 1);
+                float4 w0, w1;
+                if (src.x2) {
+                    const float4* p2 = reinterpret_cast<const float4*>(src.x2 + eoff);
+                    w0 = __ldg(p2); w1 = __ldg(p2 + 1);
                 }
-                v0 = make_float4(x[0], x[1], x[2], x[3]);
-                v1 = make_float4(x[4], x[5], x[6], x[7]);
-            }
-            if (src.x2) {                        // + the second addend of a module's residual sum
-                const float4* p2 = reinterpret_cast<const float4*>(src.x2 + ((((size_t)b * a.T + t) * a.Fin + fi) * src.C + cbase + c8 * 8));
-                const float4 w0 = __ldg(p2), w1 = __ldg(p2 + 1);
-                float x[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                if (mode2 != 0) {
-                    const float* cs = coef + 192 + c8 * 8;
+                if (mode != 0) {
+                    float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        if (mode2 == 1) { const float z = fmaf(x[i], cs[i], cs[64 + i]); x[i] = fmaxf(z, 0.f) + cs[128 + i] * fminf(z, 0.f); }
-                        else x[i] = fmaf(fmaxf(x[i], 0.f) + cs[128 + i] * fminf(x[i], 0.f), cs[i], cs[64 + i]);
+                        if (mode == 1) { const float z = fmaf(x[i], cs1[i], cs1[64 + i]); x[i] = fmaxf(z, 0.f) + cs1[128 + i] * fminf(z, 0.f); }
+                        else x[i] = fmaf(fmaxf(x[i], 0.f) + cs1[128 + i] * fminf(x[i], 0.f), cs1[i], cs1[64 + i]);
                     }
+                    v0 = make_float4(x[0], x[1], x[2], x[3]);
+                    v1 = make_float4(x[4], x[5], x[6], x[7]);
                 }
-                v0.x += x[0]; v0.y += x[1]; v0.z += x[2]; v0.w += x[3];
-                v1.x += x[4]; v1.y += x[5]; v1.z += x[6]; v1.w += x[7];
+                if (src.x2) {                        // + the second addend of a module's residual sum
+                    float x[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    if (mode2 != 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (mode2 == 1) { const float z = fmaf(x[i], cs2[i], cs2[64 + i]); x[i] = fmaxf(z, 0.f) + cs2[128 + i] * fminf(z, 0.f); }
+                            else x[i] = fmaf(fmaxf(x[i], 0.f) + cs2[128 + i] * fminf(x[i], 0.f), cs2[i], cs2[64 + i]);
+                        }
+                    }
+                    v0.x += x[0]; v0.y += x[1]; v0.z += x[2]; v0.w += x[3];
+                    v1.x += x[4]; v1.y += x[5]; v1.z += x[6]; v1.w += x[7];
+                }
             }
         }
-    }
-    uint4 hi;
-    hi.x = pack_h2(v0.x, v0.y); hi.y = pack_h2(v0.z, v0.w); hi.z = pack_h2(v1.x, v1.y); hi.w = pack_h2(v1.z, v1.w);
-    const size_t row_g = (size_t)b * a.np_rows + rho;
-    const size_t off = row_g * 128 + (size_t)((c8 ^ (rho & 7)) << 4);
-    uint8_t* dst_hi = static_cast<uint8_t*>(const_cast<void*>(a.np[ps * npb]));
-    *reinterpret_cast<uint4*>(dst_hi + off) = hi;
-    if (npb == 2) {
-        uint4 lo;
-        lo.x = pack_lo_h2(v0.x, v0.y, hi.x); lo.y = pack_lo_h2(v0.z, v0.w, hi.y);
-        lo.z = pack_lo_h2(v1.x, v1.y, hi.z); lo.w = pack_lo_h2(v1.z, v1.w, hi.w);
-        uint8_t* dst_lo = static_cast<uint8_t*>(const_cast<void*>(a.np[ps * npb + 1]));
-        *reinterpret_cast<uint4*>(dst_lo + off) = lo;
+        uint4 hi;
+        hi.x = pack_h2(v0.x, v0.y); hi.y = pack_h2(v0.z, v0.w); hi.z = pack_h2(v1.x, v1.y); hi.w = pack_h2(v1.z, v1.w);
+        const size_t row_g = (size_t)b * a.np_rows + rho;
+        const size_t off = row_g * 128 + (size_t)((c8 ^ (rho & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst_hi + off) = hi;
+        if (npb == 2) {
+            uint4 lo;
+            lo.x = pack_lo_h2(v0.x, v0.y, hi.x); lo.y = pack_lo_h2(v0.z, v0.w, hi.y);
+            lo.z = pack_lo_h2(v1.x, v1.y, hi.z); lo.w = pack_lo_h2(v1.z, v1.w, hi.w);
+            *reinterpret_cast<uint4*>(dst_lo + off) = lo;
+        }
     }
 }
 
@@ -465,7 +474,7 @@ bool staged_conv_supported(const PlaneConvArgs& a_in) {
 int launch_stage(const PlaneConvArgs& a_in, cudaStream_t st) {
     PlaneConvArgs a = a_in;
     a.p_magic = a.P == 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)a.P) + 1u;
-    dim3 grid((a.np_rows + 31) / 32, a.nplanes * a.nslab, a.B);
+    dim3 grid((a.np_rows + 32 * STAGE_RB - 1) / (32 * STAGE_RB), a.nplanes * a.nslab, a.B);
     double cin = 0;
     for (int i = 0; i < a.nsrc; ++i) cin += a.src[i].C;
     const double elems = (double)a.B * a.T * a.Fin * cin;
