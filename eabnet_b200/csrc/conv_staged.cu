@@ -30,10 +30,15 @@ constexpr int TM = 128;
 constexpr int KC = 64;
 constexpr int NSB = 3;                          // weight ring stages
 constexpr int NEPI = 256;                       // 8 epilogue warps per group
-constexpr int NGRP = 1;                         // epilogue groups (2 = alternate tiles between two groups: measured no gain, costs a plane buffer)
+constexpr int NGRP = 2;                         // epilogue groups: group g drains TMEM accumulator g (alternate tiles)
 constexpr int NTHREADS = 128 + NGRP * NEPI;     // warp 0 plane copies, 1 MMA, 2 weight loader, 3 idle, 4-11 / 12-19 epilogue
 
 inline int ceil8(int x) { return (x + 7) & ~7; }
+#ifdef EAB_CONV_EXPERIMENT
+#define CEXP(bit) ((a.exp_flags & (bit)) != 0)
+#else
+#define CEXP(bit) false
+#endif
 constexpr int STAGE_RB = 8;                     // 32-row blocks per stage CTA
 
 // ------------------------------------------------------------------------------------------------ stage kernel
@@ -136,7 +141,7 @@ struct Plan {
     int R;                           // plane rows a tile needs = 128 + back + fwd
     int plane_bytes;                 // (R + 8 rounded up to 8) * 128 : the copy starts on an 8-row (1024 B) boundary
     int buf_bytes;                   // nplanes * nslab * npb * plane_bytes
-    int b_stage_bytes, stg_ld;
+    int b_stage_bytes, stg_ld, w_images;
     int b_off, stg_off, rowoff_off, bias_off, bar_off, total;
 };
 
@@ -147,11 +152,15 @@ __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
     const int npb = a.npass == 3 ? 2 : 1;
     p.buf_bytes = a.nplanes * a.nslab * npb * p.plane_bytes;
     p.b_stage_bytes = a.N * 128;
+    // resident weights: every (tap, slab) image, hi (+ lo for the 3-pass layers), stays in shared memory for the whole
+    // launch.  Streaming them per tile through a 3-deep ring is bound by L2 latency (3 x 8..16 KB in flight ~ 16 B/clk),
+    // which is what limited this kernel (measured: 8.8 of 14.4 ms with MMA and epilogue both disabled).
+    p.w_images = a.ntaps * a.nslab * npb;
     p.stg_ld = a.Cout + 4;
     p.b_off = a.nbuf * p.buf_bytes;
-    p.stg_off = p.b_off + NSB * p.b_stage_bytes;
-    p.rowoff_off = p.stg_off + NGRP * TM * p.stg_ld * 4;
-    p.bias_off = p.rowoff_off + NGRP * TM * 8;
+    p.stg_off = p.b_off + (a.resident ? p.w_images : NSB) * p.b_stage_bytes;
+    p.rowoff_off = p.stg_off;
+    p.bias_off = p.rowoff_off;
     p.bar_off = p.bias_off + a.N * 4;
     p.total = p.bar_off + 256 + 1024;
     return p;
@@ -251,24 +260,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                 for (int slab = 0; slab < a.nslab; ++slab) {
                     const uint32_t a_hi = pbase + (uint32_t)(((a.tap_plane[tap] * a.nslab + slab) * npb) * pl.plane_bytes + arow * 128);
                     for (int pass = 0; pass < a.npass; ++pass, ++unit) {
-                        const long long w2 = dbg_on ? clock64() : 0;
-                        mbar_wait(&b_full[stage], sphase);
-                        if (dbg_on) t_wb += clock64() - w2;
-                        tc_fence_after();
+                        if (!a.resident || (tile == tile_begin && unit == 0)) {
+                            const long long w2 = dbg_on ? clock64() : 0;
+                            mbar_wait(&b_full[stage], sphase);
+                            if (dbg_on) t_wb += clock64() - w2;
+                            tc_fence_after();
+                        }
                         if (lane == 0) {
                             const uint32_t a_addr = a_hi + (pass == 1 ? (uint32_t)pl.plane_bytes : 0u);
-                            const uint32_t b_addr = smem_u32(Bs + stage * pl.b_stage_bytes);
+                            const int wimg = a.resident ? ((tap * a.nslab + slab) * npb + (pass == 2 ? 1 : 0)) : stage;
+                            const uint32_t b_addr = smem_u32(Bs + wimg * pl.b_stage_bytes);
 #pragma unroll
                             for (int k = 0; k < KC / 16; ++k)
-                                umma_f16(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, (unit | k) ? 1u : 0u);
-                            umma_commit(&b_empty[stage]);
+                                if (!CEXP(8)) umma_f16(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, (unit | k) ? 1u : 0u);
+                            if (!a.resident) umma_commit(&b_empty[stage]);
                             if (unit == units_per_tile - 1) {
                                 umma_commit(&acc_full[acc]);
                                 umma_commit(&plane_empty[buf]);
                             }
                         }
                         __syncwarp();
-                        if (++stage == NSB) { stage = 0; sphase ^= 1; }
+                        if (!a.resident && ++stage == NSB) { stage = 0; sphase ^= 1; }
                     }
                 }
             }
@@ -281,6 +293,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         int stage = 0;
         uint32_t sphase = 0;
         const uint32_t bytes = (uint32_t)pl.b_stage_bytes;
+        if (a.resident) {
+            if (lane == 0 && tile_begin < tile_end) {
+                mbar_arrive_expect_tx(&b_full[0], bytes * (uint32_t)pl.w_images);
+                for (int ts = 0; ts < a.ntaps * a.nslab; ++ts)
+                    for (int hl = 0; hl < npb; ++hl)
+                        bulk_copy_g2s(Bs + (ts * npb + hl) * pl.b_stage_bytes, (hl ? a.Wlo : a.Whi) + (size_t)ts * a.N * 32, bytes, &b_full[0]);
+            }
+            __syncwarp();
+        } else
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             for (int ts = 0; ts < a.ntaps * a.nslab; ++ts) {
                 for (int pass = 0; pass < a.npass; ++pass) {
@@ -296,45 +317,87 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             }
         }
     } else if (warp >= 4) {
-        // =========================================================================== epilogue (8 warps)
-        const int grp = (warp - 4) >> 3;        // epilogue group = TMEM accumulator it drains
-        const int et = (tid - 128) & (NEPI - 1);        // 0..255 within the group
-        stg += grp * TM * pl.stg_ld;
-        rowoff += grp * TM;
+        // =========================================================================== epilogue (8 warps per group)
+        // Register-only: thread = output row (TMEM lane), warp = (lane quadrant, half of the channels).  Values go
+        // TMEM -> registers -> HBM as full 32-byte sectors; the per-channel statistics are folded across the 32 rows of
+        // the warp with a halving butterfly (9 shuffles per 8 columns per statistic) into one owner lane per column,
+        // accumulated in registers over the CTA's tiles and flushed with fp64 atomics only when the batch item changes.
+        // No staging tile, no block barrier: shared memory is left to the operand traffic of the tensor core.
+        const int grp = (warp - 4) >> 3;        // epilogue group = TMEM accumulator it drains (NGRP == 2)
         const int quad = warp & 3;              // TMEM lane quadrant (warp % 4)
         const int chalf = ((warp - 4) >> 2) & 1;        // which half of the output channels this warp converts
         const int row = quad * 32 + lane;
         const bool gated = a.gate_off > 0;
-        const int ld = pl.stg_ld;
-        const int cper = a.Cout >> 1;           // channels per half (multiple of 8)
-        int acc = grp;                          // NGRP == 2: fixed per group; NGRP == 1: alternates
+        const int cper = a.Cout >> 1;           // channels per half (8 .. 64, multiple of 8)
+        const int niter = cper >> 3;
+        const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);     // column (of 8) this lane ends up owning
+        int acc = grp;
         uint32_t aphase = 0;
-        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && et == 0 && grp == 0;
-        long long t_wfull = 0, t_tmem = 0, t_store = 0, t_stats = 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+        long long t_wfull = 0, t_tmem = 0;
         const long long t_start = dbg_on ? clock64() : 0;
+        float ssum[2][8], ssq[2][8];            // [statistic][iteration]: totals of column chalf*cper + it*8 + own
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+            for (int it = 0; it < 8; ++it) { ssum[s2][it] = 0.f; ssq[s2][it] = 0.f; }
+        int cur_b = -1;
+        auto flush = [&](int b) {
+            if (b < 0 || a.nstats == 0) return;
+            if ((lane & 3) == 0) {
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    if (s2 >= a.nstats) continue;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        if (it >= niter) continue;
+                        double* dstp = a.stats[s2] + ((size_t)b * a.Cout + chalf * cper + it * 8 + own) * 2;
+                        atomicAdd(dstp, (double)ssum[s2][it]);
+                        atomicAdd(dstp + 1, (double)ssq[s2][it]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                for (int it = 0; it < 8; ++it) { ssum[s2][it] = 0.f; ssq[s2][it] = 0.f; }
+        };
         for (int tile = tile_begin + grp; tile < tile_end; tile += NGRP) {
             const int b = tile / a.tiles_per_b;
+            if (b != cur_b) { flush(cur_b); cur_b = b; }
             const int row0 = (tile - b * a.tiles_per_b) * TM;
+            long long off = -1;
             {
                 const int r = row0 + row;
-                long long off = -1;
                 if (r < rows_per_b) {
                     const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
                     const int e = r - t * a.P;
                     if (e < a.E) off = ((((long long)b * a.T + t) * a.Fout) + (e * a.out_stride + a.out_off)) * a.out_ld + a.out_coff;
                 }
-                if (chalf == 0) rowoff[row] = off;
             }
+            const bool row_valid = off >= 0;
             const long long e0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_full[acc], aphase);
             const long long e1 = dbg_on ? clock64() : 0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.N);
-            // ---- phase 1: TMEM -> bias / gate / ReLU -> fp32 staging tile (thread = row; 16-byte stores, conflict-free)
-            for (int c0 = chalf * cper; c0 < (chalf + 1) * cper; c0 += 8) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                if (it >= niter) continue;
+                const int c0 = chalf * cper + it * 8;
                 uint32_t rv[8], rg[8];
-                tmem_ld8_nowait(taddr + c0, rv);
-                if (gated) tmem_ld8_nowait(taddr + a.gate_off + c0, rg);
+                if (!CEXP(4)) {
+                    tmem_ld8_nowait(taddr + c0, rv);
+                    if (gated) tmem_ld8_nowait(taddr + a.gate_off + c0, rg);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { rv[i] = 0x3f800000u + lane; rg[i] = 0x3f000000u; }
+                }
+                float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+                if (a.resid && row_valid) {          // residual rows: issued under the TMEM load
+                    q0 = __ldg(reinterpret_cast<const float4*>(a.resid + off + c0));
+                    q1 = __ldg(reinterpret_cast<const float4*>(a.resid + off + c0 + 4));
+                }
                 tmem_wait_ld();
                 float v[8];
                 const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0);
@@ -353,94 +416,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
-                *reinterpret_cast<float4*>(stg + row * ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(stg + row * ld + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w;
+                v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
+                if (row_valid && !CEXP(1)) {
+                    float4* o4 = reinterpret_cast<float4*>(a.out + off + c0);
+                    o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                if (a.nstats && !CEXP(2)) {
+                    if (!row_valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        if (s2 >= a.nstats) continue;
+                        float u[8], w[8];
+                        if (a.stat_alpha[s2]) {
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(a.stat_alpha[s2] + c0));
+                            const float4 a1 = __ldg(reinterpret_cast<const float4*>(a.stat_alpha[s2] + c0 + 4));
+                            const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) u[i] = fmaxf(v[i], 0.f) + al[i] * fminf(v[i], 0.f);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) u[i] = v[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) w[i] = u[i] * u[i];
+                        // halving butterfly over the 32 rows: 8 -> 4 -> 2 -> 1 columns per lane, then the last two bits
+                        const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+                        float u4[4], w4[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float su = h16 ? u[j] : u[j + 4], ku = h16 ? u[j + 4] : u[j];
+                            const float sw = h16 ? w[j] : w[j + 4], kw = h16 ? w[j + 4] : w[j];
+                            u4[j] = ku + __shfl_xor_sync(0xffffffffu, su, 16);
+                            w4[j] = kw + __shfl_xor_sync(0xffffffffu, sw, 16);
+                        }
+                        float u2[2], w2[2];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float su = h8 ? u4[j] : u4[j + 2], ku = h8 ? u4[j + 2] : u4[j];
+                            const float sw = h8 ? w4[j] : w4[j + 2], kw = h8 ? w4[j + 2] : w4[j];
+                            u2[j] = ku + __shfl_xor_sync(0xffffffffu, su, 8);
+                            w2[j] = kw + __shfl_xor_sync(0xffffffffu, sw, 8);
+                        }
+                        float u1 = (h4 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? u2[0] : u2[1], 4);
+                        float w1 = (h4 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? w2[0] : w2[1], 4);
+                        u1 += __shfl_xor_sync(0xffffffffu, u1, 2);
+                        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+                        u1 += __shfl_xor_sync(0xffffffffu, u1, 1);
+                        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                        ssum[s2][it] += u1;
+                        ssq[s2][it] += w1;
+                    }
+                }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
-            named_bar_sync(2 + grp, NEPI);            // staging tile + row offsets complete
-            const long long e2 = dbg_on ? clock64() : 0;
-            // ---- phase 2: coalesced copy-out (a warp writes 512 contiguous bytes per instruction), residual add, and the
-            //      per-channel statistics of exactly what was stored.  16-byte chunk g = i*NEPI + et: row g / tpr, and the
-            //      channel quad cq = 4 (g % tpr) is the SAME for every i when tpr divides NEPI (Cout 16/32/64/128).
-            const int tpr = a.Cout >> 2;        // 16-byte chunks per row
-            const int cq = (et % tpr) * 4;
-            const int rows_per_it = NEPI / tpr;
-            float ssum[2][4], ssq[2][4];
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { ssum[s][j] = 0.f; ssq[s][j] = 0.f; }
-            float al[2][4];
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) al[s][j] = (s < a.nstats && a.stat_alpha[s]) ? __ldg(a.stat_alpha[s] + cq + j) : 1.f;
-            for (int r = et / tpr; r < TM; r += rows_per_it) {
-                const long long off = rowoff[r];
-                if (off < 0) continue;          // dummy / ragged rows: not stored, not counted
-                float4 o = *reinterpret_cast<const float4*>(stg + r * ld + cq);
-                if (a.resid) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + off + cq));
-                    o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-                }
-                *reinterpret_cast<float4*>(a.out + off + cq) = o;
-                const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    if (s >= a.nstats) continue;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float u = fmaxf(ov[j], 0.f) + al[s][j] * fminf(ov[j], 0.f);
-                        ssum[s][j] += u;
-                        ssq[s][j] = fmaf(u, u, ssq[s][j]);
-                    }
-                }
-            }
-            const long long e3 = dbg_on ? clock64() : 0;
-            if (a.nstats) {
-                // threads with equal et % tpr hold partial sums of the same channels: fold across the warp (lane strides
-                // of tpr), then across the 8 warps through the (now dead) staging tile, then one fp64 atomic per value
-                named_bar_sync(2 + grp, NEPI);        // every thread has finished reading the staging tile
-                for (int s = 0; s < a.nstats; ++s)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float x = ssum[s][j], y = ssq[s][j];
-                        for (int o = tpr; o < 32; o <<= 1) {
-                            x += __shfl_xor_sync(0xffffffffu, x, o);
-                            y += __shfl_xor_sync(0xffffffffu, y, o);
-                        }
-                        ssum[s][j] = x; ssq[s][j] = y;
-                    }
-                const int wv = et >> 5;
-                const int nlead = tpr < 32 ? tpr : 32;             // lanes holding distinct channel quads
-                if (lane < nlead) {
-                    for (int s = 0; s < a.nstats; ++s)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            // red[warp][s][channel][2]
-                            float* rp = stg + (((wv * 2 + s) * a.Cout) + cq + j) * 2;
-                            rp[0] = ssum[s][j]; rp[1] = ssq[s][j];
-                        }
-                }
-                named_bar_sync(2 + grp, NEPI);
-                const int nsc = a.nstats * a.Cout;
-                for (int i = et; i < nsc; i += NEPI) {
-                    const int s = i / a.Cout, c = i - s * a.Cout;
-                    float x = 0.f, y = 0.f;
-#pragma unroll
-                    for (int w = 0; w < NEPI / 32; ++w) { x += stg[(((w * 2 + s) * a.Cout) + c) * 2]; y += stg[(((w * 2 + s) * a.Cout) + c) * 2 + 1]; }
-                    double* dstp = a.stats[s] + ((size_t)b * a.Cout + c) * 2;
-                    atomicAdd(dstp, (double)x);
-                    atomicAdd(dstp + 1, (double)y);
-                }
-            }
-            named_bar_sync(2 + grp, NEPI);            // staging free for the next tile
-            if (dbg_on) { const long long e4 = clock64(); t_wfull += e1 - e0; t_tmem += e2 - e1; t_store += e3 - e2; t_stats += e4 - e3; }
+            if (dbg_on) { t_wfull += e1 - e0; t_tmem += clock64() - e1; }
             if (NGRP == 2) aphase ^= 1;
             else if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
-        if (dbg_on) { a.dbg[8] = clock64() - t_start; a.dbg[9] = t_wfull; a.dbg[10] = t_tmem; a.dbg[11] = t_store; a.dbg[12] = t_stats; }
+        flush(cur_b);
+        if (dbg_on) { a.dbg[8] = clock64() - t_start; a.dbg[9] = t_wfull; a.dbg[10] = t_tmem; a.dbg[11] = 0; a.dbg[12] = 0; }
     }
 
     tc_fence_before();
@@ -449,9 +489,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 }
 
 int choose_nbuf(PlaneConvArgs& a) {
-    for (int nb = 3; nb >= 1; --nb) {
-        a.nbuf = nb;
-        if (make_plan(a).total <= 227 * 1024) return nb;
+    for (int res = 1; res >= 0; --res) {
+        a.resident = res;
+        for (int nb = 3; nb >= (res ? 2 : 1); --nb) {
+            a.nbuf = nb;
+            if (make_plan(a).total <= 227 * 1024) return nb;
+        }
     }
     return 0;
 }

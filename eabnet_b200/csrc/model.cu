@@ -201,6 +201,7 @@ struct eab_model {
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
+    int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
@@ -869,7 +870,7 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
                 EAB_TRY(launch_stage(ps, cx.st));
                 for (int i = 0; i < n; ++i) {
                     if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) p[i].dbg = m->dbg_buf;
-                    p[i].np_rows = rows; p[i].np_front = front;
+                    p[i].np_rows = rows; p[i].np_front = front; p[i].exp_flags = m->opt_conv_exp;
                     for (int k = 0; k < nimg; ++k) p[i].np[k] = ps.np[k];
                     EAB_TRY(launch_conv_staged(p[i], cx.st));
                 }
@@ -1706,6 +1707,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "lazy") m->opt_lazy = value != 0;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
+    else if (n == "conv_exp") m->opt_conv_exp = value;
     else if (n == "fused_head") m->opt_fused_head = value != 0;
     else if (n == "head_w_tap") m->opt_head_w_tap = value != 0;
     else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
