@@ -134,6 +134,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // launch descriptors shared between model.cu and the kernel translation units
 // ---------------------------------------------------------------------------------------------------
 constexpr int kMaxTaps = 16;
+constexpr int kMaxConvUnits = 96;       // taps x 64-channel slabs x passes of one conv_tma tile
 constexpr int kMaxCin = 1024;
 
 struct ConvSrc {
@@ -210,6 +211,7 @@ struct UmmaConvArgs {
     int nstats;
     int tiles_per_b;             // ceil(T*E / 128)
     unsigned long long* dbg;     // optional [16] cycle counters of CTA 0 (diagnostics), else null
+    int stats_ld, stats_coff;    // statistics arrays are [B][stats_ld][2], this launch owns channels stats_coff.. (0 = [B][Cout][2])
 };
 bool umma_conv_supported(const UmmaConvArgs& a);
 int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st);
@@ -251,6 +253,11 @@ struct PlaneConvArgs {
     const void* np[16];
     int np_rows, np_front;
     int exp_flags;               // diagnostics builds only
+    int stats_ld, stats_coff;    // see UmmaConvArgs
+    // conv_tma: per-unit (tap, slab, pass) operand offsets, filled by the launcher: A offset / 16 relative to the tile's
+    // plane origin, weight image index.  Kernel parameters live in the constant bank => warp-uniform loads.
+    unsigned int unit_a[kMaxConvUnits];
+    unsigned short unit_b[kMaxConvUnits];
 };
 bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
 int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);

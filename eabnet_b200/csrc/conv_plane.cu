@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_plane_kernel(const PlaneConv
                         s0 += u0; q0 = fmaf(u0, u0, q0);
                         s1 += u1; q1 = fmaf(u1, u1, q1);
                     }
-                    double* dstp = a.stats[s] + ((size_t)b * a.Cout + c) * 2;
+                    double* dstp = a.stats[s] + ((size_t)b * (a.stats_ld ? a.stats_ld : a.Cout) + a.stats_coff + c) * 2;
                     atomicAdd(dstp, (double)(s0 + s1));
                     atomicAdd(dstp + 1, (double)(q0 + q1));
                 }

@@ -142,7 +142,7 @@ struct Plan {
     int plane_bytes;                 // (R + 8 rounded up to 8) * 128 : the copy starts on an 8-row (1024 B) boundary
     int buf_bytes;                   // nplanes * nslab * npb * plane_bytes
     int b_stage_bytes, stg_ld, w_images;
-    int b_off, stg_off, rowoff_off, bias_off, bar_off, total;
+    int b_off, stg_off, rowoff_off, bias_off, utab_off, bar_off, total;
 };
 
 __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
@@ -161,7 +161,8 @@ __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
     p.stg_off = p.b_off + (a.resident ? p.w_images : NSB) * p.b_stage_bytes;
     p.rowoff_off = p.stg_off;
     p.bias_off = p.rowoff_off;
-    p.bar_off = p.bias_off + a.N * 4;
+    p.utab_off = p.bias_off + a.N * 4;
+    p.bar_off = p.utab_off;
     p.total = p.bar_off + 256 + 1024;
     return p;
 }
@@ -235,12 +236,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         }
     } else if (warp == 1) {
         // =========================================================================== MMA issuer
+        // One elected thread issues every MMA and the warp is a serial instruction chain: measured ~200 cycles per MMA
+        // when the tap / slab / pass geometry was re-derived inside a lane-0-only loop (4x the tensor pipe's 48-64).
+        // The loop below is convergent (all lanes, warp-uniform operands from the constant bank), the per-unit operand
+        // offsets come tabulated from the launcher, and a K step only adds 2 to the two descriptor low words.
         const uint32_t idesc = make_idesc(a.N);
         int buf = 0, stage = 0, acc = 0;
         uint32_t bphase = 0, sphase = 0, aphase = 0;
-        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
         long long t_wacc = 0, t_wplane = 0, t_wb = 0;
         const long long t_start = dbg_on ? clock64() : 0;
+        const uint32_t bs_lo = desc_lo(smem_u32(Bs));
+        const uint32_t bstep = (uint32_t)pl.b_stage_bytes >> 4;
+        if (a.resident && tile_begin < tile_end) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
@@ -253,41 +261,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             if (dbg_on) { t_wacc += w1 - w0; t_wplane += clock64() - w1; }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.N);
-            const uint32_t pbase = smem_u32(planes + buf * pl.buf_bytes);
-            int unit = 0;
-            for (int tap = 0; tap < a.ntaps; ++tap) {
-                const int arow = lead + a.back + a.tap_shift[tap];
-                for (int slab = 0; slab < a.nslab; ++slab) {
-                    const uint32_t a_hi = pbase + (uint32_t)(((a.tap_plane[tap] * a.nslab + slab) * npb) * pl.plane_bytes + arow * 128);
-                    for (int pass = 0; pass < a.npass; ++pass, ++unit) {
-                        if (!a.resident || (tile == tile_begin && unit == 0)) {
-                            const long long w2 = dbg_on ? clock64() : 0;
-                            mbar_wait(&b_full[stage], sphase);
-                            if (dbg_on) t_wb += clock64() - w2;
-                            tc_fence_after();
-                        }
-                        if (lane == 0) {
-                            const uint32_t a_addr = a_hi + (pass == 1 ? (uint32_t)pl.plane_bytes : 0u);
-                            const int wimg = a.resident ? ((tap * a.nslab + slab) * npb + (pass == 2 ? 1 : 0)) : stage;
-                            const uint32_t b_addr = smem_u32(Bs + wimg * pl.b_stage_bytes);
-#pragma unroll
-                            for (int k = 0; k < KC / 16; ++k)
-                                if (!CEXP(8)) umma_f16(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, (unit | k) ? 1u : 0u);
-                            if (!a.resident) umma_commit(&b_empty[stage]);
-                            if (unit == units_per_tile - 1) {
-                                umma_commit(&acc_full[acc]);
-                                umma_commit(&plane_empty[buf]);
-                            }
-                        }
-                        __syncwarp();
-                        if (!a.resident && ++stage == NSB) { stage = 0; sphase ^= 1; }
-                    }
+            const uint32_t origin = (smem_u32(planes + buf * pl.buf_bytes) + (uint32_t)lead * 128u) >> 4;
+            for (int unit = 0; unit < units_per_tile; ++unit) {
+                uint32_t blo;
+                if (!a.resident) {
+                    const long long w2 = dbg_on ? clock64() : 0;
+                    mbar_wait(&b_full[stage], sphase);
+                    if (dbg_on) t_wb += clock64() - w2;
+                    tc_fence_after();
+                    blo = bs_lo + (uint32_t)stage * bstep;
+                } else {
+                    blo = bs_lo + (uint32_t)a.unit_b[unit] * bstep;
+                }
+                const uint32_t alo = ((origin + a.unit_a[unit]) & 0x3FFFu) | (1u << 16);
+                if (!CEXP(8)) {
+                    umma_f16_lo_elect(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
+                    umma_f16_lo_elect(d_tmem, alo + 2, blo + 2, idesc, 1u);
+                    umma_f16_lo_elect(d_tmem, alo + 4, blo + 4, idesc, 1u);
+                    umma_f16_lo_elect(d_tmem, alo + 6, blo + 6, idesc, 1u);
+                }
+                if (!a.resident) {
+                    umma_commit_elect(&b_empty[stage]);
+                    if (++stage == NSB) { stage = 0; sphase ^= 1; }
                 }
             }
+            umma_commit_elect(&acc_full[acc]);
+            umma_commit_elect(&plane_empty[buf]);
             if (++acc == 2) { acc = 0; aphase ^= 1; }
             if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
-        if (dbg_on) { a.dbg[4] = clock64() - t_start; a.dbg[5] = t_wacc; a.dbg[6] = t_wplane; a.dbg[7] = t_wb; a.dbg[2] = tile_end - tile_begin; a.dbg[0] = clock64() - t_start; }
+        if (dbg_on && lane == 0) { a.dbg[4] = clock64() - t_start; a.dbg[5] = t_wacc; a.dbg[6] = t_wplane; a.dbg[7] = t_wb; a.dbg[2] = tile_end - tile_begin; a.dbg[0] = clock64() - t_start; }
     } else if (warp == 2) {
         // =========================================================================== B (weight) loader
         int stage = 0;
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         if (it >= niter) continue;
-                        double* dstp = a.stats[s2] + ((size_t)b * a.Cout + chalf * cper + it * 8 + own) * 2;
+                        double* dstp = a.stats[s2] + ((size_t)b * (a.stats_ld ? a.stats_ld : a.Cout) + a.stats_coff + chalf * cper + it * 8 + own) * 2;
                         atomicAdd(dstp, (double)ssum[s2][it]);
                         atomicAdd(dstp + 1, (double)ssq[s2][it]);
                     }
@@ -510,6 +513,7 @@ int staged_rows(const PlaneConvArgs& a, int* front) {
 bool staged_conv_supported(const PlaneConvArgs& a_in) {
     if (!plane_conv_supported(a_in)) return false;
     PlaneConvArgs a = a_in;
+    if (a.ntaps * a.nslab * a.npass > kMaxConvUnits) return false;
     if ((a.Cout != 16 && a.Cout != 32 && a.Cout != 64 && a.Cout != 128) || a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1) > 16) return false;
     return choose_nbuf(a) > 0;
 }
@@ -532,6 +536,19 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
     a.p_magic = a.P == 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)a.P) + 1u;
     if (!choose_nbuf(a)) return fail("conv_staged: shared-memory budget");
     const Plan pl = make_plan(a);
+    {
+        const int npb = a.npass == 3 ? 2 : 1;
+        const int units = a.ntaps * a.nslab * a.npass;
+        if (units > kMaxConvUnits) return fail("conv_staged: too many K units");
+        for (int u = 0; u < units; ++u) {
+            const int pass = u % a.npass, ts = u / a.npass;
+            const int slab = ts % a.nslab, tap = ts / a.nslab;
+            const unsigned a_rel = (unsigned)((((a.tap_plane[tap] * a.nslab + slab) * npb) + (pass == 1 ? 1 : 0)) * pl.plane_bytes +
+                                              (a.back + a.tap_shift[tap]) * 128);
+            a.unit_a[u] = a_rel >> 4;
+            a.unit_b[u] = (unsigned short)((tap * a.nslab + slab) * npb + (pass == 2 ? 1 : 0));
+        }
+    }
     static int configured = 0;
     if (pl.total > configured) {
         EAB_CUDA(cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                         sq += u * u;
                     }
                     if (r_hi > r_lo) {
-                        double* dst = a.stats[s] + ((size_t)b * a.Cout + c) * 2;
+                        double* dst = a.stats[s] + ((size_t)b * (a.stats_ld ? a.stats_ld : a.Cout) + a.stats_coff + c) * 2;
                         atomicAdd(dst, (double)sum);
                         atomicAdd(dst + 1, (double)sq);
                     }

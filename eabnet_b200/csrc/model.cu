@@ -113,6 +113,10 @@ struct ConvLayer {
     int u_ntaps[2] = {0, 0};
     int u_dt[2][kMaxTaps], u_df[2][kMaxTaps];
     size_t off_whi[2] = {0, 0}, off_wlo[2] = {0, 0}, off_ub = 0;
+    // gated 64-channel layers also get channel-split images: split s = value | gate of channels 32 s .. 32 s + 32 (N = 64),
+    // so that a split's weights can stay resident in shared memory where the full N = 128 set cannot
+    bool has_split = false;
+    size_t off_shi[2][2] = {{0, 0}, {0, 0}}, off_slo[2][2] = {{0, 0}, {0, 0}}, off_sub[2] = {0, 0};
     NormAct na;
 };
 
@@ -201,6 +205,7 @@ struct eab_model {
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
+    int opt_split = 1;            // gated 1-pass layers whose weights cannot stay resident run as two channel-split launches
     int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
@@ -542,6 +547,36 @@ struct Packer {
         L.off_ub = alloc(cout_t);
         for (int n = 0; n < cout_t; ++n) blob[L.off_ub + n] = P(L.b)[n];
         L.umma_ok = true;
+        if (L.gated && co == 64 && !L.wide) {
+            for (int sp = 0; sp < 2; ++sp) {
+                L.off_sub[sp] = alloc(64);
+                for (int n = 0; n < 64; ++n) blob[L.off_sub[sp] + n] = P(L.b)[n < 32 ? sp * 32 + n : co + sp * 32 + (n - 32)];
+            }
+            for (int v = 0; v < L.nvar; ++v) {
+                const int nt = L.u_ntaps[v];
+                const __half* full_hi = reinterpret_cast<const __half*>(blob.data() + L.off_whi[v]);
+                const __half* full_lo = reinterpret_cast<const __half*>(blob.data() + L.off_wlo[v]);
+                for (int sp = 0; sp < 2; ++sp) {
+                    const size_t img = (size_t)nt * L.u_nslab * 64 * 32;
+                    L.off_shi[v][sp] = alloc(img);
+                    L.off_slo[v][sp] = alloc(img);
+                    // (alloc may have moved the blob: re-derive the source pointers)
+                    full_hi = reinterpret_cast<const __half*>(blob.data() + L.off_whi[v]);
+                    full_lo = reinterpret_cast<const __half*>(blob.data() + L.off_wlo[v]);
+                    __half* shi = reinterpret_cast<__half*>(blob.data() + L.off_shi[v][sp]);
+                    __half* slo = reinterpret_cast<__half*>(blob.data() + L.off_slo[v][sp]);
+                    for (int ts = 0; ts < nt * L.u_nslab; ++ts)
+                        for (int n = 0; n < 64; ++n) {
+                            const int nf = n < 32 ? sp * 32 + n : co + sp * 32 + (n - 32);
+                            for (int k = 0; k < 64; ++k) {
+                                shi[(size_t)ts * 64 * 64 + sw128_index_h(n, k)] = full_hi[(size_t)ts * cout_t * 64 + sw128_index_h(nf, k)];
+                                slo[(size_t)ts * 64 * 64 + sw128_index_h(n, k)] = full_lo[(size_t)ts * cout_t * 64 + sw128_index_h(nf, k)];
+                            }
+                        }
+                }
+            }
+            L.has_split = true;
+        }
     }
 
     void tcm(TcmLayer& t) {
@@ -822,6 +857,7 @@ bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p, int force_P = 0) {
     p->Cout = u.Cout; p->N = u.N; p->gate_off = u.gate_off; p->relu = u.relu; p->algo_frac = u.algo_frac;
     p->out = u.out; p->out_ld = u.out_ld; p->out_coff = u.out_coff; p->resid = u.resid;
     p->nstats = u.nstats;
+    p->stats_ld = u.stats_ld; p->stats_coff = u.stats_coff;
     for (int i = 0; i < 2; ++i) { p->stats[i] = u.stats[i]; p->stat_alpha[i] = u.stat_alpha[i]; }
     p->tiles_per_b = (int)(((long long)u.T * p->P + 127) / 128);
     p->nbuf = 1;
@@ -911,28 +947,42 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
     double* stats = in_stats ? cx.alloc_stats(L.cout) : nullptr;
     out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
     if (cx.tensor_ok() && L.umma_ok) {
-        UmmaConvArgs us[2];
+        UmmaConvArgs us[4];
         bool all_ok = true;
+        int nus = 0;
         for (int v = 0; v < L.nvar; ++v) {
-            UmmaConvArgs& u = us[v];
-            memset(&u, 0, sizeof(u));
-            u.nsrc = nsrc;
-            for (int i = 0; i < nsrc; ++i) set_src(u.src[i], srcs[i]);
-            u.B = cx.B; u.T = cx.T; u.Fin = Fin; u.Fout = Fout;
-            if (L.deconv) { u.in_stride = 1; u.out_stride = 2; u.out_off = v; u.E = (Fout - v + 1) / 2; }
-            else          { u.in_stride = 2; u.out_stride = 1; u.out_off = 0; u.E = Fout; }
-            u.ntaps = L.u_ntaps[v];
-            for (int i = 0; i < u.ntaps; ++i) { u.dt[i] = L.u_dt[v][i]; u.df[i] = L.u_df[v][i]; }
-            u.wide = L.wide; u.kwidth = L.u_kwidth; u.nslab = L.u_nslab; u.ncoef = cin;
-            u.npass = L.zone == 0 ? cx.m->opt_enc_passes : cx.m->opt_dec_passes;
-            u.Whi = cx.W(L.off_whi[v]); u.Wlo = cx.W(L.off_wlo[v]); u.bias = cx.W(L.off_ub);
-            u.Cout = L.cout; u.N = L.u_N; u.gate_off = L.u_gate_off; u.algo_frac = 1.f;
-            u.out = out->data; u.out_ld = L.cout; u.out_coff = 0;
-            if (stats) { u.nstats = 1; u.stats[0] = stats; }
-            u.tiles_per_b = (cx.T * u.E + 127) / 128;
-            all_ok = all_ok && umma_conv_supported(u);
+            const int npass = L.zone == 0 ? cx.m->opt_enc_passes : cx.m->opt_dec_passes;
+            // weights of the variant as one resident set: taps x slabs x (hi[, lo]) x N rows x 128 B
+            const size_t wbytes = (size_t)L.u_ntaps[v] * L.u_nslab * (npass == 3 ? 2 : 1) * L.u_N * 128;
+            const bool split = L.has_split && cx.m->opt_split && npass == 1 && wbytes > 112 * 1024;
+            for (int sp = 0; sp < (split ? 2 : 1); ++sp) {
+                UmmaConvArgs& u = us[nus++];
+                memset(&u, 0, sizeof(u));
+                u.nsrc = nsrc;
+                for (int i = 0; i < nsrc; ++i) set_src(u.src[i], srcs[i]);
+                u.B = cx.B; u.T = cx.T; u.Fin = Fin; u.Fout = Fout;
+                if (L.deconv) { u.in_stride = 1; u.out_stride = 2; u.out_off = v; u.E = (Fout - v + 1) / 2; }
+                else          { u.in_stride = 2; u.out_stride = 1; u.out_off = 0; u.E = Fout; }
+                u.ntaps = L.u_ntaps[v];
+                for (int i = 0; i < u.ntaps; ++i) { u.dt[i] = L.u_dt[v][i]; u.df[i] = L.u_df[v][i]; }
+                u.wide = L.wide; u.kwidth = L.u_kwidth; u.nslab = L.u_nslab; u.ncoef = cin;
+                u.npass = npass;
+                u.algo_frac = 1.f;
+                u.out = out->data; u.out_ld = L.cout;
+                if (split) {
+                    u.Whi = cx.W(L.off_shi[v][sp]); u.Wlo = cx.W(L.off_slo[v][sp]); u.bias = cx.W(L.off_sub[sp]);
+                    u.Cout = 32; u.N = 64; u.gate_off = 32; u.out_coff = sp * 32;
+                    u.stats_ld = L.cout; u.stats_coff = sp * 32;
+                } else {
+                    u.Whi = cx.W(L.off_whi[v]); u.Wlo = cx.W(L.off_wlo[v]); u.bias = cx.W(L.off_ub);
+                    u.Cout = L.cout; u.N = L.u_N; u.gate_off = L.u_gate_off; u.out_coff = 0;
+                }
+                if (stats) { u.nstats = 1; u.stats[0] = stats; }
+                u.tiles_per_b = (cx.T * u.E + 127) / 128;
+                all_ok = all_ok && umma_conv_supported(u);
+            }
         }
-        if (all_ok) return run_tensor_convs(cx, us, L.nvar);
+        if (all_ok) return run_tensor_convs(cx, us, nus);
     }
     if (cx.dry) return 0;
     for (int v = 0; v < L.nvar; ++v) {
@@ -1708,6 +1758,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "conv_exp") m->opt_conv_exp = value;
+    else if (n == "split") m->opt_split = value != 0;
     else if (n == "fused_head") m->opt_fused_head = value != 0;
     else if (n == "head_w_tap") m->opt_head_w_tap = value != 0;
     else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;

@@ -108,6 +108,42 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same MMA with the descriptors given as their LOW words (start address >> 4 | LBO): the high word of a K-major
+// SWIZZLE_128B descriptor (SBO = 1024 B, version 1, swizzle mode 2) is the constant DESC_HI, so an issue loop only adds
+// 2 (= 32 bytes) per K step instead of rebuilding two 64-bit descriptors (the issuing thread is a serial chain).
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+        : "memory");
+}
+// Whole-warp (convergent) forms: every lane executes the surrounding loop with warp-uniform operands, one elected lane
+// issues.  Keeping the issue loop convergent lets the compiler hold the descriptors in uniform registers; issuing from
+// inside an `if (lane == 0)` region costs an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~15 instructions) per MMA.
+__device__ __forceinline__ void umma_f16_lo_elect(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
