@@ -39,6 +39,7 @@ inline int ceil8(int x) { return (x + 7) & ~7; }
 #else
 #define CEXP(bit) false
 #endif
+constexpr bool kTwoIssuers = false;
 constexpr int STAGE_RB = 8;                     // 32-row blocks per stage CTA
 
 // ------------------------------------------------------------------------------------------------ stage kernel
@@ -234,22 +235,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             __syncwarp();
             if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
-    } else if (warp == 1) {
-        // =========================================================================== MMA issuer
+    } else if (warp == 1 || warp == 3) {
+        // =========================================================================== MMA issuers
         // One elected thread issues every MMA and the warp is a serial instruction chain: measured ~200 cycles per MMA
         // when the tap / slab / pass geometry was re-derived inside a lane-0-only loop (4x the tensor pipe's 48-64).
         // The loop below is convergent (all lanes, warp-uniform operands from the constant bank), the per-unit operand
         // offsets come tabulated from the launcher, and a K step only adds 2 to the two descriptor low words.
+        // Two issuers (warps 1 and 3) alternate tiles: issuer j owns accumulator j, so two tiles' chains are in flight.
+        // Only with resident weights and exactly two plane buffers: issuer j then owns plane buffer j and accumulator j
+        // outright, so every mbarrier it waits on advances by exactly one phase per wait (a parity wait must never
+        // be two phases away from the barrier).  Otherwise one issuer walks all tiles.
+        const int isr = warp >> 1;                               // 0 or 1
+        const int nisr = (kTwoIssuers && a.resident && a.nbuf == 2) ? 2 : 1;       // measured: no gain over one issuer + 3 plane buffers
         const uint32_t idesc = make_idesc(a.N);
-        int buf = 0, stage = 0, acc = 0;
-        uint32_t bphase = 0, sphase = 0, aphase = 0;
-        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && isr == 0;
         long long t_wacc = 0, t_wplane = 0, t_wb = 0;
         const long long t_start = dbg_on ? clock64() : 0;
         const uint32_t bs_lo = desc_lo(smem_u32(Bs));
         const uint32_t bstep = (uint32_t)pl.b_stage_bytes >> 4;
-        if (a.resident && tile_begin < tile_end) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
+        if (a.resident && isr < nisr && tile_begin + isr < tile_end) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }
+        for (int tile = isr < nisr ? tile_begin + isr : tile_end; tile < tile_end; tile += nisr) {
+            const int ord = tile - tile_begin;                   // ordinal of the tile in this CTA: every phase follows from it
+            const int acc = ord & 1;
+            const int buf = ord % a.nbuf;
+            const uint32_t bphase = (uint32_t)((ord / a.nbuf) & 1);
+            const uint32_t aphase = (uint32_t)((ord >> 1) & 1);
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
             const int rs = a.np_front + row0 - a.back;
@@ -262,11 +272,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.N);
             const uint32_t origin = (smem_u32(planes + buf * pl.buf_bytes) + (uint32_t)lead * 128u) >> 4;
-            for (int unit = 0; unit < units_per_tile; ++unit) {
+            int g = ord * units_per_tile;                        // global unit ordinal (weight ring position)
+            for (int unit = 0; unit < units_per_tile; ++unit, ++g) {
                 uint32_t blo;
+                const int stage = g % NSB;
                 if (!a.resident) {
                     const long long w2 = dbg_on ? clock64() : 0;
-                    mbar_wait(&b_full[stage], sphase);
+                    mbar_wait(&b_full[stage], (uint32_t)((g / NSB) & 1));
                     if (dbg_on) t_wb += clock64() - w2;
                     tc_fence_after();
                     blo = bs_lo + (uint32_t)stage * bstep;
@@ -280,15 +292,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                     umma_f16_lo_elect(d_tmem, alo + 4, blo + 4, idesc, 1u);
                     umma_f16_lo_elect(d_tmem, alo + 6, blo + 6, idesc, 1u);
                 }
-                if (!a.resident) {
-                    umma_commit_elect(&b_empty[stage]);
-                    if (++stage == NSB) { stage = 0; sphase ^= 1; }
-                }
+                if (!a.resident) umma_commit_elect(&b_empty[stage]);
             }
             umma_commit_elect(&acc_full[acc]);
             umma_commit_elect(&plane_empty[buf]);
-            if (++acc == 2) { acc = 0; aphase ^= 1; }
-            if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
         if (dbg_on && lane == 0) { a.dbg[4] = clock64() - t_start; a.dbg[5] = t_wacc; a.dbg[6] = t_wplane; a.dbg[7] = t_wb; a.dbg[2] = tile_end - tile_begin; a.dbg[0] = clock64() - t_start; }
     } else if (warp == 2) {
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 int choose_nbuf(PlaneConvArgs& a) {
     for (int res = 1; res >= 0; --res) {
         a.resident = res;
-        for (int nb = 3; nb >= (res ? 2 : 1); --nb) {
+        for (int nb = (res && kTwoIssuers) ? 2 : 3; nb >= (res ? 2 : 1); --nb) {
             a.nbuf = nb;
             if (make_plan(a).total <= 227 * 1024) return nb;
         }

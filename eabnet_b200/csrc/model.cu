@@ -205,7 +205,7 @@ struct eab_model {
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
-    int opt_split = 1;            // gated 1-pass layers whose weights cannot stay resident run as two channel-split launches
+    int opt_split = 0;            // gated 1-pass layers whose weights cannot stay resident run as two channel-split launches
     int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
