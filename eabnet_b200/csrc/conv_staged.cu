@@ -287,10 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                 }
                 const uint32_t alo = ((origin + a.unit_a[unit]) & 0x3FFFu) | (1u << 16);
                 if (!CEXP(8)) {
-                    umma_f16_lo_elect(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
-                    umma_f16_lo_elect(d_tmem, alo + 2, blo + 2, idesc, 1u);
-                    umma_f16_lo_elect(d_tmem, alo + 4, blo + 4, idesc, 1u);
-                    umma_f16_lo_elect(d_tmem, alo + 6, blo + 6, idesc, 1u);
+                    umma_f16_lo_elect_x4(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
                 }
                 if (!a.resident) umma_commit_elect(&b_empty[stage]);
             }

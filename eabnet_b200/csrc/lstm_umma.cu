@@ -326,6 +326,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         long long t_wait = 0, t_wx = 0;
         // one K = 64 operand slab (x: slab 0, h: slab 1) against the matching weight slab, both column halves,
         // three passes per half: A_hi B_hi, A_lo B_hi, A_hi B_lo
+        // Convergent issue (every lane runs the code, one elected lane issues): descriptor low words are a base plus
+        // compile-time offsets, a K step adds 2 (see umma.cuh).  The recurrent MMAs are ON the serial chain of the step.
+        const uint32_t a_lo0 = desc_lo(smem_u32(As)), b_lo0 = desc_lo(smem_u32(Bs));
         auto issue = [&](int slab, int buf, bool fresh, bool commit_halves) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -333,34 +336,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                 for (int pass = 0; pass < 3; ++pass) {
                     const int ahl = pass == 1 ? 1 : 0;
                     const int bhl = pass == 2 ? 1 : 0;
-                    const uint32_t aa = smem_u32(a_slab(As, ahl, slab));
-                    const uint32_t bb = smem_u32(Bs + (bhl * 2 + slab) * B_SLAB_BYTES + hf * 128 * 128);
+                    const uint32_t aa = a_lo0 + (uint32_t)(((ahl * 2 + slab) * SLAB_BYTES) >> 4);
+                    const uint32_t bb = b_lo0 + (uint32_t)(((bhl * 2 + slab) * B_SLAB_BYTES + hf * 128 * 128) >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_f16(tmem_base + buf * 256 + hf * 128, make_desc(aa + k * 32), make_desc(bb + k * 32), idesc,
-                                 (!fresh || (pass | k)) ? 1u : 0u);
+                        umma_f16_lo_elect(tmem_base + buf * 256 + hf * 128, aa + 2 * k, bb + 2 * k, idesc, (!fresh || (pass | k)) ? 1u : 0u);
                 }
-                if (commit_halves) umma_commit(&acc_full[hf]);
+                if (commit_halves) umma_commit_elect(&acc_full[hf]);
             }
         };
         MBW(x_ready, 0u);
         tc_fence_after();
-        if (lane == 0) { issue(0, 0, true, false); umma_commit(x_free); }
-        __syncwarp();
+        issue(0, 0, true, false);
+        umma_commit_elect(x_free);
         for (int t = 0; t < a.T; ++t) {
             const long long c0 = dbg_on ? clock64() : 0;
             MBW(h_ready, (uint32_t)(t & 1));
             if (dbg_on) t_wait += clock64() - c0;
             tc_fence_after();
-            if (lane == 0) issue(1, t & 1, false, true);             // recurrent half: the only MMAs on the serial chain
-            __syncwarp();
+            issue(1, t & 1, false, true);                            // recurrent half: the only MMAs on the serial chain
             if (t + 1 < a.T) {
                 const long long c2 = dbg_on ? clock64() : 0;
                 MBW(x_ready, (uint32_t)((t + 1) & 1));
                 if (dbg_on) t_wx += clock64() - c2;
                 tc_fence_after();
-                if (lane == 0) { issue(0, (t + 1) & 1, true, false); umma_commit(x_free); }   // runs under the cell phase of step t
-                __syncwarp();
+                issue(0, (t + 1) & 1, true, false);                  // runs under the cell phase of step t
+                umma_commit_elect(x_free);
             }
         }
         if (dbg_on) { a.dbg[5] = t_wait; a.dbg[7] = t_wx; }
