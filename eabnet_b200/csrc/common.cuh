@@ -258,6 +258,10 @@ struct PlaneConvArgs {
     // plane origin, weight image index.  Kernel parameters live in the constant bank => warp-uniform loads.
     unsigned int unit_a[kMaxConvUnits];
     unsigned short unit_b[kMaxConvUnits];
+    // STFT epilogue mode (stft_M > 0, see stft.cu): batch items are (b, mic) sequences, rows are hops, the 128 columns
+    // of the launch are interleaved (re, im) pairs of bins out_coff/2 ..; the epilogue applies the square-root
+    // compression and writes spec[b][t][f][mic][2] for t < stft_T, f < stft_F.
+    int stft_M, stft_T, stft_F;
 };
 bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
 int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);
@@ -266,6 +270,7 @@ int staged_rows(const PlaneConvArgs& a, int* front);    // rows per batch item o
 bool staged_conv_supported(const PlaneConvArgs& a);
 int launch_stage(const PlaneConvArgs& a, cudaStream_t st);
 int launch_conv_staged(PlaneConvArgs a, cudaStream_t st);
+extern bool g_stft_tc;           // STFT as a tcgen05 GEMM (default) / fp32 CUDA-core kernel
 
 struct CombineArgs {
     ConvSrc src[3];

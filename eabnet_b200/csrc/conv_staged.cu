@@ -425,7 +425,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                 }
                 v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w;
                 v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
-                if (row_valid && !CEXP(1)) {
+                if (a.stft_M > 0) {
+                    // DFT-as-GEMM epilogue: columns are (re, im) pairs; z |z|^-1/2 (test.py:41-43) -> spec[b][t][f][mic][2]
+                    // rows are (hop t, mic) with pitch stft_M: consecutive lanes write consecutive mics of one (t, f)
+                    const int r = row0 + row;
+                    const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
+                    const int mic = r - t * a.P;
+                    if (t < a.stft_T && mic < a.stft_M) {
+                        const int f0 = (a.out_coff + c0) >> 1;
+                        float2* sp = reinterpret_cast<float2*>(a.out) + (((size_t)b * a.stft_T + t) * a.stft_F + f0) * a.stft_M + mic;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (f0 + i < a.stft_F) {
+                                const float x = v[2 * i], y = v[2 * i + 1];
+                                const float mag = sqrtf(x * x + y * y);
+                                const float sc = mag > 0.f ? rsqrtf(mag) : 0.f;
+                                sp[(size_t)i * a.stft_M] = make_float2(x * sc, y * sc);
+                            }
+                        }
+                    }
+                } else if (row_valid && !CEXP(1)) {
                     float4* o4 = reinterpret_cast<float4*>(a.out + off + c0);
                     o4[0] = make_float4(v[0], v[1], v[2], v[3]);
                     o4[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -570,7 +589,8 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
     const double pos = (double)a.B * a.T * a.E;
     double kreal = 0;
     for (int i = 0; i < a.nsrc; ++i) kreal += a.src[i].C;
-    ProfScope ps("conv_tma", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
+    if (a.stft_M > 0) kreal = 160;                           // a hop per tap
+    ProfScope ps(a.stft_M > 0 ? "stft" : "conv_tma", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
                  (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1) + 4.0 * pos * a.Cout * (a.resid ? 2 : 1) +
                      4.0 * a.ntaps * kreal * a.N,
                  st);

@@ -15,12 +15,17 @@
 // (frames x mics, or frames) as register accumulators; the A operand sits in shared memory [k][RB], the
 // twiddle table (built in double on the host) streams from L2.
 #include <math.h>
+#include <string.h>
 #include <mutex>
 #include <vector>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace eab {
+
+bool g_stft_tc = true;
 
 namespace {
 
@@ -35,7 +40,16 @@ struct Tables {
     float* inv = nullptr;    // [161][352]: col<161: a_f cos(th f n)/320 ; col>=161: 2 sin(th f n)/320 (f in 1..159)
     float* win = nullptr;    // [320] periodic hann
     float* ienv = nullptr;   // [160] 1 / (w[n]^2 + w[n+160]^2)
+    // tensor-core forward transform: windowed DFT matrix as fp16 hi / lo weight images of the conv_tma kernel,
+    // [3 column groups][2 taps (first / second hop of a frame)][3 K slabs][128 rows][64 k], 128B-swizzled;
+    // column 2f = Re X[f], 2f+1 = Im X[f]
+    void* dft_hi = nullptr;
+    void* dft_lo = nullptr;
+    void* planes = nullptr;  // scratch: fp16 hi/lo hop planes of the waveforms (grow-only)
+    size_t planes_bytes = 0;
 };
+constexpr int DFT_GROUPS = 3, DFT_SLABS = 3;
+constexpr size_t DFT_GROUP_HALVES = (size_t)2 * DFT_SLABS * 128 * 64;
 Tables g_tab[64];
 std::mutex g_tab_mu;
 
@@ -76,6 +90,33 @@ int get_tables(Tables** out) {
         EAB_CUDA(cudaMemcpy(t.inv, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
         EAB_CUDA(cudaMemcpy(t.win, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
         EAB_CUDA(cudaMemcpy(t.ienv, ienv.data(), ienv.size() * 4, cudaMemcpyHostToDevice));
+        // DFT weight images (double precision twiddles, exact argument reduction)
+        std::vector<__half> hi(DFT_GROUPS * DFT_GROUP_HALVES), lo(DFT_GROUPS * DFT_GROUP_HALVES);
+        for (int g = 0; g < DFT_GROUPS; ++g)
+            for (int tap = 0; tap < 2; ++tap)
+                for (int sl = 0; sl < DFT_SLABS; ++sl)
+                    for (int n = 0; n < 128; ++n)
+                        for (int k = 0; k < 64; ++k) {
+                            const int col = g * 128 + n, f = col >> 1, im = col & 1;
+                            const int hs = sl * 64 + k;                       // sample inside the hop
+                            double wv = 0.0;
+                            if (f < NF && hs < HOP) {
+                                const int ns = tap * HOP + hs;                // sample inside the frame
+                                const int kf = (ns * f) % NFFT;
+                                wv = w[ns] * (im ? -sin(th * kf) : cos(th * kf));
+                                if (im && (f == 0 || f == 160)) wv = 0.0;
+                            }
+                            const float wf = (float)wv;
+                            const __half h = __float2half_rn(wf);
+                            const size_t idx = g * DFT_GROUP_HALVES + ((size_t)(tap * DFT_SLABS + sl) * 128 + n) * 64 +
+                                               (size_t)((((k >> 3) ^ (n & 7)) << 3) | (k & 7));
+                            hi[idx] = h;
+                            lo[idx] = __float2half_rn(wf - __half2float(h));
+                        }
+        EAB_CUDA(cudaMalloc(&t.dft_hi, hi.size() * 2));
+        EAB_CUDA(cudaMalloc(&t.dft_lo, lo.size() * 2));
+        EAB_CUDA(cudaMemcpy(t.dft_hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+        EAB_CUDA(cudaMemcpy(t.dft_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
     }
     *out = &t;
     return 0;
@@ -359,12 +400,107 @@ __global__ void step_advance_kernel(int* step) {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ tensor-core STFT
+// A centred frame t is two consecutive hops of the reflect-padded signal p: X_t = p_hop[t] W_first + p_hop[t+1] W_second,
+// i.e. a two-tap "convolution" over hop rows with K = 160 (+32 zero) channels per tap and 322 output columns: exactly
+// the GEMM the conv_tma kernel runs.  This kernel writes the hop rows as the kernel's fp16 hi / lo plane images
+// (np[slab*2 + hl] : [B*M][np_rows][64] halves, 128B-swizzled by row & 7; row = np_front + hop index, hops 0..T).
+__global__ void __launch_bounds__(256) stft_stage_kernel(const float* __restrict__ wave, uint8_t* __restrict__ planes,
+                                                         size_t image_bytes, int np_rows, int np_front, int L, int T, int M) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.z, slab = blockIdx.y;
+    const int c8 = threadIdx.x & 7;
+    for (int it = 0; it < 8; ++it) {
+        const int rho = (blockIdx.x * 8 + it) * 32 + (threadIdx.x >> 3);
+        if (rho >= np_rows) break;
+        const int rr = rho - np_front;                      // plane row = hop j * M + mic
+        const int j = rr >= 0 ? rr / M : -1;
+        const int mic = rr - j * M;
+        const float* x = wave + ((size_t)b * M + (j >= 0 ? mic : 0)) * L;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int hs = slab * 64 + c8 * 8 + i;
+            float s = 0.f;
+            if (j >= 0 && j <= T && hs < HOP) {
+                int q = HOP * j + hs - HOP;                 // centre padding = 160, reflect (test.py:35)
+                if (q < 0) q = -q;
+                if (q >= L) q = 2 * (L - 1) - q;
+                s = __ldg(x + q);
+            }
+            v[i] = s;
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+            h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const size_t off = ((size_t)b * np_rows + rho) * 128 + (size_t)((c8 ^ (rho & 7)) << 4);
+        *reinterpret_cast<uint4*>(planes + (size_t)(slab * 2 + 0) * image_bytes + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(planes + (size_t)(slab * 2 + 1) * image_bytes + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int L, int T, cudaStream_t st) {
+    PlaneConvArgs a;
+    memset(&a, 0, sizeof(a));
+    // rows of batch item b are (hop j, mic) with pitch M, so that the epilogue's lanes write consecutive mics
+    a.B = B; a.T = T + 1; a.Fin = M; a.E = M; a.P = M;
+    a.nplanes = 1; a.plane_cols[0] = M; a.col_stride = 1;
+    a.ntaps = 2;
+    a.tap_plane[0] = 0; a.tap_shift[0] = 0;                 // first half of the frame: hop t
+    a.tap_plane[1] = 0; a.tap_shift[1] = M;                 // second half: hop t + 1
+    a.back = 0; a.fwd = M;
+    a.out_stride = 1; a.Fout = 1;
+    a.nslab = DFT_SLABS; a.ncoef = 0; a.npass = 3;
+    a.Cout = 128; a.N = 128; a.gate_off = 0; a.algo_frac = 322.f / 384.f;
+    a.out = spec; a.out_ld = 128;
+    a.tiles_per_b = (int)(((long long)a.T * a.P + 127) / 128);
+    a.stft_M = M; a.stft_T = T; a.stft_F = NF;
+    int front = 0;
+    a.np_rows = staged_rows(a, &front);
+    a.np_front = front;
+    const size_t image_bytes = (size_t)a.B * a.np_rows * 128;
+    const size_t need = image_bytes * DFT_SLABS * 2;
+    {
+        std::lock_guard<std::mutex> lk(g_tab_mu);
+        if (t->planes_bytes < need) {
+            if (t->planes) { EAB_CUDA(cudaStreamSynchronize(st)); EAB_CUDA(cudaFree(t->planes)); }
+            t->planes = nullptr; t->planes_bytes = 0;
+            EAB_CUDA(cudaMalloc(&t->planes, need));
+            t->planes_bytes = need;
+        }
+    }
+    for (int i = 0; i < DFT_SLABS * 2; ++i) a.np[i] = static_cast<uint8_t*>(t->planes) + (size_t)i * image_bytes;
+    {
+        ProfScope ps("stage", 0.0, 4.0 * (double)B * M * L + (double)need, st);
+        dim3 grid((a.np_rows + 255) / 256, DFT_SLABS, a.B);
+        EAB_CUDA(launch_k(stft_stage_kernel, grid, dim3(256), (size_t)0, st, wave, static_cast<uint8_t*>(t->planes), image_bytes,
+                          a.np_rows, a.np_front, L, T, M));
+        EAB_LAUNCH_CHECK("stft_stage_kernel");
+    }
+    for (int g = 0; g < DFT_GROUPS; ++g) {
+        PlaneConvArgs ag = a;
+        ag.Whi = reinterpret_cast<const float*>(static_cast<const __half*>(t->dft_hi) + g * DFT_GROUP_HALVES);
+        ag.Wlo = reinterpret_cast<const float*>(static_cast<const __half*>(t->dft_lo) + g * DFT_GROUP_HALVES);
+        ag.out_coff = g * 128;
+        EAB_TRY(launch_conv_staged(ag, st));
+    }
+    return 0;
+}
+
 int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st) {
     if (L < HOP + 1) return fail("stft: need at least 161 samples (reflect padding of 160)");
     if (B <= 0 || M <= 0) return fail("stft: bad shape");
     Tables* t;
     EAB_TRY(get_tables(&t));
     const int T = 1 + L / HOP;
+    if (g_stft_tc) return launch_stft_tc(t, wave, spec, B, M, L, T, st);
     static bool configured = false;
     if (!configured) {
         EAB_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
