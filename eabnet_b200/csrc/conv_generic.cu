@@ -360,6 +360,15 @@ int launch_conv(const ConvArgs& a, cudaStream_t st) {
         if (a.out_RT < 1 || (a.resid && a.resid_RT < 1)) return fail("conv: bad output ring");
     }
     const bool g = a.gate_off > 0;
+    // streaming launches have few rows (streams x E): 64-row tiles put twice as many CTAs in flight, which is what a
+    // latency-bound step wants; the offline cold path keeps the 128-row tiles
+    if (a.step && (long long)a.B * a.E <= 148ll * 128 * 2) {
+        switch (a.N / 64) {
+            case 1: if (!g) return launch_inst<1, 4, false>(a, st); break;
+            case 2: return g ? launch_inst<2, 4, true>(a, st) : launch_inst<2, 4, false>(a, st);
+            default: break;
+        }
+    }
     switch (a.N / 64) {
         case 1: return g ? fail("conv: gated layer needs N >= 128") : launch_inst<1, 8, false>(a, st);
         case 2: return g ? launch_inst<2, 8, true>(a, st) : launch_inst<2, 8, false>(a, st);

@@ -17,7 +17,10 @@ namespace {
 constexpr int SPC = 2;          // streams per CTA
 constexpr int CD = 64;          // squeezed channels
 constexpr int DF = 256;         // feature channels
-constexpr int NT = 256;
+constexpr int NT = 1024;        // the step is L2-latency bound: many threads = many weight loads in flight
+constexpr int KG1 = NT / CD;            // 16 K groups of the squeeze   (16 k each)
+constexpr int KG2 = NT / (2 * CD);      // 8 K groups of the dilated convs
+constexpr int KG3 = NT / DF;            // 4 K groups of the expand     (16 k each)
 
 __device__ __forceinline__ float prelu_norm(float v, float a, float s, float h) {
     v = v > 0.f ? v : a * v;
@@ -28,9 +31,8 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
     __shared__ float xs[SPC][DF];
     __shared__ float accs[SPC][DF];
     __shared__ float ys[SPC][CD];
-    __shared__ float red[4][SPC][CD];
-    __shared__ float u[2][8][SPC][CD];        // [branch][tap][stream][channel] normalised dilated-conv inputs
-    __shared__ float zred[2][SPC][2 * CD];
+    __shared__ float red[NT * SPC];            // partial sums of the current phase: [K group][stream][output]
+    __shared__ float u[2][8][SPC][CD];         // [branch][tap][stream][channel] normalised dilated-conv inputs
     __shared__ float uo[SPC][CD];
     pdl_trigger();
     pdl_wait();
@@ -44,29 +46,33 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
         accs[s][j] = 0.f;
     }
     __syncthreads();
+    const int kper2 = (a.kd * CD + KG2 - 1) / KG2;         // (tap, channel) pairs per K group of the dilated convs
     for (int l = 0; l < a.ntcm; ++l) {
         const TcmStreamDesc& d = a.desc[l];
-        // ---------------------------------------------------------------- squeeze 1x1
+        // ---------------------------------------------------------------- squeeze 1x1: 64 outputs x 16 K groups
         {
-            const int n = tid & 63, kg = tid >> 6;
+            const int n = tid & (CD - 1), kg = tid / CD;
+            constexpr int KPER = DF / KG1;
             float p[SPC];
 #pragma unroll
             for (int s = 0; s < SPC; ++s) p[s] = 0.f;
-            const float* w = a.blob + d.W_in + (size_t)(kg * 64) * CD + n;
-#pragma unroll 16
-            for (int k = 0; k < 64; ++k) {
+            const float* w = a.blob + d.W_in + (size_t)(kg * KPER) * CD + n;
+#pragma unroll
+            for (int k = 0; k < KPER; ++k) {
                 const float wv = __ldg(w + (size_t)k * CD);
 #pragma unroll
-                for (int s = 0; s < SPC; ++s) p[s] = fmaf(xs[s][kg * 64 + k], wv, p[s]);
+                for (int s = 0; s < SPC; ++s) p[s] = fmaf(xs[s][kg * KPER + k], wv, p[s]);
             }
 #pragma unroll
-            for (int s = 0; s < SPC; ++s) red[kg][s][n] = p[s];
+            for (int s = 0; s < SPC; ++s) red[(kg * SPC + s) * CD + n] = p[s];
         }
         __syncthreads();
         float* ring = a.act_base + d.ring_off;
         if (tid < SPC * CD) {
-            const int s = tid >> 6, n = tid & 63;
-            const float y = red[0][s][n] + red[1][s][n] + red[2][s][n] + red[3][s][n];
+            const int s = tid / CD, n = tid & (CD - 1);
+            float y = 0.f;
+#pragma unroll
+            for (int kg = 0; kg < KG1; ++kg) y += red[(kg * SPC + s) * CD + n];
             ys[s][n] = y;
             if (s0 + s < a.S) ring[((size_t)(s0 + s) * d.RT + ring_slot(step, d.RT)) * CD + n] = y;
         }
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
         for (int i = tid; i < a.kd * SPC * CD; i += NT) {
             const int tap = i / (SPC * CD);
             const int r = i - tap * (SPC * CD);
-            const int s = r >> 6, c = r & 63;
+            const int s = r / CD, c = r & (CD - 1);
             const int n = step - d.dt[tap];
             float vl = 0.f, vr = 0.f;
             if (n >= 0 && s0 + s < a.S) {
@@ -87,53 +93,63 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
             u[1][tap][s][c] = vr;
         }
         __syncthreads();
-        // ---------------------------------------------------------------- dilated convs (block-diagonal packed weights)
+        // ---------------------------------------------------------------- dilated convs: 128 outputs x 8 K groups
         {
-            const int col = tid & 127;                 // 0..63 left outputs, 64..127 right outputs
-            const int br = col >> 6;
-            const int half = tid >> 7;                 // channel half of the K range
+            const int col = tid & (2 * CD - 1);        // 0..63 left outputs, 64..127 right outputs (block-diagonal packing)
+            const int br = col / CD;
+            const int kg = tid / (2 * CD);
             float p[SPC];
 #pragma unroll
             for (int s = 0; s < SPC; ++s) p[s] = 0.f;
-            for (int tap = 0; tap < a.kd; ++tap) {
-                const float* w = a.blob + d.W_dil + ((size_t)tap * 2 * CD + br * CD + half * 32) * (2 * CD) + col;
-#pragma unroll 16
-                for (int c = 0; c < 32; ++c) {
-                    const float wv = __ldg(w + (size_t)c * (2 * CD));
+            const int j0 = kg * kper2, j1 = min(a.kd * CD, j0 + kper2);
+#pragma unroll 8
+            for (int j = j0; j < j1; ++j) {
+                const int tap = j / CD, c = j & (CD - 1);
+                const float wv = __ldg(a.blob + d.W_dil + ((size_t)tap * 2 * CD + br * CD + c) * (2 * CD) + col);
 #pragma unroll
-                    for (int s = 0; s < SPC; ++s) p[s] = fmaf(u[br][tap][s][half * 32 + c], wv, p[s]);
-                }
+                for (int s = 0; s < SPC; ++s) p[s] = fmaf(u[br][tap][s][c], wv, p[s]);
             }
 #pragma unroll
-            for (int s = 0; s < SPC; ++s) zred[half][s][col] = p[s];
+            for (int s = 0; s < SPC; ++s) red[(kg * SPC + s) * (2 * CD) + col] = p[s];
         }
         __syncthreads();
         if (tid < SPC * CD) {
-            const int s = tid >> 6, n = tid & 63;
-            const float zl = zred[0][s][n] + zred[1][s][n];
-            const float zr = zred[0][s][CD + n] + zred[1][s][CD + n];
+            const int s = tid / CD, n = tid & (CD - 1);
+            float zl = 0.f, zr = 0.f;
+#pragma unroll
+            for (int kg = 0; kg < KG2; ++kg) {
+                zl += red[(kg * SPC + s) * (2 * CD) + n];
+                zr += red[(kg * SPC + s) * (2 * CD) + CD + n];
+            }
             const float z = zl * sigmoid_f(zr);
             uo[s][n] = prelu_norm(z, __ldg(a.blob + d.aO + n), __ldg(a.blob + d.sO + n), __ldg(a.blob + d.hO + n));
         }
         __syncthreads();
-        // ---------------------------------------------------------------- expand 1x1 + residual
+        // ---------------------------------------------------------------- expand 1x1: 256 outputs x 4 K groups
         {
+            const int j = tid & (DF - 1), kg = tid / DF;
+            constexpr int KPER = CD / KG3;
             float p[SPC];
 #pragma unroll
-            for (int s = 0; s < SPC; ++s) p[s] = xs[s][tid];
-            const float* w = a.blob + d.W_out + tid;
-#pragma unroll 16
-            for (int c = 0; c < CD; ++c) {
+            for (int s = 0; s < SPC; ++s) p[s] = 0.f;
+            const float* w = a.blob + d.W_out + (size_t)(kg * KPER) * DF + j;
+#pragma unroll
+            for (int c = 0; c < KPER; ++c) {
                 const float wv = __ldg(w + (size_t)c * DF);
 #pragma unroll
-                for (int s = 0; s < SPC; ++s) p[s] = fmaf(uo[s][c], wv, p[s]);
+                for (int s = 0; s < SPC; ++s) p[s] = fmaf(uo[s][kg * KPER + c], wv, p[s]);
             }
-            // xs[.][tid] is read and written by this thread only; uo / zred are next written two barriers from here
 #pragma unroll
-            for (int s = 0; s < SPC; ++s) {
-                xs[s][tid] = p[s];
-                if ((l + 1) % a.p == 0) accs[s][tid] += p[s];
-            }
+            for (int s = 0; s < SPC; ++s) red[(kg * SPC + s) * DF + j] = p[s];
+        }
+        __syncthreads();
+        if (tid < SPC * DF) {
+            const int s = tid / DF, j = tid & (DF - 1);
+            float o = xs[s][j];
+#pragma unroll
+            for (int kg = 0; kg < KG3; ++kg) o += red[(kg * SPC + s) * DF + j];
+            xs[s][j] = o;
+            if ((l + 1) % a.p == 0) accs[s][j] += o;
         }
         __syncthreads();
     }

@@ -89,3 +89,26 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read(), f
+
+
+def test_stream_state_planning_is_host_only(lib):
+    """eab_stream_state_bytes is a pure planning call (no GPU): BN + causal gives a size, InstanceNorm / non-causal
+    configurations are refused with a message (streaming needs static normalisation)."""
+    import ctypes as C
+    from eabnet_b200 import _lib
+
+    def make(norm, causal):
+        cfg = _lib.EabConfig(2, 3, 1, 3, 64, 9, 64, 5, 64, 256, 6, 3, causal, 1, 0, 0, 0, norm, 161)
+        h = C.c_void_p()
+        assert lib.eab_create(C.byref(cfg), C.byref(h)) == 0
+        return h
+
+    h = make(1, 1)
+    n1, n256 = lib.eab_stream_state_bytes(h, 1), lib.eab_stream_state_bytes(h, 256)
+    assert n1 > 0 and n256 > 200 * n1 and n256 < 4 << 30
+    lib.eab_destroy(h)
+    for norm, causal in ((0, 1), (1, 0)):
+        h = make(norm, causal)
+        assert lib.eab_stream_state_bytes(h, 4) == 0
+        assert b"streaming needs" in lib.eab_last_error()
+        lib.eab_destroy(h)
