@@ -313,6 +313,15 @@ def main():
             achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None}
+        # DRAM bytes of a representative launch of that family from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_traffic.json"))).get(top["kernel"])
+        except Exception:
+            tr = None
+        if tr:
+            roof["traffic"] = tr["dram_bytes"]
+            roof["traffic_note"] = ("ncu dram bytes of one launch (%s): %.3f GB against %.3f GB algorithmic for that launch; `achieved` is the "
+                                    "family total over the step" % (tr["launch"], tr["dram_bytes"] / 1e9, tr["algorithmic_bytes"] / 1e9))
         roof.update({"kernel": top["kernel"], "launches_per_step": top["launches"], "ms_per_step": top["ms"],
                      "peak_source": peaks["source"] + (" (0.5 x sustained bf16 as TF32 peak)" if gemm_like else ""),
                      "share_of_step": shares})
