@@ -246,7 +246,8 @@ struct PlaneConvArgs {
     int tiles_per_b;             // ceil(T*P / 128)
     unsigned int p_magic;        // floor(2^32 / P) + 1  (division by P in the producers)
     int nbuf;                    // plane double-buffering (1 or 2), chosen by the launcher from the smem budget
-    int resident;                // conv_tma: all weight images stay in shared memory (else a 3-stage ring per tile)
+    int resident;                // conv_tma: all weight images stay in shared memory (else a ring of nsb stages)
+    int nsb;
     unsigned long long* dbg;     // optional [16] cycle counters of CTA 0 (diagnostics)
     // "staged" variant (conv_tma_kernel): the planes were written to HBM by stage_kernel as fp16 images
     // np[(plane * nslab + slab) * npb + hl] : [B][np_rows][64] halves, row = np_front + t*P + col, 128B-swizzled by row & 7

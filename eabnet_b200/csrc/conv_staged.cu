@@ -28,7 +28,7 @@ using namespace umma;
 
 constexpr int TM = 128;
 constexpr int KC = 64;
-constexpr int NSB = 3;                          // weight ring stages
+constexpr int NSB_MAX = 8;                      // weight ring stages: a.nsb in [2, 8], as many as fit next to two plane buffers
 constexpr int NEPI = 256;                       // 8 epilogue warps per group
 constexpr int NGRP = 2;                         // epilogue groups: group g drains TMEM accumulator g (alternate tiles)
 constexpr int NTHREADS = 128 + NGRP * NEPI;     // warp 0 plane copies, 1 MMA, 2 weight loader, 3 idle, 4-11 / 12-19 epilogue
@@ -159,7 +159,7 @@ __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
     p.w_images = a.ntaps * a.nslab * npb;
     p.stg_ld = a.Cout + 4;
     p.b_off = a.nbuf * p.buf_bytes;
-    p.stg_off = p.b_off + (a.resident ? p.w_images : NSB) * p.b_stage_bytes;
+    p.stg_off = p.b_off + (a.resident ? p.w_images : a.nsb) * p.b_stage_bytes;
     p.rowoff_off = p.stg_off;
     p.bias_off = p.rowoff_off;
     p.utab_off = p.bias_off + a.N * 4;
@@ -180,11 +180,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
     uint64_t* plane_full = bars;            // [3]
     uint64_t* plane_empty = bars + 3;       // [3]
-    uint64_t* b_full = bars + 6;            // [NSB]
-    uint64_t* b_empty = bars + 9;           // [NSB]
-    uint64_t* acc_full = bars + 12;         // [2]
-    uint64_t* acc_empty = bars + 14;        // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* b_full = bars + 6;            // [NSB_MAX]
+    uint64_t* b_empty = bars + 14;          // [NSB_MAX]
+    uint64_t* acc_full = bars + 22;         // [2]
+    uint64_t* acc_empty = bars + 24;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
-        for (int i = 0; i < NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
         fence_barrier_init();
     }
@@ -253,6 +253,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         const long long t_start = dbg_on ? clock64() : 0;
         const uint32_t bs_lo = desc_lo(smem_u32(Bs));
         const uint32_t bstep = (uint32_t)pl.b_stage_bytes >> 4;
+        int stage = 0;
+        uint32_t sphase = 0;
         if (a.resident && isr < nisr && tile_begin + isr < tile_end) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }
         for (int tile = isr < nisr ? tile_begin + isr : tile_end; tile < tile_end; tile += nisr) {
             const int ord = tile - tile_begin;                   // ordinal of the tile in this CTA: every phase follows from it
@@ -272,13 +274,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.N);
             const uint32_t origin = (smem_u32(planes + buf * pl.buf_bytes) + (uint32_t)lead * 128u) >> 4;
-            int g = ord * units_per_tile;                        // global unit ordinal (weight ring position)
-            for (int unit = 0; unit < units_per_tile; ++unit, ++g) {
+            for (int unit = 0; unit < units_per_tile; ++unit) {
                 uint32_t blo;
-                const int stage = g % NSB;
-                if (!a.resident) {
+                if (!a.resident) {                               // single issuer in ring mode: the ring position runs on
                     const long long w2 = dbg_on ? clock64() : 0;
-                    mbar_wait(&b_full[stage], (uint32_t)((g / NSB) & 1));
+                    mbar_wait(&b_full[stage], sphase);
                     if (dbg_on) t_wb += clock64() - w2;
                     tc_fence_after();
                     blo = bs_lo + (uint32_t)stage * bstep;
@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                 if (!CEXP(8)) {
                     umma_f16_lo_elect_x4(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
                 }
-                if (!a.resident) umma_commit_elect(&b_empty[stage]);
+                if (!a.resident) {
+                    umma_commit_elect(&b_empty[stage]);
+                    if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
+                }
             }
             umma_commit_elect(&acc_full[acc]);
             umma_commit_elect(&plane_empty[buf]);
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                         bulk_copy_g2s(Bs + stage * pl.b_stage_bytes, img, bytes, &b_full[stage]);
                     }
                     __syncwarp();
-                    if (++stage == NSB) { stage = 0; sphase ^= 1; }
+                    if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
                 }
             }
         }
@@ -515,12 +518,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 }
 
 int choose_nbuf(PlaneConvArgs& a) {
-    for (int res = 1; res >= 0; --res) {
-        a.resident = res;
-        for (int nb = (res && kTwoIssuers) ? 2 : 3; nb >= (res ? 2 : 1); --nb) {
-            a.nbuf = nb;
+    a.nsb = 3;
+    a.resident = 1;                                      // 1. resident weights next to 3 or 2 plane buffers
+    for (int nb = kTwoIssuers ? 2 : 3; nb >= 2; --nb) {
+        a.nbuf = nb;
+        if (make_plan(a).total <= 227 * 1024) return nb;
+    }
+    a.resident = 0;                                      // 2. weight ring: as many plane buffers as fit with a 3-stage ring
+    for (int nb = 3; nb >= 1; --nb) {                    //    (measured: 3 buffers + 3 stages beats 2 buffers + 6 stages), then
+        a.nbuf = nb;                                     //    deepen the ring into whatever shared memory is left
+        a.nsb = 3;
+        if (make_plan(a).total > 227 * 1024) continue;
+        for (int ns = NSB_MAX; ns > 3; --ns) {
+            a.nsb = ns;
             if (make_plan(a).total <= 227 * 1024) return nb;
         }
+        a.nsb = 3;
+        return nb;
     }
     return 0;
 }
