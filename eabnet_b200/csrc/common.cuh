@@ -263,12 +263,16 @@ struct PlaneConvArgs {
     // of the launch are interleaved (re, im) pairs of bins out_coff/2 ..; the epilogue applies the square-root
     // compression and writes spec[b][t][f][mic][2] for t < stft_T, f < stft_F.
     int stft_M, stft_T, stft_F;
+    // "wide" staging (first layer, 2M input channels): a plane row (t, e) is the whole kf x C tap window, wide_k contiguous
+    // floats starting at column e*col_stride of frame t, zero-padded to nslab*64; the time taps are then plain row shifts
+    int wide_k;
 };
 bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
 int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);
 // staged variant: geometry helpers + the two launches (stage = normalise + fp16 + layout, conv = TMA-fed GEMM)
 int staged_rows(const PlaneConvArgs& a, int* front);    // rows per batch item of a staged plane array (multiple of 8)
 bool staged_conv_supported(const PlaneConvArgs& a);
+bool staged_conv_fits(const PlaneConvArgs& a);          // shared-memory / unit-table budget only (caller vouches for the geometry)
 int launch_stage(const PlaneConvArgs& a, cudaStream_t st);
 int launch_conv_staged(PlaneConvArgs a, cudaStream_t st);
 extern bool g_stft_tc;           // STFT as a tcgen05 GEMM (default) / fp32 CUDA-core kernel

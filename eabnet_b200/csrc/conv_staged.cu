@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
     const int plane = ps / a.nslab;
     const int slab = ps - plane * a.nslab;
     const int C0 = a.src[0].C;
-    const bool second = slab * KC >= C0;
+    const bool second = a.wide_k == 0 && slab * KC >= C0;
     const ConvSrc& src = second ? a.src[1] : a.src[0];
     const int cbase = second ? slab * KC - C0 : slab * KC;
     if (threadIdx.x < 64) {
@@ -85,7 +85,26 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
         if (rho >= a.np_rows) break;
         const int r = rho - a.np_front;
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (r >= 0 && r < a.T * a.P) {
+        if (a.wide_k > 0) {
+            // first layer: the row is the raw kf x C window itself (no transform: the network input has none)
+            if (r >= 0 && r < a.T * a.P) {
+                const int t = (int)__umulhi((unsigned)r, a.p_magic);
+                const int col = r - t * a.P;
+                const int k0 = slab * KC + c8 * 8;
+                if (col < a.plane_cols[0] && k0 < a.wide_k) {
+                    const float* p = src.x + (((size_t)b * a.T + t) * a.Fin + (size_t)col * a.col_stride) * src.C + k0;     // 8-byte aligned
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float2 q = make_float2(0.f, 0.f);
+                        if (k0 + 2 * i < a.wide_k) q = __ldg(reinterpret_cast<const float2*>(p) + i);
+                        x[2 * i] = q.x; x[2 * i + 1] = k0 + 2 * i + 1 < a.wide_k ? q.y : 0.f;
+                    }
+                    v0 = make_float4(x[0], x[1], x[2], x[3]);
+                    v1 = make_float4(x[4], x[5], x[6], x[7]);
+                }
+            }
+        } else if (r >= 0 && r < a.T * a.P) {
             const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
             const int col = r - t * a.P;
             if (col < a.plane_cols[plane]) {
@@ -545,6 +564,13 @@ int staged_rows(const PlaneConvArgs& a, int* front) {
     const int f = ceil8(a.back);
     if (front) *front = f;
     return ceil8(f + a.tiles_per_b * TM + a.fwd + 8);
+}
+
+bool staged_conv_fits(const PlaneConvArgs& a_in) {
+    PlaneConvArgs a = a_in;
+    if (a.ntaps * a.nslab * a.npass > kMaxConvUnits) return false;
+    if (a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1) > 16) return false;
+    return choose_nbuf(a) > 0;
 }
 
 bool staged_conv_supported(const PlaneConvArgs& a_in) {

@@ -205,6 +205,7 @@ struct eab_model {
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
+    int opt_wide_staged = 1;      // first layer through stage_kernel (tap-window rows) + conv_tma instead of the gather kernel
     int opt_split = 0;            // gated 1-pass layers whose weights cannot stay resident run as two channel-split launches
     int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
@@ -946,6 +947,44 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
     const bool in_stats = L.na.has_norm && cx.m->cfg.norm_type == 0;
     double* stats = in_stats ? cx.alloc_stats(L.cout) : nullptr;
     out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
+    if (cx.tensor_ok() && L.umma_ok && L.wide && cx.m->opt_staged && cx.m->opt_wide_staged && nsrc == 1 && !L.deconv &&
+        srcs[0].xf.affine == 0 && srcs[0].xf.prelu == 0 && !srcs[0].data2 && (srcs[0].C * 2) % 2 == 0) {
+        // first layer (2M input channels) on the staged path: a plane row is the whole kf x C tap window
+        PlaneConvArgs p;
+        memset(&p, 0, sizeof(p));
+        p.nsrc = 1;
+        set_src(p.src[0], srcs[0]);
+        p.B = cx.B; p.T = cx.T; p.Fin = Fin; p.E = Fout; p.P = Fout;
+        p.nplanes = 1; p.plane_cols[0] = Fout; p.col_stride = 2; p.col_off[0] = 0;
+        p.ntaps = L.u_ntaps[0];
+        int back = 0;
+        for (int i = 0; i < p.ntaps; ++i) { p.tap_plane[i] = 0; p.tap_shift[i] = -L.u_dt[0][i] * p.P; back = std::max(back, -p.tap_shift[i]); }
+        p.back = back; p.fwd = 0;
+        p.out_stride = 1; p.out_off = 0; p.Fout = Fout;
+        p.nslab = L.u_nslab; p.ncoef = cin; p.npass = L.zone == 0 ? cx.m->opt_enc_passes : cx.m->opt_dec_passes;
+        p.Whi = cx.W(L.off_whi[0]); p.Wlo = cx.W(L.off_wlo[0]); p.bias = cx.W(L.off_ub);
+        p.Cout = L.cout; p.N = L.u_N; p.gate_off = L.u_gate_off; p.algo_frac = (float)L.u_kwidth / (float)(L.u_nslab * 64);
+        p.out = out->data; p.out_ld = L.cout; p.out_coff = 0;
+        if (stats) { p.nstats = 1; p.stats[0] = stats; }
+        p.tiles_per_b = (int)(((long long)cx.T * p.P + 127) / 128);
+        p.wide_k = L.u_kwidth;
+        const bool geom_ok = (srcs[0].C * p.col_stride) % 2 == 0 && (Fin * srcs[0].C) % 2 == 0 &&      // 8-byte aligned windows
+                             (Fout - 1) * 2 + L.kf <= Fin && p.P >= 1 &&
+                             ((long long)cx.T * p.P + p.back + 4 * 128 + 2ll * p.P) * p.P < (1ll << 31);
+        if (geom_ok && staged_conv_fits(p)) {
+            int front = 0;
+            const int rows = staged_rows(p, &front);
+            const int nimg = p.nslab * (p.npass == 3 ? 2 : 1);
+            p.np_rows = rows; p.np_front = front;
+            const size_t scratch = cx.mark();
+            for (int k = 0; k < nimg; ++k) p.np[k] = cx.alloc_act((size_t)cx.B * rows * 32);
+            cx.release(scratch);
+            if (cx.dry) return 0;
+            EAB_TRY(launch_stage(p, cx.st));
+            if (cx.m->umma_launch_idx++ == cx.m->opt_dbg_launch && cx.m->dbg_buf) p.dbg = cx.m->dbg_buf;
+            return launch_conv_staged(p, cx.st);
+        }
+    }
     if (cx.tensor_ok() && L.umma_ok) {
         UmmaConvArgs us[4];
         bool all_ok = true;
@@ -1759,6 +1798,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "conv_exp") m->opt_conv_exp = value;
     else if (n == "split") m->opt_split = value != 0;
+    else if (n == "wide_staged") m->opt_wide_staged = value != 0;
     else if (n == "stft_tc") g_stft_tc = value != 0;
     else if (n == "fused_head") m->opt_fused_head = value != 0;
     else if (n == "head_w_tap") m->opt_head_w_tap = value != 0;
