@@ -266,6 +266,9 @@ struct PlaneConvArgs {
     // "wide" staging (first layer, 2M input channels): a plane row (t, e) is the whole kf x C tap window, wide_k contiguous
     // floats starting at column e*col_stride of frame t, zero-padded to nslab*64; the time taps are then plain row shifts
     int wide_k;
+    // fused producers (conv_tma): no staged planes in HBM - warps 12-19 read the raw fp32 activations, apply norm + PReLU
+    // (+ the lazy residual addend), split to fp16 hi/lo and write the tile's planes straight into shared memory
+    int fused;
 };
 bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
 int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);

@@ -181,8 +181,8 @@ __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
     p.stg_off = p.b_off + (a.resident ? p.w_images : a.nsb) * p.b_stage_bytes;
     p.rowoff_off = p.stg_off;
     p.bias_off = p.rowoff_off;
-    p.utab_off = p.bias_off + a.N * 4;
-    p.bar_off = p.utab_off;
+    p.utab_off = p.bias_off + a.N * 4;                   // fused producers: transform coefficients [2 addends][3][ncoef]
+    p.bar_off = (p.utab_off + (a.fused ? 6 * a.ncoef * 4 : 0) + 15) & ~15;
     p.total = p.bar_off + 256 + 1024;
     return p;
 }
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
     const int nimg = a.nplanes * a.nslab * npb;
 
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], a.fused ? NEPI / 32 : 1); mbar_init(&plane_empty[i], 1); }
         for (int i = 0; i < NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
         fence_barrier_init();
@@ -233,7 +233,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
     const int rows_per_b = a.T * a.P;
     const int units_per_tile = a.ntaps * a.nslab * a.npass;
 
-    if (warp == 0) {
+    if (warp == 0 && a.fused) {
+        // planes are produced in place by warps 12-19
+    } else if (warp == 0) {
         // =========================================================================== plane copies (one lane)
         int buf = 0;
         uint32_t bphase = 0;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
             const int rs = a.np_front + row0 - a.back;
-            const int lead = rs & 7;                             // rows between the copy start and the tile's first plane row
+            const int lead = a.fused ? 0 : (rs & 7);             // rows between the copy start and the tile's first plane row
             const long long w0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_empty[acc], aphase ^ 1);
             const long long w1 = dbg_on ? clock64() : 0;
@@ -345,6 +347,126 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                 }
             }
         }
+    } else if (warp >= 12 && a.fused) {
+        // =========================================================================== fused producers (8 warps)
+        // thread = (row group of 32, 16-byte chunk = 8 channels); an item is one chunk of one plane row of one image
+        // (plane, slab).  Loads of NB items go out back to back before any of them is consumed: with only 8 warps the
+        // latency has to be covered by loads in flight per thread, not by occupancy (the stand-alone stage kernel
+        // hides it with 40 warps per SM).
+        const int ptid = tid - 12 * 32;
+        const int c8 = ptid & 7, rg = ptid >> 3;
+        float* coef = reinterpret_cast<float*>(smem + pl.utab_off);      // [addend][s | h | a][ncoef]
+        const int C0 = a.src[0].C;
+        const int nps = a.nplanes * a.nslab;
+        const int nrg = (pl.R + 31) >> 5;                                // row groups per image
+        const int nitems = nps * nrg;
+        int cur_b = -1;
+        int buf = 0;
+        uint32_t bphase = 0;
+        constexpr int NB = 4;
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            const int b = tile / a.tiles_per_b;
+            const int row0 = (tile - b * a.tiles_per_b) * TM;
+            if (b != cur_b) {
+                named_bar_sync(1, NEPI);
+                for (int i = ptid; i < a.ncoef; i += NEPI) {
+                    const int sidx = i < C0 ? 0 : 1;
+                    const int c = sidx ? i - C0 : i;
+                    float cs, ch, ca;
+                    xform_coeffs(a.src[sidx].xf, b, a.src[sidx].C, c, cs, ch, ca);
+                    coef[i] = cs; coef[a.ncoef + i] = ch; coef[2 * a.ncoef + i] = a.src[sidx].xf.prelu ? ca : 1.f;
+                    if (a.src[sidx].x2) {
+                        xform_coeffs(a.src[sidx].xf2, b, a.src[sidx].C, c, cs, ch, ca);
+                        coef[3 * a.ncoef + i] = cs; coef[4 * a.ncoef + i] = ch; coef[5 * a.ncoef + i] = a.src[sidx].xf2.prelu ? ca : 1.f;
+                    }
+                }
+                named_bar_sync(1, NEPI);
+                cur_b = b;
+            }
+            mbar_wait(&plane_empty[buf], bphase ^ 1);
+            uint8_t* pbuf = planes + buf * pl.buf_bytes;
+            for (int it0 = 0; it0 < nitems; it0 += NB) {
+                float4 v[NB][2], w[NB][2];
+                int ok[NB];                      // 0 zero row, 1 one addend, 2 two addends
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int it = it0 + j;
+                    ok[j] = 0;
+                    if (it < nitems) {
+                        const int ps = it / nrg, rr = (it - ps * nrg) * 32 + rg;
+                        const int plane = ps / a.nslab, slab = ps - plane * a.nslab;
+                        const int r = row0 - a.back + rr;
+                        if (rr < pl.R && r >= 0 && r < rows_per_b) {
+                            const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
+                            const int col = r - t * a.P;
+                            if (col < a.plane_cols[plane]) {
+                                const bool second = slab * KC >= C0;
+                                const ConvSrc& src = second ? a.src[1] : a.src[0];
+                                const int cbase = (second ? slab * KC - C0 : slab * KC) + c8 * 8;
+                                const size_t eoff = (((size_t)b * a.T + t) * a.Fin + (col * a.col_stride + a.col_off[plane])) * src.C + cbase;
+                                const float4* p = reinterpret_cast<const float4*>(src.x + eoff);
+                                v[j][0] = __ldg(p); v[j][1] = __ldg(p + 1);
+                                ok[j] = 1;
+                                if (src.x2) {
+                                    const float4* p2 = reinterpret_cast<const float4*>(src.x2 + eoff);
+                                    w[j][0] = __ldg(p2); w[j][1] = __ldg(p2 + 1);
+                                    ok[j] = 2;
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int it = it0 + j;
+                    if (it >= nitems) break;
+                    const int ps = it / nrg, rr = (it - ps * nrg) * 32 + rg;
+                    if (rr >= pl.R) continue;
+                    const int slab = ps % a.nslab;
+                    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (ok[j]) {
+                        const bool second = slab * KC >= C0;
+                        const ConvSrc& src = second ? a.src[1] : a.src[0];
+                        const float* cb = coef + slab * KC + c8 * 8;
+                        const float xin[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
+                        const int md = (src.xf.affine == 0 && src.xf.prelu == 0) ? 0 : (src.xf.prelu == 1 ? 2 : 1);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float z = xin[e];
+                            if (md == 1) { z = fmaf(z, cb[e], cb[a.ncoef + e]); z = fmaxf(z, 0.f) + cb[2 * a.ncoef + e] * fminf(z, 0.f); }
+                            else if (md == 2) { z = fmaf(fmaxf(z, 0.f) + cb[2 * a.ncoef + e] * fminf(z, 0.f), cb[e], cb[a.ncoef + e]); }
+                            x[e] = z;
+                        }
+                        if (ok[j] == 2) {
+                            const float win[8] = {w[j][0].x, w[j][0].y, w[j][0].z, w[j][0].w, w[j][1].x, w[j][1].y, w[j][1].z, w[j][1].w};
+                            const float* cb2 = cb + 3 * a.ncoef;
+                            const int md2 = (src.xf2.affine == 0 && src.xf2.prelu == 0) ? 0 : (src.xf2.prelu == 1 ? 2 : 1);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                float z = win[e];
+                                if (md2 == 1) { z = fmaf(z, cb2[e], cb2[a.ncoef + e]); z = fmaxf(z, 0.f) + cb2[2 * a.ncoef + e] * fminf(z, 0.f); }
+                                else if (md2 == 2) { z = fmaf(fmaxf(z, 0.f) + cb2[2 * a.ncoef + e] * fminf(z, 0.f), cb2[e], cb2[a.ncoef + e]); }
+                                x[e] += z;
+                            }
+                        }
+                    }
+                    uint4 hi;
+                    hi.x = pack_h2(x[0], x[1]); hi.y = pack_h2(x[2], x[3]); hi.z = pack_h2(x[4], x[5]); hi.w = pack_h2(x[6], x[7]);
+                    uint8_t* drow = pbuf + (size_t)(ps * npb) * pl.plane_bytes + rr * 128 + ((c8 ^ (rr & 7)) << 4);
+                    *reinterpret_cast<uint4*>(drow) = hi;
+                    if (npb == 2) {
+                        uint4 lo;
+                        lo.x = pack_lo_h2(x[0], x[1], hi.x); lo.y = pack_lo_h2(x[2], x[3], hi.y);
+                        lo.z = pack_lo_h2(x[4], x[5], hi.z); lo.w = pack_lo_h2(x[6], x[7], hi.w);
+                        *reinterpret_cast<uint4*>(drow + pl.plane_bytes) = lo;
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&plane_full[buf]);
+            if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
+        }
     } else if (warp >= 4) {
         // =========================================================================== epilogue (8 warps per group)
         // Register-only: thread = output row (TMEM lane), warp = (lane quadrant, half of the channels).  Values go
@@ -360,6 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         const int cper = a.Cout >> 1;           // channels per half (8 .. 64, multiple of 8)
         const int niter = cper >> 3;
         const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);     // column (of 8) this lane ends up owning
+        const int ngrp = a.fused ? 1 : NGRP;   // fused mode: warps 12-19 produce, one epilogue group drains both accumulators
         int acc = grp;
         uint32_t aphase = 0;
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
@@ -391,7 +514,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 #pragma unroll
                 for (int it = 0; it < 8; ++it) { ssum[s2][it] = 0.f; ssq[s2][it] = 0.f; }
         };
-        for (int tile = tile_begin + grp; tile < tile_end; tile += NGRP) {
+        for (int tile = tile_begin + grp; tile < tile_end; tile += ngrp) {
             const int b = tile / a.tiles_per_b;
             if (b != cur_b) { flush(cur_b); cur_b = b; }
             const int row0 = (tile - b * a.tiles_per_b) * TM;
@@ -524,7 +647,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
             if (dbg_on) { t_wfull += e1 - e0; t_tmem += clock64() - e1; }
-            if (NGRP == 2) aphase ^= 1;
+            if (ngrp == 2) aphase ^= 1;
             else if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         flush(cur_b);
@@ -630,10 +753,13 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
     double kreal = 0;
     for (int i = 0; i < a.nsrc; ++i) kreal += a.src[i].C;
     if (a.stft_M > 0) kreal = 160;                           // a hop per tap
+    double in_bytes = (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1);
+    if (a.fused) {
+        in_bytes = 0;
+        for (int i = 0; i < a.nsrc; ++i) in_bytes += 4.0 * a.B * a.T * a.Fin * a.src[i].C * (a.src[i].x2 ? 2 : 1);
+    }
     ProfScope ps(a.stft_M > 0 ? "stft" : "conv_tma", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
-                 (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1) + 4.0 * pos * a.Cout * (a.resid ? 2 : 1) +
-                     4.0 * a.ntaps * kreal * a.N,
-                 st);
+                 in_bytes + 4.0 * pos * a.Cout * (a.resid ? 2 : 1) + 4.0 * a.ntaps * kreal * a.N, st);
     EAB_CUDA(launch_k(conv_tma_kernel, dim3(grid), dim3(NTHREADS), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_tma_kernel");
     return 0;

@@ -108,7 +108,7 @@ struct ConvLayer {
     size_t off_w[2] = {0, 0}, off_b = 0;
     // tcgen05 path: swizzled TF32 weight images (hi / lo), per variant
     bool umma_ok = false, wide = false;
-    int zone = 0;                       // 0 encoder, 1 decoder (precision policy)
+    int zone = 0;                       // 0 encoder, 1 decoder, 2 encoder inner U-Nets (precision policy)
     int u_nslab = 0, u_kwidth = 0, u_N = 0, u_gate_off = 0;
     int u_ntaps[2] = {0, 0};
     int u_dt[2][kMaxTaps], u_df[2][kMaxTaps];
@@ -202,9 +202,11 @@ struct eab_model {
     int opt_umma = 1;             // tcgen05 path for eligible layers
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
+    int opt_inner_passes = 3;     // inner U-Nets of the encoder modules
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
+    int opt_fused = 0;            // conv_tma with in-kernel producers (no stage pass, no plane images in HBM)
     int opt_wide_staged = 1;      // first layer through stage_kernel (tap-window rows) + conv_tma instead of the gather kernel
     int opt_split = 0;            // gated 1-pass layers whose weights cannot stay resident run as two channel-split launches
     int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
@@ -334,6 +336,8 @@ int build(eab_model* m) {
         m->de_last = bd.gated("de.last_conv", 2 * c.c, c.embed_dim, 2, 5, true, true);
         for (auto& U : m->de_mod) { U.in_conv.zone = 1; for (auto& L : U.enco) L.zone = 1; for (auto& L : U.deco) L.zone = 1; }
         m->de_last.zone = 1;
+        // zone 2: the inner U-Nets of the encoder modules (their result is the residual branch of x0 + y)
+        for (auto& U : m->en_mod) { for (auto& L : U.enco) L.zone = 2; for (auto& L : U.deco) L.zone = 2; }
     } else {
         m->en_plain.push_back(bd.gated("en.unet_list.0", 2 * c.M, c.c, 2, 5, false, true));
         m->en_plain[0].perm_ri = true;
@@ -896,6 +900,16 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
             ok = staged_conv_supported(ps);
             for (int i = 0; i < n; ++i) ok = ok && staged_conv_supported(p[i]);
             if (ok) {
+                if (m->opt_fused) {
+                    // fused producers: no plane images in HBM, every launch normalises its own operand on load
+                    if (cx.dry) return 0;
+                    for (int i = 0; i < n; ++i) {
+                        if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) p[i].dbg = m->dbg_buf;
+                        p[i].fused = 1; p[i].exp_flags = m->opt_conv_exp;
+                        EAB_TRY(launch_conv_staged(p[i], cx.st));
+                    }
+                    return 0;
+                }
                 int front = 0;
                 const int rows = staged_rows(ps, &front);
                 const int nimg = ps.nplanes * ps.nslab * (ps.npass == 3 ? 2 : 1);
@@ -921,6 +935,10 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
     if (cx.dry) return 0;
     for (int i = 0; i < n; ++i) EAB_TRY(launch_tensor_conv(m, us[i], cx.st));
     return 0;
+}
+
+inline int zone_passes(const eab_model* m, int zone) {
+    return zone == 0 ? m->opt_enc_passes : zone == 1 ? m->opt_dec_passes : m->opt_inner_passes;
 }
 
 // one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
@@ -961,7 +979,7 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
         for (int i = 0; i < p.ntaps; ++i) { p.tap_plane[i] = 0; p.tap_shift[i] = -L.u_dt[0][i] * p.P; back = std::max(back, -p.tap_shift[i]); }
         p.back = back; p.fwd = 0;
         p.out_stride = 1; p.out_off = 0; p.Fout = Fout;
-        p.nslab = L.u_nslab; p.ncoef = cin; p.npass = L.zone == 0 ? cx.m->opt_enc_passes : cx.m->opt_dec_passes;
+        p.nslab = L.u_nslab; p.ncoef = cin; p.npass = zone_passes(cx.m, L.zone);
         p.Whi = cx.W(L.off_whi[0]); p.Wlo = cx.W(L.off_wlo[0]); p.bias = cx.W(L.off_ub);
         p.Cout = L.cout; p.N = L.u_N; p.gate_off = L.u_gate_off; p.algo_frac = (float)L.u_kwidth / (float)(L.u_nslab * 64);
         p.out = out->data; p.out_ld = L.cout; p.out_coff = 0;
@@ -990,7 +1008,7 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
         bool all_ok = true;
         int nus = 0;
         for (int v = 0; v < L.nvar; ++v) {
-            const int npass = L.zone == 0 ? cx.m->opt_enc_passes : cx.m->opt_dec_passes;
+            const int npass = zone_passes(cx.m, L.zone);
             // weights of the variant as one resident set: taps x slabs x (hi[, lo]) x N rows x 128 B
             const size_t wbytes = (size_t)L.u_ntaps[v] * L.u_nslab * (npass == 3 ? 2 : 1) * L.u_N * 128;
             const bool split = L.has_split && cx.m->opt_split && npass == 1 && wbytes > 112 * 1024;
@@ -1799,11 +1817,13 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "conv_exp") m->opt_conv_exp = value;
     else if (n == "split") m->opt_split = value != 0;
     else if (n == "wide_staged") m->opt_wide_staged = value != 0;
+    else if (n == "fused") m->opt_fused = value != 0;
     else if (n == "stft_tc") g_stft_tc = value != 0;
     else if (n == "fused_head") m->opt_fused_head = value != 0;
     else if (n == "head_w_tap") m->opt_head_w_tap = value != 0;
-    else if (n == "enc_passes" && (value == 1 || value == 3)) m->opt_enc_passes = value;
+    else if (n == "enc_passes" && (value == 1 || value == 3)) { m->opt_enc_passes = value; m->opt_inner_passes = value; }
     else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
+    else if (n == "inner_passes" && (value == 1 || value == 3)) m->opt_inner_passes = value;
     else if (n == "dbg_launch") {
         m->opt_dbg_launch = value;
         if (!m->dbg_buf) { if (check_cuda(cudaMalloc(&m->dbg_buf, 16 * sizeof(unsigned long long)), "dbg alloc")) return 1; }

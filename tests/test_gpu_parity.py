@@ -123,6 +123,24 @@ def test_forward_fp32_grade_modes(opts):
     assert (out - ref).abs().max() <= EXACT * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("opts", [{"fused": 1}, {"split": 1}, {"wide_staged": 0}, {"stft_tc": 0}, {"staged": 0}, {"lazy": 0}])
+def test_alternate_kernel_paths_agree(opts):
+    """the optional kernel paths (in-kernel producers, channel-split gated layers, gather first layer, CUDA-core STFT,
+    fused-producer plane kernel, materialised residual sums) give the default path's result: wave -> wave, T = 101"""
+    cfg = O.make_cfg()
+    net, sd = _net(cfg, seed=12)
+    wave, _ = O.make_wave(2, 9, 16000, seed=33)
+    ref = O.enhance(sd, wave, cfg)
+    try:
+        for k, v in opts.items():
+            net.set_option(k, v)
+        with torch.no_grad():
+            got = net.enhance(wave.cuda()).cpu()
+    finally:
+        net.set_option("stft_tc", 1)                 # process-wide switch
+    assert (got - ref).abs().max() <= 2e-4
+
+
 def test_enhance_wave_to_wave_and_si_sdr():
     """config 1 of BASELINE.json (B=1, 4 s, default model): wave -> wave through one C-ABI call, device and host
     buffer flavours; SI-SDR of the two enhanced signals against the clean source within 0.05 dB."""

@@ -12,9 +12,9 @@ for seed, variant, L in [(0, "B", 96000), (1, "A", 96000), (2, "B", 64000)]:
     ref = O.forward(sd, spec, cfg)
     net = EaBNet(**cfg).eval(); net.load_state_dict(sd); net.cuda()
     row = []
-    for enc, dec in [(3, 3), (3, 1), (1, 1)]:
-        net.set_option("enc_passes", enc); net.set_option("dec_passes", dec)
+    for enc, dec, inner in [(3, 3, 3), (3, 1, 3), (3, 1, 1), (1, 1, 1)]:
+        net.set_option("enc_passes", enc); net.set_option("dec_passes", dec); net.set_option("inner_passes", inner)
         with torch.no_grad():
             out = net(spec.cuda()).cpu()
-        row.append("enc%d/dec%d: %.2e" % (enc, dec, float((out - ref).abs().max())))
+        row.append("enc%d/dec%d/inner%d: %.2e" % (enc, dec, inner, float((out - ref).abs().max())))
     print("seed %d variant %s T=%d |out|max %.2f  " % (seed, variant, spec.shape[1], float(ref.abs().max())), "  ".join(row), flush=True)
