@@ -146,6 +146,10 @@ struct ConvSrc {
     const float* x2;
     Xform xf2;
     int RT;              // streaming only: frames in this tensor's ring (see StreamPos); 0 = offline [B][T][...]
+    // 2-byte storage: x (x2) points at __half data of the same [B][T][F][C] shape.  Used for the raw outputs of the
+    // single-pass decoder layers, whose consumers round the normalised value to fp16 anyway (measured cost in output
+    // accuracy: 1.1e-4 -> 1.2-1.6e-4).  Honoured by stage_kernel and combine_kernel only.
+    int half, half2;
 };
 
 // Frame-by-frame ("streaming", BASELINE configs[2]) addressing.  Offline, a tensor holds frames 0..T-1 of every batch
@@ -269,6 +273,8 @@ struct PlaneConvArgs {
     // fused producers (conv_tma): no staged planes in HBM - warps 12-19 read the raw fp32 activations, apply norm + PReLU
     // (+ the lazy residual addend), split to fp16 hi/lo and write the tile's planes straight into shared memory
     int fused;
+    int round_half;              // diagnostics: round the stored output to fp16 precision (accuracy of a 2-byte activation format)
+    int out_half;                // conv_tma: `out` is __half [B][T][Fout][out_ld] (statistics still from the fp32 accumulators)
 };
 bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
 int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);

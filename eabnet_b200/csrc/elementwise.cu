@@ -1,5 +1,7 @@
 // Bandwidth-bound elementwise kernels: residual/skip sums of normalised tensors and the complex
 // filter-and-sum over microphones (EaBNet.py:114-117, :386, :104).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace eab {
@@ -34,8 +36,15 @@ __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
             const int c = (int)((i * 4) % C);
             float o[4] = {0.f, 0.f, 0.f, 0.f};
             for (int s = 0; s < a.nsrc; ++s) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(a.src[s].x + sbase[s]) + i);
-                const float x[4] = {v.x, v.y, v.z, v.w};
+                float x[4];
+                if (a.src[s].half) {
+                    const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(a.src[s].x) + sbase[s]) + i);
+                    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+                    x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
+                } else {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(a.src[s].x + sbase[s]) + i);
+                    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+                }
                 const int pr = a.src[s].xf.prelu;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -49,7 +58,8 @@ __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
             const int c = (int)(i % C);
             float o = 0.f;
             for (int s = 0; s < a.nsrc; ++s)
-                o += xform_apply(__ldg(a.src[s].x + sbase[s] + i), coef[(s * 3 + 0) * C + c], coef[(s * 3 + 1) * C + c],
+                o += xform_apply(a.src[s].half ? __half2float(__ldg(reinterpret_cast<const __half*>(a.src[s].x) + sbase[s] + i))
+                                               : __ldg(a.src[s].x + sbase[s] + i), coef[(s * 3 + 0) * C + c], coef[(s * 3 + 1) * C + c],
                                  coef[(s * 3 + 2) * C + c], a.src[s].xf.prelu);
             a.out[base + i] = o;
         }

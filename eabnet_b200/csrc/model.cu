@@ -153,10 +153,12 @@ struct Act {                 // an activation tensor as seen by a consumer
     float* data2 = nullptr;
     Xform xf2 = xform_identity();
     int RT = 0;              // streaming: frames in this tensor's ring (0 = offline)
+    bool half = false, half2 = false;       // data / data2 hold __half values (raw outputs of single-pass decoder layers)
 };
 
 inline void set_src(ConvSrc& s, const Act& a) {
     s.x = a.data; s.C = a.C; s.xf = a.xf; s.x2 = a.data2; s.xf2 = a.xf2; s.RT = a.RT;
+    s.half = a.half; s.half2 = a.half2;
 }
 
 struct Tap { Act act; int B = 0, T = 0; };
@@ -206,6 +208,8 @@ struct eab_model {
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
+    int opt_half_act = 0;         // raw outputs of the single-pass decoder layers stored as fp16: measured -1 % step time for +30 % output error, so off
+    int opt_round_half = 0;       // diagnostics: fp16-rounded storage of the decoder's inner activations
     int opt_fused = 0;            // conv_tma with in-kernel producers (no stage pass, no plane images in HBM)
     int opt_wide_staged = 1;      // first layer through stage_kernel (tap-window rows) + conv_tma instead of the gather kernel
     int opt_split = 0;            // gated 1-pass layers whose weights cannot stay resident run as two channel-split launches
@@ -879,28 +883,40 @@ int launch_tensor_conv(eab_model* m, const UmmaConvArgs& u, cudaStream_t st) {
 // Launch the 1-4 tensor-core variants of one layer (output parities of a transposed conv, column splits of a wide
 // 1x1) that read the same inputs.  Preferred path: stage the normalised fp16 planes ONCE (stage_kernel) and run the
 // TMA-fed GEMM per variant; otherwise the fused-producer kernels.  Also runs in planning mode (allocations only).
-int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
+// Can the 1-4 variants of a layer run as one stage launch + conv_tma launches?  Fills their plane arguments.
+bool plan_staged(const eab_model* m, const UmmaConvArgs* us, int n, PlaneConvArgs* p, PlaneConvArgs* ps_out) {
+    if (!m->opt_staged || us[0].wide || n > 4) return false;
+    bool ok = true;
+    int P = 0;
+    for (int i = 0; i < n; ++i) { ok = ok && to_plane_args(us[i], &p[i]); if (ok) P = std::max(P, p[i].P); }
+    if (ok)
+        for (int i = 0; i < n; ++i)
+            if (p[i].P != P) ok = ok && to_plane_args(us[i], &p[i], P);
+    if (ok)
+        for (int i = 1; i < n; ++i)
+            ok = ok && p[i].nplanes == p[0].nplanes && p[i].plane_cols[0] == p[0].plane_cols[0] &&
+                 p[i].plane_cols[1] == p[0].plane_cols[1] && p[i].nslab == p[0].nslab && p[i].npass == p[0].npass &&
+                 p[i].tiles_per_b == p[0].tiles_per_b;
+    if (!ok) return false;
+    PlaneConvArgs ps = p[0];
+    for (int i = 1; i < n; ++i) { ps.back = std::max(ps.back, p[i].back); ps.fwd = std::max(ps.fwd, p[i].fwd); }
+    ok = staged_conv_supported(ps);
+    for (int i = 0; i < n; ++i) ok = ok && staged_conv_supported(p[i]);
+    *ps_out = ps;
+    return ok;
+}
+
+int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n, bool out_half = false) {
     eab_model* m = cx.m;
-    if (m->opt_staged && !us[0].wide && n <= 4) {
+    {
         PlaneConvArgs p[4];
-        bool ok = true;
-        int P = 0;
-        for (int i = 0; i < n; ++i) { ok = ok && to_plane_args(us[i], &p[i]); if (ok) P = std::max(P, p[i].P); }
-        if (ok)
-            for (int i = 0; i < n; ++i)
-                if (p[i].P != P) ok = ok && to_plane_args(us[i], &p[i], P);
-        if (ok)
-            for (int i = 1; i < n; ++i)
-                ok = ok && p[i].nplanes == p[0].nplanes && p[i].plane_cols[0] == p[0].plane_cols[0] &&
-                     p[i].plane_cols[1] == p[0].plane_cols[1] && p[i].nslab == p[0].nslab && p[i].npass == p[0].npass &&
-                     p[i].tiles_per_b == p[0].tiles_per_b;
-        if (ok) {
-            PlaneConvArgs ps = p[0];
-            for (int i = 1; i < n; ++i) { ps.back = std::max(ps.back, p[i].back); ps.fwd = std::max(ps.fwd, p[i].fwd); }
-            ok = staged_conv_supported(ps);
-            for (int i = 0; i < n; ++i) ok = ok && staged_conv_supported(p[i]);
-            if (ok) {
-                if (m->opt_fused) {
+        PlaneConvArgs ps;
+        {
+            if (plan_staged(m, us, n, p, &ps)) {
+                bool any_half = out_half;
+                for (int i = 0; i < n; ++i)
+                    for (int k = 0; k < us[i].nsrc; ++k) any_half = any_half || us[i].src[k].half || us[i].src[k].half2;
+                if (m->opt_fused && !any_half) {
                     // fused producers: no plane images in HBM, every launch normalises its own operand on load
                     if (cx.dry) return 0;
                     for (int i = 0; i < n; ++i) {
@@ -922,6 +938,8 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
                 for (int i = 0; i < n; ++i) {
                     if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) p[i].dbg = m->dbg_buf;
                     p[i].np_rows = rows; p[i].np_front = front; p[i].exp_flags = m->opt_conv_exp;
+                    p[i].round_half = m->opt_round_half && us[i].npass == 1 && us[i].Fout != m->cfg.n_freq;
+                    p[i].out_half = out_half ? 1 : 0;
                     for (int k = 0; k < nimg; ++k) p[i].np[k] = ps.np[k];
                     EAB_TRY(launch_conv_staged(p[i], cx.st));
                 }
@@ -929,9 +947,10 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
             }
         }
     }
+    if (out_half) return fail("internal: fp16 output requested from a kernel that cannot write it");
     for (int i = 0; i < n; ++i)
         for (int k = 0; k < us[i].nsrc; ++k)
-            if (us[i].src[k].x2) return fail("internal: lazy residual sum reached a kernel that cannot read it");
+            if (us[i].src[k].x2 || us[i].src[k].half) return fail("internal: lazy residual sum / fp16 activation reached a kernel that cannot read it");
     if (cx.dry) return 0;
     for (int i = 0; i < n; ++i) EAB_TRY(launch_tensor_conv(m, us[i], cx.st));
     return 0;
@@ -943,11 +962,12 @@ inline int zone_passes(const eab_model* m, int zone) {
 
 // one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
 int materialize(Ctx& cx, Act* a);
-int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* out, float* prealloc = nullptr) {
+int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* out, float* prealloc = nullptr,
+               bool allow_half = false) {
     Act srcs[2];
     for (int i = 0; i < nsrc; ++i) srcs[i] = srcs_in[i];
-    if (!(cx.tensor_ok() && L.umma_ok && cx.m->opt_staged))
-        for (int i = 0; i < nsrc; ++i) EAB_TRY(materialize(cx, &srcs[i]));       // only the staged path reads lazy sums
+    if (!(cx.tensor_ok() && L.umma_ok && cx.m->opt_staged && !L.wide))
+        for (int i = 0; i < nsrc; ++i) EAB_TRY(materialize(cx, &srcs[i]));       // only the staged path reads lazy sums / fp16
     const int Fin = srcs[0].F;
     int cin = 0;
     for (int i = 0; i < nsrc; ++i) {
@@ -960,14 +980,25 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
     out->F = Fout;
     out->C = L.cout;
     out->data2 = nullptr;
-    out->data = prealloc ? prealloc : cx.alloc_act((size_t)cx.B * cx.T * Fout * L.cout);
-    out->RT = prealloc ? 0 : cx.last_RT;
+    out->half = out->half2 = false;
+    const size_t out_elems = (size_t)cx.B * cx.T * Fout * L.cout;
     const bool in_stats = L.na.has_norm && cx.m->cfg.norm_type == 0;
     double* stats = in_stats ? cx.alloc_stats(L.cout) : nullptr;
     out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
+    // 2-byte storage of the raw output: single-pass decoder layers on the staged path only (every consumer of such a
+    // tensor is a stage kernel, which rounds the normalised value to fp16 anyway)
+    bool want_half = allow_half && cx.m->opt_half_act && cx.tensor_ok() && cx.m->opt_staged && L.umma_ok && !L.wide &&
+                     L.zone == 1 && zone_passes(cx.m, L.zone) == 1;
+    auto allocate_out = [&]() {
+        out->data = prealloc ? prealloc : cx.alloc_act(want_half ? (out_elems + 1) / 2 : out_elems);
+        out->RT = prealloc ? 0 : cx.last_RT;
+        out->half = want_half;
+    };
     if (cx.tensor_ok() && L.umma_ok && L.wide && cx.m->opt_staged && cx.m->opt_wide_staged && nsrc == 1 && !L.deconv &&
         srcs[0].xf.affine == 0 && srcs[0].xf.prelu == 0 && !srcs[0].data2 && (srcs[0].C * 2) % 2 == 0) {
         // first layer (2M input channels) on the staged path: a plane row is the whole kf x C tap window
+        want_half = false;
+        allocate_out();
         PlaneConvArgs p;
         memset(&p, 0, sizeof(p));
         p.nsrc = 1;
@@ -1039,8 +1070,19 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
                 all_ok = all_ok && umma_conv_supported(u);
             }
         }
-        if (all_ok) return run_tensor_convs(cx, us, nus);
+        if (all_ok) {
+            if (want_half) {                                 // only if the staged path is really going to take this layer
+                PlaneConvArgs pp[4], pps;
+                want_half = plan_staged(cx.m, us, nus, pp, &pps);
+            }
+            allocate_out();
+            for (int i = 0; i < nus; ++i) us[i].out = out->data;
+            return run_tensor_convs(cx, us, nus, want_half);
+        }
     }
+    want_half = false;
+    allocate_out();
+    for (int i = 0; i < nsrc; ++i) EAB_TRY(materialize(cx, &srcs[i]));
     if (cx.dry) return 0;
     for (int v = 0; v < L.nvar; ++v) {
         ConvArgs a;
@@ -1084,8 +1126,8 @@ int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
     for (int i = 0; i < nsrc; ++i) {
         if (srcs[i].F != out->F || srcs[i].C != out->C) return fail("internal: combine shape mismatch");
         if (n + (srcs[i].data2 ? 2 : 1) > 3) return fail("internal: too many addends in combine");
-        a.src[n].x = srcs[i].data; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf; a.src[n].RT = srcs[i].RT; ++n;
-        if (srcs[i].data2) { a.src[n].x = srcs[i].data2; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf2; a.src[n].RT = srcs[i].RT; ++n; }
+        a.src[n].x = srcs[i].data; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf; a.src[n].RT = srcs[i].RT; a.src[n].half = srcs[i].half; ++n;
+        if (srcs[i].data2) { a.src[n].x = srcs[i].data2; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf2; a.src[n].RT = srcs[i].RT; a.src[n].half = srcs[i].half2; ++n; }
     }
     a.nsrc = n;
     a.B = cx.B; a.P = cx.T * out->F; a.C = out->C; a.out = out->data;
@@ -1095,7 +1137,7 @@ int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
 
 // materialise a lazy residual sum (only needed in front of kernels that cannot read one)
 int materialize(Ctx& cx, Act* a) {
-    if (!a->data2) return 0;
+    if (!a->data2 && !a->half) return 0;
     Act src = *a;
     Act dst;
     EAB_TRY(run_combine(cx, &src, 1, &dst));
@@ -1124,12 +1166,12 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
     else { out->data = cx.alloc_act(nel); out->RT = cx.last_RT; }
     const size_t scope = cx.mark();
     Act x0;
-    EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0, buf_x0));
+    EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0, buf_x0, true));
     Act y = x0;
     std::vector<Act> keep;
     for (size_t i = 0; i < U.enco.size(); ++i) {
         Act z;
-        EAB_TRY(run_conv2d(cx, U.enco[i], &y, 1, &z));
+        EAB_TRY(run_conv2d(cx, U.enco[i], &y, 1, &z, nullptr, true));
         keep.push_back(z);
         y = z;
     }
@@ -1137,22 +1179,22 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
         Act z;
         float* pre = (lazy && i + 1 == U.deco.size()) ? buf_y : nullptr;
         if (i == 0) {
-            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z, pre));
+            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z, pre, true));
         } else {
             Act pair[2] = {y, keep[keep.size() - 1 - i]};
             if (cx.m->cfg.intra_connect == 0) {
-                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z, pre));
+                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z, pre, true));
             } else {
                 Act sum;
                 EAB_TRY(run_combine(cx, pair, 2, &sum));
-                EAB_TRY(run_conv2d(cx, U.deco[i], &sum, 1, &z, pre));
+                EAB_TRY(run_conv2d(cx, U.deco[i], &sum, 1, &z, pre, true));
             }
         }
         y = z;
     }
     if (lazy) {
-        out->data = x0.data; out->xf = x0.xf;
-        out->data2 = y.data; out->xf2 = y.xf;
+        out->data = x0.data; out->xf = x0.xf; out->half = x0.half;
+        out->data2 = y.data; out->xf2 = y.xf; out->half2 = y.half;
     } else {
         Act pair[2] = {x0, y};
         EAB_TRY(run_combine_into(cx, pair, 2, out));
@@ -1201,6 +1243,8 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
         return run_tensor_convs(cx, us, uw->nsplit);
     }
     if (cx.dry) return 0;
+    for (int i = 0; i < nsrc; ++i)
+        if (srcs[i].half || srcs[i].data2) return fail("internal: fp16 / lazy activation reached the CUDA-core pointwise kernel");
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.nsrc = nsrc;
@@ -1797,8 +1841,8 @@ int64_t eab_debug_tap(eab_model* m, const char* name, float* dst, int64_t capaci
     CombineArgs a;
     memset(&a, 0, sizeof(a));
     a.nsrc = 1;
-    a.src[0].x = t.act.data; a.src[0].C = t.act.C; a.src[0].xf = t.act.xf;
-    if (t.act.data2) { a.nsrc = 2; a.src[1].x = t.act.data2; a.src[1].C = t.act.C; a.src[1].xf = t.act.xf2; }
+    a.src[0].x = t.act.data; a.src[0].C = t.act.C; a.src[0].xf = t.act.xf; a.src[0].half = t.act.half;
+    if (t.act.data2) { a.nsrc = 2; a.src[1].x = t.act.data2; a.src[1].C = t.act.C; a.src[1].xf = t.act.xf2; a.src[1].half = t.act.half2; }
     a.B = t.B; a.P = t.T * t.act.F; a.C = t.act.C; a.out = dst;
     if (launch_combine(a, static_cast<cudaStream_t>(stream))) return -1;
     return n;
@@ -1818,6 +1862,8 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "split") m->opt_split = value != 0;
     else if (n == "wide_staged") m->opt_wide_staged = value != 0;
     else if (n == "fused") m->opt_fused = value != 0;
+    else if (n == "round_half") m->opt_round_half = value != 0;
+    else if (n == "half_act") m->opt_half_act = value != 0;
     else if (n == "stft_tc") g_stft_tc = value != 0;
     else if (n == "fused_head") m->opt_fused_head = value != 0;
     else if (n == "head_w_tap") m->opt_head_w_tap = value != 0;
