@@ -42,6 +42,21 @@ inline int ceil8(int x) { return (x + 7) & ~7; }
 constexpr bool kTwoIssuers = false;
 constexpr int STAGE_RB = 8;                     // 32-row blocks per stage CTA
 
+// 8 consecutive channels starting at element offset `eoff` of an fp32 or fp16 activation tensor
+__device__ __forceinline__ void load8(const float* base, int is_half, size_t eoff, float4& v0, float4& v1) {
+    if (is_half) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(base) + eoff));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+        v0 = make_float4(a.x, a.y, b.x, b.y);
+        v1 = make_float4(c.x, c.y, d.x, d.y);
+    } else {
+        const float4* p = reinterpret_cast<const float4*>(base + eoff);
+        v0 = __ldg(p);
+        v1 = __ldg(p + 1);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ stage kernel
 // grid (row blocks, nplanes*nslab, B), 256 threads: 8 threads per plane row (8 channels = one 16-byte fp16 chunk each)
 __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
@@ -110,14 +125,9 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
             if (col < a.plane_cols[plane]) {
                 const int fi = col * a.col_stride + a.col_off[plane];
                 const size_t eoff = (((size_t)b * a.T + t) * a.Fin + fi) * src.C + cbase + c8 * 8;
-                const float4* p = reinterpret_cast<const float4*>(src.x + eoff);
-                v0 = __ldg(p);
-                v1 = __ldg(p + 1);
+                load8(src.x, src.half, eoff, v0, v1);
                 float4 w0, w1;
-                if (src.x2) {
-                    const float4* p2 = reinterpret_cast<const float4*>(src.x2 + eoff);
-                    w0 = __ldg(p2); w1 = __ldg(p2 + 1);
-                }
+                if (src.x2) load8(src.x2, src.half2, eoff, w0, w1);
                 if (mode != 0) {
                     float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
@@ -589,10 +599,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                             }
                         }
                     }
+                } else if (row_valid && !CEXP(1) && a.out_half) {
+                    uint4 h;
+                    h.x = pack_h2(v[0], v[1]); h.y = pack_h2(v[2], v[3]); h.z = pack_h2(v[4], v[5]); h.w = pack_h2(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.out) + off + c0) = h;
                 } else if (row_valid && !CEXP(1)) {
                     float4* o4 = reinterpret_cast<float4*>(a.out + off + c0);
-                    o4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    if (a.round_half) {              // experiment: what fp16 storage of this raw activation would cost in accuracy
+                        float r[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) r[i] = __half2float(__float2half_rn(v[i]));
+                        o4[0] = make_float4(r[0], r[1], r[2], r[3]);
+                        o4[1] = make_float4(r[4], r[5], r[6], r[7]);
+                    } else {
+                        o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
                 }
                 if (a.nstats && !CEXP(2)) {
                     if (!row_valid) {
@@ -708,10 +730,13 @@ int launch_stage(const PlaneConvArgs& a_in, cudaStream_t st) {
     PlaneConvArgs a = a_in;
     a.p_magic = a.P == 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)a.P) + 1u;
     dim3 grid((a.np_rows + 32 * STAGE_RB - 1) / (32 * STAGE_RB), a.nplanes * a.nslab, a.B);
-    double cin = 0;
-    for (int i = 0; i < a.nsrc; ++i) cin += a.src[i].C;
+    double cin = 0, inb = 0;
+    for (int i = 0; i < a.nsrc; ++i) {
+        cin += a.src[i].C;
+        inb += (double)a.B * a.T * a.Fin * a.src[i].C * ((a.src[i].half ? 2.0 : 4.0) + (a.src[i].x2 ? (a.src[i].half2 ? 2.0 : 4.0) : 0.0));
+    }
     const double elems = (double)a.B * a.T * a.Fin * cin;
-    ProfScope ps("stage", 4.0 * elems, elems * 4.0 + (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1), st);
+    ProfScope ps("stage", 4.0 * elems, inb + (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1), st);
     EAB_CUDA(launch_k(stage_kernel, grid, dim3(256), (size_t)0, st, a));
     EAB_LAUNCH_CHECK("stage_kernel");
     return 0;
@@ -758,8 +783,9 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
         in_bytes = 0;
         for (int i = 0; i < a.nsrc; ++i) in_bytes += 4.0 * a.B * a.T * a.Fin * a.src[i].C * (a.src[i].x2 ? 2 : 1);
     }
+    if (a.out_half && (a.resid || a.stft_M > 0)) return fail("conv_staged: fp16 output with a residual / STFT epilogue");
     ProfScope ps(a.stft_M > 0 ? "stft" : "conv_tma", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
-                 in_bytes + 4.0 * pos * a.Cout * (a.resid ? 2 : 1) + 4.0 * a.ntaps * kreal * a.N, st);
+                 in_bytes + (a.out_half ? 2.0 : 4.0) * pos * a.Cout * (a.resid ? 2 : 1) + 4.0 * a.ntaps * kreal * a.N, st);
     EAB_CUDA(launch_k(conv_tma_kernel, dim3(grid), dim3(NTHREADS), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_tma_kernel");
     return 0;
