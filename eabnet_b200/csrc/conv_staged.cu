@@ -30,8 +30,11 @@ constexpr int TM = 128;
 constexpr int KC = 64;
 constexpr int NSB_MAX = 8;                      // weight ring stages: a.nsb in [2, 8], as many as fit next to two plane buffers
 constexpr int NEPI = 256;                       // 8 epilogue warps per group
-constexpr int NGRP = 2;                         // epilogue groups: group g drains TMEM accumulator g (alternate tiles)
-constexpr int NTHREADS = 128 + NGRP * NEPI;     // warp 0 plane copies, 1 MMA, 2 weight loader, 3 idle, 4-11 / 12-19 epilogue
+// warp 0 plane copies, 1 MMA issuer, 2 weight loader, 3 idle, 4-11 epilogue; 12-19 exist in the FUSED instantiation only
+// (in-kernel producers).  One epilogue group: its statistics cost almost nothing now (per-thread running sums), and at
+// 384 threads it can afford the 64 accumulator registers.
+constexpr int NTHREADS_STAGED = 128 + NEPI;
+constexpr int NTHREADS_FUSED = 128 + 2 * NEPI;
 
 inline int ceil8(int x) { return (x + 7) & ~7; }
 #ifdef EAB_CONV_EXPERIMENT
@@ -197,7 +200,25 @@ __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
     return p;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvArgs a) {
+// fold 8 per-row values across the 32 rows (lanes) of a warp with a halving butterfly (9 shuffles): every lane gets the
+// total of column ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
+__device__ __forceinline__ float fold8(const float (&u)[8], int lane) {
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    float u4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u4[j] = (h16 ? u[j + 4] : u[j]) + __shfl_xor_sync(0xffffffffu, h16 ? u[j] : u[j + 4], 16);
+    float u2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) u2[j] = (h8 ? u4[j + 2] : u4[j]) + __shfl_xor_sync(0xffffffffu, h8 ? u4[j] : u4[j + 2], 8);
+    float u1 = (h4 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? u2[0] : u2[1], 4);
+    u1 += __shfl_xor_sync(0xffffffffu, u1, 2);
+    u1 += __shfl_xor_sync(0xffffffffu, u1, 1);
+    return u1;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) conv_tma_kernel(const PlaneConvArgs a) {
+    constexpr int NTHREADS = FUSED ? NTHREADS_FUSED : NTHREADS_STAGED;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const Plan pl = make_plan(a);
@@ -223,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
     const int nimg = a.nplanes * a.nslab * npb;
 
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], a.fused ? NEPI / 32 : 1); mbar_init(&plane_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], FUSED ? NEPI / 32 : 1); mbar_init(&plane_empty[i], 1); }
         for (int i = 0; i < NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
         fence_barrier_init();
@@ -243,7 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
     const int rows_per_b = a.T * a.P;
     const int units_per_tile = a.ntaps * a.nslab * a.npass;
 
-    if (warp == 0 && a.fused) {
+    if (warp == 0 && FUSED) {
         // planes are produced in place by warps 12-19
     } else if (warp == 0) {
         // =========================================================================== plane copies (one lane)
@@ -296,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
             const int rs = a.np_front + row0 - a.back;
-            const int lead = a.fused ? 0 : (rs & 7);             // rows between the copy start and the tile's first plane row
+            const int lead = FUSED ? 0 : (rs & 7);               // rows between the copy start and the tile's first plane row
             const long long w0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_empty[acc], aphase ^ 1);
             const long long w1 = dbg_on ? clock64() : 0;
@@ -357,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
                 }
             }
         }
-    } else if (warp >= 12 && a.fused) {
+    } else if (warp >= 12) {
         // =========================================================================== fused producers (8 warps)
         // thread = (row group of 32, 16-byte chunk = 8 channels); an item is one chunk of one plane row of one image
         // (plane, slab).  Loads of NB items go out back to back before any of them is consumed: with only 8 warps the
@@ -484,7 +505,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         // the warp with a halving butterfly (9 shuffles per 8 columns per statistic) into one owner lane per column,
         // accumulated in registers over the CTA's tiles and flushed with fp64 atomics only when the batch item changes.
         // No staging tile, no block barrier: shared memory is left to the operand traffic of the tensor core.
-        const int grp = (warp - 4) >> 3;        // epilogue group = TMEM accumulator it drains (NGRP == 2)
+        constexpr int grp = 0;
         const int quad = warp & 3;              // TMEM lane quadrant (warp % 4)
         const int chalf = ((warp - 4) >> 2) & 1;        // which half of the output channels this warp converts
         const int row = quad * 32 + lane;
@@ -492,12 +513,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         const int cper = a.Cout >> 1;           // channels per half (8 .. 64, multiple of 8)
         const int niter = cper >> 3;
         const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);     // column (of 8) this lane ends up owning
-        const int ngrp = a.fused ? 1 : NGRP;   // fused mode: warps 12-19 produce, one epilogue group drains both accumulators
+        constexpr int ngrp = 1;
         int acc = grp;
         uint32_t aphase = 0;
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
         long long t_wfull = 0, t_tmem = 0;
         const long long t_start = dbg_on ? clock64() : 0;
+        // Statistics, fast path (one statistic, <= 32 channels per thread): every thread keeps running sums of ITS row's
+        // values per channel over all the tiles of a batch item; the cross-row butterfly runs once per batch item.
+        const bool fast_stats = !FUSED && a.nstats == 1 && niter <= 4;
+        float rs_sum[FUSED ? 1 : 32], rs_sq[FUSED ? 1 : 32];
+        if (!FUSED) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { rs_sum[FUSED ? 0 : i] = 0.f; rs_sq[FUSED ? 0 : i] = 0.f; }
+        }
         float ssum[2][8], ssq[2][8];            // [statistic][iteration]: totals of column chalf*cper + it*8 + own
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2)
@@ -506,6 +535,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
         int cur_b = -1;
         auto flush = [&](int b) {
             if (b < 0 || a.nstats == 0) return;
+            if (!FUSED && fast_stats) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    if (it >= niter) continue;
+                    float u8[8], w8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { u8[i] = rs_sum[FUSED ? 0 : it * 8 + i]; w8[i] = rs_sq[FUSED ? 0 : it * 8 + i]; rs_sum[FUSED ? 0 : it * 8 + i] = 0.f; rs_sq[FUSED ? 0 : it * 8 + i] = 0.f; }
+                    ssum[0][it] = fold8(u8, lane);
+                    ssq[0][it] = fold8(w8, lane);
+                }
+            }
             if ((lane & 3) == 0) {
 #pragma unroll
                 for (int s2 = 0; s2 < 2; ++s2) {
@@ -621,48 +661,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tma_kernel(const PlaneConvAr
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = 0.f;
                     }
+                    if (!FUSED && fast_stats) {
+                        if (it < 4) {
+                            float u[8];
+                            if (a.stat_alpha[0]) {
+                                const float4 a0 = __ldg(reinterpret_cast<const float4*>(a.stat_alpha[0] + c0));
+                                const float4 a1 = __ldg(reinterpret_cast<const float4*>(a.stat_alpha[0] + c0 + 4));
+                                const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2) {
-                        if (s2 >= a.nstats) continue;
-                        float u[8], w[8];
-                        if (a.stat_alpha[s2]) {
-                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(a.stat_alpha[s2] + c0));
-                            const float4 a1 = __ldg(reinterpret_cast<const float4*>(a.stat_alpha[s2] + c0 + 4));
-                            const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                                for (int i = 0; i < 8; ++i) u[i] = fmaxf(v[i], 0.f) + al[i] * fminf(v[i], 0.f);
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) u[i] = fmaxf(v[i], 0.f) + al[i] * fminf(v[i], 0.f);
-                        } else {
+                                for (int i = 0; i < 8; ++i) u[i] = v[i];
+                            }
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) u[i] = v[i];
+                            for (int i = 0; i < 8; ++i) {
+                                rs_sum[FUSED ? 0 : (it & 3) * 8 + i] += u[i];
+                                rs_sq[FUSED ? 0 : (it & 3) * 8 + i] = fmaf(u[i], u[i], rs_sq[FUSED ? 0 : (it & 3) * 8 + i]);
+                            }
                         }
+                    } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) w[i] = u[i] * u[i];
-                        // halving butterfly over the 32 rows: 8 -> 4 -> 2 -> 1 columns per lane, then the last two bits
-                        const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
-                        float u4[4], w4[4];
+                        for (int s2 = 0; s2 < 2; ++s2) {
+                            if (s2 >= a.nstats) continue;
+                            float u[8], w[8];
+                            if (a.stat_alpha[s2]) {
+                                const float4 a0 = __ldg(reinterpret_cast<const float4*>(a.stat_alpha[s2] + c0));
+                                const float4 a1 = __ldg(reinterpret_cast<const float4*>(a.stat_alpha[s2] + c0 + 4));
+                                const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float su = h16 ? u[j] : u[j + 4], ku = h16 ? u[j + 4] : u[j];
-                            const float sw = h16 ? w[j] : w[j + 4], kw = h16 ? w[j + 4] : w[j];
-                            u4[j] = ku + __shfl_xor_sync(0xffffffffu, su, 16);
-                            w4[j] = kw + __shfl_xor_sync(0xffffffffu, sw, 16);
+                                for (int i = 0; i < 8; ++i) u[i] = fmaxf(v[i], 0.f) + al[i] * fminf(v[i], 0.f);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) u[i] = v[i];
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w[i] = u[i] * u[i];
+                            ssum[s2][it] += fold8(u, lane);
+                            ssq[s2][it] += fold8(w, lane);
                         }
-                        float u2[2], w2[2];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const float su = h8 ? u4[j] : u4[j + 2], ku = h8 ? u4[j + 2] : u4[j];
-                            const float sw = h8 ? w4[j] : w4[j + 2], kw = h8 ? w4[j + 2] : w4[j];
-                            u2[j] = ku + __shfl_xor_sync(0xffffffffu, su, 8);
-                            w2[j] = kw + __shfl_xor_sync(0xffffffffu, sw, 8);
-                        }
-                        float u1 = (h4 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? u2[0] : u2[1], 4);
-                        float w1 = (h4 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? w2[0] : w2[1], 4);
-                        u1 += __shfl_xor_sync(0xffffffffu, u1, 2);
-                        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
-                        u1 += __shfl_xor_sync(0xffffffffu, u1, 1);
-                        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-                        ssum[s2][it] += u1;
-                        ssq[s2][it] += w1;
                     }
                 }
             }
@@ -762,7 +799,8 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
     }
     static int configured = 0;
     if (pl.total > configured) {
-        EAB_CUDA(cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));
+        EAB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));
+        EAB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));
         configured = pl.total;
     }
     static int sms = 0;
@@ -786,7 +824,8 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
     if (a.out_half && (a.resid || a.stft_M > 0)) return fail("conv_staged: fp16 output with a residual / STFT epilogue");
     ProfScope ps(a.stft_M > 0 ? "stft" : "conv_tma", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
                  in_bytes + (a.out_half ? 2.0 : 4.0) * pos * a.Cout * (a.resid ? 2 : 1) + 4.0 * a.ntaps * kreal * a.N, st);
-    EAB_CUDA(launch_k(conv_tma_kernel, dim3(grid), dim3(NTHREADS), (size_t)pl.total, st, a));
+    if (a.fused) EAB_CUDA(launch_k(conv_tma_kernel<true>, dim3(grid), dim3(NTHREADS_FUSED), (size_t)pl.total, st, a));
+    else EAB_CUDA(launch_k(conv_tma_kernel<false>, dim3(grid), dim3(NTHREADS_STAGED), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_tma_kernel");
     return 0;
 }
