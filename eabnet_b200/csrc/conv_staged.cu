@@ -652,8 +652,7 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
                         o4[0] = make_float4(r[0], r[1], r[2], r[3]);
                         o4[1] = make_float4(r[4], r[5], r[6], r[7]);
                     } else {
-                        o4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        st_global_256(a.out + off + c0, v);
                     }
                 }
                 if (a.nstats && !CEXP(2)) {
@@ -822,6 +821,8 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
         for (int i = 0; i < a.nsrc; ++i) in_bytes += 4.0 * a.B * a.T * a.Fin * a.src[i].C * (a.src[i].x2 ? 2 : 1);
     }
     if (a.out_half && (a.resid || a.stft_M > 0)) return fail("conv_staged: fp16 output with a residual / STFT epilogue");
+    if (a.stft_M == 0 && ((a.out_ld & 7) || (a.out_coff & 7) || (reinterpret_cast<uintptr_t>(a.out) & 31)))
+        return fail("conv_staged: output rows must be 32-byte aligned");
     ProfScope ps(a.stft_M > 0 ? "stft" : "conv_tma", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
                  in_bytes + (a.out_half ? 2.0 : 4.0) * pos * a.Cout * (a.resid ? 2 : 1) + 4.0 * a.ntaps * kreal * a.N, st);
     if (a.fused) EAB_CUDA(launch_k(conv_tma_kernel<true>, dim3(grid), dim3(NTHREADS_FUSED), (size_t)pl.total, st, a));

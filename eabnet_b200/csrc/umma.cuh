@@ -187,6 +187,14 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one full 32-byte sector per lane in ONE store instruction (STG.256, sm_100+): the per-row epilogue stores are
+// scattered across rows, so what counts is sectors per instruction, not lanes per line
+__device__ __forceinline__ void st_global_256(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 // 8 floats -> 8 fp16 (round to nearest even), and the fp16-rounded residual for the 3-pass split
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
