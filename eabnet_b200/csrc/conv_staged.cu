@@ -54,9 +54,7 @@ __device__ __forceinline__ void load8(const float* base, int is_half, size_t eof
         v0 = make_float4(a.x, a.y, b.x, b.y);
         v1 = make_float4(c.x, c.y, d.x, d.y);
     } else {
-        const float4* p = reinterpret_cast<const float4*>(base + eoff);
-        v0 = __ldg(p);
-        v1 = __ldg(p + 1);
+        ld_global_nc_256(base + eoff, v0, v1);       // 8 channels = one 32-byte sector, one instruction
     }
 }
 

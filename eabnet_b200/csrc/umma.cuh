@@ -195,6 +195,12 @@ __device__ __forceinline__ void st_global_256(float* p, const float (&v)[8]) {
                  : "memory");
 }
 
+__device__ __forceinline__ void ld_global_nc_256(const float* p, float4& v0, float4& v1) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w), "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w)
+                 : "l"(p));
+}
+
 // 8 floats -> 8 fp16 (round to nearest even), and the fp16-rounded residual for the 3-pass split
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
