@@ -315,7 +315,8 @@ def main():
                     "traffic": None}
         # DRAM bytes of a representative launch of that family from the committed ncu --set full capture
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_traffic.json"))).get(top["kernel"])
+            import glob
+            tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1])).get(top["kernel"])
         except Exception:
             tr = None
         if tr:
