@@ -2,8 +2,11 @@
 
     from eabnet_b200 import EaBNet              # same constructor / state_dict / forward as the reference
     from eabnet_b200 import stft_compress, istft
+    from eabnet_b200 import GaGNet, EaBNetWithPostNet, make_eabnet_with_postnet     # the post-filter enhance.py runs
 """
 from .model import EaBNet, numParams  # noqa: F401
+from .postnet import EaBNetWithPostNet, GaGNet, make_eabnet_with_postnet, make_gag_net  # noqa: F401
 from .signal import istft, stft_compress  # noqa: F401
 
-__all__ = ["EaBNet", "numParams", "stft_compress", "istft"]
+__all__ = ["EaBNet", "GaGNet", "EaBNetWithPostNet", "make_gag_net", "make_eabnet_with_postnet", "numParams",
+           "stft_compress", "istft"]

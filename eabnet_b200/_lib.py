@@ -14,6 +14,13 @@ class EabConfig(C.Structure):
         "is_u2", "bf_type", "topo_type", "intra_connect", "norm_type", "n_freq")]
 
 
+class EabGagConfig(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("cin", "k1_t", "k1_f", "k2_t", "k2_f", "c", "kd1", "cd1", "d_feat", "p", "q",
+                                        "n_dilas")] + [("dilas", C.c_int * 8)] +
+                [(n, C.c_int) for n in ("fft_num", "is_u2", "is_causal", "is_squeezed", "acti_type", "intra_connect",
+                                        "norm_type")])
+
+
 # every symbol include/eabnet_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _F = C.c_void_p          # float* passed as raw address
@@ -37,6 +44,9 @@ SYMBOLS = {
     "eab_stream_reset": (C.c_int, [_P, _P, C.c_size_t, C.c_int, _P]),
     "eab_stream_step": (C.c_int, [_P, _P, C.c_size_t, _F, _F, C.c_int, _P]),
     "eab_stream_step_spec": (C.c_int, [_P, _P, C.c_size_t, _F, _F, C.c_int, _P]),
+    "eab_gag_create": (C.c_int, [C.POINTER(EabGagConfig), C.POINTER(_P)]),
+    "eab_gag_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
+    "eab_gag_forward": (C.c_int, [_P, _F, C.POINTER(C.c_int64 * 4), _F, _F, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "eab_last_launch_count": (C.c_int, [_P]),
     "eab_debug_tap": (C.c_int64, [_P, C.c_char_p, _F, C.c_int64, _P]),
     "eab_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

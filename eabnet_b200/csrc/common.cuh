@@ -365,6 +365,30 @@ struct HeadArgs {
 bool head_fused_supported(const HeadArgs& a);
 int launch_head_fused(const HeadArgs& a, cudaStream_t st);
 
+// GaGNet post-filter glue (gag_elementwise.cu)
+struct GagPackArgs {
+    const float* inpt;           // reference-microphone spectrum, element (b, c, t, f) at b*sb + c*sc + t*st + f*sf (floats)
+    long long sb, sc, st, sf;
+    const float* pre;            // [B][2][T][F] previous estimate (EaBNet output layout)
+    float* x4;                   // [B][T][F][4]  channels (inpt_r, pre_r, inpt_i, pre_i)
+    float* pre_row;              // [B][T][KP]    channel ri*F + f, zeros from 2F on
+    int B, T, F, KP, KP2;        // KP2 = KP / 2
+};
+int launch_gag_pack(const GagPackArgs& a, cudaStream_t st);
+
+struct GagCrmArgs {
+    const float* pre_row;        // [B][T][KP]
+    const float* gain;           // [B][T][ld_g] raw linear_g output (activation applied here)
+    const float* res_r;          // [B][T][ld_r] linear_r / linear_i outputs
+    const float* res_i;
+    int ld_g, ld_r;
+    int acti;                    // 0 sigmoid, 1 tanh, 2 relu (GaGNet.py:165-172)
+    float* next_row;             // [B][T][KP] the estimate as the next module's pre_x row, or null for the last module
+    float* out;                  // [B][2][T][F]
+    int B, T, F, KP, KP2;
+};
+int launch_gag_crm(const GagCrmArgs& a, cudaStream_t st);
+
 int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st);
 int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st);
 // streaming front/back end (stft.cu): one hop in -> spectrum frame *step into a ring; spectrum frame -> one hop out

@@ -138,11 +138,31 @@ struct UmmaW {
 
 struct TcmLayer {
     int dilation = 1;
+    bool single = false;                 // GaGNet's SqueezedTCM: one dilated branch, no gate (GaGNet.py:285-326)
+    bool perm = true;                    // residual stream in bottleneck order f*64+c (EaBNet); false = reference order
     UmmaW u_in, u_dil, u_out;
     int w_in = -1, w_left = -1, w_right = -1, w_out = -1;
     NormAct na_left, na_right, na_out;
     size_t off_in = 0, off_dil = 0, off_out = 0;
     int dt[kMaxTaps];
+};
+
+// GaGNet glance / gaze blocks (GaGNet.py:136-259)
+struct GagIn {                       // in_conv_main(cat) * sigmoid(in_conv_gate(cat)) as d_feat/64 gated column splits
+    int w_main = -1, b_main = -1, w_gate = -1, b_gate = -1;
+    int nsplit = 0, K = 0;
+    size_t off_dense[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    UmmaW u[8];
+};
+struct GagLin {                      // Conv1d(d_feat, F, 1) with bias
+    int w = -1, b = -1, N = 0;
+    size_t off_w = 0, off_b = 0;
+    UmmaW u;
+};
+struct GagModule {
+    GagIn in_g, in_z;
+    std::vector<TcmLayer> tcn_g, tcm_r, tcm_i;       // is_squeezed: tcm_i empty, tcm_r holds `tcm_ri`
+    GagLin lin_g, lin_r, lin_i;
 };
 
 struct Act {                 // an activation tensor as seen by a consumer
@@ -170,6 +190,9 @@ using namespace eab;
 
 struct eab_model {
     eab_config cfg;
+    int kind = 0;                                   // 0 EaBNet, 1 GaGNet post-filter (eab_gag_create)
+    eab_gag_config gcfg;
+    std::vector<GagModule> gags;
     std::vector<Param> params;
     std::unordered_map<std::string, int> index;
 
@@ -405,6 +428,113 @@ int build(eab_model* m) {
     return 0;
 }
 
+// GaGNet.__init__ (GaGNet.py:69-73): encoder on cat(inpt, pre_x), then q glance-gaze modules.  m->cfg carries the
+// settings the shared builder / packer / runner code reads (M = cin makes the first layer's 2M input channels the
+// reference's cin*2 and its (ri, m) -> (m, ri) weight permutation the one gag_pack_kernel's channel order needs).
+int build_gag(eab_model* m) {
+    const eab_gag_config& g = m->gcfg;
+    eab_config& c = m->cfg;
+    if (g.cin != 2) return fail("GaGNet: cin must be 2 (the reference's glance / gaze 1x1 convs take 2*(fft_num/2+1) + d_feat channels, GaGNet.py:160,224)");
+    if (g.n_dilas < 1 || g.n_dilas > 8) return fail("GaGNet: 1..8 dilation rates");
+    if (g.fft_num < 2 || (g.fft_num & 1)) return fail("GaGNet: fft_num must be even");
+    if (g.acti_type < 0 || g.acti_type > 2) return fail("GaGNet: a activation function must be assigned! (GaGNet.py:171-172)");
+    memset(&c, 0, sizeof(c));
+    c.k1_t = g.k1_t; c.k1_f = g.k1_f; c.k2_t = g.k2_t; c.k2_f = g.k2_f; c.c = g.c; c.M = g.cin; c.embed_dim = 64;
+    c.kd1 = g.kd1; c.cd1 = g.cd1; c.d_feat = g.d_feat; c.p = g.p; c.q = g.q; c.is_causal = g.is_causal; c.is_u2 = g.is_u2;
+    c.intra_connect = g.intra_connect; c.norm_type = g.norm_type; c.n_freq = g.fft_num / 2 + 1;
+    if (c.c < 1 || c.c > 128) return fail("c must be in 1..128");
+    if (c.kd1 < 1 || c.kd1 > kMaxTaps) return fail("kd1 must be in 1..16");
+    if (c.k1_t < 1 || c.k1_t > 2 || c.k2_t < 1 || c.k2_t > 2) return fail("temporal kernel sizes above 2 are not supported");
+    if (c.k1_t * c.k1_f > kMaxTaps || c.k2_t * c.k2_f > kMaxTaps || c.k1_f < 1 || c.k2_f < 1) return fail("kernel too large");
+    if (c.cd1 < 1 || c.cd1 > 128) return fail("cd1 must be in 1..128");
+    if (c.p < 1 || c.q < 1 || c.q > 16) return fail("p >= 1 and 1 <= q <= 16 required");
+    if (c.norm_type != 0 && c.norm_type != 1) return fail("norm_type must be 'IN' or 'BN'");
+    Builder bd{m};
+    m->Fchain.clear();
+    m->Fchain.push_back(c.n_freq);
+    {
+        int F = conv_out_f(c.n_freq, 5);
+        m->Fchain.push_back(F);
+        for (int i = 0; i < 4; ++i) { F = F > 0 ? conv_out_f(F, c.k1_f) : -1; m->Fchain.push_back(F); }
+        if (F < 1) return fail("fft_num too small for the five stride-2 encoder stages");
+        m->Fb = F;
+    }
+    if (c.d_feat != 64 * m->Fb) return fail("d_feat must equal 64 * bottleneck_F (the reference fails at run time otherwise)");
+    if (c.d_feat / 64 > 8) return fail("GaGNet: d_feat above 512 is not supported");
+    if (c.is_u2) {
+        m->en_mod.push_back(bd.module("en.meta_unet_list.0", 2 * c.M, 2, 5, 4, false));
+        for (int i = 1; i < 4; ++i)
+            m->en_mod.push_back(bd.module("en.meta_unet_list." + std::to_string(i), c.c, c.k1_t, c.k1_f, 4 - i, false));
+        m->en_mod[0].in_conv.perm_ri = true;
+        m->en_mod[0].in_conv.M = c.M;
+        m->en_last = bd.gated("en.last_conv", c.c, 64, c.k1_t, c.k1_f, false, true);
+        for (auto& U : m->en_mod) { for (auto& L : U.enco) L.zone = 2; for (auto& L : U.deco) L.zone = 2; }
+    } else {
+        // UNet_Encoder of GaGNet.py:368-413: every layer carries its norm (EaBNet's variant drops two of them)
+        m->en_plain.push_back(bd.gated("en.unet_list.0", 2 * c.M, c.c, 2, 5, false, true));
+        m->en_plain[0].perm_ri = true;
+        m->en_plain[0].M = c.M;
+        for (int i = 1; i < 4; ++i)
+            m->en_plain.push_back(bd.gated("en.unet_list." + std::to_string(i), c.c, c.c, c.k1_t, c.k1_f, false, true));
+        m->en_plain.push_back(bd.gated("en.unet_list.4", c.c, 64, c.k1_t, c.k1_f, false, true));
+    }
+    const int Fq = c.n_freq, ci = 2 * Fq + c.d_feat;
+    auto tcm_groups = [&](const std::string& pfx, std::vector<TcmLayer>& dst) -> int {
+        for (int gi = 0; gi < c.p; ++gi)
+            for (int i = 0; i < g.n_dilas; ++i) {
+                TcmLayer t;
+                t.single = true;
+                t.perm = false;
+                t.dilation = g.dilas[i];
+                if (t.dilation < 1) return fail("GaGNet: dilation rates must be positive");
+                const std::string p = pfx + "." + std::to_string(gi) + ".tcns." + std::to_string(i);
+                t.w_in = bd.add(p + ".in_conv.weight", {c.cd1, c.d_feat, 1}, EAB_P_CONV_W, c.d_feat);
+                t.na_left.C = t.na_out.C = c.cd1;
+                t.na_left.alpha = bd.add(p + ".d_conv.0.weight", {c.cd1}, EAB_P_PRELU, c.cd1);
+                bd.norm(p + ".d_conv.1", c.cd1, t.na_left);
+                t.w_left = bd.add(p + ".d_conv.3.weight", {c.cd1, c.cd1, c.kd1}, EAB_P_CONV_W, c.cd1 * c.kd1);
+                t.na_out.alpha = bd.add(p + ".out_conv.0.weight", {c.cd1}, EAB_P_PRELU, c.cd1);
+                bd.norm(p + ".out_conv.1", c.cd1, t.na_out);
+                t.w_out = bd.add(p + ".out_conv.2.weight", {c.d_feat, c.cd1, 1}, EAB_P_CONV_W, c.cd1);
+                const int span = (c.kd1 - 1) * t.dilation;
+                if (!c.is_causal && (span & 1)) return fail("non-causal TCM needs an even (kd1-1)*dilation");
+                const int pad_left = c.is_causal ? span : span / 2;
+                for (int k = 0; k < c.kd1; ++k) t.dt[k] = pad_left - k * t.dilation;
+                dst.push_back(t);
+            }
+        return 0;
+    };
+    auto in_convs = [&](const std::string& p, GagIn& in) {
+        in.w_main = bd.add(p + ".in_conv_main.weight", {c.d_feat, ci, 1}, EAB_P_CONV_W, ci);
+        in.b_main = bd.add(p + ".in_conv_main.bias", {c.d_feat}, EAB_P_CONV_B, ci);
+        in.w_gate = bd.add(p + ".in_conv_gate.0.weight", {c.d_feat, ci, 1}, EAB_P_CONV_W, ci);
+        in.b_gate = bd.add(p + ".in_conv_gate.0.bias", {c.d_feat}, EAB_P_CONV_B, ci);
+    };
+    auto lin = [&](const std::string& p, GagLin& l) {
+        l.w = bd.add(p + ".weight", {Fq, c.d_feat, 1}, EAB_P_CONV_W, c.d_feat);
+        l.b = bd.add(p + ".bias", {Fq}, EAB_P_CONV_B, c.d_feat);
+    };
+    m->gags.resize(c.q);
+    for (int i = 0; i < c.q; ++i) {
+        GagModule& G = m->gags[i];
+        std::string p = "gags." + std::to_string(i) + ".glance_block";
+        in_convs(p, G.in_g);
+        EAB_TRY(tcm_groups(p + ".tcn_g", G.tcn_g));
+        lin(p + ".linear_g.0", G.lin_g);
+        p = "gags." + std::to_string(i) + ".gaze_block";
+        in_convs(p, G.in_z);
+        if (g.is_squeezed) {
+            EAB_TRY(tcm_groups(p + ".tcm_ri", G.tcm_r));
+        } else {
+            EAB_TRY(tcm_groups(p + ".tcm_r", G.tcm_r));
+            EAB_TRY(tcm_groups(p + ".tcm_i", G.tcm_i));
+        }
+        lin(p + ".linear_r", G.lin_r);
+        lin(p + ".linear_i", G.lin_i);
+    }
+    return 0;
+}
+
 // ================================================================================================ pack
 struct Packer {
     eab_model* m;
@@ -592,34 +722,74 @@ struct Packer {
         const eab_config& c = m->cfg;
         const int Fb = m->Fb, cd = c.cd1, df = c.d_feat, kd = c.kd1;
         const int Nin = pad_n(cd);
-        // 1x1 squeeze: reference channel cc*Fb + f  ->  memory channel f*64 + cc
+        // residual-stream channel of reference channel cr: bottleneck order f*64 + cc for cr = cc*Fb + f (EaBNet), or cr itself
+        auto mem_ch = [&](int cr) { if (!t.perm) return cr; const int cc = cr / Fb, f = cr - cc * Fb; return f * 64 + cc; };
+        // 1x1 squeeze
         t.off_in = alloc((size_t)df * Nin);
         for (int n = 0; n < cd; ++n)
-            for (int cr = 0; cr < df; ++cr) {
-                const int cc = cr / Fb, f = cr - cc * Fb;
-                blob[t.off_in + (size_t)(f * 64 + cc) * Nin + n] = P(t.w_in)[(size_t)n * df + cr];
-            }
-        // dilated pair as one gated conv over K = [left-branch channels | right-branch channels]
-        const int Nd = 2 * ceil64(cd), goff = ceil64(cd);
-        t.off_dil = alloc((size_t)kd * 2 * cd * Nd);
-        for (int k = 0; k < kd; ++k)
-            for (int ci = 0; ci < cd; ++ci)
-                for (int n = 0; n < cd; ++n) {
-                    blob[t.off_dil + ((size_t)k * 2 * cd + ci) * Nd + n] = P(t.w_left)[((size_t)n * cd + ci) * kd + k];
-                    blob[t.off_dil + ((size_t)k * 2 * cd + cd + ci) * Nd + goff + n] = P(t.w_right)[((size_t)n * cd + ci) * kd + k];
-                }
-        // 1x1 expand: output reference channel cc*Fb + f -> column f*64 + cc
-        t.off_out = alloc((size_t)cd * df);
-        for (int nr = 0; nr < df; ++nr) {
-            const int cc = nr / Fb, f = nr - cc * Fb;
-            for (int ci = 0; ci < cd; ++ci) blob[t.off_out + (size_t)ci * df + (f * 64 + cc)] = P(t.w_out)[(size_t)nr * cd + ci];
+            for (int cr = 0; cr < df; ++cr)
+                blob[t.off_in + (size_t)mem_ch(cr) * Nin + n] = P(t.w_in)[(size_t)n * df + cr];
+        if (t.single) {
+            // one dilated branch, no gate (GaGNet.py:310-315)
+            t.off_dil = alloc((size_t)kd * cd * Nin);
+            for (int k = 0; k < kd; ++k)
+                for (int ci = 0; ci < cd; ++ci)
+                    for (int n = 0; n < cd; ++n)
+                        blob[t.off_dil + ((size_t)k * cd + ci) * Nin + n] = P(t.w_left)[((size_t)n * cd + ci) * kd + k];
+        } else {
+            // dilated pair as one gated conv over K = [left-branch channels | right-branch channels]
+            const int Nd = 2 * ceil64(cd), goff = ceil64(cd);
+            t.off_dil = alloc((size_t)kd * 2 * cd * Nd);
+            for (int k = 0; k < kd; ++k)
+                for (int ci = 0; ci < cd; ++ci)
+                    for (int n = 0; n < cd; ++n) {
+                        blob[t.off_dil + ((size_t)k * 2 * cd + ci) * Nd + n] = P(t.w_left)[((size_t)n * cd + ci) * kd + k];
+                        blob[t.off_dil + ((size_t)k * 2 * cd + cd + ci) * Nd + goff + n] = P(t.w_right)[((size_t)n * cd + ci) * kd + k];
+                    }
         }
+        // 1x1 expand
+        t.off_out = alloc((size_t)cd * df);
+        for (int nr = 0; nr < df; ++nr)
+            for (int ci = 0; ci < cd; ++ci) blob[t.off_out + (size_t)ci * df + mem_ch(nr)] = P(t.w_out)[(size_t)nr * cd + ci];
         t.u_in = umma_images(t.off_in, 1, df, Nin, cd, false, 0, nullptr);
-        t.u_dil = umma_images(t.off_dil, kd, 2 * cd, Nd, 2 * cd, true, goff, nullptr);
+        if (t.single) t.u_dil = umma_images(t.off_dil, kd, cd, Nin, cd, false, 0, nullptr);
+        else t.u_dil = umma_images(t.off_dil, kd, 2 * cd, 2 * ceil64(cd), 2 * cd, true, ceil64(cd), nullptr);
         t.u_out = umma_images(t.off_out, 1, cd, df, df, false, 0, nullptr);
         normact(t.na_left);
-        normact(t.na_right);
+        if (!t.single) normact(t.na_right);
         normact(t.na_out);
+    }
+
+    // GaGNet glance / gaze input convs (GaGNet.py:161-165, 190): K = [encoder feature, bottleneck order f*64+c | pre_x row
+    // ri*F+f, zero-padded to KP], columns of split sp = value channels 64 sp .. | gate channels 64 sp ..
+    void gag_in(GagIn& in) {
+        const eab_config& c = m->cfg;
+        const int Fb = m->Fb, df = c.d_feat, Fq = c.n_freq, KP = ceil64(2 * Fq), ci = 2 * Fq + df;
+        in.K = df + KP;
+        in.nsplit = df / 64;
+        for (int sp = 0; sp < in.nsplit; ++sp) {
+            in.off_dense[sp] = alloc((size_t)in.K * 128);
+            std::vector<float> bias(128);
+            for (int n = 0; n < 128; ++n) {
+                const bool gate = n >= 64;
+                const int co = sp * 64 + (n & 63);
+                const std::vector<float>& W = P(gate ? in.w_gate : in.w_main);
+                bias[n] = P(gate ? in.b_gate : in.b_main)[co];
+                for (int cr = 0; cr < df; ++cr) {
+                    const int cc = cr / Fb, f = cr - cc * Fb;
+                    blob[in.off_dense[sp] + (size_t)(f * 64 + cc) * 128 + n] = W[(size_t)co * ci + cr];
+                }
+                for (int k = 0; k < 2 * Fq; ++k) blob[in.off_dense[sp] + (size_t)(df + k) * 128 + n] = W[(size_t)co * ci + df + k];
+            }
+            in.u[sp] = umma_images(in.off_dense[sp], 1, in.K, 128, 128, true, 64, bias.data());
+        }
+    }
+
+    void gag_lin(GagLin& l) {
+        const eab_config& c = m->cfg;
+        l.off_w = linear(l.w, l.b, c.n_freq, c.d_feat, &l.N, &l.off_b);
+        std::vector<float> b0(blob.begin() + l.off_b, blob.begin() + l.off_b + l.N);
+        l.u = umma_images(l.off_w, 1, c.d_feat, l.N, c.n_freq, false, 0, b0.data());
     }
 
     // Build fp16 hi/lo images from a dense [ntaps][K][ldn] fp32 matrix that already sits in the blob at `off`
@@ -753,11 +923,21 @@ int commit(eab_model* m, cudaStream_t st) {
     Packer pk{m};
     for (auto& U : m->en_mod) { pk.conv(U.in_conv); for (auto& L : U.enco) pk.conv(L); for (auto& L : U.deco) pk.conv(L); }
     for (auto& U : m->de_mod) { pk.conv(U.in_conv); for (auto& L : U.enco) pk.conv(L); for (auto& L : U.deco) pk.conv(L); }
-    if (m->cfg.is_u2) { pk.conv(m->en_last); pk.conv(m->de_last); }
+    if (m->cfg.is_u2) { pk.conv(m->en_last); if (m->kind == 0) pk.conv(m->de_last); }
     for (auto& L : m->en_plain) pk.conv(L);
     for (auto& L : m->de_plain) pk.conv(L);
     for (auto& t : m->tcms) pk.tcm(t);
-    pk.head();
+    if (m->kind == 0) pk.head();
+    for (auto& G : m->gags) {
+        pk.gag_in(G.in_g);
+        pk.gag_in(G.in_z);
+        for (auto& t : G.tcn_g) pk.tcm(t);
+        for (auto& t : G.tcm_r) pk.tcm(t);
+        for (auto& t : G.tcm_i) pk.tcm(t);
+        pk.gag_lin(G.lin_g);
+        pk.gag_lin(G.lin_r);
+        pk.gag_lin(G.lin_i);
+    }
     if (m->blob && m->blob_floats < pk.blob.size()) { cudaFree(m->blob); m->blob = nullptr; }
     if (!m->blob) {
         EAB_CUDA(cudaMalloc(&m->blob, pk.blob.size() * sizeof(float)));
@@ -1276,6 +1456,21 @@ int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
         for (int i = 0; i < c.kd1; ++i) back = std::max(back, t.dt[i]);
         cx.next_RT = back + 1;
     }
+    Act z;
+    double* st_o[1] = {nullptr};
+    if (t.single) {
+        // GaGNet's SqueezedTCM: squeeze 1x1 (statistics of PReLU(y)), one plain dilated conv
+        double* st_d[1] = {in_stats ? cx.alloc_stats(c.cd1) : nullptr};
+        const float* al_d[1] = {cx.W(t.na_left.off_alpha)};
+        Act y;
+        EAB_TRY(run_pointwise(cx, &x, 1, cx.W(t.off_in), nullptr, c.cd1, pad_n(c.cd1), 0, 1, nullptr, 0, nullptr,
+                              in_stats ? 1 : 0, st_d, al_d, &y, &t.u_in));
+        y.xf = xf_after(cx, t.na_left, st_d[0], cx.T, 1);
+        st_o[0] = in_stats ? cx.alloc_stats(c.cd1) : nullptr;
+        const float* al_o[1] = {cx.W(t.na_out.off_alpha)};
+        EAB_TRY(run_pointwise(cx, &y, 1, cx.W(t.off_dil), nullptr, c.cd1, pad_n(c.cd1), 0, c.kd1, t.dt, 0, nullptr,
+                              in_stats ? 1 : 0, st_o, al_o, &z, &t.u_dil));
+    } else {
     // squeeze 1x1; statistics of PReLU_left(y) and PReLU_right(y) for the two branch norms
     double* st_lr[2] = {in_stats ? cx.alloc_stats(c.cd1) : nullptr, in_stats ? cx.alloc_stats(c.cd1) : nullptr};
     const float* al_lr[2] = {cx.W(t.na_left.off_alpha), cx.W(t.na_right.off_alpha)};
@@ -1286,11 +1481,11 @@ int run_tcm(Ctx& cx, const TcmLayer& t, const Act& x, Act* out) {
     Act br[2] = {y, y};
     br[0].xf = xf_after(cx, t.na_left, st_lr[0], cx.T, 1);
     br[1].xf = xf_after(cx, t.na_right, st_lr[1], cx.T, 1);
-    double* st_o[1] = {in_stats ? cx.alloc_stats(c.cd1) : nullptr};
+    st_o[0] = in_stats ? cx.alloc_stats(c.cd1) : nullptr;
     const float* al_o[1] = {cx.W(t.na_out.off_alpha)};
-    Act z;
     EAB_TRY(run_pointwise(cx, br, 2, cx.W(t.off_dil), nullptr, c.cd1, 2 * ceil64(c.cd1), ceil64(c.cd1), c.kd1, t.dt, 0,
                           nullptr, in_stats ? 1 : 0, st_o, al_o, &z, &t.u_dil));
+    }
     // expand 1x1 + residual
     z.xf = xf_after(cx, t.na_out, st_o[0], cx.T, 1);
     EAB_TRY(run_pointwise(cx, &z, 1, cx.W(t.off_out), nullptr, c.d_feat, c.d_feat, 0, 1, nullptr, 0, x.data, 0, nullptr,
@@ -1499,9 +1694,135 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- GaGNet post-filter
+// in_conv_main(cat(feat, pre)) * sigmoid(in_conv_gate(cat(feat, pre)))  (GaGNet.py:189-191, 249-251): d_feat/64 gated
+// tcgen05 launches over K = d_feat + KP (two sources, the concat is never materialised)
+int run_gag_in(Ctx& cx, const GagIn& in, const Act& feat, const Act& pre, Act* out) {
+    const eab_config& c = cx.m->cfg;
+    out->F = 1; out->C = c.d_feat; out->xf = xform_identity();
+    out->data = cx.alloc_act((size_t)cx.B * cx.T * c.d_feat);
+    out->RT = cx.last_RT;
+    if (!cx.tensor_ok()) return fail("GaGNet: the glance / gaze input convs run on the tcgen05 path only (option umma=0 is not supported)");
+    for (int sp = 0; sp < in.nsplit; ++sp) {
+        if (!cx.dry && !in.u[sp].ok) return fail("internal: GaGNet input conv images missing");
+        UmmaConvArgs u;
+        memset(&u, 0, sizeof(u));
+        u.nsrc = 2;
+        set_src(u.src[0], feat);
+        set_src(u.src[1], pre);
+        u.B = cx.B; u.T = cx.T; u.Fin = 1; u.Fout = 1; u.E = 1;
+        u.in_stride = 1; u.out_stride = 1; u.out_off = 0;
+        u.ntaps = 1; u.dt[0] = 0; u.df[0] = 0;
+        u.nslab = in.K / 64; u.ncoef = in.K; u.npass = 3;
+        u.Whi = cx.W(in.u[sp].off_hi[0]); u.Wlo = cx.W(in.u[sp].off_lo[0]); u.bias = cx.W(in.u[sp].off_bias[0]);
+        u.Cout = 64; u.N = 128; u.gate_off = 64;
+        u.algo_frac = (float)(c.d_feat + 2 * c.n_freq) / (float)in.K;
+        u.out = out->data; u.out_ld = c.d_feat; u.out_coff = sp * 64;
+        u.tiles_per_b = (cx.T + 127) / 128;
+        if (feat.C + pre.C != in.K || !umma_conv_supported(u)) return fail("internal: GaGNet input conv rejected by the tcgen05 path");
+        EAB_TRY(run_tensor_convs(cx, &u, 1));
+    }
+    return 0;
+}
+
+int run_gag_lin(Ctx& cx, const GagLin& l, const Act& x, Act* out) {
+    const eab_config& c = cx.m->cfg;
+    return run_pointwise(cx, &x, 1, cx.W(l.off_w), cx.W(l.off_b), c.n_freq, l.N, 0, 1, nullptr, 0, nullptr, 0, nullptr, nullptr,
+                         out, &l.u);
+}
+
+// GaGNet.forward (GaGNet.py:75-89).  inpt through strides sb, sc, st, sf (floats); pre [B,2,T,F]; out [q][B,2,T,F].
+int run_gag_forward(Ctx& cx, const float* inpt, const long long* strides, const float* pre_in, float* out_dev) {
+    eab_model* m = cx.m;
+    const eab_config& c = m->cfg;
+    const int F = c.n_freq, KP = ceil64(2 * F);
+    Act x;
+    x.F = F; x.C = 4; x.xf = xform_identity();
+    x.data = cx.alloc_act((size_t)cx.B * cx.T * F * 4);
+    Act pre;
+    pre.F = 1; pre.C = KP; pre.xf = xform_identity();
+    pre.data = cx.alloc_act((size_t)cx.B * cx.T * KP);
+    if (!cx.dry) {
+        GagPackArgs a;
+        memset(&a, 0, sizeof(a));
+        a.inpt = inpt; a.sb = strides[0]; a.sc = strides[1]; a.st = strides[2]; a.sf = strides[3];
+        a.pre = pre_in; a.x4 = x.data; a.pre_row = pre.data;
+        a.B = cx.B; a.T = cx.T; a.F = F; a.KP = KP; a.KP2 = KP / 2;
+        EAB_TRY(launch_gag_pack(a, cx.st));
+    }
+    // ---------------- encoder (GaGNet.py:361-365 / :408-412): only the bottleneck is used
+    if (c.is_u2) {
+        for (size_t i = 0; i < m->en_mod.size(); ++i) {
+            Act y;
+            EAB_TRY(run_module(cx, m->en_mod[i], &x, 1, &y));
+            tap(cx, ("en." + std::to_string(i)).c_str(), y);
+            x = y;
+        }
+        Act y;
+        EAB_TRY(run_conv2d(cx, m->en_last, &x, 1, &y));
+        x = y;
+    } else {
+        for (size_t i = 0; i < m->en_plain.size(); ++i) {
+            Act y;
+            EAB_TRY(run_conv2d(cx, m->en_plain[i], &x, 1, &y));
+            x = y;
+        }
+    }
+    tap(cx, "en.4", x);
+    if (x.F != m->Fb || x.C != 64) return fail("internal: bottleneck shape");
+    Act feat;                                             // [B,T,1,d_feat] finalised, channel f*64+c
+    EAB_TRY(run_combine(cx, &x, 1, &feat));
+    feat.F = 1; feat.C = c.d_feat; feat.xf = xform_identity();
+    // ---------------- glance-gaze modules (GaGNet.py:84-88, 120-134)
+    const size_t stage_elems = (size_t)cx.B * 2 * cx.T * F;
+    for (size_t gi = 0; gi < m->gags.size(); ++gi) {
+        const GagModule& G = m->gags[gi];
+        const bool last = gi + 1 == m->gags.size();
+        Act next;
+        next.F = 1; next.C = KP; next.xf = xform_identity();
+        next.data = last ? nullptr : cx.alloc_act((size_t)cx.B * cx.T * KP);      // outlives the module's scratch
+        const size_t scope = cx.mark();
+        Act xg;
+        EAB_TRY(run_gag_in(cx, G.in_g, feat, pre, &xg));
+        tap(cx, ("g.in_g." + std::to_string(gi)).c_str(), xg);
+        for (const TcmLayer& t : G.tcn_g) { Act nx; EAB_TRY(run_tcm(cx, t, xg, &nx)); xg = nx; }
+        tap(cx, ("g.tcn_g." + std::to_string(gi)).c_str(), xg);
+        Act gain;
+        EAB_TRY(run_gag_lin(cx, G.lin_g, xg, &gain));
+        Act xz;
+        EAB_TRY(run_gag_in(cx, G.in_z, feat, pre, &xz));
+        Act xr = xz, xi = xz;
+        for (const TcmLayer& t : G.tcm_r) { Act nx; EAB_TRY(run_tcm(cx, t, xr, &nx)); xr = nx; }
+        if (m->gcfg.is_squeezed) xi = xr;
+        else for (const TcmLayer& t : G.tcm_i) { Act nx; EAB_TRY(run_tcm(cx, t, xi, &nx)); xi = nx; }
+        Act rr, ri;
+        EAB_TRY(run_gag_lin(cx, G.lin_r, xr, &rr));
+        EAB_TRY(run_gag_lin(cx, G.lin_i, xi, &ri));
+        tap(cx, ("g.gain." + std::to_string(gi)).c_str(), gain);
+        tap(cx, ("g.res_r." + std::to_string(gi)).c_str(), rr);
+        if (rr.C != ri.C) return fail("internal: GaGNet residual widths differ");
+        if (!cx.dry) {
+            GagCrmArgs a;
+            memset(&a, 0, sizeof(a));
+            a.pre_row = pre.data; a.gain = gain.data; a.res_r = rr.data; a.res_i = ri.data;
+            a.ld_g = gain.C; a.ld_r = rr.C; a.acti = m->gcfg.acti_type;
+            a.next_row = next.data; a.out = out_dev + gi * stage_elems;
+            a.B = cx.B; a.T = cx.T; a.F = F; a.KP = KP; a.KP2 = KP / 2;
+            EAB_TRY(launch_gag_crm(a, cx.st));
+        }
+        cx.release(scope);
+        pre = next;
+    }
+    return 0;
+}
+
 int plan(eab_model* m, int B, int T, size_t* stats_bytes, size_t* total_bytes) {
     Ctx cx;
     cx.m = m; cx.dry = true; cx.base = nullptr; cx.B = B; cx.T = T; cx.st = nullptr;
+    if (m->kind == 1) {
+        const long long zero[4] = {0, 0, 0, 0};
+        EAB_TRY(run_gag_forward(cx, nullptr, zero, nullptr, nullptr));
+    } else
     EAB_TRY(run_forward(cx, nullptr, nullptr));
     *stats_bytes = cx.stats_off;
     *total_bytes = cx.stats_off + cx.act_peak;
@@ -1519,6 +1840,7 @@ inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
 int stream_layout(eab_model* m, int S, StreamLayout* L) {
     const eab_config& c = m->cfg;
+    if (m->kind != 0) return fail("streaming is implemented for EaBNet handles only");
     if (S < 1) return fail("stream: need at least one stream");
     if (c.norm_type != 1) return fail("streaming needs norm_type='BN': InstanceNorm statistics span the whole utterance (EaBNet.py:684-686)");
     if (!c.is_causal) return fail("streaming needs is_causal=True");
@@ -1547,7 +1869,27 @@ int stream_forward(eab_model* m, char* state, const StreamLayout& L, int S, cuda
     return run_forward(cx, reinterpret_cast<const float*>(state + L.off_spec), reinterpret_cast<float*>(state + L.off_out));
 }
 
+int gag_forward(eab_model* m, const float* inpt, const long long* strides, const float* pre, float* out, int B, int T, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+    if (m->kind != 1) return fail("eab_gag_forward: the handle is not a GaGNet (create it with eab_gag_create)");
+    if (B < 1 || T < 1) return fail("forward: B and T must be positive");
+    if (m->cfg.norm_type == 0 && T < 2) return fail("InstanceNorm1d needs more than one frame (the reference raises too)");
+    if (m->dirty) return fail("parameters not committed: call eab_commit_params first");
+    size_t sb = 0, tb = 0;
+    EAB_TRY(plan(m, B, T, &sb, &tb));
+    if (ws_bytes < tb) return fail("workspace too small: need " + std::to_string(tb) + " bytes");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail("workspace must be 256-byte aligned");
+    m->taps.clear();
+    m->umma_launch_idx = 0;
+    if (sb) EAB_CUDA(cudaMemsetAsync(ws, 0, sb, st));
+    Ctx cx;
+    cx.m = m; cx.dry = false; cx.base = static_cast<char*>(ws); cx.B = B; cx.T = T; cx.st = st;
+    cx.stats_off = 0; cx.stats_cap = sb; cx.act_off = sb; cx.act_peak = sb;
+    return run_gag_forward(cx, inpt, strides, pre, out);
+}
+
 int forward(eab_model* m, const float* inpt, float* out, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (m->kind != 0) return fail("this entry point needs an EaBNet handle (eab_create); a GaGNet runs through eab_gag_forward");
     if (B < 1 || T < 1) return fail("forward: B and T must be positive");
     if (m->cfg.norm_type == 0 && T < 2)
         return fail("InstanceNorm1d needs more than one frame (the reference raises too)");
@@ -1571,6 +1913,8 @@ int forward(eab_model* m, const float* inpt, float* out, int B, int T, void* ws,
 // =================================================================================================== C ABI
 extern "C" {
 
+size_t eab_workspace_bytes(const eab_model* m, int B, int T);
+
 int eab_create(const eab_config* cfg, eab_model** out) {
     if (!cfg || !out) return fail("eab_create: null argument");
     std::unique_ptr<eab_model> m(new eab_model());
@@ -1582,6 +1926,34 @@ int eab_create(const eab_config* cfg, eab_model** out) {
     if (!(m->cfg.topo_type == 0 && m->cfg.bf_type == 0)) m->opt_dec_passes = 3;
     *out = m.release();
     return 0;
+}
+
+int eab_gag_create(const eab_gag_config* cfg, eab_model** out) {
+    if (!cfg || !out) return fail("eab_gag_create: null argument");
+    std::unique_ptr<eab_model> m(new eab_model());
+    m->kind = 1;
+    m->gcfg = *cfg;
+    if (build_gag(m.get())) return 1;
+    // the post-filter refines an estimate that is already within tolerance: keep its whole encoder fp32-grade
+    m->opt_enc_passes = 3;
+    m->opt_inner_passes = 3;
+    *out = m.release();
+    return 0;
+}
+
+size_t eab_gag_workspace_bytes(const eab_model* m, int B, int T) {
+    if (!m || m->kind != 1) return 0;
+    return eab_workspace_bytes(m, B, T);
+}
+
+int eab_gag_forward(eab_model* m, const float* inpt, const int64_t inpt_strides[4], const float* pre, float* out, int B, int T,
+                    void* ws, size_t ws_bytes, void* stream) {
+    if (!m || !inpt || !inpt_strides || !pre || !out || !ws) return fail("eab_gag_forward: null argument");
+    const long long st4[4] = {(long long)inpt_strides[0], (long long)inpt_strides[1], (long long)inpt_strides[2], (long long)inpt_strides[3]};
+    reset_launch_count();
+    const int rc = gag_forward(m, inpt, st4, pre, out, B, T, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    m->last_launches = launch_count();
+    return rc;
 }
 
 void eab_destroy(eab_model* m) {
@@ -1667,6 +2039,7 @@ size_t eab_enhance_workspace_bytes(const eab_model* m, int B, int L) {
 
 int eab_enhance(eab_model* m, const float* wave, float* enhanced, int B, int L, void* ws, size_t ws_bytes, void* stream) {
     if (!m || !wave || !enhanced || !ws) return fail("eab_enhance: null argument");
+    if (m->kind != 0) return fail("eab_enhance needs an EaBNet handle");
     if (m->cfg.topo_type == 1) return fail("eab_enhance: the 'miso' topology returns [B,2,T], which has no iSTFT");
     if (m->cfg.n_freq != 161) return fail("eab_enhance: the 320-point STFT gives 161 bins");
     if (L < 161) return fail("eab_enhance: need at least 161 samples");

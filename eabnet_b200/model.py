@@ -31,10 +31,10 @@ def _ptr(t: torch.Tensor) -> int:
 class _Native:
     """Owns an eab_model* and frees it with the module."""
 
-    def __init__(self, cfg: _lib.EabConfig):
+    def __init__(self, cfg, creator: str = "eab_create"):
         self.lib = _lib.load()
         self.h = C.c_void_p()
-        _lib.check(self.lib.eab_create(C.byref(cfg), C.byref(self.h)), "eab_create")
+        _lib.check(getattr(self.lib, creator)(C.byref(cfg), C.byref(self.h)), creator)
 
     def __del__(self):
         try:
@@ -55,33 +55,21 @@ class _Native:
         return out
 
 
-class EaBNet(nn.Module):
-    def __init__(self, k1: tuple = (2, 3), k2: tuple = (1, 3), c: int = 64, M: int = 9, embed_dim: int = 64,
-                 kd1: int = 5, cd1: int = 64, d_feat: int = 256, p: int = 6, q: int = 3, is_causal: bool = True,
-                 is_u2: bool = True, bf_type: str = "lstm", topo_type: str = "mimo", intra_connect: str = "cat",
-                 norm_type: str = "IN"):
-        super().__init__()
-        self.k1, self.k2, self.c, self.M, self.embed_dim = tuple(k1), tuple(k2), c, M, embed_dim
-        self.kd1, self.cd1, self.d_feat, self.p, self.q = kd1, cd1, d_feat, p, q
-        self.is_causal, self.is_u2, self.bf_type = is_causal, is_u2, bf_type
-        self.intra_connect, self.topo_type, self.norm_type = intra_connect, topo_type, norm_type
-        if norm_type == "cLN":
-            # the reference raises a TypeError here as well (NormSwitch passes a string as num_features)
-            raise TypeError("norm_type 'cLN' cannot be constructed (EaBNet.py:689,691)")
-        for val, table, what in ((bf_type, _BF, "bf_type"), (topo_type, _TOPO, "topo_type"),
-                                 (intra_connect, _INTRA, "intra_connect"), (norm_type, _NORM, "norm_type")):
-            if val not in table:
-                raise ValueError("unknown %s %r" % (what, val))
-        cfg = _lib.EabConfig(self.k1[0], self.k1[1], self.k2[0], self.k2[1], c, M, embed_dim, kd1, cd1, d_feat, p, q,
-                             int(bool(is_causal)), int(bool(is_u2)), _BF[bf_type], _TOPO[topo_type],
-                             _INTRA[intra_connect], _NORM[norm_type], N_FREQ)
-        object.__setattr__(self, "_native", _Native(cfg))
-        object.__setattr__(self, "_table", self._native.param_table())
+class _NativeModule(nn.Module):
+    """nn.Module whose parameter tree is declared by a native handle's state_dict table (shared by EaBNet and GaGNet)."""
+
+    def _setup_native(self, native: "_Native") -> None:
+        object.__setattr__(self, "_native", native)
+        object.__setattr__(self, "_table", native.param_table())
         object.__setattr__(self, "_packed_key", None)
         object.__setattr__(self, "_ws", None)
         object.__setattr__(self, "_pack_device", None)
         for name, shape, kind, fan in self._table:
             self._register(name, self._init_tensor(shape, kind, fan), is_buffer=kind in (8, 9, 10))
+
+    @property
+    def _is_bn(self) -> bool:
+        return getattr(self, "norm_type", "IN") == "BN"
 
     # ---------------------------------------------------------------- parameter tree
     @staticmethod
@@ -161,6 +149,62 @@ class EaBNet(nn.Module):
                                "torch.no_grad() / torch.inference_mode()")
         if self.norm_type == "BN" and self.training:
             raise RuntimeError("norm_type='BN' is supported in eval() mode only (running statistics)")
+
+    # ---------------------------------------------------------------- introspection for tests / bench
+    def last_launch_count(self) -> int:
+        return int(self._native.lib.eab_last_launch_count(self._native.h))
+
+    def set_option(self, name: str, value: int) -> None:
+        """kernel-selection / precision knobs of the native path (see include/eabnet_b200.h: eab_set_option)"""
+        _lib.check(self._native.lib.eab_set_option(self._native.h, name.encode(), int(value)), "eab_set_option")
+
+    def profile(self, on) -> None:
+        """switch per-launch CUDA-event timing on/off for this thread's launches (2 = one entry per launch)"""
+        _lib.check(self._native.lib.eab_profile_enable(self._native.h, int(on)))
+
+    def profile_summary(self) -> list:
+        """[{kernel, launches, ms, flops, bytes}] since the last call (synchronises the device)"""
+        import json
+        buf = C.create_string_buffer(1 << 18)
+        n = self._native.lib.eab_profile_summary(self._native.h, buf, len(buf))
+        if n < 0:
+            _lib.check(1, "eab_profile_summary")
+        return json.loads(buf.value.decode())
+
+    def debug_tap(self, name: str, shape: Tuple[int, ...]) -> torch.Tensor:
+        """Named intermediate of the last forward (normalised + activated), channels-last [B,T,F',C']."""
+        dev = self._pack_device
+        dst = torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            n = self._native.lib.eab_debug_tap(self._native.h, name.encode(), _ptr(dst), dst.numel(),
+                                               torch.cuda.current_stream(dev).cuda_stream)
+        if n != dst.numel():
+            raise RuntimeError("debug_tap(%s): got %d elements, expected %d (%s)" % (
+                name, n, dst.numel(), (self._native.lib.eab_last_error() or b"").decode()))
+        return dst
+
+
+class EaBNet(_NativeModule):
+    def __init__(self, k1: tuple = (2, 3), k2: tuple = (1, 3), c: int = 64, M: int = 9, embed_dim: int = 64,
+                 kd1: int = 5, cd1: int = 64, d_feat: int = 256, p: int = 6, q: int = 3, is_causal: bool = True,
+                 is_u2: bool = True, bf_type: str = "lstm", topo_type: str = "mimo", intra_connect: str = "cat",
+                 norm_type: str = "IN"):
+        super().__init__()
+        self.k1, self.k2, self.c, self.M, self.embed_dim = tuple(k1), tuple(k2), c, M, embed_dim
+        self.kd1, self.cd1, self.d_feat, self.p, self.q = kd1, cd1, d_feat, p, q
+        self.is_causal, self.is_u2, self.bf_type = is_causal, is_u2, bf_type
+        self.intra_connect, self.topo_type, self.norm_type = intra_connect, topo_type, norm_type
+        if norm_type == "cLN":
+            # the reference raises a TypeError here as well (NormSwitch passes a string as num_features)
+            raise TypeError("norm_type 'cLN' cannot be constructed (EaBNet.py:689,691)")
+        for val, table, what in ((bf_type, _BF, "bf_type"), (topo_type, _TOPO, "topo_type"),
+                                 (intra_connect, _INTRA, "intra_connect"), (norm_type, _NORM, "norm_type")):
+            if val not in table:
+                raise ValueError("unknown %s %r" % (what, val))
+        cfg = _lib.EabConfig(self.k1[0], self.k1[1], self.k2[0], self.k2[1], c, M, embed_dim, kd1, cd1, d_feat, p, q,
+                             int(bool(is_causal)), int(bool(is_u2)), _BF[bf_type], _TOPO[topo_type],
+                             _INTRA[intra_connect], _NORM[norm_type], N_FREQ)
+        self._setup_native(_Native(cfg))
 
     # ---------------------------------------------------------------- the reference contract
     def forward(self, inpt: torch.Tensor) -> torch.Tensor:
@@ -254,39 +298,6 @@ class EaBNet(nn.Module):
     def stream(self, n_streams: int, device: torch.device | str | None = None) -> "EaBNetStream":
         """Carried-state, frame-by-frame inference for `n_streams` concurrent causal streams (eab_stream_*)."""
         return EaBNetStream(self, n_streams, device)
-
-    # ---------------------------------------------------------------- introspection for tests / bench
-    def last_launch_count(self) -> int:
-        return int(self._native.lib.eab_last_launch_count(self._native.h))
-
-    def set_option(self, name: str, value: int) -> None:
-        """kernel-selection / precision knobs of the native path (see include/eabnet_b200.h: eab_set_option)"""
-        _lib.check(self._native.lib.eab_set_option(self._native.h, name.encode(), int(value)), "eab_set_option")
-
-    def profile(self, on) -> None:
-        """switch per-launch CUDA-event timing on/off for this thread's launches (2 = one entry per launch)"""
-        _lib.check(self._native.lib.eab_profile_enable(self._native.h, int(on)))
-
-    def profile_summary(self) -> list:
-        """[{kernel, launches, ms, flops, bytes}] since the last call (synchronises the device)"""
-        import json
-        buf = C.create_string_buffer(1 << 18)
-        n = self._native.lib.eab_profile_summary(self._native.h, buf, len(buf))
-        if n < 0:
-            _lib.check(1, "eab_profile_summary")
-        return json.loads(buf.value.decode())
-
-    def debug_tap(self, name: str, shape: Tuple[int, ...]) -> torch.Tensor:
-        """Named intermediate of the last forward (normalised + activated), channels-last [B,T,F',C']."""
-        dev = self._pack_device
-        dst = torch.empty(shape, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            n = self._native.lib.eab_debug_tap(self._native.h, name.encode(), _ptr(dst), dst.numel(),
-                                               torch.cuda.current_stream(dev).cuda_stream)
-        if n != dst.numel():
-            raise RuntimeError("debug_tap(%s): got %d elements, expected %d (%s)" % (
-                name, n, dst.numel(), (self._native.lib.eab_last_error() or b"").decode()))
-        return dst
 
 
 class EaBNetStream:

@@ -126,6 +126,47 @@ EAB_API int  eab_stream_step(eab_model* m, void* state_dev, size_t state_bytes, 
 EAB_API int  eab_stream_step_spec(eab_model* m, void* state_dev, size_t state_bytes, const float* frame_dev,
                           float* out_frame_dev, int n_streams, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * GaGNet post-filter: what `enhance.py` runs behind EaBNet through
+ * `EaBNetWithPostNet` (EaBNet.py:127-148, GaGNet.py:5-89).  Constructor arguments of GaGNet.__init__ (GaGNet.py:6-24),
+ * same meaning.  The handle is an eab_model: the parameter table / eab_set_param / eab_commit_params / eab_set_option /
+ * eab_debug_tap / eab_destroy entry points above apply unchanged (state_dict keys are GaGNet's: `en.*`, `gags.*`). */
+typedef struct eab_gag_config {
+    int cin;             /* 2     real/imag planes of each of the two inputs (only 2 runs in the reference)   */
+    int k1_t, k1_f;      /* (2,3) */
+    int k2_t, k2_f;      /* (1,3) */
+    int c;               /* 64    */
+    int kd1;             /* 3     */
+    int cd1;             /* 64    */
+    int d_feat;          /* 256   */
+    int p;               /* 2     TCM groups per branch                                                      */
+    int q;               /* 3     glance-gaze modules                                                        */
+    int n_dilas;         /* 4     */
+    int dilas[8];        /* 1,2,5,9 */
+    int fft_num;         /* 320   */
+    int is_u2;           /* 1     */
+    int is_causal;       /* 1     */
+    int is_squeezed;     /* 0     one TCM stack shared by the real / imaginary residual branches             */
+    int acti_type;       /* 0 "sigmoid", 1 "tanh", 2 "relu"  (gain activation, GaGNet.py:165-172)             */
+    int intra_connect;   /* 0 "cat", 1 "add" */
+    int norm_type;       /* 0 "IN",  1 "BN"  */
+} eab_gag_config;
+
+/* GaGNet.__init__ (GaGNet.py:50-73); pure host work like eab_create. */
+EAB_API int    eab_gag_create(const eab_gag_config* cfg, eab_model** out);
+EAB_API size_t eab_gag_workspace_bytes(const eab_model* m, int B, int T);
+/* GaGNet.forward(inpt, pre_x) (GaGNet.py:75-89).
+ *   inpt_dev      the [B,2,T,F] input read through explicit element strides (in floats) for its (b, c, t, f) axes, so
+ *                 that the reference-microphone view `noisy_stft[..., ref_mic, :]` of a [B,T,F,M,2] spectrum
+ *                 (EaBNet.py:141-142) is passed without a copy: strides (T*F*M*2, 1, F*M*2, M*2), pointer offset
+ *                 ref_mic*2.  A contiguous [B,2,T,F] tensor has strides (2*T*F, T*F, F, 1).
+ *   pre_dev       [B,2,T,F] contiguous (the layout eab_forward writes).
+ *   out_dev       [q][B,2,T,F]: every module's estimate, time-major.  The reference returns each as [B,2,F,T]
+ *                 (GaGNet.py:133,88); the host layer hands out transposed views, and `esti_stft` of
+ *                 EaBNetWithPostNet (EaBNet.py:147) is out_dev[q-1] as it lies. */
+EAB_API int    eab_gag_forward(eab_model* m, const float* inpt_dev, const int64_t inpt_strides[4], const float* pre_dev,
+                       float* out_dev, int B, int T, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Introspection used by tests and bench: number of kernels launched by the last forward/enhance call, and a
  * copy of a named intermediate of the last eab_forward ("en.0".."en.4", "tcm", "de.0".."de.3", "embed",
  * "h1", "h2", "w") with its normalisation/activation applied, channels-last [B,T,F',C'].  Returns the

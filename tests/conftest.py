@@ -26,7 +26,13 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    """EaBNet cases (tools/make_golden.py)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("gag_"))
+
+
+def gag_golden_cases():
+    """GaGNet post-filter cases (tools/make_golden_gag.py), without the wrapper case"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("gag_") and "wrapper" not in f)
 
 
 def load_golden(name):

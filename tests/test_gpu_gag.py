@@ -1,0 +1,91 @@
+"""GPU (-m gpu): the GaGNet post-filter and the EaBNetWithPostNet wrapper on the CUDA path (C ABI: eab_gag_*) against
+the committed reference golden vectors and the CPU oracle.  Tolerance: the north_star bar (max-abs 1e-3, relative to
+the output scale where random weights push it above 1)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import gag_golden_cases, load_golden
+from oracle import eabnet_oracle as O
+from oracle import gagnet_oracle as G
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+TIGHT = 1e-4        # every tensor-core layer of the post-filter runs the 3-pass fp16 split (fp32-grade)
+
+
+def _gag(cfg, variant="B", seed=0):
+    from eabnet_b200 import GaGNet
+    net = GaGNet(**cfg).eval()
+    sd = G.make_gag_weights(cfg, seed, variant)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda(), sd
+
+
+@pytest.mark.parametrize("name", gag_golden_cases())
+def test_gag_forward_matches_reference_golden(name):
+    g = load_golden(name)
+    cfg = G.make_gag_cfg(**g["cfg"])
+    net, _ = _gag(cfg, g["variant"])
+    with torch.no_grad():
+        outs = net(torch.from_numpy(g["inpt"]).cuda(), torch.from_numpy(g["pre"]).cuda())
+    assert len(outs) == cfg["q"] and tuple(outs[0].shape) == g["outs"].shape[1:]
+    got = torch.stack([o.contiguous() for o in outs]).cpu().numpy()
+    scale = max(1.0, float(np.abs(g["outs"]).max()))
+    err = np.abs(got - g["outs"]).reshape(cfg["q"], -1).max(axis=1)
+    assert (err <= TIGHT * scale).all(), err
+    assert net.last_launch_count() > 0
+
+
+@pytest.mark.parametrize("B,T", [(1, 2), (3, 50), (2, 130)])
+def test_gag_forward_matches_oracle_strided_input(B, T):
+    """other sizes / seed, with inpt handed over as the reference-microphone view of a [B,T,F,M,2] spectrum"""
+    cfg = G.make_gag_cfg()
+    net, sd = _gag(cfg, "B", seed=2)
+    g = torch.Generator().manual_seed(100 + T)
+    spec = 0.5 * torch.randn(B, T, 161, 5, 2, generator=g)
+    pre = 0.3 * torch.randn(B, 2, T, 161, generator=g)
+    view = spec[..., 3, :].permute(0, 3, 1, 2)
+    ref = torch.stack(G.gag_forward(sd, view.contiguous(), pre, cfg))
+    # conditioning of the case itself (InstanceNorm over a handful of frames is ill-conditioned): oracle fp64 vs fp32
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    ref64 = torch.stack(G.gag_forward(sd64, view.contiguous().double(), pre.double(), cfg))
+    cond = float((ref.double() - ref64).abs().max())
+    with torch.no_grad():
+        got = net.forward_time_major(spec.cuda()[..., 3, :].permute(0, 3, 1, 2), pre.cuda()).cpu()
+    got = got.transpose(-2, -1)
+    scale = max(1.0, float(ref.abs().max()))
+    err = float((got.double() - ref64).abs().max())
+    assert err <= max(TIGHT * scale, 8 * cond), (err, cond)
+
+
+def test_postnet_wrapper_matches_reference_golden():
+    from eabnet_b200 import make_eabnet_with_postnet
+    from eabnet_b200.postnet import default_postnet_args
+    g = load_golden("gag_wrapper_default_b1_t21")
+    w = make_eabnet_with_postnet(default_postnet_args()).eval()
+    w.load_state_dict(G.make_postnet_weights(None, None, 0, "B"), strict=True)
+    w.cuda()
+    with torch.no_grad():
+        r = w(torch.from_numpy(g["spec"]).cuda())
+    assert set(r) == {"esti0_stft", "esti1_stft_list", "esti_stft"}
+    scale = max(1.0, float(np.abs(g["esti"]).max()))
+    assert np.abs(r["esti0_stft"].cpu().numpy() - g["esti0"]).max() <= 4e-4
+    # the post-filter sees the beamformer estimate with its (in-tolerance) error: the bar is the contractual one
+    assert np.abs(r["esti_stft"].cpu().numpy() - g["esti"]).max() <= TOL * scale
+    stages = torch.stack([s.contiguous() for s in r["esti1_stft_list"]]).cpu().numpy()
+    assert stages.shape == g["stages"].shape
+    assert np.abs(stages - g["stages"]).max() <= TOL * scale
+
+
+def test_gag_batch_items_independent_and_repeatable():
+    cfg = G.make_gag_cfg()
+    net, _ = _gag(cfg)
+    g = torch.Generator().manual_seed(9)
+    x, pre = torch.randn(3, 2, 40, 161, generator=g).cuda(), torch.randn(3, 2, 40, 161, generator=g).cuda()
+    with torch.no_grad():
+        a = net.forward_time_major(x, pre)
+        b = net.forward_time_major(x, pre)
+        c = net.forward_time_major(x[1:2], pre[1:2])
+    assert torch.equal(a, b)
+    assert float((a[:, 1:2] - c).abs().max()) <= 1e-5 * max(1.0, float(a.abs().max()))
