@@ -2061,6 +2061,52 @@ int eab_enhance(eab_model* m, const float* wave, float* enhanced, int B, int L, 
     return rc;
 }
 
+// enhance.py:49-62 on device buffers: STFT + compression, EaBNet, GaGNet on (reference microphone, EaBNet estimate), iSTFT
+// of the last glance-gaze module's estimate.
+size_t eab_enhance_postnet_workspace_bytes(const eab_model* eab, const eab_model* gag, int B, int L) {
+    if (!eab || !gag || eab->kind != 0 || gag->kind != 1 || B < 1 || L < 161) return 0;
+    const int T = 1 + L / 160;
+    const size_t f1 = eab_workspace_bytes(eab, B, T), f2 = eab_workspace_bytes(gag, B, T);
+    if (!f1 || !f2) return 0;
+    const size_t spec = align256((size_t)B * T * eab->cfg.n_freq * eab->cfg.M * 2 * sizeof(float));
+    const size_t est = align256((size_t)B * 2 * T * eab->cfg.n_freq * sizeof(float));
+    return spec + est * (1 + gag->cfg.q) + std::max(f1, f2);
+}
+
+int eab_enhance_postnet(eab_model* eab, eab_model* gag, int ref_mic, const float* wave, float* enhanced, int B, int L, void* ws,
+                        size_t ws_bytes, void* stream) {
+    if (!eab || !gag || !wave || !enhanced || !ws) return fail("eab_enhance_postnet: null argument");
+    if (eab->kind != 0 || gag->kind != 1) return fail("eab_enhance_postnet: needs an EaBNet handle and a GaGNet handle");
+    if (eab->cfg.topo_type == 1) return fail("eab_enhance_postnet: the 'miso' topology returns [B,2,T]");
+    if (eab->cfg.n_freq != 161 || gag->cfg.n_freq != 161) return fail("eab_enhance_postnet: the 320-point STFT gives 161 bins");
+    if (ref_mic < 0 || ref_mic >= eab->cfg.M) return fail("eab_enhance_postnet: ref_mic out of range");
+    const size_t need = eab_enhance_postnet_workspace_bytes(eab, gag, B, L);
+    if (!need) return fail("eab_enhance_postnet: bad shape");
+    if (ws_bytes < need) return fail("workspace too small: need " + std::to_string(need) + " bytes");
+    const int T = 1 + L / 160, F = 161, M = eab->cfg.M;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* p = static_cast<char*>(ws);
+    float* spec = reinterpret_cast<float*>(p);
+    p += align256((size_t)B * T * F * M * 2 * sizeof(float));
+    const size_t est = align256((size_t)B * 2 * T * F * sizeof(float));
+    float* est0 = reinterpret_cast<float*>(p);
+    p += est;
+    float* stages = reinterpret_cast<float*>(p);
+    p += est * gag->cfg.q;
+    // (the q estimates are written back to back, B*2*T*F floats each; only the last one is read here)
+    const size_t rest = ws_bytes - (size_t)(p - static_cast<char*>(ws));
+    reset_launch_count();
+    int rc = launch_stft(wave, spec, B, M, L, st);
+    if (!rc) rc = forward(eab, spec, est0, B, T, p, rest, st);
+    const long long strides[4] = {(long long)T * F * M * 2, 1, (long long)F * M * 2, (long long)M * 2};
+    if (!rc) rc = gag_forward(gag, spec + (size_t)ref_mic * 2, strides, est0, stages, B, T, p, rest, st);
+    if (!rc) rc = launch_istft(stages + (size_t)(gag->cfg.q - 1) * B * 2 * T * F, enhanced, B, T, st);
+    const int n = launch_count();
+    eab->last_launches = n;
+    gag->last_launches = n;
+    return rc;
+}
+
 // Host front door.  Batch i+1 is uploaded (copy stream) and batch i-1 downloaded (second copy stream) while batch i
 // computes on the caller's stream: two device input slots, two output slots, one workspace.
 int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float* const* enhanced_host, int n_batches,

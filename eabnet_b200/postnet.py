@@ -115,6 +115,30 @@ class EaBNetWithPostNet(nn.Module):
                 "esti1_stft_list": [tm[i].transpose(-2, -1) for i in range(self.postnet.q)],
                 "esti_stft": tm[-1]}
 
+    def enhance(self, wave: torch.Tensor) -> torch.Tensor:
+        """wave [B,M,L] on the GPU -> enhanced [B,160*(L//160)]: the enhance.py:35-62 sequence (STFT + compression,
+        beamformer, post-filter, iSTFT of `esti_stft`) as one native call (eab_enhance_postnet)."""
+        e, g = self.eabnet, self.postnet
+        e._check_input(wave, "wave")
+        B, M, L = wave.shape
+        if M != e.M:
+            raise RuntimeError("expected %d microphones, got %d" % (e.M, M))
+        dev = wave.device
+        x = wave.contiguous()
+        with torch.cuda.device(dev):
+            e._sync_params(dev)
+            g._sync_params(dev)
+            lib = e._native.lib
+            nbytes = lib.eab_enhance_postnet_workspace_bytes(e._native.h, g._native.h, B, L)
+            if nbytes == 0:
+                _lib.check(1, "eab_enhance_postnet_workspace_bytes")
+            ws = e._workspace(nbytes, dev)
+            out = torch.empty((B, 160 * (L // 160)), dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.eab_enhance_postnet(e._native.h, g._native.h, int(self.ref_mic), _ptr(x), _ptr(out), B, L, _ptr(ws),
+                                               ws.numel(), stream), "eab_enhance_postnet")
+        return out
+
     def freeze_eabnet(self):
         for param in self.eabnet.parameters():
             param.requires_grad = False

@@ -167,6 +167,12 @@ EAB_API size_t eab_gag_workspace_bytes(const eab_model* m, int B, int T);
 EAB_API int    eab_gag_forward(eab_model* m, const float* inpt_dev, const int64_t inpt_strides[4], const float* pre_dev,
                        float* out_dev, int B, int T, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* enhance.py:49-62 on device buffers: wave [B,M,L] -> STFT + compression -> EaBNet -> GaGNet on (microphone `ref_mic`,
+ * EaBNet's estimate) -> iSTFT of the last module's estimate -> enhanced [B,160*(L/160)]. */
+EAB_API size_t eab_enhance_postnet_workspace_bytes(const eab_model* eabnet, const eab_model* gagnet, int B, int L);
+EAB_API int    eab_enhance_postnet(eab_model* eabnet, eab_model* gagnet, int ref_mic, const float* wave_dev,
+                           float* enhanced_dev, int B, int L, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Introspection used by tests and bench: number of kernels launched by the last forward/enhance call, and a
  * copy of a named intermediate of the last eab_forward ("en.0".."en.4", "tcm", "de.0".."de.3", "embed",
  * "h1", "h2", "w") with its normalisation/activation applied, channels-last [B,T,F',C'].  Returns the

@@ -89,3 +89,25 @@ def test_gag_batch_items_independent_and_repeatable():
         c = net.forward_time_major(x[1:2], pre[1:2])
     assert torch.equal(a, b)
     assert float((a[:, 1:2] - c).abs().max()) <= 1e-5 * max(1.0, float(a.abs().max()))
+
+
+def test_postnet_enhance_wave_to_wave_matches_oracle():
+    """eab_enhance_postnet (enhance.py:35-62 as one call) == oracle STFT -> EaBNet -> GaGNet -> iSTFT"""
+    from eabnet_b200 import make_eabnet_with_postnet
+    from eabnet_b200.postnet import default_postnet_args
+    w = make_eabnet_with_postnet(default_postnet_args(ref_mic=2)).eval()
+    sd = G.make_postnet_weights(None, None, 1, "B")
+    w.load_state_dict(sd, strict=True)
+    w.cuda()
+    wave, clean = O.make_wave(2, 9, 8000, seed=77)
+    r = G.postnet_forward(sd, O.stft_compress(wave), O.make_cfg(), G.make_gag_cfg(), ref_mic=2)
+    ref = O.istft(r["esti_stft"].contiguous())
+    with torch.no_grad():
+        got = w.enhance(wave.cuda()).cpu()
+        spec_out = w(O.stft_compress(wave).cuda())["esti_stft"].cpu()
+    scale = max(1.0, float(r["esti_stft"].abs().max()))
+    assert float((spec_out - r["esti_stft"]).abs().max()) <= TOL * scale
+    assert got.shape == ref.shape == (2, 8000)
+    assert float((got - ref).abs().max()) <= TOL * max(1.0, float(ref.abs().max()))
+    for b in range(2):
+        assert abs(O.si_sdr(clean[b].numpy(), got[b].numpy()) - O.si_sdr(clean[b].numpy(), ref[b].numpy())) <= 0.05
