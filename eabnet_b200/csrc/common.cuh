@@ -365,6 +365,35 @@ struct HeadArgs {
 bool head_fused_supported(const HeadArgs& a);
 int launch_head_fused(const HeadArgs& a, cudaStream_t st);
 
+// A chain of single-branch squeezed TCMs (GaGNet) as one persistent cooperative launch (tcm_chain.cu).  Offsets are in
+// floats into the weight blob / in doubles into the statistics arena.
+constexpr int kMaxChainLayers = 24;
+struct TcmChainLayer {
+    unsigned win_hi, win_lo;             // [4 slabs][64 rows][64 k] fp16 images of the 1x1 squeeze (hi / lo)
+    unsigned wd_hi, wd_lo;               // [kd taps][64 rows][64 k] dilated conv
+    unsigned wo_hi[2], wo_lo[2];         // 2 x [128 rows][64 k] 1x1 expand
+    unsigned sc_d, sh_d, al_d;           // norm gamma / beta (or folded BatchNorm scale / shift) and PReLU slope in front of the dilated conv
+    unsigned sc_o, sh_o, al_o;           // ... in front of the expand conv
+    unsigned st_d, st_o;                 // [B][64][2] statistics accumulators (InstanceNorm)
+    short dt[8];                         // tap k reads frame t - dt[k]
+};
+struct TcmChainArgs {
+    const float* blob;
+    double* stats;
+    unsigned* barrier;                   // zeroed grid-barrier counter
+    const float* x_in[3];                // [B][T][256] chain inputs (read by the first layer only)
+    float* x_buf[3];                     // [B][T][256] residual streams (chain outputs)
+    float* y[3];                         // [B][T][64] scratch
+    float* z[3];
+    int nchains, nlayers, kd;
+    int B, T, tiles_per_b;
+    int instance_norm;
+    float inv_count;                     // 1 / T
+    TcmChainLayer L[kMaxChainLayers];    // [chain][layer]
+};
+bool tcm_chain_supported(const TcmChainArgs& a);
+int launch_tcm_chain(const TcmChainArgs& a, cudaStream_t st);
+
 // GaGNet post-filter glue (gag_elementwise.cu)
 struct GagPackArgs {
     const float* inpt;           // reference-microphone spectrum, element (b, c, t, f) at b*sb + c*sc + t*st + f*sf (floats)

@@ -239,6 +239,7 @@ struct eab_model {
     int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
+    int opt_tcm_chain = 1;        // GaGNet: every TCM stack of a glance-gaze module as one cooperative launch (tcm_chain.cu)
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
     int opt_plane = 1;            // "stage once, shift by descriptor" kernel with fused producers (fallback)
     int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
@@ -1731,6 +1732,67 @@ int run_gag_lin(Ctx& cx, const GagLin& l, const Act& x, Act* out) {
                          out, &l.u);
 }
 
+// 1-3 equally long chains of single-branch TCMs as one cooperative launch (tcm_chain.cu)
+bool tcm_chain_ok(Ctx& cx, const std::vector<TcmLayer>* const* chains, int nch) {
+    const eab_config& c = cx.m->cfg;
+    if (!cx.m->opt_tcm_chain || !cx.tensor_ok() || c.cd1 != 64 || c.d_feat != 256 || c.kd1 > 4 || c.kd1 > 8) return false;
+    const size_t nl = chains[0]->size();
+    if (nl < 1 || nch < 1 || nch > 3 || nch * nl > (size_t)kMaxChainLayers) return false;
+    for (int i = 0; i < nch; ++i) {
+        if (chains[i]->size() != nl) return false;
+        for (const TcmLayer& t : *chains[i]) {
+            // (planning runs before the weights are packed: the image flags are only known once committed)
+            if (!t.single) return false;
+            if (!cx.m->dirty && !(t.u_in.ok && t.u_dil.ok && t.u_out.ok && t.u_out.nsplit == 2 && t.u_in.nslab == 4)) return false;
+            for (int k = 0; k < c.kd1; ++k) if (t.dt[k] > 30000 || t.dt[k] < -30000) return false;
+        }
+    }
+    return true;
+}
+
+int run_tcm_chains(Ctx& cx, const std::vector<TcmLayer>* const* chains, int nch, const Act* ins, Act* outs) {
+    const eab_config& c = cx.m->cfg;
+    const int nl = (int)chains[0]->size();
+    const size_t rows = (size_t)cx.B * cx.T;
+    TcmChainArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < nch; ++i) {
+        if (ins[i].xf.affine != 0 || ins[i].xf.prelu != 0 || ins[i].data2 || ins[i].half || ins[i].C != 256)
+            return fail("internal: TCM chain input must be a plain fp32 [B,T,256] tensor");
+        outs[i].F = 1; outs[i].C = c.d_feat; outs[i].xf = xform_identity();
+        outs[i].data = cx.alloc_act(rows * 256);
+        outs[i].RT = cx.last_RT;
+        a.x_in[i] = ins[i].data;
+        a.x_buf[i] = outs[i].data;
+    }
+    const size_t scope = cx.mark();
+    for (int i = 0; i < nch; ++i) { a.y[i] = cx.alloc_act(rows * 64); a.z[i] = cx.alloc_act(rows * 64); }
+    cx.release(scope);                                   // y / z die with the launch
+    const bool in_stats = c.norm_type == 0;
+    double* sbase = reinterpret_cast<double*>(cx.base);
+    a.barrier = reinterpret_cast<unsigned*>(cx.alloc_stats(1));
+    for (int i = 0; i < nch; ++i)
+        for (int l = 0; l < nl; ++l) {
+            const TcmLayer& t = (*chains[i])[l];
+            TcmChainLayer& L = a.L[i * nl + l];
+            L.win_hi = (unsigned)t.u_in.off_hi[0]; L.win_lo = (unsigned)t.u_in.off_lo[0];
+            L.wd_hi = (unsigned)t.u_dil.off_hi[0]; L.wd_lo = (unsigned)t.u_dil.off_lo[0];
+            for (int sp = 0; sp < 2; ++sp) { L.wo_hi[sp] = (unsigned)t.u_out.off_hi[sp]; L.wo_lo[sp] = (unsigned)t.u_out.off_lo[sp]; }
+            L.sc_d = (unsigned)t.na_left.off_scale; L.sh_d = (unsigned)t.na_left.off_shift; L.al_d = (unsigned)t.na_left.off_alpha;
+            L.sc_o = (unsigned)t.na_out.off_scale; L.sh_o = (unsigned)t.na_out.off_shift; L.al_o = (unsigned)t.na_out.off_alpha;
+            if (in_stats) {
+                L.st_d = (unsigned)(cx.alloc_stats(64) - sbase);
+                L.st_o = (unsigned)(cx.alloc_stats(64) - sbase);
+            }
+            for (int k = 0; k < c.kd1; ++k) L.dt[k] = (short)t.dt[k];
+        }
+    if (cx.dry) return 0;
+    a.blob = cx.m->blob; a.stats = sbase;
+    a.nchains = nch; a.nlayers = nl; a.kd = c.kd1; a.B = cx.B; a.T = cx.T;
+    a.instance_norm = in_stats ? 1 : 0; a.inv_count = 1.f / (float)cx.T;
+    return launch_tcm_chain(a, cx.st);
+}
+
 // GaGNet.forward (GaGNet.py:75-89).  inpt through strides sb, sc, st, sf (floats); pre [B,2,T,F]; out [q][B,2,T,F].
 int run_gag_forward(Ctx& cx, const float* inpt, const long long* strides, const float* pre_in, float* out_dev) {
     eab_model* m = cx.m;
@@ -1782,19 +1844,28 @@ int run_gag_forward(Ctx& cx, const float* inpt, const long long* strides, const 
         next.F = 1; next.C = KP; next.xf = xform_identity();
         next.data = last ? nullptr : cx.alloc_act((size_t)cx.B * cx.T * KP);      // outlives the module's scratch
         const size_t scope = cx.mark();
-        Act xg;
+        Act xg, xz;
         EAB_TRY(run_gag_in(cx, G.in_g, feat, pre, &xg));
+        EAB_TRY(run_gag_in(cx, G.in_z, feat, pre, &xz));
         tap(cx, ("g.in_g." + std::to_string(gi)).c_str(), xg);
-        for (const TcmLayer& t : G.tcn_g) { Act nx; EAB_TRY(run_tcm(cx, t, xg, &nx)); xg = nx; }
+        Act xr = xz, xi = xz;
+        {
+            const std::vector<TcmLayer>* chains[3] = {&G.tcn_g, &G.tcm_r, &G.tcm_i};
+            const int nch = m->gcfg.is_squeezed ? 2 : 3;
+            if (tcm_chain_ok(cx, chains, nch)) {
+                Act ins[3] = {xg, xz, xz}, outs[3];
+                EAB_TRY(run_tcm_chains(cx, chains, nch, ins, outs));
+                xg = outs[0]; xr = outs[1]; xi = nch == 3 ? outs[2] : outs[1];
+            } else {
+                for (const TcmLayer& t : G.tcn_g) { Act nx; EAB_TRY(run_tcm(cx, t, xg, &nx)); xg = nx; }
+                for (const TcmLayer& t : G.tcm_r) { Act nx; EAB_TRY(run_tcm(cx, t, xr, &nx)); xr = nx; }
+                if (m->gcfg.is_squeezed) xi = xr;
+                else for (const TcmLayer& t : G.tcm_i) { Act nx; EAB_TRY(run_tcm(cx, t, xi, &nx)); xi = nx; }
+            }
+        }
         tap(cx, ("g.tcn_g." + std::to_string(gi)).c_str(), xg);
         Act gain;
         EAB_TRY(run_gag_lin(cx, G.lin_g, xg, &gain));
-        Act xz;
-        EAB_TRY(run_gag_in(cx, G.in_z, feat, pre, &xz));
-        Act xr = xz, xi = xz;
-        for (const TcmLayer& t : G.tcm_r) { Act nx; EAB_TRY(run_tcm(cx, t, xr, &nx)); xr = nx; }
-        if (m->gcfg.is_squeezed) xi = xr;
-        else for (const TcmLayer& t : G.tcm_i) { Act nx; EAB_TRY(run_tcm(cx, t, xi, &nx)); xi = nx; }
         Act rr, ri;
         EAB_TRY(run_gag_lin(cx, G.lin_r, xr, &rr));
         EAB_TRY(run_gag_lin(cx, G.lin_i, xi, &ri));
@@ -2275,6 +2346,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "pdl") g_use_pdl = value != 0;
     else if (n == "staged") m->opt_staged = value != 0;
     else if (n == "lazy") m->opt_lazy = value != 0;
+    else if (n == "tcm_chain") m->opt_tcm_chain = value != 0;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "conv_exp") m->opt_conv_exp = value;

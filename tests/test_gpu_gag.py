@@ -111,3 +111,23 @@ def test_postnet_enhance_wave_to_wave_matches_oracle():
     assert float((got - ref).abs().max()) <= TOL * max(1.0, float(ref.abs().max()))
     for b in range(2):
         assert abs(O.si_sdr(clean[b].numpy(), got[b].numpy()) - O.si_sdr(clean[b].numpy(), ref[b].numpy())) <= 0.05
+
+
+@pytest.mark.parametrize("over", [{}, {"norm_type": "BN", "is_squeezed": True}, {"is_causal": False, "dilas": (1, 2, 4), "p": 1}])
+def test_gag_tcm_chain_kernel_agrees_with_layer_by_layer_path(over):
+    """the cooperative TCM-chain launch (default) and the per-layer stage + GEMM launches compute the same thing"""
+    cfg = G.make_gag_cfg(**over)
+    net, sd = _gag(cfg, "B", seed=4)
+    g = torch.Generator().manual_seed(11)
+    x, pre = 0.5 * torch.randn(2, 2, 150, 161, generator=g), 0.3 * torch.randn(2, 2, 150, 161, generator=g)
+    ref = torch.stack(G.gag_forward(sd, x, pre, cfg)).transpose(-2, -1)
+    with torch.no_grad():
+        a = net.forward_time_major(x.cuda(), pre.cuda()).cpu()
+        n_chain = net.last_launch_count()
+        net.set_option("tcm_chain", 0)
+        b = net.forward_time_major(x.cuda(), pre.cuda()).cpu()
+        n_layer = net.last_launch_count()
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((a - ref).abs().max()) <= TIGHT * scale
+    assert float((b - ref).abs().max()) <= TIGHT * scale
+    assert n_chain < n_layer
