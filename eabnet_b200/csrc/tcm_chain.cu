@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
             const float* xsrc = (l == 0 ? a.x_in[chain] : a.x_buf[chain]);
             const int t = t0 + lrow;
             const float* xrow = xsrc + ((size_t)b * a.T + t) * 256 + lhalf * 32;
-            for (int s = 0; s < 4; ++s) {
-                float v[32];
+            float v[32];
+            auto load_x = [&](int s) {
                 if (t < a.T) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(&v[k * 4]) = ldcg4(xrow + s * 64 + k * 4);
@@ -228,8 +228,12 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.f;
                 }
+            };
+            load_x(0);
+            for (int s = 0; s < 4; ++s) {
                 if (s > 0) wait_mma();                     // the previous slab's MMAs have read As
                 store_operand(As, lrow, lhalf, v);
+                if (s < 3) load_x(s + 1);                  // in flight while this slab's MMAs run
                 issue(idesc64, s * 64 * 128, s == 0);
             }
             wait_mma();
@@ -252,13 +256,20 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
             load_coef(a.stats + L.st_d, b, L.sc_d, L.sh_d, L.al_d);
             __syncthreads();
             const int t = t0 + lrow;
-            for (int k = 0; k < a.kd; ++k) {
+            float v[32];
+            bool ok = false;
+            auto load_y = [&](int k) {
                 const int ts = t - L.dt[k];
-                float v[32];
-                if (t < a.T && ts >= 0 && ts < a.T) {
+                ok = t < a.T && ts >= 0 && ts < a.T;
+                if (ok) {
                     const float* yrow = a.y[chain] + ((size_t)b * a.T + ts) * 64 + lhalf * 32;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = ldcg4(yrow + q * 4);
+                }
+            };
+            load_y(0);
+            for (int k = 0; k < a.kd; ++k) {
+                if (ok) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int c = lhalf * 32 + i;
@@ -270,6 +281,7 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
                 }
                 if (k > 0) wait_mma();
                 store_operand(As, lrow, lhalf, v);
+                if (k + 1 < a.kd) load_y(k + 1);           // in flight while this tap's MMAs run
                 issue(idesc64, k * 64 * 128, k == 0);
             }
             wait_mma();
@@ -319,22 +331,31 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
                 const float* xsrc = (l == 0 ? a.x_in[chain] : a.x_buf[chain]) + ((size_t)b * a.T + t) * 256 + chalf * 128;
                 float* xdst = a.x_buf[chain] + ((size_t)b * a.T + t) * 256 + chalf * 128;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 128);
+                float4 xr[2][4];                   // residual of the next 16 columns in flight while this group is added / stored
+                auto load_res = [&](int g, float4 (&dst)[4]) {
+                    if (valid) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t rv[4][8];
+                        for (int k = 0; k < 4; ++k) dst[k] = ldcg4(xsrc + g * 16 + k * 4);
+                    }
+                };
+                load_res(0, xr[0]);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tmem_ld8_nowait(taddr + g * 32 + k * 8, rv[k]);
+                for (int g = 0; g < 8; ++g) {
+                    uint32_t rv[2][8];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) tmem_ld8_nowait(taddr + g * 16 + k * 8, rv[k]);
+                    if (g < 7) load_res(g + 1, xr[(g + 1) & 1]);
                     tmem_wait_ld();
                     if (valid) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float4 x0 = ldcg4(xsrc + g * 32 + k * 8), x1 = ldcg4(xsrc + g * 32 + k * 8 + 4);
+                        for (int k = 0; k < 2; ++k) {
+                            const float4 x0 = xr[g & 1][2 * k], x1 = xr[g & 1][2 * k + 1];
                             float o[8];
                             o[0] = __uint_as_float(rv[k][0]) + x0.x; o[1] = __uint_as_float(rv[k][1]) + x0.y;
                             o[2] = __uint_as_float(rv[k][2]) + x0.z; o[3] = __uint_as_float(rv[k][3]) + x0.w;
                             o[4] = __uint_as_float(rv[k][4]) + x1.x; o[5] = __uint_as_float(rv[k][5]) + x1.y;
                             o[6] = __uint_as_float(rv[k][6]) + x1.z; o[7] = __uint_as_float(rv[k][7]) + x1.w;
-                            st_global_256(xdst + g * 32 + k * 8, o);
+                            st_global_256(xdst + g * 16 + k * 8, o);
                         }
                     }
                 }
@@ -362,6 +383,7 @@ int launch_tcm_chain(const TcmChainArgs& a_in, cudaStream_t st) {
     static int max_ctas = 0;
     if (!max_ctas) {
         EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int dev = 0, sms = 0, per_sm = 0, coop = 0;
         EAB_CUDA(cudaGetDevice(&dev));
         EAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
