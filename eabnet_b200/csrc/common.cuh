@@ -389,6 +389,7 @@ struct TcmChainArgs {
     int B, T, tiles_per_b;
     int instance_norm;
     float inv_count;                     // 1 / T
+    unsigned long long* dbg;             // optional [16] cycle counters of CTA 0 (diagnostics), else null
     TcmChainLayer L[kMaxChainLayers];    // [chain][layer]
 };
 bool tcm_chain_supported(const TcmChainArgs& a);

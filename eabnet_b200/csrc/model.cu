@@ -1790,6 +1790,19 @@ int run_tcm_chains(Ctx& cx, const std::vector<TcmLayer>* const* chains, int nch,
     a.blob = cx.m->blob; a.stats = sbase;
     a.nchains = nch; a.nlayers = nl; a.kd = c.kd1; a.B = cx.B; a.T = cx.T;
     a.instance_norm = in_stats ? 1 : 0; a.inv_count = 1.f / (float)cx.T;
+    if (cx.m->opt_dbg_launch == -200 && cx.m->dbg_buf) a.dbg = cx.m->dbg_buf;
+    if (cx.m->opt_tcm_chain == 2 && nch > 1) {
+        // one chain per launch: a single chain's residual stream + scratch (59 MB at 64 x 6 s) stays in the 126 MB L2
+        for (int i = 0; i < nch; ++i) {
+            TcmChainArgs s = a;
+            s.nchains = 1;
+            s.x_in[0] = a.x_in[i]; s.x_buf[0] = a.x_buf[i]; s.y[0] = a.y[i]; s.z[0] = a.z[i];
+            for (int l = 0; l < nl; ++l) s.L[l] = a.L[i * nl + l];
+            s.barrier = a.barrier + 4 * i;
+            EAB_TRY(launch_tcm_chain(s, cx.st));
+        }
+        return 0;
+    }
     return launch_tcm_chain(a, cx.st);
 }
 
@@ -2346,7 +2359,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "pdl") g_use_pdl = value != 0;
     else if (n == "staged") m->opt_staged = value != 0;
     else if (n == "lazy") m->opt_lazy = value != 0;
-    else if (n == "tcm_chain") m->opt_tcm_chain = value != 0;
+    else if (n == "tcm_chain") m->opt_tcm_chain = value;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "conv_exp") m->opt_conv_exp = value;

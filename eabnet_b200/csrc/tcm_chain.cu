@@ -12,8 +12,13 @@
 // InstanceNorm needs the statistics of ALL frames of a batch item (and phase B reads rows written by other CTAs), so
 // A->B and B->C are grid-wide barriers (a counter in the workspace; the launch is cooperative, so every CTA is
 // resident); C -> next layer's A needs none.  Up to three independent chains (glance, gaze-real, gaze-imaginary) share
-// a launch so that 3 x B x ceil(T/128) tiles fill the 2 x 148 resident CTAs.  All GEMMs are 3-pass fp16 splits
+// a launch so that 3 x B x ceil(T/128) tiles fill the 148 persistent CTAs evenly.  All GEMMs are 3-pass fp16 splits
 // (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM): fp32-grade, like the layer-by-layer path.
+// One 512-thread CTA per SM.  A tile's whole operand (4 K slabs in phase A, one per tap in phase B) is staged at once,
+// so a tile-phase is one memory round trip, one block barrier, one convergent burst of MMAs and one accumulator wait
+// (the first version staged slab by slab with 8 warps per SM: every slab exposed a full L2 / HBM round trip, 19 us per
+// tile-phase; a version that kept the NEXT tile's rows in flight in registers across the epilogue spilled 1.3 KB per
+// thread at the 128-register cap of a 512-thread CTA and was slower still - profiles/r01_v6_chain_*).
 // Everything that crosses CTAs inside the launch (x, y, z, statistics) is read with ld.global.cg (L2): L1 is not
 // coherent across SMs.
 #include "common.cuh"
@@ -26,11 +31,18 @@ namespace {
 using namespace umma;
 
 constexpr int TM = 128;
-constexpr int NT = 256;
+constexpr int NT = 512;
+constexpr int TPR = NT / TM;                   // loader threads per operand row = epilogue column groups
+constexpr int CPT = 64 / TPR;                  // channels of a 64-channel slab per loader thread / accumulator columns of N = 64 per epilogue thread
+constexpr int CF4 = CPT / 4;                   // ... in float4
 constexpr int SLAB = TM * 128;                 // one 64-channel fp16 K slab of an A operand (16 KB)
-constexpr int A_BYTES = 2 * SLAB;              // hi | lo
+constexpr int A_UNIT = 2 * SLAB;               // hi | lo of one slab
+constexpr int A_UNITS = 4;                     // phase A: 4 channel slabs; phase B: one unit per tap (kd <= 4); phase C: 1
+constexpr int A_BYTES = A_UNITS * A_UNIT;      // 128 KB
 constexpr int W_BYTES = 64 * 1024;             // phase A: 4 slabs x (hi 8 KB | lo 8 KB); B: taps; C: 256 rows x (hi | lo)
 constexpr int W_HALF = W_BYTES / 2;
+// 194.3 KB: stays under the 196 KB shared-memory carve-out step, which leaves the L1 (register spills, weights) its ~60 KB;
+// a version with 5 KB more shared memory dropped to the next step and ran 25 % slower
 constexpr int SMEM_BYTES = A_BYTES + W_BYTES + (3 * 64 + 2 * 64) * 4 + 64 + 1024;
 
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
@@ -44,7 +56,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
             unsigned v;
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             if (v >= target) break;
-            __nanosleep(64);
+            __nanosleep(32);
             if (++spins > (1u << 26)) __trap();          // a protocol bug must fault, never hang the GPU
         }
         __threadfence();
@@ -52,10 +64,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     __syncthreads();
 }
 
-// column sums over the 32 lanes of a warp: lane l ends with the total of v[l] (31 shuffles instead of 160)
-__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+// column sums over the 32 lanes of a warp for 8 columns per lane: every lane ends with the total of column lane & 7
+// (halving butterfly: 7 + 2 shuffles instead of 5 per column)
+__device__ __forceinline__ float warp_column_sums8(float (&v)[8], int lane) {
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
+    for (int s = 4; s >= 1; s >>= 1) {
         const bool up = (lane & s) != 0;
 #pragma unroll
         for (int i = 0; i < s; ++i) {
@@ -64,35 +77,39 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
             v[i] = mine + __shfl_xor_sync(0xffffffffu, other, s);
         }
     }
-    return v[0];
+    float r = v[0];
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    return r;
 }
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// 32 fp32 values of one operand row -> fp16 hi / lo, written as four 16-byte chunks of the 128-byte swizzled row
-__device__ __forceinline__ void store_operand(uint8_t* A, int row, int half, const float (&v)[32]) {
-    uint8_t* hi_row = A + row * 128;
+// CPT fp32 values (channels q*CPT .. of a 64-channel slab row) -> fp16 hi / lo, 16-byte chunks of the swizzled row
+__device__ __forceinline__ void store_part(uint8_t* unit, int row, int q, const float (&v)[CPT]) {
+    uint8_t* hi_row = unit + row * 128;
     uint8_t* lo_row = hi_row + SLAB;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < CPT / 8; ++k) {
         const float* p = v + k * 8;
         uint4 hi, lo;
         hi.x = pack_h2(p[0], p[1]); hi.y = pack_h2(p[2], p[3]); hi.z = pack_h2(p[4], p[5]); hi.w = pack_h2(p[6], p[7]);
         lo.x = pack_lo_h2(p[0], p[1], hi.x); lo.y = pack_lo_h2(p[2], p[3], hi.y);
         lo.z = pack_lo_h2(p[4], p[5], hi.z); lo.w = pack_lo_h2(p[6], p[7], hi.w);
-        const int off = ((half * 4 + k) ^ (row & 7)) << 4;
+        const int off = ((q * (CPT / 8) + k) ^ (row & 7)) << 4;
         *reinterpret_cast<uint4*>(hi_row + off) = hi;
         *reinterpret_cast<uint4*>(lo_row + off) = lo;
     }
 }
 
-__global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) {
+template <int KD>
+__global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* As = smem;
     uint8_t* Ws = smem + A_BYTES;
     float* coef = reinterpret_cast<float*>(Ws + W_BYTES);        // [3][64] scale, shift, PReLU slope of the consumer's transform
-    float* sstat = coef + 3 * 64;                                // [2][64] per-tile column sums
+    float* sstat = coef + 3 * 64;                      // [2][64] per-tile column sums
     uint64_t* bar = reinterpret_cast<uint64_t*>(sstat + 2 * 64);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -112,31 +129,42 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
 
     uint32_t par = 0;                  // parity of the next completion of `bar`
     unsigned bar_target = 0;
-    // loader role: 2 threads per operand row; epilogue role: thread = (TMEM lane = row, column half)
-    const int lrow = tid >> 1, lhalf = tid & 1;
-    const int quad = warp & 3, chalf = warp >> 2;
+    // loader role: TPR threads per operand row (CPT channels of every slab each); epilogue role: thread = (TMEM lane = row,
+    // column group cg of TPR)
+    const int lrow = tid / TPR, lq = tid % TPR;
+    const int quad = warp & 3, cg = warp >> 2;
     const int erow = quad * 32 + lane;
     const uint32_t idesc64 = make_idesc(64), idesc256 = make_idesc(256);
 
-    // one K slab (already in As) against weight slab `wslab` (hi at Ws + wslab*stride, lo at + W_HALF): 3 passes x 4 K steps
-    auto issue = [&](uint32_t idesc, int w_off, bool first) {
+    struct TileId { int chain, b, t0; };
+    auto tile_of = [&](int ti) {
+        TileId t;
+        t.chain = ti / tiles_per_chain;
+        const int rem = ti - t.chain * tiles_per_chain;
+        t.b = rem / a.tiles_per_b;
+        t.t0 = (rem - t.b * a.tiles_per_b) * TM;
+        return t;
+    };
+
+    // `units` K slabs in As against `units` weight slabs of `w_stride` bytes (hi at Ws, lo at Ws + W_HALF): per slab three
+    // passes (hi*hi, lo*hi, hi*lo) of four K = 16 steps, issued by warp 0 as one convergent loop
+    auto issue = [&](uint32_t idesc, int units, int w_stride) {
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc_fence_after();
-            const uint32_t ah = smem_u32(As), al = ah + SLAB;
-            const uint32_t wh = smem_u32(Ws) + (uint32_t)w_off, wl = wh + W_HALF;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_f16(tmem_base, make_desc((pass == 1 ? al : ah) + k * 32), make_desc((pass == 2 ? wl : wh) + k * 32), idesc,
-                             (!first || pass || k) ? 1u : 0u);
-            umma_commit(bar);
+            const uint32_t a0 = desc_lo(smem_u32(As)), w0 = desc_lo(smem_u32(Ws));
+            for (int u = 0; u < units; ++u) {
+                const uint32_t ah = a0 + (uint32_t)((u * A_UNIT) >> 4), al = ah + (SLAB >> 4);
+                const uint32_t wh = w0 + (uint32_t)((u * w_stride) >> 4), wl = wh + (W_HALF >> 4);
+                umma_f16_lo_elect_x4(tmem_base, ah, wh, idesc, u > 0 ? 1u : 0u);
+                umma_f16_lo_elect_x4(tmem_base, al, wh, idesc, 1u);
+                umma_f16_lo_elect_x4(tmem_base, ah, wl, idesc, 1u);
+            }
+            umma_commit_elect(bar);
         }
     };
     auto wait_mma = [&]() { mbar_wait(bar, par); par ^= 1u; };
-    // copy `bytes` of a weight image into the hi half (lo = false) or lo half of Ws at byte offset `dst_off`
     auto load_w = [&](const float* src, int dst_off, int bytes) {
         const uint4* s = reinterpret_cast<const uint4*>(src);
         uint4* d = reinterpret_cast<uint4*>(Ws + dst_off);
@@ -162,189 +190,236 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
             coef[tid] = s; coef[64 + tid] = h; coef[128 + tid] = __ldg(a.blob + off_al + tid);
         }
     };
-    // epilogue of phases A / B: 32 accumulator columns of this thread's row -> global rows + statistics of PReLU(value)
+    auto transform = [&](float (&v)[CPT]) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int c = lq * CPT + i;
+            v[i] = fmaf(prelu_f(v[i], coef[128 + c]), coef[c], coef[64 + c]);
+        }
+    };
+    // epilogue of phases A / B: CPT accumulator columns of this thread's row -> global rows + statistics of PReLU(value)
     auto epilogue64 = [&](float* dst, int b, int t0, double* stats, unsigned off_alpha) {
         const int t = t0 + erow;
         const bool valid = t < a.T;
-        float v[32];
-        {
-            uint32_t rv[4][8];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 32);
+        // 8 columns at a time: the next tile's prefetched rows stay in registers across this epilogue
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tmem_ld8_nowait(taddr + k * 8, rv[k]);
+        for (int k = 0; k < CPT / 8; ++k) {
+            uint32_t rv[8];
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * CPT + k * 8), rv);
             tmem_wait_ld();
+            float v[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rv[e]);
+            if (valid) st_global_256(dst + ((size_t)b * a.T + t) * 64 + cg * CPT + k * 8, v);
+            if (in_stats) {
+                const float* al = a.blob + off_alpha + cg * CPT + k * 8;
+                float w[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[k * 8 + e] = __uint_as_float(rv[k][e]);
-        }
-        if (valid) {
-            float* p = dst + ((size_t)b * a.T + t) * 64 + chalf * 32;
+                for (int i = 0; i < 8; ++i) { v[i] = valid ? prelu_f(v[i], __ldg(al + i)) : 0.f; w[i] = v[i]; }
+                const float s1 = warp_column_sums8(w, lane);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) st_global_256(p + k * 8, *reinterpret_cast<const float(*)[8]>(&v[k * 8]));
-        }
-        if (in_stats) {
-            float w[32];
-            const float* al = a.blob + off_alpha + chalf * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = valid ? prelu_f(v[i], __ldg(al + i)) : 0.f; w[i] = v[i]; }
-            const float s1 = warp_column_sums(w, lane);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
-            const float s2 = warp_column_sums(w, lane);
-            atomicAdd(&sstat[chalf * 32 + lane], s1);
-            atomicAdd(&sstat[64 + chalf * 32 + lane], s2);
+                for (int i = 0; i < 8; ++i) w[i] = v[i] * v[i];
+                const float s2 = warp_column_sums8(w, lane);
+                if (lane < 8) {
+                    atomicAdd(&sstat[cg * CPT + k * 8 + lane], s1);
+                    atomicAdd(&sstat[64 + cg * CPT + k * 8 + lane], s2);
+                }
+            }
         }
         tc_fence_before();
         __syncthreads();
         if (in_stats && tid < 128) {
             const int c = tid & 63, which = tid >> 6;
             atomicAdd(stats + ((size_t)b * 64 + c) * 2 + which, (double)sstat[which * 64 + c]);
+            sstat[tid] = 0.f;                              // ready for the next tile (ordered by the barriers in between)
         }
     };
 
+    if (tid < 128) sstat[tid] = 0.f;
+
+    // diagnostics (builds with -DEAB_CHAIN_DEBUG only: the counters cost 30 registers, and at the 128-register cap of a
+    // 512-thread CTA every spilled byte goes through an L1 that is almost entirely carved out as shared memory):
+    // cycles of CTA 0 per section [0] A load+store [1] A mma [2] A epilogue [3] barrier 1 [4] B load+store [5] B mma
+    // [6] B epilogue [7] barrier 2 [8] C load+store [9] C mma [10] C epilogue [11] total [12] tiles
+#ifdef EAB_CHAIN_DEBUG
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    long long dc[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) dc[i] = 0;
+    long long tk = clock64();
+    const long long t_start = tk;
+    auto tick = [&](int slot) { if (dbg_on) { const long long n = clock64(); dc[slot] += n - tk; tk = n; } };
+#else
+    auto tick = [&](int) {};
+#endif
+
     for (int l = 0; l < a.nlayers; ++l) {
         // ======================================================================= phase A: y = W_in x
-        int loaded = -1;
-        for (int ti = tile_begin; ti < tile_end; ++ti) {
-            const int chain = ti / tiles_per_chain, rem = ti - chain * tiles_per_chain;
-            const int b = rem / a.tiles_per_b, t0 = (rem - b * a.tiles_per_b) * TM;
-            const TcmChainLayer& L = a.L[chain * a.nlayers + l];
-            if (loaded != chain) {
-                load_w(a.blob + L.win_hi, 0, 4 * 64 * 128);
-                load_w(a.blob + L.win_lo, W_HALF, 4 * 64 * 128);
-                loaded = chain;
-            }
-            if (tid < 128) sstat[tid] = 0.f;
-            const float* xsrc = (l == 0 ? a.x_in[chain] : a.x_buf[chain]);
-            const int t = t0 + lrow;
-            const float* xrow = xsrc + ((size_t)b * a.T + t) * 256 + lhalf * 32;
-            float v[32];
-            auto load_x = [&](int s) {
+        {
+            int loaded = -1;
+            float4 xv[4][CF4];                             // [slab][CPT channels] of this thread's row
+            auto fetch = [&](int ti) {
+                const TileId tl = tile_of(ti);
+                const int t = tl.t0 + lrow;
+                const float* xsrc = (l == 0 ? a.x_in[tl.chain] : a.x_buf[tl.chain]);
                 if (t < a.T) {
+                    const float* xrow = xsrc + ((size_t)tl.b * a.T + t) * 256 + lq * CPT;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(&v[k * 4]) = ldcg4(xrow + s * 64 + k * 4);
+                    for (int s = 0; s < 4; ++s)
+#pragma unroll
+                        for (int k = 0; k < CF4; ++k) xv[s][k] = ldcg4(xrow + s * 64 + k * 4);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                    for (int s = 0; s < 4; ++s)
+#pragma unroll
+                        for (int k = 0; k < CF4; ++k) xv[s][k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            load_x(0);
-            for (int s = 0; s < 4; ++s) {
-                if (s > 0) wait_mma();                     // the previous slab's MMAs have read As
-                store_operand(As, lrow, lhalf, v);
-                if (s < 3) load_x(s + 1);                  // in flight while this slab's MMAs run
-                issue(idesc64, s * 64 * 128, s == 0);
+            for (int ti = tile_begin; ti < tile_end; ++ti) {
+                fetch(ti);                                 // in flight under the weight / coefficient set-up below
+                const TileId tl = tile_of(ti);
+                const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
+                if (loaded != tl.chain) {
+                    load_w(a.blob + L.win_hi, 0, 4 * 64 * 128);
+                    load_w(a.blob + L.win_lo, W_HALF, 4 * 64 * 128);
+                    loaded = tl.chain;
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) store_part(As + s * A_UNIT, lrow, lq, *reinterpret_cast<const float(*)[CPT]>(&xv[s][0]));
+                tick(0);
+                issue(idesc64, 4, 64 * 128);
+                wait_mma();
+                tc_fence_after();
+                tick(1);
+                epilogue64(a.y[tl.chain], tl.b, tl.t0, a.stats + L.st_d, L.al_d);
+                tick(2);
             }
-            wait_mma();
-            tc_fence_after();
-            epilogue64(a.y[chain], b, t0, a.stats + L.st_d, L.al_d);
         }
         grid_barrier(a.barrier, bar_target);
+        tick(3);
         // ======================================================================= phase B: z = W_dil * norm(PReLU(y)) (dilated)
-        loaded = -1;
-        for (int ti = tile_begin; ti < tile_end; ++ti) {
-            const int chain = ti / tiles_per_chain, rem = ti - chain * tiles_per_chain;
-            const int b = rem / a.tiles_per_b, t0 = (rem - b * a.tiles_per_b) * TM;
-            const TcmChainLayer& L = a.L[chain * a.nlayers + l];
-            if (loaded != chain) {
-                load_w(a.blob + L.wd_hi, 0, a.kd * 64 * 128);
-                load_w(a.blob + L.wd_lo, W_HALF, a.kd * 64 * 128);
-                loaded = chain;
-            }
-            if (tid < 128) sstat[tid] = 0.f;
-            load_coef(a.stats + L.st_d, b, L.sc_d, L.sh_d, L.al_d);
-            __syncthreads();
-            const int t = t0 + lrow;
-            float v[32];
-            bool ok = false;
-            auto load_y = [&](int k) {
-                const int ts = t - L.dt[k];
-                ok = t < a.T && ts >= 0 && ts < a.T;
-                if (ok) {
-                    const float* yrow = a.y[chain] + ((size_t)b * a.T + ts) * 64 + lhalf * 32;
+        {
+            int loaded = -1;
+            float4 yv[KD][CF4];                            // [tap][CPT channels]
+            unsigned okmask = 0;
+            auto fetch = [&](int ti) {
+                const TileId tl = tile_of(ti);
+                const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
+                const int t = tl.t0 + lrow;
+                okmask = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = ldcg4(yrow + q * 4);
+                for (int k = 0; k < KD; ++k) {
+                    {
+                        const int ts = t - L.dt[k];
+                        if (t < a.T && ts >= 0 && ts < a.T) okmask |= 1u << k;
+                        // unconditional loads from a clamped row (zeroed below): keeps the rows in registers
+                        const int tc = ts < 0 ? 0 : (ts >= a.T ? a.T - 1 : ts);
+                        const float* yrow = a.y[tl.chain] + ((size_t)tl.b * a.T + tc) * 64 + lq * CPT;
+#pragma unroll
+                        for (int q = 0; q < CF4; ++q) yv[k][q] = ldcg4(yrow + q * 4);
+                    }
                 }
             };
-            load_y(0);
-            for (int k = 0; k < a.kd; ++k) {
-                if (ok) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = lhalf * 32 + i;
-                        v[i] = fmaf(prelu_f(v[i], coef[128 + c]), coef[c], coef[64 + c]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;        // literal zeros AFTER the norm (GaGNet.py:313)
+            for (int ti = tile_begin; ti < tile_end; ++ti) {
+                fetch(ti);                                 // in flight under the weight / coefficient set-up below
+                const TileId tl = tile_of(ti);
+                const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
+                if (loaded != tl.chain) {
+                    load_w(a.blob + L.wd_hi, 0, KD * 64 * 128);
+                    load_w(a.blob + L.wd_lo, W_HALF, KD * 64 * 128);
+                    loaded = tl.chain;
                 }
-                if (k > 0) wait_mma();
-                store_operand(As, lrow, lhalf, v);
-                if (k + 1 < a.kd) load_y(k + 1);           // in flight while this tap's MMAs run
-                issue(idesc64, k * 64 * 128, k == 0);
+                load_coef(a.stats + L.st_d, tl.b, L.sc_d, L.sh_d, L.al_d);
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < KD; ++k) {
+                    {
+                        float v[CPT];
+#pragma unroll
+                        for (int q = 0; q < CF4; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = yv[k][q];
+                        transform(v);
+                        const bool ok = (okmask >> k) & 1u;
+#pragma unroll
+                        for (int i = 0; i < CPT; ++i) v[i] = ok ? v[i] : 0.f;       // literal zeros AFTER the norm (GaGNet.py:313)
+                        store_part(As + k * A_UNIT, lrow, lq, v);
+                    }
+                }
+                tick(4);
+                issue(idesc64, KD, 64 * 128);
+                wait_mma();
+                tc_fence_after();
+                tick(5);
+                epilogue64(a.z[tl.chain], tl.b, tl.t0, a.stats + L.st_o, L.al_o);
+                tick(6);
             }
-            wait_mma();
-            tc_fence_after();
-            epilogue64(a.z[chain], b, t0, a.stats + L.st_o, L.al_o);
         }
         grid_barrier(a.barrier, bar_target);
+        tick(7);
         // ======================================================================= phase C: x += W_out * norm(PReLU(z))
-        loaded = -1;
-        for (int ti = tile_begin; ti < tile_end; ++ti) {
-            const int chain = ti / tiles_per_chain, rem = ti - chain * tiles_per_chain;
-            const int b = rem / a.tiles_per_b, t0 = (rem - b * a.tiles_per_b) * TM;
-            const TcmChainLayer& L = a.L[chain * a.nlayers + l];
-            if (loaded != chain) {
-                load_w(a.blob + L.wo_hi[0], 0, 128 * 128);
-                load_w(a.blob + L.wo_hi[1], 128 * 128, 128 * 128);
-                load_w(a.blob + L.wo_lo[0], W_HALF, 128 * 128);
-                load_w(a.blob + L.wo_lo[1], W_HALF + 128 * 128, 128 * 128);
-                loaded = chain;
-            }
-            load_coef(a.stats + L.st_o, b, L.sc_o, L.sh_o, L.al_o);
-            __syncthreads();
-            {
-                const int t = t0 + lrow;
-                float v[32];
-                if (t < a.T) {
-                    const float* zrow = a.z[chain] + ((size_t)b * a.T + t) * 64 + lhalf * 32;
+        {
+            int loaded = -1;
+            float4 zv[CF4];
+            bool zok = false;
+            auto fetch = [&](int ti) {
+                const TileId tl = tile_of(ti);
+                const int t = tl.t0 + lrow;
+                zok = t < a.T;
+                if (zok) {
+                    const float* zrow = a.z[tl.chain] + ((size_t)tl.b * a.T + t) * 64 + lq * CPT;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = ldcg4(zrow + q * 4);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = lhalf * 32 + i;
-                        v[i] = fmaf(prelu_f(v[i], coef[128 + c]), coef[c], coef[64 + c]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                    for (int q = 0; q < CF4; ++q) zv[q] = ldcg4(zrow + q * 4);
                 }
-                store_operand(As, lrow, lhalf, v);
-                issue(idesc256, 0, true);
-            }
-            wait_mma();
-            tc_fence_after();
-            {
-                const int t = t0 + erow;
+            };
+            for (int ti = tile_begin; ti < tile_end; ++ti) {
+                fetch(ti);                                 // in flight under the weight / coefficient set-up below
+                const TileId tl = tile_of(ti);
+                const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
+                if (loaded != tl.chain) {
+                    load_w(a.blob + L.wo_hi[0], 0, 128 * 128);
+                    load_w(a.blob + L.wo_hi[1], 128 * 128, 128 * 128);
+                    load_w(a.blob + L.wo_lo[0], W_HALF, 128 * 128);
+                    load_w(a.blob + L.wo_lo[1], W_HALF + 128 * 128, 128 * 128);
+                    loaded = tl.chain;
+                }
+                load_coef(a.stats + L.st_o, tl.b, L.sc_o, L.sh_o, L.al_o);
+                __syncthreads();
+                {
+                    float v[CPT];
+                    if (zok) {
+#pragma unroll
+                        for (int q = 0; q < CF4; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = zv[q];
+                        transform(v);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CPT; ++i) v[i] = 0.f;
+                    }
+                    store_part(As, lrow, lq, v);
+                }
+                tick(8);
+                issue(idesc256, 1, 0);
+                // this row's residual (256 / TPR columns of x) and the next tile's z rows: in flight under the MMAs
+                const int t = tl.t0 + erow;
                 const bool valid = t < a.T;
-                const float* xsrc = (l == 0 ? a.x_in[chain] : a.x_buf[chain]) + ((size_t)b * a.T + t) * 256 + chalf * 128;
-                float* xdst = a.x_buf[chain] + ((size_t)b * a.T + t) * 256 + chalf * 128;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 128);
-                float4 xr[2][4];                   // residual of the next 16 columns in flight while this group is added / stored
-                auto load_res = [&](int g, float4 (&dst)[4]) {
+                const float* xsrc = (l == 0 ? a.x_in[tl.chain] : a.x_buf[tl.chain]) + ((size_t)tl.b * a.T + t) * 256 + cg * (4 * CPT);
+                float* xdst = a.x_buf[tl.chain] + ((size_t)tl.b * a.T + t) * 256 + cg * (4 * CPT);
+                float4 xr[2][4];                       // residual of 16 columns, the next group in flight
+                auto load_res = [&](int g, float4 (&d)[4]) {
                     if (valid) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) dst[k] = ldcg4(xsrc + g * 16 + k * 4);
+                        for (int k = 0; k < 4; ++k) d[k] = ldcg4(xsrc + g * 16 + k * 4);
                     }
                 };
                 load_res(0, xr[0]);
+                wait_mma();
+                tc_fence_after();
+                tick(9);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 4 * CPT);
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
+                for (int g = 0; g < CPT / 4; ++g) {
                     uint32_t rv[2][8];
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) tmem_ld8_nowait(taddr + g * 16 + k * 8, rv[k]);
-                    if (g < 7) load_res(g + 1, xr[(g + 1) & 1]);
+                    tmem_ld8_nowait(taddr + g * 16, rv[0]);
+                    tmem_ld8_nowait(taddr + g * 16 + 8, rv[1]);
+                    if (g + 1 < CPT / 4) load_res(g + 1, xr[(g + 1) & 1]);
                     tmem_wait_ld();
                     if (valid) {
 #pragma unroll
@@ -359,12 +434,20 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
                         }
                     }
                 }
+                tc_fence_before();
+                __syncthreads();
+                tick(10);
             }
-            tc_fence_before();
-            __syncthreads();
         }
         // no grid barrier: the next layer's phase A reads only this CTA's own rows of x_buf (ld.cg, after the block barrier)
     }
+#ifdef EAB_CHAIN_DEBUG
+    if (dbg_on) {
+        dc[11] = clock64() - t_start;
+        dc[12] = tile_end - tile_begin;
+        for (int i = 0; i < 13; ++i) a.dbg[i] = (unsigned long long)dc[i];
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -374,25 +457,28 @@ __global__ void __launch_bounds__(NT, 2) tcm_chain_kernel(const TcmChainArgs a) 
 
 bool tcm_chain_supported(const TcmChainArgs& a) {
     return a.nchains >= 1 && a.nchains <= 3 && a.nlayers >= 1 && a.nchains * a.nlayers <= kMaxChainLayers && a.kd >= 1 &&
-           a.kd * 64 * 128 <= W_HALF && a.B >= 1 && a.T >= 1;
+           a.kd <= A_UNITS && a.kd * 64 * 128 <= W_HALF && a.B >= 1 && a.T >= 1;
 }
 
 int launch_tcm_chain(const TcmChainArgs& a_in, cudaStream_t st) {
     TcmChainArgs a = a_in;
     if (!tcm_chain_supported(a)) return fail("tcm_chain: unsupported shape");
+    const void* kernel = a.kd == 1 ? reinterpret_cast<const void*>(tcm_chain_kernel<1>)
+                       : a.kd == 2 ? reinterpret_cast<const void*>(tcm_chain_kernel<2>)
+                       : a.kd == 3 ? reinterpret_cast<const void*>(tcm_chain_kernel<3>)
+                                   : reinterpret_cast<const void*>(tcm_chain_kernel<4>);
     static int max_ctas = 0;
     if (!max_ctas) {
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        int dev = 0, sms = 0, per_sm = 0, coop = 0;
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        int dev = 0, sms = 0, coop = 0;
         EAB_CUDA(cudaGetDevice(&dev));
         EAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         EAB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         if (!coop) return fail("tcm_chain: the device does not support cooperative launches");
-        EAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tcm_chain_kernel, NT, SMEM_BYTES));
-        if (per_sm < 1) return fail("tcm_chain: kernel does not fit an SM");
-        if (per_sm > 2) per_sm = 2;                      // 256 TMEM columns per CTA
-        max_ctas = per_sm * sms;
+        max_ctas = sms;                                  // one persistent CTA per SM (194 KB of shared memory each)
     }
     a.tiles_per_b = (a.T + TM - 1) / TM;
     const long long total = (long long)a.nchains * a.B * a.tiles_per_b;
@@ -402,7 +488,7 @@ int launch_tcm_chain(const TcmChainArgs& a_in, cudaStream_t st) {
     ProfScope ps("tcm_chain", 2.0 * rows * (256.0 * 64 + a.kd * 64.0 * 64 + 64.0 * 256),
                  4.0 * rows * (256 + 64 + 64 * a.kd + 64 + 64 + 256 + 256), st);
     void* params[1] = {&a};
-    EAB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(tcm_chain_kernel), dim3(grid), dim3(NT), params,
+    EAB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(NT), params,
                                          (size_t)SMEM_BYTES, st));
     EAB_LAUNCH_CHECK("tcm_chain_kernel");
     return 0;

@@ -171,6 +171,12 @@ class _NativeModule(nn.Module):
             _lib.check(1, "eab_profile_summary")
         return json.loads(buf.value.decode())
 
+    def debug_counters(self) -> list:
+        """16 cycle counters written by the kernel launch selected with option dbg_launch (diagnostics)"""
+        buf = (C.c_uint64 * 16)()
+        _lib.check(self._native.lib.eab_debug_counters(self._native.h, C.byref(buf)), "eab_debug_counters")
+        return [int(v) for v in buf]
+
     def debug_tap(self, name: str, shape: Tuple[int, ...]) -> torch.Tensor:
         """Named intermediate of the last forward (normalised + activated), channels-last [B,T,F',C']."""
         dev = self._pack_device

@@ -20,6 +20,8 @@ t_eab = run(lambda: w.eabnet.enhance(wave))
 print("EaBNet + GaGNet wave->wave: %.2f ms/step ; EaBNet alone: %.2f ms ; post-filter: %.2f ms ; launches %d" % (
     t_all, t_eab, t_all - t_eab, w.eabnet.last_launch_count()))
 print("workspace GB", w.eabnet._ws.numel() / 1e9)
+for o in [x for x in sys.argv[1:] if "=" in x]:
+    k, v = o.split("="); w.postnet.set_option(k, int(v))
 with torch.no_grad():
     spec = torch.randn(B, 601, 161, 9, 2, device="cuda") * 0.3
     est0 = w.eabnet(spec)
@@ -33,3 +35,11 @@ for k in sorted(prof, key=lambda k: -k["ms"])[:40]:
     print("%-28s n=%4d  %8.3f ms  %5.1f%%  %8.1f GB/s  %8.1f TF/s" % (k["kernel"], k["launches"], k["ms"], 100 * k["ms"] / tot,
           k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] else 0, k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] else 0))
 print("total %.3f ms" % tot)
+if "dbg" in sys.argv:
+    w.postnet.set_option("dbg_launch", -200)
+    with torch.no_grad():
+        w.postnet.forward_time_major(inpt, est0)
+    d = w.postnet.debug_counters()
+    names = ["A load+store", "A mma", "A epilogue", "barrier1", "B load+store", "B mma", "B epilogue", "barrier2", "C load+store", "C mma", "C epilogue", "total", "tiles"]
+    for n, v in zip(names, d):
+        print("%-14s %12d cycles  %6.1f%%" % (n, v, 100.0 * v / max(d[11], 1)))
