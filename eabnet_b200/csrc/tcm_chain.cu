@@ -262,21 +262,17 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 const TileId tl = tile_of(ti);
                 const int t = tl.t0 + lrow;
                 const float* xsrc = (l == 0 ? a.x_in[tl.chain] : a.x_buf[tl.chain]);
-                if (t < a.T) {
-                    const float* xrow = xsrc + ((size_t)tl.b * a.T + t) * 256 + lq * CPT;
+                // rows past T: a clamped row is loaded and multiplied into nothing (their outputs are never stored and
+                // are excluded from the statistics), so the loads stay unconditional and in registers
+                const int tc = t < a.T ? t : a.T - 1;
+                const float* xrow = xsrc + ((size_t)tl.b * a.T + tc) * 256 + lq * CPT;
 #pragma unroll
-                    for (int s = 0; s < 4; ++s)
+                for (int s = 0; s < 4; ++s)
 #pragma unroll
-                        for (int k = 0; k < CF4; ++k) xv[s][k] = ldcg4(xrow + s * 64 + k * 4);
-                } else {
-#pragma unroll
-                    for (int s = 0; s < 4; ++s)
-#pragma unroll
-                        for (int k = 0; k < CF4; ++k) xv[s][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                    for (int k = 0; k < CF4; ++k) xv[s][k] = ldcg4(xrow + s * 64 + k * 4);
             };
+            if (tile_begin < tile_end) fetch(tile_begin);
             for (int ti = tile_begin; ti < tile_end; ++ti) {
-                fetch(ti);                                 // in flight under the weight / coefficient set-up below
                 const TileId tl = tile_of(ti);
                 const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
                 if (loaded != tl.chain) {
@@ -288,6 +284,7 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 for (int s = 0; s < 4; ++s) store_part(As + s * A_UNIT, lrow, lq, *reinterpret_cast<const float(*)[CPT]>(&xv[s][0]));
                 tick(0);
                 issue(idesc64, 4, 64 * 128);
+                if (ti + 1 < tile_end) fetch(ti + 1);      // the next tile's rows: in flight under the MMAs and the epilogue
                 wait_mma();
                 tc_fence_after();
                 tick(1);
@@ -320,8 +317,10 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                     }
                 }
             };
+            unsigned okcur = 0;
+            if (tile_begin < tile_end) fetch(tile_begin);
             for (int ti = tile_begin; ti < tile_end; ++ti) {
-                fetch(ti);                                 // in flight under the weight / coefficient set-up below
+                okcur = okmask;
                 const TileId tl = tile_of(ti);
                 const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
                 if (loaded != tl.chain) {
@@ -338,7 +337,7 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
 #pragma unroll
                         for (int q = 0; q < CF4; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = yv[k][q];
                         transform(v);
-                        const bool ok = (okmask >> k) & 1u;
+                        const bool ok = (okcur >> k) & 1u;
 #pragma unroll
                         for (int i = 0; i < CPT; ++i) v[i] = ok ? v[i] : 0.f;       // literal zeros AFTER the norm (GaGNet.py:313)
                         store_part(As + k * A_UNIT, lrow, lq, v);
@@ -346,6 +345,7 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 }
                 tick(4);
                 issue(idesc64, KD, 64 * 128);
+                if (ti + 1 < tile_end) fetch(ti + 1);      // the next tile's rows: in flight under the MMAs and the epilogue
                 wait_mma();
                 tc_fence_after();
                 tick(5);
@@ -364,14 +364,14 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 const TileId tl = tile_of(ti);
                 const int t = tl.t0 + lrow;
                 zok = t < a.T;
-                if (zok) {
-                    const float* zrow = a.z[tl.chain] + ((size_t)tl.b * a.T + t) * 64 + lq * CPT;
+                const int tc = zok ? t : a.T - 1;
+                const float* zrow = a.z[tl.chain] + ((size_t)tl.b * a.T + tc) * 64 + lq * CPT;
 #pragma unroll
-                    for (int q = 0; q < CF4; ++q) zv[q] = ldcg4(zrow + q * 4);
-                }
+                for (int q = 0; q < CF4; ++q) zv[q] = ldcg4(zrow + q * 4);
             };
+            if (tile_begin < tile_end) fetch(tile_begin);
             for (int ti = tile_begin; ti < tile_end; ++ti) {
-                fetch(ti);                                 // in flight under the weight / coefficient set-up below
+                const bool zcur = zok;
                 const TileId tl = tile_of(ti);
                 const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
                 if (loaded != tl.chain) {
@@ -385,14 +385,11 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 __syncthreads();
                 {
                     float v[CPT];
-                    if (zok) {
 #pragma unroll
-                        for (int q = 0; q < CF4; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = zv[q];
-                        transform(v);
-                    } else {
+                    for (int q = 0; q < CF4; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = zv[q];
+                    transform(v);
 #pragma unroll
-                        for (int i = 0; i < CPT; ++i) v[i] = 0.f;
-                    }
+                    for (int i = 0; i < CPT; ++i) v[i] = zcur ? v[i] : 0.f;
                     store_part(As, lrow, lq, v);
                 }
                 tick(8);
@@ -400,39 +397,31 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 // this row's residual (256 / TPR columns of x) and the next tile's z rows: in flight under the MMAs
                 const int t = tl.t0 + erow;
                 const bool valid = t < a.T;
-                const float* xsrc = (l == 0 ? a.x_in[tl.chain] : a.x_buf[tl.chain]) + ((size_t)tl.b * a.T + t) * 256 + cg * (4 * CPT);
                 float* xdst = a.x_buf[tl.chain] + ((size_t)tl.b * a.T + t) * 256 + cg * (4 * CPT);
-                float4 xr[2][4];                       // residual of 16 columns, the next group in flight
-                auto load_res = [&](int g, float4 (&d)[4]) {
-                    if (valid) {
+                // the whole residual of this thread (4 * CPT columns) in flight under the MMAs; unconditional loads from a
+                // clamped row keep it in registers
+                const int tclamp = t < a.T ? t : a.T - 1;
+                const float* xres = (l == 0 ? a.x_in[tl.chain] : a.x_buf[tl.chain]) + ((size_t)tl.b * a.T + tclamp) * 256 + cg * (4 * CPT);
+                float4 xr[CPT];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) d[k] = ldcg4(xsrc + g * 16 + k * 4);
-                    }
-                };
-                load_res(0, xr[0]);
+                for (int k = 0; k < CPT; ++k) xr[k] = ldcg4(xres + k * 4);
+                if (ti + 1 < tile_end) fetch(ti + 1);      // the next tile's z rows
                 wait_mma();
                 tc_fence_after();
                 tick(9);
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 4 * CPT);
 #pragma unroll
-                for (int g = 0; g < CPT / 4; ++g) {
-                    uint32_t rv[2][8];
-                    tmem_ld8_nowait(taddr + g * 16, rv[0]);
-                    tmem_ld8_nowait(taddr + g * 16 + 8, rv[1]);
-                    if (g + 1 < CPT / 4) load_res(g + 1, xr[(g + 1) & 1]);
+                for (int g = 0; g < CPT / 2; ++g) {
+                    uint32_t rv[8];
+                    tmem_ld8_nowait(taddr + g * 8, rv);
                     tmem_wait_ld();
-                    if (valid) {
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const float4 x0 = xr[g & 1][2 * k], x1 = xr[g & 1][2 * k + 1];
-                            float o[8];
-                            o[0] = __uint_as_float(rv[k][0]) + x0.x; o[1] = __uint_as_float(rv[k][1]) + x0.y;
-                            o[2] = __uint_as_float(rv[k][2]) + x0.z; o[3] = __uint_as_float(rv[k][3]) + x0.w;
-                            o[4] = __uint_as_float(rv[k][4]) + x1.x; o[5] = __uint_as_float(rv[k][5]) + x1.y;
-                            o[6] = __uint_as_float(rv[k][6]) + x1.z; o[7] = __uint_as_float(rv[k][7]) + x1.w;
-                            st_global_256(xdst + g * 16 + k * 8, o);
-                        }
-                    }
+                    const float4 x0 = xr[2 * g], x1 = xr[2 * g + 1];
+                    float o[8];
+                    o[0] = __uint_as_float(rv[0]) + x0.x; o[1] = __uint_as_float(rv[1]) + x0.y;
+                    o[2] = __uint_as_float(rv[2]) + x0.z; o[3] = __uint_as_float(rv[3]) + x0.w;
+                    o[4] = __uint_as_float(rv[4]) + x1.x; o[5] = __uint_as_float(rv[5]) + x1.y;
+                    o[6] = __uint_as_float(rv[6]) + x1.z; o[7] = __uint_as_float(rv[7]) + x1.w;
+                    if (valid) st_global_256(xdst + g * 8, o);
                 }
                 tc_fence_before();
                 __syncthreads();
