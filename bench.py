@@ -192,6 +192,38 @@ def stream_latency(args, dev):
             "realtime_factor": S * 10.0 / wall[N // 2]}
 
 
+def postnet_throughput(args, dev, wave):
+    """what enhance.py actually runs - EaBNetWithPostNet (EaBNet + GaGNet post-filter) wave -> wave
+    on the same synthetic batch, through eab_enhance_postnet; device-resident inputs, CUDA events."""
+    import torch
+    from eabnet_b200 import make_eabnet_with_postnet
+    from eabnet_b200.postnet import default_postnet_args
+    torch.manual_seed(4321)
+    w = make_eabnet_with_postnet(default_postnet_args()).eval().to(dev)
+    steps = max(3, min(args.steps, 10))
+    with torch.no_grad():
+        for _ in range(3):
+            y = w.enhance(wave)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            y = w.enhance(wave)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        launches = w.eabnet.last_launch_count()
+        w.postnet.profile(True)
+        w.enhance(wave)
+        prof = w.postnet.profile_summary()
+        w.postnet.profile(False)
+    assert torch.isfinite(y).all()
+    B, L = wave.shape[0], wave.shape[2]
+    return {"workload": "EaBNetWithPostNet (EaBNet + GaGNet post-filter, enhance.py:21,49-62) wave->wave, %d x %.0f s per GPU" % (B, L / SR),
+            "value": B * (L / SR) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "launches_per_step": launches,
+            "kernels": prof}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,6 +236,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=256, help="concurrent causal streams of the latency measurement")
     ap.add_argument("--stream-steps", type=int, default=1000, help="timed 10 ms hops of the latency measurement (0 = skip)")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step's launches from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-postnet", action="store_true", help="skip the EaBNet + GaGNet post-filter measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
 
@@ -245,20 +279,27 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()                      # nvidia-smi needs ~1 s to produce its first sample: start before the warm-up
     with torch.no_grad():
+        # the device-resident step is replayed from a CUDA graph (EaBNet.graphed_enhance): the ~260 launches of a step are
+        # enqueued by the driver, not by this Python thread, so a busy host cannot turn the measurement launch-bound
+        step = net.graphed_enhance(wave) if not args.no_graph else None
+        run_step = step.step if step is not None else (lambda: net.enhance(wave))
         for _ in range(args.warmup):
-            net.enhance(wave)
+            run_step()
         barrier()
         sampler.rows.clear()             # keep only samples taken from here on (timed regions)
         # ---- device-resident throughput
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         e0.record()
-        for _ in range(args.steps):
-            y = net.enhance(wave)
+        for i in range(args.steps):
+            y = run_step()
+            marks[i].record()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) / args.steps
-        launches = net.last_launch_count()
+        step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
+        launches = step.launches if step is not None else net.last_launch_count()
         # ---- end to end with host buffers: the dataset-scale public call (eab_enhance_host_batches), `steps` batches,
         # every batch uploaded from pinned host memory and its enhanced audio downloaded inside the timed region
         # (uploads / downloads of neighbouring batches overlap compute on the library's copy streams)
@@ -288,6 +329,7 @@ def main():
         assert torch.isfinite(y).all()
 
     latency = stream_latency(args, dev) if args.stream_steps > 0 else None
+    postnet = postnet_throughput(args, dev, wave) if (rank == 0 and not args.no_postnet) else None
 
     from eabnet_b200.shard import max_over_ranks
     ms, ms_e2e = max_over_ranks([ms, ms_e2e], dev)
@@ -333,16 +375,19 @@ def main():
                                        "64 x 6 s utterances per GPU (BASELINE configs[1])",
                            "batch_per_gpu": B, "seconds": args.seconds, "frames": 1 + L // 160,
                            "parallelism": "utterance shards, %d rank(s), no collective" % world,
-                           "l2": "inputs (%.0f MB/step) and activations exceed the 126 MB L2" % (B * M * L * 4 / 1e6)},
+                           "l2": "inputs (%.0f MB/step) and activations exceed the 126 MB L2" % (B * M * L * 4 / 1e6),
+                           "launch": "python enqueue" if args.no_graph else "CUDA graph replay of eab_enhance"},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * M * L * 4,
                         "d2h_bytes_per_step": B * 160 * (L // 160) * 4,
                         "api": "EaBNet.enhance_host_batches (eab_enhance_host_batches): %d host batches per call, wall clock "
                                "around the call, copies overlapped with compute" % args.steps,
                         "single_batch_call_ms": ms_e2e_single},
-                "gpu_launches": launches * args.steps,
+                "gpu_launches": launches * args.steps, "step_ms": step_ms,
                 "roofline": roof, "clocks": clocks, "kernels": prof}
         if latency is not None:
             line["latency"] = latency
+        if postnet is not None:
+            line["postnet"] = postnet
         if world == 1 and not args.no_cpu_baseline:
             val, med, cores, sample = cpu_reference_throughput(args.ref_batch, args.seconds, 3, 1)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

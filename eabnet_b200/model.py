@@ -301,9 +301,34 @@ class EaBNet(_NativeModule):
                        "eab_enhance_host_batches")
         return outs
 
+    def graphed_enhance(self, wave: torch.Tensor) -> "GraphedEnhance":
+        """The wave -> wave step on a fixed device buffer captured once into a CUDA graph (one replay = the ~260 kernel
+        launches of eab_enhance without their host-side enqueue cost).  Re-capture after loading new weights."""
+        return GraphedEnhance(self, wave)
+
     def stream(self, n_streams: int, device: torch.device | str | None = None) -> "EaBNetStream":
         """Carried-state, frame-by-frame inference for `n_streams` concurrent causal streams (eab_stream_*)."""
         return EaBNetStream(self, n_streams, device)
+
+
+class GraphedEnhance:
+    """eab_enhance on a fixed input buffer as a CUDA graph: `step()` replays it and returns the (static) output tensor.
+    The input tensor is read in place, so new audio is enhanced by copying it into `wave` before the replay."""
+
+    def __init__(self, net: "EaBNet", wave: torch.Tensor):
+        self.net, self.wave = net, wave
+        dev = wave.device
+        with torch.cuda.device(dev), torch.no_grad():
+            net.enhance(wave)                              # packs weights, sizes the workspace, configures the kernels
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = net.enhance(wave)
+        self.launches = net.last_launch_count()
+
+    def step(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.out
 
 
 class EaBNetStream:

@@ -222,3 +222,20 @@ def test_full_size_config2_slice_against_oracle():
         out = net.enhance(big).cpu()
     assert torch.isfinite(out).all()
     assert (out[:2] - got).abs().max() <= 1e-5 and (out[62:] - got).abs().max() <= 1e-5
+
+
+def test_graphed_enhance_matches_eager_call():
+    """the CUDA-graph replay of eab_enhance (what bench.py times) returns what the plain call returns, also for new audio"""
+    cfg = O.make_cfg()
+    net, _ = _net(cfg, seed=5)
+    wave, _ = O.make_wave(2, 9, 4800, seed=3)
+    buf = wave.cuda()
+    with torch.no_grad():
+        ref = net.enhance(buf).clone()
+        g = net.graphed_enhance(buf)
+        assert torch.equal(g.step(), ref)
+        wave2, _ = O.make_wave(2, 9, 4800, seed=4)
+        buf.copy_(wave2.cuda())
+        out2 = g.step().clone()
+        assert torch.equal(out2, net.enhance(buf))
+    assert g.launches > 0
