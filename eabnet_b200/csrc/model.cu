@@ -150,7 +150,7 @@ struct TcmLayer {
 // GaGNet glance / gaze blocks (GaGNet.py:136-259)
 struct GagIn {                       // in_conv_main(cat) * sigmoid(in_conv_gate(cat)) as d_feat/64 gated column splits
     int w_main = -1, b_main = -1, w_gate = -1, b_gate = -1;
-    int nsplit = 0, K = 0;
+    int nsplit = 0, K = 0, SW = 64;      // SW: value (= gate) columns per split
     size_t off_dense[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     UmmaW u[8];
 };
@@ -766,23 +766,26 @@ struct Packer {
     void gag_in(GagIn& in) {
         const eab_config& c = m->cfg;
         const int Fb = m->Fb, df = c.d_feat, Fq = c.n_freq, KP = ceil64(2 * Fq), ci = 2 * Fq + df;
+        // widest gated split the tensor-core kernel takes: 128 value + 128 gate columns (each split re-reads the whole input)
+        const int SW = df % 128 == 0 ? 128 : 64;
         in.K = df + KP;
-        in.nsplit = df / 64;
+        in.SW = SW;
+        in.nsplit = df / SW;
         for (int sp = 0; sp < in.nsplit; ++sp) {
-            in.off_dense[sp] = alloc((size_t)in.K * 128);
-            std::vector<float> bias(128);
-            for (int n = 0; n < 128; ++n) {
-                const bool gate = n >= 64;
-                const int co = sp * 64 + (n & 63);
+            in.off_dense[sp] = alloc((size_t)in.K * 2 * SW);
+            std::vector<float> bias(2 * SW);
+            for (int n = 0; n < 2 * SW; ++n) {
+                const bool gate = n >= SW;
+                const int co = sp * SW + (n % SW);
                 const std::vector<float>& W = P(gate ? in.w_gate : in.w_main);
                 bias[n] = P(gate ? in.b_gate : in.b_main)[co];
                 for (int cr = 0; cr < df; ++cr) {
                     const int cc = cr / Fb, f = cr - cc * Fb;
-                    blob[in.off_dense[sp] + (size_t)(f * 64 + cc) * 128 + n] = W[(size_t)co * ci + cr];
+                    blob[in.off_dense[sp] + (size_t)(f * 64 + cc) * 2 * SW + n] = W[(size_t)co * ci + cr];
                 }
-                for (int k = 0; k < 2 * Fq; ++k) blob[in.off_dense[sp] + (size_t)(df + k) * 128 + n] = W[(size_t)co * ci + df + k];
+                for (int k = 0; k < 2 * Fq; ++k) blob[in.off_dense[sp] + (size_t)(df + k) * 2 * SW + n] = W[(size_t)co * ci + df + k];
             }
-            in.u[sp] = umma_images(in.off_dense[sp], 1, in.K, 128, 128, true, 64, bias.data());
+            in.u[sp] = umma_images(in.off_dense[sp], 1, in.K, 2 * SW, 2 * SW, true, SW, bias.data());
         }
     }
 
@@ -1716,9 +1719,9 @@ int run_gag_in(Ctx& cx, const GagIn& in, const Act& feat, const Act& pre, Act* o
         u.ntaps = 1; u.dt[0] = 0; u.df[0] = 0;
         u.nslab = in.K / 64; u.ncoef = in.K; u.npass = 3;
         u.Whi = cx.W(in.u[sp].off_hi[0]); u.Wlo = cx.W(in.u[sp].off_lo[0]); u.bias = cx.W(in.u[sp].off_bias[0]);
-        u.Cout = 64; u.N = 128; u.gate_off = 64;
+        u.Cout = in.SW; u.N = 2 * in.SW; u.gate_off = in.SW;
         u.algo_frac = (float)(c.d_feat + 2 * c.n_freq) / (float)in.K;
-        u.out = out->data; u.out_ld = c.d_feat; u.out_coff = sp * 64;
+        u.out = out->data; u.out_ld = c.d_feat; u.out_coff = sp * in.SW;
         u.tiles_per_b = (cx.T + 127) / 128;
         if (feat.C + pre.C != in.K || !umma_conv_supported(u)) return fail("internal: GaGNet input conv rejected by the tcgen05 path");
         EAB_TRY(run_tensor_convs(cx, &u, 1));
