@@ -375,6 +375,8 @@ struct TcmChainLayer {
     unsigned sc_d, sh_d, al_d;           // norm gamma / beta (or folded BatchNorm scale / shift) and PReLU slope in front of the dilated conv
     unsigned sc_o, sh_o, al_o;           // ... in front of the expand conv
     unsigned st_d, st_o;                 // [B][64][2] statistics accumulators (InstanceNorm)
+    // gated TCMs (EaBNet.py:532-578): *_d above is the value (left) branch, these are the gate (right) branch
+    unsigned wr_hi, wr_lo, sc_r, sh_r, al_r, st_r;
     short dt[8];                         // tap k reads frame t - dt[k]
 };
 struct TcmChainArgs {
@@ -388,6 +390,7 @@ struct TcmChainArgs {
     int nchains, nlayers, kd;
     int B, T, tiles_per_b;
     int instance_norm;
+    int gated;                           // two dilated branches, value * sigmoid(gate)
     float inv_count;                     // 1 / T
     unsigned long long* dbg;             // optional [16] cycle counters of CTA 0 (diagnostics), else null
     TcmChainLayer L[kMaxChainLayers];    // [chain][layer]

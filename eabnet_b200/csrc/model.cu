@@ -141,6 +141,7 @@ struct TcmLayer {
     bool single = false;                 // GaGNet's SqueezedTCM: one dilated branch, no gate (GaGNet.py:285-326)
     bool perm = true;                    // residual stream in bottleneck order f*64+c (EaBNet); false = reference order
     UmmaW u_in, u_dil, u_out;
+    UmmaW u_dl, u_dr;                    // gated TCM: the two dilated branches as separate [kd][64][64] image sets (tcm_chain.cu)
     int w_in = -1, w_left = -1, w_right = -1, w_out = -1;
     NormAct na_left, na_right, na_out;
     size_t off_in = 0, off_dil = 0, off_out = 0;
@@ -239,7 +240,7 @@ struct eab_model {
     int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
-    int opt_tcm_chain = 1;        // GaGNet: every TCM stack of a glance-gaze module as one cooperative launch (tcm_chain.cu)
+    int opt_tcm_chain = 1;        // TCM stacks as persistent cooperative launches (tcm_chain.cu): a GaGNet module's three stacks / an EaBNet group
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
     int opt_plane = 1;            // "stage once, shift by descriptor" kernel with fused producers (fallback)
     int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
@@ -754,7 +755,20 @@ struct Packer {
             for (int ci = 0; ci < cd; ++ci) blob[t.off_out + (size_t)ci * df + mem_ch(nr)] = P(t.w_out)[(size_t)nr * cd + ci];
         t.u_in = umma_images(t.off_in, 1, df, Nin, cd, false, 0, nullptr);
         if (t.single) t.u_dil = umma_images(t.off_dil, kd, cd, Nin, cd, false, 0, nullptr);
-        else t.u_dil = umma_images(t.off_dil, kd, 2 * cd, 2 * ceil64(cd), 2 * cd, true, ceil64(cd), nullptr);
+        else {
+            t.u_dil = umma_images(t.off_dil, kd, 2 * cd, 2 * ceil64(cd), 2 * cd, true, ceil64(cd), nullptr);
+            if (cd == 64) {
+                // the branches separately (the merged form above is block-diagonal: half of its MMAs multiply zeros)
+                for (int br = 0; br < 2; ++br) {
+                    const size_t off = alloc((size_t)kd * cd * Nin);
+                    const std::vector<float>& W = P(br ? t.w_right : t.w_left);
+                    for (int k = 0; k < kd; ++k)
+                        for (int ci = 0; ci < cd; ++ci)
+                            for (int n = 0; n < cd; ++n) blob[off + ((size_t)k * cd + ci) * Nin + n] = W[((size_t)n * cd + ci) * kd + k];
+                    (br ? t.u_dr : t.u_dl) = umma_images(off, kd, cd, Nin, cd, false, 0, nullptr);
+                }
+            }
+        }
         t.u_out = umma_images(t.off_out, 1, cd, df, df, false, 0, nullptr);
         normact(t.na_left);
         if (!t.single) normact(t.na_right);
@@ -1505,6 +1519,10 @@ void tap(Ctx& cx, const char* name, const Act& a) {
     cx.m->taps[name] = t;
 }
 
+struct ChainRef { const TcmLayer* l; int n; };
+bool tcm_chain_ok(Ctx& cx, const ChainRef* chains, int nch);
+int run_tcm_chains(Ctx& cx, const ChainRef* chains, int nch, const Act* ins, Act* outs);
+
 int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
     eab_model* m = cx.m;
     const eab_config& c = m->cfg;
@@ -1581,10 +1599,19 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
     std::vector<Act> group_out;
     size_t ti = 0;
     for (int g = 0; g < c.q; ++g) {
-        for (int i = 0; i < c.p; ++i) {
+        const ChainRef chain = {m->tcms.data() + (size_t)g * c.p, c.p};
+        if (!cx.streaming && tcm_chain_ok(cx, &chain, 1)) {
+            // a whole group (p gated TCMs) as one persistent cooperative launch (tcm_chain.cu)
             Act nx;
-            EAB_TRY(run_tcm(cx, m->tcms[ti++], r, &nx));
+            EAB_TRY(run_tcm_chains(cx, &chain, 1, &r, &nx));
             r = nx;
+            ti += c.p;
+        } else {
+            for (int i = 0; i < c.p; ++i) {
+                Act nx;
+                EAB_TRY(run_tcm(cx, m->tcms[ti++], r, &nx));
+                r = nx;
+            }
         }
         group_out.push_back(r);
     }
@@ -1736,26 +1763,30 @@ int run_gag_lin(Ctx& cx, const GagLin& l, const Act& x, Act* out) {
 }
 
 // 1-3 equally long chains of single-branch TCMs as one cooperative launch (tcm_chain.cu)
-bool tcm_chain_ok(Ctx& cx, const std::vector<TcmLayer>* const* chains, int nch) {
+bool tcm_chain_ok(Ctx& cx, const ChainRef* chains, int nch) {
     const eab_config& c = cx.m->cfg;
-    if (!cx.m->opt_tcm_chain || !cx.tensor_ok() || c.cd1 != 64 || c.d_feat != 256 || c.kd1 > 4 || c.kd1 > 8) return false;
-    const size_t nl = chains[0]->size();
+    if (!cx.m->opt_tcm_chain || !cx.tensor_ok() || c.cd1 != 64 || c.d_feat != 256 || c.kd1 > 8) return false;
+    const bool gated = !chains[0].l[0].single;
+    if (gated ? (c.kd1 != 3 && c.kd1 != 5) : c.kd1 > 4) return false;
+    const size_t nl = (size_t)chains[0].n;
     if (nl < 1 || nch < 1 || nch > 3 || nch * nl > (size_t)kMaxChainLayers) return false;
     for (int i = 0; i < nch; ++i) {
-        if (chains[i]->size() != nl) return false;
-        for (const TcmLayer& t : *chains[i]) {
+        if ((size_t)chains[i].n != nl) return false;
+        for (int li = 0; li < chains[i].n; ++li) {
+            const TcmLayer& t = chains[i].l[li];
             // (planning runs before the weights are packed: the image flags are only known once committed)
-            if (!t.single) return false;
-            if (!cx.m->dirty && !(t.u_in.ok && t.u_dil.ok && t.u_out.ok && t.u_out.nsplit == 2 && t.u_in.nslab == 4)) return false;
+            if (t.single == gated) return false;
+            if (!cx.m->dirty && !(t.u_in.ok && t.u_out.ok && t.u_out.nsplit == 2 && t.u_in.nslab == 4)) return false;
+            if (!cx.m->dirty && !(gated ? (t.u_dl.ok && t.u_dr.ok) : t.u_dil.ok)) return false;
             for (int k = 0; k < c.kd1; ++k) if (t.dt[k] > 30000 || t.dt[k] < -30000) return false;
         }
     }
     return true;
 }
 
-int run_tcm_chains(Ctx& cx, const std::vector<TcmLayer>* const* chains, int nch, const Act* ins, Act* outs) {
+int run_tcm_chains(Ctx& cx, const ChainRef* chains, int nch, const Act* ins, Act* outs) {
     const eab_config& c = cx.m->cfg;
-    const int nl = (int)chains[0]->size();
+    const int nl = chains[0].n;
     const size_t rows = (size_t)cx.B * cx.T;
     TcmChainArgs a;
     memset(&a, 0, sizeof(a));
@@ -1776,10 +1807,16 @@ int run_tcm_chains(Ctx& cx, const std::vector<TcmLayer>* const* chains, int nch,
     a.barrier = reinterpret_cast<unsigned*>(cx.alloc_stats(1));
     for (int i = 0; i < nch; ++i)
         for (int l = 0; l < nl; ++l) {
-            const TcmLayer& t = (*chains[i])[l];
+            const TcmLayer& t = chains[i].l[l];
             TcmChainLayer& L = a.L[i * nl + l];
             L.win_hi = (unsigned)t.u_in.off_hi[0]; L.win_lo = (unsigned)t.u_in.off_lo[0];
-            L.wd_hi = (unsigned)t.u_dil.off_hi[0]; L.wd_lo = (unsigned)t.u_dil.off_lo[0];
+            const bool gated = !t.single;
+            L.wd_hi = (unsigned)(gated ? t.u_dl : t.u_dil).off_hi[0]; L.wd_lo = (unsigned)(gated ? t.u_dl : t.u_dil).off_lo[0];
+            if (gated) {
+                L.wr_hi = (unsigned)t.u_dr.off_hi[0]; L.wr_lo = (unsigned)t.u_dr.off_lo[0];
+                L.sc_r = (unsigned)t.na_right.off_scale; L.sh_r = (unsigned)t.na_right.off_shift; L.al_r = (unsigned)t.na_right.off_alpha;
+                if (in_stats) L.st_r = (unsigned)(cx.alloc_stats(64) - sbase);
+            }
             for (int sp = 0; sp < 2; ++sp) { L.wo_hi[sp] = (unsigned)t.u_out.off_hi[sp]; L.wo_lo[sp] = (unsigned)t.u_out.off_lo[sp]; }
             L.sc_d = (unsigned)t.na_left.off_scale; L.sh_d = (unsigned)t.na_left.off_shift; L.al_d = (unsigned)t.na_left.off_alpha;
             L.sc_o = (unsigned)t.na_out.off_scale; L.sh_o = (unsigned)t.na_out.off_shift; L.al_o = (unsigned)t.na_out.off_alpha;
@@ -1792,6 +1829,7 @@ int run_tcm_chains(Ctx& cx, const std::vector<TcmLayer>* const* chains, int nch,
     if (cx.dry) return 0;
     a.blob = cx.m->blob; a.stats = sbase;
     a.nchains = nch; a.nlayers = nl; a.kd = c.kd1; a.B = cx.B; a.T = cx.T;
+    a.gated = chains[0].l[0].single ? 0 : 1;
     a.instance_norm = in_stats ? 1 : 0; a.inv_count = 1.f / (float)cx.T;
     if (cx.m->opt_dbg_launch == -200 && cx.m->dbg_buf) a.dbg = cx.m->dbg_buf;
     if (cx.m->opt_tcm_chain == 2 && nch > 1) {
@@ -1866,7 +1904,8 @@ int run_gag_forward(Ctx& cx, const float* inpt, const long long* strides, const 
         tap(cx, ("g.in_g." + std::to_string(gi)).c_str(), xg);
         Act xr = xz, xi = xz;
         {
-            const std::vector<TcmLayer>* chains[3] = {&G.tcn_g, &G.tcm_r, &G.tcm_i};
+            const ChainRef chains[3] = {{G.tcn_g.data(), (int)G.tcn_g.size()}, {G.tcm_r.data(), (int)G.tcm_r.size()},
+                                        {G.tcm_i.data(), (int)G.tcm_i.size()}};
             const int nch = m->gcfg.is_squeezed ? 2 : 3;
             if (tcm_chain_ok(cx, chains, nch)) {
                 Act ins[3] = {xg, xz, xz}, outs[3];

@@ -102,15 +102,15 @@ __device__ __forceinline__ void store_part(uint8_t* unit, int row, int q, const 
     }
 }
 
-template <int KD>
+template <int KD, bool GATED>
 __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* As = smem;
     uint8_t* Ws = smem + A_BYTES;
     float* coef = reinterpret_cast<float*>(Ws + W_BYTES);        // [3][64] scale, shift, PReLU slope of the consumer's transform
-    float* sstat = coef + 3 * 64;                      // [2][64] per-tile column sums
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sstat + 2 * 64);
+    float* coefR = coef + 3 * 64;                                // [2][64] scale, shift of the gate (right) branch (gated TCMs)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(coefR + 2 * 64);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
 
     // `units` K slabs in As against `units` weight slabs of `w_stride` bytes (hi at Ws, lo at Ws + W_HALF): per slab three
     // passes (hi*hi, lo*hi, hi*lo) of four K = 16 steps, issued by warp 0 as one convergent loop
-    auto issue = [&](uint32_t idesc, int units, int w_stride) {
+    auto issue = [&](uint32_t idesc, int units, int w_stride, unsigned dmask = 0u, unsigned fmask = 1u) {
         fence_proxy_async();
         __syncthreads();
         if (warp == 0) {
@@ -157,9 +157,10 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
             for (int u = 0; u < units; ++u) {
                 const uint32_t ah = a0 + (uint32_t)((u * A_UNIT) >> 4), al = ah + (SLAB >> 4);
                 const uint32_t wh = w0 + (uint32_t)((u * w_stride) >> 4), wl = wh + (W_HALF >> 4);
-                umma_f16_lo_elect_x4(tmem_base, ah, wh, idesc, u > 0 ? 1u : 0u);
-                umma_f16_lo_elect_x4(tmem_base, al, wh, idesc, 1u);
-                umma_f16_lo_elect_x4(tmem_base, ah, wl, idesc, 1u);
+                const uint32_t d = tmem_base + (((dmask >> u) & 1u) ? 64u : 0u);       // gated: value cols 0-63, gate cols 64-127
+                umma_f16_lo_elect_x4(d, ah, wh, idesc, ((fmask >> u) & 1u) ? 0u : 1u);
+                umma_f16_lo_elect_x4(d, al, wh, idesc, 1u);
+                umma_f16_lo_elect_x4(d, ah, wl, idesc, 1u);
             }
             umma_commit_elect(bar);
         }
@@ -171,23 +172,40 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
         for (int i = tid; i < bytes / 16; i += NT) d[i] = __ldg(s + i);
     };
     // per-channel transform of the consumer: PReLU(alpha) then x*s + h, (s, h) from instance statistics or precomputed
+    auto coef_of = [&](const double* stats, int b, int c, unsigned off_sc, unsigned off_sh, float& s, float& h) {
+        if (in_stats) {
+            const double* st = stats + ((size_t)b * 64 + c) * 2;
+            const double mean = __ldcg(st) * (double)a.inv_count;
+            double var = __ldcg(st + 1) * (double)a.inv_count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double rstd = rsqrt(var + 1e-5);
+            const double g = (double)__ldg(a.blob + off_sc + c);
+            s = (float)(g * rstd);
+            h = (float)((double)__ldg(a.blob + off_sh + c) - mean * g * rstd);
+        } else {
+            s = __ldg(a.blob + off_sc + c);
+            h = __ldg(a.blob + off_sh + c);
+        }
+    };
     auto load_coef = [&](const double* stats, int b, unsigned off_sc, unsigned off_sh, unsigned off_al) {
         if (tid < 64) {
             float s, h;
-            if (in_stats) {
-                const double* st = stats + ((size_t)b * 64 + tid) * 2;
-                const double mean = __ldcg(st) * (double)a.inv_count;
-                double var = __ldcg(st + 1) * (double)a.inv_count - mean * mean;
-                if (var < 0.0) var = 0.0;
-                const double rstd = rsqrt(var + 1e-5);
-                const double g = (double)__ldg(a.blob + off_sc + tid);
-                s = (float)(g * rstd);
-                h = (float)((double)__ldg(a.blob + off_sh + tid) - mean * g * rstd);
-            } else {
-                s = __ldg(a.blob + off_sc + tid);
-                h = __ldg(a.blob + off_sh + tid);
-            }
+            coef_of(stats, b, tid, off_sc, off_sh, s, h);
             coef[tid] = s; coef[64 + tid] = h; coef[128 + tid] = __ldg(a.blob + off_al + tid);
+        }
+    };
+    auto load_coef_right = [&](const double* stats, int b, unsigned off_sc, unsigned off_sh) {      // threads 64..127
+        if (tid >= 64 && tid < 128) {
+            float s, h;
+            coef_of(stats, b, tid - 64, off_sc, off_sh, s, h);
+            coefR[tid - 64] = s; coefR[tid] = h;
+        }
+    };
+    auto transform_right = [&](float (&v)[CPT], const float* alpha) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int c = lq * CPT + i;
+            v[i] = fmaf(prelu_f(v[i], __ldg(alpha + c)), coefR[c], coefR[64 + c]);
         }
     };
     auto transform = [&](float (&v)[CPT]) {
@@ -198,44 +216,64 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
         }
     };
     // epilogue of phases A / B: CPT accumulator columns of this thread's row -> global rows + statistics of PReLU(value)
-    auto epilogue64 = [&](float* dst, int b, int t0, double* stats, unsigned off_alpha) {
+    // stats2 / off_alpha2: a second statistics set of the same values under another PReLU (the gate branch of a gated TCM);
+    // gate: the stored value is acc[col] * sigmoid(acc[64 + col]) (phase B of a gated TCM, EaBNet.py:575)
+    auto epilogue64 = [&](float* dst, int b, int t0, double* stats, unsigned off_alpha, double* stats2, unsigned off_alpha2, bool gate) {
         const int t = t0 + erow;
         const bool valid = t < a.T;
         // 8 columns at a time: the next tile's prefetched rows stay in registers across this epilogue
 #pragma unroll
         for (int k = 0; k < CPT / 8; ++k) {
             uint32_t rv[8];
-            tmem_ld8_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * CPT + k * 8), rv);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * CPT + k * 8);
+            tmem_ld8_nowait(taddr, rv);
             tmem_wait_ld();
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rv[e]);
+            if (GATED && gate) {
+                uint32_t rg[8];
+                tmem_ld8_nowait(taddr + 64, rg);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] *= sigmoid_f(__uint_as_float(rg[e]));
+            }
             if (valid) st_global_256(dst + ((size_t)b * a.T + t) * 64 + cg * CPT + k * 8, v);
             if (in_stats) {
                 const float* al = a.blob + off_alpha + cg * CPT + k * 8;
-                float w[8];
+                float p[8], w[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { v[i] = valid ? prelu_f(v[i], __ldg(al + i)) : 0.f; w[i] = v[i]; }
+                for (int i = 0; i < 8; ++i) { p[i] = valid ? prelu_f(v[i], __ldg(al + i)) : 0.f; w[i] = p[i]; }
                 const float s1 = warp_column_sums8(w, lane);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = v[i] * v[i];
+                for (int i = 0; i < 8; ++i) w[i] = p[i] * p[i];
                 const float s2 = warp_column_sums8(w, lane);
                 if (lane < 8) {
-                    atomicAdd(&sstat[cg * CPT + k * 8 + lane], s1);
-                    atomicAdd(&sstat[64 + cg * CPT + k * 8 + lane], s2);
+                    // per-warp partial sums (fixed shuffle order) straight to the fp64 accumulators: an fp32 shared-memory
+                    // accumulation across warps would make the statistics depend on the warps' arrival order
+                    double* d1 = stats + ((size_t)b * 64 + cg * CPT + k * 8 + lane) * 2;
+                    atomicAdd(d1, (double)s1);
+                    atomicAdd(d1 + 1, (double)s2);
+                }
+                if (GATED && stats2) {
+                    const float* al2 = a.blob + off_alpha2 + cg * CPT + k * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { p[i] = valid ? prelu_f(v[i], __ldg(al2 + i)) : 0.f; w[i] = p[i]; }
+                    const float r1 = warp_column_sums8(w, lane);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = p[i] * p[i];
+                    const float r2 = warp_column_sums8(w, lane);
+                    if (lane < 8) {                        // second set: straight to the global accumulators (one per warp and column)
+                        double* d2 = stats2 + ((size_t)b * 64 + cg * CPT + k * 8 + lane) * 2;
+                        atomicAdd(d2, (double)r1);
+                        atomicAdd(d2 + 1, (double)r2);
+                    }
                 }
             }
         }
         tc_fence_before();
         __syncthreads();
-        if (in_stats && tid < 128) {
-            const int c = tid & 63, which = tid >> 6;
-            atomicAdd(stats + ((size_t)b * 64 + c) * 2 + which, (double)sstat[which * 64 + c]);
-            sstat[tid] = 0.f;                              // ready for the next tile (ordered by the barriers in between)
-        }
     };
-
-    if (tid < 128) sstat[tid] = 0.f;
 
     // diagnostics (builds with -DEAB_CHAIN_DEBUG only: the counters cost 30 registers, and at the 128-register cap of a
     // 512-thread CTA every spilled byte goes through an L1 that is almost entirely carved out as shared memory):
@@ -288,13 +326,83 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 wait_mma();
                 tc_fence_after();
                 tick(1);
-                epilogue64(a.y[tl.chain], tl.b, tl.t0, a.stats + L.st_d, L.al_d);
+                epilogue64(a.y[tl.chain], tl.b, tl.t0, a.stats + L.st_d, L.al_d, GATED ? a.stats + L.st_r : nullptr, L.al_r, false);
                 tick(2);
             }
         }
         grid_barrier(a.barrier, bar_target);
         tick(3);
         // ======================================================================= phase B: z = W_dil * norm(PReLU(y)) (dilated)
+        if constexpr (GATED) {
+            // two branches (EaBNet.py:554-566, 575): value = W_left * norm_l(PReLU_l(y)), gate = W_right * norm_r(PReLU_r(y)), both
+            // dilated; 2 KD (branch, tap) units of 32 KB operand + 16 KB weights each, staged in rounds of 4 units
+            constexpr int NU = 2 * KD, NR = (NU + 3) / 4;
+            float4 yv[4][CF4];
+            unsigned okmask = 0;
+            auto fetch = [&](int ti, int r) {
+                const TileId tl = tile_of(ti);
+                const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
+                const int t = tl.t0 + lrow;
+                okmask = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = r * 4 + u;
+                    if (g < NU) {
+                        const int ts = t - L.dt[g % KD];
+                        if (t < a.T && ts >= 0 && ts < a.T) okmask |= 1u << u;
+                        const int tc = ts < 0 ? 0 : (ts >= a.T ? a.T - 1 : ts);
+                        const float* yrow = a.y[tl.chain] + ((size_t)tl.b * a.T + tc) * 64 + lq * CPT;
+#pragma unroll
+                        for (int q = 0; q < CF4; ++q) yv[u][q] = ldcg4(yrow + q * 4);
+                    }
+                }
+            };
+            if (tile_begin < tile_end) fetch(tile_begin, 0);
+            for (int ti = tile_begin; ti < tile_end; ++ti) {
+                const TileId tl = tile_of(ti);
+                const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
+                load_coef(a.stats + L.st_d, tl.b, L.sc_d, L.sh_d, L.al_d);
+                load_coef_right(a.stats + L.st_r, tl.b, L.sc_r, L.sh_r);
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const unsigned okcur = okmask;
+                    if (r > 0) wait_mma();                 // the previous round's MMAs have read As / Ws
+                    unsigned dmask = 0, fmask = 0;
+                    int nun = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int g = r * 4 + u;
+                        if (g < NU) {
+                            const bool right = g >= KD;
+                            const int tap = g % KD;
+                            load_w(a.blob + (right ? L.wr_hi : L.wd_hi) + tap * (64 * 128 / 4), u * 64 * 128, 64 * 128);
+                            load_w(a.blob + (right ? L.wr_lo : L.wd_lo) + tap * (64 * 128 / 4), W_HALF + u * 64 * 128, 64 * 128);
+                            float v[CPT];
+#pragma unroll
+                            for (int q = 0; q < CF4; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = yv[u][q];
+                            if (right) transform_right(v, a.blob + L.al_r); else transform(v);
+                            const bool ok = (okcur >> u) & 1u;
+#pragma unroll
+                            for (int i = 0; i < CPT; ++i) v[i] = ok ? v[i] : 0.f;       // literal zeros AFTER the norm (EaBNet.py:557)
+                            store_part(As + u * A_UNIT, lrow, lq, v);
+                            if (right) dmask |= 1u << u;
+                            if (tap == 0) fmask |= 1u << u;
+                            ++nun;
+                        }
+                    }
+                    tick(4);
+                    issue(idesc64, nun, 64 * 128, dmask, fmask);
+                    if (r + 1 < NR) fetch(ti, r + 1);      // the next round's rows: in flight under the MMAs
+                    else if (ti + 1 < tile_end) fetch(ti + 1, 0);
+                }
+                wait_mma();
+                tc_fence_after();
+                tick(5);
+                epilogue64(a.z[tl.chain], tl.b, tl.t0, a.stats + L.st_o, L.al_o, nullptr, 0u, true);
+                tick(6);
+            }
+        } else
         {
             int loaded = -1;
             float4 yv[KD][CF4];                            // [tap][CPT channels]
@@ -349,7 +457,7 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 wait_mma();
                 tc_fence_after();
                 tick(5);
-                epilogue64(a.z[tl.chain], tl.b, tl.t0, a.stats + L.st_o, L.al_o);
+                epilogue64(a.z[tl.chain], tl.b, tl.t0, a.stats + L.st_o, L.al_o, nullptr, 0u, false);
                 tick(6);
             }
         }
@@ -445,23 +553,32 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
 }  // namespace
 
 bool tcm_chain_supported(const TcmChainArgs& a) {
-    return a.nchains >= 1 && a.nchains <= 3 && a.nlayers >= 1 && a.nchains * a.nlayers <= kMaxChainLayers && a.kd >= 1 &&
-           a.kd <= A_UNITS && a.kd * 64 * 128 <= W_HALF && a.B >= 1 && a.T >= 1;
+    if (a.nchains < 1 || a.nchains > 3 || a.nlayers < 1 || a.nchains * a.nlayers > kMaxChainLayers || a.B < 1 || a.T < 1) return false;
+    return a.gated ? (a.kd == 3 || a.kd == 5) : (a.kd >= 1 && a.kd <= A_UNITS);
 }
 
 int launch_tcm_chain(const TcmChainArgs& a_in, cudaStream_t st) {
     TcmChainArgs a = a_in;
     if (!tcm_chain_supported(a)) return fail("tcm_chain: unsupported shape");
-    const void* kernel = a.kd == 1 ? reinterpret_cast<const void*>(tcm_chain_kernel<1>)
-                       : a.kd == 2 ? reinterpret_cast<const void*>(tcm_chain_kernel<2>)
-                       : a.kd == 3 ? reinterpret_cast<const void*>(tcm_chain_kernel<3>)
-                                   : reinterpret_cast<const void*>(tcm_chain_kernel<4>);
+    const void* kernel = nullptr;
+    if (a.gated) {
+        kernel = a.kd == 3 ? reinterpret_cast<const void*>(tcm_chain_kernel<3, true>)
+               : a.kd == 5 ? reinterpret_cast<const void*>(tcm_chain_kernel<5, true>) : nullptr;
+    } else {
+        kernel = a.kd == 1 ? reinterpret_cast<const void*>(tcm_chain_kernel<1, false>)
+               : a.kd == 2 ? reinterpret_cast<const void*>(tcm_chain_kernel<2, false>)
+               : a.kd == 3 ? reinterpret_cast<const void*>(tcm_chain_kernel<3, false>)
+               : a.kd == 4 ? reinterpret_cast<const void*>(tcm_chain_kernel<4, false>) : nullptr;
+    }
+    if (!kernel) return fail("tcm_chain: unsupported kernel size");
     static int max_ctas = 0;
     if (!max_ctas) {
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         int dev = 0, sms = 0, coop = 0;
         EAB_CUDA(cudaGetDevice(&dev));
         EAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -474,7 +591,8 @@ int launch_tcm_chain(const TcmChainArgs& a_in, cudaStream_t st) {
     if (total >= (1ll << 30)) return fail("tcm_chain: too many tiles");
     const int grid = (int)(total < max_ctas ? total : max_ctas);
     const double rows = (double)a.nchains * a.B * a.T * a.nlayers;
-    ProfScope ps("tcm_chain", 2.0 * rows * (256.0 * 64 + a.kd * 64.0 * 64 + 64.0 * 256),
+    const double nb = a.gated ? 2.0 : 1.0;
+    ProfScope ps("tcm_chain", 2.0 * rows * (256.0 * 64 + nb * a.kd * 64.0 * 64 + 64.0 * 256),
                  4.0 * rows * (256 + 64 + 64 * a.kd + 64 + 64 + 256 + 256), st);
     void* params[1] = {&a};
     EAB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(NT), params,
