@@ -422,6 +422,16 @@ struct GagCrmArgs {
 };
 int launch_gag_crm(const GagCrmArgs& a, cudaStream_t st);
 
+// 16-bit PCM wire format (elementwise.cu)
+struct PcmArgs {
+    const short* pcm;            // [B][M][L] int16, microphones in file order
+    float* wave;                 // [B][M][L] fp32 = pcm / 32768, microphone m taken from file channel order[m]
+    int B, M, L;
+    int order[64];
+};
+int launch_pcm16_to_float(const PcmArgs& a, cudaStream_t st);
+int launch_float_to_pcm16(const float* x, short* out, size_t n, cudaStream_t st);
+
 int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st);
 int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st);
 // streaming front/back end (stft.cu): one hop in -> spectrum frame *step into a ring; spectrum frame -> one hop out

@@ -2293,6 +2293,50 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
     return 0;
 }
 
+// enhance.py:35-43 + the int16 writer of the dataset tools, end to end on HOST 16-bit PCM buffers: H2D of the PCM (half the
+// bytes of the fp32 front door), int16 -> float / 32768 with the microphone permutation, EaBNet (+ GaGNet), float -> int16, D2H.
+int eab_enhance_host_pcm16(eab_model* m, eab_model* gag, int ref_mic, const int16_t* pcm_host, const int* mic_order,
+                           int16_t* enhanced_pcm_host, int B, int L, void* stream) {
+    if (!m || !pcm_host || !enhanced_pcm_host) return fail("eab_enhance_host_pcm16: null argument");
+    if (m->kind != 0 || (gag && gag->kind != 1)) return fail("eab_enhance_host_pcm16: needs an EaBNet handle (and optionally a GaGNet handle)");
+    const int M = m->cfg.M;
+    if (M > 64) return fail("eab_enhance_host_pcm16: at most 64 microphones");
+    PcmArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    for (int i = 0; i < M; ++i) {
+        pa.order[i] = mic_order ? mic_order[i] : i;
+        if (pa.order[i] < 0 || pa.order[i] >= M) return fail("eab_enhance_host_pcm16: mic_order entries must be in [0, M)");
+    }
+    const size_t need = gag ? eab_enhance_postnet_workspace_bytes(m, gag, B, L) : eab_enhance_workspace_bytes(m, B, L);
+    if (!need) return fail("eab_enhance_host_pcm16: bad shape");
+    const size_t n_in = (size_t)B * M * L, n_out = (size_t)B * 160 * (L / 160);
+    const size_t o_pcm = 0, o_wave = align256(n_in * 2), o_enh = o_wave + align256(n_in * 4), o_epcm = o_enh + align256(n_out * 4),
+                 o_ws = o_epcm + align256(n_out * 2), total = o_ws + need;
+    if (m->scratch_bytes < total) {
+        if (m->scratch) cudaFree(m->scratch);
+        m->scratch = nullptr;
+        m->scratch_bytes = 0;
+        EAB_CUDA(cudaMalloc(&m->scratch, total));
+        m->scratch_bytes = total;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* p = static_cast<char*>(m->scratch);
+    short* d_pcm = reinterpret_cast<short*>(p + o_pcm);
+    float* d_wave = reinterpret_cast<float*>(p + o_wave);
+    float* d_enh = reinterpret_cast<float*>(p + o_enh);
+    short* d_epcm = reinterpret_cast<short*>(p + o_epcm);
+    EAB_CUDA(cudaMemcpyAsync(d_pcm, pcm_host, n_in * 2, cudaMemcpyHostToDevice, st));
+    pa.pcm = d_pcm; pa.wave = d_wave; pa.B = B; pa.M = M; pa.L = L;
+    EAB_TRY(launch_pcm16_to_float(pa, st));
+    if (gag) EAB_TRY(eab_enhance_postnet(m, gag, ref_mic, d_wave, d_enh, B, L, p + o_ws, need, stream));
+    else EAB_TRY(eab_enhance(m, d_wave, d_enh, B, L, p + o_ws, need, stream));
+    m->last_launches += 2;
+    EAB_TRY(launch_float_to_pcm16(d_enh, d_epcm, n_out, st));
+    EAB_CUDA(cudaMemcpyAsync(enhanced_pcm_host, d_epcm, n_out * 2, cudaMemcpyDeviceToHost, st));
+    EAB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host, int B, int L, void* stream) {
     if (!m || !wave_host || !enhanced_host) return fail("eab_enhance_host: null argument");
     return eab_enhance_host_batches(m, &wave_host, &enhanced_host, 1, B, L, stream);

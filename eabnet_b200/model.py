@@ -301,6 +301,38 @@ class EaBNet(_NativeModule):
                        "eab_enhance_host_batches")
         return outs
 
+    def enhance_pcm16(self, pcm: torch.Tensor, mic_order=None, out: torch.Tensor | None = None, postnet=None, ref_mic: int = 0,
+                      device: torch.device | str = "cuda") -> torch.Tensor:
+        """HOST int16 PCM [B,M,L] (file channel order) -> HOST int16 enhanced [B,160*(L//160)]: torchaudio.load's / 32768,
+        enhance.py:41-42's microphone permutation, the network (+ `postnet`, a GaGNet), and the dataset tools' int16 writer, as one
+        native call (eab_enhance_host_pcm16)."""
+        if pcm.is_cuda or pcm.dtype != torch.int16 or pcm.ndim != 3:
+            raise TypeError("enhance_pcm16 takes an int16 CPU tensor [B,M,L]")
+        B, M, L = pcm.shape
+        if M != self.M:
+            raise RuntimeError("expected %d microphones, got %d" % (self.M, M))
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        x = pcm.contiguous()
+        if out is None:
+            out = torch.empty((B, 160 * (L // 160)), dtype=torch.int16, pin_memory=True)
+        order = None
+        if mic_order is not None:
+            if len(mic_order) != M:
+                raise ValueError("mic_order needs %d entries" % M)
+            order = (C.c_int * M)(*[int(v) for v in mic_order])
+        with torch.cuda.device(dev):
+            self._sync_params(dev)
+            gh = None
+            if postnet is not None:
+                postnet._sync_params(dev)
+                gh = postnet._native.h
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self._native.lib.eab_enhance_host_pcm16(self._native.h, gh, int(ref_mic), _ptr(x), order, _ptr(out), B, L, stream),
+                       "eab_enhance_host_pcm16")
+        return out
+
     def graphed_enhance(self, wave: torch.Tensor) -> "GraphedEnhance":
         """The wave -> wave step on a fixed device buffer captured once into a CUDA graph (one replay = the ~260 kernel
         launches of eab_enhance without their host-side enqueue cost).  Re-capture after loading new weights."""

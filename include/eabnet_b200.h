@@ -173,6 +173,14 @@ EAB_API size_t eab_enhance_postnet_workspace_bytes(const eab_model* eabnet, cons
 EAB_API int    eab_enhance_postnet(eab_model* eabnet, eab_model* gagnet, int ref_mic, const float* wave_dev,
                            float* enhanced_dev, int B, int L, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* 16-bit PCM wire format end to end on HOST buffers (enhance.py:35-43 reads the file with
+ * torchaudio.load, i.e. int16 / 32768, and permutes the microphones with index_select; dataset/mcse_dataset_offline_gen.py:38-39
+ * writes int16(clip(y,-1,1) * 32767)).  pcm_host [B][M][L] int16 in file channel order; microphone m of the model is file
+ * channel mic_order[m] (NULL = identity); gagnet may be NULL (EaBNet only); enhanced_pcm_host [B][160*(L/160)] int16.
+ * Half the H2D bytes of eab_enhance_host; the library keeps its own device scratch; synchronises before returning. */
+EAB_API int    eab_enhance_host_pcm16(eab_model* eabnet, eab_model* gagnet, int ref_mic, const int16_t* pcm_host,
+                              const int* mic_order, int16_t* enhanced_pcm_host, int B, int L, void* stream);
+
 /* Introspection used by tests and bench: number of kernels launched by the last forward/enhance call, and a
  * copy of a named intermediate of the last eab_forward ("en.0".."en.4", "tcm", "de.0".."de.3", "embed",
  * "h1", "h2", "w") with its normalisation/activation applied, channels-last [B,T,F',C'].  Returns the

@@ -131,3 +131,20 @@ def test_gag_tcm_chain_kernel_agrees_with_layer_by_layer_path(over):
     assert float((a - ref).abs().max()) <= TIGHT * scale
     assert float((b - ref).abs().max()) <= TIGHT * scale
     assert n_chain < n_layer
+
+
+def test_postnet_pcm16_front_door():
+    """enhance.py end to end on 16-bit PCM: permuted int16 microphones -> EaBNet + GaGNet -> int16"""
+    from eabnet_b200 import make_eabnet_with_postnet
+    from eabnet_b200.postnet import default_postnet_args
+    w = make_eabnet_with_postnet(default_postnet_args(ref_mic=1)).eval()
+    w.load_state_dict(G.make_postnet_weights(None, None, 2, "B"), strict=True)
+    w.cuda()
+    wave, _ = O.make_wave(1, 9, 4800, seed=5)
+    pcm = (wave * 32768.0).round().clamp(-32768, 32767).to(torch.int16)
+    order = [7, 0, 1, 2, 3, 4, 5, 6, 8]
+    x = (pcm.float() / 32768.0)[:, order].contiguous()
+    with torch.no_grad():
+        exp = (w.enhance(x.cuda()).cpu().clamp(-1, 1) * 32767.0).to(torch.int16)
+    got = w.eabnet.enhance_pcm16(pcm, mic_order=order, postnet=w.postnet, ref_mic=w.ref_mic)
+    assert int((got.int() - exp.int()).abs().max()) <= 1

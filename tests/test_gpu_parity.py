@@ -239,3 +239,25 @@ def test_graphed_enhance_matches_eager_call():
         out2 = g.step().clone()
         assert torch.equal(out2, net.enhance(buf))
     assert g.launches > 0
+
+
+def test_enhance_pcm16_front_door():
+    """16-bit PCM in / out: int16 / 32768 + microphone permutation (enhance.py:35-42) -> network -> the dataset
+    tools' int16 writer; against the fp32 device path on the same samples (<= 1 LSB) and the CPU oracle (tolerance in LSBs)"""
+    cfg = O.make_cfg()
+    net, sd = _net(cfg, seed=6)
+    wave, _ = O.make_wave(2, 9, 8000, seed=9)
+    pcm = (wave * 32768.0).round().clamp(-32768, 32767).to(torch.int16)
+    order = [8, 0, 1, 2, 3, 4, 5, 6, 7]
+    x = (pcm.float() / 32768.0)[:, order].contiguous()
+    quant = lambda y: (y.clamp(-1, 1) * 32767.0).to(torch.int16)            # noqa: E731  (astype(int16): truncation)
+    with torch.no_grad():
+        exp = quant(net.enhance(x.cuda()).cpu())
+    got = net.enhance_pcm16(pcm, mic_order=order)
+    assert got.dtype == torch.int16 and got.shape == (2, 8000)
+    assert int((got.int() - exp.int()).abs().max()) <= 1
+    ref = quant(O.enhance(sd, x, cfg))
+    assert int((got.int() - ref.int()).abs().max()) <= 8                    # 1e-4 of full scale = 3.3 LSB
+    assert int(got.abs().max()) > 50                                        # a real signal came back
+    with pytest.raises(RuntimeError):
+        net.enhance_pcm16(pcm, mic_order=[0] * 8 + [9])
