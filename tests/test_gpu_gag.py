@@ -148,3 +148,30 @@ def test_postnet_pcm16_front_door():
         exp = (w.enhance(x.cuda()).cpu().clamp(-1, 1) * 32767.0).to(torch.int16)
     got = w.eabnet.enhance_pcm16(pcm, mic_order=order, postnet=w.postnet, ref_mic=w.ref_mic)
     assert int((got.int() - exp.int()).abs().max()) <= 1
+
+
+@pytest.mark.slow
+def test_postnet_full_size_config2_slice_against_oracle():
+    """T = 601 (6 s) at B = 2 against the oracle (spectrum bar 1e-3 relative, SI-SDR 0.05 dB), plus B = 64 finiteness and
+    batch-item independence of the EaBNet + GaGNet wave -> wave call at the full config-2 size."""
+    from eabnet_b200 import make_eabnet_with_postnet
+    from eabnet_b200.postnet import default_postnet_args
+    w = make_eabnet_with_postnet(default_postnet_args()).eval()
+    sd = G.make_postnet_weights(None, None, 3, "B")
+    w.load_state_dict(sd, strict=True)
+    w.cuda()
+    wave, clean = O.make_wave(2, 9, 96000, seed=19)
+    r = G.postnet_forward(sd, O.stft_compress(wave), O.make_cfg(), G.make_gag_cfg(), ref_mic=0)
+    ref = O.istft(r["esti_stft"].contiguous())
+    with torch.no_grad():
+        spec = w(O.stft_compress(wave).cuda())["esti_stft"].cpu()
+        got = w.enhance(wave.cuda()).cpu()
+        big = w.enhance(wave.repeat(32, 1, 1).cuda()).cpu()
+    scale = max(1.0, float(r["esti_stft"].abs().max()))
+    assert float((spec - r["esti_stft"]).abs().max()) <= TOL * scale
+    assert float((got - ref).abs().max()) <= TOL * max(1.0, float(ref.abs().max()))
+    for b in range(2):
+        assert abs(O.si_sdr(clean[b, :96000].numpy(), got[b].numpy()) - O.si_sdr(clean[b, :96000].numpy(), ref[b].numpy())) <= 0.05
+    assert torch.isfinite(big).all()
+    assert float((big[:2] - got).abs().max()) <= 1e-5 * max(1.0, float(got.abs().max()))
+    assert float((big[62:] - got).abs().max()) <= 1e-5 * max(1.0, float(got.abs().max()))
