@@ -218,8 +218,9 @@ def test_full_size_config2_slice_against_oracle():
     with torch.no_grad():
         got = net.enhance(wave.cuda()).cpu()
         assert (got - ref).abs().max() <= 1e-4
-        big = wave.repeat(32, 1, 1).cuda()                 # 64 x 6 s
-        out = net.enhance(big).cpu()
+        # 64 x 6 s: the two utterances first and last, 60 unrelated ones in between (a cross-item mix-up would show)
+        filler = 0.1 * torch.randn(60, 9, 96000, generator=torch.Generator().manual_seed(5))
+        out = net.enhance(torch.cat((wave, filler, wave)).cuda()).cpu()
     assert torch.isfinite(out).all()
     assert (out[:2] - got).abs().max() <= 1e-5 and (out[62:] - got).abs().max() <= 1e-5
 
