@@ -67,6 +67,7 @@ ProfScope::~ProfScope() {
     if (!rec) return;
     cudaEventRecord(g_prof.recs[reinterpret_cast<size_t>(rec) - 1].b, st);
 }
+bool g_prof_on() { return g_prof.on; }
 int launch_count() { return g_launches; }
 void reset_launch_count() { g_launches = 0; }
 
@@ -223,6 +224,13 @@ struct eab_model {
     void* scratch = nullptr;      // eab_enhance_host / eab_enhance_host_batches
     size_t scratch_bytes = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host front door
+    cudaStream_t s_comp = nullptr;                    // its compute stream when the caller passes the legacy default stream (not capturable)
+    // the per-slot step of the host front door as a CUDA graph (captured on the slot's second use, replayed afterwards)
+    struct SlotGraph { cudaGraphExec_t exec = nullptr; const void* in = nullptr; void* out = nullptr; void* ws = nullptr; int B = 0, L = 0;
+                       unsigned long long version = 0; int launches = 0; };
+    SlotGraph slot_graph[2];
+    unsigned long long param_version = 0;           // bumped by every commit
+    int opt_host_graph = 1;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // options (eab_set_option)
     int opt_umma = 1;             // tcgen05 path for eligible layers
@@ -964,6 +972,7 @@ int commit(eab_model* m, cudaStream_t st) {
     EAB_CUDA(cudaMemcpyAsync(m->blob, pk.blob.data(), pk.blob.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     EAB_CUDA(cudaStreamSynchronize(st));        // the staging vector dies with this scope
     m->dirty = false;
+    ++m->param_version;
     return 0;
 }
 
@@ -2086,9 +2095,11 @@ void eab_destroy(eab_model* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
     if (m->scratch) cudaFree(m->scratch);
+    for (auto& sg : m->slot_graph) if (sg.exec) cudaGraphExecDestroy(sg.exec);
     if (m->s_in) {
         cudaStreamDestroy(m->s_in);
         cudaStreamDestroy(m->s_out);
+        cudaStreamDestroy(m->s_comp);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_comp[i]); cudaEventDestroy(m->ev_out[i]); }
     }
     delete m;
@@ -2258,13 +2269,22 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
     if (!m->s_in) {
         EAB_CUDA(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
         EAB_CUDA(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+        EAB_CUDA(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             EAB_CUDA(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
             EAB_CUDA(cudaEventCreateWithFlags(&m->ev_comp[i], cudaEventDisableTiming));
             EAB_CUDA(cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming));
         }
     }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t caller = static_cast<cudaStream_t>(stream);
+    // the legacy default stream cannot be captured into a graph: compute on the library's own stream then, ordered after the
+    // caller's queued work (the call synchronises before it returns, so the caller's stream semantics are unchanged)
+    cudaStream_t st = caller ? caller : m->s_comp;
+    if (!caller) {
+        EAB_CUDA(cudaEventRecord(m->ev_out[0], caller));
+        EAB_CUDA(cudaStreamWaitEvent(st, m->ev_out[0], 0));
+        stream = st;
+    }
     char* p = static_cast<char*>(m->scratch);
     float* din[2] = {reinterpret_cast<float*>(p), reinterpret_cast<float*>(p + (nslot - 1) * in_b)};
     float* dout[2] = {reinterpret_cast<float*>(p + nslot * in_b), reinterpret_cast<float*>(p + nslot * in_b + (nslot - 1) * out_b)};
@@ -2280,7 +2300,38 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
         EAB_CUDA(cudaEventRecord(m->ev_in[s], m->s_in));
         EAB_CUDA(cudaStreamWaitEvent(st, m->ev_in[s], 0));
         if (i >= 2) EAB_CUDA(cudaStreamWaitEvent(st, m->ev_out[s], 0));                // batch i-2 has left this output slot
-        EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, stream));
+        // the slot's step: replayed from a CUDA graph once the slot has run it directly (same buffers, same shape, same weights)
+        {
+            eab_model::SlotGraph& sg = m->slot_graph[s];
+            const bool match = sg.exec && sg.in == din[s] && sg.out == dout[s] && sg.ws == ws && sg.B == B && sg.L == L &&
+                               sg.version == m->param_version;
+            if (match) {
+                EAB_CUDA(cudaGraphLaunch(sg.exec, st));
+                m->last_launches = sg.launches;
+            } else if (m->opt_host_graph && i >= 2 && !g_prof_on()) {
+                if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                int rc = 1;
+                if (ok) {
+                    rc = eab_enhance(m, din[s], dout[s], B, L, ws, need, stream);
+                    ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+                }
+                if (ok) ok = cudaGraphInstantiate(&sg.exec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                if (ok) {
+                    sg.in = din[s]; sg.out = dout[s]; sg.ws = ws; sg.B = B; sg.L = L; sg.version = m->param_version;
+                    sg.launches = m->last_launches;
+                    EAB_CUDA(cudaGraphLaunch(sg.exec, st));
+                } else {
+                    sg.exec = nullptr;
+                    cudaGetLastError();                        // capture refused (e.g. a legacy-stream caller): run the step directly
+                    EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, stream));
+                }
+            } else {
+                EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, stream));
+            }
+        }
         launches += m->last_launches;
         EAB_CUDA(cudaEventRecord(m->ev_comp[s], st));
         EAB_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_comp[s], 0));
@@ -2446,6 +2497,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "staged") m->opt_staged = value != 0;
     else if (n == "lazy") m->opt_lazy = value != 0;
     else if (n == "tcm_chain") m->opt_tcm_chain = value;
+    else if (n == "host_graph") m->opt_host_graph = value != 0;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "conv_exp") m->opt_conv_exp = value;
