@@ -107,14 +107,16 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
                 const int t = (int)__umulhi((unsigned)r, a.p_magic);
                 const int col = r - t * a.P;
                 const int k0 = slab * KC + c8 * 8;
-                if (col < a.plane_cols[0] && k0 < a.wide_k) {
+                // the window never leaves its frame: in the pair layout the last row's second position is past the last bin
+                const int wk = min(a.wide_k, (a.Fin - col * a.col_stride) * src.C);
+                if (col < a.plane_cols[0] && k0 < wk) {
                     const float* p = src.x + (((size_t)b * a.T + t) * a.Fin + (size_t)col * a.col_stride) * src.C + k0;     // 8-byte aligned
                     float x[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float2 q = make_float2(0.f, 0.f);
-                        if (k0 + 2 * i < a.wide_k) q = __ldg(reinterpret_cast<const float2*>(p) + i);
-                        x[2 * i] = q.x; x[2 * i + 1] = k0 + 2 * i + 1 < a.wide_k ? q.y : 0.f;
+                        if (k0 + 2 * i < wk) q = __ldg(reinterpret_cast<const float2*>(p) + i);
+                        x[2 * i] = q.x; x[2 * i + 1] = k0 + 2 * i + 1 < wk ? q.y : 0.f;
                     }
                     v0 = make_float4(x[0], x[1], x[2], x[3]);
                     v1 = make_float4(x[4], x[5], x[6], x[7]);

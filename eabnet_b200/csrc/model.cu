@@ -116,6 +116,11 @@ struct ConvLayer {
     size_t off_whi[2] = {0, 0}, off_wlo[2] = {0, 0}, off_ub = 0;
     // gated 64-channel layers also get channel-split images: split s = value | gate of channels 32 s .. 32 s + 32 (N = 64),
     // so that a split's weights can stay resident in shared memory where the full N = 128 set cannot
+    // first layer, "pair" layout: a plane row holds two adjacent frequency positions (2 x cin values, one 64-wide slab); an
+    // output position reads ceil(kf / 2) consecutive rows, so taps = kt x ceil(kf / 2) row shifts (stride-2 conv only)
+    bool pair_ok = false;
+    int p_ntaps = 0, p_dt[kMaxTaps], p_ds[kMaxTaps];
+    size_t off_phi = 0, off_plo = 0;
     bool has_split = false;
     size_t off_shi[2][2] = {{0, 0}, {0, 0}}, off_slo[2][2] = {{0, 0}, {0, 0}}, off_sub[2] = {0, 0};
     NormAct na;
@@ -237,12 +242,14 @@ struct eab_model {
     int opt_enc_passes = 3;       // 3xTF32 in the encoder (single-pass TF32 there costs 4.8e-4 of the 1e-3 budget)
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
     int opt_inner_passes = 3;     // inner U-Nets of the encoder modules
+    int opt_first_passes = 3;     // the first gated conv (2M input channels, tap-window rows: 3.5x the input bytes per pass-plane)
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
     int opt_half_act = 0;         // raw outputs of the single-pass decoder layers stored as fp16: measured -1 % step time for +30 % output error, so off
     int opt_round_half = 0;       // diagnostics: fp16-rounded storage of the decoder's inner activations
     int opt_fused = 0;            // conv_tma with in-kernel producers (no stage pass, no plane images in HBM)
+    int opt_pair = 1;             // first layer: frequency-pair plane rows instead of whole tap-window rows
     int opt_wide_staged = 1;      // first layer through stage_kernel (tap-window rows) + conv_tma instead of the gather kernel
     int opt_split = 0;            // gated 1-pass layers whose weights cannot stay resident run as two channel-split launches
     int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
@@ -366,6 +373,7 @@ int build(eab_model* m) {
             m->en_mod.push_back(bd.module("en.meta_unet_list." + std::to_string(i), c.c, c.k1_t, c.k1_f, 4 - i, false));
         m->en_mod[0].in_conv.perm_ri = true;
         m->en_mod[0].in_conv.M = c.M;
+        m->en_mod[0].in_conv.zone = 3;
         m->en_last = bd.gated("en.last_conv", c.c, 64, c.k1_t, c.k1_f, false, true);
         m->de_mod.push_back(bd.module("de.meta_unet_list.0", 128, c.k1_t, c.k1_f, 1, true));
         for (int i = 1; i < 4; ++i)
@@ -696,6 +704,36 @@ struct Packer {
         L.off_ub = alloc(cout_t);
         for (int n = 0; n < cout_t; ++n) blob[L.off_ub + n] = P(L.b)[n];
         L.umma_ok = true;
+        if (L.wide && !L.deconv && 2 * L.cin <= 64 && L.kt * ((L.kf + 1) / 2) <= kMaxTaps) {
+            const int ns = (L.kf + 1) / 2;
+            L.p_ntaps = L.kt * ns;
+            const size_t img = (size_t)L.p_ntaps * cout_t * 32;            // floats: one 64-wide slab per tap
+            L.off_phi = alloc(img);
+            L.off_plo = alloc(img);
+            __half* phi = reinterpret_cast<__half*>(blob.data() + L.off_phi);
+            __half* plo = reinterpret_cast<__half*>(blob.data() + L.off_plo);
+            int q = 0;
+            for (int j = 0; j < L.kt; ++j)
+                for (int sft = 0; sft < ns; ++sft, ++q) {
+                    L.p_dt[q] = L.kt - 1 - j;
+                    L.p_ds[q] = sft;
+                    const size_t base = (size_t)q * cout_t * 64;
+                    for (int n = 0; n < cout_t; ++n)
+                        for (int k = 0; k < 64; ++k) {
+                            const int pos = k / L.cin, cm = k - pos * L.cin;       // position inside the pair, memory channel
+                            float w = 0.f;
+                            if (pos < 2 && 2 * sft + pos < L.kf) {
+                                int ci = cm;                                      // memory channel -> reference channel
+                                if (L.perm_ri) { const int mic = cm / 2, ri = cm - 2 * mic; ci = ri * L.M + mic; }
+                                w = W[(((size_t)n * L.cin + ci) * L.kt + j) * L.kf + 2 * sft + pos];
+                            }
+                            const __half hi = __float2half_rn(w);
+                            phi[base + sw128_index_h(n, k)] = hi;
+                            plo[base + sw128_index_h(n, k)] = __float2half_rn(w - __half2float(hi));
+                        }
+                }
+            L.pair_ok = true;
+        }
         if (L.gated && co == 64 && !L.wide) {
             for (int sp = 0; sp < 2; ++sp) {
                 L.off_sub[sp] = alloc(64);
@@ -1164,7 +1202,7 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n, bool out_half = false) {
 }
 
 inline int zone_passes(const eab_model* m, int zone) {
-    return zone == 0 ? m->opt_enc_passes : zone == 1 ? m->opt_dec_passes : m->opt_inner_passes;
+    return zone == 3 ? m->opt_first_passes : zone == 0 ? m->opt_enc_passes : zone == 1 ? m->opt_dec_passes : m->opt_inner_passes;
 }
 
 // one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
@@ -1210,20 +1248,41 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
         memset(&p, 0, sizeof(p));
         p.nsrc = 1;
         set_src(p.src[0], srcs[0]);
-        p.B = cx.B; p.T = cx.T; p.Fin = Fin; p.E = Fout; p.P = Fout;
-        p.nplanes = 1; p.plane_cols[0] = Fout; p.col_stride = 2; p.col_off[0] = 0;
-        p.ntaps = L.u_ntaps[0];
-        int back = 0;
-        for (int i = 0; i < p.ntaps; ++i) { p.tap_plane[i] = 0; p.tap_shift[i] = -L.u_dt[0][i] * p.P; back = std::max(back, -p.tap_shift[i]); }
-        p.back = back; p.fwd = 0;
+        const bool pair = L.pair_ok && cx.m->opt_pair;
+        p.B = cx.B; p.T = cx.T; p.Fin = Fin; p.E = Fout;
+        p.nplanes = 1; p.col_stride = 2; p.col_off[0] = 0;
+        int back = 0, fwd = 0;
+        if (pair) {
+            // rows = frequency PAIRS (2 x cin values each): 1.8x the input bytes per pass-plane instead of 3.6x for window rows
+            p.P = (Fin + 1) / 2;
+            p.plane_cols[0] = p.P;
+            p.ntaps = L.p_ntaps;
+            for (int i = 0; i < p.ntaps; ++i) {
+                p.tap_plane[i] = 0; p.tap_shift[i] = -L.p_dt[i] * p.P + L.p_ds[i];
+                back = std::max(back, -p.tap_shift[i]); fwd = std::max(fwd, p.tap_shift[i]);
+            }
+            p.nslab = 1;
+            p.Whi = cx.W(L.off_phi); p.Wlo = cx.W(L.off_plo);
+            p.algo_frac = (float)(L.kf * cin) / (float)(((L.kf + 1) / 2) * 64);
+            p.wide_k = 2 * cin;
+        } else {
+            p.P = Fout;
+            p.plane_cols[0] = Fout;
+            p.ntaps = L.u_ntaps[0];
+            for (int i = 0; i < p.ntaps; ++i) { p.tap_plane[i] = 0; p.tap_shift[i] = -L.u_dt[0][i] * p.P; back = std::max(back, -p.tap_shift[i]); }
+            p.nslab = L.u_nslab;
+            p.Whi = cx.W(L.off_whi[0]); p.Wlo = cx.W(L.off_wlo[0]);
+            p.algo_frac = (float)L.u_kwidth / (float)(L.u_nslab * 64);
+            p.wide_k = L.u_kwidth;
+        }
+        p.back = back; p.fwd = fwd;
         p.out_stride = 1; p.out_off = 0; p.Fout = Fout;
-        p.nslab = L.u_nslab; p.ncoef = cin; p.npass = zone_passes(cx.m, L.zone);
-        p.Whi = cx.W(L.off_whi[0]); p.Wlo = cx.W(L.off_wlo[0]); p.bias = cx.W(L.off_ub);
-        p.Cout = L.cout; p.N = L.u_N; p.gate_off = L.u_gate_off; p.algo_frac = (float)L.u_kwidth / (float)(L.u_nslab * 64);
+        p.ncoef = cin; p.npass = zone_passes(cx.m, L.zone);
+        p.bias = cx.W(L.off_ub);
+        p.Cout = L.cout; p.N = L.u_N; p.gate_off = L.u_gate_off;
         p.out = out->data; p.out_ld = L.cout; p.out_coff = 0;
         if (stats) { p.nstats = 1; p.stats[0] = stats; }
         p.tiles_per_b = (int)(((long long)cx.T * p.P + 127) / 128);
-        p.wide_k = L.u_kwidth;
         const bool geom_ok = (srcs[0].C * p.col_stride) % 2 == 0 && (Fin * srcs[0].C) % 2 == 0 &&      // 8-byte aligned windows
                              (Fout - 1) * 2 + L.kf <= Fin && p.P >= 1 &&
                              ((long long)cx.T * p.P + p.back + 4 * 128 + 2ll * p.P) * p.P < (1ll << 31);
@@ -2503,6 +2562,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "conv_exp") m->opt_conv_exp = value;
     else if (n == "split") m->opt_split = value != 0;
     else if (n == "wide_staged") m->opt_wide_staged = value != 0;
+    else if (n == "pair") m->opt_pair = value != 0;
     else if (n == "fused") m->opt_fused = value != 0;
     else if (n == "round_half") m->opt_round_half = value != 0;
     else if (n == "half_act") m->opt_half_act = value != 0;
@@ -2512,6 +2572,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "enc_passes" && (value == 1 || value == 3)) { m->opt_enc_passes = value; m->opt_inner_passes = value; }
     else if (n == "dec_passes" && (value == 1 || value == 3)) m->opt_dec_passes = value;
     else if (n == "inner_passes" && (value == 1 || value == 3)) m->opt_inner_passes = value;
+    else if (n == "first_passes" && (value == 1 || value == 3)) m->opt_first_passes = value;
     else if (n == "dbg_launch") {
         m->opt_dbg_launch = value;
         if (!m->dbg_buf) { if (check_cuda(cudaMalloc(&m->dbg_buf, 16 * sizeof(unsigned long long)), "dbg alloc")) return 1; }

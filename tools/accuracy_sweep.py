@@ -17,7 +17,12 @@ for seed, variant, L in [(0, "B", 96000), (1, "A", 96000), (2, "B", 64000)]:
         with torch.no_grad():
             out = net(spec.cuda()).cpu()
         row.append("enc%d/dec%d/inner%d: %.2e" % (enc, dec, inner, float((out - ref).abs().max())))
-    net.set_option("enc_passes", 3); net.set_option("dec_passes", 1); net.set_option("round_half", 1)
+    net.set_option("enc_passes", 3); net.set_option("dec_passes", 1); net.set_option("first_passes", 1)
+    with torch.no_grad():
+        out = net(spec.cuda()).cpu()
+    net.set_option("first_passes", 3)
+    row.append("default + single-pass first layer: %.2e" % float((out - ref).abs().max()))
+    net.set_option("round_half", 1)
     with torch.no_grad():
         out = net(spec.cuda()).cpu()
     net.set_option("round_half", 0)
