@@ -202,17 +202,19 @@ def postnet_throughput(args, dev, wave):
     w = make_eabnet_with_postnet(default_postnet_args()).eval().to(dev)
     steps = max(3, min(args.steps, 10))
     with torch.no_grad():
+        g = w.graphed_enhance(wave) if not args.no_graph else None
+        run_step = g.step if g is not None else (lambda: w.enhance(wave))
         for _ in range(3):
-            y = w.enhance(wave)
+            y = run_step()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            y = w.enhance(wave)
+            y = run_step()
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / steps
-        launches = w.eabnet.last_launch_count()
+        launches = g.launches if g is not None else w.eabnet.last_launch_count()
         w.postnet.profile(True)
         w.enhance(wave)
         prof = w.postnet.profile_summary()

@@ -347,7 +347,8 @@ class GraphedEnhance:
     """eab_enhance on a fixed input buffer as a CUDA graph: `step()` replays it and returns the (static) output tensor.
     The input tensor is read in place, so new audio is enhanced by copying it into `wave` before the replay."""
 
-    def __init__(self, net: "EaBNet", wave: torch.Tensor):
+    def __init__(self, net, wave: torch.Tensor):
+        # `net`: anything with enhance(wave) and last_launch_count() - EaBNet, or EaBNetWithPostNet (beamformer + post-filter)
         self.net, self.wave = net, wave
         dev = wave.device
         with torch.cuda.device(dev), torch.no_grad():

@@ -139,6 +139,14 @@ class EaBNetWithPostNet(nn.Module):
                                                ws.numel(), stream), "eab_enhance_postnet")
         return out
 
+    def last_launch_count(self) -> int:
+        return self.eabnet.last_launch_count()
+
+    def graphed_enhance(self, wave: torch.Tensor):
+        """`enhance` on a fixed device buffer captured once into a CUDA graph (see EaBNet.graphed_enhance)."""
+        from .model import GraphedEnhance
+        return GraphedEnhance(self, wave)
+
     def freeze_eabnet(self):
         for param in self.eabnet.parameters():
             param.requires_grad = False

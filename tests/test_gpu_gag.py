@@ -180,3 +180,20 @@ def test_postnet_full_size_config2_slice_against_oracle():
     for sl in (slice(0, 2), slice(62, 64)):
         assert float((big[sl] - ref).abs().max()) <= TOL * max(1.0, float(ref.abs().max()))
         assert float((big[sl] - got).abs().max()) <= 5e-4 * max(1.0, float(got.abs().max()))
+
+
+def test_postnet_graphed_enhance_matches_eager_call():
+    """CUDA-graph replay of eab_enhance_postnet (cooperative chain launches included) == the plain call"""
+    from eabnet_b200 import make_eabnet_with_postnet
+    from eabnet_b200.postnet import default_postnet_args
+    w = make_eabnet_with_postnet(default_postnet_args()).eval()
+    w.load_state_dict(G.make_postnet_weights(None, None, 4, "B"), strict=True)
+    w.cuda()
+    wave, _ = O.make_wave(2, 9, 4800, seed=8)
+    buf = wave.cuda()
+    with torch.no_grad():
+        ref = w.enhance(buf).clone()
+        g = w.graphed_enhance(buf)
+        assert torch.equal(g.step(), ref)
+        assert torch.equal(g.step(), ref)
+    assert g.launches > 0
