@@ -87,3 +87,31 @@ def test_gag_oracle_matches_live_reference():
         ref = net(x, pre)
     for a, b in zip(ref, G.gag_forward(sd, x, pre, cfg)):
         assert (a - b).abs().max() <= 2e-5 * max(1.0, float(a.abs().max()))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present on this box")
+def test_default_postnet_args_equal_reference_argparse_defaults():
+    """eabnet_b200.postnet.default_postnet_args() mirrors the argparse defaults of train_distributed.py:277-318"""
+    import ast
+    from eabnet_b200.postnet import default_postnet_args
+    src = open("/root/reference/train_distributed.py").read()
+    ref = {}
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument" and node.args:
+            name = getattr(node.args[0], "value", "")
+            if not isinstance(name, str) or not name.startswith("--"):
+                continue
+            for kw in node.keywords:
+                if kw.arg == "default":
+                    try:
+                        ref[name[2:]] = ast.literal_eval(kw.value)
+                    except Exception:
+                        pass
+    mine = vars(default_postnet_args())
+    checked = 0
+    for k, v in mine.items():
+        if k in ref:
+            a, b = (list(v) if isinstance(v, (tuple, list)) else v), (list(ref[k]) if isinstance(ref[k], (tuple, list)) else ref[k])
+            assert a == b, (k, v, ref[k])
+            checked += 1
+    assert checked >= 25, checked

@@ -197,3 +197,19 @@ def test_postnet_graphed_enhance_matches_eager_call():
         assert torch.equal(g.step(), ref)
         assert torch.equal(g.step(), ref)
     assert g.launches > 0
+
+
+@pytest.mark.parametrize("over", [{"kd1": 2, "p": 1, "q": 1}, {"kd1": 5, "p": 1, "q": 2, "dilas": (1, 3)}, {"kd1": 4, "q": 1, "norm_type": "BN"},
+                                  {"cd1": 32, "p": 1, "q": 1}])
+def test_gag_other_kernel_sizes_and_widths(over):
+    """dilated kernel sizes 2 / 4 (chain kernel templates), 5 (layer-by-layer path: more than four operand units) and a squeezed
+    width the chain kernel does not take (cd1 = 32: generic path) against the oracle"""
+    cfg = G.make_gag_cfg(**over)
+    net, sd = _gag(cfg, "B", seed=6)
+    g = torch.Generator().manual_seed(21)
+    x, pre = 0.5 * torch.randn(2, 2, 70, 161, generator=g), 0.3 * torch.randn(2, 2, 70, 161, generator=g)
+    ref = torch.stack(G.gag_forward(sd, x, pre, cfg)).transpose(-2, -1)
+    with torch.no_grad():
+        got = net.forward_time_major(x.cuda(), pre.cuda()).cpu()
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) <= TIGHT * scale
