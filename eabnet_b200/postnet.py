@@ -162,7 +162,8 @@ def make_eabnet_with_postnet(args) -> EaBNetWithPostNet:
 
 
 def default_postnet_args(**over):
-    """The argparse defaults of train_distributed.py:277-318 / enhance.py as a namespace (convenience for tests / bench)."""
+    """The argparse defaults of train_distributed.py:277-318 / enhance.py as a namespace (convenience for tests / bench),
+    except M: the script defaults to its 8-microphone checkpoint, this follows EaBNet.py's own default and BASELINE.json (9)."""
     import argparse
     d = dict(k1=(2, 3), k2=(1, 3), c=64, M=9, embed_dim=64, kd1=5, cd1=64, d_feat=256, p=6, q=3, is_causal=True, is_u2=True,
              bf_type="lstm", topo_type="mimo", intra_connect="cat", norm_type="IN", ref_mic=0, freeze_eabnet=False,

@@ -109,9 +109,10 @@ def test_default_postnet_args_equal_reference_argparse_defaults():
                         pass
     mine = vars(default_postnet_args())
     checked = 0
+    assert ref["M"] == 8 and mine["M"] == 9          # the script's default is its 8-mic checkpoint; ours is EaBNet.py's / BASELINE's 9
     for k, v in mine.items():
-        if k in ref:
+        if k in ref and k != "M":
             a, b = (list(v) if isinstance(v, (tuple, list)) else v), (list(ref[k]) if isinstance(ref[k], (tuple, list)) else ref[k])
             assert a == b, (k, v, ref[k])
             checked += 1
-    assert checked >= 25, checked
+    assert checked >= 24, checked
