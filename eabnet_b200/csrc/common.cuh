@@ -432,7 +432,8 @@ struct PcmArgs {
 int launch_pcm16_to_float(const PcmArgs& a, cudaStream_t st);
 int launch_float_to_pcm16(const float* x, short* out, size_t n, cudaStream_t st);
 
-int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st);
+// scratch: optional device buffer for the tensor-core path's hop planes (else a library-owned grow-only buffer, one per device)
+int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st, void* scratch = nullptr, size_t scratch_bytes = 0);
 int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st);
 // streaming front/back end (stft.cu): one hop in -> spectrum frame *step into a ring; spectrum frame -> one hop out
 // (delayed by one hop: overlap-add needs the next frame), carried state in prev_hop [S][M][160] / tail [S][160]

@@ -230,6 +230,8 @@ struct eab_model {
     size_t scratch_bytes = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host front door
     cudaStream_t s_comp = nullptr;                    // its compute stream when the caller passes the legacy default stream (not capturable)
+    cudaStream_t s_comp2 = nullptr;                   // second compute stream: odd batches (option dual_stream)
+    int opt_dual_stream = 1;
     // the per-slot step of the host front door as a CUDA graph (captured on the slot's second use, replayed afterwards)
     struct SlotGraph { cudaGraphExec_t exec = nullptr; const void* in = nullptr; void* out = nullptr; void* ws = nullptr; int B = 0, L = 0;
                        unsigned long long version = 0; int launches = 0; };
@@ -2159,6 +2161,7 @@ void eab_destroy(eab_model* m) {
         cudaStreamDestroy(m->s_in);
         cudaStreamDestroy(m->s_out);
         cudaStreamDestroy(m->s_comp);
+        cudaStreamDestroy(m->s_comp2);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_in[i]); cudaEventDestroy(m->ev_comp[i]); cudaEventDestroy(m->ev_out[i]); }
     }
     delete m;
@@ -2250,7 +2253,8 @@ int eab_enhance(eab_model* m, const float* wave, float* enhanced, int B, int L, 
     float* outp = reinterpret_cast<float*>(p);
     p += align256((size_t)B * 2 * T * 161 * sizeof(float));
     reset_launch_count();
-    int rc = launch_stft(wave, spec, B, m->cfg.M, L, st);
+    // the forward workspace is idle until the STFT has finished: it doubles as the STFT's plane scratch
+    int rc = launch_stft(wave, spec, B, m->cfg.M, L, st, p, ws_bytes - (size_t)(p - static_cast<char*>(ws)));
     if (!rc) rc = forward(m, spec, outp, B, T, p, ws_bytes - (size_t)(p - static_cast<char*>(ws)), st);
     if (!rc) rc = launch_istft(outp, enhanced, B, T, st);
     m->last_launches = launch_count();
@@ -2317,7 +2321,10 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
     const size_t in_bytes = (size_t)B * m->cfg.M * L * sizeof(float);
     const size_t out_bytes = (size_t)B * 160 * (L / 160) * sizeof(float);
     const size_t in_b = align256(in_bytes), out_b = align256(out_bytes);
-    const size_t total = nslot * (in_b + out_b) + need;
+    // two compute streams (even / odd batches, a workspace each): consecutive batches overlap wherever one leaves SMs idle
+    // (the LSTM runs on 108 of the 148 SMs for 4 ms of a 22 ms step)
+    const bool dual = m->opt_dual_stream && nslot == 2;
+    const size_t total = nslot * (in_b + out_b) + (dual ? 2 : 1) * align256(need);
     if (m->scratch_bytes < total) {
         if (m->scratch) cudaFree(m->scratch);
         m->scratch = nullptr;
@@ -2329,6 +2336,7 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
         EAB_CUDA(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
         EAB_CUDA(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
         EAB_CUDA(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
+        EAB_CUDA(cudaStreamCreateWithFlags(&m->s_comp2, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             EAB_CUDA(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
             EAB_CUDA(cudaEventCreateWithFlags(&m->ev_comp[i], cudaEventDisableTiming));
@@ -2347,52 +2355,56 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
     char* p = static_cast<char*>(m->scratch);
     float* din[2] = {reinterpret_cast<float*>(p), reinterpret_cast<float*>(p + (nslot - 1) * in_b)};
     float* dout[2] = {reinterpret_cast<float*>(p + nslot * in_b), reinterpret_cast<float*>(p + nslot * in_b + (nslot - 1) * out_b)};
-    char* ws = p + nslot * (in_b + out_b);
+    char* ws_slot[2] = {p + nslot * (in_b + out_b), p + nslot * (in_b + out_b) + (dual ? align256(need) : 0)};
+    cudaStream_t cs[2] = {st, dual ? m->s_comp2 : st};
     // the copy streams start after everything already queued on the caller's stream (scratch may still be in use)
     EAB_CUDA(cudaEventRecord(m->ev_comp[0], st));
     EAB_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_comp[0], 0));
+    if (dual) EAB_CUDA(cudaStreamWaitEvent(m->s_comp2, m->ev_comp[0], 0));
     int launches = 0;
     for (int i = 0; i < n_batches; ++i) {
         const int s = i & 1;
+        cudaStream_t cst = cs[s];
+        char* ws = ws_slot[s];
         if (i >= 2) EAB_CUDA(cudaStreamWaitEvent(m->s_in, m->ev_comp[s], 0));          // batch i-2 has consumed this input slot
         EAB_CUDA(cudaMemcpyAsync(din[s], waves_host[i], in_bytes, cudaMemcpyHostToDevice, m->s_in));
         EAB_CUDA(cudaEventRecord(m->ev_in[s], m->s_in));
-        EAB_CUDA(cudaStreamWaitEvent(st, m->ev_in[s], 0));
-        if (i >= 2) EAB_CUDA(cudaStreamWaitEvent(st, m->ev_out[s], 0));                // batch i-2 has left this output slot
+        EAB_CUDA(cudaStreamWaitEvent(cst, m->ev_in[s], 0));
+        if (i >= 2) EAB_CUDA(cudaStreamWaitEvent(cst, m->ev_out[s], 0));               // batch i-2 has left this output slot
         // the slot's step: replayed from a CUDA graph once the slot has run it directly (same buffers, same shape, same weights)
         {
             eab_model::SlotGraph& sg = m->slot_graph[s];
             const bool match = sg.exec && sg.in == din[s] && sg.out == dout[s] && sg.ws == ws && sg.B == B && sg.L == L &&
                                sg.version == m->param_version;
             if (match) {
-                EAB_CUDA(cudaGraphLaunch(sg.exec, st));
+                EAB_CUDA(cudaGraphLaunch(sg.exec, cst));
                 m->last_launches = sg.launches;
             } else if (m->opt_host_graph && i >= 2 && !g_prof_on()) {
                 if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
                 cudaGraph_t graph = nullptr;
-                bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                bool ok = cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
                 int rc = 1;
                 if (ok) {
-                    rc = eab_enhance(m, din[s], dout[s], B, L, ws, need, stream);
-                    ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+                    rc = eab_enhance(m, din[s], dout[s], B, L, ws, need, cst);
+                    ok = cudaStreamEndCapture(cst, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
                 }
                 if (ok) ok = cudaGraphInstantiate(&sg.exec, graph, 0) == cudaSuccess;
                 if (graph) cudaGraphDestroy(graph);
                 if (ok) {
                     sg.in = din[s]; sg.out = dout[s]; sg.ws = ws; sg.B = B; sg.L = L; sg.version = m->param_version;
                     sg.launches = m->last_launches;
-                    EAB_CUDA(cudaGraphLaunch(sg.exec, st));
+                    EAB_CUDA(cudaGraphLaunch(sg.exec, cst));
                 } else {
                     sg.exec = nullptr;
                     cudaGetLastError();                        // capture refused (e.g. a legacy-stream caller): run the step directly
-                    EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, stream));
+                    EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, cst));
                 }
             } else {
-                EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, stream));
+                EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, cst));
             }
         }
         launches += m->last_launches;
-        EAB_CUDA(cudaEventRecord(m->ev_comp[s], st));
+        EAB_CUDA(cudaEventRecord(m->ev_comp[s], cst));
         EAB_CUDA(cudaStreamWaitEvent(m->s_out, m->ev_comp[s], 0));
         EAB_CUDA(cudaMemcpyAsync(enhanced_host[i], dout[s], out_bytes, cudaMemcpyDeviceToHost, m->s_out));
         EAB_CUDA(cudaEventRecord(m->ev_out[s], m->s_out));
@@ -2400,6 +2412,7 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
     m->last_launches = launches;
     EAB_CUDA(cudaStreamSynchronize(m->s_out));
     EAB_CUDA(cudaStreamSynchronize(st));
+    if (dual) EAB_CUDA(cudaStreamSynchronize(m->s_comp2));
     return 0;
 }
 
@@ -2557,6 +2570,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "lazy") m->opt_lazy = value != 0;
     else if (n == "tcm_chain") m->opt_tcm_chain = value;
     else if (n == "host_graph") m->opt_host_graph = value != 0;
+    else if (n == "dual_stream") m->opt_dual_stream = value != 0;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "conv_exp") m->opt_conv_exp = value;

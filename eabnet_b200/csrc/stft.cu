@@ -446,7 +446,8 @@ __global__ void __launch_bounds__(256) stft_stage_kernel(const float* __restrict
     }
 }
 
-int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int L, int T, cudaStream_t st) {
+int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int L, int T, cudaStream_t st, void* scratch,
+                   size_t scratch_bytes) {
     PlaneConvArgs a;
     memset(&a, 0, sizeof(a));
     // rows of batch item b are (hop j, mic) with pitch M, so that the epilogue's lanes write consecutive mics
@@ -467,7 +468,11 @@ int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int 
     a.np_front = front;
     const size_t image_bytes = (size_t)a.B * a.np_rows * 128;
     const size_t need = image_bytes * DFT_SLABS * 2;
-    {
+    // hop planes: the caller's scratch when it is large enough (eab_enhance lends the forward workspace, which is idle until
+    // the STFT has finished - concurrent calls on different streams then share nothing), else the library's grow-only buffer
+    uint8_t* planes = nullptr;
+    if (scratch && scratch_bytes >= need) planes = static_cast<uint8_t*>(scratch);
+    if (!planes) {
         std::lock_guard<std::mutex> lk(g_tab_mu);
         if (t->planes_bytes < need) {
             if (t->planes) { EAB_CUDA(cudaStreamSynchronize(st)); EAB_CUDA(cudaFree(t->planes)); }
@@ -475,12 +480,13 @@ int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int 
             EAB_CUDA(cudaMalloc(&t->planes, need));
             t->planes_bytes = need;
         }
+        planes = static_cast<uint8_t*>(t->planes);
     }
-    for (int i = 0; i < DFT_SLABS * 2; ++i) a.np[i] = static_cast<uint8_t*>(t->planes) + (size_t)i * image_bytes;
+    for (int i = 0; i < DFT_SLABS * 2; ++i) a.np[i] = planes + (size_t)i * image_bytes;
     {
         ProfScope ps("stage", 0.0, 4.0 * (double)B * M * L + (double)need, st);
         dim3 grid((a.np_rows + 255) / 256, DFT_SLABS, a.B);
-        EAB_CUDA(launch_k(stft_stage_kernel, grid, dim3(256), (size_t)0, st, wave, static_cast<uint8_t*>(t->planes), image_bytes,
+        EAB_CUDA(launch_k(stft_stage_kernel, grid, dim3(256), (size_t)0, st, wave, planes, image_bytes,
                           a.np_rows, a.np_front, L, T, M));
         EAB_LAUNCH_CHECK("stft_stage_kernel");
     }
@@ -494,13 +500,13 @@ int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int 
     return 0;
 }
 
-int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st) {
+int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st, void* scratch, size_t scratch_bytes) {
     if (L < HOP + 1) return fail("stft: need at least 161 samples (reflect padding of 160)");
     if (B <= 0 || M <= 0) return fail("stft: bad shape");
     Tables* t;
     EAB_TRY(get_tables(&t));
     const int T = 1 + L / HOP;
-    if (g_stft_tc) return launch_stft_tc(t, wave, spec, B, M, L, T, st);
+    if (g_stft_tc) return launch_stft_tc(t, wave, spec, B, M, L, T, st, scratch, scratch_bytes);
     static bool configured = false;
     if (!configured) {
         EAB_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
