@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=256, help="concurrent causal streams of the latency measurement")
     ap.add_argument("--stream-steps", type=int, default=1000, help="timed 10 ms hops of the latency measurement (0 = skip)")
+    ap.add_argument("--single-stream", action="store_true", help="replay the step graph on one stream instead of alternating two")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step's launches from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-postnet", action="store_true", help="skip the EaBNet + GaGNet post-filter measurement")
     args = ap.parse_args()
@@ -283,10 +284,34 @@ def main():
     with torch.no_grad():
         # the device-resident step is replayed from a CUDA graph (EaBNet.graphed_enhance): the ~260 launches of a step are
         # enqueued by the driver, not by this Python thread, so a busy host cannot turn the measurement launch-bound
-        step = net.graphed_enhance(wave) if not args.no_graph else None
-        run_step = step.step if step is not None else (lambda: net.enhance(wave))
-        for _ in range(args.warmup):
-            run_step()
+        # Two graphs (a workspace each) alternate on two streams, like the two compute streams of the host front door: while one
+        # step's LSTM holds 108 of the 148 SMs, the other step's kernels use the rest.  Every step is a full pass over the batch.
+        if args.no_graph:
+            graphs, streams = [], [torch.cuda.current_stream(dev)]
+            run_step = lambda i: net.enhance(wave)            # noqa: E731
+        else:
+            ng = 1 if args.single_stream else 2
+            graphs = [net.graphed_enhance(wave, private_workspace=True) for _ in range(ng)]
+            streams = [torch.cuda.Stream(dev) for _ in range(ng)]
+
+            def run_step(i):
+                with torch.cuda.stream(streams[i % ng]):
+                    return graphs[i % ng].step()
+        cur = torch.cuda.current_stream(dev)
+
+        def fork():                                           # the side streams start after everything queued so far
+            if graphs:
+                for s_ in streams:
+                    s_.wait_stream(cur)
+
+        def join():                                           # ... and the current stream continues after them
+            if graphs:
+                for s_ in streams:
+                    cur.wait_stream(s_)
+        fork()
+        for i in range(args.warmup):
+            run_step(i)
+        join()
         barrier()
         sampler.rows.clear()             # keep only samples taken from here on (timed regions)
         # ---- device-resident throughput
@@ -294,14 +319,17 @@ def main():
         barrier()
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         e0.record()
+        fork()
         for i in range(args.steps):
-            y = run_step()
-            marks[i].record()
+            y = run_step(i)
+            marks[i].record(streams[i % len(streams)])
+        join()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) / args.steps
-        step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
-        launches = step.launches if step is not None else net.last_launch_count()
+        done = sorted(e0.elapsed_time(mk) for mk in marks)    # completion times; consecutive differences = per-step pace
+        step_ms = [round(b - a, 3) for a, b in zip([0.0] + done[:-1], done)]
+        launches = graphs[0].launches if graphs else net.last_launch_count()
         # ---- end to end with host buffers: the dataset-scale public call (eab_enhance_host_batches), `steps` batches,
         # every batch uploaded from pinned host memory and its enhanced audio downloaded inside the timed region
         # (uploads / downloads of neighbouring batches overlap compute on the library's copy streams)
@@ -378,7 +406,8 @@ def main():
                            "batch_per_gpu": B, "seconds": args.seconds, "frames": 1 + L // 160,
                            "parallelism": "utterance shards, %d rank(s), no collective" % world,
                            "l2": "inputs (%.0f MB/step) and activations exceed the 126 MB L2" % (B * M * L * 4 / 1e6),
-                           "launch": "python enqueue" if args.no_graph else "CUDA graph replay of eab_enhance"},
+                           "launch": "python enqueue" if args.no_graph else ("CUDA graph replay of eab_enhance" + ("" if args.single_stream else
+                                     ", steps alternating on two streams (two graphs, a workspace each)"))},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * M * L * 4,
                         "d2h_bytes_per_step": B * 160 * (L // 160) * 4,
                         "api": "EaBNet.enhance_host_batches (eab_enhance_host_batches): %d host batches per call, wall clock "

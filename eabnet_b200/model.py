@@ -238,8 +238,10 @@ class EaBNet(_NativeModule):
         return out
 
     # ---------------------------------------------------------------- wave-to-wave (test.py:178-190)
-    def enhance(self, wave: torch.Tensor) -> torch.Tensor:
-        """wave [B,M,L] on the GPU -> enhanced [B,160*(L//160)]: STFT+compression, forward, iSTFT in one call."""
+    def enhance(self, wave: torch.Tensor, workspace: torch.Tensor | None = None) -> torch.Tensor:
+        """wave [B,M,L] on the GPU -> enhanced [B,160*(L//160)]: STFT+compression, forward, iSTFT in one call.
+        `workspace`: a caller-owned uint8 CUDA tensor of at least eab_enhance_workspace_bytes (calls that may run
+        concurrently on different streams must not share the module's own workspace)."""
         self._check_input(wave, "wave")
         B, M, L = wave.shape
         if M != self.M:
@@ -252,7 +254,12 @@ class EaBNet(_NativeModule):
             nbytes = lib.eab_enhance_workspace_bytes(h, B, L)
             if nbytes == 0:
                 _lib.check(1, "eab_enhance_workspace_bytes")
-            ws = self._workspace(nbytes, dev)
+            if workspace is not None:
+                if workspace.device != dev or workspace.dtype != torch.uint8 or workspace.numel() < nbytes:
+                    raise ValueError("workspace must be a uint8 tensor of at least %d bytes on %s" % (nbytes, dev))
+                ws = workspace
+            else:
+                ws = self._workspace(nbytes, dev)
             out = torch.empty((B, 160 * (L // 160)), dtype=torch.float32, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(lib.eab_enhance(h, _ptr(x), _ptr(out), B, L, _ptr(ws), ws.numel(), stream), "eab_enhance")
@@ -333,10 +340,11 @@ class EaBNet(_NativeModule):
                        "eab_enhance_host_pcm16")
         return out
 
-    def graphed_enhance(self, wave: torch.Tensor) -> "GraphedEnhance":
-        """The wave -> wave step on a fixed device buffer captured once into a CUDA graph (one replay = the ~260 kernel
-        launches of eab_enhance without their host-side enqueue cost).  Re-capture after loading new weights."""
-        return GraphedEnhance(self, wave)
+    def graphed_enhance(self, wave: torch.Tensor, private_workspace: bool = False) -> "GraphedEnhance":
+        """The wave -> wave step on a fixed device buffer captured once into a CUDA graph (one replay = the kernel launches
+        of eab_enhance without their host-side enqueue cost).  Re-capture after loading new weights.  With
+        private_workspace=True the graph owns its workspace, so several graphs may replay concurrently on different streams."""
+        return GraphedEnhance(self, wave, private_workspace)
 
     def stream(self, n_streams: int, device: torch.device | str | None = None) -> "EaBNetStream":
         """Carried-state, frame-by-frame inference for `n_streams` concurrent causal streams (eab_stream_*)."""
@@ -347,16 +355,24 @@ class GraphedEnhance:
     """eab_enhance on a fixed input buffer as a CUDA graph: `step()` replays it and returns the (static) output tensor.
     The input tensor is read in place, so new audio is enhanced by copying it into `wave` before the replay."""
 
-    def __init__(self, net, wave: torch.Tensor):
+    def __init__(self, net, wave: torch.Tensor, private_workspace: bool = False):
         # `net`: anything with enhance(wave) and last_launch_count() - EaBNet, or EaBNetWithPostNet (beamformer + post-filter)
         self.net, self.wave = net, wave
         dev = wave.device
+        kw = {}
+        if private_workspace:                              # EaBNet only: a workspace of its own (concurrent replays)
+            B, _, L = wave.shape
+            with torch.cuda.device(dev):
+                net._sync_params(dev)                      # the plan (and its size) depends on the packed weights
+            nbytes = net._native.lib.eab_enhance_workspace_bytes(net._native.h, B, L)
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            kw["workspace"] = self.workspace
         with torch.cuda.device(dev), torch.no_grad():
-            net.enhance(wave)                              # packs weights, sizes the workspace, configures the kernels
+            net.enhance(wave, **kw)                        # packs weights, sizes the workspace, configures the kernels
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.out = net.enhance(wave)
+                self.out = net.enhance(wave, **kw)
         self.launches = net.last_launch_count()
 
     def step(self) -> torch.Tensor:
