@@ -262,3 +262,28 @@ def test_enhance_pcm16_front_door():
     assert int(got.abs().max()) > 50                                        # a real signal came back
     with pytest.raises(RuntimeError):
         net.enhance_pcm16(pcm, mic_order=[0] * 8 + [9])
+
+
+def test_two_private_graphs_on_two_streams():
+    """what bench.py times: two graphs with a workspace each replaying concurrently on two streams == the eager call"""
+    cfg = O.make_cfg()
+    net, _ = _net(cfg, seed=7)
+    wave, _ = O.make_wave(3, 9, 9600, seed=13)
+    buf = wave.cuda()
+    with torch.no_grad():
+        ref = net.enhance(buf).clone()
+        gs = [net.graphed_enhance(buf, private_workspace=True) for _ in range(2)]
+        ss = [torch.cuda.Stream() for _ in range(2)]
+        cur = torch.cuda.current_stream()
+        for s in ss:
+            s.wait_stream(cur)
+        outs = []
+        for i in range(6):
+            with torch.cuda.stream(ss[i % 2]):
+                outs.append(gs[i % 2].step())
+        for s in ss:
+            cur.wait_stream(s)
+        torch.cuda.synchronize()
+    assert torch.equal(outs[-1], ref) and torch.equal(outs[-2], ref)
+    with pytest.raises(ValueError), torch.no_grad():
+        net.enhance(buf, workspace=torch.empty(16, dtype=torch.uint8, device="cuda"))
