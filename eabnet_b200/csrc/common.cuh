@@ -12,6 +12,10 @@ namespace eab {
 void set_error(const std::string& msg);
 int  fail(const std::string& msg);                       // sets the message, returns 1
 int  check_cuda(cudaError_t e, const char* what);        // 0 if ok
+// per-device launch state, safe for several devices / host threads in one process: SM count, and the largest dynamic
+// shared-memory size a kernel has been configured for on the CURRENT device (cudaFuncSetAttribute is per device)
+int device_sm_count(int* sms);
+int ensure_dynamic_smem(const void* kernel, int bytes);
 void count_launch(int n = 1);                            // per-thread launch counter
 int  launch_count();
 void reset_launch_count();
@@ -285,6 +289,54 @@ bool staged_conv_fits(const PlaneConvArgs& a);          // shared-memory / unit-
 int launch_stage(const PlaneConvArgs& a, cudaStream_t st);
 int launch_conv_staged(PlaneConvArgs a, cudaStream_t st);
 extern bool g_stft_tc;           // STFT as a tcgen05 GEMM (default) / fp32 CUDA-core kernel
+
+// ---------------------------------------------------------------------------------------------------
+// conv_raw.cu: the conv layer as ONE kernel, no staged planes in HBM.  The loader bulk-copies the RAW fp32 rows a
+// tile needs (a contiguous (t, fi) range per source tensor) into a shared-memory ring, transform warps apply the
+// producer's norm + PReLU (+ the lazy residual addend), split to fp16 hi (/lo) and write the 128-byte-swizzled operand
+// planes in shared memory, the MMA warp runs the row-shifted-descriptor GEMM of conv_tma on them.  The two output
+// parities of a transposed conv are two "variants" of one launch: they share the operand planes and differ in taps,
+// weights and accumulator columns, so the input is read and normalised once.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRawGroup = 32;            // operand rows per ring stage
+constexpr int kRawMaxStreams = 4;        // (source, addend) tensors
+constexpr int kRawMaxSlabs = 4;          // 64-channel K slabs
+struct RawConvArgs {
+    int nstreams;
+    const float* sx[kRawMaxStreams];     // [B][T][Fin][C] raw fp32
+    int s_C[kRawMaxStreams];
+    int s_stage_off[kRawMaxStreams];     // byte offset of the stream inside a ring stage
+    int s_coef_off[kRawMaxStreams];      // float offset of the stream's [3][C] coefficient block in shared memory
+    Xform s_xf[kRawMaxStreams];
+    int s_mode[kRawMaxStreams];          // 0 none, 1 norm -> PReLU, 2 PReLU -> norm
+    int stage_bytes, ncoef;              // ring stage size (all streams) ; sum of C over the streams
+    int nslab;
+    int sl_s0[kRawMaxSlabs], sl_s1[kRawMaxSlabs];    // streams of the slab's addends (sl_s1 < 0: one addend)
+    int sl_c0[kRawMaxSlabs];             // first channel of the slab inside its stream's rows
+    int B, T, Fin, P;
+    int nplanes, plane_cols[2], col_stride, col_off[2];
+    int back, fwd, tiles_per_b;
+    unsigned int p_magic;
+    int npass;
+    int nvar;                            // 1, or 2 output parities of a transposed conv
+    int E[2], out_off[2], out_stride, Fout;
+    int ntaps[2];
+    const float* Whi[2];
+    const float* Wlo[2];
+    const float* bias;
+    int Cout, N, gate_off;               // Cout == 64 ; N = 64, or 128 when gated (gate_off == 64)
+    float* out;                          // [B][T][Fout][Cout]
+    double* stats;                       // [B][Cout][2] or null
+    int nunits;                          // K units of a tile: (variant, tap, slab, pass)
+    unsigned int unit_a[kMaxConvUnits];  // A operand offset / 16 from the operand buffer origin
+    unsigned short unit_b[kMaxConvUnits];// resident weight image slot
+    unsigned char unit_c[kMaxConvUnits]; // bit 0: variant, bit 7: first unit of the variant, bit 6: last
+    int nbuf, nstage, resident, nsb;     // shared-memory plan (chosen by the launcher)
+    float algo_frac;
+    unsigned long long* dbg;
+};
+bool raw_conv_supported(const PlaneConvArgs* p, int n);
+int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned long long* dbg);
 
 struct CombineArgs {
     ConvSrc src[3];

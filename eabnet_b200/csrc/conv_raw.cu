@@ -1,0 +1,640 @@
+// The 2-D conv layer as ONE kernel (sm_100a): no normalise / stage pass, no fp16 plane images in HBM.
+//
+// A layer's input is stored RAW (what its producer wrote) next to the per-(b,c) InstanceNorm sums; the reference order is
+// conv -> norm -> PReLU (EaBNet.py:402-405, 426-429, 684-686), so the consumer has to apply norm + PReLU before its GEMM.
+// Round 1 did that in a stand-alone stage_kernel that wrote fp16 operand planes to HBM (26 % of the step, 2.25x the
+// algorithmic traffic of the conv stack).  Here the operand is built on chip:
+//
+//   warp 0        loader: per group of 32 operand rows of a tile, the raw fp32 rows it needs are ONE contiguous (t, fi)
+//                 range of each source tensor -> one cp.async.bulk per (source, addend) into a shared-memory ring
+//   warps 12..    transform: ring -> registers -> gamma (x - mean) rstd + beta -> PReLU (+ second addend of a lazy residual
+//                 sum) -> fp16 hi (/ lo for the 3-pass layers) -> 128-byte-swizzled operand planes in shared memory
+//                 (column-parity planes of a stride-2 conv, literal zeros for pad rows / columns), fence.proxy.async,
+//                 mbarrier
+//   warp 1        MMA issuer: taps are row-shifted UMMA descriptors into the planes (as conv_tma), accumulators in TMEM
+//   warp 2        weight loader (resident images, or a ring when they do not fit)
+//   warps 4-11    epilogue: tcgen05.ld -> bias / gate -> 32-byte stores of the RAW output + per-thread running sums for
+//                 the output's InstanceNorm statistics
+//
+// The two output parities of a transposed conv (EaBNet.py:410-431, 463-490) are two variants of the same launch: they
+// share the operand planes (read + normalised once) and use their own taps, weights and accumulator columns.
+// Arithmetic is the stage_kernel + conv_tma_kernel arithmetic, operation for operation: results are bit-identical.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace eab {
+
+namespace {
+
+using namespace umma;
+
+constexpr int TM = 128;
+constexpr int GROUP = kRawGroup;
+constexpr int NSTAGE_MAX = 8;
+constexpr int NSB_MAX = 8;
+constexpr int NCTRL = 128;                       // warps 0-3: loader, MMA issuer, weight loader, spare
+constexpr int NEPI = 256;                        // warps 4-11
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+inline int ceil8(int x) { return (x + 7) & ~7; }
+
+struct RawPlan {
+    int R, plane_bytes, buf_bytes, b_stage_bytes, w_images, ngroups;
+    int b_off, ring_off, bias_off, coef_off, bar_off, total;
+};
+
+__host__ __device__ inline RawPlan make_raw_plan(const RawConvArgs& a) {
+    RawPlan p;
+    p.R = TM + a.back + a.fwd;
+    p.plane_bytes = ((p.R + 7) & ~7) * 128;
+    const int npb = a.npass == 3 ? 2 : 1;
+    p.buf_bytes = a.nplanes * a.nslab * npb * p.plane_bytes;
+    p.b_stage_bytes = a.N * 128;
+    p.w_images = 0;
+    for (int v = 0; v < a.nvar; ++v) p.w_images += a.ntaps[v] * a.nslab * npb;
+    p.ngroups = (p.R + GROUP - 1) / GROUP;
+    p.b_off = a.nbuf * p.buf_bytes;
+    p.ring_off = p.b_off + (a.resident ? p.w_images : a.nsb) * p.b_stage_bytes;
+    p.bias_off = p.ring_off + a.nstage * a.stage_bytes;
+    p.coef_off = p.bias_off + a.N * 4;
+    p.bar_off = (p.coef_off + 3 * a.ncoef * 4 + 15) & ~15;
+    p.total = p.bar_off + 512 + 1024;                    // barriers + slack for the 1024-byte alignment of the base
+    return p;
+}
+
+// raw rows (units of one [C] row of a source tensor, relative to the batch item) that operand rows [32 j, 32 j + 32) of the
+// tile at padded row `row0` read: [g_lo, g_lo + n).  Operand row rho <-> padded row r = row0 - back + rho = t P + col;
+// plane p holds input column col * col_stride + col_off[p] (zeros where that is >= Fin or r is outside [0, T P)).
+__device__ __forceinline__ void group_range(const RawConvArgs& a, int R, int rows_per_b, int row0, int j, int& g_lo, int& n) {
+    int r_a = row0 - a.back + j * GROUP;
+    int r_b = min(r_a + GROUP - 1, row0 - a.back + R - 1);
+    r_a = max(r_a, 0);
+    r_b = min(r_b, rows_per_b - 1);
+    g_lo = 0; n = 0;
+    if (r_a > r_b) return;
+    const int t_a = a.P == 1 ? r_a : (int)__umulhi((unsigned)r_a, a.p_magic);
+    const int c_a = r_a - t_a * a.P;
+    const int t_b = a.P == 1 ? r_b : (int)__umulhi((unsigned)r_b, a.p_magic);
+    const int c_b = r_b - t_b * a.P;
+    g_lo = t_a * a.Fin + min(c_a * a.col_stride, a.Fin);
+    n = t_b * a.Fin + min((c_b + 1) * a.col_stride, a.Fin) - g_lo;
+}
+
+__device__ __forceinline__ float4 lds128(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+
+// norm + PReLU of four channels; mode 0 none, 1 norm -> PReLU (2-D blocks), 2 PReLU -> norm (TCM order).  The expressions
+// are the ones stage_kernel uses, so both paths round identically.
+__device__ __forceinline__ void xf4(float4& v, const float* cf, int C, int mode) {
+    if (mode == 0) return;
+    const float4 s = *reinterpret_cast<const float4*>(cf);
+    const float4 h = *reinterpret_cast<const float4*>(cf + C);
+    const float4 al = *reinterpret_cast<const float4*>(cf + 2 * C);
+    if (mode == 1) {
+        float z;
+        z = fmaf(v.x, s.x, h.x); v.x = fmaxf(z, 0.f) + al.x * fminf(z, 0.f);
+        z = fmaf(v.y, s.y, h.y); v.y = fmaxf(z, 0.f) + al.y * fminf(z, 0.f);
+        z = fmaf(v.z, s.z, h.z); v.z = fmaxf(z, 0.f) + al.z * fminf(z, 0.f);
+        z = fmaf(v.w, s.w, h.w); v.w = fmaxf(z, 0.f) + al.w * fminf(z, 0.f);
+    } else {
+        v.x = fmaf(fmaxf(v.x, 0.f) + al.x * fminf(v.x, 0.f), s.x, h.x);
+        v.y = fmaf(fmaxf(v.y, 0.f) + al.y * fminf(v.y, 0.f), s.y, h.y);
+        v.z = fmaf(fmaxf(v.z, 0.f) + al.z * fminf(v.z, 0.f), s.z, h.z);
+        v.w = fmaf(fmaxf(v.w, 0.f) + al.w * fminf(v.w, 0.f), s.w, h.w);
+    }
+}
+
+// fold 8 per-row values across the 32 rows (lanes) of a warp with a halving butterfly (9 shuffles): every lane gets the
+// total of column ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
+__device__ __forceinline__ float fold8(const float (&u)[8], int lane) {
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    float u4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u4[j] = (h16 ? u[j + 4] : u[j]) + __shfl_xor_sync(0xffffffffu, h16 ? u[j] : u[j + 4], 16);
+    float u2[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) u2[j] = (h8 ? u4[j + 2] : u4[j]) + __shfl_xor_sync(0xffffffffu, h8 ? u4[j] : u4[j + 2], 8);
+    float u1 = (h4 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? u2[0] : u2[1], 4);
+    u1 += __shfl_xor_sync(0xffffffffu, u1, 2);
+    u1 += __shfl_xor_sync(0xffffffffu, u1, 1);
+    return u1;
+}
+
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+// NTW transform warps (8: 640 threads, the register file is re-partitioned between the roles with setmaxnreg)
+template <int NTW>
+__global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(const RawConvArgs a) {
+    constexpr int NTHREADS = NCTRL + NEPI + NTW * 32;
+    constexpr int NTT = NTW * 32;                            // transform threads
+    constexpr int TR0 = NCTRL + NEPI;                        // first transform thread
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const RawPlan pl = make_raw_plan(a);
+    uint8_t* opnd = smem;
+    uint8_t* Bs = smem + pl.b_off;
+    uint8_t* ring = smem + pl.ring_off;
+    float* sbias = reinterpret_cast<float*>(smem + pl.bias_off);
+    float* coef = reinterpret_cast<float*>(smem + pl.coef_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
+    uint64_t* raw_full = bars;              // [NSTAGE_MAX]
+    uint64_t* raw_empty = bars + 8;         // [NSTAGE_MAX]
+    uint64_t* opnd_full = bars + 16;        // [2]
+    uint64_t* opnd_empty = bars + 18;       // [2]
+    uint64_t* b_full = bars + 20;           // [NSB_MAX]
+    uint64_t* b_empty = bars + 28;          // [NSB_MAX]
+    uint64_t* acc_full = bars + 36;         // [2 accumulator sets][2 variants]
+    uint64_t* acc_empty = bars + 40;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int acc_cols = a.nvar * a.N;                       // TMEM columns of one accumulator set
+    const uint32_t tmem_cols = 2 * acc_cols <= 128 ? 128u : (2 * acc_cols <= 256 ? 256u : 512u);
+    const int npb = a.npass == 3 ? 2 : 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE_MAX; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], NTW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&opnd_full[i], NTW); mbar_init(&opnd_empty[i], 1); }
+        for (int i = 0; i < NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&acc_empty[i], NEPI);
+        fence_barrier_init();
+    }
+    pdl_trigger();
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long ntiles = (long long)a.B * a.tiles_per_b;
+    const int tile_begin = (int)(ntiles * blockIdx.x / gridDim.x);
+    const int tile_end = (int)(ntiles * (blockIdx.x + 1) / gridDim.x);
+    const int rows_per_b = a.T * a.P;
+
+    if (warp < 4) {
+        if (NTW == 8) reg_dec<40>();
+        if (warp == 0) {
+            // =========================================================================== raw loader
+            int stage = 0;
+            uint32_t sphase = 0;
+            int rowbytes_all = 0;
+            for (int s = 0; s < a.nstreams; ++s) rowbytes_all += a.s_C[s] * 4;
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                const int b = tile / a.tiles_per_b;
+                const int row0 = (tile - b * a.tiles_per_b) * TM;
+                for (int j = 0; j < pl.ngroups; ++j) {
+                    int g_lo, n;
+                    group_range(a, pl.R, rows_per_b, row0, j, g_lo, n);
+                    mbar_wait(&raw_empty[stage], sphase ^ 1);
+                    if (lane == 0) {
+                        if (n > 0) {
+                            mbar_arrive_expect_tx(&raw_full[stage], (uint32_t)(n * rowbytes_all));
+                            uint8_t* dst = ring + (size_t)stage * a.stage_bytes;
+                            for (int s = 0; s < a.nstreams; ++s) {
+                                const float* src = a.sx[s] + ((size_t)b * a.T * a.Fin + g_lo) * a.s_C[s];
+                                bulk_copy_g2s(dst + a.s_stage_off[s], src, (uint32_t)(n * a.s_C[s] * 4), &raw_full[stage]);
+                            }
+                        } else {
+                            mbar_arrive(&raw_full[stage]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == a.nstage) { stage = 0; sphase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            // =========================================================================== MMA issuer (convergent, see conv_tma)
+            const uint32_t idesc = make_idesc(a.N);
+            const uint32_t bs_lo = desc_lo(smem_u32(Bs));
+            const uint32_t bstep = (uint32_t)pl.b_stage_bytes >> 4;
+            int stage = 0;
+            uint32_t sphase = 0;
+            if (a.resident && tile_begin < tile_end) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                const int ord = tile - tile_begin;
+                const int acc = ord & 1;
+                const int buf = ord % a.nbuf;
+                const uint32_t bphase = (uint32_t)((ord / a.nbuf) & 1);
+                const uint32_t aphase = (uint32_t)((ord >> 1) & 1);
+                mbar_wait(&acc_empty[acc], aphase ^ 1);
+                mbar_wait(&opnd_full[buf], bphase);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+                const uint32_t origin = smem_u32(opnd + buf * pl.buf_bytes) >> 4;
+                for (int unit = 0; unit < a.nunits; ++unit) {
+                    const uint32_t fl = a.unit_c[unit];
+                    uint32_t blo;
+                    if (!a.resident) {
+                        mbar_wait(&b_full[stage], sphase);
+                        tc_fence_after();
+                        blo = bs_lo + (uint32_t)stage * bstep;
+                    } else {
+                        blo = bs_lo + (uint32_t)a.unit_b[unit] * bstep;
+                    }
+                    const uint32_t alo = ((origin + a.unit_a[unit]) & 0x3FFFu) | (1u << 16);
+                    umma_f16_lo_elect_x4(d_tmem + (fl & 1u) * (uint32_t)a.N, alo, blo, idesc, (fl & 0x80u) ? 0u : 1u);
+                    if (!a.resident) {
+                        umma_commit_elect(&b_empty[stage]);
+                        if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
+                    }
+                    if (fl & 0x40u) umma_commit_elect(&acc_full[acc * 2 + (int)(fl & 1u)]);
+                }
+                umma_commit_elect(&opnd_empty[buf]);
+            }
+        } else if (warp == 2) {
+            // =========================================================================== weight loader
+            const uint32_t bytes = (uint32_t)pl.b_stage_bytes;
+            if (a.resident) {
+                if (lane == 0 && tile_begin < tile_end) {
+                    mbar_arrive_expect_tx(&b_full[0], bytes * (uint32_t)pl.w_images);
+                    int slot = 0;
+                    for (int v = 0; v < a.nvar; ++v)
+                        for (int ts = 0; ts < a.ntaps[v] * a.nslab; ++ts)
+                            for (int hl = 0; hl < npb; ++hl, ++slot)
+                                bulk_copy_g2s(Bs + (size_t)slot * pl.b_stage_bytes, (hl ? a.Wlo[v] : a.Whi[v]) + (size_t)ts * a.N * 32, bytes, &b_full[0]);
+                }
+                __syncwarp();
+            } else {
+                int stage = 0;
+                uint32_t sphase = 0;
+                for (int tile = tile_begin; tile < tile_end; ++tile)
+                    for (int v = 0; v < a.nvar; ++v)
+                        for (int ts = 0; ts < a.ntaps[v] * a.nslab; ++ts)
+                            for (int pass = 0; pass < a.npass; ++pass) {
+                                mbar_wait(&b_empty[stage], sphase ^ 1);
+                                if (lane == 0) {
+                                    const float* img = (pass == 2 ? a.Wlo[v] : a.Whi[v]) + (size_t)ts * a.N * 32;
+                                    mbar_arrive_expect_tx(&b_full[stage], bytes);
+                                    bulk_copy_g2s(Bs + (size_t)stage * pl.b_stage_bytes, img, bytes, &b_full[stage]);
+                                }
+                                __syncwarp();
+                                if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
+                            }
+            }
+        }
+    } else if (warp < 12) {
+        // =========================================================================== epilogue (8 warps)
+        // thread = output row (TMEM lane), warp = (lane quadrant, half of the 64 output channels); see conv_tma_kernel
+        if (NTW == 8) reg_inc<152>();
+        const int quad = warp & 3;
+        const int chalf = ((warp - 4) >> 2) & 1;
+        const int row = quad * 32 + lane;
+        const bool gated = a.gate_off > 0;
+        const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        float rs_sum[32], rs_sq[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { rs_sum[i] = 0.f; rs_sq[i] = 0.f; }
+        int cur_b = -1;
+        auto flush = [&](int b) {
+            if (b < 0 || a.stats == nullptr) return;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                float u8[8], w8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { u8[i] = rs_sum[it * 8 + i]; w8[i] = rs_sq[it * 8 + i]; rs_sum[it * 8 + i] = 0.f; rs_sq[it * 8 + i] = 0.f; }
+                const float s1 = fold8(u8, lane);
+                const float s2 = fold8(w8, lane);
+                if ((lane & 3) == 0) {
+                    double* dstp = a.stats + ((size_t)b * a.Cout + chalf * 32 + it * 8 + own) * 2;
+                    atomicAdd(dstp, (double)s1);
+                    atomicAdd(dstp + 1, (double)s2);
+                }
+            }
+        };
+        int acc = 0;
+        uint32_t aphase = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            const int b = tile / a.tiles_per_b;
+            if (b != cur_b) { flush(cur_b); cur_b = b; }
+            const int row0 = (tile - b * a.tiles_per_b) * TM;
+            const int r = row0 + row;
+            int t = 0, e = a.P;                              // e = P: invalid for every variant
+            if (r < rows_per_b) {
+                t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
+                e = r - t * a.P;
+            }
+            const long long fbase = ((long long)b * a.T + t) * a.Fout;
+#pragma unroll 1
+            for (int v = 0; v < a.nvar; ++v) {
+                const bool row_valid = e < a.E[v];
+                const long long off = (fbase + (e * a.out_stride + a.out_off[v])) * 64;
+                mbar_wait(&acc_full[acc * 2 + v], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols + v * a.N);
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int c0 = chalf * 32 + it * 8;
+                    uint32_t rv[8], rg[8];
+                    tmem_ld8_nowait(taddr + c0, rv);
+                    if (gated) tmem_ld8_nowait(taddr + a.gate_off + c0, rg);
+                    tmem_wait_ld();
+                    float val[8];
+                    const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0);
+                    const float4 b1 = *reinterpret_cast<const float4*>(sbias + c0 + 4);
+                    val[0] = __uint_as_float(rv[0]) + b0.x; val[1] = __uint_as_float(rv[1]) + b0.y; val[2] = __uint_as_float(rv[2]) + b0.z; val[3] = __uint_as_float(rv[3]) + b0.w;
+                    val[4] = __uint_as_float(rv[4]) + b1.x; val[5] = __uint_as_float(rv[5]) + b1.y; val[6] = __uint_as_float(rv[6]) + b1.z; val[7] = __uint_as_float(rv[7]) + b1.w;
+                    if (gated) {
+                        const float4 g0 = *reinterpret_cast<const float4*>(sbias + a.gate_off + c0);
+                        const float4 g1 = *reinterpret_cast<const float4*>(sbias + a.gate_off + c0 + 4);
+                        val[0] *= sigmoid_f(__uint_as_float(rg[0]) + g0.x); val[1] *= sigmoid_f(__uint_as_float(rg[1]) + g0.y);
+                        val[2] *= sigmoid_f(__uint_as_float(rg[2]) + g0.z); val[3] *= sigmoid_f(__uint_as_float(rg[3]) + g0.w);
+                        val[4] *= sigmoid_f(__uint_as_float(rg[4]) + g1.x); val[5] *= sigmoid_f(__uint_as_float(rg[5]) + g1.y);
+                        val[6] *= sigmoid_f(__uint_as_float(rg[6]) + g1.z); val[7] *= sigmoid_f(__uint_as_float(rg[7]) + g1.w);
+                    }
+                    // conv_tma adds a (zero) residual here; x + 0.f is the identity except for -0, which no statistic or consumer sees
+                    if (row_valid) {
+                        st_global_256(a.out + off + c0, val);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            rs_sum[it * 8 + i] += val[i];
+                            rs_sq[it * 8 + i] = fmaf(val[i], val[i], rs_sq[it * 8 + i]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; aphase ^= 1; }
+        }
+        flush(cur_b);
+    } else {
+        // =========================================================================== transform warps
+        // thread = (operand row of the group, 16-byte fp16 chunk = 8 channels).  The two 16-byte halves of the thread's
+        // 32 raw bytes are read in an order that depends on the chunk (c8 >= 4: upper half first) so that the eight
+        // lanes of a quarter-warp touch all 32 banks in both loads.
+        if (NTW == 8) reg_dec<80>();
+        const int ttid = tid - TR0;
+        const int c8 = ttid & 7;
+        const int qa = (c8 >> 2) & 1;                        // which half this thread loads first
+        const int chA = c8 * 8 + qa * 4, chB = c8 * 8 + (qa ^ 1) * 4;
+        int stage = 0;
+        uint32_t sphase = 0;
+        int cur_b = -1;
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            const int ord = tile - tile_begin;
+            const int buf = ord % a.nbuf;
+            const uint32_t bphase = (uint32_t)((ord / a.nbuf) & 1);
+            const int b = tile / a.tiles_per_b;
+            const int row0 = (tile - b * a.tiles_per_b) * TM;
+            if (b != cur_b) {
+                named_bar_sync(1, NTT);
+                for (int s = 0; s < a.nstreams; ++s) {
+                    const int C = a.s_C[s];
+                    float* cf = coef + a.s_coef_off[s];
+                    for (int c = ttid; c < C; c += NTT) {
+                        float cs, ch, ca;
+                        xform_coeffs(a.s_xf[s], b, C, c, cs, ch, ca);
+                        cf[c] = cs; cf[C + c] = ch; cf[2 * C + c] = a.s_xf[s].prelu ? ca : 1.f;
+                    }
+                }
+                named_bar_sync(1, NTT);
+                cur_b = b;
+            }
+            mbar_wait(&opnd_empty[buf], bphase ^ 1);
+            uint8_t* obuf = opnd + (size_t)buf * pl.buf_bytes;
+            for (int j = 0; j < pl.ngroups; ++j) {
+                int g_lo, n;
+                group_range(a, pl.R, rows_per_b, row0, j, g_lo, n);
+                mbar_wait(&raw_full[stage], sphase);
+                const uint8_t* sbase = ring + (size_t)stage * a.stage_bytes;
+#pragma unroll 1
+                for (int rr = ttid >> 3; rr < GROUP; rr += NTT / 8) {
+                    const int rho = j * GROUP + rr;
+                    if (rho >= pl.R) break;
+                    const int r = row0 - a.back + rho;
+                    const bool rvalid = r >= 0 && r < rows_per_b;
+                    int t = 0, col = 0;
+                    if (rvalid) {
+                        t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
+                        col = r - t * a.P;
+                    }
+                    uint8_t* drow = obuf + rho * 128 + ((c8 ^ (rho & 7)) << 4);
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        if (p >= a.nplanes) break;
+                        const bool ok = rvalid && col < a.plane_cols[p];
+                        const int lrow = t * a.Fin + col * a.col_stride + a.col_off[p] - g_lo;
+#pragma unroll 1
+                        for (int s = 0; s < a.nslab; ++s) {
+                            float4 vA = make_float4(0.f, 0.f, 0.f, 0.f), vB = vA;
+                            if (ok) {
+                                const int s0 = a.sl_s0[s], s1 = a.sl_s1[s];
+                                const int C0 = a.s_C[s0];
+                                const uint8_t* src = sbase + a.s_stage_off[s0] + (size_t)lrow * (C0 * 4) + a.sl_c0[s] * 4 + c8 * 32;
+                                vA = lds128(src + qa * 16);
+                                vB = lds128(src + (qa ^ 1) * 16);
+                                const float* cf = coef + a.s_coef_off[s0] + a.sl_c0[s];
+                                xf4(vA, cf + chA, C0, a.s_mode[s0]);
+                                xf4(vB, cf + chB, C0, a.s_mode[s0]);
+                                if (s1 >= 0) {                   // + the second addend of a module's lazy residual sum
+                                    const int C1 = a.s_C[s1];
+                                    const uint8_t* src2 = sbase + a.s_stage_off[s1] + (size_t)lrow * (C1 * 4) + a.sl_c0[s] * 4 + c8 * 32;
+                                    float4 wA = lds128(src2 + qa * 16);
+                                    float4 wB = lds128(src2 + (qa ^ 1) * 16);
+                                    const float* cf2 = coef + a.s_coef_off[s1] + a.sl_c0[s];
+                                    xf4(wA, cf2 + chA, C1, a.s_mode[s1]);
+                                    xf4(wB, cf2 + chB, C1, a.s_mode[s1]);
+                                    vA.x += wA.x; vA.y += wA.y; vA.z += wA.z; vA.w += wA.w;
+                                    vB.x += wB.x; vB.y += wB.y; vB.z += wB.z; vB.w += wB.w;
+                                }
+                            }
+                            const uint32_t hA0 = pack_h2(vA.x, vA.y), hA1 = pack_h2(vA.z, vA.w);
+                            const uint32_t hB0 = pack_h2(vB.x, vB.y), hB1 = pack_h2(vB.z, vB.w);
+                            uint8_t* dst = drow + (size_t)((p * a.nslab + s) * npb) * pl.plane_bytes;
+                            *reinterpret_cast<uint4*>(dst) = qa ? make_uint4(hB0, hB1, hA0, hA1) : make_uint4(hA0, hA1, hB0, hB1);
+                            if (npb == 2) {
+                                const uint32_t lA0 = pack_lo_h2(vA.x, vA.y, hA0), lA1 = pack_lo_h2(vA.z, vA.w, hA1);
+                                const uint32_t lB0 = pack_lo_h2(vB.x, vB.y, hB0), lB1 = pack_lo_h2(vB.z, vB.w, hB1);
+                                *reinterpret_cast<uint4*>(dst + pl.plane_bytes) = qa ? make_uint4(lB0, lB1, lA0, lA1) : make_uint4(lA0, lA1, lB0, lB1);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_empty[stage]);
+                if (++stage == a.nstage) { stage = 0; sphase ^= 1; }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&opnd_full[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// shared-memory plan: resident weights before a weight ring, two operand buffers if the raw ring still gets >= 3 stages
+bool choose_plan(RawConvArgs& a) {
+    for (int resident = 1; resident >= 0; --resident) {
+        for (int nbuf = 2; nbuf >= 1; --nbuf) {
+            a.resident = resident; a.nbuf = nbuf; a.nsb = 3; a.nstage = 0;
+            const int fixed = make_raw_plan(a).total;
+            if (fixed >= SMEM_LIMIT) continue;
+            const int ns = std::min(NSTAGE_MAX, (SMEM_LIMIT - fixed) / a.stage_bytes);
+            if (ns < (nbuf == 2 ? 3 : 2)) continue;
+            a.nstage = ns;
+            if (!resident)                                   // leftover shared memory deepens the weight ring
+                for (int nsb = NSB_MAX; nsb > 3; --nsb) {
+                    a.nsb = nsb;
+                    if (make_raw_plan(a).total <= SMEM_LIMIT) break;
+                    a.nsb = 3;
+                }
+            return true;
+        }
+    }
+    return false;
+}
+
+// variants of one layer (plan_staged has already made their plane geometry identical) -> kernel arguments
+bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
+    if (n < 1 || n > 2) return false;
+    const PlaneConvArgs& q = p[0];
+    RawConvArgs a;
+    memset(&a, 0, sizeof(a));
+    if (q.Cout != 64 || (q.N != 64 && q.N != 128) || (q.gate_off != 0 && (q.gate_off != 64 || q.N != 128)) || (q.gate_off == 0 && q.N != 64))
+        return false;
+    if (q.relu || q.resid || q.nstats > 1 || q.stat_alpha[0] || q.stft_M > 0 || q.wide_k > 0 || q.out_half || q.round_half) return false;
+    if (q.out_ld != 64 || q.out_coff != 0 || q.stats_ld != 0 || q.stats_coff != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(q.out) & 31) != 0) return false;
+    if (q.npass != 1 && q.npass != 3) return false;
+    if (q.nplanes < 1 || q.nplanes > 2 || q.P < 1) return false;
+    // streams and slabs
+    int nslab = 0, ncoef = 0, stage_bytes = 0;
+    for (int i = 0; i < q.nsrc; ++i) {
+        const ConvSrc& s = q.src[i];
+        if (s.C % 64 != 0 || s.C < 64 || s.half || s.half2 || s.RT != 0) return false;     // (no null check: planning passes run on offsets)
+        if ((reinterpret_cast<uintptr_t>(s.x) & 15) || (s.x2 && (reinterpret_cast<uintptr_t>(s.x2) & 15))) return false;
+        const int st0 = a.nstreams;
+        const int nadd = s.x2 ? 2 : 1;
+        if (a.nstreams + nadd > kRawMaxStreams) return false;
+        for (int k = 0; k < nadd; ++k) {
+            const int st = a.nstreams++;
+            a.sx[st] = k ? s.x2 : s.x;
+            a.s_xf[st] = k ? s.xf2 : s.xf;
+            a.s_C[st] = s.C;
+            a.s_mode[st] = (a.s_xf[st].affine == 0 && a.s_xf[st].prelu == 0) ? 0 : (a.s_xf[st].prelu == 1 ? 2 : 1);
+            a.s_stage_off[st] = stage_bytes;
+            a.s_coef_off[st] = 3 * ncoef;
+            stage_bytes += GROUP * q.col_stride * s.C * 4;
+            ncoef += s.C;
+        }
+        for (int c = 0; c < s.C; c += 64) {
+            if (nslab >= kRawMaxSlabs) return false;
+            a.sl_s0[nslab] = st0;
+            a.sl_s1[nslab] = s.x2 ? st0 + 1 : -1;
+            a.sl_c0[nslab] = c;
+            ++nslab;
+        }
+    }
+    if (nslab != q.nslab) return false;
+    a.nslab = nslab; a.ncoef = ncoef; a.stage_bytes = stage_bytes;
+    a.B = q.B; a.T = q.T; a.Fin = q.Fin; a.P = q.P;
+    a.nplanes = q.nplanes; a.col_stride = q.col_stride;
+    for (int i = 0; i < 2; ++i) { a.plane_cols[i] = q.plane_cols[i]; a.col_off[i] = q.col_off[i]; }
+    if (a.col_stride < 1 || a.col_stride > 2 || a.plane_cols[0] > a.P || (a.nplanes == 2 && a.plane_cols[1] > a.P)) return false;
+    if ((long long)a.P * a.col_stride < a.Fin) return false;         // group_range: a frame's columns fit its padded pitch
+    for (int pl = 0; pl < a.nplanes; ++pl)                          // planes cover input columns < Fin only
+        if (a.plane_cols[pl] > 0 && (a.plane_cols[pl] - 1) * a.col_stride + a.col_off[pl] >= a.Fin) return false;
+    a.tiles_per_b = q.tiles_per_b;
+    a.p_magic = a.P == 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)a.P) + 1u;
+    if (((long long)a.T * a.P + 4 * TM + 2ll * a.P) * a.P >= (1ll << 31)) return false;              // magic-division range
+    if ((long long)a.T * a.Fin >= (1ll << 30)) return false;
+    a.npass = q.npass; a.nvar = n;
+    a.out_stride = q.out_stride; a.Fout = q.Fout;
+    a.bias = q.bias; a.Cout = q.Cout; a.N = q.N; a.gate_off = q.gate_off;
+    a.out = q.out;
+    a.stats = q.nstats ? q.stats[0] : nullptr;
+    a.algo_frac = q.algo_frac;
+    int back = 0, fwd = 0;
+    for (int v = 0; v < n; ++v) {
+        const PlaneConvArgs& w = p[v];
+        if (w.P != q.P || w.nplanes != q.nplanes || w.nslab != q.nslab || w.npass != q.npass || w.tiles_per_b != q.tiles_per_b ||
+            w.Cout != q.Cout || w.N != q.N || w.gate_off != q.gate_off || w.bias != q.bias || w.out != q.out || w.out_stride != q.out_stride ||
+            w.Fout != q.Fout || w.B != q.B || w.T != q.T || w.Fin != q.Fin || w.nsrc != q.nsrc || w.col_stride != q.col_stride ||
+            w.plane_cols[0] != q.plane_cols[0] || w.plane_cols[1] != q.plane_cols[1] || w.nstats != q.nstats || w.stats[0] != q.stats[0] ||
+            w.relu || w.resid || w.stft_M > 0 || w.wide_k > 0 || w.out_half || w.round_half || w.out_ld != 64 || w.out_coff != 0)
+            return false;
+        for (int i = 0; i < q.nsrc; ++i)
+            if (w.src[i].x != q.src[i].x || w.src[i].x2 != q.src[i].x2 || w.src[i].C != q.src[i].C) return false;
+        if (w.ntaps < 1 || w.ntaps > kMaxTaps || w.E < 1 || w.E > w.P) return false;
+        a.E[v] = w.E; a.out_off[v] = w.out_off; a.ntaps[v] = w.ntaps;
+        a.Whi[v] = w.Whi; a.Wlo[v] = w.Wlo;
+        if ((reinterpret_cast<uintptr_t>(w.Whi) & 15) || (w.npass == 3 && (reinterpret_cast<uintptr_t>(w.Wlo) & 15))) return false;
+        for (int i = 0; i < w.ntaps; ++i) {
+            if (w.tap_plane[i] < 0 || w.tap_plane[i] >= w.nplanes) return false;
+            back = std::max(back, -w.tap_shift[i]);
+            fwd = std::max(fwd, w.tap_shift[i]);
+        }
+    }
+    a.back = back; a.fwd = fwd;
+    // K units: variant-major, then (tap, slab), pass fastest (the weight ring streams images in the same order)
+    const int npb = a.npass == 3 ? 2 : 1;
+    a.nbuf = 1; a.nstage = 2; a.resident = 0; a.nsb = 3;
+    const int plane_bytes = make_raw_plan(a).plane_bytes;
+    int nunits = 0, slot_base = 0;
+    for (int v = 0; v < n; ++v) {
+        const PlaneConvArgs& w = p[v];
+        const int uv = w.ntaps * a.nslab * a.npass;
+        if (nunits + uv > kMaxConvUnits) return false;
+        for (int u = 0; u < uv; ++u) {
+            const int pass = u % a.npass, ts = u / a.npass;
+            const int slab = ts % a.nslab, tap = ts / a.nslab;
+            const unsigned a_rel = (unsigned)(((w.tap_plane[tap] * a.nslab + slab) * npb + (pass == 1 ? 1 : 0)) * plane_bytes +
+                                              (back + w.tap_shift[tap]) * 128);
+            a.unit_a[nunits] = a_rel >> 4;
+            a.unit_b[nunits] = (unsigned short)(slot_base + (tap * a.nslab + slab) * npb + (pass == 2 ? 1 : 0));
+            a.unit_c[nunits] = (unsigned char)(v | (u == 0 ? 0x80 : 0) | (u == uv - 1 ? 0x40 : 0));
+            ++nunits;
+        }
+        slot_base += w.ntaps * a.nslab * npb;
+    }
+    a.nunits = nunits;
+    if (!choose_plan(a)) return false;
+    *out = a;
+    return true;
+}
+
+}  // namespace
+
+bool raw_conv_supported(const PlaneConvArgs* p, int n) {
+    RawConvArgs a;
+    return build_args(p, n, &a);
+}
+
+int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned long long* dbg) {
+    RawConvArgs a;
+    if (!build_args(p, n, &a)) return fail("conv_raw: unsupported layer");
+    if (a.B <= 0 || a.T <= 0) return 0;
+    a.dbg = dbg;
+    const RawPlan pl = make_raw_plan(a);
+    constexpr int NTW = 8;
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_raw_kernel<NTW>), pl.total));
+    int sms = 0;
+    EAB_TRY(device_sm_count(&sms));
+    const long long ntiles = (long long)a.B * a.tiles_per_b;
+    if (ntiles >= (1ll << 30)) return fail("conv_raw: too many tiles");
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    double pos = 0, kn = 0, in_bytes = 0;
+    for (int v = 0; v < a.nvar; ++v) { pos += (double)a.B * a.T * a.E[v]; kn += (double)a.B * a.T * a.E[v] * a.ntaps[v]; }
+    for (int s = 0; s < a.nstreams; ++s) in_bytes += 4.0 * a.B * a.T * a.Fin * a.s_C[s];
+    const double kreal = 64.0 * a.nslab;
+    double wbytes = 0;
+    for (int v = 0; v < a.nvar; ++v) wbytes += 4.0 * a.ntaps[v] * kreal * a.N;
+    ProfScope ps("conv_raw", 2.0 * kn * kreal * a.N * a.algo_frac, in_bytes + 4.0 * pos * a.Cout + wbytes, st);
+    EAB_CUDA(launch_k(conv_raw_kernel<NTW>, dim3(grid), dim3(NCTRL + NEPI + NTW * 32), (size_t)pl.total, st, a));
+    EAB_LAUNCH_CHECK("conv_raw_kernel");
+    return 0;
+}
+
+}  // namespace eab

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -32,6 +33,31 @@ int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return 0;
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return 1;
+}
+namespace {
+struct DevState { int sms = 0; std::map<const void*, int> smem; };
+std::mutex g_dev_mu;
+std::map<int, DevState> g_dev;
+}  // namespace
+int device_sm_count(int* sms) {
+    int dev = 0;
+    EAB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DevState& d = g_dev[dev];
+    if (!d.sms) EAB_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    *sms = d.sms;
+    return 0;
+}
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+    int dev = 0;
+    EAB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    int& cur = g_dev[dev].smem[kernel];
+    if (bytes > cur) {
+        EAB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        cur = bytes;
+    }
+    return 0;
 }
 bool g_use_pdl = false;     // measured on B200: 35.2 ms/step with PDL vs 34.0 without (dependents crowd multi-wave kernels)
 void count_launch(int n) { g_launches += n; }
@@ -245,7 +271,8 @@ struct eab_model {
     int opt_dec_passes = 1;       // single-pass TF32 in the decoder
     int opt_inner_passes = 3;     // inner U-Nets of the encoder modules
     int opt_first_passes = 3;     // the first gated conv (2M input channels, tap-window rows: 3.5x the input bytes per pass-plane)
-    int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (preferred)
+    int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (layers conv_raw does not take)
+    int opt_raw = 1;              // conv_raw_kernel: raw fp32 tiles normalised in shared memory, no stage pass (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
     int opt_half_act = 0;         // raw outputs of the single-pass decoder layers stored as fp16: measured -1 % step time for +30 % output error, so off
@@ -1172,6 +1199,13 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n, bool out_half = false) {
                         EAB_TRY(launch_conv_staged(p[i], cx.st));
                     }
                     return 0;
+                }
+                if (m->opt_raw && !out_half && raw_conv_supported(p, n)) {
+                    // one launch per layer: raw tiles -> norm + PReLU -> fp16 operand in shared memory -> GEMM (both parities)
+                    if (cx.dry) return 0;
+                    unsigned long long* dbg = nullptr;
+                    if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) dbg = m->dbg_buf;
+                    return launch_conv_raw(p, n, cx.st, dbg);
                 }
                 int front = 0;
                 const int rows = staged_rows(ps, &front);
@@ -2567,6 +2601,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "plane") m->opt_plane = value != 0;
     else if (n == "pdl") g_use_pdl = value != 0;
     else if (n == "staged") m->opt_staged = value != 0;
+    else if (n == "raw") m->opt_raw = value != 0;
     else if (n == "lazy") m->opt_lazy = value != 0;
     else if (n == "tcm_chain") m->opt_tcm_chain = value;
     else if (n == "host_graph") m->opt_host_graph = value != 0;

@@ -7,6 +7,20 @@ namespace eab {
 namespace umma {
 
 constexpr uint32_t SPIN_LIMIT = 1u << 22;     // x the ~10 ms suspend hint: far beyond any legitimate wait
+constexpr unsigned long long WAIT_LIMIT_NS = 4000000000ull;      // wall-clock bound of one mbarrier wait (4 s)
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// true once a wait has lasted WAIT_LIMIT_NS (checked every 256 polls from the 64th on)
+__device__ __forceinline__ bool wait_expired(uint32_t spins, unsigned long long& t0) {
+    if (spins < 64 || (spins & 255u) != 64u) return false;
+    const unsigned long long now = global_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > WAIT_LIMIT_NS;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -24,6 +38,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0, spins = 0;
+    unsigned long long t0 = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -33,7 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity), "r"(0x989680u)
             : "memory");
         if (done) break;
-        if (++spins > SPIN_LIMIT) __trap();        // a protocol bug must fault, never hang the GPU
+        if (++spins > SPIN_LIMIT || wait_expired(spins, t0)) __trap();        // a protocol bug must fault, never hang the GPU
     }
 }
 // Latency-critical variant: no suspend hint, the warp polls (a serial chain such as the LSTM step cannot afford the
