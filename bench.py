@@ -11,7 +11,13 @@ max over ranks.
 `value`  : throughput with the input waveforms already resident in HBM (eab_enhance, device pointers).
 `e2e`    : the same work with HOST (pinned) buffers through eab_enhance_host_batches (`steps` batches per call): H2D of
            every batch's waveforms and D2H of its enhanced audio inside the timed region, overlapped with compute.
-`roofline`: the kernel family with the largest share of the step, timed live per launch with CUDA events.
+`roofline`: the kernel family with the largest share of the step, timed live per launch with CUDA events, against SURVEY.md
+           section 8(d)'s ALGORITHMIC bytes (every fused layer reads its fp32 inputs once and writes its output once: 2-D convs
+           674 888 B + TCM 73 728 B + head 301 392 B per frame = 40.4 GB per 64 x 6 s step); what the design actually moves
+           is reported next to it (`moved_bytes`, `traffic_ratio`), as are all families and the whole step.
+`gpu_eager_baseline`: the oracle port run on the SAME GPU through torch eager (cuDNN / cuFFT / cuBLAS, TF32 off) - BASELINE.md
+           section 3.4's "real bar to beat"; `single_utterance` = BASELINE configs[0] shape (B = 1, 4 s) on the GPU;
+           `config4` = BASELINE configs[3] (2048 x 6 s through shard_range + enhance_host_batches, fixed total size).
 `cpu_baseline` / `--impl reference`: the CPU oracle port of the reference path (oracle/eabnet_oracle.py, torch
            fp32 ops, all host threads) on a bounded sample of the same workload.
 """
@@ -29,6 +35,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "audio_seconds_enhanced_per_second"
+DTYPE = "f32 io/accum; fp16x3 (hi/lo split) enc/TCM/LSTM/head/STFT, fp16x1 decoder"
+WORKLOAD = ("EaBNet default (M=9, causal, U2, LSTM head, IN) batched wave->wave enhancement, "
+            "64 x 6 s utterances per GPU (BASELINE configs[1])")
+# algorithmic bytes per frame of the layer-fused path (fp32, inputs once + output once per layer)
+ALGO_BYTES_PER_FRAME = {"conv2d": 674888.0, "tcm": 73728.0, "head": 301392.0}
+# kernel families: profiler categories -> SURVEY rows (a3-a7/a11 2-D conv stack, a10 TCM stack, a12-a13 head, a1, a14)
+FAMILY_OF = {"conv_raw": "conv2d", "conv_tma": "conv2d", "stage": "conv2d", "conv_umma": "conv2d", "conv_generic": "conv2d",
+             "combine": "conv2d", "tcm_chain": "tcm", "lstm_umma": "head", "lstm": "head", "head_fused": "head", "beam": "head",
+             "stft": "stft", "stft_stage": "stft", "istft": "istft"}
 UNIT = "audio-s/s"
 SR = 16000
 
@@ -142,9 +157,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "EaBNet default (M=9, causal, U2, LSTM head, IN) batched wave->wave enhancement, "
-                                   "64 x 6 s utterances per GPU (BASELINE configs[1])",
-                       "batch_per_gpu": args.batch, "seconds": args.seconds, "sample_batch": args.ref_batch},
+            "config": {"workload": WORKLOAD,
+                       "batch_per_gpu": args.batch, "seconds": args.seconds, "sample_batch": args.ref_batch,
+                       "caps": "CPU arm: at most 5 timed steps and 1 warm-up of an %d x %.0f s sample (about 12 s each on 16 cores), "
+                               "whatever --steps / --warmup ask for; value = median step" % (args.ref_batch, args.seconds)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -226,6 +242,152 @@ def postnet_throughput(args, dev, wave):
             "kernels": prof}
 
 
+def gpu_eager_baseline(args, dev):
+    """the reference's own op sequence in PyTorch eager on this GPU (cuDNN convs, cuFFT, cuBLAS, the
+    fused cuDNN LSTM), TF32 off so that it computes what the CPU reference computes.  The oracle port stands in for the
+    reference module (same torch primitives; the module itself does not travel to the GPU box).  Bounded sample."""
+    import torch
+    from oracle import eabnet_oracle as O          # baseline leg (checker / timed baseline only)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        cfg = O.make_cfg()
+        sd = {k: v.to(dev) for k, v in O.make_weights(cfg, 0, "B").items()}
+        Bs, L = args.ref_batch, int(args.seconds * SR)
+        wave = O.make_wave(Bs, 9, L, seed=1234)[0].to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                y = O.enhance(sd, wave, cfg)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                y = O.enhance(sd, wave, cfg)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        assert torch.isfinite(y).all()
+        return {"value": Bs * args.seconds / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kind": "port",
+                "what": "oracle port in torch eager on cuda (cuDNN / cuFFT / cuBLAS, allow_tf32 = False), wave -> wave, device-resident",
+                "sample": "%d x %.0f s 9-mic utterances per step, mean of 5 steps after 2 warm-ups" % (Bs, args.seconds)}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
+def single_utterance(dev, net):
+    """BASELINE configs[0] on the GPU: one 4 s 9-mic utterance, the shape enhance.py feeds (B = 1, T = 401)."""
+    import torch
+    from eabnet_b200 import stft_compress
+    L = 64000
+    g = torch.Generator().manual_seed(5)
+    wave_host = (0.1 * torch.randn(1, 9, L, generator=g)).pin_memory()
+    out_host = torch.empty(1, 160 * (L // 160)).pin_memory()
+    wave = wave_host.to(dev)
+    with torch.no_grad():
+        spec = stft_compress(wave)
+        fwd, host = [], []
+        for i in range(60):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = net(spec)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if i >= 10:
+                fwd.append(e0.elapsed_time(e1))
+        launches = net.last_launch_count()
+        for i in range(60):
+            t0 = time.perf_counter()
+            net.enhance_host(wave_host, out_host, dev)
+            torch.cuda.synchronize(dev)
+            if i >= 10:
+                host.append((time.perf_counter() - t0) * 1e3)
+    fwd.sort()
+    host.sort()
+    assert torch.isfinite(y).all() and torch.isfinite(out_host).all()
+    return {"workload": "one 4 s 9-mic utterance (BASELINE configs[0] shape, B = 1, T = 401)",
+            "forward_p50_ms": fwd[len(fwd) // 2], "forward_launches": launches,
+            "enhance_host_p50_ms": host[len(host) // 2], "enhance_host_p99_ms": host[min(len(host) - 1, int(len(host) * 0.99))],
+            "audio_s_per_s_host": 4.0 / (host[len(host) // 2] * 1e-3),
+            "timing": "forward: CUDA events around net(noisy_stft), p50 of 50; enhance_host: wall clock around the host-buffer call "
+                      "(H2D + STFT + net + iSTFT + D2H + sync), p50 of 50"}
+
+
+def config4(args, dev, net, world, rank, ins2, outs2):
+    """BASELINE configs[3]: 2048 x 6 s utterances (fixed total), batches of 64 dealt to the ranks by shard_range, each rank
+    pushing its batches through enhance_host_batches (host buffers, copies overlapped); wall clock, max over ranks."""
+    import torch
+    from eabnet_b200.shard import max_over_ranks, shard_range
+    total_utt = 2048
+    nb_total = (total_utt + args.batch - 1) // args.batch
+    b0, b1 = shard_range(nb_total, rank, world)
+    n = b1 - b0
+    ins = [ins2[i % 2] for i in range(n)]
+    outs = [outs2[i % 2] for i in range(n)]
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    if n:
+        net.enhance_host_batches(ins, outs, dev)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    (dt,) = max_over_ranks([dt], dev)
+    return {"workload": "2048 x %.0f s 9-mic utterances in batches of %d, dealt to %d rank(s) with shard_range, host buffers "
+                        "(BASELINE configs[3]); synthetic batches re-used from two pinned buffers" % (args.seconds, args.batch, world),
+            "utterances": nb_total * args.batch, "batches_this_rank": n, "seconds_total": dt, "scaling": "strong",
+            "value": nb_total * args.batch * args.seconds / dt, "unit": UNIT}
+
+
+def build_roofline(prof, ms_step, frames, peaks):
+    """Per-family and whole-step roofline fractions on SURVEY 8(d) algorithmic bytes; `prof` = one profiled step."""
+    fam = {}
+    for k in prof:
+        f = FAMILY_OF.get(k["kernel"], "other")
+        d = fam.setdefault(f, {"ms": 0.0, "flops": 0.0, "launcher_bytes": 0.0, "moved_bytes": 0.0, "launches": 0, "kernels": {}})
+        d["ms"] += k["ms"]; d["flops"] += k["flops"]; d["launcher_bytes"] += k["bytes"]
+        d["moved_bytes"] += k.get("moved_bytes", k["bytes"]); d["launches"] += k["launches"]
+        d["kernels"][k["kernel"]] = round(k["ms"], 4)
+    hbm, tens = peaks["hbm_gbs"], peaks["bf16_tflops_sustained"]
+    out = {}
+    for f, d in fam.items():
+        algo = ALGO_BYTES_PER_FRAME[f] * frames if f in ALGO_BYTES_PER_FRAME else d["launcher_bytes"]
+        gbs = algo / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+        tfs = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+        out[f] = {"ms": round(d["ms"], 4), "launches": d["launches"], "kernels": d["kernels"], "algorithmic_bytes": algo,
+                  "launcher_algorithmic_bytes": d["launcher_bytes"], "moved_bytes": d["moved_bytes"],
+                  "traffic_ratio": d["moved_bytes"] / algo if algo else None,
+                  "hbm_gbs": gbs, "hbm_frac": gbs / hbm, "algorithmic_tflops": tfs, "tensor_frac": tfs / tens}
+    top = max(out, key=lambda f: out[f]["ms"])
+    t = out[top]
+    total_algo = sum(ALGO_BYTES_PER_FRAME.values()) * frames
+    total_flops = sum(d["flops"] for d in fam.values())
+    whole_gbs = total_algo / (ms_step * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": t["hbm_gbs"], "peak": hbm, "unit": "GB/s", "frac": t["hbm_frac"], "traffic": None,
+            "kernel": max(t["kernels"], key=t["kernels"].get), "family": top, "family_ms_per_step": t["ms"],
+            "algorithmic_bytes": t["algorithmic_bytes"], "moved_bytes": t["moved_bytes"], "traffic_ratio": t["traffic_ratio"],
+            "tensor": {"achieved": t["algorithmic_tflops"], "peak": tens, "unit": "TFLOP/s", "frac": t["tensor_frac"],
+                       "note": "algorithmic FLOPs against the measured sustained bf16 rate (fp16 operands run at the bf16 rate); "
+                               "the 3-pass layers execute 3x their algorithmic FLOPs"},
+            "whole_step": {"algorithmic_bytes": total_algo, "ms": ms_step, "achieved": whole_gbs, "frac": whole_gbs / hbm,
+                           "algorithmic_tflops": total_flops / (ms_step * 1e-3) / 1e12,
+                           "tensor_frac": total_flops / (ms_step * 1e-3) / 1e12 / tens},
+            "families": out, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json: HBM copy GB/s, sustained bf16 TFLOP/s)",
+            "definition": "achieved = SURVEY 8(d) algorithmic bytes of the family (inputs once + output once per fused layer, fp32) / "
+                          "its CUDA-event time in one profiled step; moved_bytes = what the launchers actually request"}
+    # measured DRAM bytes of the family's launches in one step (ncu --set full of this build, tools/summarize_ncu.py traffic)
+    try:
+        import glob
+        tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]))
+        ent = tr.get(top)
+        if ent and "dram_bytes_per_step" in ent:
+            roof["traffic"] = ent["dram_bytes_per_step"]
+            roof["traffic_note"] = "%s; %s" % (tr.get("_source", ""), ent.get("note", ""))
+    except Exception:
+        pass
+    return roof
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -241,6 +403,9 @@ def main():
     ap.add_argument("--single-stream", action="store_true", help="replay the step graph on one stream instead of alternating two")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step's launches from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-postnet", action="store_true", help="skip the EaBNet + GaGNet post-filter measurement")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 2048-utterance dataset-scale measurement (BASELINE configs[3])")
+    ap.add_argument("--no-single", action="store_true", help="skip the one-utterance latency measurement (BASELINE configs[0] shape)")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager-on-GPU baseline (oracle port on cuda)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
 
@@ -358,6 +523,9 @@ def main():
         clocks = sampler.stop()
         assert torch.isfinite(y).all()
 
+    c4 = config4(args, dev, net, world, rank, [wave_host, wave_host2], [out_host, out_host2]) if not args.no_config4 else None
+    single = single_utterance(dev, net) if (rank == 0 and not args.no_single) else None
+    eager = gpu_eager_baseline(args, dev) if (rank == 0 and world == 1 and not args.no_gpu_eager) else None
     latency = stream_latency(args, dev) if args.stream_steps > 0 else None
     postnet = postnet_throughput(args, dev, wave) if (rank == 0 and not args.no_postnet) else None
 
@@ -369,40 +537,11 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        total_ms = sum(k["ms"] for k in prof) or 1.0
-        top = max(prof, key=lambda k: k["ms"])
-        shares = {k["kernel"]: round(k["ms"] / total_ms, 4) for k in prof}
-        gemm_like = top["kernel"] in ("conv_generic", "conv_umma", "lstm", "stft", "istft")
-        if gemm_like:
-            # GEMM-shaped kernel family: measured against the tensor pipe.  TF32 is not in MEASURED_PEAKS.json; the
-            # stated fallback is half the measured sustained bf16 figure.
-            peak = 0.5 * peaks["bf16_tflops_sustained"]
-            achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None}
-        else:
-            peak = peaks["hbm_gbs"]
-            achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None}
-        # DRAM bytes of a representative launch of that family from the committed ncu --set full capture
-        try:
-            import glob
-            tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1])).get(top["kernel"])
-        except Exception:
-            tr = None
-        if tr:
-            roof["traffic"] = tr["dram_bytes"]
-            roof["traffic_note"] = ("ncu dram bytes of one launch (%s): %.3f GB against %.3f GB algorithmic for that launch; `achieved` is the "
-                                    "family total over the step" % (tr["launch"], tr["dram_bytes"] / 1e9, tr["algorithmic_bytes"] / 1e9))
-        roof.update({"kernel": top["kernel"], "launches_per_step": top["launches"], "ms_per_step": top["ms"],
-                     "peak_source": peaks["source"] + (" (0.5 x sustained bf16 as TF32 peak)" if gemm_like else ""),
-                     "share_of_step": shares})
+        roof = build_roofline(prof, ms, B * (1 + L // 160), peaks)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "EaBNet default (M=9, causal, U2, LSTM head, IN) batched wave->wave enhancement, "
-                                       "64 x 6 s utterances per GPU (BASELINE configs[1])",
+                "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+                "config": {"workload": WORKLOAD,
                            "batch_per_gpu": B, "seconds": args.seconds, "frames": 1 + L // 160,
                            "parallelism": "utterance shards, %d rank(s), no collective" % world,
                            "l2": "inputs (%.0f MB/step) and activations exceed the 126 MB L2" % (B * M * L * 4 / 1e6),
@@ -415,6 +554,12 @@ def main():
                         "single_batch_call_ms": ms_e2e_single},
                 "gpu_launches": launches * args.steps, "step_ms": step_ms,
                 "roofline": roof, "clocks": clocks, "kernels": prof}
+        if c4 is not None:
+            line["config4"] = c4
+        if single is not None:
+            line["single_utterance"] = single
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
         if latency is not None:
             line["latency"] = latency
         if postnet is not None:

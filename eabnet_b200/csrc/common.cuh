@@ -21,9 +21,12 @@ int  launch_count();
 void reset_launch_count();
 
 // Optional per-launch timing (CUDA events on the launching stream), switched on by eab_profile_enable; used by
-// bench.py for the live roofline of the dominant kernel.  `flops` / `bytes` are ALGORITHMIC figures of the launch.
+// bench.py for the live roofline.  `flops` / `bytes` are ALGORITHMIC figures of the launch in SURVEY.md section 8(d)'s
+// sense (a fused layer reads each input tensor once and writes its output once, fp32; a lazy residual pair counts as one
+// tensor; weights and design-specific copies are not counted); `moved` is what THIS design asks the memory system for
+// (both addends of a lazy sum, staged fp16 planes written and read back, weights) - default: the same figure.
 struct ProfScope {
-    ProfScope(const char* category, double flops, double bytes, cudaStream_t st);
+    ProfScope(const char* category, double flops, double bytes, cudaStream_t st, double moved = -1.0);
     ~ProfScope();
     void* rec;
     cudaStream_t st;
@@ -68,23 +71,13 @@ static inline Xform xform_identity() {
     return x;
 }
 
-// Programmatic dependent launch: every kernel is launched with the stream-serialisation attribute, calls pdl_trigger()
-// first (its successor may be scheduled onto SMs as they free up and run its data-independent prologue) and pdl_wait()
-// before it reads anything its predecessor wrote or writes anything at all.
-extern bool g_use_pdl;
+// Plain launch helper.  (Programmatic dependent launch was measured in round 1: +6 % step time - dependents crowd the
+// multi-wave kernels - and removed.)
 #ifdef __CUDACC__
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = g_use_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif
@@ -150,10 +143,6 @@ struct ConvSrc {
     const float* x2;
     Xform xf2;
     int RT;              // streaming only: frames in this tensor's ring (see StreamPos); 0 = offline [B][T][...]
-    // 2-byte storage: x (x2) points at __half data of the same [B][T][F][C] shape.  Used for the raw outputs of the
-    // single-pass decoder layers, whose consumers round the normalised value to fp16 anyway (measured cost in output
-    // accuracy: 1.1e-4 -> 1.2-1.6e-4).  Honoured by stage_kernel and combine_kernel only.
-    int half, half2;
 };
 
 // Frame-by-frame ("streaming", BASELINE configs[2]) addressing.  Offline, a tensor holds frames 0..T-1 of every batch
@@ -224,9 +213,10 @@ struct UmmaConvArgs {
 bool umma_conv_supported(const UmmaConvArgs& a);
 int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st);
 
-// "Stage once, shift by descriptor" variant (conv_plane.cu): GEMM rows are (t, e') with a padded pitch P >= E rows per
-// frame; the transformed fp16 input of a tile (+ halo) is staged ONCE per tile as 1-2 column planes with the same
-// pitch, and every tap is the same shared-memory plane viewed through a row-shifted UMMA descriptor.
+// "Stage once, shift by descriptor": GEMM rows are (t, e') with a padded pitch P >= E rows per frame; the transformed fp16
+// input of a tile (+ halo) exists ONCE per tile as 1-2 column planes with the same pitch, and every tap is the same
+// shared-memory plane viewed through a row-shifted UMMA descriptor (conv_staged.cu: planes staged through HBM by
+// stage_kernel; conv_raw.cu: planes built in shared memory from raw tiles).
 struct PlaneConvArgs {
     ConvSrc src[2];
     int nsrc;
@@ -261,7 +251,6 @@ struct PlaneConvArgs {
     // np[(plane * nslab + slab) * npb + hl] : [B][np_rows][64] halves, row = np_front + t*P + col, 128B-swizzled by row & 7
     const void* np[16];
     int np_rows, np_front;
-    int exp_flags;               // diagnostics builds only
     int stats_ld, stats_coff;    // see UmmaConvArgs
     // conv_tma: per-unit (tap, slab, pass) operand offsets, filled by the launcher: A offset / 16 relative to the tile's
     // plane origin, weight image index.  Kernel parameters live in the constant bank => warp-uniform loads.
@@ -274,14 +263,9 @@ struct PlaneConvArgs {
     // "wide" staging (first layer, 2M input channels): a plane row (t, e) is the whole kf x C tap window, wide_k contiguous
     // floats starting at column e*col_stride of frame t, zero-padded to nslab*64; the time taps are then plain row shifts
     int wide_k;
-    // fused producers (conv_tma): no staged planes in HBM - warps 12-19 read the raw fp32 activations, apply norm + PReLU
-    // (+ the lazy residual addend), split to fp16 hi/lo and write the tile's planes straight into shared memory
-    int fused;
-    int round_half;              // diagnostics: round the stored output to fp16 precision (accuracy of a 2-byte activation format)
-    int out_half;                // conv_tma: `out` is __half [B][T][Fout][out_ld] (statistics still from the fp32 accumulators)
+    float algo_in_share;         // profiling only: share of the layer's input bytes this launch accounts for (0 = all)
 };
-bool plane_conv_supported(const PlaneConvArgs& a);      // also fills nothing; pure check incl. shared-memory budget
-int launch_conv_plane(PlaneConvArgs a, cudaStream_t st);
+bool plane_conv_supported(const PlaneConvArgs& a);      // shape rules of the padded-pitch row space (pure check)
 // staged variant: geometry helpers + the two launches (stage = normalise + fp16 + layout, conv = TMA-fed GEMM)
 int staged_rows(const PlaneConvArgs& a, int* front);    // rows per batch item of a staged plane array (multiple of 8)
 bool staged_conv_supported(const PlaneConvArgs& a);
@@ -298,21 +282,15 @@ extern bool g_stft_tc;           // STFT as a tcgen05 GEMM (default) / fp32 CUDA
 // parities of a transposed conv are two "variants" of one launch: they share the operand planes and differ in taps,
 // weights and accumulator columns, so the input is read and normalised once.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kRawGroup = 32;            // operand rows per ring stage
-constexpr int kRawMaxStreams = 4;        // (source, addend) tensors
-constexpr int kRawMaxSlabs = 4;          // 64-channel K slabs
+constexpr int kRawMaxSlabs = 4;          // 64-channel K slabs = source tensors (each [B][T][Fin][64] fp32, one or two addends)
 struct RawConvArgs {
-    int nstreams;
-    const float* sx[kRawMaxStreams];     // [B][T][Fin][C] raw fp32
-    int s_C[kRawMaxStreams];
-    int s_stage_off[kRawMaxStreams];     // byte offset of the stream inside a ring stage
-    int s_coef_off[kRawMaxStreams];      // float offset of the stream's [3][C] coefficient block in shared memory
-    Xform s_xf[kRawMaxStreams];
-    int s_mode[kRawMaxStreams];          // 0 none, 1 norm -> PReLU, 2 PReLU -> norm
-    int stage_bytes, ncoef;              // ring stage size (all streams) ; sum of C over the streams
     int nslab;
-    int sl_s0[kRawMaxSlabs], sl_s1[kRawMaxSlabs];    // streams of the slab's addends (sl_s1 < 0: one addend)
-    int sl_c0[kRawMaxSlabs];             // first channel of the slab inside its stream's rows
+    const float* x0[kRawMaxSlabs];       // first addend of the slab's source
+    const float* x1[kRawMaxSlabs];       // second addend (lazy residual sum of a module) or null
+    Xform xf0[kRawMaxSlabs], xf1[kRawMaxSlabs];
+    int mode0[kRawMaxSlabs], mode1[kRawMaxSlabs];    // 0 none, 1 norm -> PReLU, 2 PReLU -> norm
+    // ring stage = the raw rows one group of G operand rows needs from ONE slab: addend 0 at byte 0, addend 1 at add1_off
+    int G, stage_bytes, add1_off;
     int B, T, Fin, P;
     int nplanes, plane_cols[2], col_stride, col_off[2];
     int back, fwd, tiles_per_b;

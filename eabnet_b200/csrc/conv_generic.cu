@@ -30,8 +30,6 @@ __global__ void __launch_bounds__(NTHREADS) conv_generic_kernel(const ConvArgs a
     float* Bs = As + 2 * KC * TM;                // [2][KC][N]
     float* coef = Bs + 2 * KC * N;               // [3][Ctot]
 
-    pdl_trigger();
-    pdl_wait();
     const int tid = threadIdx.x;
     // streaming: rows of all streams share one row space (r = stream * E + e, one frame each); offline: rows (t, e) of item b
     const bool streaming = a.step != nullptr;

@@ -33,14 +33,11 @@ namespace {
 using namespace umma;
 
 constexpr int TM = 128;
-constexpr int GROUP = kRawGroup;
 constexpr int NSTAGE_MAX = 8;
 constexpr int NSB_MAX = 8;
 constexpr int NCTRL = 128;                       // warps 0-3: loader, MMA issuer, weight loader, spare
 constexpr int NEPI = 256;                        // warps 4-11
 constexpr int SMEM_LIMIT = 227 * 1024;
-
-inline int ceil8(int x) { return (x + 7) & ~7; }
 
 struct RawPlan {
     int R, plane_bytes, buf_bytes, b_stage_bytes, w_images, ngroups;
@@ -56,22 +53,22 @@ __host__ __device__ inline RawPlan make_raw_plan(const RawConvArgs& a) {
     p.b_stage_bytes = a.N * 128;
     p.w_images = 0;
     for (int v = 0; v < a.nvar; ++v) p.w_images += a.ntaps[v] * a.nslab * npb;
-    p.ngroups = (p.R + GROUP - 1) / GROUP;
+    p.ngroups = (p.R + a.G - 1) / a.G;
     p.b_off = a.nbuf * p.buf_bytes;
     p.ring_off = p.b_off + (a.resident ? p.w_images : a.nsb) * p.b_stage_bytes;
     p.bias_off = p.ring_off + a.nstage * a.stage_bytes;
     p.coef_off = p.bias_off + a.N * 4;
-    p.bar_off = (p.coef_off + 3 * a.ncoef * 4 + 15) & ~15;
+    p.bar_off = (p.coef_off + a.nslab * 2 * 3 * 64 * 4 + 15) & ~15;          // coefficients [slab][addend][s | h | alpha][64]
     p.total = p.bar_off + 512 + 1024;                    // barriers + slack for the 1024-byte alignment of the base
     return p;
 }
 
-// raw rows (units of one [C] row of a source tensor, relative to the batch item) that operand rows [32 j, 32 j + 32) of the
+// raw rows (units of one 64-channel row of a source tensor, relative to the batch item) that operand rows [G j, G j + G) of the
 // tile at padded row `row0` read: [g_lo, g_lo + n).  Operand row rho <-> padded row r = row0 - back + rho = t P + col;
 // plane p holds input column col * col_stride + col_off[p] (zeros where that is >= Fin or r is outside [0, T P)).
 __device__ __forceinline__ void group_range(const RawConvArgs& a, int R, int rows_per_b, int row0, int j, int& g_lo, int& n) {
-    int r_a = row0 - a.back + j * GROUP;
-    int r_b = min(r_a + GROUP - 1, row0 - a.back + R - 1);
+    int r_a = row0 - a.back + j * a.G;
+    int r_b = min(r_a + a.G - 1, row0 - a.back + R - 1);
     r_a = max(r_a, 0);
     r_b = min(r_b, rows_per_b - 1);
     g_lo = 0; n = 0;
@@ -88,22 +85,76 @@ __device__ __forceinline__ float4 lds128(const uint8_t* p) { return *reinterpret
 
 // norm + PReLU of four channels; mode 0 none, 1 norm -> PReLU (2-D blocks), 2 PReLU -> norm (TCM order).  The expressions
 // are the ones stage_kernel uses, so both paths round identically.
-__device__ __forceinline__ void xf4(float4& v, const float* cf, int C, int mode) {
-    if (mode == 0) return;
-    const float4 s = *reinterpret_cast<const float4*>(cf);
-    const float4 h = *reinterpret_cast<const float4*>(cf + C);
-    const float4 al = *reinterpret_cast<const float4*>(cf + 2 * C);
+__device__ __forceinline__ void xf4(float4& v, const float4& s, const float4& h, const float4& al, int mode) {
     if (mode == 1) {
         float z;
         z = fmaf(v.x, s.x, h.x); v.x = fmaxf(z, 0.f) + al.x * fminf(z, 0.f);
         z = fmaf(v.y, s.y, h.y); v.y = fmaxf(z, 0.f) + al.y * fminf(z, 0.f);
         z = fmaf(v.z, s.z, h.z); v.z = fmaxf(z, 0.f) + al.z * fminf(z, 0.f);
         z = fmaf(v.w, s.w, h.w); v.w = fmaxf(z, 0.f) + al.w * fminf(z, 0.f);
-    } else {
+    } else if (mode == 2) {
         v.x = fmaf(fmaxf(v.x, 0.f) + al.x * fminf(v.x, 0.f), s.x, h.x);
         v.y = fmaf(fmaxf(v.y, 0.f) + al.y * fminf(v.y, 0.f), s.y, h.y);
         v.z = fmaf(fmaxf(v.z, 0.f) + al.z * fminf(v.z, 0.f), s.z, h.z);
         v.w = fmaf(fmaxf(v.w, 0.f) + al.w * fminf(v.w, 0.f), s.w, h.w);
+    }
+}
+
+// One batch of NI operand chunks (8 channels each) of ONE slab for one thread: every raw load is issued before any
+// arithmetic, the NI chains are independent (a lone chain runs at ALU latency: measured 2.1 k cycles per 32-row group with
+// one chunk per thread at a time).  soff = byte offset of the item's raw row in the stage (0 for pad items, whose result is
+// replaced by zeros), dst = its 16-byte slot in the hi image (lo image plane_bytes further).  cf = [addend][s | h | alpha][64].
+template <int NI, bool DUAL>
+__device__ __forceinline__ void xf_items(const uint8_t* st0, const uint8_t* st1, const int (&soff)[NI], const bool (&ok)[NI],
+                                         uint8_t* const (&dst)[NI], const float* cf, int mode0, int mode1, int qa, int chA,
+                                         int chB, bool with_lo, int plane_bytes) {
+    float4 vA[NI], vB[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        vA[i] = lds128(st0 + soff[i] + qa * 16);
+        vB[i] = lds128(st0 + soff[i] + (qa ^ 1) * 16);
+    }
+    if (mode0 != 0) {
+        const float4 sA = *reinterpret_cast<const float4*>(cf + chA), hA = *reinterpret_cast<const float4*>(cf + 64 + chA),
+                     aA = *reinterpret_cast<const float4*>(cf + 128 + chA);
+        const float4 sB = *reinterpret_cast<const float4*>(cf + chB), hB = *reinterpret_cast<const float4*>(cf + 64 + chB),
+                     aB = *reinterpret_cast<const float4*>(cf + 128 + chB);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) { xf4(vA[i], sA, hA, aA, mode0); xf4(vB[i], sB, hB, aB, mode0); }
+    }
+    if (DUAL) {                                  // + the second addend of a module's lazy residual sum (EaBNet.py:386)
+        float4 wA[NI], wB[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            wA[i] = lds128(st1 + soff[i] + qa * 16);
+            wB[i] = lds128(st1 + soff[i] + (qa ^ 1) * 16);
+        }
+        if (mode1 != 0) {
+            const float* c1 = cf + 192;
+            const float4 sA = *reinterpret_cast<const float4*>(c1 + chA), hA = *reinterpret_cast<const float4*>(c1 + 64 + chA),
+                         aA = *reinterpret_cast<const float4*>(c1 + 128 + chA);
+            const float4 sB = *reinterpret_cast<const float4*>(c1 + chB), hB = *reinterpret_cast<const float4*>(c1 + 64 + chB),
+                         aB = *reinterpret_cast<const float4*>(c1 + 128 + chB);
+#pragma unroll
+            for (int i = 0; i < NI; ++i) { xf4(wA[i], sA, hA, aA, mode1); xf4(wB[i], sB, hB, aB, mode1); }
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            vA[i].x += wA[i].x; vA[i].y += wA[i].y; vA[i].z += wA[i].z; vA[i].w += wA[i].w;
+            vB[i].x += wB[i].x; vB[i].y += wB[i].y; vB[i].z += wB[i].z; vB[i].w += wB[i].w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        if (!ok[i]) { vA[i] = make_float4(0.f, 0.f, 0.f, 0.f); vB[i] = vA[i]; }     // literal zeros: pad rows / columns
+        const uint32_t hA0 = pack_h2(vA[i].x, vA[i].y), hA1 = pack_h2(vA[i].z, vA[i].w);
+        const uint32_t hB0 = pack_h2(vB[i].x, vB[i].y), hB1 = pack_h2(vB[i].z, vB[i].w);
+        *reinterpret_cast<uint4*>(dst[i]) = qa ? make_uint4(hB0, hB1, hA0, hA1) : make_uint4(hA0, hA1, hB0, hB1);
+        if (with_lo) {
+            const uint32_t lA0 = pack_lo_h2(vA[i].x, vA[i].y, hA0), lA1 = pack_lo_h2(vA[i].z, vA[i].w, hA1);
+            const uint32_t lB0 = pack_lo_h2(vB[i].x, vB[i].y, hB0), lB1 = pack_lo_h2(vB[i].z, vB[i].w, hB1);
+            *reinterpret_cast<uint4*>(dst[i] + plane_bytes) = qa ? make_uint4(lB0, lB1, lA0, lA1) : make_uint4(lA0, lA1, lB0, lB1);
+        }
     }
 }
 
@@ -122,6 +173,21 @@ __device__ __forceinline__ float fold8(const float (&u)[8], int lane) {
     u1 += __shfl_xor_sync(0xffffffffu, u1, 1);
     return u1;
 }
+
+// setmaxnreg moves registers inside the CTA's OWN allocation (640 threads x 96 at launch = 61 440): the increases must be
+// covered by the decreases of the same CTA (128 x 48 + 256 x 128 + 256 x 88 = 61 440), or the increase spins forever.
+// mbarrier waits of this kernel: the polling form (try_wait without a suspend-time hint).  The hinted form compiles to
+// TRYWAIT + NANOSLEEP.SYNCS, whose wake-up latency is paid on every ring stage here (a handshake per 32 operand rows).
+#ifdef EAB_RAW_SUSPEND
+#define RWAIT mbar_wait
+#else
+#define RWAIT mbar_wait_spin
+#endif
+#ifdef EAB_RAW_DEBUG
+constexpr bool kDbg = true;
+#else
+constexpr bool kDbg = false;
+#endif
 
 template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
@@ -166,10 +232,8 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
         for (int i = 0; i < 2; ++i) mbar_init(&acc_empty[i], NEPI);
         fence_barrier_init();
     }
-    pdl_trigger();
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
-    pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,36 +245,42 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
     const int rows_per_b = a.T * a.P;
 
     if (warp < 4) {
-        if (NTW == 8) reg_dec<40>();
+        if (NTW == 8) reg_dec<48>();
         if (warp == 0) {
             // =========================================================================== raw loader
             int stage = 0;
             uint32_t sphase = 0;
-            int rowbytes_all = 0;
-            for (int s = 0; s < a.nstreams; ++s) rowbytes_all += a.s_C[s] * 4;
+            const bool dbg_on = kDbg && a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+            long long t_w = 0;
+            const long long t_start = dbg_on ? clock64() : 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int b = tile / a.tiles_per_b;
                 const int row0 = (tile - b * a.tiles_per_b) * TM;
                 for (int j = 0; j < pl.ngroups; ++j) {
                     int g_lo, n;
                     group_range(a, pl.R, rows_per_b, row0, j, g_lo, n);
-                    mbar_wait(&raw_empty[stage], sphase ^ 1);
-                    if (lane == 0) {
-                        if (n > 0) {
-                            mbar_arrive_expect_tx(&raw_full[stage], (uint32_t)(n * rowbytes_all));
-                            uint8_t* dst = ring + (size_t)stage * a.stage_bytes;
-                            for (int s = 0; s < a.nstreams; ++s) {
-                                const float* src = a.sx[s] + ((size_t)b * a.T * a.Fin + g_lo) * a.s_C[s];
-                                bulk_copy_g2s(dst + a.s_stage_off[s], src, (uint32_t)(n * a.s_C[s] * 4), &raw_full[stage]);
+                    const size_t goff = ((size_t)b * a.T * a.Fin + g_lo) * 64;
+                    for (int s = 0; s < a.nslab; ++s) {
+                        const long long w0 = dbg_on ? clock64() : 0;
+                        RWAIT(&raw_empty[stage], sphase ^ 1);
+                        if (dbg_on) t_w += clock64() - w0;
+                        if (lane == 0) {
+                            if (n > 0) {
+                                const bool dual = a.x1[s] != nullptr;
+                                mbar_arrive_expect_tx(&raw_full[stage], (uint32_t)(n * 256 * (dual ? 2 : 1)));
+                                uint8_t* dst = ring + (size_t)stage * a.stage_bytes;
+                                bulk_copy_g2s(dst, a.x0[s] + goff, (uint32_t)(n * 256), &raw_full[stage]);
+                                if (dual) bulk_copy_g2s(dst + a.add1_off, a.x1[s] + goff, (uint32_t)(n * 256), &raw_full[stage]);
+                            } else {
+                                mbar_arrive(&raw_full[stage]);
                             }
-                        } else {
-                            mbar_arrive(&raw_full[stage]);
                         }
+                        __syncwarp();
+                        if (++stage == a.nstage) { stage = 0; sphase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == a.nstage) { stage = 0; sphase ^= 1; }
                 }
             }
+            if (dbg_on) { a.dbg[4] = t_w; a.dbg[5] = clock64() - t_start; }
         } else if (warp == 1) {
             // =========================================================================== MMA issuer (convergent, see conv_tma)
             const uint32_t idesc = make_idesc(a.N);
@@ -218,15 +288,21 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
             const uint32_t bstep = (uint32_t)pl.b_stage_bytes >> 4;
             int stage = 0;
             uint32_t sphase = 0;
-            if (a.resident && tile_begin < tile_end) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }
+            const bool dbg_on = kDbg && a.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+            long long t_wa = 0, t_wo = 0, t_wb = 0;
+            const long long t_start = dbg_on ? clock64() : 0;
+            if (a.resident && tile_begin < tile_end) { RWAIT(&b_full[0], 0u); tc_fence_after(); }
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int ord = tile - tile_begin;
                 const int acc = ord & 1;
                 const int buf = ord % a.nbuf;
                 const uint32_t bphase = (uint32_t)((ord / a.nbuf) & 1);
                 const uint32_t aphase = (uint32_t)((ord >> 1) & 1);
-                mbar_wait(&acc_empty[acc], aphase ^ 1);
-                mbar_wait(&opnd_full[buf], bphase);
+                const long long w0 = dbg_on ? clock64() : 0;
+                RWAIT(&acc_empty[acc], aphase ^ 1);
+                const long long w1 = dbg_on ? clock64() : 0;
+                RWAIT(&opnd_full[buf], bphase);
+                if (dbg_on) { t_wa += w1 - w0; t_wo += clock64() - w1; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
                 const uint32_t origin = smem_u32(opnd + buf * pl.buf_bytes) >> 4;
@@ -234,7 +310,9 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                     const uint32_t fl = a.unit_c[unit];
                     uint32_t blo;
                     if (!a.resident) {
-                        mbar_wait(&b_full[stage], sphase);
+                        const long long w2 = dbg_on ? clock64() : 0;
+                        RWAIT(&b_full[stage], sphase);
+                        if (dbg_on) t_wb += clock64() - w2;
                         tc_fence_after();
                         blo = bs_lo + (uint32_t)stage * bstep;
                     } else {
@@ -250,6 +328,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                 }
                 umma_commit_elect(&opnd_empty[buf]);
             }
+            if (dbg_on) { a.dbg[6] = t_wa; a.dbg[7] = t_wo; a.dbg[8] = t_wb; a.dbg[9] = clock64() - t_start; a.dbg[12] = tile_end - tile_begin; a.dbg[13] = pl.ngroups; }
         } else if (warp == 2) {
             // =========================================================================== weight loader
             const uint32_t bytes = (uint32_t)pl.b_stage_bytes;
@@ -270,7 +349,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                     for (int v = 0; v < a.nvar; ++v)
                         for (int ts = 0; ts < a.ntaps[v] * a.nslab; ++ts)
                             for (int pass = 0; pass < a.npass; ++pass) {
-                                mbar_wait(&b_empty[stage], sphase ^ 1);
+                                RWAIT(&b_empty[stage], sphase ^ 1);
                                 if (lane == 0) {
                                     const float* img = (pass == 2 ? a.Wlo[v] : a.Whi[v]) + (size_t)ts * a.N * 32;
                                     mbar_arrive_expect_tx(&b_full[stage], bytes);
@@ -284,7 +363,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
     } else if (warp < 12) {
         // =========================================================================== epilogue (8 warps)
         // thread = output row (TMEM lane), warp = (lane quadrant, half of the 64 output channels); see conv_tma_kernel
-        if (NTW == 8) reg_inc<152>();
+        if (NTW == 8) reg_inc<128>();
         const int quad = warp & 3;
         const int chalf = ((warp - 4) >> 2) & 1;
         const int row = quad * 32 + lane;
@@ -312,6 +391,9 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
         };
         int acc = 0;
         uint32_t aphase = 0;
+        const bool dbg_on = kDbg && a.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+        long long t_wf = 0;
+        const long long t_start = dbg_on ? clock64() : 0;
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int b = tile / a.tiles_per_b;
             if (b != cur_b) { flush(cur_b); cur_b = b; }
@@ -327,7 +409,9 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
             for (int v = 0; v < a.nvar; ++v) {
                 const bool row_valid = e < a.E[v];
                 const long long off = (fbase + (e * a.out_stride + a.out_off[v])) * 64;
-                mbar_wait(&acc_full[acc * 2 + v], aphase);
+                const long long w0 = dbg_on ? clock64() : 0;
+                RWAIT(&acc_full[acc * 2 + v], aphase);
+                if (dbg_on) t_wf += clock64() - w0;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols + v * a.N);
 #pragma unroll
@@ -366,19 +450,26 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         flush(cur_b);
+        if (dbg_on) { a.dbg[10] = t_wf; a.dbg[11] = clock64() - t_start; }
     } else {
         // =========================================================================== transform warps
-        // thread = (operand row of the group, 16-byte fp16 chunk = 8 channels).  The two 16-byte halves of the thread's
-        // 32 raw bytes are read in an order that depends on the chunk (c8 >= 4: upper half first) so that the eight
-        // lanes of a quarter-warp touch all 32 banks in both loads.
-        if (NTW == 8) reg_dec<80>();
+        // thread = (row rr of each 32-row block of the group, 16-byte fp16 chunk c8 = 8 channels); a ring stage is one
+        // (group, slab) and gives the thread NI = (G / 32) x nplanes chunks, transformed as one batch (xf_items).  The two
+        // 16-byte halves of a chunk's 32 raw bytes are read in an order that depends on c8 (c8 >= 4: upper half first) so that
+        // the eight lanes of a quarter-warp touch all 32 banks in both loads.
+        if (NTW == 8) reg_dec<88>();
         const int ttid = tid - TR0;
         const int c8 = ttid & 7;
+        const int rr = ttid >> 3;                            // 0..31
         const int qa = (c8 >> 2) & 1;                        // which half this thread loads first
         const int chA = c8 * 8 + qa * 4, chB = c8 * 8 + (qa ^ 1) * 4;
+        const int rpt = a.G >> 5;                            // rows per thread per group: 1, 2 or 4
         int stage = 0;
         uint32_t sphase = 0;
         int cur_b = -1;
+        const bool dbg_on = kDbg && a.dbg != nullptr && blockIdx.x == 0 && ttid == 0;
+        long long t_wo = 0, t_wr = 0, t_cf = 0;
+        const long long t_start = dbg_on ? clock64() : 0;
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int ord = tile - tile_begin;
             const int buf = ord % a.nbuf;
@@ -386,87 +477,95 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
             if (b != cur_b) {
+                const long long w0 = dbg_on ? clock64() : 0;
                 named_bar_sync(1, NTT);
-                for (int s = 0; s < a.nstreams; ++s) {
-                    const int C = a.s_C[s];
-                    float* cf = coef + a.s_coef_off[s];
-                    for (int c = ttid; c < C; c += NTT) {
-                        float cs, ch, ca;
-                        xform_coeffs(a.s_xf[s], b, C, c, cs, ch, ca);
-                        cf[c] = cs; cf[C + c] = ch; cf[2 * C + c] = a.s_xf[s].prelu ? ca : 1.f;
-                    }
+                for (int i = ttid; i < a.nslab * 2 * 64; i += NTT) {
+                    const int s = i >> 7, ad = (i >> 6) & 1, c = i & 63;
+                    float cs = 1.f, ch = 0.f, ca = 1.f;
+                    if (ad == 0) { xform_coeffs(a.xf0[s], b, 64, c, cs, ch, ca); if (!a.xf0[s].prelu) ca = 1.f; }
+                    else if (a.x1[s]) { xform_coeffs(a.xf1[s], b, 64, c, cs, ch, ca); if (!a.xf1[s].prelu) ca = 1.f; }
+                    float* cf = coef + (s * 2 + ad) * 192;
+                    cf[c] = cs; cf[64 + c] = ch; cf[128 + c] = ca;
                 }
                 named_bar_sync(1, NTT);
                 cur_b = b;
+                if (dbg_on) t_cf += clock64() - w0;
             }
-            mbar_wait(&opnd_empty[buf], bphase ^ 1);
+            const long long w1 = dbg_on ? clock64() : 0;
+            RWAIT(&opnd_empty[buf], bphase ^ 1);
+            if (dbg_on) t_wo += clock64() - w1;
             uint8_t* obuf = opnd + (size_t)buf * pl.buf_bytes;
             for (int j = 0; j < pl.ngroups; ++j) {
                 int g_lo, n;
                 group_range(a, pl.R, rows_per_b, row0, j, g_lo, n);
-                mbar_wait(&raw_full[stage], sphase);
-                const uint8_t* sbase = ring + (size_t)stage * a.stage_bytes;
-#pragma unroll 1
-                for (int rr = ttid >> 3; rr < GROUP; rr += NTT / 8) {
-                    const int rho = j * GROUP + rr;
-                    if (rho >= pl.R) break;
+                // this thread's items: (row block h, plane p) -> raw row offset in the stage, validity, destination slot
+                int soff[4];
+                bool ok[4];
+                int doff[4];
+                bool any = false;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int h = a.nplanes == 2 ? (i >> 1) : i;
+                    const int p = a.nplanes == 2 ? (i & 1) : 0;
+                    const int rho = j * a.G + rr + 32 * h;
                     const int r = row0 - a.back + rho;
-                    const bool rvalid = r >= 0 && r < rows_per_b;
+                    const bool live = h < rpt && rho < pl.R;             // the thread has this item at all
+                    const bool rvalid = live && r >= 0 && r < rows_per_b;
                     int t = 0, col = 0;
                     if (rvalid) {
                         t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
                         col = r - t * a.P;
                     }
-                    uint8_t* drow = obuf + rho * 128 + ((c8 ^ (rho & 7)) << 4);
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) {
-                        if (p >= a.nplanes) break;
-                        const bool ok = rvalid && col < a.plane_cols[p];
-                        const int lrow = t * a.Fin + col * a.col_stride + a.col_off[p] - g_lo;
+                    ok[i] = rvalid && col < a.plane_cols[p];
+                    soff[i] = ok[i] ? (t * a.Fin + col * a.col_stride + a.col_off[p] - g_lo) * 256 + c8 * 32 : c8 * 32;
+                    doff[i] = live ? (p * a.nslab * npb) * pl.plane_bytes + rho * 128 + ((c8 ^ (rho & 7)) << 4) : -1;
+                    any = any || live;
+                }
+                const int ni = rpt * a.nplanes;                          // 1 (dual, stride 1 ... never), 2 or 4 live item slots
 #pragma unroll 1
-                        for (int s = 0; s < a.nslab; ++s) {
-                            float4 vA = make_float4(0.f, 0.f, 0.f, 0.f), vB = vA;
-                            if (ok) {
-                                const int s0 = a.sl_s0[s], s1 = a.sl_s1[s];
-                                const int C0 = a.s_C[s0];
-                                const uint8_t* src = sbase + a.s_stage_off[s0] + (size_t)lrow * (C0 * 4) + a.sl_c0[s] * 4 + c8 * 32;
-                                vA = lds128(src + qa * 16);
-                                vB = lds128(src + (qa ^ 1) * 16);
-                                const float* cf = coef + a.s_coef_off[s0] + a.sl_c0[s];
-                                xf4(vA, cf + chA, C0, a.s_mode[s0]);
-                                xf4(vB, cf + chB, C0, a.s_mode[s0]);
-                                if (s1 >= 0) {                   // + the second addend of a module's lazy residual sum
-                                    const int C1 = a.s_C[s1];
-                                    const uint8_t* src2 = sbase + a.s_stage_off[s1] + (size_t)lrow * (C1 * 4) + a.sl_c0[s] * 4 + c8 * 32;
-                                    float4 wA = lds128(src2 + qa * 16);
-                                    float4 wB = lds128(src2 + (qa ^ 1) * 16);
-                                    const float* cf2 = coef + a.s_coef_off[s1] + a.sl_c0[s];
-                                    xf4(wA, cf2 + chA, C1, a.s_mode[s1]);
-                                    xf4(wB, cf2 + chB, C1, a.s_mode[s1]);
-                                    vA.x += wA.x; vA.y += wA.y; vA.z += wA.z; vA.w += wA.w;
-                                    vB.x += wB.x; vB.y += wB.y; vB.z += wB.z; vB.w += wB.w;
-                                }
+                for (int s = 0; s < a.nslab; ++s) {
+                    const long long w2 = dbg_on ? clock64() : 0;
+                    RWAIT(&raw_full[stage], sphase);
+                    if (dbg_on) t_wr += clock64() - w2;
+                    const uint8_t* st0 = ring + (size_t)stage * a.stage_bytes;
+                    const uint8_t* st1 = st0 + a.add1_off;
+                    const float* cf = coef + s * 2 * 192;
+                    const int sadd = s * npb * pl.plane_bytes;
+                    const bool dual = a.x1[s] != nullptr;
+                    if (any) {
+                        if (ni == 4) {
+                            // a pad-only tail slot (doff < 0) writes nothing: send it to the thread's first slot, with its value
+                            uint8_t* dst[4];
+                            int so[4]; bool k[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const bool use = doff[i] >= 0;
+                                dst[i] = obuf + sadd + (use ? doff[i] : doff[0]); so[i] = use ? soff[i] : soff[0]; k[i] = use ? ok[i] : ok[0];
                             }
-                            const uint32_t hA0 = pack_h2(vA.x, vA.y), hA1 = pack_h2(vA.z, vA.w);
-                            const uint32_t hB0 = pack_h2(vB.x, vB.y), hB1 = pack_h2(vB.z, vB.w);
-                            uint8_t* dst = drow + (size_t)((p * a.nslab + s) * npb) * pl.plane_bytes;
-                            *reinterpret_cast<uint4*>(dst) = qa ? make_uint4(hB0, hB1, hA0, hA1) : make_uint4(hA0, hA1, hB0, hB1);
-                            if (npb == 2) {
-                                const uint32_t lA0 = pack_lo_h2(vA.x, vA.y, hA0), lA1 = pack_lo_h2(vA.z, vA.w, hA1);
-                                const uint32_t lB0 = pack_lo_h2(vB.x, vB.y, hB0), lB1 = pack_lo_h2(vB.z, vB.w, hB1);
-                                *reinterpret_cast<uint4*>(dst + pl.plane_bytes) = qa ? make_uint4(lB0, lB1, lA0, lA1) : make_uint4(lA0, lA1, lB0, lB1);
+                            // (four chunks per thread only in launches without lazy pairs: the launcher halves G for those)
+                            xf_items<4, false>(st0, st1, so, k, dst, cf, a.mode0[s], a.mode1[s], qa, chA, chB, npb == 2, pl.plane_bytes);
+                        } else {
+                            uint8_t* dst[2];
+                            int so[2]; bool k[2];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const bool use = i < ni && doff[i] >= 0;
+                                dst[i] = obuf + sadd + (use ? doff[i] : doff[0]); so[i] = use ? soff[i] : soff[0]; k[i] = use ? ok[i] : ok[0];
                             }
+                            if (dual) xf_items<2, true>(st0, st1, so, k, dst, cf, a.mode0[s], a.mode1[s], qa, chA, chB, npb == 2, pl.plane_bytes);
+                            else xf_items<2, false>(st0, st1, so, k, dst, cf, a.mode0[s], a.mode1[s], qa, chA, chB, npb == 2, pl.plane_bytes);
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_empty[stage]);
+                    if (++stage == a.nstage) { stage = 0; sphase ^= 1; }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&raw_empty[stage]);
-                if (++stage == a.nstage) { stage = 0; sphase ^= 1; }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&opnd_full[buf]);
         }
+        if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wo; a.dbg[2] = t_wr; a.dbg[3] = t_cf; }
     }
 
     tc_fence_before();
@@ -504,45 +603,42 @@ bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
     memset(&a, 0, sizeof(a));
     if (q.Cout != 64 || (q.N != 64 && q.N != 128) || (q.gate_off != 0 && (q.gate_off != 64 || q.N != 128)) || (q.gate_off == 0 && q.N != 64))
         return false;
-    if (q.relu || q.resid || q.nstats > 1 || q.stat_alpha[0] || q.stft_M > 0 || q.wide_k > 0 || q.out_half || q.round_half) return false;
+    if (q.relu || q.resid || q.nstats > 1 || q.stat_alpha[0] || q.stft_M > 0 || q.wide_k > 0) return false;
     if (q.out_ld != 64 || q.out_coff != 0 || q.stats_ld != 0 || q.stats_coff != 0) return false;
     if ((reinterpret_cast<uintptr_t>(q.out) & 31) != 0) return false;
     if (q.npass != 1 && q.npass != 3) return false;
     if (q.nplanes < 1 || q.nplanes > 2 || q.P < 1) return false;
-    // streams and slabs
-    int nslab = 0, ncoef = 0, stage_bytes = 0;
+    // slabs = sources (64 channels each, one or two addends)
+    int nslab = 0;
+    bool any_dual = false;
     for (int i = 0; i < q.nsrc; ++i) {
         const ConvSrc& s = q.src[i];
-        if (s.C % 64 != 0 || s.C < 64 || s.half || s.half2 || s.RT != 0) return false;     // (no null check: planning passes run on offsets)
+        if (s.C != 64 || s.RT != 0) return false;     // (no null check: planning passes run on offsets)
         if ((reinterpret_cast<uintptr_t>(s.x) & 15) || (s.x2 && (reinterpret_cast<uintptr_t>(s.x2) & 15))) return false;
-        const int st0 = a.nstreams;
-        const int nadd = s.x2 ? 2 : 1;
-        if (a.nstreams + nadd > kRawMaxStreams) return false;
-        for (int k = 0; k < nadd; ++k) {
-            const int st = a.nstreams++;
-            a.sx[st] = k ? s.x2 : s.x;
-            a.s_xf[st] = k ? s.xf2 : s.xf;
-            a.s_C[st] = s.C;
-            a.s_mode[st] = (a.s_xf[st].affine == 0 && a.s_xf[st].prelu == 0) ? 0 : (a.s_xf[st].prelu == 1 ? 2 : 1);
-            a.s_stage_off[st] = stage_bytes;
-            a.s_coef_off[st] = 3 * ncoef;
-            stage_bytes += GROUP * q.col_stride * s.C * 4;
-            ncoef += s.C;
+        if (nslab >= kRawMaxSlabs) return false;
+        a.x0[nslab] = s.x; a.xf0[nslab] = s.xf;
+        a.mode0[nslab] = (s.xf.affine == 0 && s.xf.prelu == 0) ? 0 : (s.xf.prelu == 1 ? 2 : 1);
+        a.x1[nslab] = s.x2;
+        if (s.x2) {
+            a.xf1[nslab] = s.xf2;
+            a.mode1[nslab] = (s.xf2.affine == 0 && s.xf2.prelu == 0) ? 0 : (s.xf2.prelu == 1 ? 2 : 1);
+            any_dual = true;
+        } else {
+            a.xf1[nslab] = xform_identity();
         }
-        for (int c = 0; c < s.C; c += 64) {
-            if (nslab >= kRawMaxSlabs) return false;
-            a.sl_s0[nslab] = st0;
-            a.sl_s1[nslab] = s.x2 ? st0 + 1 : -1;
-            a.sl_c0[nslab] = c;
-            ++nslab;
-        }
+        ++nslab;
     }
     if (nslab != q.nslab) return false;
-    a.nslab = nslab; a.ncoef = ncoef; a.stage_bytes = stage_bytes;
+    a.nslab = nslab;
+    if (q.col_stride < 1 || q.col_stride > 2 || q.nplanes != q.col_stride) return false;
+    // group size: a stage holds <= 128 raw rows per addend (32 KB), i.e. 2 or 4 operand chunks per transform thread
+    a.G = 128 / (q.col_stride * (any_dual ? 2 : 1));
+    a.add1_off = a.G * q.col_stride * 256;
+    a.stage_bytes = a.add1_off * (any_dual ? 2 : 1);
     a.B = q.B; a.T = q.T; a.Fin = q.Fin; a.P = q.P;
     a.nplanes = q.nplanes; a.col_stride = q.col_stride;
     for (int i = 0; i < 2; ++i) { a.plane_cols[i] = q.plane_cols[i]; a.col_off[i] = q.col_off[i]; }
-    if (a.col_stride < 1 || a.col_stride > 2 || a.plane_cols[0] > a.P || (a.nplanes == 2 && a.plane_cols[1] > a.P)) return false;
+    if (a.plane_cols[0] > a.P || (a.nplanes == 2 && a.plane_cols[1] > a.P)) return false;
     if ((long long)a.P * a.col_stride < a.Fin) return false;         // group_range: a frame's columns fit its padded pitch
     for (int pl = 0; pl < a.nplanes; ++pl)                          // planes cover input columns < Fin only
         if (a.plane_cols[pl] > 0 && (a.plane_cols[pl] - 1) * a.col_stride + a.col_off[pl] >= a.Fin) return false;
@@ -563,7 +659,7 @@ bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
             w.Cout != q.Cout || w.N != q.N || w.gate_off != q.gate_off || w.bias != q.bias || w.out != q.out || w.out_stride != q.out_stride ||
             w.Fout != q.Fout || w.B != q.B || w.T != q.T || w.Fin != q.Fin || w.nsrc != q.nsrc || w.col_stride != q.col_stride ||
             w.plane_cols[0] != q.plane_cols[0] || w.plane_cols[1] != q.plane_cols[1] || w.nstats != q.nstats || w.stats[0] != q.stats[0] ||
-            w.relu || w.resid || w.stft_M > 0 || w.wide_k > 0 || w.out_half || w.round_half || w.out_ld != 64 || w.out_coff != 0)
+            w.relu || w.resid || w.stft_M > 0 || w.wide_k > 0 || w.out_ld != 64 || w.out_coff != 0)
             return false;
         for (int i = 0; i < q.nsrc; ++i)
             if (w.src[i].x != q.src[i].x || w.src[i].x2 != q.src[i].x2 || w.src[i].C != q.src[i].C) return false;
@@ -625,13 +721,18 @@ int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned lon
     const long long ntiles = (long long)a.B * a.tiles_per_b;
     if (ntiles >= (1ll << 30)) return fail("conv_raw: too many tiles");
     const int grid = (int)(ntiles < sms ? ntiles : sms);
-    double pos = 0, kn = 0, in_bytes = 0;
+    // algorithmic bytes: every input tensor once (a lazy residual pair is ONE tensor), the output once, fp32;
+    // moved: both addends of a lazy pair, and the weights
+    double pos = 0, kn = 0, in_algo = 0, in_moved = 0;
     for (int v = 0; v < a.nvar; ++v) { pos += (double)a.B * a.T * a.E[v]; kn += (double)a.B * a.T * a.E[v] * a.ntaps[v]; }
-    for (int s = 0; s < a.nstreams; ++s) in_bytes += 4.0 * a.B * a.T * a.Fin * a.s_C[s];
+    for (int s = 0; s < a.nslab; ++s) {
+        in_algo += 4.0 * a.B * a.T * a.Fin * 64.0;
+        in_moved += 4.0 * a.B * a.T * a.Fin * 64.0 * (a.x1[s] ? 2 : 1);
+    }
     const double kreal = 64.0 * a.nslab;
     double wbytes = 0;
-    for (int v = 0; v < a.nvar; ++v) wbytes += 4.0 * a.ntaps[v] * kreal * a.N;
-    ProfScope ps("conv_raw", 2.0 * kn * kreal * a.N * a.algo_frac, in_bytes + 4.0 * pos * a.Cout + wbytes, st);
+    for (int v = 0; v < a.nvar; ++v) wbytes += 2.0 * (a.npass == 3 ? 2 : 1) * a.ntaps[v] * kreal * a.N;
+    ProfScope ps("conv_raw", 2.0 * kn * kreal * a.N * a.algo_frac, in_algo + 4.0 * pos * a.Cout, st, in_moved + 4.0 * pos * a.Cout + wbytes);
     EAB_CUDA(launch_k(conv_raw_kernel<NTW>, dim3(grid), dim3(NCTRL + NEPI + NTW * 32), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_raw_kernel");
     return 0;

@@ -8,13 +8,13 @@
 //   conv_tma_kernel  : the GEMM.  Because a tile's plane rows are now one contiguous, pre-swizzled byte range, the
 //                      whole A operand of a tile is fetched by ONE elected thread with cp.async.bulk (a few copies of
 //                      ~30 KB) straight into shared memory - no register staging, no conversion, no proxy fence, the
-//                      copy engine hides the latency.  Taps are row-shifted UMMA descriptors into those planes (see
-//                      conv_plane.cu), weights stream through a small ring, accumulators are double-buffered in TMEM, and
-//                      8 epilogue warps do bias / gate / ReLU / residual / statistics / bulk row stores.
+//                      copy engine hides the latency.  Taps are row-shifted UMMA descriptors into those planes, weights are
+//                      resident or stream through a small ring, accumulators are double-buffered in TMEM, and
+//                      8 epilogue warps do bias / gate / ReLU / residual / statistics / 32-byte row stores.
 //
-// conv_plane.cu (fused gather + transform producers) measured ~11k cycles per 128-row tile in the producer warps against
-// ~1k cycles of MMA; splitting the elementwise work out trades ~40 % more activation bytes for a conv kernel whose
-// critical path is the epilogue / MMA only.
+// Since round 2 the 2-D conv layers with 64-channel sources run on conv_raw.cu (no stage pass, no planes in HBM); this pair
+// remains for what that kernel does not take: the first layer (2M input channels, frequency-pair rows), the STFT-as-GEMM,
+// pointwise / dilated GEMMs with a residual, ReLU, two statistics or wide sources (TCM layer path, w_dnn, GaGNet heads).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -30,40 +30,20 @@ constexpr int TM = 128;
 constexpr int KC = 64;
 constexpr int NSB_MAX = 8;                      // weight ring stages: a.nsb in [2, 8], as many as fit next to two plane buffers
 constexpr int NEPI = 256;                       // 8 epilogue warps per group
-// warp 0 plane copies, 1 MMA issuer, 2 weight loader, 3 idle, 4-11 epilogue; 12-19 exist in the FUSED instantiation only
-// (in-kernel producers).  One epilogue group: its statistics cost almost nothing now (per-thread running sums), and at
-// 384 threads it can afford the 64 accumulator registers.
+// warp 0 plane copies, 1 MMA issuer, 2 weight loader, 3 idle, 4-11 epilogue.  One epilogue group: its statistics cost
+// almost nothing (per-thread running sums), and at 384 threads it can afford the 64 accumulator registers.
 constexpr int NTHREADS_STAGED = 128 + NEPI;
-constexpr int NTHREADS_FUSED = 128 + 2 * NEPI;
 
 inline int ceil8(int x) { return (x + 7) & ~7; }
-#ifdef EAB_CONV_EXPERIMENT
-#define CEXP(bit) ((a.exp_flags & (bit)) != 0)
-#else
-#define CEXP(bit) false
-#endif
-constexpr bool kTwoIssuers = false;
 constexpr int STAGE_RB = 8;                     // 32-row blocks per stage CTA
 
-// 8 consecutive channels starting at element offset `eoff` of an fp32 or fp16 activation tensor
-__device__ __forceinline__ void load8(const float* base, int is_half, size_t eoff, float4& v0, float4& v1) {
-    if (is_half) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(base) + eoff));
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
-        v0 = make_float4(a.x, a.y, b.x, b.y);
-        v1 = make_float4(c.x, c.y, d.x, d.y);
-    } else {
-        ld_global_nc_256(base + eoff, v0, v1);       // 8 channels = one 32-byte sector, one instruction
-    }
-}
+// 8 consecutive channels (one 32-byte sector, one instruction) starting at element offset `eoff`
+__device__ __forceinline__ void load8(const float* base, size_t eoff, float4& v0, float4& v1) { ld_global_nc_256(base + eoff, v0, v1); }
 
 // ------------------------------------------------------------------------------------------------ stage kernel
 // grid (row blocks, nplanes*nslab, B), 256 threads: 8 threads per plane row (8 channels = one 16-byte fp16 chunk each)
 __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
     __shared__ float coef[6 * 64];
-    pdl_trigger();
-    pdl_wait();
     const int b = blockIdx.z;
     const int ps = blockIdx.y;
     const int plane = ps / a.nslab;
@@ -128,9 +108,9 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
             if (col < a.plane_cols[plane]) {
                 const int fi = col * a.col_stride + a.col_off[plane];
                 const size_t eoff = (((size_t)b * a.T + t) * a.Fin + fi) * src.C + cbase + c8 * 8;
-                load8(src.x, src.half, eoff, v0, v1);
+                load8(src.x, eoff, v0, v1);
                 float4 w0, w1;
-                if (src.x2) load8(src.x2, src.half2, eoff, w0, w1);
+                if (src.x2) load8(src.x2, eoff, w0, w1);
                 if (mode != 0) {
                     float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
@@ -194,8 +174,8 @@ __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
     p.stg_off = p.b_off + (a.resident ? p.w_images : a.nsb) * p.b_stage_bytes;
     p.rowoff_off = p.stg_off;
     p.bias_off = p.rowoff_off;
-    p.utab_off = p.bias_off + a.N * 4;                   // fused producers: transform coefficients [2 addends][3][ncoef]
-    p.bar_off = (p.utab_off + (a.fused ? 6 * a.ncoef * 4 : 0) + 15) & ~15;
+    p.utab_off = p.bias_off + a.N * 4;
+    p.bar_off = (p.utab_off + 15) & ~15;
     p.total = p.bar_off + 256 + 1024;
     return p;
 }
@@ -216,9 +196,8 @@ __device__ __forceinline__ float fold8(const float (&u)[8], int lane) {
     return u1;
 }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) conv_tma_kernel(const PlaneConvArgs a) {
-    constexpr int NTHREADS = FUSED ? NTHREADS_FUSED : NTHREADS_STAGED;
+__global__ void __launch_bounds__(NTHREADS_STAGED, 1) conv_tma_kernel(const PlaneConvArgs a) {
+    constexpr int NTHREADS = NTHREADS_STAGED;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const Plan pl = make_plan(a);
@@ -244,15 +223,13 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
     const int nimg = a.nplanes * a.nslab * npb;
 
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], FUSED ? NEPI / 32 : 1); mbar_init(&plane_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
         for (int i = 0; i < NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
         fence_barrier_init();
     }
-    pdl_trigger();
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
-    pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -264,9 +241,7 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
     const int rows_per_b = a.T * a.P;
     const int units_per_tile = a.ntaps * a.nslab * a.npass;
 
-    if (warp == 0 && FUSED) {
-        // planes are produced in place by warps 12-19
-    } else if (warp == 0) {
+    if (warp == 0) {
         // =========================================================================== plane copies (one lane)
         int buf = 0;
         uint32_t bphase = 0;
@@ -287,28 +262,24 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
             __syncwarp();
             if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
-    } else if (warp == 1 || warp == 3) {
+    } else if (warp == 1) {
         // =========================================================================== MMA issuers
         // One elected thread issues every MMA and the warp is a serial instruction chain: measured ~200 cycles per MMA
         // when the tap / slab / pass geometry was re-derived inside a lane-0-only loop (4x the tensor pipe's 48-64).
         // The loop below is convergent (all lanes, warp-uniform operands from the constant bank), the per-unit operand
         // offsets come tabulated from the launcher, and a K step only adds 2 to the two descriptor low words.
-        // Two issuers (warps 1 and 3) alternate tiles: issuer j owns accumulator j, so two tiles' chains are in flight.
-        // Only with resident weights and exactly two plane buffers: issuer j then owns plane buffer j and accumulator j
-        // outright, so every mbarrier it waits on advances by exactly one phase per wait (a parity wait must never
-        // be two phases away from the barrier).  Otherwise one issuer walks all tiles.
-        const int isr = warp >> 1;                               // 0 or 1
-        const int nisr = (kTwoIssuers && a.resident && a.nbuf == 2) ? 2 : 1;       // measured: no gain over one issuer + 3 plane buffers
+        // (Two issuing warps alternating tiles were measured in round 1: no gain over one issuer + 3 plane buffers.)
+
         const uint32_t idesc = make_idesc(a.N);
-        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && isr == 0;
+        const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
         long long t_wacc = 0, t_wplane = 0, t_wb = 0;
         const long long t_start = dbg_on ? clock64() : 0;
         const uint32_t bs_lo = desc_lo(smem_u32(Bs));
         const uint32_t bstep = (uint32_t)pl.b_stage_bytes >> 4;
         int stage = 0;
         uint32_t sphase = 0;
-        if (a.resident && isr < nisr && tile_begin + isr < tile_end) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }
-        for (int tile = isr < nisr ? tile_begin + isr : tile_end; tile < tile_end; tile += nisr) {
+        if (a.resident && tile_begin < tile_end) { mbar_wait(&b_full[0], 0u); tc_fence_after(); }
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int ord = tile - tile_begin;                   // ordinal of the tile in this CTA: every phase follows from it
             const int acc = ord & 1;
             const int buf = ord % a.nbuf;
@@ -317,7 +288,7 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
             const int b = tile / a.tiles_per_b;
             const int row0 = (tile - b * a.tiles_per_b) * TM;
             const int rs = a.np_front + row0 - a.back;
-            const int lead = FUSED ? 0 : (rs & 7);               // rows between the copy start and the tile's first plane row
+            const int lead = rs & 7;               // rows between the copy start and the tile's first plane row
             const long long w0 = dbg_on ? clock64() : 0;
             mbar_wait(&acc_empty[acc], aphase ^ 1);
             const long long w1 = dbg_on ? clock64() : 0;
@@ -338,9 +309,7 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
                     blo = bs_lo + (uint32_t)a.unit_b[unit] * bstep;
                 }
                 const uint32_t alo = ((origin + a.unit_a[unit]) & 0x3FFFu) | (1u << 16);
-                if (!CEXP(8)) {
-                    umma_f16_lo_elect_x4(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
-                }
+                umma_f16_lo_elect_x4(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
                 if (!a.resident) {
                     umma_commit_elect(&b_empty[stage]);
                     if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
@@ -378,126 +347,6 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
                 }
             }
         }
-    } else if (warp >= 12) {
-        // =========================================================================== fused producers (8 warps)
-        // thread = (row group of 32, 16-byte chunk = 8 channels); an item is one chunk of one plane row of one image
-        // (plane, slab).  Loads of NB items go out back to back before any of them is consumed: with only 8 warps the
-        // latency has to be covered by loads in flight per thread, not by occupancy (the stand-alone stage kernel
-        // hides it with 40 warps per SM).
-        const int ptid = tid - 12 * 32;
-        const int c8 = ptid & 7, rg = ptid >> 3;
-        float* coef = reinterpret_cast<float*>(smem + pl.utab_off);      // [addend][s | h | a][ncoef]
-        const int C0 = a.src[0].C;
-        const int nps = a.nplanes * a.nslab;
-        const int nrg = (pl.R + 31) >> 5;                                // row groups per image
-        const int nitems = nps * nrg;
-        int cur_b = -1;
-        int buf = 0;
-        uint32_t bphase = 0;
-        constexpr int NB = 4;
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
-            const int b = tile / a.tiles_per_b;
-            const int row0 = (tile - b * a.tiles_per_b) * TM;
-            if (b != cur_b) {
-                named_bar_sync(1, NEPI);
-                for (int i = ptid; i < a.ncoef; i += NEPI) {
-                    const int sidx = i < C0 ? 0 : 1;
-                    const int c = sidx ? i - C0 : i;
-                    float cs, ch, ca;
-                    xform_coeffs(a.src[sidx].xf, b, a.src[sidx].C, c, cs, ch, ca);
-                    coef[i] = cs; coef[a.ncoef + i] = ch; coef[2 * a.ncoef + i] = a.src[sidx].xf.prelu ? ca : 1.f;
-                    if (a.src[sidx].x2) {
-                        xform_coeffs(a.src[sidx].xf2, b, a.src[sidx].C, c, cs, ch, ca);
-                        coef[3 * a.ncoef + i] = cs; coef[4 * a.ncoef + i] = ch; coef[5 * a.ncoef + i] = a.src[sidx].xf2.prelu ? ca : 1.f;
-                    }
-                }
-                named_bar_sync(1, NEPI);
-                cur_b = b;
-            }
-            mbar_wait(&plane_empty[buf], bphase ^ 1);
-            uint8_t* pbuf = planes + buf * pl.buf_bytes;
-            for (int it0 = 0; it0 < nitems; it0 += NB) {
-                float4 v[NB][2], w[NB][2];
-                int ok[NB];                      // 0 zero row, 1 one addend, 2 two addends
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int it = it0 + j;
-                    ok[j] = 0;
-                    if (it < nitems) {
-                        const int ps = it / nrg, rr = (it - ps * nrg) * 32 + rg;
-                        const int plane = ps / a.nslab, slab = ps - plane * a.nslab;
-                        const int r = row0 - a.back + rr;
-                        if (rr < pl.R && r >= 0 && r < rows_per_b) {
-                            const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
-                            const int col = r - t * a.P;
-                            if (col < a.plane_cols[plane]) {
-                                const bool second = slab * KC >= C0;
-                                const ConvSrc& src = second ? a.src[1] : a.src[0];
-                                const int cbase = (second ? slab * KC - C0 : slab * KC) + c8 * 8;
-                                const size_t eoff = (((size_t)b * a.T + t) * a.Fin + (col * a.col_stride + a.col_off[plane])) * src.C + cbase;
-                                const float4* p = reinterpret_cast<const float4*>(src.x + eoff);
-                                v[j][0] = __ldg(p); v[j][1] = __ldg(p + 1);
-                                ok[j] = 1;
-                                if (src.x2) {
-                                    const float4* p2 = reinterpret_cast<const float4*>(src.x2 + eoff);
-                                    w[j][0] = __ldg(p2); w[j][1] = __ldg(p2 + 1);
-                                    ok[j] = 2;
-                                }
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int it = it0 + j;
-                    if (it >= nitems) break;
-                    const int ps = it / nrg, rr = (it - ps * nrg) * 32 + rg;
-                    if (rr >= pl.R) continue;
-                    const int slab = ps % a.nslab;
-                    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (ok[j]) {
-                        const bool second = slab * KC >= C0;
-                        const ConvSrc& src = second ? a.src[1] : a.src[0];
-                        const float* cb = coef + slab * KC + c8 * 8;
-                        const float xin[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
-                        const int md = (src.xf.affine == 0 && src.xf.prelu == 0) ? 0 : (src.xf.prelu == 1 ? 2 : 1);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float z = xin[e];
-                            if (md == 1) { z = fmaf(z, cb[e], cb[a.ncoef + e]); z = fmaxf(z, 0.f) + cb[2 * a.ncoef + e] * fminf(z, 0.f); }
-                            else if (md == 2) { z = fmaf(fmaxf(z, 0.f) + cb[2 * a.ncoef + e] * fminf(z, 0.f), cb[e], cb[a.ncoef + e]); }
-                            x[e] = z;
-                        }
-                        if (ok[j] == 2) {
-                            const float win[8] = {w[j][0].x, w[j][0].y, w[j][0].z, w[j][0].w, w[j][1].x, w[j][1].y, w[j][1].z, w[j][1].w};
-                            const float* cb2 = cb + 3 * a.ncoef;
-                            const int md2 = (src.xf2.affine == 0 && src.xf2.prelu == 0) ? 0 : (src.xf2.prelu == 1 ? 2 : 1);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                float z = win[e];
-                                if (md2 == 1) { z = fmaf(z, cb2[e], cb2[a.ncoef + e]); z = fmaxf(z, 0.f) + cb2[2 * a.ncoef + e] * fminf(z, 0.f); }
-                                else if (md2 == 2) { z = fmaf(fmaxf(z, 0.f) + cb2[2 * a.ncoef + e] * fminf(z, 0.f), cb2[e], cb2[a.ncoef + e]); }
-                                x[e] += z;
-                            }
-                        }
-                    }
-                    uint4 hi;
-                    hi.x = pack_h2(x[0], x[1]); hi.y = pack_h2(x[2], x[3]); hi.z = pack_h2(x[4], x[5]); hi.w = pack_h2(x[6], x[7]);
-                    uint8_t* drow = pbuf + (size_t)(ps * npb) * pl.plane_bytes + rr * 128 + ((c8 ^ (rr & 7)) << 4);
-                    *reinterpret_cast<uint4*>(drow) = hi;
-                    if (npb == 2) {
-                        uint4 lo;
-                        lo.x = pack_lo_h2(x[0], x[1], hi.x); lo.y = pack_lo_h2(x[2], x[3], hi.y);
-                        lo.z = pack_lo_h2(x[4], x[5], hi.z); lo.w = pack_lo_h2(x[6], x[7], hi.w);
-                        *reinterpret_cast<uint4*>(drow + pl.plane_bytes) = lo;
-                    }
-                }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&plane_full[buf]);
-            if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
-        }
     } else if (warp >= 4) {
         // =========================================================================== epilogue (8 warps per group)
         // Register-only: thread = output row (TMEM lane), warp = (lane quadrant, half of the channels).  Values go
@@ -521,12 +370,10 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
         const long long t_start = dbg_on ? clock64() : 0;
         // Statistics, fast path (one statistic, <= 32 channels per thread): every thread keeps running sums of ITS row's
         // values per channel over all the tiles of a batch item; the cross-row butterfly runs once per batch item.
-        const bool fast_stats = !FUSED && a.nstats == 1 && niter <= 4;
-        float rs_sum[FUSED ? 1 : 32], rs_sq[FUSED ? 1 : 32];
-        if (!FUSED) {
+        const bool fast_stats = a.nstats == 1 && niter <= 4;
+        float rs_sum[32], rs_sq[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { rs_sum[FUSED ? 0 : i] = 0.f; rs_sq[FUSED ? 0 : i] = 0.f; }
-        }
+        for (int i = 0; i < 32; ++i) { rs_sum[i] = 0.f; rs_sq[i] = 0.f; }
         float ssum[2][8], ssq[2][8];            // [statistic][iteration]: totals of column chalf*cper + it*8 + own
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2)
@@ -535,13 +382,13 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
         int cur_b = -1;
         auto flush = [&](int b) {
             if (b < 0 || a.nstats == 0) return;
-            if (!FUSED && fast_stats) {
+            if (fast_stats) {
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     if (it >= niter) continue;
                     float u8[8], w8[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { u8[i] = rs_sum[FUSED ? 0 : it * 8 + i]; w8[i] = rs_sq[FUSED ? 0 : it * 8 + i]; rs_sum[FUSED ? 0 : it * 8 + i] = 0.f; rs_sq[FUSED ? 0 : it * 8 + i] = 0.f; }
+                    for (int i = 0; i < 8; ++i) { u8[i] = rs_sum[it * 8 + i]; w8[i] = rs_sq[it * 8 + i]; rs_sum[it * 8 + i] = 0.f; rs_sq[it * 8 + i] = 0.f; }
                     ssum[0][it] = fold8(u8, lane);
                     ssq[0][it] = fold8(w8, lane);
                 }
@@ -588,13 +435,8 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
                 if (it >= niter) continue;
                 const int c0 = chalf * cper + it * 8;
                 uint32_t rv[8], rg[8];
-                if (!CEXP(4)) {
-                    tmem_ld8_nowait(taddr + c0, rv);
-                    if (gated) tmem_ld8_nowait(taddr + a.gate_off + c0, rg);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { rv[i] = 0x3f800000u + lane; rg[i] = 0x3f000000u; }
-                }
+                tmem_ld8_nowait(taddr + c0, rv);
+                if (gated) tmem_ld8_nowait(taddr + a.gate_off + c0, rg);
                 float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
                 if (a.resid && row_valid) {          // residual rows: issued under the TMEM load
                     q0 = __ldg(reinterpret_cast<const float4*>(a.resid + off + c0));
@@ -639,28 +481,15 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
                             }
                         }
                     }
-                } else if (row_valid && !CEXP(1) && a.out_half) {
-                    uint4 h;
-                    h.x = pack_h2(v[0], v[1]); h.y = pack_h2(v[2], v[3]); h.z = pack_h2(v[4], v[5]); h.w = pack_h2(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.out) + off + c0) = h;
-                } else if (row_valid && !CEXP(1)) {
-                    float4* o4 = reinterpret_cast<float4*>(a.out + off + c0);
-                    if (a.round_half) {              // experiment: what fp16 storage of this raw activation would cost in accuracy
-                        float r[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) r[i] = __half2float(__float2half_rn(v[i]));
-                        o4[0] = make_float4(r[0], r[1], r[2], r[3]);
-                        o4[1] = make_float4(r[4], r[5], r[6], r[7]);
-                    } else {
-                        st_global_256(a.out + off + c0, v);
-                    }
+                } else if (row_valid) {
+                    st_global_256(a.out + off + c0, v);
                 }
-                if (a.nstats && !CEXP(2)) {
+                if (a.nstats) {
                     if (!row_valid) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = 0.f;
                     }
-                    if (!FUSED && fast_stats) {
+                    if (fast_stats) {
                         if (it < 4) {
                             float u[8];
                             if (a.stat_alpha[0]) {
@@ -675,8 +504,8 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
                             }
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                rs_sum[FUSED ? 0 : (it & 3) * 8 + i] += u[i];
-                                rs_sq[FUSED ? 0 : (it & 3) * 8 + i] = fmaf(u[i], u[i], rs_sq[FUSED ? 0 : (it & 3) * 8 + i]);
+                                rs_sum[(it & 3) * 8 + i] += u[i];
+                                rs_sq[(it & 3) * 8 + i] = fmaf(u[i], u[i], rs_sq[(it & 3) * 8 + i]);
                             }
                         }
                     } else {
@@ -720,7 +549,7 @@ __global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS_STAGED, 1) c
 int choose_nbuf(PlaneConvArgs& a) {
     a.nsb = 3;
     a.resident = 1;                                      // 1. resident weights next to 3 or 2 plane buffers
-    for (int nb = kTwoIssuers ? 2 : 3; nb >= 2; --nb) {
+    for (int nb = 3; nb >= 2; --nb) {
         a.nbuf = nb;
         if (make_plan(a).total <= 227 * 1024) return nb;
     }
@@ -740,6 +569,24 @@ int choose_nbuf(PlaneConvArgs& a) {
 }
 
 }  // namespace
+
+// shape rules of the padded-pitch row space (shared by stage_kernel / conv_tma_kernel / conv_raw_kernel)
+bool plane_conv_supported(const PlaneConvArgs& a) {
+    if (a.N % 16 != 0 || a.N < 16 || a.N > 256) return false;
+    if (a.Cout != 16 && a.Cout != 32 && a.Cout != 64 && a.Cout != 128) return false;
+    if (a.gate_off > 0 && (a.gate_off != a.Cout || a.N != 2 * a.Cout)) return false;
+    if (a.gate_off == 0 && a.N != a.Cout) return false;
+    if (a.ntaps < 1 || a.ntaps > kMaxTaps || a.nplanes < 1 || a.nplanes > 2) return false;
+    for (int i = 0; i < a.nsrc; ++i)
+        if (a.src[i].C % KC != 0) return false;
+    for (int i = 0; i < a.nplanes; ++i)
+        if (a.plane_cols[i] > a.P) return false;
+    for (int i = 0; i < a.ntaps; ++i)
+        if (a.back + a.tap_shift[i] < 0 || a.tap_shift[i] > a.fwd) return false;
+    if (a.out_ld % 4 != 0 || a.out_coff % 4 != 0 || a.P < a.E || a.P < 1) return false;
+    if (((long long)a.T * a.P + a.back + 4 * TM + 2ll * a.P) * a.P >= (1ll << 31)) return false;     // magic-division range
+    return true;
+}
 
 int staged_rows(const PlaneConvArgs& a, int* front) {
     const int f = ceil8(a.back);
@@ -769,10 +616,11 @@ int launch_stage(const PlaneConvArgs& a_in, cudaStream_t st) {
     double cin = 0, inb = 0;
     for (int i = 0; i < a.nsrc; ++i) {
         cin += a.src[i].C;
-        inb += (double)a.B * a.T * a.Fin * a.src[i].C * ((a.src[i].half ? 2.0 : 4.0) + (a.src[i].x2 ? (a.src[i].half2 ? 2.0 : 4.0) : 0.0));
+        inb += (double)a.B * a.T * a.Fin * a.src[i].C * 4.0 * (a.src[i].x2 ? 2 : 1);
     }
     const double elems = (double)a.B * a.T * a.Fin * cin;
-    ProfScope ps("stage", 4.0 * elems, inb + (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1), st);
+    // a pure design cost: no algorithmic bytes (SURVEY.md 8d counts the layer's fp32 input once, at the conv launch)
+    ProfScope ps("stage", 4.0 * elems, 0.0, st, inb + (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1));
     EAB_CUDA(launch_k(stage_kernel, grid, dim3(256), (size_t)0, st, a));
     EAB_LAUNCH_CHECK("stage_kernel");
     return 0;
@@ -796,18 +644,9 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
             a.unit_b[u] = (unsigned short)((tap * a.nslab + slab) * npb + (pass == 2 ? 1 : 0));
         }
     }
-    static int configured = 0;
-    if (pl.total > configured) {
-        EAB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));
-        EAB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.total));
-        configured = pl.total;
-    }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        EAB_CUDA(cudaGetDevice(&dev));
-        EAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_tma_kernel), pl.total));
+    int sms = 0;
+    EAB_TRY(device_sm_count(&sms));
     const long long ntiles = (long long)a.B * a.tiles_per_b;
     if (ntiles >= (1ll << 30)) return fail("conv_staged: too many tiles");
     const int grid = (int)(ntiles < sms ? ntiles : sms);
@@ -815,18 +654,21 @@ int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
     double kreal = 0;
     for (int i = 0; i < a.nsrc; ++i) kreal += a.src[i].C;
     if (a.stft_M > 0) kreal = 160;                           // a hop per tap
-    double in_bytes = (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1);
-    if (a.fused) {
-        in_bytes = 0;
-        for (int i = 0; i < a.nsrc; ++i) in_bytes += 4.0 * a.B * a.T * a.Fin * a.src[i].C * (a.src[i].x2 ? 2 : 1);
-    }
-    if (a.out_half && (a.resid || a.stft_M > 0)) return fail("conv_staged: fp16 output with a residual / STFT epilogue");
+    const double in_bytes = (double)a.B * a.np_rows * 128.0 * a.nplanes * a.nslab * (a.npass == 3 ? 2 : 1);
     if (a.stft_M == 0 && ((a.out_ld & 7) || (a.out_coff & 7) || (reinterpret_cast<uintptr_t>(a.out) & 31)))
         return fail("conv_staged: output rows must be 32-byte aligned");
+    // algorithmic: the layer's fp32 input(s) once + its output once; the parity launches of a transposed conv each count a
+    // share (algo_in_share) of the input they both read.  moved: the staged fp16 planes this launch reads + output + weights
+    double in_algo = 0;
+    for (int i = 0; i < a.nsrc; ++i) in_algo += 4.0 * a.B * a.T * a.Fin * a.src[i].C;
+    if (a.stft_M > 0) in_algo = 4.0 * a.B * a.stft_M * 160.0 * a.T;
+    else if (a.wide_k > 0) in_algo = 4.0 * a.B * a.T * a.Fin * a.src[0].C;
+    in_algo *= a.algo_in_share > 0.f ? a.algo_in_share : 1.f;
+    const double out_b = a.stft_M > 0 ? 8.0 * a.B * a.stft_T * a.stft_M * 64.0 * (a.out_coff / 128 == 2 ? 33.0 / 64.0 : 1.0) : 4.0 * pos * a.Cout;
     ProfScope ps(a.stft_M > 0 ? "stft" : "conv_tma", 2.0 * pos * a.ntaps * kreal * a.N * a.algo_frac,
-                 in_bytes + (a.out_half ? 2.0 : 4.0) * pos * a.Cout * (a.resid ? 2 : 1) + 4.0 * a.ntaps * kreal * a.N, st);
-    if (a.fused) EAB_CUDA(launch_k(conv_tma_kernel<true>, dim3(grid), dim3(NTHREADS_FUSED), (size_t)pl.total, st, a));
-    else EAB_CUDA(launch_k(conv_tma_kernel<false>, dim3(grid), dim3(NTHREADS_STAGED), (size_t)pl.total, st, a));
+                 in_algo + out_b + (a.resid ? 4.0 * pos * a.Cout : 0.0), st,
+                 in_bytes + 4.0 * pos * a.Cout * (a.resid ? 2 : 1) + 4.0 * a.ntaps * kreal * a.N);
+    EAB_CUDA(launch_k(conv_tma_kernel, dim3(grid), dim3(NTHREADS_STAGED), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_tma_kernel");
     return 0;
 }

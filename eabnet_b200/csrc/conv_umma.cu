@@ -94,10 +94,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
         fence_barrier_init();
     }
-    pdl_trigger();
     if (warp == NPROD / 32) tmem_alloc(tmem_slot, tmem_cols);
     for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
-    pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

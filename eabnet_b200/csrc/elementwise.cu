@@ -11,8 +11,6 @@ namespace {
 // out[b,p,c] = sum_s xform_s(src_s[b,p,c]);  grid (chunks, B); 128-bit accesses when C % 4 == 0
 __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
     extern __shared__ float coef[];                  // [nsrc][3][C]
-    pdl_trigger();
-    pdl_wait();
     const int b = blockIdx.y;
     const int C = a.C;
     for (int i = threadIdx.x; i < a.nsrc * C; i += blockDim.x) {
@@ -36,15 +34,8 @@ __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
             const int c = (int)((i * 4) % C);
             float o[4] = {0.f, 0.f, 0.f, 0.f};
             for (int s = 0; s < a.nsrc; ++s) {
-                float x[4];
-                if (a.src[s].half) {
-                    const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(a.src[s].x) + sbase[s]) + i);
-                    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-                    x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
-                } else {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(a.src[s].x + sbase[s]) + i);
-                    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-                }
+                const float4 v = __ldg(reinterpret_cast<const float4*>(a.src[s].x + sbase[s]) + i);
+                const float x[4] = {v.x, v.y, v.z, v.w};
                 const int pr = a.src[s].xf.prelu;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -58,8 +49,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
             const int c = (int)(i % C);
             float o = 0.f;
             for (int s = 0; s < a.nsrc; ++s)
-                o += xform_apply(a.src[s].half ? __half2float(__ldg(reinterpret_cast<const __half*>(a.src[s].x) + sbase[s] + i))
-                                               : __ldg(a.src[s].x + sbase[s] + i), coef[(s * 3 + 0) * C + c], coef[(s * 3 + 1) * C + c],
+                o += xform_apply(__ldg(a.src[s].x + sbase[s] + i), coef[(s * 3 + 0) * C + c], coef[(s * 3 + 1) * C + c],
                                  coef[(s * 3 + 2) * C + c], a.src[s].xf.prelu);
             a.out[base + i] = o;
         }
@@ -68,8 +58,6 @@ __global__ void __launch_bounds__(256) combine_kernel(const CombineArgs a) {
 
 // mimo: y[b,:,t,f] = sum_m w[b,t,f,m] * x[b,t,f,m]  (complex);  one thread per (b,t,f)
 __global__ void __launch_bounds__(256) beam_mimo_kernel(const BeamArgs a) {
-    pdl_trigger();
-    pdl_wait();
     const size_t n = (size_t)a.B * a.T * a.F;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -97,8 +85,6 @@ __global__ void __launch_bounds__(256) beam_mimo_kernel(const BeamArgs a) {
 // miso: the reference multiplies by mic 0 and then sums its last axis, which is F (EaBNet.py:123-124),
 // so the result is [B,2,T].  One warp per (b,t).
 __global__ void __launch_bounds__(256) beam_miso_kernel(const BeamArgs a) {
-    pdl_trigger();
-    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.B * a.T) return;

@@ -15,8 +15,6 @@ namespace {
 
 // one thread per (b, t, f)
 __global__ void __launch_bounds__(256) gag_pack_kernel(const GagPackArgs a) {
-    pdl_trigger();
-    pdl_wait();
     const size_t n = (size_t)a.B * a.T * a.KP2;              // KP2 = KP / 2 >= F : threads f >= F write the zero padding
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -46,8 +44,6 @@ __global__ void __launch_bounds__(256) gag_pack_kernel(const GagPackArgs a) {
 
 // one thread per (b, t, f)
 __global__ void __launch_bounds__(256) gag_crm_kernel(const GagCrmArgs a) {
-    pdl_trigger();
-    pdl_wait();
     const size_t n = (size_t)a.B * a.T * a.KP2;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -61,7 +61,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) head_fused_kernel(const HeadArgs 
         }
         fence_barrier_init();
     }
-    pdl_trigger();
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 256);      // D1: cols [0,64) [64,128);  D2: cols [128,160) [160,192)
     {
         const uint4* s1 = reinterpret_cast<const uint4*>(a.W1hi);
@@ -75,7 +74,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) head_fused_kernel(const HeadArgs 
         for (int i = tid; i < 64; i += NTHREADS) sb1[i] = __ldg(a.b1 + i);
         for (int i = tid; i < 32; i += NTHREADS) sb2[i] = __ldg(a.b2 + i);
     }
-    pdl_wait();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();

@@ -32,8 +32,6 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const LstmArgs a) {
     float* lng = coef + 2 * 3 * E;                          // [E]
     float* lnb = lng + E;                                   // [E]
 
-    pdl_trigger();
-    pdl_wait();
     const int tid = threadIdx.x;
     const int j = tid & 63;
     const int sg = tid >> 6;

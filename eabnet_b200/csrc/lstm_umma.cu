@@ -95,13 +95,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         mbar_init(hs_free, NXP);
         fence_barrier_init();
     }
-    pdl_trigger();
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.Wimg);
         uint4* dst = reinterpret_cast<uint4*>(Bs);
         for (int i = tid; i < B_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);     // static weights: before the wait
-        pdl_wait();
         uint4* az = reinterpret_cast<uint4*>(As);
         for (int i = tid; i < A_BYTES / 16; i += NTHREADS) az[i] = make_uint4(0, 0, 0, 0);      // h_{-1} = 0
         for (int i = tid; i < 256; i += NTHREADS)       // image row order: half*128 + quarter*32 + gate*8 + j; gate 2 (g) feeds tanh

@@ -59,11 +59,10 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
     }
     return 0;
 }
-bool g_use_pdl = false;     // measured on B200: 35.2 ms/step with PDL vs 34.0 without (dependents crowd multi-wave kernels)
 void count_launch(int n) { g_launches += n; }
 
 // ------------------------------------------------------------------------------------------------ profiler
-struct ProfRec { const char* cat; double flops, bytes; cudaEvent_t a, b; };
+struct ProfRec { const char* cat; double flops, bytes, moved; cudaEvent_t a, b; };
 struct Profiler {
     bool on = false;
     bool detail = false;
@@ -82,9 +81,9 @@ struct Profiler {
 };
 static thread_local Profiler g_prof;
 
-ProfScope::ProfScope(const char* category, double flops, double bytes, cudaStream_t s) : rec(nullptr), st(s) {
+ProfScope::ProfScope(const char* category, double flops, double bytes, cudaStream_t s, double moved) : rec(nullptr), st(s) {
     if (!g_prof.on) return;
-    ProfRec r{category, flops, bytes, g_prof.get(), g_prof.get()};
+    ProfRec r{category, flops, bytes, moved < 0 ? bytes : moved, g_prof.get(), g_prof.get()};
     cudaEventRecord(r.a, st);
     g_prof.recs.push_back(r);
     rec = reinterpret_cast<void*>(g_prof.recs.size());      // index + 1
@@ -140,15 +139,11 @@ struct ConvLayer {
     int u_ntaps[2] = {0, 0};
     int u_dt[2][kMaxTaps], u_df[2][kMaxTaps];
     size_t off_whi[2] = {0, 0}, off_wlo[2] = {0, 0}, off_ub = 0;
-    // gated 64-channel layers also get channel-split images: split s = value | gate of channels 32 s .. 32 s + 32 (N = 64),
-    // so that a split's weights can stay resident in shared memory where the full N = 128 set cannot
     // first layer, "pair" layout: a plane row holds two adjacent frequency positions (2 x cin values, one 64-wide slab); an
     // output position reads ceil(kf / 2) consecutive rows, so taps = kt x ceil(kf / 2) row shifts (stride-2 conv only)
     bool pair_ok = false;
     int p_ntaps = 0, p_dt[kMaxTaps], p_ds[kMaxTaps];
     size_t off_phi = 0, off_plo = 0;
-    bool has_split = false;
-    size_t off_shi[2][2] = {{0, 0}, {0, 0}}, off_slo[2][2] = {{0, 0}, {0, 0}}, off_sub[2] = {0, 0};
     NormAct na;
 };
 
@@ -206,12 +201,10 @@ struct Act {                 // an activation tensor as seen by a consumer
     float* data2 = nullptr;
     Xform xf2 = xform_identity();
     int RT = 0;              // streaming: frames in this tensor's ring (0 = offline)
-    bool half = false, half2 = false;       // data / data2 hold __half values (raw outputs of single-pass decoder layers)
 };
 
 inline void set_src(ConvSrc& s, const Act& a) {
     s.x = a.data; s.C = a.C; s.xf = a.xf; s.x2 = a.data2; s.xf2 = a.xf2; s.RT = a.RT;
-    s.half = a.half; s.half2 = a.half2;
 }
 
 struct Tap { Act act; int B = 0, T = 0; };
@@ -275,18 +268,10 @@ struct eab_model {
     int opt_raw = 1;              // conv_raw_kernel: raw fp32 tiles normalised in shared memory, no stage pass (preferred)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
-    int opt_half_act = 0;         // raw outputs of the single-pass decoder layers stored as fp16: measured -1 % step time for +30 % output error, so off
-    int opt_round_half = 0;       // diagnostics: fp16-rounded storage of the decoder's inner activations
-    int opt_fused = 0;            // conv_tma with in-kernel producers (no stage pass, no plane images in HBM)
-    int opt_pair = 1;             // first layer: frequency-pair plane rows instead of whole tap-window rows
-    int opt_wide_staged = 1;      // first layer through stage_kernel (tap-window rows) + conv_tma instead of the gather kernel
-    int opt_split = 0;            // gated 1-pass layers whose weights cannot stay resident run as two channel-split launches
-    int opt_conv_exp = 0;         // diagnostics (EAB_CONV_EXPERIMENT builds)
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
     int opt_tcm_chain = 1;        // TCM stacks as persistent cooperative launches (tcm_chain.cu): a GaGNet module's three stacks / an EaBNet group
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
-    int opt_plane = 1;            // "stage once, shift by descriptor" kernel with fused producers (fallback)
     int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
     int umma_launch_idx = 0;
     unsigned long long* dbg_buf = nullptr;
@@ -763,36 +748,6 @@ struct Packer {
                 }
             L.pair_ok = true;
         }
-        if (L.gated && co == 64 && !L.wide) {
-            for (int sp = 0; sp < 2; ++sp) {
-                L.off_sub[sp] = alloc(64);
-                for (int n = 0; n < 64; ++n) blob[L.off_sub[sp] + n] = P(L.b)[n < 32 ? sp * 32 + n : co + sp * 32 + (n - 32)];
-            }
-            for (int v = 0; v < L.nvar; ++v) {
-                const int nt = L.u_ntaps[v];
-                const __half* full_hi = reinterpret_cast<const __half*>(blob.data() + L.off_whi[v]);
-                const __half* full_lo = reinterpret_cast<const __half*>(blob.data() + L.off_wlo[v]);
-                for (int sp = 0; sp < 2; ++sp) {
-                    const size_t img = (size_t)nt * L.u_nslab * 64 * 32;
-                    L.off_shi[v][sp] = alloc(img);
-                    L.off_slo[v][sp] = alloc(img);
-                    // (alloc may have moved the blob: re-derive the source pointers)
-                    full_hi = reinterpret_cast<const __half*>(blob.data() + L.off_whi[v]);
-                    full_lo = reinterpret_cast<const __half*>(blob.data() + L.off_wlo[v]);
-                    __half* shi = reinterpret_cast<__half*>(blob.data() + L.off_shi[v][sp]);
-                    __half* slo = reinterpret_cast<__half*>(blob.data() + L.off_slo[v][sp]);
-                    for (int ts = 0; ts < nt * L.u_nslab; ++ts)
-                        for (int n = 0; n < 64; ++n) {
-                            const int nf = n < 32 ? sp * 32 + n : co + sp * 32 + (n - 32);
-                            for (int k = 0; k < 64; ++k) {
-                                shi[(size_t)ts * 64 * 64 + sw128_index_h(n, k)] = full_hi[(size_t)ts * cout_t * 64 + sw128_index_h(nf, k)];
-                                slo[(size_t)ts * 64 * 64 + sw128_index_h(n, k)] = full_lo[(size_t)ts * cout_t * 64 + sw128_index_h(nf, k)];
-                            }
-                        }
-                }
-            }
-            L.has_split = true;
-        }
     }
 
     void tcm(TcmLayer& t) {
@@ -1101,7 +1056,7 @@ Xform xf_after(Ctx& cx, const NormAct& na, double* stats, int count, int prelu_p
     return x;
 }
 
-// Re-express a per-tap gather launch as a "stage once" launch (conv_plane.cu); false if the shape does not qualify.
+// Re-express a per-tap gather launch in the padded-pitch row space of conv_raw / the staged pair; false if the shape does not qualify.
 bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p, int force_P = 0) {
     if (u.wide) return false;
     memset(p, 0, sizeof(*p));
@@ -1148,18 +1103,16 @@ bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p, int force_P = 0) {
 }
 
 int launch_tensor_conv(eab_model* m, const UmmaConvArgs& u, cudaStream_t st) {
-    PlaneConvArgs p;
-    // single-tap layers gain nothing from staging planes (measured: 22.6 vs 22.2 ms per step): keep the gather kernel
-    if (m->opt_plane && u.ntaps > 1 && to_plane_args(u, &p)) { p.dbg = u.dbg; return launch_conv_plane(p, st); }
-    return launch_conv_umma(u, st);
+    (void)m;
+    return launch_conv_umma(u, st);      // per-tap gather ring: what neither conv_raw nor the staged pair takes (K = 578, `staged` = 0)
 }
 
 // Launch the 1-4 tensor-core variants of one layer (output parities of a transposed conv, column splits of a wide
 // 1x1) that read the same inputs.  Preferred path: stage the normalised fp16 planes ONCE (stage_kernel) and run the
 // TMA-fed GEMM per variant; otherwise the fused-producer kernels.  Also runs in planning mode (allocations only).
 // Can the 1-4 variants of a layer run as one stage launch + conv_tma launches?  Fills their plane arguments.
-bool plan_staged(const eab_model* m, const UmmaConvArgs* us, int n, PlaneConvArgs* p, PlaneConvArgs* ps_out) {
-    if (!m->opt_staged || us[0].wide || n > 4) return false;
+bool plan_planes(const UmmaConvArgs* us, int n, PlaneConvArgs* p, PlaneConvArgs* ps_out) {
+    if (us[0].wide || n > 4) return false;
     bool ok = true;
     int P = 0;
     for (int i = 0; i < n; ++i) { ok = ok && to_plane_args(us[i], &p[i]); if (ok) P = std::max(P, p[i].P); }
@@ -1174,64 +1127,48 @@ bool plan_staged(const eab_model* m, const UmmaConvArgs* us, int n, PlaneConvArg
     if (!ok) return false;
     PlaneConvArgs ps = p[0];
     for (int i = 1; i < n; ++i) { ps.back = std::max(ps.back, p[i].back); ps.fwd = std::max(ps.fwd, p[i].fwd); }
-    ok = staged_conv_supported(ps);
-    for (int i = 0; i < n; ++i) ok = ok && staged_conv_supported(p[i]);
     *ps_out = ps;
-    return ok;
+    return true;
 }
 
-int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n, bool out_half = false) {
+int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
     eab_model* m = cx.m;
-    {
-        PlaneConvArgs p[4];
-        PlaneConvArgs ps;
+    PlaneConvArgs p[4];
+    PlaneConvArgs ps;
+    const bool planes_ok = plan_planes(us, n, p, &ps);
+    if (planes_ok && m->opt_raw && raw_conv_supported(p, n)) {
         {
-            if (plan_staged(m, us, n, p, &ps)) {
-                bool any_half = out_half;
-                for (int i = 0; i < n; ++i)
-                    for (int k = 0; k < us[i].nsrc; ++k) any_half = any_half || us[i].src[k].half || us[i].src[k].half2;
-                if (m->opt_fused && !any_half) {
-                    // fused producers: no plane images in HBM, every launch normalises its own operand on load
-                    if (cx.dry) return 0;
-                    for (int i = 0; i < n; ++i) {
-                        if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) p[i].dbg = m->dbg_buf;
-                        p[i].fused = 1; p[i].exp_flags = m->opt_conv_exp;
-                        EAB_TRY(launch_conv_staged(p[i], cx.st));
-                    }
-                    return 0;
-                }
-                if (m->opt_raw && !out_half && raw_conv_supported(p, n)) {
-                    // one launch per layer: raw tiles -> norm + PReLU -> fp16 operand in shared memory -> GEMM (both parities)
-                    if (cx.dry) return 0;
-                    unsigned long long* dbg = nullptr;
-                    if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) dbg = m->dbg_buf;
-                    return launch_conv_raw(p, n, cx.st, dbg);
-                }
-                int front = 0;
-                const int rows = staged_rows(ps, &front);
-                const int nimg = ps.nplanes * ps.nslab * (ps.npass == 3 ? 2 : 1);
-                ps.np_rows = rows; ps.np_front = front;
-                const size_t scratch = cx.mark();           // the staged planes die with this layer
-                for (int k = 0; k < nimg; ++k) ps.np[k] = cx.alloc_act((size_t)cx.B * rows * 32);     // 128 B per row
-                cx.release(scratch);
-                if (cx.dry) return 0;
-                EAB_TRY(launch_stage(ps, cx.st));
-                for (int i = 0; i < n; ++i) {
-                    if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) p[i].dbg = m->dbg_buf;
-                    p[i].np_rows = rows; p[i].np_front = front; p[i].exp_flags = m->opt_conv_exp;
-                    p[i].round_half = m->opt_round_half && us[i].npass == 1 && us[i].Fout != m->cfg.n_freq;
-                    p[i].out_half = out_half ? 1 : 0;
-                    for (int k = 0; k < nimg; ++k) p[i].np[k] = ps.np[k];
-                    EAB_TRY(launch_conv_staged(p[i], cx.st));
-                }
-                return 0;
-            }
+            // one launch per layer: raw tiles -> norm + PReLU -> fp16 operand in shared memory -> GEMM (both parities)
+            if (cx.dry) return 0;
+            unsigned long long* dbg = nullptr;
+            if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) dbg = m->dbg_buf;
+            return launch_conv_raw(p, n, cx.st, dbg);
         }
     }
-    if (out_half) return fail("internal: fp16 output requested from a kernel that cannot write it");
+    bool staged_ok = planes_ok && m->opt_staged && staged_conv_supported(ps);
+    for (int i = 0; staged_ok && i < n; ++i) staged_ok = staged_conv_supported(p[i]);
+    if (staged_ok) {
+        int front = 0;
+        const int rows = staged_rows(ps, &front);
+        const int nimg = ps.nplanes * ps.nslab * (ps.npass == 3 ? 2 : 1);
+        ps.np_rows = rows; ps.np_front = front;
+        const size_t scratch = cx.mark();           // the staged planes die with this layer
+        for (int k = 0; k < nimg; ++k) ps.np[k] = cx.alloc_act((size_t)cx.B * rows * 32);     // 128 B per row
+        cx.release(scratch);
+        if (cx.dry) return 0;
+        EAB_TRY(launch_stage(ps, cx.st));
+        for (int i = 0; i < n; ++i) {
+            if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) p[i].dbg = m->dbg_buf;
+            p[i].np_rows = rows; p[i].np_front = front;
+            for (int k = 0; k < nimg; ++k) p[i].np[k] = ps.np[k];
+            p[i].algo_in_share = 1.f / (float)n;
+            EAB_TRY(launch_conv_staged(p[i], cx.st));
+        }
+        return 0;
+    }
     for (int i = 0; i < n; ++i)
         for (int k = 0; k < us[i].nsrc; ++k)
-            if (us[i].src[k].x2 || us[i].src[k].half) return fail("internal: lazy residual sum / fp16 activation reached a kernel that cannot read it");
+            if (us[i].src[k].x2) return fail("internal: lazy residual sum reached a kernel that cannot read it");
     if (cx.dry) return 0;
     for (int i = 0; i < n; ++i) EAB_TRY(launch_tensor_conv(m, us[i], cx.st));
     return 0;
@@ -1243,12 +1180,11 @@ inline int zone_passes(const eab_model* m, int zone) {
 
 // one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
 int materialize(Ctx& cx, Act* a);
-int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* out, float* prealloc = nullptr,
-               bool allow_half = false) {
+int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* out, float* prealloc = nullptr) {
     Act srcs[2];
     for (int i = 0; i < nsrc; ++i) srcs[i] = srcs_in[i];
     if (!(cx.tensor_ok() && L.umma_ok && cx.m->opt_staged && !L.wide))
-        for (int i = 0; i < nsrc; ++i) EAB_TRY(materialize(cx, &srcs[i]));       // only the staged path reads lazy sums / fp16
+        for (int i = 0; i < nsrc; ++i) EAB_TRY(materialize(cx, &srcs[i]));       // only conv_raw / the staged pair read lazy sums
     const int Fin = srcs[0].F;
     int cin = 0;
     for (int i = 0; i < nsrc; ++i) {
@@ -1261,30 +1197,23 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
     out->F = Fout;
     out->C = L.cout;
     out->data2 = nullptr;
-    out->half = out->half2 = false;
     const size_t out_elems = (size_t)cx.B * cx.T * Fout * L.cout;
     const bool in_stats = L.na.has_norm && cx.m->cfg.norm_type == 0;
     double* stats = in_stats ? cx.alloc_stats(L.cout) : nullptr;
     out->xf = xf_after(cx, L.na, stats, cx.T * Fout, 2);
-    // 2-byte storage of the raw output: single-pass decoder layers on the staged path only (every consumer of such a
-    // tensor is a stage kernel, which rounds the normalised value to fp16 anyway)
-    bool want_half = allow_half && cx.m->opt_half_act && cx.tensor_ok() && cx.m->opt_staged && L.umma_ok && !L.wide &&
-                     L.zone == 1 && zone_passes(cx.m, L.zone) == 1;
     auto allocate_out = [&]() {
-        out->data = prealloc ? prealloc : cx.alloc_act(want_half ? (out_elems + 1) / 2 : out_elems);
+        out->data = prealloc ? prealloc : cx.alloc_act(out_elems);
         out->RT = prealloc ? 0 : cx.last_RT;
-        out->half = want_half;
     };
-    if (cx.tensor_ok() && L.umma_ok && L.wide && cx.m->opt_staged && cx.m->opt_wide_staged && nsrc == 1 && !L.deconv &&
+    if (cx.tensor_ok() && L.umma_ok && L.wide && cx.m->opt_staged && nsrc == 1 && !L.deconv &&
         srcs[0].xf.affine == 0 && srcs[0].xf.prelu == 0 && !srcs[0].data2 && (srcs[0].C * 2) % 2 == 0) {
-        // first layer (2M input channels) on the staged path: a plane row is the whole kf x C tap window
-        want_half = false;
+        // first layer (2M input channels) on the staged path: a plane row is a frequency PAIR (or the whole kf x C tap window)
         allocate_out();
         PlaneConvArgs p;
         memset(&p, 0, sizeof(p));
         p.nsrc = 1;
         set_src(p.src[0], srcs[0]);
-        const bool pair = L.pair_ok && cx.m->opt_pair;
+        const bool pair = L.pair_ok;
         p.B = cx.B; p.T = cx.T; p.Fin = Fin; p.E = Fout;
         p.nplanes = 1; p.col_stride = 2; p.col_off[0] = 0;
         int back = 0, fwd = 0;
@@ -1342,10 +1271,7 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
         int nus = 0;
         for (int v = 0; v < L.nvar; ++v) {
             const int npass = zone_passes(cx.m, L.zone);
-            // weights of the variant as one resident set: taps x slabs x (hi[, lo]) x N rows x 128 B
-            const size_t wbytes = (size_t)L.u_ntaps[v] * L.u_nslab * (npass == 3 ? 2 : 1) * L.u_N * 128;
-            const bool split = L.has_split && cx.m->opt_split && npass == 1 && wbytes > 112 * 1024;
-            for (int sp = 0; sp < (split ? 2 : 1); ++sp) {
+            {
                 UmmaConvArgs& u = us[nus++];
                 memset(&u, 0, sizeof(u));
                 u.nsrc = nsrc;
@@ -1359,30 +1285,19 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
                 u.npass = npass;
                 u.algo_frac = 1.f;
                 u.out = out->data; u.out_ld = L.cout;
-                if (split) {
-                    u.Whi = cx.W(L.off_shi[v][sp]); u.Wlo = cx.W(L.off_slo[v][sp]); u.bias = cx.W(L.off_sub[sp]);
-                    u.Cout = 32; u.N = 64; u.gate_off = 32; u.out_coff = sp * 32;
-                    u.stats_ld = L.cout; u.stats_coff = sp * 32;
-                } else {
-                    u.Whi = cx.W(L.off_whi[v]); u.Wlo = cx.W(L.off_wlo[v]); u.bias = cx.W(L.off_ub);
-                    u.Cout = L.cout; u.N = L.u_N; u.gate_off = L.u_gate_off; u.out_coff = 0;
-                }
+                u.Whi = cx.W(L.off_whi[v]); u.Wlo = cx.W(L.off_wlo[v]); u.bias = cx.W(L.off_ub);
+                u.Cout = L.cout; u.N = L.u_N; u.gate_off = L.u_gate_off; u.out_coff = 0;
                 if (stats) { u.nstats = 1; u.stats[0] = stats; }
                 u.tiles_per_b = (cx.T * u.E + 127) / 128;
                 all_ok = all_ok && umma_conv_supported(u);
             }
         }
         if (all_ok) {
-            if (want_half) {                                 // only if the staged path is really going to take this layer
-                PlaneConvArgs pp[4], pps;
-                want_half = plan_staged(cx.m, us, nus, pp, &pps);
-            }
             allocate_out();
             for (int i = 0; i < nus; ++i) us[i].out = out->data;
-            return run_tensor_convs(cx, us, nus, want_half);
+            return run_tensor_convs(cx, us, nus);
         }
     }
-    want_half = false;
     allocate_out();
     for (int i = 0; i < nsrc; ++i) EAB_TRY(materialize(cx, &srcs[i]));
     if (cx.dry) return 0;
@@ -1428,8 +1343,8 @@ int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
     for (int i = 0; i < nsrc; ++i) {
         if (srcs[i].F != out->F || srcs[i].C != out->C) return fail("internal: combine shape mismatch");
         if (n + (srcs[i].data2 ? 2 : 1) > 3) return fail("internal: too many addends in combine");
-        a.src[n].x = srcs[i].data; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf; a.src[n].RT = srcs[i].RT; a.src[n].half = srcs[i].half; ++n;
-        if (srcs[i].data2) { a.src[n].x = srcs[i].data2; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf2; a.src[n].RT = srcs[i].RT; a.src[n].half = srcs[i].half2; ++n; }
+        a.src[n].x = srcs[i].data; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf; a.src[n].RT = srcs[i].RT; ++n;
+        if (srcs[i].data2) { a.src[n].x = srcs[i].data2; a.src[n].C = srcs[i].C; a.src[n].xf = srcs[i].xf2; a.src[n].RT = srcs[i].RT; ++n; }
     }
     a.nsrc = n;
     a.B = cx.B; a.P = cx.T * out->F; a.C = out->C; a.out = out->data;
@@ -1439,7 +1354,7 @@ int run_combine_into(Ctx& cx, const Act* srcs, int nsrc, Act* out) {
 
 // materialise a lazy residual sum (only needed in front of kernels that cannot read one)
 int materialize(Ctx& cx, Act* a) {
-    if (!a->data2 && !a->half) return 0;
+    if (!a->data2) return 0;
     Act src = *a;
     Act dst;
     EAB_TRY(run_combine(cx, &src, 1, &dst));
@@ -1468,12 +1383,12 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
     else { out->data = cx.alloc_act(nel); out->RT = cx.last_RT; }
     const size_t scope = cx.mark();
     Act x0;
-    EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0, buf_x0, true));
+    EAB_TRY(run_conv2d(cx, U.in_conv, srcs, nsrc, &x0, buf_x0));
     Act y = x0;
     std::vector<Act> keep;
     for (size_t i = 0; i < U.enco.size(); ++i) {
         Act z;
-        EAB_TRY(run_conv2d(cx, U.enco[i], &y, 1, &z, nullptr, true));
+        EAB_TRY(run_conv2d(cx, U.enco[i], &y, 1, &z, nullptr));
         keep.push_back(z);
         y = z;
     }
@@ -1481,22 +1396,22 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
         Act z;
         float* pre = (lazy && i + 1 == U.deco.size()) ? buf_y : nullptr;
         if (i == 0) {
-            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z, pre, true));
+            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z, pre));
         } else {
             Act pair[2] = {y, keep[keep.size() - 1 - i]};
             if (cx.m->cfg.intra_connect == 0) {
-                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z, pre, true));
+                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z, pre));
             } else {
                 Act sum;
                 EAB_TRY(run_combine(cx, pair, 2, &sum));
-                EAB_TRY(run_conv2d(cx, U.deco[i], &sum, 1, &z, pre, true));
+                EAB_TRY(run_conv2d(cx, U.deco[i], &sum, 1, &z, pre));
             }
         }
         y = z;
     }
     if (lazy) {
-        out->data = x0.data; out->xf = x0.xf; out->half = x0.half;
-        out->data2 = y.data; out->xf2 = y.xf; out->half2 = y.half;
+        out->data = x0.data; out->xf = x0.xf;
+        out->data2 = y.data; out->xf2 = y.xf;
     } else {
         Act pair[2] = {x0, y};
         EAB_TRY(run_combine_into(cx, pair, 2, out));
@@ -1546,7 +1461,7 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
     }
     if (cx.dry) return 0;
     for (int i = 0; i < nsrc; ++i)
-        if (srcs[i].half || srcs[i].data2) return fail("internal: fp16 / lazy activation reached the CUDA-core pointwise kernel");
+        if (srcs[i].data2) return fail("internal: lazy activation reached the CUDA-core pointwise kernel");
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.nsrc = nsrc;
@@ -1895,7 +1810,7 @@ int run_tcm_chains(Ctx& cx, const ChainRef* chains, int nch, const Act* ins, Act
     TcmChainArgs a;
     memset(&a, 0, sizeof(a));
     for (int i = 0; i < nch; ++i) {
-        if (ins[i].xf.affine != 0 || ins[i].xf.prelu != 0 || ins[i].data2 || ins[i].half || ins[i].C != 256)
+        if (ins[i].xf.affine != 0 || ins[i].xf.prelu != 0 || ins[i].data2 || ins[i].C != 256)
             return fail("internal: TCM chain input must be a plain fp32 [B,T,256] tensor");
         outs[i].F = 1; outs[i].C = c.d_feat; outs[i].xf = xform_identity();
         outs[i].data = cx.alloc_act(rows * 256);
@@ -2330,7 +2245,7 @@ int eab_enhance_postnet(eab_model* eab, eab_model* gag, int ref_mic, const float
     // (the q estimates are written back to back, B*2*T*F floats each; only the last one is read here)
     const size_t rest = ws_bytes - (size_t)(p - static_cast<char*>(ws));
     reset_launch_count();
-    int rc = launch_stft(wave, spec, B, M, L, st);
+    int rc = launch_stft(wave, spec, B, M, L, st, p, rest);      // the forward workspace is idle until the STFT has finished
     if (!rc) rc = forward(eab, spec, est0, B, T, p, rest, st);
     const long long strides[4] = {(long long)T * F * M * 2, 1, (long long)F * M * 2, (long long)M * 2};
     if (!rc) rc = gag_forward(gag, spec + (size_t)ref_mic * 2, strides, est0, stages, B, T, p, rest, st);
@@ -2587,8 +2502,8 @@ int64_t eab_debug_tap(eab_model* m, const char* name, float* dst, int64_t capaci
     CombineArgs a;
     memset(&a, 0, sizeof(a));
     a.nsrc = 1;
-    a.src[0].x = t.act.data; a.src[0].C = t.act.C; a.src[0].xf = t.act.xf; a.src[0].half = t.act.half;
-    if (t.act.data2) { a.nsrc = 2; a.src[1].x = t.act.data2; a.src[1].C = t.act.C; a.src[1].xf = t.act.xf2; a.src[1].half = t.act.half2; }
+    a.src[0].x = t.act.data; a.src[0].C = t.act.C; a.src[0].xf = t.act.xf;
+    if (t.act.data2) { a.nsrc = 2; a.src[1].x = t.act.data2; a.src[1].C = t.act.C; a.src[1].xf = t.act.xf2; }
     a.B = t.B; a.P = t.T * t.act.F; a.C = t.act.C; a.out = dst;
     if (launch_combine(a, static_cast<cudaStream_t>(stream))) return -1;
     return n;
@@ -2598,8 +2513,6 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     if (!m || !name) return fail("eab_set_option: null argument");
     const std::string n(name);
     if (n == "umma") m->opt_umma = value != 0;
-    else if (n == "plane") m->opt_plane = value != 0;
-    else if (n == "pdl") g_use_pdl = value != 0;
     else if (n == "staged") m->opt_staged = value != 0;
     else if (n == "raw") m->opt_raw = value != 0;
     else if (n == "lazy") m->opt_lazy = value != 0;
@@ -2608,13 +2521,6 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "dual_stream") m->opt_dual_stream = value != 0;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
-    else if (n == "conv_exp") m->opt_conv_exp = value;
-    else if (n == "split") m->opt_split = value != 0;
-    else if (n == "wide_staged") m->opt_wide_staged = value != 0;
-    else if (n == "pair") m->opt_pair = value != 0;
-    else if (n == "fused") m->opt_fused = value != 0;
-    else if (n == "round_half") m->opt_round_half = value != 0;
-    else if (n == "half_act") m->opt_half_act = value != 0;
     else if (n == "stft_tc") g_stft_tc = value != 0;
     else if (n == "fused_head") m->opt_fused_head = value != 0;
     else if (n == "head_w_tap") m->opt_head_w_tap = value != 0;
@@ -2650,7 +2556,7 @@ int64_t eab_profile_summary(eab_model* m, char* buf, int64_t cap) {
     (void)m;
     if (!buf || cap < 2) { fail("eab_profile_summary: bad buffer"); return -1; }
     if (check_cuda(cudaDeviceSynchronize(), "profile sync")) return -1;
-    struct Agg { int n = 0; double ms = 0, flops = 0, bytes = 0; };
+    struct Agg { int n = 0; double ms = 0, flops = 0, bytes = 0, moved = 0; };
     std::map<std::string, Agg> agg;
     int seq = 0;
     for (auto& r : g_prof.recs) {
@@ -2659,14 +2565,14 @@ int64_t eab_profile_summary(eab_model* m, char* buf, int64_t cap) {
         char key[64];
         if (g_prof.detail) snprintf(key, sizeof(key), "%04d:%s", seq++, r.cat); else snprintf(key, sizeof(key), "%s", r.cat);
         Agg& a = agg[key];
-        a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+        a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes; a.moved += r.moved;
     }
     std::string js = "[";
     bool first = true;
     for (auto& kv : agg) {
         char tmp[256];
-        snprintf(tmp, sizeof(tmp), "%s{\"kernel\":\"%s\",\"launches\":%d,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}",
-                 first ? "" : ",", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+        snprintf(tmp, sizeof(tmp), "%s{\"kernel\":\"%s\",\"launches\":%d,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e,\"moved_bytes\":%.6e}",
+                 first ? "" : ",", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes, kv.second.moved);
         js += tmp;
         first = false;
     }

@@ -149,8 +149,6 @@ __global__ void __launch_bounds__(THREADS) stft_kernel(const float* __restrict__
                                                        const float* __restrict__ tab, const float* __restrict__ win,
                                                        int B, int M, int L, int T) {
     extern __shared__ __align__(16) float dsm[];
-    pdl_trigger();
-    pdl_wait();
     float* Aev = dsm;                                   // [NF][RB]
     float* Aod = Aev + NF * RB;                         // [NF][RB]
     float2* Xs = reinterpret_cast<float2*>(Aod + NF * RB);   // [RB][NF]
@@ -223,8 +221,6 @@ __global__ void __launch_bounds__(THREADS) istft_kernel(const float* __restrict_
                                                         const float* __restrict__ tab, const float* __restrict__ win,
                                                         const float* __restrict__ ienv, int B, int T) {
     extern __shared__ __align__(16) float dsm[];
-    pdl_trigger();
-    pdl_wait();
     float* Are = dsm;                    // [NF][RB]
     float* Aim = Are + NF * RB;          // [NF][RB]
     float* PQ = Aim + NF * RB;           // [frame][col]: P[n] (col<161), Q[n] (col>=161)
@@ -281,8 +277,6 @@ __global__ void __launch_bounds__(THREADS) stft_frame_kernel(const float* __rest
     float* Aev = dsm;
     float* Aod = Aev + NF * RB;
     float2* Xs = reinterpret_cast<float2*>(Aod + NF * RB);
-    pdl_trigger();
-    pdl_wait();
     const int step = *step_p;
     const int s0 = blockIdx.x * SG;
     const int nrows = SG * M;
@@ -357,8 +351,6 @@ __global__ void __launch_bounds__(THREADS) istft_frame_kernel(const float* __res
     float* Are = dsm;
     float* Aim = Are + NF * RB;
     float* PQ = Aim + NF * RB;
-    pdl_trigger();
-    pdl_wait();
     const int step = *step_p;
     const int s0 = blockIdx.x * RB;
     for (int i = threadIdx.x; i < RB * NF; i += THREADS) {
@@ -393,8 +385,6 @@ __global__ void __launch_bounds__(THREADS) istft_frame_kernel(const float* __res
 }
 
 __global__ void step_advance_kernel(int* step) {
-    pdl_trigger();
-    pdl_wait();
     if (threadIdx.x == 0) *step += 1;
 }
 
@@ -407,8 +397,6 @@ __global__ void step_advance_kernel(int* step) {
 // (np[slab*2 + hl] : [B*M][np_rows][64] halves, 128B-swizzled by row & 7; row = np_front + hop index, hops 0..T).
 __global__ void __launch_bounds__(256) stft_stage_kernel(const float* __restrict__ wave, uint8_t* __restrict__ planes,
                                                          size_t image_bytes, int np_rows, int np_front, int L, int T, int M) {
-    pdl_trigger();
-    pdl_wait();
     const int b = blockIdx.z, slab = blockIdx.y;
     const int c8 = threadIdx.x & 7;
     for (int it = 0; it < 8; ++it) {
@@ -470,21 +458,21 @@ int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int 
     const size_t need = image_bytes * DFT_SLABS * 2;
     // hop planes: the caller's scratch when it is large enough (eab_enhance lends the forward workspace, which is idle until
     // the STFT has finished - concurrent calls on different streams then share nothing), else the library's grow-only buffer
+    // hop planes: the caller's scratch when it is large enough (eab_enhance / eab_enhance_postnet lend the forward workspace,
+    // which is idle until the STFT has finished), else a stream-ordered allocation private to this call (legal during stream
+    // capture, nothing shared between streams or models, nothing a captured graph could see freed under it)
     uint8_t* planes = nullptr;
+    bool own = false;
     if (scratch && scratch_bytes >= need) planes = static_cast<uint8_t*>(scratch);
     if (!planes) {
-        std::lock_guard<std::mutex> lk(g_tab_mu);
-        if (t->planes_bytes < need) {
-            if (t->planes) { EAB_CUDA(cudaStreamSynchronize(st)); EAB_CUDA(cudaFree(t->planes)); }
-            t->planes = nullptr; t->planes_bytes = 0;
-            EAB_CUDA(cudaMalloc(&t->planes, need));
-            t->planes_bytes = need;
-        }
-        planes = static_cast<uint8_t*>(t->planes);
+        void* q = nullptr;
+        EAB_CUDA(cudaMallocAsync(&q, need, st));
+        planes = static_cast<uint8_t*>(q);
+        own = true;
     }
     for (int i = 0; i < DFT_SLABS * 2; ++i) a.np[i] = planes + (size_t)i * image_bytes;
     {
-        ProfScope ps("stage", 0.0, 4.0 * (double)B * M * L + (double)need, st);
+        ProfScope ps("stft_stage", 0.0, 0.0, st, 4.0 * (double)B * M * L + (double)need);
         dim3 grid((a.np_rows + 255) / 256, DFT_SLABS, a.B);
         EAB_CUDA(launch_k(stft_stage_kernel, grid, dim3(256), (size_t)0, st, wave, planes, image_bytes,
                           a.np_rows, a.np_front, L, T, M));
@@ -495,8 +483,9 @@ int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int 
         ag.Whi = reinterpret_cast<const float*>(static_cast<const __half*>(t->dft_hi) + g * DFT_GROUP_HALVES);
         ag.Wlo = reinterpret_cast<const float*>(static_cast<const __half*>(t->dft_lo) + g * DFT_GROUP_HALVES);
         ag.out_coff = g * 128;
-        EAB_TRY(launch_conv_staged(ag, st));
+        if (launch_conv_staged(ag, st)) { if (own) cudaFreeAsync(planes, st); return 1; }
     }
+    if (own) EAB_CUDA(cudaFreeAsync(planes, st));
     return 0;
 }
 

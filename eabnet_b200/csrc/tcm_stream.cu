@@ -34,8 +34,6 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
     __shared__ float red[NT * SPC];            // partial sums of the current phase: [K group][stream][output]
     __shared__ float u[2][8][SPC][CD];         // [branch][tap][stream][channel] normalised dilated-conv inputs
     __shared__ float uo[SPC][CD];
-    pdl_trigger();
-    pdl_wait();
     const int tid = threadIdx.x;
     const int step = *a.step;
     const int s0 = blockIdx.x * SPC;

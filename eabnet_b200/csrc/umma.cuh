@@ -56,6 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0, spins = 0;
+    unsigned long long t0 = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -65,7 +66,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (++spins > (1u << 28)) __trap();
+        if (++spins > (1u << 28) || wait_expired(spins, t0)) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

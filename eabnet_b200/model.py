@@ -430,6 +430,14 @@ class EaBNetStream:
             if self._graph is None:
                 self._hop_in, self._hop_out = torch.empty_like(hop), torch.empty_like(out)
                 self.net._sync_params(self.dev)
+                # one eager step first: first-use work of the library (constant tables, shared-memory attributes) is not
+                # capturable; the carried state it advanced is put back before the capture
+                snapshot = self.state.clone()
+                self._hop_in.zero_()
+                self._launch(self._hop_in, self._hop_out)
+                self.state.copy_(snapshot)
+                del snapshot
+                torch.cuda.current_stream(self.dev).synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._launch(self._hop_in, self._hop_out)

@@ -58,7 +58,7 @@ def stft_compress(wave: Tensor) -> Tensor:
     kept, written the way the reference does it (norm ** 0.5, atan2, cos/sin) so that the rounding matches.
     """
     B, M, L = wave.shape
-    win = torch.hann_window(N_FFT, dtype=wave.dtype)
+    win = torch.hann_window(N_FFT, dtype=wave.dtype, device=wave.device)
     z = torch.stft(wave.reshape(B * M, L), N_FFT, HOP, N_FFT, win, return_complex=True)   # [BM, F, T]
     z = torch.view_as_real(z)                                                            # [BM, F, T, 2]
     Fq, T = z.shape[1], z.shape[2]
@@ -71,7 +71,7 @@ def stft_compress(wave: Tensor) -> Tensor:
 def istft(spec: Tensor) -> Tensor:
     """spec [B, 2, T, F] -> wave [B, 160 (T-1)]  (enhance.py:59-61); no de-compression, as the reference."""
     z = torch.view_as_complex(spec.permute(0, 3, 2, 1).contiguous())                      # [B, F, T]
-    win = torch.hann_window(N_FFT, dtype=spec.dtype)
+    win = torch.hann_window(N_FFT, dtype=spec.dtype, device=spec.device)
     return torch.istft(z, N_FFT, HOP, N_FFT, win)
 
 
@@ -221,7 +221,7 @@ def lstm_layer(x: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor
     the reference makes (EaBNet.py:610-611), so the CPU baseline is not handicapped by a Python time loop.
     tests/test_oracle_golden.py checks it against the step-by-step restatement below."""
     H = w_hh.shape[1]
-    rnn = torch.nn.LSTM(input_size=w_ih.shape[1], hidden_size=H, batch_first=True).to(x.dtype)
+    rnn = torch.nn.LSTM(input_size=w_ih.shape[1], hidden_size=H, batch_first=True).to(device=x.device, dtype=x.dtype)
     with torch.no_grad():
         rnn.weight_ih_l0.copy_(w_ih)
         rnn.weight_hh_l0.copy_(w_hh)

@@ -123,10 +123,11 @@ def test_forward_fp32_grade_modes(opts):
     assert (out - ref).abs().max() <= EXACT * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("opts", [{"fused": 1}, {"split": 1}, {"wide_staged": 0}, {"stft_tc": 0}, {"staged": 0}, {"lazy": 0}, {"half_act": 1}, {"tcm_chain": 0}, {"pair": 0}])
+@pytest.mark.parametrize("opts", [{"raw": 0}, {"stft_tc": 0}, {"staged": 0}, {"raw": 0, "staged": 0}, {"lazy": 0}, {"raw": 0, "lazy": 0},
+                                  {"tcm_chain": 0}])
 def test_alternate_kernel_paths_agree(opts):
-    """the optional kernel paths (in-kernel producers, channel-split gated layers, gather first layer, CUDA-core STFT,
-    fused-producer plane kernel, materialised residual sums) give the default path's result: wave -> wave, T = 101"""
+    """the optional kernel paths (stage + conv_tma pair instead of conv_raw, CUDA-core STFT, per-tap gather kernel,
+    materialised residual sums, layer-by-layer TCMs) give the default path's result: wave -> wave, T = 101"""
     cfg = O.make_cfg()
     net, sd = _net(cfg, seed=12)
     wave, _ = O.make_wave(2, 9, 16000, seed=33)

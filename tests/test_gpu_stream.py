@@ -81,3 +81,26 @@ def test_stream_rejects_instance_norm_and_noncausal():
         net = EaBNet(**kw).eval().cuda()
         with pytest.raises(RuntimeError):
             net.stream(2)
+
+
+def test_stream_graph_capture_as_first_cuda_work_of_a_process():
+    """graph=True must not depend on an earlier eager call having initialised the library's tables (fresh process)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch\n"
+            "from eabnet_b200 import EaBNet\n"
+            "from eabnet_b200.model import EaBNetStream\n"
+            "torch.manual_seed(0)\n"
+            "net = EaBNet(norm_type='BN').eval().cuda()\n"
+            "ses = EaBNetStream(net, 3, graph=True)\n"
+            "hop = 0.1 * torch.randn(3, 9, 160, device='cuda')\n"
+            "a = ses.step(hop).clone(); b = ses.step(hop).clone()\n"
+            "ref = EaBNetStream(net, 3, graph=False)\n"
+            "c = ref.step(hop).clone(); d = ref.step(hop).clone()\n"
+            "torch.cuda.synchronize()\n"
+            "assert torch.isfinite(b).all() and torch.equal(a, c) and torch.equal(b, d)\n"
+            "print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -2,6 +2,10 @@
 
     python tools/summarize_ncu.py launches gpurun_out/launches_v0.csv profiles/r01_v0_launches.txt
     python tools/summarize_ncu.py full gpurun_out/prof_conv_v0.ncu-rep profiles/r01_v0_conv_generic_full.txt
+    python tools/summarize_ncu.py traffic gpurun_out/traffic.csv profiles/r02_traffic.json
+        (traffic.csv: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv
+         over ONE step of tools/prof_step.py --steps 1: DRAM bytes of every launch, summed per kernel family)
+    python tools/summarize_ncu.py sass eabnet_b200/libeabnet_b200.so profiles/r02_sass_opcodes.txt
 """
 import collections
 import csv
@@ -57,5 +61,76 @@ def full(src, dst):
     print(open(dst).read())
 
 
+FAMILY = [("conv_raw_kernel", "conv2d"), ("conv_tma_kernel", "conv2d"), ("stage_kernel", "conv2d"), ("conv_umma_kernel", "conv2d"),
+          ("conv_generic_kernel", "conv2d"), ("combine_kernel", "conv2d"), ("tcm_chain_kernel", "tcm"), ("lstm_umma_kernel", "head"),
+          ("lstm_kernel", "head"), ("head_fused_kernel", "head"), ("beam_", "head"), ("istft_kernel", "istft"), ("stft_stage_kernel", "stft"),
+          ("stft_kernel", "stft")]
+
+
+def traffic(src, dst):
+    """per-family DRAM bytes of one step from a per-launch ncu CSV (see the module docstring)"""
+    import json
+    lines = [l for l in open(src) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        d = per.setdefault(row["ID"], {"name": row["Kernel Name"]})
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"]
+        if row["Metric Name"].startswith("dram__bytes"):
+            v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        else:
+            v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1.0)
+        d[row["Metric Name"]] = v
+    fam = collections.OrderedDict()
+    stft_left = 0
+    for d in per.values():
+        name = d["name"]
+        if "eab::" not in name:
+            continue
+        f = next((fm for key, fm in FAMILY if key in name), "other")
+        if "stft_stage_kernel" in name:
+            stft_left = 3                       # the three DFT-GEMM launches of the STFT follow its stage kernel
+        elif "conv_tma_kernel" in name and stft_left > 0:
+            f, stft_left = "stft", stft_left - 1
+        a = fam.setdefault(f, {"dram_bytes_per_step": 0.0, "read": 0.0, "write": 0.0, "ms_under_ncu": 0.0, "launches": 0})
+        a["read"] += d.get("dram__bytes_read.sum", 0.0)
+        a["write"] += d.get("dram__bytes_write.sum", 0.0)
+        a["dram_bytes_per_step"] = a["read"] + a["write"]
+        a["ms_under_ncu"] += d.get("gpu__time_duration.sum", 0.0)
+        a["launches"] += 1
+    out = {"_source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none over one "
+                      "64 x 6 s step (%s); per-family sums over every launch of the step" % src}
+    for f, a in fam.items():
+        a["note"] = "%d launches, %.3f GB read + %.3f GB written, %.3f ms under ncu (cold-cache, serialised)" % (
+            a["launches"], a["read"] / 1e9, a["write"] / 1e9, a["ms_under_ncu"])
+        out[f] = a
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+def sass(src, dst):
+    """tensor-core / TMA opcode counts per kernel of the built library (cuobjdump -sass)"""
+    txt = subprocess.run(["cuobjdump", "-sass", src], capture_output=True, text=True).stdout
+    ops = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "USETMAXREG", "SYNCS", "FFMA", "MUFU", "STL", "LDL"]
+    cur, counts = None, collections.OrderedDict()
+    for line in txt.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            counts[cur] = collections.Counter()
+        elif cur:
+            for o in ops:
+                if (" " + o) in line or ("\t" + o) in line:
+                    counts[cur][o] += 1
+    with open(dst, "w") as f:
+        f.write("# cuobjdump -sass %s : opcode counts per kernel (UTCHMMA = tcgen05.mma kind::f16, LDTM = tcgen05.ld, UBLKCP = cp.async.bulk,\n" % src)
+        f.write("# UTMALDG/UTMASTG = tensor-map TMA, USETMAXREG = setmaxnreg, SYNCS = mbarrier ops, STL/LDL = local-memory spills)\n")
+        f.write("%-90s %s\n" % ("kernel", " ".join("%10s" % o for o in ops)))
+        for k, c in counts.items():
+            short = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip() or k
+            short = short.replace("eab::(anonymous namespace)::", "").split("(")[0]
+            f.write("%-90s %s\n" % (short[:90], " ".join("%10d" % c[o] for o in ops)))
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic, "sass": sass}[sys.argv[1]](sys.argv[2], sys.argv[3])
