@@ -62,12 +62,13 @@ struct Xform {
     float inv_count;       // 1 / (#elements per (b,c)) for affine==1
     int affine;            // 0 none, 1 instance statistics, 2 precomputed
     int prelu;             // 0 none, 1 before the affine, 2 after it
+    int alpha01;           // all slopes in [0, 1] (checked on the host at commit): PReLU(z) == max(z, alpha z), bit for bit
 };
 
 static inline Xform xform_identity() {
     Xform x;
     x.stats = nullptr; x.scale = nullptr; x.shift = nullptr; x.alpha = nullptr;
-    x.inv_count = 0.f; x.affine = 0; x.prelu = 0;
+    x.inv_count = 0.f; x.affine = 0; x.prelu = 0; x.alpha01 = 0;
     return x;
 }
 
@@ -288,7 +289,7 @@ struct RawConvArgs {
     const float* x0[kRawMaxSlabs];       // first addend of the slab's source
     const float* x1[kRawMaxSlabs];       // second addend (lazy residual sum of a module) or null
     Xform xf0[kRawMaxSlabs], xf1[kRawMaxSlabs];
-    int mode0[kRawMaxSlabs], mode1[kRawMaxSlabs];    // 0 none, 1 norm -> PReLU, 2 PReLU -> norm
+    int mode0[kRawMaxSlabs], mode1[kRawMaxSlabs];    // 0 none, 1 norm -> PReLU, 2 PReLU -> norm, 3 norm -> PReLU with slopes in [0, 1]
     // ring stage = the raw rows one group of G operand rows needs from ONE slab: addend 0 at byte 0, addend 1 at add1_off
     int G, stage_bytes, add1_off;
     int B, T, Fin, P;

@@ -83,44 +83,82 @@ __device__ __forceinline__ void group_range(const RawConvArgs& a, int R, int row
 
 __device__ __forceinline__ float4 lds128(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
 
-// norm + PReLU of four channels; mode 0 none, 1 norm -> PReLU (2-D blocks), 2 PReLU -> norm (TCM order).  The expressions
-// are the ones stage_kernel uses, so both paths round identically.
-__device__ __forceinline__ void xf4(float4& v, const float4& s, const float4& h, const float4& al, int mode) {
-    if (mode == 1) {
-        float z;
-        z = fmaf(v.x, s.x, h.x); v.x = fmaxf(z, 0.f) + al.x * fminf(z, 0.f);
-        z = fmaf(v.y, s.y, h.y); v.y = fmaxf(z, 0.f) + al.y * fminf(z, 0.f);
-        z = fmaf(v.z, s.z, h.z); v.z = fmaxf(z, 0.f) + al.z * fminf(z, 0.f);
-        z = fmaf(v.w, s.w, h.w); v.w = fmaxf(z, 0.f) + al.w * fminf(z, 0.f);
-    } else if (mode == 2) {
-        v.x = fmaf(fmaxf(v.x, 0.f) + al.x * fminf(v.x, 0.f), s.x, h.x);
-        v.y = fmaf(fmaxf(v.y, 0.f) + al.y * fminf(v.y, 0.f), s.y, h.y);
-        v.z = fmaf(fmaxf(v.z, 0.f) + al.z * fminf(v.z, 0.f), s.z, h.z);
-        v.w = fmaf(fmaxf(v.w, 0.f) + al.w * fminf(v.w, 0.f), s.w, h.w);
+// two fp32 operations per instruction (sm_100: FFMA2 / FMUL2 / FADD2); each lane rounds exactly like the scalar form
+__device__ __forceinline__ void ffma2(float& dx, float& dy, float ax, float ay, float bx, float by, float cx, float cy) {
+    uint64_t ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(bx), "f"(by));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(cx), "f"(cy));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(dx), "=f"(dy) : "l"(rd));
+}
+__device__ __forceinline__ void fmul2(float& dx, float& dy, float ax, float ay, float bx, float by) {
+    uint64_t ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(bx), "f"(by));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(dx), "=f"(dy) : "l"(rd));
+}
+__device__ __forceinline__ void fsub2(float& dx, float& dy, float ax, float ay, float bx, float by) {
+    uint64_t ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(bx), "f"(by));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(dx), "=f"(dy) : "l"(rd));
+}
+
+// norm + PReLU of four channels (2-D blocks: conv -> norm -> PReLU, EaBNet.py:402-405).  FAST: every slope of the launch
+// lies in [0, 1], where max(z, 0) + a min(z, 0) == max(z, a z) bit for bit (z > 0: a z <= z; z < 0: a z >= z; the sum's other
+// term is an exact zero).  Each channel goes through the operations stage_kernel applies, in the same order and rounding
+// (fma, then the PReLU), two channels per instruction where the ISA has a packed form.  A source without norm / PReLU runs
+// with the identity coefficients (1, 0, 1), which reproduce x exactly.  The variant is a template parameter: as a run-time
+// switch the compiler re-dispatched on it around every quad (branches instead of four independent chains).
+template <bool FAST>
+__device__ __forceinline__ void xf4(float4& v, const float4& s, const float4& h, const float4& al) {
+    float z0, z1, z2, z3;
+    ffma2(z0, z1, v.x, v.y, s.x, s.y, h.x, h.y);
+    ffma2(z2, z3, v.z, v.w, s.z, s.w, h.z, h.w);
+    if (FAST) {
+        float a0, a1, a2, a3;
+        fmul2(a0, a1, z0, z1, al.x, al.y);
+        fmul2(a2, a3, z2, z3, al.z, al.w);
+        v.x = fmaxf(z0, a0); v.y = fmaxf(z1, a1); v.z = fmaxf(z2, a2); v.w = fmaxf(z3, a3);
+    } else {
+        ffma2(v.x, v.y, al.x, al.y, fminf(z0, 0.f), fminf(z1, 0.f), fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+        ffma2(v.z, v.w, al.z, al.w, fminf(z2, 0.f), fminf(z3, 0.f), fmaxf(z2, 0.f), fmaxf(z3, 0.f));
     }
 }
 
+// fp16 hi pair of two floats and the fp16-rounded residual (3-pass split), residual subtraction as one packed instruction
+__device__ __forceinline__ uint32_t pack_lo2(float a, float b, uint32_t hi) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    float dx, dy;
+    fsub2(dx, dy, a, b, f.x, f.y);
+    return pack_h2(dx, dy);
+}
+
 // One batch of NI operand chunks (8 channels each) of ONE slab for one thread: every raw load is issued before any
-// arithmetic, the NI chains are independent (a lone chain runs at ALU latency: measured 2.1 k cycles per 32-row group with
-// one chunk per thread at a time).  soff = byte offset of the item's raw row in the stage (0 for pad items, whose result is
-// replaced by zeros), dst = its 16-byte slot in the hi image (lo image plane_bytes further).  cf = [addend][s | h | alpha][64].
-template <int NI, bool DUAL>
+// arithmetic and the NI chains are independent.  soff = byte offset of the item's raw row in the stage (a valid address for
+// pad items too, whose result is replaced by zeros), dst = its 16-byte slot in the hi image (lo image plane_bytes further).
+// The thread's two 4-channel quads are stored as two 8-byte halves (the quad it loaded first is the chunk's half qa).
+// cf = [addend][s | h | alpha][64].  `act` = the lanes of the warp that call this together (for the all-valid vote).
+template <int NI, bool DUAL, bool LO, bool FAST>
 __device__ __forceinline__ void xf_items(const uint8_t* st0, const uint8_t* st1, const int (&soff)[NI], const bool (&ok)[NI],
-                                         uint8_t* const (&dst)[NI], const float* cf, int mode0, int mode1, int qa, int chA,
-                                         int chB, bool with_lo, int plane_bytes) {
+                                         uint8_t* const (&dst)[NI], const float* cf, int qa, int chA, int chB, int plane_bytes,
+                                         unsigned act) {
     float4 vA[NI], vB[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
         vA[i] = lds128(st0 + soff[i] + qa * 16);
         vB[i] = lds128(st0 + soff[i] + (qa ^ 1) * 16);
     }
-    if (mode0 != 0) {
+    {
         const float4 sA = *reinterpret_cast<const float4*>(cf + chA), hA = *reinterpret_cast<const float4*>(cf + 64 + chA),
                      aA = *reinterpret_cast<const float4*>(cf + 128 + chA);
         const float4 sB = *reinterpret_cast<const float4*>(cf + chB), hB = *reinterpret_cast<const float4*>(cf + 64 + chB),
                      aB = *reinterpret_cast<const float4*>(cf + 128 + chB);
 #pragma unroll
-        for (int i = 0; i < NI; ++i) { xf4(vA[i], sA, hA, aA, mode0); xf4(vB[i], sB, hB, aB, mode0); }
+        for (int i = 0; i < NI; ++i) { xf4<FAST>(vA[i], sA, hA, aA); xf4<FAST>(vB[i], sB, hB, aB); }
     }
     if (DUAL) {                                  // + the second addend of a module's lazy residual sum (EaBNet.py:386)
         float4 wA[NI], wB[NI];
@@ -129,14 +167,14 @@ __device__ __forceinline__ void xf_items(const uint8_t* st0, const uint8_t* st1,
             wA[i] = lds128(st1 + soff[i] + qa * 16);
             wB[i] = lds128(st1 + soff[i] + (qa ^ 1) * 16);
         }
-        if (mode1 != 0) {
+        {
             const float* c1 = cf + 192;
             const float4 sA = *reinterpret_cast<const float4*>(c1 + chA), hA = *reinterpret_cast<const float4*>(c1 + 64 + chA),
                          aA = *reinterpret_cast<const float4*>(c1 + 128 + chA);
             const float4 sB = *reinterpret_cast<const float4*>(c1 + chB), hB = *reinterpret_cast<const float4*>(c1 + 64 + chB),
                          aB = *reinterpret_cast<const float4*>(c1 + 128 + chB);
 #pragma unroll
-            for (int i = 0; i < NI; ++i) { xf4(wA[i], sA, hA, aA, mode1); xf4(wB[i], sB, hB, aB, mode1); }
+            for (int i = 0; i < NI; ++i) { xf4<FAST>(wA[i], sA, hA, aA); xf4<FAST>(wB[i], sB, hB, aB); }
         }
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
@@ -144,16 +182,25 @@ __device__ __forceinline__ void xf_items(const uint8_t* st0, const uint8_t* st1,
             vB[i].x += wB[i].x; vB[i].y += wB[i].y; vB[i].z += wB[i].z; vB[i].w += wB[i].w;
         }
     }
+    bool all_ok = true;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) all_ok = all_ok && ok[i];
+    if (!__all_sync(act, all_ok)) {              // rare (pad rows / columns): literal zeros
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+            if (!ok[i]) { vA[i] = make_float4(0.f, 0.f, 0.f, 0.f); vB[i] = vA[i]; }
+    }
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-        if (!ok[i]) { vA[i] = make_float4(0.f, 0.f, 0.f, 0.f); vB[i] = vA[i]; }     // literal zeros: pad rows / columns
         const uint32_t hA0 = pack_h2(vA[i].x, vA[i].y), hA1 = pack_h2(vA[i].z, vA[i].w);
         const uint32_t hB0 = pack_h2(vB[i].x, vB[i].y), hB1 = pack_h2(vB[i].z, vB[i].w);
-        *reinterpret_cast<uint4*>(dst[i]) = qa ? make_uint4(hB0, hB1, hA0, hA1) : make_uint4(hA0, hA1, hB0, hB1);
-        if (with_lo) {
-            const uint32_t lA0 = pack_lo_h2(vA[i].x, vA[i].y, hA0), lA1 = pack_lo_h2(vA[i].z, vA[i].w, hA1);
-            const uint32_t lB0 = pack_lo_h2(vB[i].x, vB[i].y, hB0), lB1 = pack_lo_h2(vB[i].z, vB[i].w, hB1);
-            *reinterpret_cast<uint4*>(dst[i] + plane_bytes) = qa ? make_uint4(lB0, lB1, lA0, lA1) : make_uint4(lA0, lA1, lB0, lB1);
+        *reinterpret_cast<uint2*>(dst[i] + qa * 8) = make_uint2(hA0, hA1);
+        *reinterpret_cast<uint2*>(dst[i] + (qa ^ 1) * 8) = make_uint2(hB0, hB1);
+        if (LO) {
+            const uint32_t lA0 = pack_lo2(vA[i].x, vA[i].y, hA0), lA1 = pack_lo2(vA[i].z, vA[i].w, hA1);
+            const uint32_t lB0 = pack_lo2(vB[i].x, vB[i].y, hB0), lB1 = pack_lo2(vB[i].z, vB[i].w, hB1);
+            *reinterpret_cast<uint2*>(dst[i] + plane_bytes + qa * 8) = make_uint2(lA0, lA1);
+            *reinterpret_cast<uint2*>(dst[i] + plane_bytes + (qa ^ 1) * 8) = make_uint2(lB0, lB1);
         }
     }
 }
@@ -175,14 +222,11 @@ __device__ __forceinline__ float fold8(const float (&u)[8], int lane) {
 }
 
 // setmaxnreg moves registers inside the CTA's OWN allocation (640 threads x 96 at launch = 61 440): the increases must be
-// covered by the decreases of the same CTA (128 x 48 + 256 x 128 + 256 x 88 = 61 440), or the increase spins forever.
-// mbarrier waits of this kernel: the polling form (try_wait without a suspend-time hint).  The hinted form compiles to
-// TRYWAIT + NANOSLEEP.SYNCS, whose wake-up latency is paid on every ring stage here (a handshake per 32 operand rows).
-#ifdef EAB_RAW_SUSPEND
-#define RWAIT mbar_wait
-#else
-#define RWAIT mbar_wait_spin
-#endif
+// covered by the decreases of the same CTA (128 x 48 + 256 x 120 + 256 x 96 = 61 440), or the increase spins forever.
+// mbarrier waits of this kernel: polling (try_wait without a suspend-time hint; the hinted form compiles to TRYWAIT +
+// NANOSLEEP.SYNCS with a wake-up latency paid on every handshake), with a 128 ns back-off for the roles that have slack.
+#define RWAIT mbar_wait_spin                         // critical path: the MMA issuer, the transform warps' data waits
+#define RWAIT_IDLE(bar, par) mbar_wait_backoff(bar, par, 128u)      // roles with slack: epilogue, loaders, operand-buffer reuse
 #ifdef EAB_RAW_DEBUG
 constexpr bool kDbg = true;
 #else
@@ -193,7 +237,8 @@ template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("se
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 // NTW transform warps (8: 640 threads, the register file is re-partitioned between the roles with setmaxnreg)
-template <int NTW>
+// LO: 3-pass layers (fp16 hi + lo operand images); FAST: every PReLU slope of the inputs in [0, 1] (xf4)
+template <int NTW, bool LO, bool FAST>
 __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(const RawConvArgs a) {
     constexpr int NTHREADS = NCTRL + NEPI + NTW * 32;
     constexpr int NTT = NTW * 32;                            // transform threads
@@ -262,7 +307,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                     const size_t goff = ((size_t)b * a.T * a.Fin + g_lo) * 64;
                     for (int s = 0; s < a.nslab; ++s) {
                         const long long w0 = dbg_on ? clock64() : 0;
-                        RWAIT(&raw_empty[stage], sphase ^ 1);
+                        RWAIT_IDLE(&raw_empty[stage], sphase ^ 1);
                         if (dbg_on) t_w += clock64() - w0;
                         if (lane == 0) {
                             if (n > 0) {
@@ -349,7 +394,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                     for (int v = 0; v < a.nvar; ++v)
                         for (int ts = 0; ts < a.ntaps[v] * a.nslab; ++ts)
                             for (int pass = 0; pass < a.npass; ++pass) {
-                                RWAIT(&b_empty[stage], sphase ^ 1);
+                                RWAIT_IDLE(&b_empty[stage], sphase ^ 1);
                                 if (lane == 0) {
                                     const float* img = (pass == 2 ? a.Wlo[v] : a.Whi[v]) + (size_t)ts * a.N * 32;
                                     mbar_arrive_expect_tx(&b_full[stage], bytes);
@@ -363,7 +408,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
     } else if (warp < 12) {
         // =========================================================================== epilogue (8 warps)
         // thread = output row (TMEM lane), warp = (lane quadrant, half of the 64 output channels); see conv_tma_kernel
-        if (NTW == 8) reg_inc<128>();
+        if (NTW == 8) reg_inc<120>();
         const int quad = warp & 3;
         const int chalf = ((warp - 4) >> 2) & 1;
         const int row = quad * 32 + lane;
@@ -410,7 +455,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                 const bool row_valid = e < a.E[v];
                 const long long off = (fbase + (e * a.out_stride + a.out_off[v])) * 64;
                 const long long w0 = dbg_on ? clock64() : 0;
-                RWAIT(&acc_full[acc * 2 + v], aphase);
+                RWAIT_IDLE(&acc_full[acc * 2 + v], aphase);
                 if (dbg_on) t_wf += clock64() - w0;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * acc_cols + v * a.N);
@@ -457,7 +502,6 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
         // (group, slab) and gives the thread NI = (G / 32) x nplanes chunks, transformed as one batch (xf_items).  The two
         // 16-byte halves of a chunk's 32 raw bytes are read in an order that depends on c8 (c8 >= 4: upper half first) so that
         // the eight lanes of a quarter-warp touch all 32 banks in both loads.
-        if (NTW == 8) reg_dec<88>();
         const int ttid = tid - TR0;
         const int c8 = ttid & 7;
         const int rr = ttid >> 3;                            // 0..31
@@ -492,7 +536,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                 if (dbg_on) t_cf += clock64() - w0;
             }
             const long long w1 = dbg_on ? clock64() : 0;
-            RWAIT(&opnd_empty[buf], bphase ^ 1);
+            RWAIT_IDLE(&opnd_empty[buf], bphase ^ 1);
             if (dbg_on) t_wo += clock64() - w1;
             uint8_t* obuf = opnd + (size_t)buf * pl.buf_bytes;
             for (int j = 0; j < pl.ngroups; ++j) {
@@ -532,6 +576,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                     const float* cf = coef + s * 2 * 192;
                     const int sadd = s * npb * pl.plane_bytes;
                     const bool dual = a.x1[s] != nullptr;
+                    const unsigned act = __ballot_sync(0xffffffffu, any);
                     if (any) {
                         if (ni == 4) {
                             // a pad-only tail slot (doff < 0) writes nothing: send it to the thread's first slot, with its value
@@ -543,7 +588,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                                 dst[i] = obuf + sadd + (use ? doff[i] : doff[0]); so[i] = use ? soff[i] : soff[0]; k[i] = use ? ok[i] : ok[0];
                             }
                             // (four chunks per thread only in launches without lazy pairs: the launcher halves G for those)
-                            xf_items<4, false>(st0, st1, so, k, dst, cf, a.mode0[s], a.mode1[s], qa, chA, chB, npb == 2, pl.plane_bytes);
+                            xf_items<4, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
                         } else {
                             uint8_t* dst[2];
                             int so[2]; bool k[2];
@@ -552,8 +597,8 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                                 const bool use = i < ni && doff[i] >= 0;
                                 dst[i] = obuf + sadd + (use ? doff[i] : doff[0]); so[i] = use ? soff[i] : soff[0]; k[i] = use ? ok[i] : ok[0];
                             }
-                            if (dual) xf_items<2, true>(st0, st1, so, k, dst, cf, a.mode0[s], a.mode1[s], qa, chA, chB, npb == 2, pl.plane_bytes);
-                            else xf_items<2, false>(st0, st1, so, k, dst, cf, a.mode0[s], a.mode1[s], qa, chA, chB, npb == 2, pl.plane_bytes);
+                            if (dual) xf_items<2, true, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
+                            else xf_items<2, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
                         }
                     }
                     __syncwarp();
@@ -573,7 +618,8 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// shared-memory plan: resident weights before a weight ring, two operand buffers if the raw ring still gets >= 3 stages
+// shared-memory plan: resident weights before a weight ring, two operand buffers (the transform of tile i+1 runs under the
+// MMAs of tile i) whenever two ring stages still fit
 bool choose_plan(RawConvArgs& a) {
     for (int resident = 1; resident >= 0; --resident) {
         for (int nbuf = 2; nbuf >= 1; --nbuf) {
@@ -581,7 +627,7 @@ bool choose_plan(RawConvArgs& a) {
             const int fixed = make_raw_plan(a).total;
             if (fixed >= SMEM_LIMIT) continue;
             const int ns = std::min(NSTAGE_MAX, (SMEM_LIMIT - fixed) / a.stage_bytes);
-            if (ns < (nbuf == 2 ? 3 : 2)) continue;
+            if (ns < 2) continue;
             a.nstage = ns;
             if (!resident)                                   // leftover shared memory deepens the weight ring
                 for (int nsb = NSB_MAX; nsb > 3; --nsb) {
@@ -617,11 +663,12 @@ bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
         if ((reinterpret_cast<uintptr_t>(s.x) & 15) || (s.x2 && (reinterpret_cast<uintptr_t>(s.x2) & 15))) return false;
         if (nslab >= kRawMaxSlabs) return false;
         a.x0[nslab] = s.x; a.xf0[nslab] = s.xf;
-        a.mode0[nslab] = (s.xf.affine == 0 && s.xf.prelu == 0) ? 0 : (s.xf.prelu == 1 ? 2 : 1);
+        if (s.xf.prelu == 1 || (s.x2 && s.xf2.prelu == 1)) return false;      // PReLU -> norm (TCM order): the staged pair
+        a.mode0[nslab] = (s.xf.prelu == 0 || s.xf.alpha01) ? 3 : 1;
         a.x1[nslab] = s.x2;
         if (s.x2) {
             a.xf1[nslab] = s.xf2;
-            a.mode1[nslab] = (s.xf2.affine == 0 && s.xf2.prelu == 0) ? 0 : (s.xf2.prelu == 1 ? 2 : 1);
+            a.mode1[nslab] = (s.xf2.prelu == 0 || s.xf2.alpha01) ? 3 : 1;
             any_dual = true;
         } else {
             a.xf1[nslab] = xform_identity();
@@ -715,7 +762,12 @@ int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned lon
     a.dbg = dbg;
     const RawPlan pl = make_raw_plan(a);
     constexpr int NTW = 8;
-    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_raw_kernel<NTW>), pl.total));
+    bool fast = true;
+    for (int s = 0; s < a.nslab; ++s) fast = fast && a.mode0[s] == 3 && (!a.x1[s] || a.mode1[s] == 3);
+    const bool lo = a.npass == 3;
+    void (*kern)(RawConvArgs) = lo ? (fast ? conv_raw_kernel<NTW, true, true> : conv_raw_kernel<NTW, true, false>)
+                                   : (fast ? conv_raw_kernel<NTW, false, true> : conv_raw_kernel<NTW, false, false>);
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), pl.total));
     int sms = 0;
     EAB_TRY(device_sm_count(&sms));
     const long long ntiles = (long long)a.B * a.tiles_per_b;
@@ -733,7 +785,7 @@ int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned lon
     double wbytes = 0;
     for (int v = 0; v < a.nvar; ++v) wbytes += 2.0 * (a.npass == 3 ? 2 : 1) * a.ntaps[v] * kreal * a.N;
     ProfScope ps("conv_raw", 2.0 * kn * kreal * a.N * a.algo_frac, in_algo + 4.0 * pos * a.Cout, st, in_moved + 4.0 * pos * a.Cout + wbytes);
-    EAB_CUDA(launch_k(conv_raw_kernel<NTW>, dim3(grid), dim3(NCTRL + NEPI + NTW * 32), (size_t)pl.total, st, a));
+    EAB_CUDA(launch_k(kern, dim3(grid), dim3(NCTRL + NEPI + NTW * 32), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_raw_kernel");
     return 0;
 }

@@ -118,6 +118,7 @@ struct NormAct {
     int C = 0;
     int gamma = -1, beta = -1, mean = -1, var = -1, alpha = -1;   // param indices
     size_t off_scale = 0, off_shift = 0, off_alpha = 0;           // floats into the device blob
+    bool alpha01 = false;                                         // every PReLU slope lies in [0, 1]: PReLU(z) == max(z, a z)
 };
 
 struct ConvLayer {
@@ -595,7 +596,12 @@ struct Packer {
             }
         }
         na.off_alpha = alloc(C);
-        for (int c = 0; c < C; ++c) blob[na.off_alpha + c] = P(na.alpha)[c];
+        na.alpha01 = true;
+        for (int c = 0; c < C; ++c) {
+            const float al = P(na.alpha)[c];
+            blob[na.off_alpha + c] = al;
+            if (!(al >= 0.f && al <= 1.f)) na.alpha01 = false;
+        }
     }
 
     void conv(ConvLayer& L) {
@@ -1052,6 +1058,7 @@ Xform xf_after(Ctx& cx, const NormAct& na, double* stats, int count, int prelu_p
         x.shift = cx.W(na.off_shift);
     }
     x.alpha = cx.W(na.off_alpha);
+    x.alpha01 = na.alpha01 ? 1 : 0;
     x.prelu = prelu_pos;
     return x;
 }
