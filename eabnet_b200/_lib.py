@@ -50,6 +50,7 @@ SYMBOLS = {
     "eab_enhance_postnet_workspace_bytes": (C.c_size_t, [_P, _P, C.c_int, C.c_int]),
     "eab_enhance_postnet": (C.c_int, [_P, _P, C.c_int, _F, _F, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "eab_enhance_host_pcm16": (C.c_int, [_P, _P, C.c_int, _P, C.POINTER(C.c_int), _P, C.c_int, C.c_int, _P]),
+    "eab_enhance_host_batches_pcm16": (C.c_int, [_P, C.POINTER(_F), C.POINTER(C.c_int), C.POINTER(_F), C.c_int, C.c_int, C.c_int, _P]),
     "eab_last_launch_count": (C.c_int, [_P]),
     "eab_debug_tap": (C.c_int64, [_P, C.c_char_p, _F, C.c_int64, _P]),
     "eab_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

@@ -315,7 +315,8 @@ struct RawConvArgs {
     unsigned long long* dbg;
 };
 bool raw_conv_supported(const PlaneConvArgs* p, int n);
-int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned long long* dbg);
+// max_grid > 0 caps the number of CTAs (tests: every CTA then walks many tiles even on small inputs)
+int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned long long* dbg, int max_grid = 0);
 
 struct CombineArgs {
     ConvSrc src[3];
@@ -453,19 +454,13 @@ struct GagCrmArgs {
 };
 int launch_gag_crm(const GagCrmArgs& a, cudaStream_t st);
 
-// 16-bit PCM wire format (elementwise.cu)
-struct PcmArgs {
-    const short* pcm;            // [B][M][L] int16, microphones in file order
-    float* wave;                 // [B][M][L] fp32 = pcm / 32768, microphone m taken from file channel order[m]
-    int B, M, L;
-    int order[64];
-};
-int launch_pcm16_to_float(const PcmArgs& a, cudaStream_t st);
-int launch_float_to_pcm16(const float* x, short* out, size_t n, cudaStream_t st);
-
 // scratch: optional device buffer for the tensor-core path's hop planes (else a library-owned grow-only buffer, one per device)
 int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_t st, void* scratch = nullptr, size_t scratch_bytes = 0);
-int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st);
+// 16-bit PCM source (file channel order, microphone m = file channel order[m], null = identity) for the same spectrum
+int launch_stft_pcm16(const short* pcm, const int* order, float* spec, int B, int M, int L, cudaStream_t st, void* scratch = nullptr,
+                      size_t scratch_bytes = 0);
+// wave16 != null: write int16(clip(y, -1, 1) * 32767) there instead of fp32 samples to `wave`
+int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st, short* wave16 = nullptr);
 // streaming front/back end (stft.cu): one hop in -> spectrum frame *step into a ring; spectrum frame -> one hop out
 // (delayed by one hop: overlap-add needs the next frame), carried state in prev_hop [S][M][160] / tail [S][160]
 int launch_stft_frame(const float* hop, float* prev_hop, float* spec_ring, int spec_RT, const int* step, int S, int M,

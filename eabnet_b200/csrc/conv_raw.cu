@@ -38,6 +38,7 @@ constexpr int NSB_MAX = 8;
 constexpr int NCTRL = 128;                       // warps 0-3: loader, MMA issuer, weight loader, spare
 constexpr int NEPI = 256;                        // warps 4-11
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int kTail = 8;                         // operand rows the last group of a tile may hold beyond G (R = 129 -> 2 groups, not 3)
 
 struct RawPlan {
     int R, plane_bytes, buf_bytes, b_stage_bytes, w_images, ngroups;
@@ -53,12 +54,12 @@ __host__ __device__ inline RawPlan make_raw_plan(const RawConvArgs& a) {
     p.b_stage_bytes = a.N * 128;
     p.w_images = 0;
     for (int v = 0; v < a.nvar; ++v) p.w_images += a.ntaps[v] * a.nslab * npb;
-    p.ngroups = (p.R + a.G - 1) / a.G;
+    p.ngroups = p.R <= a.G + kTail ? 1 : (p.R - kTail + a.G - 1) / a.G;      // the last group also takes a tail of <= kTail rows
     p.b_off = a.nbuf * p.buf_bytes;
     p.ring_off = p.b_off + (a.resident ? p.w_images : a.nsb) * p.b_stage_bytes;
     p.bias_off = p.ring_off + a.nstage * a.stage_bytes;
     p.coef_off = p.bias_off + a.N * 4;
-    p.bar_off = (p.coef_off + a.nslab * 2 * 3 * 64 * 4 + 15) & ~15;          // coefficients [slab][addend][s | h | alpha][64]
+    p.bar_off = (p.coef_off + a.nslab * 2 * 192 * 4 + 15) & ~15;              // coefficients [slab][addend][s | h | alpha][64]
     p.total = p.bar_off + 512 + 1024;                    // barriers + slack for the 1024-byte alignment of the base
     return p;
 }
@@ -66,9 +67,9 @@ __host__ __device__ inline RawPlan make_raw_plan(const RawConvArgs& a) {
 // raw rows (units of one 64-channel row of a source tensor, relative to the batch item) that operand rows [G j, G j + G) of the
 // tile at padded row `row0` read: [g_lo, g_lo + n).  Operand row rho <-> padded row r = row0 - back + rho = t P + col;
 // plane p holds input column col * col_stride + col_off[p] (zeros where that is >= Fin or r is outside [0, T P)).
-__device__ __forceinline__ void group_range(const RawConvArgs& a, int R, int rows_per_b, int row0, int j, int& g_lo, int& n) {
+__device__ __forceinline__ void group_range(const RawConvArgs& a, int R, int ngroups, int rows_per_b, int row0, int j, int& g_lo, int& n) {
     int r_a = row0 - a.back + j * a.G;
-    int r_b = min(r_a + a.G - 1, row0 - a.back + R - 1);
+    int r_b = j == ngroups - 1 ? row0 - a.back + R - 1 : r_a + a.G - 1;        // the last group runs to the end of the tile's rows
     r_a = max(r_a, 0);
     r_b = min(r_b, rows_per_b - 1);
     g_lo = 0; n = 0;
@@ -241,7 +242,6 @@ template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("se
 template <int NTW, bool LO, bool FAST>
 __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(const RawConvArgs a) {
     constexpr int NTHREADS = NCTRL + NEPI + NTW * 32;
-    constexpr int NTT = NTW * 32;                            // transform threads
     constexpr int TR0 = NCTRL + NEPI;                        // first transform thread
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
     uint8_t* Bs = smem + pl.b_off;
     uint8_t* ring = smem + pl.ring_off;
     float* sbias = reinterpret_cast<float*>(smem + pl.bias_off);
-    float* coef = reinterpret_cast<float*>(smem + pl.coef_off);
+    float* coef = reinterpret_cast<float*>(smem + pl.coef_off);            // [slab][addend][s | h | alpha][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bar_off);
     uint64_t* raw_full = bars;              // [NSTAGE_MAX]
     uint64_t* raw_empty = bars + 8;         // [NSTAGE_MAX]
@@ -289,6 +289,151 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
     const int tile_end = (int)(ntiles * (blockIdx.x + 1) / gridDim.x);
     const int rows_per_b = a.T * a.P;
 
+    // ----------------------------------------------------------------------------------------------- transform of one tile
+    // thread = (row rr of each 32-row block of the group, 16-byte fp16 chunk c8 = 8 channels); a ring stage (group, slab) gives
+    // the thread NI = (G / 32) x nplanes chunks, transformed as one batch (xf_items).  The two 16-byte halves of a chunk's 32
+    // raw bytes are read in an order that depends on c8 (c8 >= 4: upper half first) so that the eight lanes of a quarter-warp
+    // touch all 32 banks in both loads.
+    // (Tried: the epilogue warps - idle most of the time on the non-gated layers - transforming every second or third stage
+    // of a tile.  Bit-exact, but SLOWER, 14.6 ms of conv_raw per step against 9.9: their 64 statistics registers go to local
+    // memory around the transform code and their epilogue, which frees the accumulator the next MMA waits for, runs late.)
+    struct XfState { int stage; uint32_t sphase; int cur_b; long long t_wo, t_wr, t_cf; };
+    auto xf_tile = [&](const int tile, const int ttid, XfState& xs, const bool dbg_on) {
+        const int c8 = ttid & 7;
+        const int rr = ttid >> 3;                            // 0..31
+        const int qa = (c8 >> 2) & 1;                        // which half this thread loads first
+        const int chA = c8 * 8 + qa * 4, chB = c8 * 8 + (qa ^ 1) * 4;
+        const int rpt = a.G >> 5;                            // rows per thread per group: 1, 2 or 4
+        int& stage = xs.stage;
+        uint32_t& sphase = xs.sphase;
+        int& cur_b = xs.cur_b;
+        long long& t_wo = xs.t_wo; long long& t_wr = xs.t_wr; long long& t_cf = xs.t_cf;
+        {
+            const int ord = tile - tile_begin;
+            const int buf = ord % a.nbuf;
+            const uint32_t bphase = (uint32_t)((ord / a.nbuf) & 1);
+            const int b = tile / a.tiles_per_b;
+            const int row0 = (tile - b * a.tiles_per_b) * TM;
+            if (b != cur_b) {
+                const long long w0 = dbg_on ? clock64() : 0;
+                named_bar_sync(1, 256);
+                for (int i = ttid; i < a.nslab * 2 * 64; i += 256) {
+                    const int s = i >> 7, ad = (i >> 6) & 1, c = i & 63;
+                    float cs = 1.f, ch = 0.f, ca = 1.f;
+                    if (ad == 0) { xform_coeffs(a.xf0[s], b, 64, c, cs, ch, ca); if (!a.xf0[s].prelu) ca = 1.f; }
+                    else if (a.x1[s]) { xform_coeffs(a.xf1[s], b, 64, c, cs, ch, ca); if (!a.xf1[s].prelu) ca = 1.f; }
+                    float* cf = coef + (s * 2 + ad) * 192;
+                    cf[c] = cs; cf[64 + c] = ch; cf[128 + c] = ca;
+                }
+                named_bar_sync(1, 256);
+                cur_b = b;
+                if (dbg_on) t_cf += clock64() - w0;
+            }
+            const long long w1 = dbg_on ? clock64() : 0;
+            RWAIT_IDLE(&opnd_empty[buf], bphase ^ 1);
+            if (dbg_on) t_wo += clock64() - w1;
+            uint8_t* obuf = opnd + (size_t)buf * pl.buf_bytes;
+            for (int j = 0; j < pl.ngroups; ++j) {
+                int g_lo, n;
+                group_range(a, pl.R, pl.ngroups, rows_per_b, row0, j, g_lo, n);
+                // Item set-up, shared inside each 8-lane row group: lane i of the group works out item i of the row (row block
+                // h, plane p: i = h nplanes + p; i = 4 + p: the tail block of the last group) - padded row -> (frame, column),
+                // validity, raw row in the stage - and the lanes fetch the words of their items with shuffles.
+                // word: bit 31 valid (else literal zeros), bit 30 live (the thread owns such an item), bits 0-29 stage offset
+                unsigned word = 0;
+                {
+                    const int i = lane & 7;
+                    const bool tail = i >= 4;
+                    const int ii = tail ? i - 4 : i;
+                    const int h = tail ? rpt : (a.nplanes == 2 ? (ii >> 1) : ii);
+                    const int p = a.nplanes == 2 ? (ii & 1) : 0;
+                    const int rho = j * a.G + rr + 32 * h;
+                    const int rho_end = j == pl.ngroups - 1 ? pl.R : (j + 1) * a.G;
+                    const bool live = rho < rho_end && (tail ? (ii < a.nplanes && rr < kTail) : (h < rpt));
+                    if (live) {
+                        word = 1u << 30;
+                        const int r = row0 - a.back + rho;
+                        if (r >= 0 && r < rows_per_b) {
+                            const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
+                            const int col = r - t * a.P;
+                            if (col < a.plane_cols[p])
+                                word = (3u << 30) | (unsigned)((t * a.Fin + col * a.col_stride + a.col_off[p] - g_lo) * 256);
+                        }
+                    }
+                }
+                unsigned w[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) w[i] = __shfl_sync(0xffffffffu, word, (lane & 24) + i);
+                const int drow = (j * a.G + rr) * 128 + ((c8 ^ (rr & 7)) << 4);      // 32 h more rows: + 4096 h (same swizzle phase)
+                const int ni = rpt * a.nplanes;                                       // 2 or 4 regular items per thread and group
+                const bool any = (w[0] >> 30) & 1u;
+                const bool any_tail = (w[4] >> 30) & 1u;
+#pragma unroll 1
+                for (int s = 0; s < a.nslab; ++s) {
+                    const long long w2 = dbg_on ? clock64() : 0;
+                    RWAIT(&raw_full[stage], sphase);
+                    if (dbg_on) t_wr += clock64() - w2;
+                    const uint8_t* st0 = ring + (size_t)stage * a.stage_bytes + c8 * 32;
+                    const uint8_t* st1 = st0 + a.add1_off;
+                    const float* cf = coef + s * 2 * 192;
+                    uint8_t* ob = obuf + s * npb * pl.plane_bytes + drow;
+                    const int pstep = a.nslab * npb * pl.plane_bytes;                 // plane 1 images follow plane 0's
+                    const bool dual = a.x1[s] != nullptr;
+                    const unsigned act = __ballot_sync(0xffffffffu, any);
+                    if (any) {
+                        if (ni == 4) {
+                            // (four chunks per thread only in launches without lazy pairs: the launcher halves G for those)
+                            uint8_t* dst[4];
+                            int so[4]; bool k[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int h = a.nplanes == 2 ? (i >> 1) : i, pp = a.nplanes == 2 ? (i & 1) : 0;
+                                const bool use = (w[i] >> 30) & 1u;                   // a slot past the tile's rows repeats slot 0
+                                const unsigned ww = use ? w[i] : w[0];
+                                dst[i] = ob + (use ? h * 4096 + pp * pstep : 0);
+                                so[i] = (int)(ww & 0x3fffffffu); k[i] = (ww >> 31) != 0;
+                            }
+                            xf_items<4, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
+                        } else {
+                            uint8_t* dst[2];
+                            int so[2]; bool k[2];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const int h = a.nplanes == 2 ? 0 : i, pp = a.nplanes == 2 ? i : 0;
+                                const bool use = (w[i] >> 30) & 1u;
+                                const unsigned ww = use ? w[i] : w[0];
+                                dst[i] = ob + (use ? h * 4096 + pp * pstep : 0);
+                                so[i] = (int)(ww & 0x3fffffffu); k[i] = (ww >> 31) != 0;
+                            }
+                            if (dual) xf_items<2, true, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
+                            else xf_items<2, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
+                        }
+                    }
+                    const unsigned act_t = __ballot_sync(0xffffffffu, any_tail);
+                    if (any_tail) {                                                   // the <= kTail rows past the last group's G
+                        uint8_t* dst[2];
+                        int so[2]; bool k[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const bool use = (w[4 + i] >> 30) & 1u;
+                            const unsigned ww = use ? w[4 + i] : w[4];
+                            dst[i] = ob + rpt * 4096 + (use ? i * pstep : 0);
+                            so[i] = (int)(ww & 0x3fffffffu); k[i] = (ww >> 31) != 0;
+                        }
+                        if (dual) xf_items<2, true, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act_t);
+                        else xf_items<2, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act_t);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_empty[stage]);
+                    if (++stage == a.nstage) { stage = 0; sphase ^= 1; }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&opnd_full[buf]);
+        }
+    };
+
     if (warp < 4) {
         if (NTW == 8) reg_dec<48>();
         if (warp == 0) {
@@ -303,7 +448,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                 const int row0 = (tile - b * a.tiles_per_b) * TM;
                 for (int j = 0; j < pl.ngroups; ++j) {
                     int g_lo, n;
-                    group_range(a, pl.R, rows_per_b, row0, j, g_lo, n);
+                    group_range(a, pl.R, pl.ngroups, rows_per_b, row0, j, g_lo, n);
                     const size_t goff = ((size_t)b * a.T * a.Fin + g_lo) * 64;
                     for (int s = 0; s < a.nslab; ++s) {
                         const long long w0 = dbg_on ? clock64() : 0;
@@ -346,7 +491,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                 const long long w0 = dbg_on ? clock64() : 0;
                 RWAIT(&acc_empty[acc], aphase ^ 1);
                 const long long w1 = dbg_on ? clock64() : 0;
-                RWAIT(&opnd_full[buf], bphase);
+                mbar_wait_backoff(&opnd_full[buf], bphase, 20u);                     // a lone poller still takes ~1/4 of its scheduler's issue slots
                 if (dbg_on) { t_wa += w1 - w0; t_wo += clock64() - w1; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
@@ -439,7 +584,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
         const bool dbg_on = kDbg && a.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
         long long t_wf = 0;
         const long long t_start = dbg_on ? clock64() : 0;
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
+        auto epi_tile = [&](const int tile) {
             const int b = tile / a.tiles_per_b;
             if (b != cur_b) { flush(cur_b); cur_b = b; }
             const int row0 = (tile - b * a.tiles_per_b) * TM;
@@ -493,123 +638,18 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
             if (++acc == 2) { acc = 0; aphase ^= 1; }
-        }
+        };
+        for (int tile = tile_begin; tile < tile_end; ++tile) epi_tile(tile);
         flush(cur_b);
         if (dbg_on) { a.dbg[10] = t_wf; a.dbg[11] = clock64() - t_start; }
     } else {
         // =========================================================================== transform warps
-        // thread = (row rr of each 32-row block of the group, 16-byte fp16 chunk c8 = 8 channels); a ring stage is one
-        // (group, slab) and gives the thread NI = (G / 32) x nplanes chunks, transformed as one batch (xf_items).  The two
-        // 16-byte halves of a chunk's 32 raw bytes are read in an order that depends on c8 (c8 >= 4: upper half first) so that
-        // the eight lanes of a quarter-warp touch all 32 banks in both loads.
         const int ttid = tid - TR0;
-        const int c8 = ttid & 7;
-        const int rr = ttid >> 3;                            // 0..31
-        const int qa = (c8 >> 2) & 1;                        // which half this thread loads first
-        const int chA = c8 * 8 + qa * 4, chB = c8 * 8 + (qa ^ 1) * 4;
-        const int rpt = a.G >> 5;                            // rows per thread per group: 1, 2 or 4
-        int stage = 0;
-        uint32_t sphase = 0;
-        int cur_b = -1;
+        XfState xs = {0, 0u, -1, 0, 0, 0};
         const bool dbg_on = kDbg && a.dbg != nullptr && blockIdx.x == 0 && ttid == 0;
-        long long t_wo = 0, t_wr = 0, t_cf = 0;
         const long long t_start = dbg_on ? clock64() : 0;
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
-            const int ord = tile - tile_begin;
-            const int buf = ord % a.nbuf;
-            const uint32_t bphase = (uint32_t)((ord / a.nbuf) & 1);
-            const int b = tile / a.tiles_per_b;
-            const int row0 = (tile - b * a.tiles_per_b) * TM;
-            if (b != cur_b) {
-                const long long w0 = dbg_on ? clock64() : 0;
-                named_bar_sync(1, NTT);
-                for (int i = ttid; i < a.nslab * 2 * 64; i += NTT) {
-                    const int s = i >> 7, ad = (i >> 6) & 1, c = i & 63;
-                    float cs = 1.f, ch = 0.f, ca = 1.f;
-                    if (ad == 0) { xform_coeffs(a.xf0[s], b, 64, c, cs, ch, ca); if (!a.xf0[s].prelu) ca = 1.f; }
-                    else if (a.x1[s]) { xform_coeffs(a.xf1[s], b, 64, c, cs, ch, ca); if (!a.xf1[s].prelu) ca = 1.f; }
-                    float* cf = coef + (s * 2 + ad) * 192;
-                    cf[c] = cs; cf[64 + c] = ch; cf[128 + c] = ca;
-                }
-                named_bar_sync(1, NTT);
-                cur_b = b;
-                if (dbg_on) t_cf += clock64() - w0;
-            }
-            const long long w1 = dbg_on ? clock64() : 0;
-            RWAIT_IDLE(&opnd_empty[buf], bphase ^ 1);
-            if (dbg_on) t_wo += clock64() - w1;
-            uint8_t* obuf = opnd + (size_t)buf * pl.buf_bytes;
-            for (int j = 0; j < pl.ngroups; ++j) {
-                int g_lo, n;
-                group_range(a, pl.R, rows_per_b, row0, j, g_lo, n);
-                // this thread's items: (row block h, plane p) -> raw row offset in the stage, validity, destination slot
-                int soff[4];
-                bool ok[4];
-                int doff[4];
-                bool any = false;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int h = a.nplanes == 2 ? (i >> 1) : i;
-                    const int p = a.nplanes == 2 ? (i & 1) : 0;
-                    const int rho = j * a.G + rr + 32 * h;
-                    const int r = row0 - a.back + rho;
-                    const bool live = h < rpt && rho < pl.R;             // the thread has this item at all
-                    const bool rvalid = live && r >= 0 && r < rows_per_b;
-                    int t = 0, col = 0;
-                    if (rvalid) {
-                        t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
-                        col = r - t * a.P;
-                    }
-                    ok[i] = rvalid && col < a.plane_cols[p];
-                    soff[i] = ok[i] ? (t * a.Fin + col * a.col_stride + a.col_off[p] - g_lo) * 256 + c8 * 32 : c8 * 32;
-                    doff[i] = live ? (p * a.nslab * npb) * pl.plane_bytes + rho * 128 + ((c8 ^ (rho & 7)) << 4) : -1;
-                    any = any || live;
-                }
-                const int ni = rpt * a.nplanes;                          // 1 (dual, stride 1 ... never), 2 or 4 live item slots
-#pragma unroll 1
-                for (int s = 0; s < a.nslab; ++s) {
-                    const long long w2 = dbg_on ? clock64() : 0;
-                    RWAIT(&raw_full[stage], sphase);
-                    if (dbg_on) t_wr += clock64() - w2;
-                    const uint8_t* st0 = ring + (size_t)stage * a.stage_bytes;
-                    const uint8_t* st1 = st0 + a.add1_off;
-                    const float* cf = coef + s * 2 * 192;
-                    const int sadd = s * npb * pl.plane_bytes;
-                    const bool dual = a.x1[s] != nullptr;
-                    const unsigned act = __ballot_sync(0xffffffffu, any);
-                    if (any) {
-                        if (ni == 4) {
-                            // a pad-only tail slot (doff < 0) writes nothing: send it to the thread's first slot, with its value
-                            uint8_t* dst[4];
-                            int so[4]; bool k[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const bool use = doff[i] >= 0;
-                                dst[i] = obuf + sadd + (use ? doff[i] : doff[0]); so[i] = use ? soff[i] : soff[0]; k[i] = use ? ok[i] : ok[0];
-                            }
-                            // (four chunks per thread only in launches without lazy pairs: the launcher halves G for those)
-                            xf_items<4, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
-                        } else {
-                            uint8_t* dst[2];
-                            int so[2]; bool k[2];
-#pragma unroll
-                            for (int i = 0; i < 2; ++i) {
-                                const bool use = i < ni && doff[i] >= 0;
-                                dst[i] = obuf + sadd + (use ? doff[i] : doff[0]); so[i] = use ? soff[i] : soff[0]; k[i] = use ? ok[i] : ok[0];
-                            }
-                            if (dual) xf_items<2, true, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
-                            else xf_items<2, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&raw_empty[stage]);
-                    if (++stage == a.nstage) { stage = 0; sphase ^= 1; }
-                }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&opnd_full[buf]);
-        }
+        for (int tile = tile_begin; tile < tile_end; ++tile) xf_tile(tile, ttid, xs, dbg_on);
+        const long long t_wo = xs.t_wo, t_wr = xs.t_wr, t_cf = xs.t_cf;
         if (dbg_on) { a.dbg[0] = clock64() - t_start; a.dbg[1] = t_wo; a.dbg[2] = t_wr; a.dbg[3] = t_cf; }
     }
 
@@ -678,10 +718,6 @@ bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
     if (nslab != q.nslab) return false;
     a.nslab = nslab;
     if (q.col_stride < 1 || q.col_stride > 2 || q.nplanes != q.col_stride) return false;
-    // group size: a stage holds <= 128 raw rows per addend (32 KB), i.e. 2 or 4 operand chunks per transform thread
-    a.G = 128 / (q.col_stride * (any_dual ? 2 : 1));
-    a.add1_off = a.G * q.col_stride * 256;
-    a.stage_bytes = a.add1_off * (any_dual ? 2 : 1);
     a.B = q.B; a.T = q.T; a.Fin = q.Fin; a.P = q.P;
     a.nplanes = q.nplanes; a.col_stride = q.col_stride;
     for (int i = 0; i < 2; ++i) { a.plane_cols[i] = q.plane_cols[i]; a.col_off[i] = q.col_off[i]; }
@@ -721,6 +757,16 @@ bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
         }
     }
     a.back = back; a.fwd = fwd;
+    // group size: a stage holds <= 128 raw rows per addend (32 KB), i.e. 2 or 4 operand chunks per transform thread; the
+    // last group of a tile also takes a tail of <= kTail rows (stage capacity = the largest group)
+    a.G = 128 / (q.col_stride * (any_dual ? 2 : 1));
+    {
+        const int R = TM + back + fwd;
+        const int ng = R <= a.G + kTail ? 1 : (R - kTail + a.G - 1) / a.G;
+        const int cap = ng == 1 ? R : std::max(a.G, R - (ng - 1) * a.G);
+        a.add1_off = cap * q.col_stride * 256;
+        a.stage_bytes = a.add1_off * (any_dual ? 2 : 1);
+    }
     // K units: variant-major, then (tap, slab), pass fastest (the weight ring streams images in the same order)
     const int npb = a.npass == 3 ? 2 : 1;
     a.nbuf = 1; a.nstage = 2; a.resident = 0; a.nsb = 3;
@@ -755,7 +801,7 @@ bool raw_conv_supported(const PlaneConvArgs* p, int n) {
     return build_args(p, n, &a);
 }
 
-int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned long long* dbg) {
+int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned long long* dbg, int max_grid) {
     RawConvArgs a;
     if (!build_args(p, n, &a)) return fail("conv_raw: unsupported layer");
     if (a.B <= 0 || a.T <= 0) return 0;
@@ -772,7 +818,8 @@ int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned lon
     EAB_TRY(device_sm_count(&sms));
     const long long ntiles = (long long)a.B * a.tiles_per_b;
     if (ntiles >= (1ll << 30)) return fail("conv_raw: too many tiles");
-    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    int grid = (int)(ntiles < sms ? ntiles : sms);
+    if (max_grid > 0 && grid > max_grid) grid = max_grid;      // diagnostics / tests: many tiles per CTA at small sizes
     // algorithmic bytes: every input tensor once (a lazy residual pair is ONE tensor), the output once, fp32;
     // moved: both addends of a lazy pair, and the weights
     double pos = 0, kn = 0, in_algo = 0, in_moved = 0;

@@ -113,47 +113,7 @@ __global__ void __launch_bounds__(256) beam_miso_kernel(const BeamArgs a) {
     }
 }
 
-// 16-bit PCM wire format.  In: what torchaudio.load does to int16 files (enhance.py:35), x / 32768,
-// plus enhance.py:41-42's microphone permutation; out: the reference's writer (dataset/mcse_dataset_offline_gen.py:38-39),
-// int16(clip(y, -1, 1) * 32767) truncated toward zero.
-__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const PcmArgs a) {
-    const size_t n = (size_t)a.B * a.M * a.L;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t row = i / a.L, l = i - row * a.L;
-        const int b = (int)(row / a.M), m = (int)(row - (size_t)b * a.M);
-        a.wave[i] = (float)__ldg(a.pcm + ((size_t)b * a.M + a.order[m]) * a.L + l) * (1.f / 32768.f);
-    }
-}
-__global__ void __launch_bounds__(256) float_to_pcm16_kernel(const float* x, short* out, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float v = fminf(fmaxf(__ldg(x + i), -1.f), 1.f) * 32767.f;
-        out[i] = (short)(int)v;                       // numpy's astype(int16): truncation toward zero
-    }
-}
-
 }  // namespace
-
-int launch_pcm16_to_float(const PcmArgs& a, cudaStream_t st) {
-    if (a.B <= 0 || a.M <= 0 || a.L <= 0) return 0;
-    if (a.M > 64) return fail("pcm16: at most 64 microphones");
-    const size_t n = (size_t)a.B * a.M * a.L;
-    int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    ProfScope ps("pcm16", 0.0, 6.0 * n, st);
-    EAB_CUDA(launch_k(pcm16_to_float_kernel, dim3(blocks), dim3(256), (size_t)0, st, a));
-    EAB_LAUNCH_CHECK("pcm16_to_float_kernel");
-    return 0;
-}
-
-int launch_float_to_pcm16(const float* x, short* out, size_t n, cudaStream_t st) {
-    if (n == 0) return 0;
-    int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    ProfScope ps("pcm16", 0.0, 6.0 * n, st);
-    EAB_CUDA(launch_k(float_to_pcm16_kernel, dim3(blocks), dim3(256), (size_t)0, st, x, out, n));
-    EAB_LAUNCH_CHECK("float_to_pcm16_kernel");
-    return 0;
-}
 
 int launch_combine(const CombineArgs& a, cudaStream_t st) {
     if (a.nsrc < 1 || a.nsrc > 3) return fail("combine: 1..3 sources");

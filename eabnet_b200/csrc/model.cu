@@ -254,7 +254,7 @@ struct eab_model {
     int opt_dual_stream = 1;
     // the per-slot step of the host front door as a CUDA graph (captured on the slot's second use, replayed afterwards)
     struct SlotGraph { cudaGraphExec_t exec = nullptr; const void* in = nullptr; void* out = nullptr; void* ws = nullptr; int B = 0, L = 0;
-                       unsigned long long version = 0; int launches = 0; };
+                       unsigned long long version = 0, mode = 0; int launches = 0; };
     SlotGraph slot_graph[2];
     unsigned long long param_version = 0;           // bumped by every commit
     int opt_host_graph = 1;
@@ -267,6 +267,7 @@ struct eab_model {
     int opt_first_passes = 3;     // the first gated conv (2M input channels, tap-window rows: 3.5x the input bytes per pass-plane)
     int opt_staged = 1;           // stage_kernel + TMA-fed conv kernel (layers conv_raw does not take)
     int opt_raw = 1;              // conv_raw_kernel: raw fp32 tiles normalised in shared memory, no stage pass (preferred)
+    int opt_raw_grid = 0;         // diagnostics / tests: cap on conv_raw's grid size (0 = one CTA per SM)
     int opt_fused_head = 1;       // w_dnn + filter-and-sum as one kernel
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
@@ -1149,7 +1150,7 @@ int run_tensor_convs(Ctx& cx, UmmaConvArgs* us, int n) {
             if (cx.dry) return 0;
             unsigned long long* dbg = nullptr;
             if (m->umma_launch_idx++ == m->opt_dbg_launch && m->dbg_buf) dbg = m->dbg_buf;
-            return launch_conv_raw(p, n, cx.st, dbg);
+            return launch_conv_raw(p, n, cx.st, dbg, m->opt_raw_grid);
         }
     }
     bool staged_ok = planes_ok && m->opt_staged && staged_conv_supported(ps);
@@ -2192,8 +2193,11 @@ size_t eab_enhance_workspace_bytes(const eab_model* m, int B, int L) {
     return spec + outp + fw;
 }
 
-int eab_enhance(eab_model* m, const float* wave, float* enhanced, int B, int L, void* ws, size_t ws_bytes, void* stream) {
-    if (!m || !wave || !enhanced || !ws) return fail("eab_enhance: null argument");
+// wave -> wave on device buffers.  Input: fp32 [B][M][L], or (pcm != null) int16 PCM in file channel order with microphone
+// m = file channel order[m]; output: fp32 samples, or (enhanced16 != null) the reference's int16 writer.
+static int enhance_dev(eab_model* m, const float* wave, const int16_t* pcm, const int* order, float* enhanced, int16_t* enhanced16,
+                       int B, int L, void* ws, size_t ws_bytes, void* stream) {
+    if (!m || (!wave && !pcm) || (!enhanced && !enhanced16) || !ws) return fail("eab_enhance: null argument");
     if (m->kind != 0) return fail("eab_enhance needs an EaBNet handle");
     if (m->cfg.topo_type == 1) return fail("eab_enhance: the 'miso' topology returns [B,2,T], which has no iSTFT");
     if (m->cfg.n_freq != 161) return fail("eab_enhance: the 320-point STFT gives 161 bins");
@@ -2210,11 +2214,17 @@ int eab_enhance(eab_model* m, const float* wave, float* enhanced, int B, int L, 
     p += align256((size_t)B * 2 * T * 161 * sizeof(float));
     reset_launch_count();
     // the forward workspace is idle until the STFT has finished: it doubles as the STFT's plane scratch
-    int rc = launch_stft(wave, spec, B, m->cfg.M, L, st, p, ws_bytes - (size_t)(p - static_cast<char*>(ws)));
-    if (!rc) rc = forward(m, spec, outp, B, T, p, ws_bytes - (size_t)(p - static_cast<char*>(ws)), st);
-    if (!rc) rc = launch_istft(outp, enhanced, B, T, st);
+    const size_t rest = ws_bytes - (size_t)(p - static_cast<char*>(ws));
+    int rc = pcm ? launch_stft_pcm16(pcm, order, spec, B, m->cfg.M, L, st, p, rest) : launch_stft(wave, spec, B, m->cfg.M, L, st, p, rest);
+    if (!rc) rc = forward(m, spec, outp, B, T, p, rest, st);
+    if (!rc) rc = launch_istft(outp, enhanced, B, T, st, enhanced16);
     m->last_launches = launch_count();
     return rc;
+}
+
+int eab_enhance(eab_model* m, const float* wave, float* enhanced, int B, int L, void* ws, size_t ws_bytes, void* stream) {
+    if (!wave || !enhanced) return fail("eab_enhance: null argument");
+    return enhance_dev(m, wave, nullptr, nullptr, enhanced, nullptr, B, L, ws, ws_bytes, stream);
 }
 
 // enhance.py:49-62 on device buffers: STFT + compression, EaBNet, GaGNet on (reference microphone, EaBNet estimate), iSTFT
@@ -2229,9 +2239,9 @@ size_t eab_enhance_postnet_workspace_bytes(const eab_model* eab, const eab_model
     return spec + est * (1 + gag->cfg.q) + std::max(f1, f2);
 }
 
-int eab_enhance_postnet(eab_model* eab, eab_model* gag, int ref_mic, const float* wave, float* enhanced, int B, int L, void* ws,
-                        size_t ws_bytes, void* stream) {
-    if (!eab || !gag || !wave || !enhanced || !ws) return fail("eab_enhance_postnet: null argument");
+static int enhance_postnet_dev(eab_model* eab, eab_model* gag, int ref_mic, const float* wave, const int16_t* pcm, const int* order,
+                               float* enhanced, int16_t* enhanced16, int B, int L, void* ws, size_t ws_bytes, void* stream) {
+    if (!eab || !gag || (!wave && !pcm) || (!enhanced && !enhanced16) || !ws) return fail("eab_enhance_postnet: null argument");
     if (eab->kind != 0 || gag->kind != 1) return fail("eab_enhance_postnet: needs an EaBNet handle and a GaGNet handle");
     if (eab->cfg.topo_type == 1) return fail("eab_enhance_postnet: the 'miso' topology returns [B,2,T]");
     if (eab->cfg.n_freq != 161 || gag->cfg.n_freq != 161) return fail("eab_enhance_postnet: the 320-point STFT gives 161 bins");
@@ -2252,30 +2262,50 @@ int eab_enhance_postnet(eab_model* eab, eab_model* gag, int ref_mic, const float
     // (the q estimates are written back to back, B*2*T*F floats each; only the last one is read here)
     const size_t rest = ws_bytes - (size_t)(p - static_cast<char*>(ws));
     reset_launch_count();
-    int rc = launch_stft(wave, spec, B, M, L, st, p, rest);      // the forward workspace is idle until the STFT has finished
+    // (the forward workspace is idle until the STFT has finished: it doubles as the STFT's plane scratch)
+    int rc = pcm ? launch_stft_pcm16(pcm, order, spec, B, M, L, st, p, rest) : launch_stft(wave, spec, B, M, L, st, p, rest);
     if (!rc) rc = forward(eab, spec, est0, B, T, p, rest, st);
     const long long strides[4] = {(long long)T * F * M * 2, 1, (long long)F * M * 2, (long long)M * 2};
     if (!rc) rc = gag_forward(gag, spec + (size_t)ref_mic * 2, strides, est0, stages, B, T, p, rest, st);
-    if (!rc) rc = launch_istft(stages + (size_t)(gag->cfg.q - 1) * B * 2 * T * F, enhanced, B, T, st);
+    if (!rc) rc = launch_istft(stages + (size_t)(gag->cfg.q - 1) * B * 2 * T * F, enhanced, B, T, st, enhanced16);
     const int n = launch_count();
     eab->last_launches = n;
     gag->last_launches = n;
     return rc;
 }
 
+int eab_enhance_postnet(eab_model* eab, eab_model* gag, int ref_mic, const float* wave, float* enhanced, int B, int L, void* ws,
+                        size_t ws_bytes, void* stream) {
+    if (!wave || !enhanced) return fail("eab_enhance_postnet: null argument");
+    return enhance_postnet_dev(eab, gag, ref_mic, wave, nullptr, nullptr, enhanced, nullptr, B, L, ws, ws_bytes, stream);
+}
+
 // Host front door.  Batch i+1 is uploaded (copy stream) and batch i-1 downloaded (second copy stream) while batch i
 // computes on the caller's stream: two device input slots, two output slots, one workspace.
-int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float* const* enhanced_host, int n_batches,
-                             int B, int L, void* stream) {
+// pcm: the batches are int16 PCM in file channel order (microphone m = file channel order[m]) and the results int16 PCM
+static int host_batches(eab_model* m, const void* const* waves_host, void* const* enhanced_host, bool pcm, const int* order,
+                        int n_batches, int B, int L, void* stream) {
     if (!m || !waves_host || !enhanced_host) return fail("eab_enhance_host_batches: null argument");
+    if (m->kind != 0) return fail("eab_enhance_host_batches needs an EaBNet handle");
+    int ord[64];
+    unsigned long long ord_hash = pcm ? 1469598103934665603ull : 0ull;
+    if (pcm) {
+        if (m->cfg.M > 64) return fail("pcm16: at most 64 microphones");
+        for (int i = 0; i < m->cfg.M; ++i) {
+            ord[i] = order ? order[i] : i;
+            if (ord[i] < 0 || ord[i] >= m->cfg.M) return fail("pcm16: mic_order entries must be in [0, M)");
+            ord_hash = (ord_hash ^ (unsigned long long)(ord[i] + 1)) * 1099511628211ull;
+        }
+    }
+    const size_t esz = pcm ? sizeof(int16_t) : sizeof(float);
     if (n_batches < 1) return 0;
     for (int i = 0; i < n_batches; ++i)
         if (!waves_host[i] || !enhanced_host[i]) return fail("eab_enhance_host_batches: null batch pointer");
     const size_t need = eab_enhance_workspace_bytes(m, B, L);
     if (!need) return fail("eab_enhance_host_batches: bad shape");
     const int nslot = n_batches > 1 ? 2 : 1;
-    const size_t in_bytes = (size_t)B * m->cfg.M * L * sizeof(float);
-    const size_t out_bytes = (size_t)B * 160 * (L / 160) * sizeof(float);
+    const size_t in_bytes = (size_t)B * m->cfg.M * L * esz;
+    const size_t out_bytes = (size_t)B * 160 * (L / 160) * esz;
     const size_t in_b = align256(in_bytes), out_b = align256(out_bytes);
     // two compute streams (even / odd batches, a workspace each): consecutive batches overlap wherever one leaves SMs idle
     // (the LSTM runs on 108 of the 148 SMs for 4 ms of a 22 ms step)
@@ -2309,8 +2339,8 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
         stream = st;
     }
     char* p = static_cast<char*>(m->scratch);
-    float* din[2] = {reinterpret_cast<float*>(p), reinterpret_cast<float*>(p + (nslot - 1) * in_b)};
-    float* dout[2] = {reinterpret_cast<float*>(p + nslot * in_b), reinterpret_cast<float*>(p + nslot * in_b + (nslot - 1) * out_b)};
+    char* din[2] = {p, p + (nslot - 1) * in_b};
+    char* dout[2] = {p + nslot * in_b, p + nslot * in_b + (nslot - 1) * out_b};
     char* ws_slot[2] = {p + nslot * (in_b + out_b), p + nslot * (in_b + out_b) + (dual ? align256(need) : 0)};
     cudaStream_t cs[2] = {st, dual ? m->s_comp2 : st};
     // the copy streams start after everything already queued on the caller's stream (scratch may still be in use)
@@ -2331,7 +2361,13 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
         {
             eab_model::SlotGraph& sg = m->slot_graph[s];
             const bool match = sg.exec && sg.in == din[s] && sg.out == dout[s] && sg.ws == ws && sg.B == B && sg.L == L &&
-                               sg.version == m->param_version;
+                               sg.version == m->param_version && sg.mode == ord_hash;
+            auto step = [&]() {
+                return pcm ? enhance_dev(m, nullptr, reinterpret_cast<const int16_t*>(din[s]), ord, nullptr, reinterpret_cast<int16_t*>(dout[s]),
+                                         B, L, ws, need, cst)
+                           : enhance_dev(m, reinterpret_cast<const float*>(din[s]), nullptr, nullptr, reinterpret_cast<float*>(dout[s]), nullptr,
+                                         B, L, ws, need, cst);
+            };
             if (match) {
                 EAB_CUDA(cudaGraphLaunch(sg.exec, cst));
                 m->last_launches = sg.launches;
@@ -2341,22 +2377,22 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
                 bool ok = cudaStreamBeginCapture(cst, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
                 int rc = 1;
                 if (ok) {
-                    rc = eab_enhance(m, din[s], dout[s], B, L, ws, need, cst);
+                    rc = step();
                     ok = cudaStreamEndCapture(cst, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
                 }
                 if (ok) ok = cudaGraphInstantiate(&sg.exec, graph, 0) == cudaSuccess;
                 if (graph) cudaGraphDestroy(graph);
                 if (ok) {
-                    sg.in = din[s]; sg.out = dout[s]; sg.ws = ws; sg.B = B; sg.L = L; sg.version = m->param_version;
+                    sg.in = din[s]; sg.out = dout[s]; sg.ws = ws; sg.B = B; sg.L = L; sg.version = m->param_version; sg.mode = ord_hash;
                     sg.launches = m->last_launches;
                     EAB_CUDA(cudaGraphLaunch(sg.exec, cst));
                 } else {
                     sg.exec = nullptr;
                     cudaGetLastError();                        // capture refused (e.g. a legacy-stream caller): run the step directly
-                    EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, cst));
+                    EAB_TRY(step());
                 }
             } else {
-                EAB_TRY(eab_enhance(m, din[s], dout[s], B, L, ws, need, cst));
+                EAB_TRY(step());
             }
         }
         launches += m->last_launches;
@@ -2372,25 +2408,38 @@ int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float
     return 0;
 }
 
+int eab_enhance_host_batches(eab_model* m, const float* const* waves_host, float* const* enhanced_host, int n_batches,
+                             int B, int L, void* stream) {
+    return host_batches(m, reinterpret_cast<const void* const*>(waves_host), reinterpret_cast<void* const*>(enhanced_host), false, nullptr,
+                        n_batches, B, L, stream);
+}
+
+// The same pipeline on the 16-bit PCM wire format (half the H2D / D2H bytes): the int16 -> float conversion and the microphone
+// permutation happen in the STFT's operand staging, the int16 writer in the iSTFT's store.
+int eab_enhance_host_batches_pcm16(eab_model* m, const int16_t* const* pcm_host, const int* mic_order, int16_t* const* enhanced_pcm_host,
+                                   int n_batches, int B, int L, void* stream) {
+    return host_batches(m, reinterpret_cast<const void* const*>(pcm_host), reinterpret_cast<void* const*>(enhanced_pcm_host), true, mic_order,
+                        n_batches, B, L, stream);
+}
+
 // enhance.py:35-43 + the int16 writer of the dataset tools, end to end on HOST 16-bit PCM buffers: H2D of the PCM (half the
 // bytes of the fp32 front door), int16 -> float / 32768 with the microphone permutation, EaBNet (+ GaGNet), float -> int16, D2H.
 int eab_enhance_host_pcm16(eab_model* m, eab_model* gag, int ref_mic, const int16_t* pcm_host, const int* mic_order,
                            int16_t* enhanced_pcm_host, int B, int L, void* stream) {
     if (!m || !pcm_host || !enhanced_pcm_host) return fail("eab_enhance_host_pcm16: null argument");
     if (m->kind != 0 || (gag && gag->kind != 1)) return fail("eab_enhance_host_pcm16: needs an EaBNet handle (and optionally a GaGNet handle)");
+    if (!gag) return eab_enhance_host_batches_pcm16(m, &pcm_host, mic_order, &enhanced_pcm_host, 1, B, L, stream);
     const int M = m->cfg.M;
     if (M > 64) return fail("eab_enhance_host_pcm16: at most 64 microphones");
-    PcmArgs pa;
-    memset(&pa, 0, sizeof(pa));
+    int order[64];
     for (int i = 0; i < M; ++i) {
-        pa.order[i] = mic_order ? mic_order[i] : i;
-        if (pa.order[i] < 0 || pa.order[i] >= M) return fail("eab_enhance_host_pcm16: mic_order entries must be in [0, M)");
+        order[i] = mic_order ? mic_order[i] : i;
+        if (order[i] < 0 || order[i] >= M) return fail("eab_enhance_host_pcm16: mic_order entries must be in [0, M)");
     }
-    const size_t need = gag ? eab_enhance_postnet_workspace_bytes(m, gag, B, L) : eab_enhance_workspace_bytes(m, B, L);
+    const size_t need = eab_enhance_postnet_workspace_bytes(m, gag, B, L);
     if (!need) return fail("eab_enhance_host_pcm16: bad shape");
     const size_t n_in = (size_t)B * M * L, n_out = (size_t)B * 160 * (L / 160);
-    const size_t o_pcm = 0, o_wave = align256(n_in * 2), o_enh = o_wave + align256(n_in * 4), o_epcm = o_enh + align256(n_out * 4),
-                 o_ws = o_epcm + align256(n_out * 2), total = o_ws + need;
+    const size_t o_pcm = 0, o_epcm = align256(n_in * 2), o_ws = o_epcm + align256(n_out * 2), total = o_ws + need;
     if (m->scratch_bytes < total) {
         if (m->scratch) cudaFree(m->scratch);
         m->scratch = nullptr;
@@ -2400,17 +2449,10 @@ int eab_enhance_host_pcm16(eab_model* m, eab_model* gag, int ref_mic, const int1
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* p = static_cast<char*>(m->scratch);
-    short* d_pcm = reinterpret_cast<short*>(p + o_pcm);
-    float* d_wave = reinterpret_cast<float*>(p + o_wave);
-    float* d_enh = reinterpret_cast<float*>(p + o_enh);
-    short* d_epcm = reinterpret_cast<short*>(p + o_epcm);
+    int16_t* d_pcm = reinterpret_cast<int16_t*>(p + o_pcm);
+    int16_t* d_epcm = reinterpret_cast<int16_t*>(p + o_epcm);
     EAB_CUDA(cudaMemcpyAsync(d_pcm, pcm_host, n_in * 2, cudaMemcpyHostToDevice, st));
-    pa.pcm = d_pcm; pa.wave = d_wave; pa.B = B; pa.M = M; pa.L = L;
-    EAB_TRY(launch_pcm16_to_float(pa, st));
-    if (gag) EAB_TRY(eab_enhance_postnet(m, gag, ref_mic, d_wave, d_enh, B, L, p + o_ws, need, stream));
-    else EAB_TRY(eab_enhance(m, d_wave, d_enh, B, L, p + o_ws, need, stream));
-    m->last_launches += 2;
-    EAB_TRY(launch_float_to_pcm16(d_enh, d_epcm, n_out, st));
+    EAB_TRY(enhance_postnet_dev(m, gag, ref_mic, nullptr, d_pcm, order, nullptr, d_epcm, B, L, p + o_ws, need, stream));
     EAB_CUDA(cudaMemcpyAsync(enhanced_pcm_host, d_epcm, n_out * 2, cudaMemcpyDeviceToHost, st));
     EAB_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -2522,6 +2564,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     if (n == "umma") m->opt_umma = value != 0;
     else if (n == "staged") m->opt_staged = value != 0;
     else if (n == "raw") m->opt_raw = value != 0;
+    else if (n == "raw_grid") m->opt_raw_grid = value;
     else if (n == "lazy") m->opt_lazy = value != 0;
     else if (n == "tcm_chain") m->opt_tcm_chain = value;
     else if (n == "host_graph") m->opt_host_graph = value != 0;
@@ -2541,6 +2584,8 @@ int eab_set_option(eab_model* m, const char* name, int value) {
         cudaMemset(m->dbg_buf, 0, 16 * sizeof(unsigned long long));
     }
     else return fail("eab_set_option: unknown option or bad value: " + n);
+    for (auto& sg : m->slot_graph)               // graphs captured under the old options must not be replayed
+        if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
     return 0;
 }
 

@@ -217,9 +217,11 @@ __global__ void __launch_bounds__(THREADS) stft_kernel(const float* __restrict__
 constexpr int IFR = RB;          // frames per CTA in the inverse transform -> IFR-1 output hops
 
 // grid (ceil((T-1)/(IFR-1)), B)
+// wave16 != null: the reference's int16 writer instead of fp32 samples, int16(clip(y, -1, 1) * 32767) truncated toward zero
+// (dataset/mcse_dataset_offline_gen.py:38-39)
 __global__ void __launch_bounds__(THREADS) istft_kernel(const float* __restrict__ spec, float* __restrict__ wave,
-                                                        const float* __restrict__ tab, const float* __restrict__ win,
-                                                        const float* __restrict__ ienv, int B, int T) {
+                                                        short* __restrict__ wave16, const float* __restrict__ tab,
+                                                        const float* __restrict__ win, const float* __restrict__ ienv, int B, int T) {
     extern __shared__ __align__(16) float dsm[];
     float* Are = dsm;                    // [NF][RB]
     float* Aim = Are + NF * RB;          // [NF][RB]
@@ -259,7 +261,9 @@ __global__ void __launch_bounds__(THREADS) istft_kernel(const float* __restrict_
         const float sa = Pa[HOP - n] + Pa[NF + HOP - n];          // s_a[n+160] * 320 / 320 (scale in table)
         const float sb = Pb[n] - Pb[NF + n];                      // s_b[n]
         const float v = (__ldg(win + n + HOP) * sa + __ldg(win + n) * sb) * __ldg(ienv + n);
-        wave[(size_t)b * out_len + (size_t)ta * HOP + n] = v;
+        const size_t o = (size_t)b * out_len + (size_t)ta * HOP + n;
+        if (wave16) wave16[o] = (short)(int)(fminf(fmaxf(v, -1.f), 1.f) * 32767.f);
+        else wave[o] = v;
     }
 }
 
@@ -395,7 +399,11 @@ __global__ void step_advance_kernel(int* step) {
 // i.e. a two-tap "convolution" over hop rows with K = 160 (+32 zero) channels per tap and 322 output columns: exactly
 // the GEMM the conv_tma kernel runs.  This kernel writes the hop rows as the kernel's fp16 hi / lo plane images
 // (np[slab*2 + hl] : [B*M][np_rows][64] halves, 128B-swizzled by row & 7; row = np_front + hop index, hops 0..T).
-__global__ void __launch_bounds__(256) stft_stage_kernel(const float* __restrict__ wave, uint8_t* __restrict__ planes,
+// The waveform is fp32 [B][M][L], or (pcm.data != null) the 16-bit PCM wire format [B][M][L] int16 in file channel order:
+// sample / 32768 (what torchaudio.load does, enhance.py:35) of file channel pcm.order[mic] (enhance.py:41-42) - the int16 ->
+// float conversion and the microphone permutation cost nothing here, the stand-alone pcm16_to_float pass is gone.
+struct PcmSrc { const short* data; int order[64]; };
+__global__ void __launch_bounds__(256) stft_stage_kernel(const float* __restrict__ wave, const PcmSrc pcm, uint8_t* __restrict__ planes,
                                                          size_t image_bytes, int np_rows, int np_front, int L, int T, int M) {
     const int b = blockIdx.z, slab = blockIdx.y;
     const int c8 = threadIdx.x & 7;
@@ -405,7 +413,9 @@ __global__ void __launch_bounds__(256) stft_stage_kernel(const float* __restrict
         const int rr = rho - np_front;                      // plane row = hop j * M + mic
         const int j = rr >= 0 ? rr / M : -1;
         const int mic = rr - j * M;
-        const float* x = wave + ((size_t)b * M + (j >= 0 ? mic : 0)) * L;
+        const int mic_ok = j >= 0 ? mic : 0;
+        const float* x = wave + ((size_t)b * M + mic_ok) * L;
+        const short* xp = pcm.data ? pcm.data + ((size_t)b * M + pcm.order[mic_ok]) * L : nullptr;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(256) stft_stage_kernel(const float* __restrict
                 int q = HOP * j + hs - HOP;                 // centre padding = 160, reflect (test.py:35)
                 if (q < 0) q = -q;
                 if (q >= L) q = 2 * (L - 1) - q;
-                s = __ldg(x + q);
+                s = xp ? (float)__ldg(xp + q) * (1.f / 32768.f) : __ldg(x + q);
             }
             v[i] = s;
         }
@@ -434,8 +444,8 @@ __global__ void __launch_bounds__(256) stft_stage_kernel(const float* __restrict
     }
 }
 
-int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int L, int T, cudaStream_t st, void* scratch,
-                   size_t scratch_bytes) {
+int launch_stft_tc(Tables* t, const float* wave, const PcmSrc& pcm, float* spec, int B, int M, int L, int T, cudaStream_t st,
+                   void* scratch, size_t scratch_bytes) {
     PlaneConvArgs a;
     memset(&a, 0, sizeof(a));
     // rows of batch item b are (hop j, mic) with pitch M, so that the epilogue's lanes write consecutive mics
@@ -472,9 +482,9 @@ int launch_stft_tc(Tables* t, const float* wave, float* spec, int B, int M, int 
     }
     for (int i = 0; i < DFT_SLABS * 2; ++i) a.np[i] = planes + (size_t)i * image_bytes;
     {
-        ProfScope ps("stft_stage", 0.0, 0.0, st, 4.0 * (double)B * M * L + (double)need);
+        ProfScope ps("stft_stage", 0.0, 0.0, st, (pcm.data ? 2.0 : 4.0) * (double)B * M * L + (double)need);
         dim3 grid((a.np_rows + 255) / 256, DFT_SLABS, a.B);
-        EAB_CUDA(launch_k(stft_stage_kernel, grid, dim3(256), (size_t)0, st, wave, planes, image_bytes,
+        EAB_CUDA(launch_k(stft_stage_kernel, grid, dim3(256), (size_t)0, st, wave, pcm, planes, image_bytes,
                           a.np_rows, a.np_front, L, T, M));
         EAB_LAUNCH_CHECK("stft_stage_kernel");
     }
@@ -495,7 +505,7 @@ int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_
     Tables* t;
     EAB_TRY(get_tables(&t));
     const int T = 1 + L / HOP;
-    if (g_stft_tc) return launch_stft_tc(t, wave, spec, B, M, L, T, st, scratch, scratch_bytes);
+    if (g_stft_tc) { PcmSrc none; memset(&none, 0, sizeof(none)); return launch_stft_tc(t, wave, none, spec, B, M, L, T, st, scratch, scratch_bytes); }
     static bool configured = false;
     if (!configured) {
         EAB_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -506,6 +516,23 @@ int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_
     EAB_CUDA(launch_k(stft_kernel, dim3((T + FR - 1) / FR, B), dim3(THREADS), kSmemBytes, st, wave, spec, (const float*)t->fwd, (const float*)t->win, B, M, L, T));
     EAB_LAUNCH_CHECK("stft_kernel");
     return 0;
+}
+
+int launch_stft_pcm16(const short* pcm, const int* order, float* spec, int B, int M, int L, cudaStream_t st, void* scratch,
+                      size_t scratch_bytes) {
+    if (L < HOP + 1) return fail("stft: need at least 161 samples (reflect padding of 160)");
+    if (B <= 0 || M <= 0 || M > 64) return fail("stft (pcm16): bad shape (at most 64 microphones)");
+    if (!g_stft_tc) return fail("the 16-bit PCM front door runs on the tensor-core STFT (option stft_tc = 1)");
+    Tables* t;
+    EAB_TRY(get_tables(&t));
+    PcmSrc src;
+    memset(&src, 0, sizeof(src));
+    src.data = pcm;
+    for (int i = 0; i < M; ++i) {
+        src.order[i] = order ? order[i] : i;
+        if (src.order[i] < 0 || src.order[i] >= M) return fail("pcm16: mic_order entries must be in [0, M)");
+    }
+    return launch_stft_tc(t, nullptr, src, spec, B, M, L, 1 + L / HOP, st, scratch, scratch_bytes);
 }
 
 static int configure_smem() {
@@ -550,7 +577,7 @@ int launch_step_advance(int* step, cudaStream_t st) {
     return 0;
 }
 
-int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st) {
+int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st, short* wave16) {
     if (T < 2) return fail("istft: need at least 2 frames");
     Tables* t;
     EAB_TRY(get_tables(&t));
@@ -561,7 +588,7 @@ int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st) 
         configured = true;
     }
     ProfScope ps("istft", 2.0 * NF * NCOL * (double)B * T, 4.0 * ((double)B * 2 * T * NF + (double)B * HOP * (T - 1)), st);
-    EAB_CUDA(launch_k(istft_kernel, dim3((T - 1 + IFR - 2) / (IFR - 1), B), dim3(THREADS), kSmemBytes, st, spec, wave, (const float*)t->inv, (const float*)t->win, (const float*)t->ienv, B, T));
+    EAB_CUDA(launch_k(istft_kernel, dim3((T - 1 + IFR - 2) / (IFR - 1), B), dim3(THREADS), kSmemBytes, st, spec, wave, wave16, (const float*)t->inv, (const float*)t->win, (const float*)t->ienv, B, T));
     EAB_LAUNCH_CHECK("istft_kernel");
     return 0;
 }

@@ -284,28 +284,49 @@ class EaBNet(_NativeModule):
                        "eab_enhance_host")
         return out
 
-    def enhance_host_batches(self, waves, outs=None, device: torch.device | str = "cuda"):
+    def enhance_host_batches(self, waves, outs=None, device: torch.device | str = "cuda", mic_order=None):
         """A list of HOST batches [B,M,L] (same shape, ideally pinned) -> list of HOST enhanced batches.  Uploads,
-        compute and downloads of consecutive batches overlap (eab_enhance_host_batches)."""
+        compute and downloads of consecutive batches overlap (eab_enhance_host_batches).  float32 batches give float32
+        results; int16 batches (the PCM wire format: sample / 32768, microphone m = file channel mic_order[m]) give int16
+        results through eab_enhance_host_batches_pcm16 at half the copy bytes."""
         if not waves:
             return []
         B, M, L = waves[0].shape
+        dt = waves[0].dtype
+        if dt not in (torch.float32, torch.int16):
+            raise TypeError("enhance_host_batches takes float32 or int16 batches")
         for w in waves:
-            if w.is_cuda or w.dtype != torch.float32 or tuple(w.shape) != (B, M, L) or not w.is_contiguous():
-                raise TypeError("enhance_host_batches takes contiguous float32 CPU tensors of one shape")
+            if w.is_cuda or w.dtype != dt or tuple(w.shape) != (B, M, L) or not w.is_contiguous():
+                raise TypeError("enhance_host_batches takes contiguous CPU tensors of one shape and dtype (float32 or int16)")
+        if M != self.M:
+            raise RuntimeError("expected %d microphones, got %d" % (self.M, M))
+        if mic_order is not None and dt != torch.int16:
+            raise TypeError("mic_order applies to int16 PCM batches")
         dev = torch.device(device)
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         if outs is None:
-            outs = [torch.empty((B, 160 * (L // 160)), dtype=torch.float32, pin_memory=True) for _ in waves]
+            outs = [torch.empty((B, 160 * (L // 160)), dtype=dt, pin_memory=True) for _ in waves]
+        for o in outs:
+            if o.is_cuda or o.dtype != dt or tuple(o.shape) != (B, 160 * (L // 160)) or not o.is_contiguous():
+                raise TypeError("outs must be contiguous CPU tensors [B, 160 * (L // 160)] of the input dtype")
         n = len(waves)
         wp = (C.c_void_p * n)(*[_ptr(w) for w in waves])
         op = (C.c_void_p * n)(*[_ptr(o) for o in outs])
         with torch.cuda.device(dev):
             self._sync_params(dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(self._native.lib.eab_enhance_host_batches(self._native.h, wp, op, n, B, L, stream),
-                       "eab_enhance_host_batches")
+            if dt == torch.int16:
+                order = None
+                if mic_order is not None:
+                    if len(mic_order) != M:
+                        raise ValueError("mic_order needs %d entries" % M)
+                    order = (C.c_int * M)(*[int(v) for v in mic_order])
+                _lib.check(self._native.lib.eab_enhance_host_batches_pcm16(self._native.h, wp, order, op, n, B, L, stream),
+                           "eab_enhance_host_batches_pcm16")
+            else:
+                _lib.check(self._native.lib.eab_enhance_host_batches(self._native.h, wp, op, n, B, L, stream),
+                           "eab_enhance_host_batches")
         return outs
 
     def enhance_pcm16(self, pcm: torch.Tensor, mic_order=None, out: torch.Tensor | None = None, postnet=None, ref_mic: int = 0,

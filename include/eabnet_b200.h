@@ -180,6 +180,11 @@ EAB_API int    eab_enhance_postnet(eab_model* eabnet, eab_model* gagnet, int ref
  * Half the H2D bytes of eab_enhance_host; the library keeps its own device scratch; synchronises before returning. */
 EAB_API int    eab_enhance_host_pcm16(eab_model* eabnet, eab_model* gagnet, int ref_mic, const int16_t* pcm_host,
                               const int* mic_order, int16_t* enhanced_pcm_host, int B, int L, void* stream);
+/* Dataset-scale form on the PCM wire format: eab_enhance_host_batches with int16 batches in and out (110 MB instead of 221 MB
+ * of H2D per 64 x 6 s batch); the conversions are fused into the STFT's operand staging and the iSTFT's store, the uploads /
+ * downloads of neighbouring batches overlap compute and every slot's step is replayed from a CUDA graph, exactly as there. */
+EAB_API int    eab_enhance_host_batches_pcm16(eab_model* m, const int16_t* const* pcm_host, const int* mic_order,
+                                      int16_t* const* enhanced_pcm_host, int n_batches, int B, int L, void* stream);
 
 /* Introspection used by tests and bench: number of kernels launched by the last forward/enhance call, and a
  * copy of a named intermediate of the last eab_forward ("en.0".."en.4", "tcm", "de.0".."de.3", "embed",
@@ -188,16 +193,34 @@ EAB_API int    eab_enhance_host_pcm16(eab_model* eabnet, eab_model* gagnet, int 
 EAB_API int     eab_last_launch_count(const eab_model* m);
 EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, int64_t capacity, void* stream);
 
-/* Precision / kernel-selection knobs of the sm_100a path (defaults in parentheses):
- *   "umma" (1)        tcgen05 implicit-GEMM kernel for every eligible conv layer; 0 = fp32 CUDA-core kernel only
- *   "enc_passes" (3)  1 = single-pass TF32, 3 = 3xTF32 split (fp32-grade) in the encoder convs
- *   "dec_passes" (1)  same for the decoder convs */
+/* Precision / kernel-selection knobs of the sm_100a path, per model (defaults in parentheses).  Tensor-core operands are fp16:
+ * "1 pass" = operands rounded to fp16 (the 10-bit mantissa of TF32), fp32 accumulation; "3 passes" = hi/lo fp16 split of both
+ * operands, hi*hi + lo*hi + hi*lo (~22 mantissa bits, fp32-grade).  The splits are unscaled: post-normalisation activations and
+ * weights are O(1e-3 .. 1e2); magnitudes below fp16's subnormal step (6e-8) lose their lo part and magnitudes above 65504 would
+ * overflow - neither occurs behind a normalisation layer, and the STFT input is audio in [-1, 1].
+ *   "umma" (1)          tcgen05 kernels for every eligible layer; 0 = fp32 CUDA-core kernels only
+ *   "enc_passes" (3)    encoder 2-D convs incl. their inner U-Nets ("inner_passes" sets the inner U-Nets alone)
+ *   "dec_passes" (1)    decoder 2-D convs            "first_passes" (3)  the first gated conv (2M input channels)
+ *   "raw" (1)           conv_raw_kernel: the layer's raw fp32 input tiles are normalised in shared memory (no stage pass);
+ *                       0 = stage_kernel + conv_tma_kernel (fp16 operand planes staged through HBM)
+ *   "staged" (1)        the stage + conv_tma pair for what conv_raw does not take; 0 = per-tap gather kernel (conv_umma)
+ *   "lazy" (1)          a module's residual sum x0 + y is summed by its consumers, never materialised
+ *   "tcm_chain" (1)     a group of squeezed TCMs as one persistent launch; 0 = three GEMM launches per TCM
+ *   "fused_head" (1)    w_dnn + filter-and-sum as one kernel     "head_w_tap" (0)  ... which also writes the beam weights (tap "w")
+ *   "stft_tc" (1)       STFT as a tensor-core DFT-GEMM; 0 = fp32 CUDA-core kernel.  PROCESS-WIDE switch (eab_stft has no handle)
+ *   "host_graph" (1) / "dual_stream" (1)   eab_enhance_host_batches: replay each slot's step from a CUDA graph / alternate
+ *                       batches on two compute streams
+ *   "stream_tcm" (1)    streaming: the TCM stack as one launch
+ *   "raw_grid" (0), "dbg_launch" (-1), "lstm_exp" (0)   diagnostics (grid cap of conv_raw so that small inputs walk many tiles per
+ *                       CTA; which tensor-core conv launch fills eab_debug_counters; LSTM ablation switches of debug builds)
+ * Changing an option invalidates the CUDA graphs eab_enhance_host_batches has captured (they are re-captured on next use). */
 EAB_API int     eab_set_option(eab_model* m, const char* name, int value);
 /* diagnostics: cycle counters of CTA 0 of the tcgen05 conv launch selected with option "dbg_launch" */
 EAB_API int     eab_debug_counters(eab_model* m, unsigned long long* out16);
 
 /* Per-launch CUDA-event timing of the calling thread's launches, aggregated per kernel family; the summary is a
- * JSON array [{"kernel","launches","ms","flops","bytes"}] with ALGORITHMIC flops/bytes, written to
+ * JSON array [{"kernel","launches","ms","flops","bytes","moved_bytes"}] - ALGORITHMIC flops/bytes in SURVEY.md 8(d)'s sense
+ * (every fused layer reads its fp32 inputs once and writes its output once) and the bytes the launches really request -, written to
  * `buf` (returns its length, or -1).  Reading the summary synchronises the device and clears the records. */
 EAB_API int     eab_profile_enable(eab_model* m, int on);
 EAB_API int64_t eab_profile_summary(eab_model* m, char* buf, int64_t capacity);
