@@ -44,6 +44,8 @@ SYMBOLS = {
     "eab_stream_reset": (C.c_int, [_P, _P, C.c_size_t, C.c_int, _P]),
     "eab_stream_step": (C.c_int, [_P, _P, C.c_size_t, _F, _F, C.c_int, _P]),
     "eab_stream_step_spec": (C.c_int, [_P, _P, C.c_size_t, _F, _F, C.c_int, _P]),
+    "eab_stream_step_pcm16": (C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
+    "eab_stream_reset_one": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int, _P]),
     "eab_gag_create": (C.c_int, [C.POINTER(EabGagConfig), C.POINTER(_P)]),
     "eab_gag_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "eab_gag_forward": (C.c_int, [_P, _F, C.POINTER(C.c_int64 * 4), _F, _F, C.c_int, C.c_int, _P, C.c_size_t, _P]),

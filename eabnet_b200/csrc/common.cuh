@@ -178,6 +178,8 @@ struct ConvArgs {
     const float* stat_alpha[2];  // if set, statistics are taken of PReLU(out, alpha) (TCM convention)
     int nstats;
     const int* step;             // streaming: device pointer to the absolute frame index (null = offline)
+    const int* start;            // streaming: [streams] absolute frame index at which each stream (re)started: frames before it
+                                 // read as the literal zeros of the causal padding (eab_stream_reset_one); null = all zero
     int out_RT, resid_RT;        // streaming: ring sizes of out / resid
 };
 int launch_conv(const ConvArgs& a, cudaStream_t st);
@@ -375,6 +377,7 @@ struct TcmStreamArgs {
     const float* blob;
     int ntcm, p, kd, S;
     const int* step;
+    const int* start;                                    // [S] first frame of each stream (see ConvArgs::start), or null
     float* act_base;
     const float* x;  int x_RT;                           // [S][x_RT][256] residual stream entering the stack
     float* out;      int out_RT;                         // [S][out_RT][256] sum of the group outputs
@@ -423,6 +426,7 @@ struct TcmChainArgs {
     int B, T, tiles_per_b;
     int instance_norm;
     int gated;                           // two dilated branches, value * sigmoid(gate)
+    int no_cluster;                      // force the cooperative (grid-barrier) form (option tcm_chain = 2; diagnostics / tests)
     float inv_count;                     // 1 / T
     unsigned long long* dbg;             // optional [16] cycle counters of CTA 0 (diagnostics), else null
     TcmChainLayer L[kMaxChainLayers];    // [chain][layer]
@@ -463,9 +467,13 @@ int launch_stft_pcm16(const short* pcm, const int* order, float* spec, int B, in
 int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st, short* wave16 = nullptr);
 // streaming front/back end (stft.cu): one hop in -> spectrum frame *step into a ring; spectrum frame -> one hop out
 // (delayed by one hop: overlap-add needs the next frame), carried state in prev_hop [S][M][160] / tail [S][160]
-int launch_stft_frame(const float* hop, float* prev_hop, float* spec_ring, int spec_RT, const int* step, int S, int M,
-                      cudaStream_t st);
-int launch_istft_frame(const float* frame, float* tail, float* hop_out, const int* step, int S, cudaStream_t st);
+// hop16 / hop_out16 non-null: the hop arrives / leaves as 16-bit PCM (sample / 32768 in, int16(clip(y) * 32767) out);
+// start: [S] first frame of each stream (eab_stream_reset_one), or null
+int launch_stft_frame(const float* hop, const short* hop16, float* prev_hop, float* spec_ring, int spec_RT, const int* step,
+                      const int* start, int S, int M, cudaStream_t st);
+int launch_istft_frame(const float* frame, float* tail, float* hop_out, short* hop_out16, const int* step, const int* start, int S,
+                       cudaStream_t st);
+int launch_stream_restart(int* start, const int* step, int idx, cudaStream_t st);       // start[idx] = *step
 int launch_step_advance(int* step, cudaStream_t st);
 
 }  // namespace eab

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_generic_kernel(const ConvArgs a
             bool tok;
             if (streaming) {
                 const int n = step - dtv;
-                tok = n >= 0 && n <= step;
+                tok = n >= (a.start ? __ldg(a.start + lt[i]) : 0) && n <= step;       // lt = stream index when streaming
                 frame = (size_t)lt[i] * src.RT + ring_slot(n, src.RT);
             } else {
                 const int tt = lt[i] - dtv;
@@ -319,12 +319,7 @@ int launch_inst(const ConvArgs& a, cudaStream_t st) {
     size_t smem = (size_t)(2 * KC * TM + 2 * KC * N + 3 * Ctot) * sizeof(float);
     const size_t red = (size_t)8 * 2 * N * 2 * sizeof(float);
     if (smem < red) smem = red;
-    static size_t configured = 0;
-    if (smem > configured) {
-        EAB_CUDA(cudaFuncSetAttribute(conv_generic_kernel<NV, RPT, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        configured = smem;
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_generic_kernel<NV, RPT, GATED>), (int)smem));
     const bool streaming = a.step != nullptr;
     const int rows = streaming ? a.B * a.E : a.T * a.E;
     dim3 grid((rows + TM - 1) / TM, streaming ? 1 : a.B);

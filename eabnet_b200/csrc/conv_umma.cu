@@ -460,18 +460,10 @@ int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
     if (a.B <= 0 || a.T <= 0 || a.E <= 0) return 0;
     const Smem sp = smem_plan(a.N, a.Cout, a.ncoef);
     if (sp.nstages < 2) return fail("conv_umma: not enough shared memory for two stages");
-    static int configured = 0;
-    if (sp.total > configured) {
-        EAB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-        EAB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-        configured = sp.total;
-    }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        EAB_CUDA(cudaGetDevice(&dev));
-        EAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<false>), sp.total));
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<true>), sp.total));
+    int sms = 0;
+    EAB_TRY(device_sm_count(&sms));
     const long long ntiles = (long long)a.B * a.tiles_per_b;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     const double pos = (double)a.B * a.T * a.E;

@@ -271,17 +271,9 @@ bool head_fused_supported(const HeadArgs& a) {
 
 int launch_head_fused(const HeadArgs& a, cudaStream_t st) {
     if (!head_fused_supported(a)) return fail("head_fused: unsupported shape");
-    static bool configured = false;
-    if (!configured) {
-        EAB_CUDA(cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        EAB_CUDA(cudaGetDevice(&dev));
-        EAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(head_fused_kernel), SMEM_BYTES));
+    int sms = 0;
+    EAB_TRY(device_sm_count(&sms));
     const long long ntiles = (a.rows + TM - 1) / TM;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     const double rows = (double)a.rows;

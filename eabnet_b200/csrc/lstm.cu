@@ -230,11 +230,7 @@ int launch_inst(const LstmArgs& a, cudaStream_t st) {
     constexpr int S = 4 * SPT;
     constexpr int SP = ((SPT + 3) / 4) * 4;
     const size_t smem = ((size_t)(E * H + H * H) * 4 + (size_t)(E + H) * 4 * SP + 2 * 3 * E + 2 * E) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        EAB_CUDA(cudaFuncSetAttribute(lstm_kernel<SPT, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(lstm_kernel<SPT, E>), (int)smem));
     const int NQ = a.B * a.F;
     ProfScope ps("lstm", 2.0 * NQ * a.T * (E + H) * 4.0 * H, 4.0 * NQ * a.T * (E + H), st);
     EAB_CUDA(launch_k(lstm_kernel<SPT, E>, dim3((NQ + S - 1) / S), dim3(256), smem, st, a));

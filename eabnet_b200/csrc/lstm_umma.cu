@@ -375,11 +375,7 @@ bool lstm_umma_supported(const LstmArgs& a) { return a.E == 64 && a.F >= RPC && 
 
 int launch_lstm_umma(const LstmArgs& a, cudaStream_t st) {
     if (!lstm_umma_supported(a)) return fail("lstm_umma: unsupported shape");
-    static bool configured = false;
-    if (!configured) {
-        EAB_CUDA(cudaFuncSetAttribute(lstm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(lstm_umma_kernel), SMEM_BYTES));
     const int NQ = a.B * a.F;
     ProfScope ps("lstm_umma", 2.0 * NQ * a.T * (64 + H) * 4.0 * H, 4.0 * NQ * a.T * (64 + H), st);
     EAB_CUDA(launch_k(lstm_umma_kernel, dim3((NQ + RPC - 1) / RPC), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a));

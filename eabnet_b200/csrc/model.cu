@@ -272,7 +272,7 @@ struct eab_model {
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
-    int opt_tcm_chain = 1;        // TCM stacks as persistent cooperative launches (tcm_chain.cu): a GaGNet module's three stacks / an EaBNet group
+    int opt_tcm_chain = 1;        // TCM stacks as single launches (tcm_chain.cu): a GaGNet module's three stacks / an EaBNet group; 2: one chain per launch, 3: cooperative grid-barrier form
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
     int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
     int umma_launch_idx = 0;
@@ -1019,10 +1019,12 @@ struct Ctx {
     // state blob (same allocation order every step => same addresses), nothing is reused, tensor-core kernels are off
     bool streaming = false;
     const int* step = nullptr;
+    const int* start = nullptr;   // [streams] first absolute frame of each stream (eab_stream_reset_one)
     int next_RT = 0;          // ring size of the next allocation (0 = the default of 2: current + previous frame)
     int last_RT = 0;          // ring size of the last allocation (0 offline)
     bool tensor_ok() const { return m->opt_umma && !streaming; }
     std::vector<TcmStreamDesc>* tcm_desc = nullptr;     // planning pass of eab_stream_reset: receives the descriptors
+    std::vector<std::pair<size_t, size_t>>* per_stream = nullptr;      // planning pass: carried per-stream state to zero on a restart
     const TcmStreamDesc* tcm_desc_dev = nullptr;        // step: the table inside the state blob
 
     size_t act_peak = 0;
@@ -1314,7 +1316,7 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
         memset(&a, 0, sizeof(a));
         a.nsrc = nsrc;
         for (int i = 0; i < nsrc; ++i) { a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf; a.src[i].RT = srcs[i].RT; }
-        a.step = cx.step; a.out_RT = out->RT;
+        a.step = cx.step; a.start = cx.start; a.out_RT = out->RT;
         a.B = cx.B; a.T = cx.T; a.Fin = Fin; a.Fout = Fout;
         if (L.deconv) { a.in_stride = 1; a.out_stride = 2; a.out_off = v; a.E = (Fout - v + 1) / 2; }
         else          { a.in_stride = 2; a.out_stride = 1; a.out_off = 0; a.E = Fout; }
@@ -1474,7 +1476,7 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
     memset(&a, 0, sizeof(a));
     a.nsrc = nsrc;
     for (int i = 0; i < nsrc; ++i) { a.src[i].x = srcs[i].data; a.src[i].C = srcs[i].C; a.src[i].xf = srcs[i].xf; a.src[i].RT = srcs[i].RT; }
-    a.step = cx.step; a.out_RT = out->RT; a.resid_RT = resid_RT;
+    a.step = cx.step; a.start = cx.start; a.out_RT = out->RT; a.resid_RT = resid_RT;
     a.B = cx.B; a.T = cx.T; a.Fin = srcs[0].F; a.Fout = srcs[0].F; a.E = srcs[0].F;
     a.in_stride = 1; a.out_stride = 1; a.out_off = 0;
     a.ntaps = ntaps;
@@ -1618,7 +1620,7 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
             memset(&a, 0, sizeof(a));
             a.desc = cx.tcm_desc_dev; a.blob = m->blob;
             a.ntcm = (int)m->tcms.size(); a.p = c.p; a.kd = c.kd1; a.S = cx.B;
-            a.step = cx.step; a.act_base = reinterpret_cast<float*>(cx.base);
+            a.step = cx.step; a.start = cx.start; a.act_base = reinterpret_cast<float*>(cx.base);
             a.x = r.data; a.x_RT = r.RT; a.out = acc.data; a.out_RT = acc.RT;
             EAB_TRY(launch_tcm_stream(a, cx.st));
         }
@@ -1683,7 +1685,10 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
             h[l].RT = cx.last_RT;
             float* hc_state[2] = {nullptr, nullptr};
             if (cx.streaming)
-                for (int k = 0; k < 2; ++k) { cx.next_RT = 1; hc_state[k] = cx.alloc_act((size_t)cx.B * c.n_freq * 64); }
+                for (int k = 0; k < 2; ++k) {
+                    cx.next_RT = 1; hc_state[k] = cx.alloc_act((size_t)cx.B * c.n_freq * 64);
+                    if (cx.per_stream) cx.per_stream->push_back({(size_t)(reinterpret_cast<char*>(hc_state[k]) - cx.base), (size_t)c.n_freq * 64 * sizeof(float)});
+                }
             if (!cx.dry) {
                 LstmArgs a;
                 memset(&a, 0, sizeof(a));
@@ -1859,6 +1864,7 @@ int run_tcm_chains(Ctx& cx, const ChainRef* chains, int nch, const Act* ins, Act
     a.gated = chains[0].l[0].single ? 0 : 1;
     a.instance_norm = in_stats ? 1 : 0; a.inv_count = 1.f / (float)cx.T;
     if (cx.m->opt_dbg_launch == -200 && cx.m->dbg_buf) a.dbg = cx.m->dbg_buf;
+    a.no_cluster = cx.m->opt_tcm_chain == 3 ? 1 : 0;
     if (cx.m->opt_tcm_chain == 2 && nch > 1) {
         // one chain per launch: a single chain's residual stream + scratch (59 MB at 64 x 6 s) stays in the 126 MB L2
         for (int i = 0; i < nch; ++i) {
@@ -1986,8 +1992,9 @@ int plan(eab_model* m, int B, int T, size_t* stats_bytes, size_t* total_bytes) {
 // State blob layout (device, caller-owned): [0,256) absolute frame counter | carried hop [S][M][160] | iSTFT tail
 // [S][160] | spectrum ring [S][2][F][M][2] | output frame [S][2][F] | activation rings + LSTM state (run_forward order)
 struct StreamLayout {
-    size_t off_desc, off_prev, off_tail, off_spec, off_out, off_act, total;
+    size_t off_start, off_desc, off_prev, off_tail, off_spec, off_out, off_act, total;
     std::vector<TcmStreamDesc> descs;
+    std::vector<std::pair<size_t, size_t>> per_stream;      // (offset from off_act, bytes per stream) of the carried LSTM (h, c)
 };
 inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -1998,6 +2005,7 @@ int stream_layout(eab_model* m, int S, StreamLayout* L) {
     if (c.norm_type != 1) return fail("streaming needs norm_type='BN': InstanceNorm statistics span the whole utterance (EaBNet.py:684-686)");
     if (!c.is_causal) return fail("streaming needs is_causal=True");
     size_t o = 256;
+    L->off_start = o; o += up256((size_t)S * sizeof(int));
     L->off_desc = o; o += up256(m->tcms.size() * sizeof(TcmStreamDesc));
     L->off_prev = o; o += up256((size_t)S * c.M * 160 * sizeof(float));
     L->off_tail = o; o += up256((size_t)S * 160 * sizeof(float));
@@ -2007,6 +2015,7 @@ int stream_layout(eab_model* m, int S, StreamLayout* L) {
     Ctx cx;
     cx.m = m; cx.dry = true; cx.base = nullptr; cx.B = S; cx.T = 1; cx.st = nullptr; cx.streaming = true;
     cx.tcm_desc = &L->descs;
+    cx.per_stream = &L->per_stream;
     EAB_TRY(run_forward(cx, nullptr, nullptr));
     if (cx.stats_off != 0) return fail("internal: streaming plan allocated statistics");
     L->total = o + cx.act_peak;
@@ -2018,6 +2027,7 @@ int stream_forward(eab_model* m, char* state, const StreamLayout& L, int S, cuda
     Ctx cx;
     cx.m = m; cx.dry = false; cx.base = state + L.off_act; cx.B = S; cx.T = 1; cx.st = st;
     cx.streaming = true; cx.step = reinterpret_cast<const int*>(state);
+    cx.start = reinterpret_cast<const int*>(state + L.off_start);
     cx.tcm_desc_dev = reinterpret_cast<const TcmStreamDesc*>(state + L.off_desc);
     return run_forward(cx, reinterpret_cast<const float*>(state + L.off_spec), reinterpret_cast<float*>(state + L.off_out));
 }
@@ -2517,25 +2527,54 @@ int eab_stream_step_spec(eab_model* m, void* state, size_t state_bytes, const fl
     return 0;
 }
 
-int eab_stream_step(eab_model* m, void* state, size_t state_bytes, const float* hop, float* enhanced_hop, int n_streams,
-                    void* stream) {
+static int stream_step_any(eab_model* m, void* state, size_t state_bytes, const float* hop, const int16_t* hop16, float* enhanced_hop,
+                           int16_t* enhanced16, int n_streams, void* stream) {
     StreamLayout L;
     EAB_TRY(stream_check(m, state, state_bytes, n_streams, &L));
-    if (!hop || !enhanced_hop) return fail("eab_stream_step: null argument");
+    if ((!hop && !hop16) || (!enhanced_hop && !enhanced16)) return fail("eab_stream_step: null argument");
     const eab_config& c = m->cfg;
     if (c.topo_type == 1) return fail("eab_stream_step: the 'miso' topology returns [B,2,T], which has no iSTFT");
     if (c.n_freq != 161) return fail("eab_stream_step: the 320-point STFT gives 161 bins");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* p = static_cast<char*>(state);
     int* step = reinterpret_cast<int*>(p);
+    const int* start = reinterpret_cast<const int*>(p + L.off_start);
     reset_launch_count();
-    EAB_TRY(launch_stft_frame(hop, reinterpret_cast<float*>(p + L.off_prev), reinterpret_cast<float*>(p + L.off_spec), 2, step,
-                              n_streams, c.M, st));
+    EAB_TRY(launch_stft_frame(hop, hop16, reinterpret_cast<float*>(p + L.off_prev), reinterpret_cast<float*>(p + L.off_spec), 2, step,
+                              start, n_streams, c.M, st));
     EAB_TRY(stream_forward(m, p, L, n_streams, st));
     EAB_TRY(launch_istft_frame(reinterpret_cast<const float*>(p + L.off_out), reinterpret_cast<float*>(p + L.off_tail),
-                               enhanced_hop, step, n_streams, st));
+                               enhanced_hop, enhanced16, step, start, n_streams, st));
     EAB_TRY(launch_step_advance(step, st));
     m->last_launches = launch_count();
+    return 0;
+}
+
+int eab_stream_step(eab_model* m, void* state, size_t state_bytes, const float* hop, float* enhanced_hop, int n_streams,
+                    void* stream) {
+    if (!hop || !enhanced_hop) return fail("eab_stream_step: null argument");
+    return stream_step_any(m, state, state_bytes, hop, nullptr, enhanced_hop, nullptr, n_streams, stream);
+}
+
+// the same step on the 16-bit PCM wire format: hop [S][M][160] int16 (sample / 32768), enhanced hop [S][160] int16
+int eab_stream_step_pcm16(eab_model* m, void* state, size_t state_bytes, const int16_t* hop, int16_t* enhanced_hop, int n_streams,
+                          void* stream) {
+    if (!hop || !enhanced_hop) return fail("eab_stream_step_pcm16: null argument");
+    return stream_step_any(m, state, state_bytes, nullptr, hop, nullptr, enhanced_hop, n_streams, stream);
+}
+
+// One stream leaves and a new one joins in its slot: from the next step on stream `idx` starts over (its frame 0), the other
+// streams carry on untouched.  Its history rings need no clearing: every kernel treats frames before the stream's start index
+// as the literal zeros of the causal padding; the carried LSTM state is zeroed.  Stream-ordered, no synchronisation.
+int eab_stream_reset_one(eab_model* m, void* state, size_t state_bytes, int n_streams, int idx, void* stream) {
+    StreamLayout L;
+    EAB_TRY(stream_check(m, state, state_bytes, n_streams, &L));
+    if (idx < 0 || idx >= n_streams) return fail("eab_stream_reset_one: stream index out of range");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* p = static_cast<char*>(state);
+    EAB_TRY(launch_stream_restart(reinterpret_cast<int*>(p + L.off_start), reinterpret_cast<const int*>(p), idx, st));
+    for (const auto& ps : L.per_stream)
+        EAB_CUDA(cudaMemsetAsync(p + L.off_act + ps.first + (size_t)idx * ps.second, 0, ps.second, st));
     return 0;
 }
 

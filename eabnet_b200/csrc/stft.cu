@@ -273,10 +273,13 @@ constexpr size_t kSmemBytes = (size_t)(2 * NF * RB + RB * NCOL) * sizeof(float);
 // Frame n of the centred STFT covers samples [160 n - 160, 160 n + 160): the previous hop (carried) and the new one.
 // Frame 0's first half is the reflection of hop 0 (sample 160 - k at position k; position 0 is multiplied by
 // hann[0] = 0, so the one sample that would come from hop 1 never matters).  grid (ceil(S / SG)), rows = (stream, mic).
-__global__ void __launch_bounds__(THREADS) stft_frame_kernel(const float* __restrict__ hop, float* __restrict__ prev,
-                                                             float* __restrict__ spec, int spec_RT,
-                                                             const int* __restrict__ step_p, const float* __restrict__ tab,
-                                                             const float* __restrict__ win, int S, int M, int SG) {
+// hop16 != null: the hop is 16-bit PCM (sample / 32768).  start[s] = absolute frame at which stream s (re)started: that
+// frame is the stream's frame 0 (reflection instead of the carried hop).
+__global__ void __launch_bounds__(THREADS) stft_frame_kernel(const float* __restrict__ hop, const short* __restrict__ hop16,
+                                                             float* __restrict__ prev, float* __restrict__ spec, int spec_RT,
+                                                             const int* __restrict__ step_p, const int* __restrict__ start,
+                                                             const float* __restrict__ tab, const float* __restrict__ win, int S,
+                                                             int M, int SG) {
     extern __shared__ __align__(16) float dsm[];
     float* Aev = dsm;
     float* Aod = Aev + NF * RB;
@@ -290,13 +293,15 @@ __global__ void __launch_bounds__(THREADS) stft_frame_kernel(const float* __rest
         float ev = 0.f, od = 0.f;
         const int sl = r / M, m = r - sl * M;
         if (r < nrows && s0 + sl < S) {
-            const float* cur = hop + ((size_t)(s0 + sl) * M + m) * HOP;
-            const float* pv = prev + ((size_t)(s0 + sl) * M + m) * HOP;
+            const size_t cbase = ((size_t)(s0 + sl) * M + m) * HOP;
+            const float* pv = prev + cbase;
+            const bool first = step <= (start ? __ldg(start + s0 + sl) : 0);      // the stream's frame 0
+            auto cur = [&](int n) -> float { return hop16 ? (float)__ldg(hop16 + cbase + n) * (1.f / 32768.f) : __ldg(hop + cbase + n); };
             auto sample = [&](int n) -> float {
                 float x;
-                if (n >= HOP) x = __ldg(cur + n - HOP);
-                else if (step > 0) x = pv[n];
-                else x = n == 0 ? 0.f : __ldg(cur + HOP - n);
+                if (n >= HOP) x = cur(n - HOP);
+                else if (!first) x = pv[n];
+                else x = n == 0 ? 0.f : cur(HOP - n);
                 return x * __ldg(win + n);
             };
             const float g0 = sample(k);
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(THREADS) stft_frame_kernel(const float* __rest
         const int sl = r / M, m = r - sl * M;
         if (s0 + sl < S) {
             const size_t o = ((size_t)(s0 + sl) * M + m) * HOP + n;
-            prev[o] = __ldg(hop + o);
+            prev[o] = hop16 ? (float)__ldg(hop16 + o) * (1.f / 32768.f) : __ldg(hop + o);
         }
     }
     if (col < NCOL) {
@@ -347,8 +352,11 @@ __global__ void __launch_bounds__(THREADS) stft_frame_kernel(const float* __rest
 
 // Spectrum frame n [S][2][161] -> windowed inverse DFT; output hop n-1 = (second half of frame n-1, carried in `tail`,
 // + first half of frame n) / envelope.  The first call (n == 0) emits zeros.  grid (ceil(S / RB)), rows = streams.
+// hop_out16 != null: the hop leaves as int16(clip(y, -1, 1) * 32767); start: see stft_frame_kernel (a stream's first frame emits
+// zeros: its overlap-add partner does not exist yet).
 __global__ void __launch_bounds__(THREADS) istft_frame_kernel(const float* __restrict__ frame, float* __restrict__ tail,
-                                                              float* __restrict__ hop_out, const int* __restrict__ step_p,
+                                                              float* __restrict__ hop_out, short* __restrict__ hop_out16,
+                                                              const int* __restrict__ step_p, const int* __restrict__ start,
                                                               const float* __restrict__ tab, const float* __restrict__ win,
                                                               const float* __restrict__ ienv, int S) {
     extern __shared__ __align__(16) float dsm[];
@@ -383,13 +391,19 @@ __global__ void __launch_bounds__(THREADS) istft_frame_kernel(const float* __res
         const float first = P[n] - P[NF + n];                       // s[n]
         const float second = P[HOP - n] + P[NF + HOP - n];          // s[n + 160]
         const size_t o = (size_t)(s0 + r) * HOP + n;
-        hop_out[o] = step > 0 ? (tail[o] + __ldg(win + n) * first) * __ldg(ienv + n) : 0.f;
+        const bool begun = step > (start ? __ldg(start + s0 + r) : 0);
+        const float y = begun ? (tail[o] + __ldg(win + n) * first) * __ldg(ienv + n) : 0.f;
+        if (hop_out16) hop_out16[o] = (short)(int)(fminf(fmaxf(y, -1.f), 1.f) * 32767.f);
+        else hop_out[o] = y;
         tail[o] = __ldg(win + n + HOP) * second;
     }
 }
 
 __global__ void step_advance_kernel(int* step) {
     if (threadIdx.x == 0) *step += 1;
+}
+__global__ void stream_restart_kernel(int* start, const int* step, int idx) {
+    if (threadIdx.x == 0) start[idx] = *step;
 }
 
 }  // namespace
@@ -506,12 +520,8 @@ int launch_stft(const float* wave, float* spec, int B, int M, int L, cudaStream_
     EAB_TRY(get_tables(&t));
     const int T = 1 + L / HOP;
     if (g_stft_tc) { PcmSrc none; memset(&none, 0, sizeof(none)); return launch_stft_tc(t, wave, none, spec, B, M, L, T, st, scratch, scratch_bytes); }
-    static bool configured = false;
-    if (!configured) {
-        EAB_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        EAB_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        configured = true;
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(stft_kernel), (int)kSmemBytes));
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(istft_kernel), (int)kSmemBytes));
     ProfScope ps("stft", 2.0 * NF * NCOL * (double)B * M * T, 4.0 * ((double)B * M * L + (double)B * T * NF * M * 2), st);
     EAB_CUDA(launch_k(stft_kernel, dim3((T + FR - 1) / FR, B), dim3(THREADS), kSmemBytes, st, wave, spec, (const float*)t->fwd, (const float*)t->win, B, M, L, T));
     EAB_LAUNCH_CHECK("stft_kernel");
@@ -536,38 +546,41 @@ int launch_stft_pcm16(const short* pcm, const int* order, float* spec, int B, in
 }
 
 static int configure_smem() {
-    static bool configured = false;
-    if (!configured) {
-        EAB_CUDA(cudaFuncSetAttribute(stft_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        EAB_CUDA(cudaFuncSetAttribute(istft_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        configured = true;
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(stft_frame_kernel), (int)kSmemBytes));
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(istft_frame_kernel), (int)kSmemBytes));
     return 0;
 }
 
-int launch_stft_frame(const float* hop, float* prev_hop, float* spec_ring, int spec_RT, const int* step, int S, int M,
-                      cudaStream_t st) {
+int launch_stft_frame(const float* hop, const short* hop16, float* prev_hop, float* spec_ring, int spec_RT, const int* step,
+                      const int* start, int S, int M, cudaStream_t st) {
     if (S <= 0 || M <= 0 || M > RB) return fail("stft_frame: bad shape (at most 24 microphones)");
     Tables* t;
     EAB_TRY(get_tables(&t));
     EAB_TRY(configure_smem());
     const int SG = RB / M;
     ProfScope ps("stft_frame", 2.0 * NF * NCOL * (double)S * M, 4.0 * ((double)S * M * HOP * 3 + (double)S * NF * M * 2), st);
-    EAB_CUDA(launch_k(stft_frame_kernel, dim3((S + SG - 1) / SG), dim3(THREADS), kSmemBytes, st, hop, prev_hop, spec_ring,
-                      spec_RT, step, (const float*)t->fwd, (const float*)t->win, S, M, SG));
+    EAB_CUDA(launch_k(stft_frame_kernel, dim3((S + SG - 1) / SG), dim3(THREADS), kSmemBytes, st, hop, hop16, prev_hop, spec_ring,
+                      spec_RT, step, start, (const float*)t->fwd, (const float*)t->win, S, M, SG));
     EAB_LAUNCH_CHECK("stft_frame_kernel");
     return 0;
 }
 
-int launch_istft_frame(const float* frame, float* tail, float* hop_out, const int* step, int S, cudaStream_t st) {
+int launch_istft_frame(const float* frame, float* tail, float* hop_out, short* hop_out16, const int* step, const int* start, int S,
+                       cudaStream_t st) {
     if (S <= 0) return fail("istft_frame: bad shape");
     Tables* t;
     EAB_TRY(get_tables(&t));
     EAB_TRY(configure_smem());
     ProfScope ps("istft_frame", 2.0 * NF * NCOL * (double)S, 4.0 * ((double)S * 2 * NF + (double)S * HOP * 3), st);
-    EAB_CUDA(launch_k(istft_frame_kernel, dim3((S + RB - 1) / RB), dim3(THREADS), kSmemBytes, st, frame, tail, hop_out, step,
+    EAB_CUDA(launch_k(istft_frame_kernel, dim3((S + RB - 1) / RB), dim3(THREADS), kSmemBytes, st, frame, tail, hop_out, hop_out16, step, start,
                       (const float*)t->inv, (const float*)t->win, (const float*)t->ienv, S));
     EAB_LAUNCH_CHECK("istft_frame_kernel");
+    return 0;
+}
+
+int launch_stream_restart(int* start, const int* step, int idx, cudaStream_t st) {
+    EAB_CUDA(launch_k(stream_restart_kernel, dim3(1), dim3(32), (size_t)0, st, start, step, idx));
+    EAB_LAUNCH_CHECK("stream_restart_kernel");
     return 0;
 }
 
@@ -581,12 +594,8 @@ int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st, 
     if (T < 2) return fail("istft: need at least 2 frames");
     Tables* t;
     EAB_TRY(get_tables(&t));
-    static bool configured = false;
-    if (!configured) {
-        EAB_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        EAB_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        configured = true;
-    }
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(stft_kernel), (int)kSmemBytes));
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(istft_kernel), (int)kSmemBytes));
     ProfScope ps("istft", 2.0 * NF * NCOL * (double)B * T, 4.0 * ((double)B * 2 * T * NF + (double)B * HOP * (T - 1)), st);
     EAB_CUDA(launch_k(istft_kernel, dim3((T - 1 + IFR - 2) / (IFR - 1), B), dim3(THREADS), kSmemBytes, st, spec, wave, wave16, (const float*)t->inv, (const float*)t->win, (const float*)t->ienv, B, T));
     EAB_LAUNCH_CHECK("istft_kernel");

@@ -43,7 +43,7 @@ constexpr int W_BYTES = 64 * 1024;             // phase A: 4 slabs x (hi 8 KB | 
 constexpr int W_HALF = W_BYTES / 2;
 // 194.3 KB: stays under the 196 KB shared-memory carve-out step, which leaves the L1 (register spills, weights) its ~60 KB;
 // a version with 5 KB more shared memory dropped to the next step and ran 25 % slower
-constexpr int SMEM_BYTES = A_BYTES + W_BYTES + (3 * 64 + 2 * 64) * 4 + 64 + 1024;
+constexpr int SMEM_BYTES = A_BYTES + W_BYTES + (3 * 64 + 2 * 64) * 4 + 128 + 1024;     // (10 mbarriers and the TMEM slot inside the 128)
 
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     __syncthreads();
@@ -102,7 +102,18 @@ __device__ __forceinline__ void store_part(uint8_t* unit, int row, int q, const 
     }
 }
 
-template <int KD, bool GATED>
+// InstanceNorm's statistics and the dilated halo couple the frames of ONE utterance only (EaBNet.py:554-571), so with
+// CLUSTER the launch is not cooperative: a thread-block cluster of ceil(T / 128) CTAs owns one (chain, utterance) unit, a
+// CTA one 128-frame tile of it for the whole chain, and the two synchronisations per layer are cluster barriers among those
+// few CTAs instead of barriers across the whole grid (measured on the grid-barrier form: 0.81 ms per 6-layer launch at
+// 6 % tensor-pipe and 3 % DRAM utilisation - barrier skew of 148 CTAs holding 2 or 3 tiles each).  The hardware schedules
+// the clusters as SMs free up.  T > 1024 (more than 8 tiles per utterance) keeps the cooperative form.
+__device__ __forceinline__ void cluster_barrier() {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int KD, bool GATED, bool CLUSTER>
 __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -111,10 +122,17 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
     float* coef = reinterpret_cast<float*>(Ws + W_BYTES);        // [3][64] scale, shift, PReLU slope of the consumer's transform
     float* coefR = coef + 3 * 64;                                // [2][64] scale, shift of the gate (right) branch (gated TCMs)
     uint64_t* bar = reinterpret_cast<uint64_t*>(coefR + 2 * 64);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    uint64_t* wbar = bar + 1;                                    // weight images have landed in Ws (bulk copies)
+    uint64_t* wfull = bar + 2;                                   // [4] gated phase B: weight ring slot filled / consumed
+    uint64_t* wempty = bar + 6;                                  // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 10);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (tid == 0) {
+        mbar_init(bar, 1); mbar_init(wbar, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+        fence_barrier_init();
+    }
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
@@ -123,11 +141,14 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
 
     const int tiles_per_chain = a.B * a.tiles_per_b;
     const int total = a.nchains * tiles_per_chain;
-    const int tile_begin = (int)((long long)total * blockIdx.x / gridDim.x);
-    const int tile_end = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+    // CLUSTER: one tile per CTA, the tiles_per_b CTAs of a cluster are the consecutive tiles of one (chain, utterance)
+    const int tile_begin = CLUSTER ? (int)blockIdx.x : (int)((long long)total * blockIdx.x / gridDim.x);
+    const int tile_end = CLUSTER ? (int)blockIdx.x + 1 : (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
     const bool in_stats = a.instance_norm != 0;
 
     uint32_t par = 0;                  // parity of the next completion of `bar`
+    uint32_t wpar = 0;                 // ... of `wbar`
+    uint32_t wf_par = 0, we_par = 0;   // ... of wfull[i] / wempty[i] (bit i; tracked by warp 0 only)
     unsigned bar_target = 0;
     // loader role: TPR threads per operand row (CPT channels of every slab each); epilogue role: thread = (TMEM lane = row,
     // column group cg of TPR)
@@ -166,11 +187,13 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
         }
     };
     auto wait_mma = [&]() { mbar_wait(bar, par); par ^= 1u; };
-    auto load_w = [&](const float* src, int dst_off, int bytes) {
-        const uint4* s = reinterpret_cast<const uint4*>(src);
-        uint4* d = reinterpret_cast<uint4*>(Ws + dst_off);
-        for (int i = tid; i < bytes / 16; i += NT) d[i] = __ldg(s + i);
-    };
+    // Weight images -> Ws as bulk copies issued by ONE thread (they complete on `wbar` while the other threads load and
+    // transform the operand rows): w_begin(total bytes), any number of w_copy, then w_wait() by everybody before the MMAs.
+    // (The first version copied them with per-thread loads: one exposed L2 round trip per image, 8 per round of phase B -
+    // 38 % of a layer's time in "B load + store".)  The caller guarantees that the MMAs that last read Ws have completed.
+    auto w_begin = [&](int bytes) { if (tid == 0) mbar_arrive_expect_tx(wbar, (uint32_t)bytes); };
+    auto w_copy = [&](const float* src, int dst_off, int bytes) { if (tid == 0) bulk_copy_g2s(Ws + dst_off, src, (uint32_t)bytes, wbar); };
+    auto w_wait = [&]() { mbar_wait_spin(wbar, wpar); wpar ^= 1u; };
     // per-channel transform of the consumer: PReLU(alpha) then x*s + h, (s, h) from instance statistics or precomputed
     auto coef_of = [&](const double* stats, int b, int c, unsigned off_sc, unsigned off_sh, float& s, float& h) {
         if (in_stats) {
@@ -309,20 +332,30 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
 #pragma unroll
                     for (int k = 0; k < CF4; ++k) xv[s][k] = ldcg4(xrow + s * 64 + k * 4);
             };
-            if (tile_begin < tile_end) fetch(tile_begin);
+            // (Tried in the cluster form: phase C's epilogue leaving the new x rows in As as the next layer's operand and
+            // starting its weight copies - bit-exact, "A load + store" 6.1k -> 2.5k cycles per layer, but the time reappeared in
+            // the waits of phases B and C: 1.90 ms either way.  What bounds a tile-phase is the L2 -> shared-memory latency of
+            // the 288 KB of weight images every CTA streams per layer.)
+            constexpr bool fused_in = false;
+            if (!fused_in && tile_begin < tile_end) fetch(tile_begin);
             for (int ti = tile_begin; ti < tile_end; ++ti) {
                 const TileId tl = tile_of(ti);
                 const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
-                if (loaded != tl.chain) {
-                    load_w(a.blob + L.win_hi, 0, 4 * 64 * 128);
-                    load_w(a.blob + L.win_lo, W_HALF, 4 * 64 * 128);
+                const bool neww = !fused_in && loaded != tl.chain;
+                if (neww) {
+                    w_begin(2 * 4 * 64 * 128);
+                    w_copy(a.blob + L.win_hi, 0, 4 * 64 * 128);
+                    w_copy(a.blob + L.win_lo, W_HALF, 4 * 64 * 128);
                     loaded = tl.chain;
                 }
+                if (!fused_in) {
 #pragma unroll
-                for (int s = 0; s < 4; ++s) store_part(As + s * A_UNIT, lrow, lq, *reinterpret_cast<const float(*)[CPT]>(&xv[s][0]));
+                    for (int s = 0; s < 4; ++s) store_part(As + s * A_UNIT, lrow, lq, *reinterpret_cast<const float(*)[CPT]>(&xv[s][0]));
+                }
+                if (neww || fused_in) w_wait();
                 tick(0);
                 issue(idesc64, 4, 64 * 128);
-                if (ti + 1 < tile_end) fetch(ti + 1);      // the next tile's rows: in flight under the MMAs and the epilogue
+                if (!fused_in && ti + 1 < tile_end) fetch(ti + 1);      // the next tile's rows: in flight under the MMAs and the epilogue
                 wait_mma();
                 tc_fence_after();
                 tick(1);
@@ -330,71 +363,124 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 tick(2);
             }
         }
-        grid_barrier(a.barrier, bar_target);
+        if (CLUSTER) cluster_barrier(); else grid_barrier(a.barrier, bar_target);
         tick(3);
         // ======================================================================= phase B: z = W_dil * norm(PReLU(y)) (dilated)
         if constexpr (GATED) {
             // two branches (EaBNet.py:554-566, 575): value = W_left * norm_l(PReLU_l(y)), gate = W_right * norm_r(PReLU_r(y)), both
-            // dilated; 2 KD (branch, tap) units of 32 KB operand + 16 KB weights each, staged in rounds of 4 units
-            constexpr int NU = 2 * KD, NR = (NU + 3) / 4;
-            float4 yv[4][CF4];
-            unsigned okmask = 0;
-            auto fetch = [&](int ti, int r) {
-                const TileId tl = tile_of(ti);
-                const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
-                const int t = tl.t0 + lrow;
-                okmask = 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int g = r * 4 + u;
-                    if (g < NU) {
-                        const int ts = t - L.dt[g % KD];
-                        if (t < a.T && ts >= 0 && ts < a.T) okmask |= 1u << u;
-                        const int tc = ts < 0 ? 0 : (ts >= a.T ? a.T - 1 : ts);
-                        const float* yrow = a.y[tl.chain] + ((size_t)tl.b * a.T + tc) * 64 + lq * CPT;
-#pragma unroll
-                        for (int q = 0; q < CF4; ++q) yv[u][q] = ldcg4(yrow + q * 4);
-                    }
-                }
-            };
-            if (tile_begin < tile_end) fetch(tile_begin, 0);
+            // dilated.  "Stage once, shift by descriptor": the tile's y rows plus the dilated halo (frames t0 - back ..
+            // t0 + 127 + fwd, at most 256 rows) are normalised ONCE per branch into a plane [hi | lo] in shared memory, and every
+            // one of the 2 KD (branch, tap) units is that plane viewed through a row-shifted UMMA descriptor.  (The first
+            // version re-staged the 128 operand rows of every unit: 10 transforms of the tile per layer instead of 2-4,
+            // 38 % of a layer's time.)  The units' weights (16 KB each) stream through a 4-slot ring of bulk copies that warp 0
+            // keeps three units ahead of its own MMAs.
+            constexpr int NU = 2 * KD;
             for (int ti = tile_begin; ti < tile_end; ++ti) {
                 const TileId tl = tile_of(ti);
                 const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
+                int back = 0, fwd = 0;
+#pragma unroll
+                for (int k = 0; k < KD; ++k) { back = max(back, (int)L.dt[k]); fwd = max(fwd, -(int)L.dt[k]); }
+                const int R = TM + back + fwd;                 // <= 256 (checked by the launcher)
+                const int PB = ((R + 7) & ~7) * 128;           // bytes of one plane image
+                // weights of the first four units: in flight under the transform
+                if (warp == 0) {
+#pragma unroll
+                    for (int g = 0; g < 4 && g < NU; ++g) {
+                        if (lane == 0) {
+                            const bool right = g >= KD;
+                            const int tap = g % KD;
+                            mbar_arrive_expect_tx(&wfull[g], 2 * 64 * 128);
+                            bulk_copy_g2s(Ws + g * 64 * 128, a.blob + (right ? L.wr_hi : L.wd_hi) + tap * (64 * 128 / 4), 64 * 128, &wfull[g]);
+                            bulk_copy_g2s(Ws + W_HALF + g * 64 * 128, a.blob + (right ? L.wr_lo : L.wd_lo) + tap * (64 * 128 / 4), 64 * 128, &wfull[g]);
+                        }
+                    }
+                }
                 load_coef(a.stats + L.st_d, tl.b, L.sc_d, L.sh_d, L.al_d);
                 load_coef_right(a.stats + L.st_r, tl.b, L.sc_r, L.sh_r);
                 __syncthreads();
+                {   // thread = (plane row, half of the 64 channels)
+                    const int rho = tid >> 1, half = tid & 1;
+                    if (rho < R) {
+                        const int t = tl.t0 - back + rho;
+                        const bool ok = t >= 0 && t < a.T;
+                        const int tc = t < 0 ? 0 : (t >= a.T ? a.T - 1 : t);
+                        const float* yrow = a.y[tl.chain] + ((size_t)tl.b * a.T + tc) * 64 + half * 32;
+                        float4 yv[8];
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    const unsigned okcur = okmask;
-                    if (r > 0) wait_mma();                 // the previous round's MMAs have read As / Ws
-                    unsigned dmask = 0, fmask = 0;
-                    int nun = 0;
+                        for (int q = 0; q < 8; ++q) yv[q] = ldcg4(yrow + q * 4);
+                        const float* alr = a.blob + L.al_r + half * 32;
+                        uint8_t* rowL = As + rho * 128;                       // plane (left, hi); lo at + PB
+                        uint8_t* rowR = As + 2 * PB + rho * 128;              // plane (right, hi)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int g = r * 4 + u;
-                        if (g < NU) {
-                            const bool right = g >= KD;
-                            const int tap = g % KD;
-                            load_w(a.blob + (right ? L.wr_hi : L.wd_hi) + tap * (64 * 128 / 4), u * 64 * 128, 64 * 128);
-                            load_w(a.blob + (right ? L.wr_lo : L.wd_lo) + tap * (64 * 128 / 4), W_HALF + u * 64 * 128, 64 * 128);
-                            float v[CPT];
+                        for (int k = 0; k < 4; ++k) {
+                            const float y8[8] = {yv[2 * k].x, yv[2 * k].y, yv[2 * k].z, yv[2 * k].w, yv[2 * k + 1].x, yv[2 * k + 1].y, yv[2 * k + 1].z, yv[2 * k + 1].w};
+                            float vl[8], vr[8];
 #pragma unroll
-                            for (int q = 0; q < CF4; ++q) *reinterpret_cast<float4*>(&v[q * 4]) = yv[u][q];
-                            if (right) transform_right(v, a.blob + L.al_r); else transform(v);
-                            const bool ok = (okcur >> u) & 1u;
-#pragma unroll
-                            for (int i = 0; i < CPT; ++i) v[i] = ok ? v[i] : 0.f;       // literal zeros AFTER the norm (EaBNet.py:557)
-                            store_part(As + u * A_UNIT, lrow, lq, v);
-                            if (right) dmask |= 1u << u;
-                            if (tap == 0) fmask |= 1u << u;
-                            ++nun;
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = half * 32 + k * 8 + i;
+                                // literal zeros AFTER the norm for frames outside the utterance (EaBNet.py:557)
+                                vl[i] = ok ? fmaf(prelu_f(y8[i], coef[128 + c]), coef[c], coef[64 + c]) : 0.f;
+                                vr[i] = ok ? fmaf(prelu_f(y8[i], __ldg(alr + k * 8 + i)), coefR[c], coefR[64 + c]) : 0.f;
+                            }
+                            const int off = ((half * 4 + k) ^ (rho & 7)) << 4;
+                            uint4 hi, lo;
+                            hi.x = pack_h2(vl[0], vl[1]); hi.y = pack_h2(vl[2], vl[3]); hi.z = pack_h2(vl[4], vl[5]); hi.w = pack_h2(vl[6], vl[7]);
+                            lo.x = pack_lo_h2(vl[0], vl[1], hi.x); lo.y = pack_lo_h2(vl[2], vl[3], hi.y);
+                            lo.z = pack_lo_h2(vl[4], vl[5], hi.z); lo.w = pack_lo_h2(vl[6], vl[7], hi.w);
+                            *reinterpret_cast<uint4*>(rowL + off) = hi;
+                            *reinterpret_cast<uint4*>(rowL + PB + off) = lo;
+                            hi.x = pack_h2(vr[0], vr[1]); hi.y = pack_h2(vr[2], vr[3]); hi.z = pack_h2(vr[4], vr[5]); hi.w = pack_h2(vr[6], vr[7]);
+                            lo.x = pack_lo_h2(vr[0], vr[1], hi.x); lo.y = pack_lo_h2(vr[2], vr[3], hi.y);
+                            lo.z = pack_lo_h2(vr[4], vr[5], hi.z); lo.w = pack_lo_h2(vr[6], vr[7], hi.w);
+                            *reinterpret_cast<uint4*>(rowR + off) = hi;
+                            *reinterpret_cast<uint4*>(rowR + PB + off) = lo;
                         }
                     }
-                    tick(4);
-                    issue(idesc64, nun, 64 * 128, dmask, fmask);
-                    if (r + 1 < NR) fetch(ti, r + 1);      // the next round's rows: in flight under the MMAs
-                    else if (ti + 1 < tile_end) fetch(ti + 1, 0);
+                }
+                tick(4);
+                fence_proxy_async();
+                __syncthreads();
+                if (warp == 0) {
+                    tc_fence_after();
+                    const uint32_t a0 = desc_lo(smem_u32(As)), w0 = desc_lo(smem_u32(Ws));
+#pragma unroll 1
+                    for (int g = 0; g < NU; ++g) {
+                        const int slot = g & 3;
+                        const bool right = g >= KD;
+                        const int tap = g % KD;
+                        mbar_wait_spin(&wfull[slot], (wf_par >> slot) & 1u);
+                        wf_par ^= 1u << slot;
+                        tc_fence_after();
+                        const uint32_t ah = a0 + (uint32_t)(((right ? 2 : 0) * PB + (back - (int)L.dt[tap]) * 128) >> 4), al = ah + (uint32_t)(PB >> 4);
+                        const uint32_t wh = w0 + (uint32_t)((slot * 64 * 128) >> 4), wl = wh + (W_HALF >> 4);
+                        const uint32_t d = tmem_base + (right ? 64u : 0u);             // value cols 0-63, gate cols 64-127
+                        umma_f16_lo_elect_x4(d, ah, wh, idesc64, tap == 0 ? 0u : 1u);
+                        umma_f16_lo_elect_x4(d, al, wh, idesc64, 1u);
+                        umma_f16_lo_elect_x4(d, ah, wl, idesc64, 1u);
+                        umma_commit_elect(&wempty[slot]);
+                        if (g >= 1 && g + 3 < NU) {            // unit g + 3 -> the slot unit g - 1 has just finished with
+                            const int ps = (g - 1) & 3, gn = g + 3;
+                            mbar_wait_spin(&wempty[ps], (we_par >> ps) & 1u);
+                            we_par ^= 1u << ps;
+                            if (lane == 0) {
+                                const bool rn = gn >= KD;
+                                const int tn = gn % KD;
+                                mbar_arrive_expect_tx(&wfull[ps], 2 * 64 * 128);
+                                bulk_copy_g2s(Ws + ps * 64 * 128, a.blob + (rn ? L.wr_hi : L.wd_hi) + tn * (64 * 128 / 4), 64 * 128, &wfull[ps]);
+                                bulk_copy_g2s(Ws + W_HALF + ps * 64 * 128, a.blob + (rn ? L.wr_lo : L.wd_lo) + tn * (64 * 128 / 4), 64 * 128, &wfull[ps]);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    umma_commit_elect(bar);
+                    // drain the wempty completions nobody waited for, so that every slot's parity is known at the next use
+#pragma unroll 1
+                    for (int g = (NU > 4 ? NU - 4 : 0); g < NU; ++g) {
+                        const int ps = g & 3;
+                        mbar_wait_spin(&wempty[ps], (we_par >> ps) & 1u);
+                        we_par ^= 1u << ps;
+                    }
                 }
                 wait_mma();
                 tc_fence_after();
@@ -431,9 +517,11 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 okcur = okmask;
                 const TileId tl = tile_of(ti);
                 const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
-                if (loaded != tl.chain) {
-                    load_w(a.blob + L.wd_hi, 0, KD * 64 * 128);
-                    load_w(a.blob + L.wd_lo, W_HALF, KD * 64 * 128);
+                const bool neww = loaded != tl.chain;
+                if (neww) {
+                    w_begin(2 * KD * 64 * 128);
+                    w_copy(a.blob + L.wd_hi, 0, KD * 64 * 128);
+                    w_copy(a.blob + L.wd_lo, W_HALF, KD * 64 * 128);
                     loaded = tl.chain;
                 }
                 load_coef(a.stats + L.st_d, tl.b, L.sc_d, L.sh_d, L.al_d);
@@ -451,6 +539,7 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                         store_part(As + k * A_UNIT, lrow, lq, v);
                     }
                 }
+                if (neww) w_wait();
                 tick(4);
                 issue(idesc64, KD, 64 * 128);
                 if (ti + 1 < tile_end) fetch(ti + 1);      // the next tile's rows: in flight under the MMAs and the epilogue
@@ -461,7 +550,7 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 tick(6);
             }
         }
-        grid_barrier(a.barrier, bar_target);
+        if (CLUSTER) cluster_barrier(); else grid_barrier(a.barrier, bar_target);
         tick(7);
         // ======================================================================= phase C: x += W_out * norm(PReLU(z))
         {
@@ -482,11 +571,13 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                 const bool zcur = zok;
                 const TileId tl = tile_of(ti);
                 const TcmChainLayer& L = a.L[tl.chain * a.nlayers + l];
-                if (loaded != tl.chain) {
-                    load_w(a.blob + L.wo_hi[0], 0, 128 * 128);
-                    load_w(a.blob + L.wo_hi[1], 128 * 128, 128 * 128);
-                    load_w(a.blob + L.wo_lo[0], W_HALF, 128 * 128);
-                    load_w(a.blob + L.wo_lo[1], W_HALF + 128 * 128, 128 * 128);
+                const bool neww = loaded != tl.chain;
+                if (neww) {
+                    w_begin(4 * 128 * 128);
+                    w_copy(a.blob + L.wo_hi[0], 0, 128 * 128);
+                    w_copy(a.blob + L.wo_hi[1], 128 * 128, 128 * 128);
+                    w_copy(a.blob + L.wo_lo[0], W_HALF, 128 * 128);
+                    w_copy(a.blob + L.wo_lo[1], W_HALF + 128 * 128, 128 * 128);
                     loaded = tl.chain;
                 }
                 load_coef(a.stats + L.st_o, tl.b, L.sc_o, L.sh_o, L.al_o);
@@ -500,6 +591,7 @@ __global__ void __launch_bounds__(NT, 1) tcm_chain_kernel(const TcmChainArgs a) 
                     for (int i = 0; i < CPT; ++i) v[i] = zcur ? v[i] : 0.f;
                     store_part(As, lrow, lq, v);
                 }
+                if (neww) w_wait();
                 tick(8);
                 issue(idesc256, 1, 0);
                 // this row's residual (256 / TPR columns of x) and the next tile's z rows: in flight under the MMAs
@@ -560,43 +652,46 @@ bool tcm_chain_supported(const TcmChainArgs& a) {
 int launch_tcm_chain(const TcmChainArgs& a_in, cudaStream_t st) {
     TcmChainArgs a = a_in;
     if (!tcm_chain_supported(a)) return fail("tcm_chain: unsupported shape");
-    const void* kernel = nullptr;
-    if (a.gated) {
-        kernel = a.kd == 3 ? reinterpret_cast<const void*>(tcm_chain_kernel<3, true>)
-               : a.kd == 5 ? reinterpret_cast<const void*>(tcm_chain_kernel<5, true>) : nullptr;
-    } else {
-        kernel = a.kd == 1 ? reinterpret_cast<const void*>(tcm_chain_kernel<1, false>)
-               : a.kd == 2 ? reinterpret_cast<const void*>(tcm_chain_kernel<2, false>)
-               : a.kd == 3 ? reinterpret_cast<const void*>(tcm_chain_kernel<3, false>)
-               : a.kd == 4 ? reinterpret_cast<const void*>(tcm_chain_kernel<4, false>) : nullptr;
-    }
-    if (!kernel) return fail("tcm_chain: unsupported kernel size");
-    static int max_ctas = 0;
-    if (!max_ctas) {
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        EAB_CUDA(cudaFuncSetAttribute(tcm_chain_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        int dev = 0, sms = 0, coop = 0;
-        EAB_CUDA(cudaGetDevice(&dev));
-        EAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        EAB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        if (!coop) return fail("tcm_chain: the device does not support cooperative launches");
-        max_ctas = sms;                                  // one persistent CTA per SM (194 KB of shared memory each)
-    }
     a.tiles_per_b = (a.T + TM - 1) / TM;
+    const bool cluster = a.tiles_per_b <= 8 && !a.no_cluster;
+    const void* kernel = nullptr;
+#define EAB_CHAIN_PICK(CL)                                                                               \
+    (a.gated ? (a.kd == 3 ? reinterpret_cast<const void*>(tcm_chain_kernel<3, true, CL>)                  \
+                : a.kd == 5 ? reinterpret_cast<const void*>(tcm_chain_kernel<5, true, CL>) : nullptr)     \
+             : (a.kd == 1 ? reinterpret_cast<const void*>(tcm_chain_kernel<1, false, CL>)                 \
+                : a.kd == 2 ? reinterpret_cast<const void*>(tcm_chain_kernel<2, false, CL>)               \
+                : a.kd == 3 ? reinterpret_cast<const void*>(tcm_chain_kernel<3, false, CL>)               \
+                : a.kd == 4 ? reinterpret_cast<const void*>(tcm_chain_kernel<4, false, CL>) : nullptr))
+    kernel = cluster ? EAB_CHAIN_PICK(true) : EAB_CHAIN_PICK(false);
+#undef EAB_CHAIN_PICK
+    if (!kernel) return fail("tcm_chain: unsupported kernel size");
+    EAB_TRY(ensure_dynamic_smem(kernel, SMEM_BYTES));
     const long long total = (long long)a.nchains * a.B * a.tiles_per_b;
     if (total >= (1ll << 30)) return fail("tcm_chain: too many tiles");
-    const int grid = (int)(total < max_ctas ? total : max_ctas);
     const double rows = (double)a.nchains * a.B * a.T * a.nlayers;
     const double nb = a.gated ? 2.0 : 1.0;
-    ProfScope ps("tcm_chain", 2.0 * rows * (256.0 * 64 + nb * a.kd * 64.0 * 64 + 64.0 * 256),
-                 4.0 * rows * (256 + 64 + 64 * a.kd + 64 + 64 + 256 + 256), st);
-    void* params[1] = {&a};
-    EAB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(NT), params,
-                                         (size_t)SMEM_BYTES, st));
+    // algorithmic bytes: per TCM the residual stream in and out (256 channels) + the squeezed tensor once
+    ProfScope ps("tcm_chain", 2.0 * rows * (256.0 * 64 + nb * a.kd * 64.0 * 64 + 64.0 * 256), 4.0 * rows * (256 + 64 + 256), st,
+                 4.0 * rows * (256 + 64 + 64 * a.kd * nb + 64 + 64 + 256 + 256));
+    if (cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)total); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)a.tiles_per_b; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        void* params[1] = {&a};
+        EAB_CUDA(cudaLaunchKernelExC(&cfg, kernel, params));
+    } else {
+        int sms = 0, dev = 0, coop = 0;
+        EAB_TRY(device_sm_count(&sms));
+        EAB_CUDA(cudaGetDevice(&dev));
+        EAB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        if (!coop) return fail("tcm_chain: the device does not support cooperative launches");
+        const int grid = (int)(total < sms ? total : sms);      // one persistent CTA per SM (194 KB of shared memory each)
+        void* params[1] = {&a};
+        EAB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(NT), params, (size_t)SMEM_BYTES, st));
+    }
     EAB_LAUNCH_CHECK("tcm_chain_kernel");
     return 0;
 }

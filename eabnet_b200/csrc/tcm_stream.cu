@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
             const int s = r / CD, c = r & (CD - 1);
             const int n = step - d.dt[tap];
             float vl = 0.f, vr = 0.f;
-            if (n >= 0 && s0 + s < a.S) {
+            if (s0 + s < a.S && n >= (a.start ? __ldg(a.start + s0 + s) : 0)) {
                 const float v = d.dt[tap] == 0 ? ys[s][c] : ring[((size_t)(s0 + s) * d.RT + ring_slot(n, d.RT)) * CD + c];
                 vl = prelu_norm(v, __ldg(a.blob + d.aL + c), __ldg(a.blob + d.sL + c), __ldg(a.blob + d.hL + c));
                 vr = prelu_norm(v, __ldg(a.blob + d.aR + c), __ldg(a.blob + d.sR + c), __ldg(a.blob + d.hR + c));

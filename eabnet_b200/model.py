@@ -433,22 +433,39 @@ class EaBNetStream:
             _lib.check(self.net._native.lib.eab_stream_reset(self.net._native.h, _ptr(self.state), self.state.numel(),
                                                              self.S, st), "eab_stream_reset")
 
+    def reset_stream(self, idx: int) -> None:
+        """Stream `idx` leaves and a new one joins in its slot: it starts over at its frame 0 from the next step on, the other
+        streams carry on bit-identically (eab_stream_reset_one; stream-ordered, valid between graph replays too)."""
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            _lib.check(self.net._native.lib.eab_stream_reset_one(self.net._native.h, _ptr(self.state), self.state.numel(),
+                                                                 self.S, int(idx), st), "eab_stream_reset_one")
+
     def _launch(self, hop: torch.Tensor, out: torch.Tensor) -> None:
         st = torch.cuda.current_stream(self.dev).cuda_stream
-        _lib.check(self.net._native.lib.eab_stream_step(self.net._native.h, _ptr(self.state), self.state.numel(),
-                                                        _ptr(hop), _ptr(out), self.S, st), "eab_stream_step")
+        lib, h = self.net._native.lib, self.net._native.h
+        if hop.dtype == torch.int16:
+            _lib.check(lib.eab_stream_step_pcm16(h, _ptr(self.state), self.state.numel(), _ptr(hop), _ptr(out), self.S, st),
+                       "eab_stream_step_pcm16")
+        else:
+            _lib.check(lib.eab_stream_step(h, _ptr(self.state), self.state.numel(), _ptr(hop), _ptr(out), self.S, st),
+                       "eab_stream_step")
 
     def step(self, hop: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        if tuple(hop.shape) != (self.S, self.net.M, 160) or hop.dtype != torch.float32 or hop.device != self.dev:
-            raise ValueError("expected a float32 [%d,%d,160] tensor on %s" % (self.S, self.net.M, self.dev))
+        """One 10 ms hop for every stream: float32 [S,M,160] -> float32 [S,160], or the 16-bit PCM wire format
+        int16 [S,M,160] -> int16 [S,160] (eab_stream_step_pcm16)."""
+        if tuple(hop.shape) != (self.S, self.net.M, 160) or hop.dtype not in (torch.float32, torch.int16) or hop.device != self.dev:
+            raise ValueError("expected a float32 or int16 [%d,%d,160] tensor on %s" % (self.S, self.net.M, self.dev))
         hop = hop.contiguous()
         if out is None:
-            out = torch.empty((self.S, 160), dtype=torch.float32, device=self.dev)
+            out = torch.empty((self.S, 160), dtype=hop.dtype, device=self.dev)
+        elif out.dtype != hop.dtype:
+            raise ValueError("out must have the hop's dtype")
         with torch.cuda.device(self.dev):
             if not self.use_graph:
                 self._launch(hop, out)
                 return out
-            if self._graph is None:
+            if self._graph is None or self._hop_in.dtype != hop.dtype:
                 self._hop_in, self._hop_out = torch.empty_like(hop), torch.empty_like(out)
                 self.net._sync_params(self.dev)
                 # one eager step first: first-use work of the library (constant tables, shared-memory attributes) is not

@@ -125,6 +125,16 @@ EAB_API int  eab_stream_step(eab_model* m, void* state_dev, size_t state_bytes, 
                      float* enhanced_hop_dev, int n_streams, void* stream);
 EAB_API int  eab_stream_step_spec(eab_model* m, void* state_dev, size_t state_bytes, const float* frame_dev,
                           float* out_frame_dev, int n_streams, void* stream);
+/* The servable front door around the step:
+ *   eab_stream_step_pcm16  the same step on the 16-bit PCM wire format: hop_dev [S][M][160] int16 (sample / 32768, what
+ *                          torchaudio.load yields, enhance.py:35) -> enhanced_hop_dev [S][160] int16(clip(y,-1,1) * 32767)
+ *                          (dataset/mcse_dataset_offline_gen.py:38-39); the conversions live in the STFT / iSTFT frame kernels.
+ *   eab_stream_reset_one   stream `idx` leaves and a new one joins in its slot: from the next step on it starts over at its frame
+ *                          0 (zero causal history, zero LSTM state, reflected first half-frame) while the other streams carry on
+ *                          bit-identically.  Stream-ordered (capturable), no synchronisation. */
+EAB_API int  eab_stream_step_pcm16(eab_model* m, void* state_dev, size_t state_bytes, const int16_t* hop_dev,
+                           int16_t* enhanced_hop_dev, int n_streams, void* stream);
+EAB_API int  eab_stream_reset_one(eab_model* m, void* state_dev, size_t state_bytes, int n_streams, int idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GaGNet post-filter: what `enhance.py` runs behind EaBNet through
@@ -205,7 +215,8 @@ EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, in
  *                       0 = stage_kernel + conv_tma_kernel (fp16 operand planes staged through HBM)
  *   "staged" (1)        the stage + conv_tma pair for what conv_raw does not take; 0 = per-tap gather kernel (conv_umma)
  *   "lazy" (1)          a module's residual sum x0 + y is summed by its consumers, never materialised
- *   "tcm_chain" (1)     a group of squeezed TCMs as one persistent launch; 0 = three GEMM launches per TCM
+ *   "tcm_chain" (1)     a group of squeezed TCMs as one launch (a thread-block cluster per utterance); 0 = three GEMM launches
+ *                       per TCM, 2 = one chain per launch, 3 = the cooperative grid-barrier form (also taken when T > 1024)
  *   "fused_head" (1)    w_dnn + filter-and-sum as one kernel     "head_w_tap" (0)  ... which also writes the beam weights (tap "w")
  *   "stft_tc" (1)       STFT as a tensor-core DFT-GEMM; 0 = fp32 CUDA-core kernel.  PROCESS-WIDE switch (eab_stft has no handle)
  *   "host_graph" (1) / "dual_stream" (1)   eab_enhance_host_batches: replay each slot's step from a CUDA graph / alternate

@@ -102,7 +102,11 @@ def test_forward_matches_oracle(over, B, L):
     for name, r in taps.items():
         got = net.debug_tap(name, tuple(r.shape)).cpu()
         cond = float((r.double() - taps64[name]).abs().max())
-        assert (got.double() - taps64[name]).abs().max() <= max(5e-3 * max(1.0, float(r.abs().max())), 8 * cond), name
+        # per-stage bars (relative to the stage's scale): the 3-pass stages (encoder, TCMs) are fp32-grade, 1e-4; everything
+        # from the single-pass decoder on carries its fp16 operand rounding, 2e-3 - a single-pass regression in the encoder
+        # shows here long before the output moves
+        bar = 1e-4 if (name.startswith("en.") or name == "tcm") else 2e-3
+        assert (got.double() - taps64[name]).abs().max() <= max(bar * max(1.0, float(r.abs().max())), 8 * cond), name
     err = float((out.double() - ref64).abs().max())
     cond = float((ref.double() - ref64).abs().max())
     assert err <= max(TIGHT * scale, 8 * cond) and err <= TOL * scale, (err, cond)
@@ -124,7 +128,7 @@ def test_forward_fp32_grade_modes(opts):
 
 
 @pytest.mark.parametrize("opts", [{"raw": 0}, {"stft_tc": 0}, {"staged": 0}, {"raw": 0, "staged": 0}, {"lazy": 0}, {"raw": 0, "lazy": 0},
-                                  {"tcm_chain": 0}])
+                                  {"tcm_chain": 0}, {"tcm_chain": 3}])
 def test_alternate_kernel_paths_agree(opts):
     """the optional kernel paths (stage + conv_tma pair instead of conv_raw, CUDA-core STFT, per-tap gather kernel,
     materialised residual sums, layer-by-layer TCMs) give the default path's result: wave -> wave, T = 101"""
@@ -224,6 +228,49 @@ def test_full_size_config2_slice_against_oracle():
         out = net.enhance(torch.cat((wave, filler, wave)).cuda()).cpu()
     assert torch.isfinite(out).all()
     assert (out[:2] - got).abs().max() <= 1e-5 and (out[62:] - got).abs().max() <= 1e-5
+    # ... and four of the 64 items straight against the oracle (the fillers included: items 2, 33 and 61 are fillers)
+    idx = [1, 2, 33, 61]
+    ref4 = O.enhance(sd, torch.cat((wave, filler, wave))[idx], cfg)
+    assert (out[idx] - ref4).abs().max() <= 1e-4
+
+
+def test_many_tiles_per_cta_match_one_tile_per_cta():
+    """conv_raw's grid capped to 3 CTAs (option raw_grid): every CTA walks dozens of tiles, so all of the kernel's mbarrier
+    phase logic, ring wrap-arounds and batch-item changes run at a size the oracle checks in a second; BatchNorm models are
+    bit-identical to the uncapped launch (InstanceNorm statistics are summed in a different order)."""
+    for over, exact in (({"norm_type": "BN"}, True), ({}, False)):
+        cfg = O.make_cfg(**over)
+        net, sd = _net(cfg, seed=9)
+        wave, _ = O.make_wave(3, 9, 12800, seed=41)
+        spec = O.stft_compress(wave)
+        ref = O.forward(sd, spec, cfg)
+        with torch.no_grad():
+            full = net(spec.cuda()).cpu()
+            net.set_option("raw_grid", 3)
+            capped = net(spec.cuda()).cpu()
+            net.set_option("raw_grid", 0)
+        assert (capped - ref).abs().max() <= TIGHT and (full - ref).abs().max() <= TIGHT
+        if exact:
+            assert torch.equal(capped, full)
+
+
+def test_two_devices_in_one_process_match_one_device():
+    """two models on two GPUs driven from one process (per-device launch state: shared-memory attributes, SM counts) give the
+    single-device result"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from eabnet_b200 import EaBNet
+    cfg = O.make_cfg()
+    sd = O.make_weights(cfg, 3, "B")
+    wave, _ = O.make_wave(2, 9, 8000, seed=19)
+    outs = []
+    for d in (0, 1):
+        net = EaBNet(**cfg).eval()
+        net.load_state_dict(sd, strict=True)
+        net = net.to("cuda:%d" % d)
+        with torch.no_grad():
+            outs.append(net.enhance(wave.to("cuda:%d" % d)).cpu())
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_graphed_enhance_matches_eager_call():
@@ -241,6 +288,24 @@ def test_graphed_enhance_matches_eager_call():
         out2 = g.step().clone()
         assert torch.equal(out2, net.enhance(buf))
     assert g.launches > 0
+
+
+def test_enhance_host_batches_pcm16_matches_fp32_batches():
+    """the pipelined PCM front door (int16 in / out, conversions fused into the STFT staging and the iSTFT store) against the
+    fp32 pipeline on the same samples: <= 1 LSB; 5 batches, so slots are reused and their steps replayed from CUDA graphs"""
+    cfg = O.make_cfg()
+    net, _ = _net(cfg, seed=2)
+    order = [3, 0, 1, 2, 4, 5, 6, 7, 8]
+    pcms = [(O.make_wave(2, 9, 4800, seed=60 + i)[0] * 32768.0).round().clamp(-32768, 32767).to(torch.int16).pin_memory() for i in range(5)]
+    outs = net.enhance_host_batches(pcms, mic_order=order)
+    waves = [(p.float() / 32768.0)[:, order].contiguous().pin_memory() for p in pcms]
+    refs = net.enhance_host_batches(waves)
+    again = net.enhance_host_batches(pcms, mic_order=order)
+    for o, r, o2 in zip(outs, refs, again):
+        assert o.dtype == torch.int16 and o.shape == (2, 4800)
+        exp = (r.clamp(-1, 1) * 32767.0).to(torch.int16)
+        assert int((o.int() - exp.int()).abs().max()) <= 1
+        assert torch.equal(o, o2)
 
 
 def test_enhance_pcm16_front_door():

@@ -104,3 +104,51 @@ def test_stream_graph_capture_as_first_cuda_work_of_a_process():
             "print('ok')\n")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_stream_reset_one_restarts_that_stream_only():
+    """eab_stream_reset_one: stream 1 is restarted mid-run with new audio; streams 0 and 2 continue bit-identically, and the
+    restarted stream reproduces a fresh run of its new audio (causal history, LSTM state, STFT reflection, overlap-add)"""
+    from eabnet_b200.model import EaBNetStream
+    cfg = O.make_cfg(norm_type="BN")
+    net, sd = _net(cfg, seed=11)
+    S, nh, k0 = 3, 30, 11
+    wave, _ = O.make_wave(S, 9, 160 * nh, seed=51)
+    wave2, _ = O.make_wave(1, 9, 160 * (nh - k0), seed=52)
+    dw, dw2 = wave.cuda(), wave2.cuda()
+    plain = EaBNetStream(net, S)
+    ref_hops = [plain.step(dw[:, :, 160 * k:160 * (k + 1)].contiguous()).clone() for k in range(nh)]
+    fresh = EaBNetStream(net, 1)
+    fresh_hops = [fresh.step(dw2[:, :, 160 * k:160 * (k + 1)].contiguous()).clone() for k in range(nh - k0)]
+    ses = EaBNetStream(net, S)
+    for k in range(nh):
+        hop = dw[:, :, 160 * k:160 * (k + 1)].clone()
+        if k == k0:
+            ses.reset_stream(1)
+        if k >= k0:
+            hop[1] = dw2[0, :, 160 * (k - k0):160 * (k - k0 + 1)]
+        out = ses.step(hop.contiguous())
+        assert torch.equal(out[0], ref_hops[k][0]) and torch.equal(out[2], ref_hops[k][2]), k
+        if k < k0:
+            assert torch.equal(out[1], ref_hops[k][1])
+        else:
+            assert (out[1] - fresh_hops[k - k0][0]).abs().max() <= 1e-6, k
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_stream_pcm16_hops(graph):
+    """the 16-bit PCM hop ABI: int16 hops in / out against the float step on the same samples (<= 1 LSB)"""
+    from eabnet_b200.model import EaBNetStream
+    cfg = O.make_cfg(norm_type="BN")
+    net, _ = _net(cfg, seed=7)
+    S, nh = 2, 12
+    wave, _ = O.make_wave(S, 9, 160 * nh, seed=61)
+    pcm = (wave * 32768.0).round().clamp(-32768, 32767).to(torch.int16).cuda()
+    f = EaBNetStream(net, S)
+    q = EaBNetStream(net, S, graph=graph)
+    for k in range(nh):
+        hp = pcm[:, :, 160 * k:160 * (k + 1)].contiguous()
+        a = f.step(hp.float() / 32768.0)
+        b = q.step(hp)
+        exp = (a.clamp(-1, 1) * 32767.0).to(torch.int16)
+        assert b.dtype == torch.int16 and int((b.int() - exp.int()).abs().max()) <= 1, k

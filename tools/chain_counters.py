@@ -5,11 +5,14 @@ from eabnet_b200 import EaBNet
 torch.manual_seed(0)
 net = EaBNet().eval().cuda()
 wave = 0.1 * torch.randn(64, 9, 96000, device="cuda")
-with torch.no_grad():
-    for _ in range(2): net.enhance(wave)
-    net.set_option("dbg_launch", -200)
-    net.enhance(wave)
-d = net.debug_counters()
 names = ["A load+store", "A mma", "A epilogue", "barrier1", "B load+store", "B mma", "B epilogue", "barrier2", "C load+store", "C mma", "C epilogue", "total", "tiles"]
-for n, v in zip(names, d):
-    print("%-14s %12d cycles  %6.1f%%" % (n, v, 100.0 * v / max(d[11], 1)))
+for mode in [int(x) for x in sys.argv[1:]] or [1, 3]:
+    net.set_option("tcm_chain", mode)
+    with torch.no_grad():
+        for _ in range(2): net.enhance(wave)
+        net.set_option("dbg_launch", -200)
+        net.enhance(wave)
+    d = net.debug_counters()
+    print("tcm_chain = %d (1: cluster per utterance, 3: cooperative grid barriers)" % mode)
+    for n, v in zip(names, d):
+        print("  %-14s %12d cycles  %6.1f%%" % (n, v, 100.0 * v / max(d[11], 1)), flush=True)

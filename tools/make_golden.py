@@ -34,6 +34,7 @@ CASES = [
     ("unet_cnn_m8_b1_t17", {"is_u2": False, "bf_type": "cnn", "M": 8}, 1, 2560, "B"),
     ("miso_add_m1_b2_t9", {"topo_type": "miso", "intra_connect": "add", "M": 1}, 2, 1280, "B"),
     ("noncausal_b1_t40", {"is_causal": False}, 1, 6240, "B"),
+    ("default_b1_t601", {}, 1, 96000, "B"),         # the BASELINE config-2 length (6 s, T = 601): ~6.5 MB
 ]
 
 
@@ -50,11 +51,14 @@ def load_reference():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--only", default="", help="comma-separated case names (default: all)")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     EaBNet, prepare_data = load_reference()
     torch.set_num_threads(os.cpu_count())
     for name, over, B, L, variant in CASES:
+        if a.only and name not in a.only.split(","):
+            continue
         cfg = O.make_cfg(**over)
         net = EaBNet(**cfg).eval()
         ref_shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}

@@ -61,10 +61,9 @@ def full(src, dst):
     print(open(dst).read())
 
 
-FAMILY = [("conv_raw_kernel", "conv2d"), ("conv_tma_kernel", "conv2d"), ("stage_kernel", "conv2d"), ("conv_umma_kernel", "conv2d"),
+FAMILY = [("stft_stage_kernel", "stft"), ("conv_raw_kernel", "conv2d"), ("conv_tma_kernel", "conv2d"), ("stage_kernel", "conv2d"), ("conv_umma_kernel", "conv2d"),
           ("conv_generic_kernel", "conv2d"), ("combine_kernel", "conv2d"), ("tcm_chain_kernel", "tcm"), ("lstm_umma_kernel", "head"),
-          ("lstm_kernel", "head"), ("head_fused_kernel", "head"), ("beam_", "head"), ("istft_kernel", "istft"), ("stft_stage_kernel", "stft"),
-          ("stft_kernel", "stft")]
+          ("lstm_kernel", "head"), ("head_fused_kernel", "head"), ("beam_", "head"), ("istft_kernel", "istft"), ("stft_kernel", "stft")]
 
 
 def traffic(src, dst):
@@ -85,9 +84,9 @@ def traffic(src, dst):
     stft_left = 0
     for d in per.values():
         name = d["name"]
-        if "eab::" not in name:
+        f = next((fm for key, fm in FAMILY if key in name), None)
+        if f is None:                            # not one of the library's kernels (torch's own launches)
             continue
-        f = next((fm for key, fm in FAMILY if key in name), "other")
         if "stft_stage_kernel" in name:
             stft_left = 3                       # the three DFT-GEMM launches of the STFT follow its stage kernel
         elif "conv_tma_kernel" in name and stft_left > 0:
