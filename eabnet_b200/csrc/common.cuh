@@ -294,6 +294,9 @@ struct RawConvArgs {
     int mode0[kRawMaxSlabs], mode1[kRawMaxSlabs];    // 0 none, 1 norm -> PReLU, 2 PReLU -> norm, 3 norm -> PReLU with slopes in [0, 1]
     // ring stage = the raw rows one group of G operand rows needs from ONE slab: addend 0 at byte 0, addend 1 at add1_off
     int G, stage_bytes, add1_off;
+    int q32, r32, qG, rG;                // divmod(32, P), divmod(G, P): row / group advance of the transform threads
+    unsigned int dual_mask;              // bit s: slab s has a second addend
+    int exp_flags;                       // timing experiments (EAB_RAW_EXP): bit 0 no transform, bit 1 no tail rows
     int B, T, Fin, P;
     int nplanes, plane_cols[2], col_stride, col_off[2];
     int back, fwd, tiles_per_b;

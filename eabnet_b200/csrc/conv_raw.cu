@@ -22,6 +22,8 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -298,6 +300,8 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
     // of a tile.  Bit-exact, but SLOWER, 14.6 ms of conv_raw per step against 9.9: their 64 statistics registers go to local
     // memory around the transform code and their epilogue, which frees the accumulator the next MMA waits for, runs late.)
     struct XfState { int stage; uint32_t sphase; int cur_b; long long t_wo, t_wr, t_cf; };
+    const int pcols0 = a.plane_cols[0], pcols1 = a.plane_cols[1], coff0 = a.col_off[0], coff1 = a.col_off[1];
+    const bool np2 = a.nplanes == 2;
     auto xf_tile = [&](const int tile, const int ttid, XfState& xs, const bool dbg_on) {
         const int c8 = ttid & 7;
         const int rr = ttid >> 3;                            // 0..31
@@ -333,41 +337,52 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
             RWAIT_IDLE(&opnd_empty[buf], bphase ^ 1);
             if (dbg_on) t_wo += clock64() - w1;
             uint8_t* obuf = opnd + (size_t)buf * pl.buf_bytes;
+            // This thread's operand rows of the tile are rho = rr, rr + 32, rr + 64, ... across the groups; their (frame,
+            // column) advance by (q32, r32) = divmod(32, P) per row and the groups' first rows by divmod(G, P): two divisions
+            // per tile.  (A per-item set-up - division, indexed constant loads, shuffles between the lanes of a row - cost more
+            // than the transform arithmetic: ncu, profiles/r02_raw_l48_*.)
+            int t_r, c_r, t_a, c_a;                          // padded row r = row0 - back + rho = t P + c ; the group's first row
+            {
+                const unsigned u_a = (unsigned)(row0 - a.back + 4 * a.P);      // >= 0: back <= 4 P (launcher)
+                const unsigned q_a = a.P == 1 ? u_a : __umulhi(u_a, a.p_magic);
+                t_a = (int)q_a - 4; c_a = (int)(u_a - q_a * (unsigned)a.P);
+                const unsigned u_r = u_a + (unsigned)rr;
+                const unsigned q_r = a.P == 1 ? u_r : __umulhi(u_r, a.p_magic);
+                t_r = (int)q_r - 4; c_r = (int)(u_r - q_r * (unsigned)a.P);
+            }
+            int rho = rr;
+            const int pstep = a.nslab * npb * pl.plane_bytes;                         // plane 1 images follow plane 0's
+            const int ni = rpt * a.nplanes;                                           // 2 or 4 regular items per thread and group
             for (int j = 0; j < pl.ngroups; ++j) {
-                int g_lo, n;
-                group_range(a, pl.R, pl.ngroups, rows_per_b, row0, j, g_lo, n);
-                // Item set-up, shared inside each 8-lane row group: lane i of the group works out item i of the row (row block
-                // h, plane p: i = h nplanes + p; i = 4 + p: the tail block of the last group) - padded row -> (frame, column),
-                // validity, raw row in the stage - and the lanes fetch the words of their items with shuffles.
-                // word: bit 31 valid (else literal zeros), bit 30 live (the thread owns such an item), bits 0-29 stage offset
-                unsigned word = 0;
-                {
-                    const int i = lane & 7;
-                    const bool tail = i >= 4;
-                    const int ii = tail ? i - 4 : i;
-                    const int h = tail ? rpt : (a.nplanes == 2 ? (ii >> 1) : ii);
-                    const int p = a.nplanes == 2 ? (ii & 1) : 0;
-                    const int rho = j * a.G + rr + 32 * h;
-                    const int rho_end = j == pl.ngroups - 1 ? pl.R : (j + 1) * a.G;
-                    const bool live = rho < rho_end && (tail ? (ii < a.nplanes && rr < kTail) : (h < rpt));
-                    if (live) {
-                        word = 1u << 30;
-                        const int r = row0 - a.back + rho;
-                        if (r >= 0 && r < rows_per_b) {
-                            const int t = a.P == 1 ? r : (int)__umulhi((unsigned)r, a.p_magic);
-                            const int col = r - t * a.P;
-                            if (col < a.plane_cols[p])
-                                word = (3u << 30) | (unsigned)((t * a.Fin + col * a.col_stride + a.col_off[p] - g_lo) * 256);
+                const bool last = j == pl.ngroups - 1;
+                const int rho_end = last ? pl.R : (j + 1) * a.G;
+                // first raw row of the stage = the group's first padded row clamped to 0 (group_range, what the loader copied from)
+                const int g_lo = t_a < 0 ? 0 : t_a * a.Fin + min(c_a * a.col_stride, a.Fin);
+                c_a += a.rG; t_a += a.qG;
+                if (c_a >= a.P) { c_a -= a.P; ++t_a; }
+                // row slots h = 0..rpt-1 (row rho = j G + rr + 32 h) and the tail slot 4 (the <= kTail rows past the last group's
+                // G).  sc: column, 0x7fffffff for a row outside [0, T P) (literal zeros), -1 for a slot past the tile's rows
+                // (it repeats slot 0: no divergence) ; sb: raw row in the stage of column 0 of the row's frame position
+                int sb[5], sc[5];
+#pragma unroll
+                for (int h = 0; h < 5; ++h) {
+                    sb[h] = 0; sc[h] = -1;
+                    const bool slot = h < 4 ? h < rpt : (last && rr < kTail);
+                    if (slot) {
+                        if (rho < rho_end || (h == 4 && rho < pl.R)) {
+                            const bool in = t_r >= 0 && t_r < a.T;
+                            sc[h] = in ? c_r : 0x7fffffff;
+                            sb[h] = in ? t_r * a.Fin + c_r * a.col_stride - g_lo : 0;
+                        }
+                        if (h < 4) {
+                            rho += 32; c_r += a.r32; t_r += a.q32;
+                            if (c_r >= a.P) { c_r -= a.P; ++t_r; }
                         }
                     }
                 }
-                unsigned w[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) w[i] = __shfl_sync(0xffffffffu, word, (lane & 24) + i);
                 const int drow = (j * a.G + rr) * 128 + ((c8 ^ (rr & 7)) << 4);      // 32 h more rows: + 4096 h (same swizzle phase)
-                const int ni = rpt * a.nplanes;                                       // 2 or 4 regular items per thread and group
-                const bool any = (w[0] >> 30) & 1u;
-                const bool any_tail = (w[4] >> 30) & 1u;
+                const bool any = sc[0] >= 0;
+                const bool any_tail = sc[4] >= 0;
 #pragma unroll 1
                 for (int s = 0; s < a.nslab; ++s) {
                     const long long w2 = dbg_on ? clock64() : 0;
@@ -377,21 +392,24 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                     const uint8_t* st1 = st0 + a.add1_off;
                     const float* cf = coef + s * 2 * 192;
                     uint8_t* ob = obuf + s * npb * pl.plane_bytes + drow;
-                    const int pstep = a.nslab * npb * pl.plane_bytes;                 // plane 1 images follow plane 0's
-                    const bool dual = a.x1[s] != nullptr;
+                    const bool dual = (a.dual_mask >> s) & 1u;
                     const unsigned act = __ballot_sync(0xffffffffu, any);
-                    if (any) {
+                    if (any && !(a.exp_flags & 1)) {
                         if (ni == 4) {
                             // (four chunks per thread only in launches without lazy pairs: the launcher halves G for those)
                             uint8_t* dst[4];
                             int so[4]; bool k[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int h = a.nplanes == 2 ? (i >> 1) : i, pp = a.nplanes == 2 ? (i & 1) : 0;
-                                const bool use = (w[i] >> 30) & 1u;                   // a slot past the tile's rows repeats slot 0
-                                const unsigned ww = use ? w[i] : w[0];
-                                dst[i] = ob + (use ? h * 4096 + pp * pstep : 0);
-                                so[i] = (int)(ww & 0x3fffffffu); k[i] = (ww >> 31) != 0;
+                                // (every array index a compile-time constant: a run-time one sends the slot arrays to local memory)
+                                const int h = np2 ? (i >> 1) : i;
+                                const bool p1 = np2 && (i & 1);
+                                const int sch = np2 ? sc[i >> 1] : sc[i], sbh = np2 ? sb[i >> 1] : sb[i];
+                                const bool use = sch >= 0;                            // a slot past the tile's rows repeats slot 0
+                                const int scx = use ? sch : sc[0], sbx = use ? sbh : sb[0];
+                                k[i] = (unsigned)scx < (unsigned)(p1 ? pcols1 : pcols0);
+                                so[i] = k[i] ? (sbx + (p1 ? coff1 : coff0)) * 256 : 0;
+                                dst[i] = ob + (use ? h * 4096 : 0) + (p1 ? pstep : 0);
                             }
                             xf_items<4, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
                         } else {
@@ -399,26 +417,29 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                             int so[2]; bool k[2];
 #pragma unroll
                             for (int i = 0; i < 2; ++i) {
-                                const int h = a.nplanes == 2 ? 0 : i, pp = a.nplanes == 2 ? i : 0;
-                                const bool use = (w[i] >> 30) & 1u;
-                                const unsigned ww = use ? w[i] : w[0];
-                                dst[i] = ob + (use ? h * 4096 + pp * pstep : 0);
-                                so[i] = (int)(ww & 0x3fffffffu); k[i] = (ww >> 31) != 0;
+                                const int h = np2 ? 0 : i;
+                                const bool p1 = np2 && i == 1;
+                                const int sch = np2 ? sc[0] : sc[i], sbh = np2 ? sb[0] : sb[i];
+                                const bool use = sch >= 0;
+                                const int scx = use ? sch : sc[0], sbx = use ? sbh : sb[0];
+                                k[i] = (unsigned)scx < (unsigned)(p1 ? pcols1 : pcols0);
+                                so[i] = k[i] ? (sbx + (p1 ? coff1 : coff0)) * 256 : 0;
+                                dst[i] = ob + (use ? h * 4096 : 0) + (p1 ? pstep : 0);
                             }
                             if (dual) xf_items<2, true, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
                             else xf_items<2, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act);
                         }
                     }
                     const unsigned act_t = __ballot_sync(0xffffffffu, any_tail);
-                    if (any_tail) {                                                   // the <= kTail rows past the last group's G
+                    if (any_tail && !(a.exp_flags & 3)) {                                                   // the <= kTail rows past the last group's G
                         uint8_t* dst[2];
                         int so[2]; bool k[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
-                            const bool use = (w[4 + i] >> 30) & 1u;
-                            const unsigned ww = use ? w[4 + i] : w[4];
-                            dst[i] = ob + rpt * 4096 + (use ? i * pstep : 0);
-                            so[i] = (int)(ww & 0x3fffffffu); k[i] = (ww >> 31) != 0;
+                            const bool p1 = np2 && i == 1;                            // one plane: the second item repeats the first
+                            k[i] = (unsigned)sc[4] < (unsigned)(p1 ? pcols1 : pcols0);
+                            so[i] = k[i] ? (sb[4] + (p1 ? coff1 : coff0)) * 256 : 0;
+                            dst[i] = ob + rpt * 4096 + (p1 ? pstep : 0);
                         }
                         if (dual) xf_items<2, true, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act_t);
                         else xf_items<2, false, LO, FAST>(st0, st1, so, k, dst, cf, qa, chA, chB, pl.plane_bytes, act_t);
@@ -455,7 +476,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                         RWAIT_IDLE(&raw_empty[stage], sphase ^ 1);
                         if (dbg_on) t_w += clock64() - w0;
                         if (lane == 0) {
-                            if (n > 0) {
+                            if (n > 0 && !(a.exp_flags & 16)) {
                                 const bool dual = a.x1[s] != nullptr;
                                 mbar_arrive_expect_tx(&raw_full[stage], (uint32_t)(n * 256 * (dual ? 2 : 1)));
                                 uint8_t* dst = ring + (size_t)stage * a.stage_bytes;
@@ -500,17 +521,21 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                     const uint32_t fl = a.unit_c[unit];
                     uint32_t blo;
                     if (!a.resident) {
-                        const long long w2 = dbg_on ? clock64() : 0;
-                        RWAIT(&b_full[stage], sphase);
-                        if (dbg_on) t_wb += clock64() - w2;
-                        tc_fence_after();
+                        // 3-pass layers: passes 0 (A hi) and 1 (A lo) of a (tap, slab) multiply the SAME weight image (W hi):
+                        // one ring stage serves both (bit 5 of the unit flags = "weights already in the stage")
+                        if (!(fl & 0x20u)) {
+                            const long long w2 = dbg_on ? clock64() : 0;
+                            RWAIT(&b_full[stage], sphase);
+                            if (dbg_on) t_wb += clock64() - w2;
+                            tc_fence_after();
+                        }
                         blo = bs_lo + (uint32_t)stage * bstep;
                     } else {
                         blo = bs_lo + (uint32_t)a.unit_b[unit] * bstep;
                     }
                     const uint32_t alo = ((origin + a.unit_a[unit]) & 0x3FFFu) | (1u << 16);
-                    umma_f16_lo_elect_x4(d_tmem + (fl & 1u) * (uint32_t)a.N, alo, blo, idesc, (fl & 0x80u) ? 0u : 1u);
-                    if (!a.resident) {
+                    if (!(a.exp_flags & 4)) umma_f16_lo_elect_x4(d_tmem + (fl & 1u) * (uint32_t)a.N, alo, blo, idesc, (fl & 0x80u) ? 0u : 1u);
+                    if (!a.resident && !(fl & 0x10u)) {                 // (bit 4: the next unit reads the same stage)
                         umma_commit_elect(&b_empty[stage]);
                         if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
                     }
@@ -538,12 +563,15 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                 for (int tile = tile_begin; tile < tile_end; ++tile)
                     for (int v = 0; v < a.nvar; ++v)
                         for (int ts = 0; ts < a.ntaps[v] * a.nslab; ++ts)
-                            for (int pass = 0; pass < a.npass; ++pass) {
+                            for (int hl = 0; hl < npb; ++hl) {               // W hi (passes 0 and 1), W lo (pass 2)
                                 RWAIT_IDLE(&b_empty[stage], sphase ^ 1);
                                 if (lane == 0) {
-                                    const float* img = (pass == 2 ? a.Wlo[v] : a.Whi[v]) + (size_t)ts * a.N * 32;
-                                    mbar_arrive_expect_tx(&b_full[stage], bytes);
-                                    bulk_copy_g2s(Bs + (size_t)stage * pl.b_stage_bytes, img, bytes, &b_full[stage]);
+                                    const float* img = (hl ? a.Wlo[v] : a.Whi[v]) + (size_t)ts * a.N * 32;
+                                    if (a.exp_flags & 32) { mbar_arrive(&b_full[stage]); }
+                                    else {
+                                        mbar_arrive_expect_tx(&b_full[stage], bytes);
+                                        bulk_copy_g2s(Bs + (size_t)stage * pl.b_stage_bytes, img, bytes, &b_full[stage]);
+                                    }
                                 }
                                 __syncwarp();
                                 if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
@@ -625,7 +653,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                         val[6] *= sigmoid_f(__uint_as_float(rg[6]) + g1.z); val[7] *= sigmoid_f(__uint_as_float(rg[7]) + g1.w);
                     }
                     // conv_tma adds a (zero) residual here; x + 0.f is the identity except for -0, which no statistic or consumer sees
-                    if (row_valid) {
+                    if (row_valid && !(a.exp_flags & 8)) {
                         st_global_256(a.out + off + c0, val);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -658,24 +686,40 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// shared-memory plan: resident weights before a weight ring, two operand buffers (the transform of tile i+1 runs under the
-// MMAs of tile i) whenever two ring stages still fit
-bool choose_plan(RawConvArgs& a) {
-    for (int resident = 1; resident >= 0; --resident) {
-        for (int nbuf = 2; nbuf >= 1; --nbuf) {
-            a.resident = resident; a.nbuf = nbuf; a.nsb = 3; a.nstage = 0;
-            const int fixed = make_raw_plan(a).total;
-            if (fixed >= SMEM_LIMIT) continue;
-            const int ns = std::min(NSTAGE_MAX, (SMEM_LIMIT - fixed) / a.stage_bytes);
-            if (ns < 2) continue;
-            a.nstage = ns;
-            if (!resident)                                   // leftover shared memory deepens the weight ring
-                for (int nsb = NSB_MAX; nsb > 3; --nsb) {
-                    a.nsb = nsb;
-                    if (make_raw_plan(a).total <= SMEM_LIMIT) break;
-                    a.nsb = 3;
-                }
-            return true;
+// stage geometry for a group size G: the last group of a tile also takes a tail of <= kTail rows (capacity = largest group)
+void set_group(RawConvArgs& a, int G, bool any_dual) {
+    a.G = G;
+    const int R = TM + a.back + a.fwd;
+    const int ng = R <= G + kTail ? 1 : (R - kTail + G - 1) / G;
+    const int cap = ng == 1 ? R : std::max(G, R - (ng - 1) * G);
+    a.add1_off = cap * a.col_stride * 256;
+    a.stage_bytes = a.add1_off * (any_dual ? 2 : 1);
+}
+
+// shared-memory plan.  Two operand buffers first (the transform of tile i+1 runs under the MMAs of tile i: measured 1.3-2x
+// on the 3-pass layers, whose hi + lo images leave room for one buffer only at the full group size), with resident weights
+// before a weight ring; the group size (= ring stage size) is halved when that is what makes the second buffer fit.
+bool choose_plan(RawConvArgs& a, int G0, bool any_dual) {
+    static const int force_nbuf = getenv("EAB_RAW_NBUF") ? atoi(getenv("EAB_RAW_NBUF")) : 0;      // diagnostics
+    for (int nbuf = 2; nbuf >= 1; --nbuf) {
+        if (force_nbuf && nbuf != force_nbuf) continue;
+        for (int resident = 1; resident >= 0; --resident) {
+            for (int G = G0; G >= 32 && G * a.nplanes >= 64 && G >= G0 / 2; G >>= 1) {      // >= 2 chunks per transform thread
+                set_group(a, G, any_dual);
+                a.resident = resident; a.nbuf = nbuf; a.nsb = 3; a.nstage = 0;
+                const int fixed = make_raw_plan(a).total;
+                if (fixed >= SMEM_LIMIT) continue;
+                const int ns = std::min(NSTAGE_MAX, (SMEM_LIMIT - fixed) / a.stage_bytes);
+                if (ns < 2) continue;
+                a.nstage = ns;
+                if (!resident)                                   // leftover shared memory deepens the weight ring
+                    for (int nsb = NSB_MAX; nsb > 3; --nsb) {
+                        a.nsb = nsb;
+                        if (make_raw_plan(a).total <= SMEM_LIMIT) break;
+                        a.nsb = 3;
+                    }
+                return true;
+            }
         }
     }
     return false;
@@ -727,7 +771,7 @@ bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
         if (a.plane_cols[pl] > 0 && (a.plane_cols[pl] - 1) * a.col_stride + a.col_off[pl] >= a.Fin) return false;
     a.tiles_per_b = q.tiles_per_b;
     a.p_magic = a.P == 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)a.P) + 1u;
-    if (((long long)a.T * a.P + 4 * TM + 2ll * a.P) * a.P >= (1ll << 31)) return false;              // magic-division range
+    if (((long long)a.T * a.P + 4 * TM + 6ll * a.P) * a.P >= (1ll << 31)) return false;              // magic-division range
     if ((long long)a.T * a.Fin >= (1ll << 30)) return false;
     a.npass = q.npass; a.nvar = n;
     a.out_stride = q.out_stride; a.Fout = q.Fout;
@@ -757,16 +801,9 @@ bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
         }
     }
     a.back = back; a.fwd = fwd;
-    // group size: a stage holds <= 128 raw rows per addend (32 KB), i.e. 2 or 4 operand chunks per transform thread; the
-    // last group of a tile also takes a tail of <= kTail rows (stage capacity = the largest group)
-    a.G = 128 / (q.col_stride * (any_dual ? 2 : 1));
-    {
-        const int R = TM + back + fwd;
-        const int ng = R <= a.G + kTail ? 1 : (R - kTail + a.G - 1) / a.G;
-        const int cap = ng == 1 ? R : std::max(a.G, R - (ng - 1) * a.G);
-        a.add1_off = cap * q.col_stride * 256;
-        a.stage_bytes = a.add1_off * (any_dual ? 2 : 1);
-    }
+    // group size: a stage holds <= 128 raw rows per addend (32 KB), i.e. 2 or 4 operand chunks per transform thread
+    const int G0 = 128 / (q.col_stride * (any_dual ? 2 : 1));
+    set_group(a, G0, any_dual);
     // K units: variant-major, then (tap, slab), pass fastest (the weight ring streams images in the same order)
     const int npb = a.npass == 3 ? 2 : 1;
     a.nbuf = 1; a.nstage = 2; a.resident = 0; a.nsb = 3;
@@ -783,13 +820,18 @@ bool build_args(const PlaneConvArgs* p, int n, RawConvArgs* out) {
                                               (back + w.tap_shift[tap]) * 128);
             a.unit_a[nunits] = a_rel >> 4;
             a.unit_b[nunits] = (unsigned short)(slot_base + (tap * a.nslab + slab) * npb + (pass == 2 ? 1 : 0));
-            a.unit_c[nunits] = (unsigned char)(v | (u == 0 ? 0x80 : 0) | (u == uv - 1 ? 0x40 : 0));
+            a.unit_c[nunits] = (unsigned char)(v | (u == 0 ? 0x80 : 0) | (u == uv - 1 ? 0x40 : 0) | (a.npass == 3 && pass == 1 ? 0x20 : 0) |
+                                               (a.npass == 3 && pass == 0 ? 0x10 : 0));
             ++nunits;
         }
         slot_base += w.ntaps * a.nslab * npb;
     }
     a.nunits = nunits;
-    if (!choose_plan(a)) return false;
+    if (!choose_plan(a, G0, any_dual)) return false;
+    if (a.back > 4 * a.P) return false;                               // xf_tile: floor division of row0 - back through + 4 P
+    a.q32 = 32 / a.P; a.r32 = 32 % a.P; a.qG = a.G / a.P; a.rG = a.G % a.P;
+    a.dual_mask = 0;
+    for (int i = 0; i < a.nslab; ++i) a.dual_mask |= a.x1[i] ? 1u << i : 0u;
     *out = a;
     return true;
 }
@@ -806,6 +848,8 @@ int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned lon
     if (!build_args(p, n, &a)) return fail("conv_raw: unsupported layer");
     if (a.B <= 0 || a.T <= 0) return 0;
     a.dbg = dbg;
+    static const int exp_flags = getenv("EAB_RAW_EXP") ? atoi(getenv("EAB_RAW_EXP")) : 0;      // timing experiments (wrong results)
+    a.exp_flags = exp_flags;
     const RawPlan pl = make_raw_plan(a);
     constexpr int NTW = 8;
     bool fast = true;
@@ -831,6 +875,12 @@ int launch_conv_raw(const PlaneConvArgs* p, int n, cudaStream_t st, unsigned lon
     const double kreal = 64.0 * a.nslab;
     double wbytes = 0;
     for (int v = 0; v < a.nvar; ++v) wbytes += 2.0 * (a.npass == 3 ? 2 : 1) * a.ntaps[v] * kreal * a.N;
+    static const bool verbose = getenv("EAB_RAW_VERBOSE") != nullptr;     // diagnostics: one line per launch
+    if (verbose)
+        fprintf(stderr, "conv_raw: Fin %d Fout %d P %d nslab %d dual %d planes %d npass %d N %d nvar %d taps %d+%d R %d G %d groups %d nbuf %d nstage %d "
+                        "resident %d nsb %d stage_bytes %d smem %d tiles %lld\n", a.Fin, a.Fout, a.P, a.nslab, a.add1_off != a.stage_bytes, a.nplanes,
+                a.npass, a.N, a.nvar, a.ntaps[0], a.nvar > 1 ? a.ntaps[1] : 0, pl.R, a.G, pl.ngroups, a.nbuf, a.nstage, a.resident, a.nsb,
+                a.stage_bytes, pl.total, ntiles);
     ProfScope ps("conv_raw", 2.0 * kn * kreal * a.N * a.algo_frac, in_algo + 4.0 * pos * a.Cout, st, in_moved + 4.0 * pos * a.Cout + wbytes);
     EAB_CUDA(launch_k(kern, dim3(grid), dim3(NCTRL + NEPI + NTW * 32), (size_t)pl.total, st, a));
     EAB_LAUNCH_CHECK("conv_raw_kernel");
