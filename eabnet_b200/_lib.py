@@ -53,6 +53,13 @@ SYMBOLS = {
     "eab_enhance_postnet": (C.c_int, [_P, _P, C.c_int, _F, _F, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "eab_enhance_host_pcm16": (C.c_int, [_P, _P, C.c_int, _P, C.POINTER(C.c_int), _P, C.c_int, C.c_int, _P]),
     "eab_enhance_host_batches_pcm16": (C.c_int, [_P, C.POINTER(_F), C.POINTER(C.c_int), C.POINTER(_F), C.c_int, C.c_int, C.c_int, _P]),
+    "eab_wav_info": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int),
+                              C.POINTER(C.c_int)]),
+    "eab_wav_decode": (C.c_int, [_P, C.c_size_t, _F, _P]),
+    "eab_wav_encode_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "eab_wav_encode": (C.c_int, [_F, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_size_t]),
+    "eab_resample_length": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "eab_resample": (C.c_int, [_F, _F, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
     "eab_last_launch_count": (C.c_int, [_P]),
     "eab_debug_tap": (C.c_int64, [_P, C.c_char_p, _F, C.c_int64, _P]),
     "eab_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

@@ -137,6 +137,31 @@ EAB_API int  eab_stream_step_pcm16(eab_model* m, void* state_dev, size_t state_b
 EAB_API int  eab_stream_reset_one(eab_model* m, void* state_dev, size_t state_bytes, int n_streams, int idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * I/O edges of enhance.py: the wav container and the sample-rate conversion.
+ *   eab_wav_info / eab_wav_decode   `noisy, sr = torchaudio.load(path)` (enhance.py:35) on the bytes of a RIFF/WAVE file held
+ *                                   in HOST memory: planar float32 [channels][frames], integer PCM scaled like torchaudio
+ *                                   (uint8: (x-128)/128, int16 / 2^15, int24 / 2^23, int32 / 2^31), float32 / float64 as stored
+ *                                   (PCM, IEEE float and WAVE_FORMAT_EXTENSIBLE files).  `planar_pcm16` (optional, 16-bit PCM
+ *                                   files only) receives the raw samples for the int16 front doors (eab_enhance_host_pcm16).
+ *   eab_resample                    `torchaudio.transforms.Resample(sr, 16000)(noisy)` (enhance.py:36-37) on DEVICE rows
+ *                                   [rows][length] -> [rows][eab_resample_length(length, sr, 16000)]: torchaudio's default
+ *                                   kernel (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99, built in float64 and
+ *                                   rounded to float32), applied as a polyphase FIR.  orig == new copies (Resample.forward).
+ *   eab_wav_encode                  `wavfile.write(path, 16000, esti_wav[0])` (enhance.py:63): scipy's writer byte for byte -
+ *                                   a float32 array becomes a WAVE_FORMAT_IEEE_FLOAT file (18-byte fmt chunk + fact chunk),
+ *                                   an int16 array (`interleaved_pcm16` non-NULL) a 44-byte-header PCM file.  Samples are
+ *                                   interleaved [frames][channels] as in the file.  HOST buffers. */
+EAB_API int     eab_wav_info(const void* bytes, size_t n, int* channels, int* sample_rate, int64_t* frames, int* bits_per_sample,
+                             int* is_float);
+EAB_API int     eab_wav_decode(const void* bytes, size_t n, float* planar, int16_t* planar_pcm16);
+EAB_API size_t  eab_wav_encode_bytes(int64_t frames, int channels, int pcm16);
+EAB_API int     eab_wav_encode(const float* interleaved, const int16_t* interleaved_pcm16, int64_t frames, int channels,
+                               int sample_rate, void* out, size_t capacity);
+EAB_API int64_t eab_resample_length(int64_t length, int orig_freq, int new_freq);
+EAB_API int     eab_resample(const float* wave_dev, float* out_dev, int rows, int64_t length, int orig_freq, int new_freq,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * GaGNet post-filter: what `enhance.py` runs behind EaBNet through
  * `EaBNetWithPostNet` (EaBNet.py:127-148, GaGNet.py:5-89).  Constructor arguments of GaGNet.__init__ (GaGNet.py:6-24),
  * same meaning.  The handle is an eab_model: the parameter table / eab_set_param / eab_commit_params / eab_set_option /

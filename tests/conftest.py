@@ -27,7 +27,7 @@ def pytest_collection_modifyitems(config, items):
 
 def golden_cases():
     """EaBNet cases (tools/make_golden.py)"""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("gag_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("gag_", "resample_")))
 
 
 def gag_golden_cases():
