@@ -60,6 +60,8 @@ SYMBOLS = {
     "eab_wav_encode": (C.c_int, [_F, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_size_t]),
     "eab_resample_length": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "eab_resample": (C.c_int, [_F, _F, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
+    "eab_norm_stats_count": (C.c_int, [_P]),
+    "eab_norm_stats": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), _P, _P]),
     "eab_last_launch_count": (C.c_int, [_P]),
     "eab_debug_tap": (C.c_int64, [_P, C.c_char_p, _F, C.c_int64, _P]),
     "eab_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

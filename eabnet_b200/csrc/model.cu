@@ -273,6 +273,9 @@ struct eab_model {
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
     int opt_tcm_chain = 1;        // TCM stacks as single launches (tcm_chain.cu): a GaGNet module's three stacks / an EaBNet group; 2: one chain per launch, 3: cooperative grid-barrier form
+    int opt_norm_log = 0;         // record where every InstanceNorm's (sum, sum of squares) of a forward live (eab_norm_stats)
+    struct NormLog { int gamma; const double* stats; int C, count, B; };
+    std::vector<NormLog> norm_log;
     int opt_lazy = 1;             // module residual sums are summed by the consumers' stage kernels, never materialised
     int opt_dbg_launch = -1;      // diagnostics: instrument the n-th tcgen05 conv launch of a forward
     int umma_launch_idx = 0;
@@ -1055,7 +1058,10 @@ struct Ctx {
 Xform xf_after(Ctx& cx, const NormAct& na, double* stats, int count, int prelu_pos) {
     Xform x = xform_identity();
     if (na.has_norm) {
-        if (cx.m->cfg.norm_type == 0) { x.affine = 1; x.stats = stats; x.inv_count = 1.f / (float)count; }
+        if (cx.m->cfg.norm_type == 0) {
+            x.affine = 1; x.stats = stats; x.inv_count = 1.f / (float)count;
+            if (cx.m->opt_norm_log && !cx.dry && stats) cx.m->norm_log.push_back({na.gamma, stats, na.C, count, cx.B});
+        }
         else x.affine = 2;
         x.scale = cx.W(na.off_scale);
         x.shift = cx.W(na.off_shift);
@@ -2043,6 +2049,7 @@ int gag_forward(eab_model* m, const float* inpt, const long long* strides, const
     if (ws_bytes < tb) return fail("workspace too small: need " + std::to_string(tb) + " bytes");
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail("workspace must be 256-byte aligned");
     m->taps.clear();
+    m->norm_log.clear();
     m->umma_launch_idx = 0;
     if (sb) EAB_CUDA(cudaMemsetAsync(ws, 0, sb, st));
     Ctx cx;
@@ -2580,6 +2587,28 @@ int eab_stream_reset_one(eab_model* m, void* state, size_t state_bytes, int n_st
 
 int eab_last_launch_count(const eab_model* m) { return m ? m->last_launches : 0; }
 
+// InstanceNorm statistics of the last eab_forward (option "norm_log" = 1 before it): the i-th normalisation layer the
+// forward applied, in execution order.  sums_host [C][2] = (sum, sum of squares) of the layer's input over `count`
+// positions (all batch items pooled).  Synchronises the stream; the workspace of that forward must still be intact.
+int eab_norm_stats_count(const eab_model* m) { return m ? (int)m->norm_log.size() : 0; }
+int eab_norm_stats(eab_model* m, int i, const char** weight_name, int* C, int64_t* count, double* sums_host, void* stream) {
+    if (!m) return fail("eab_norm_stats: null handle");
+    if (i < 0 || i >= (int)m->norm_log.size()) return fail("eab_norm_stats: index out of range (set option norm_log = 1 before the forward)");
+    const auto& r = m->norm_log[i];
+    if (weight_name) *weight_name = m->params[r.gamma].name.c_str();
+    if (C) *C = r.C;
+    if (count) *count = (int64_t)r.count * r.B;
+    if (sums_host) {
+        std::vector<double> h((size_t)r.B * r.C * 2);
+        EAB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+        EAB_CUDA(cudaMemcpy(h.data(), r.stats, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int c = 0; c < r.C * 2; ++c) sums_host[c] = 0.0;
+        for (int b = 0; b < r.B; ++b)
+            for (int c = 0; c < r.C * 2; ++c) sums_host[c] += h[(size_t)b * r.C * 2 + c];
+    }
+    return 0;
+}
+
 int64_t eab_debug_tap(eab_model* m, const char* name, float* dst, int64_t capacity, void* stream) {
     if (!m || !name || !dst) { fail("eab_debug_tap: null argument"); return -1; }
     auto it = m->taps.find(name);
@@ -2605,6 +2634,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "raw") m->opt_raw = value != 0;
     else if (n == "raw_grid") m->opt_raw_grid = value;
     else if (n == "lazy") m->opt_lazy = value != 0;
+    else if (n == "norm_log") { m->opt_norm_log = value != 0; m->norm_log.clear(); }
     else if (n == "tcm_chain") m->opt_tcm_chain = value;
     else if (n == "host_graph") m->opt_host_graph = value != 0;
     else if (n == "dual_stream") m->opt_dual_stream = value != 0;

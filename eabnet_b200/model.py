@@ -237,6 +237,56 @@ class EaBNet(_NativeModule):
             _lib.check(lib.eab_forward(h, _ptr(x), _ptr(out), B, T, _ptr(ws), ws.numel(), stream), "eab_forward")
         return out
 
+    # ---------------------------------------------------------------- streaming an InstanceNorm-trained model
+    def to_batchnorm(self, specs) -> "EaBNet":
+        """An InstanceNorm model cannot be stepped causally (its statistics span the utterance, EaBNet.py:45-48, 684-686).
+        This returns the same network with norm_type="BN" - the same weights, and as running_mean / running_var of every norm
+        the statistics its InstanceNorm saw on the calibration spectra `specs` (an iterable of [B,T,F,M,2] CUDA tensors, all
+        positions pooled, biased variance like InstanceNorm's own).  Its state_dict is what the reference's
+        EaBNet(norm_type="BN") loads; it streams (`.stream(n)`).  On a single calibration utterance the two models agree."""
+        if self.norm_type != "IN":
+            raise RuntimeError("to_batchnorm: the model already has static normalisation (norm_type=%r)" % self.norm_type)
+        lib, h = self._native.lib, self._native.h
+        sums, counts = {}, {}
+        self.set_option("tcm_chain", 0)         # the chain kernel keeps the TCM statistics to itself
+        self.set_option("norm_log", 1)
+        try:
+            with torch.no_grad():
+                for spec in specs:
+                    self.forward(spec)
+                    st = torch.cuda.current_stream(spec.device).cuda_stream
+                    for i in range(lib.eab_norm_stats_count(h)):
+                        name, Cn, cnt = C.c_char_p(), C.c_int(), C.c_int64()
+                        _lib.check(lib.eab_norm_stats(h, i, C.byref(name), C.byref(Cn), C.byref(cnt), None, st), "eab_norm_stats")
+                        buf = torch.empty((Cn.value, 2), dtype=torch.float64)
+                        _lib.check(lib.eab_norm_stats(h, i, None, None, None, buf.data_ptr(), st), "eab_norm_stats")
+                        key = name.value.decode()
+                        sums[key] = sums.get(key, 0) + buf
+                        counts[key] = counts.get(key, 0) + cnt.value
+        finally:
+            self.set_option("norm_log", 0)
+            self.set_option("tcm_chain", 1)
+        if not sums:
+            raise RuntimeError("to_batchnorm: no calibration data")
+        bn = EaBNet(k1=self.k1, k2=self.k2, c=self.c, M=self.M, embed_dim=self.embed_dim, kd1=self.kd1, cd1=self.cd1,
+                    d_feat=self.d_feat, p=self.p, q=self.q, is_causal=self.is_causal, is_u2=self.is_u2, bf_type=self.bf_type,
+                    topo_type=self.topo_type, intra_connect=self.intra_connect, norm_type="BN").eval()
+        sd = bn.state_dict()
+        for k, v in self.state_dict().items():
+            sd[k] = v.detach().clone()
+        for key, sm in sums.items():
+            assert key.endswith(".weight"), key
+            mean = sm[:, 0] / counts[key]
+            var = (sm[:, 1] / counts[key] - mean * mean).clamp_min(0)
+            sd[key[:-len("weight")] + "running_mean"] = mean.float()
+            sd[key[:-len("weight")] + "running_var"] = var.float()
+        missing = [k for k in sd if k.endswith("running_mean") and k[:-len("running_mean")] + "weight" not in sums]
+        if missing:
+            raise RuntimeError("to_batchnorm: no statistics recorded for %s" % missing[:3])
+        bn.load_state_dict(sd, strict=True)
+        dev = next(self.parameters()).device
+        return bn.to(dev)
+
     # ---------------------------------------------------------------- wave-to-wave (test.py:178-190)
     def enhance(self, wave: torch.Tensor, workspace: torch.Tensor | None = None) -> torch.Tensor:
         """wave [B,M,L] on the GPU -> enhanced [B,160*(L//160)]: STFT+compression, forward, iSTFT in one call.

@@ -136,6 +136,18 @@ EAB_API int  eab_stream_step_pcm16(eab_model* m, void* state_dev, size_t state_b
                            int16_t* enhanced_hop_dev, int n_streams, void* stream);
 EAB_API int  eab_stream_reset_one(eab_model* m, void* state_dev, size_t state_bytes, int n_streams, int idx, void* stream);
 
+/* Streaming an InstanceNorm-trained model.  InstanceNorm statistics span the whole utterance (EaBNet.py:684-686), so an IN
+ * model cannot be stepped causally; the reference's own note (EaBNet.py:45-48) points at accumulated statistics or another norm.
+ * What this library offers is the second: the per-channel statistics every InstanceNorm layer saw on calibration audio become
+ * the running_mean / running_var of the same network built with norm_type = "BN" (same weights, same state_dict the reference's
+ * EaBNet(norm_type="BN") loads), which streams.  On the calibration utterance itself (B = 1) the two models are the same function.
+ *   option "norm_log" = 1, then eab_forward: records every InstanceNorm the forward applied (use "tcm_chain" = 0 as well: the
+ *   chain kernel keeps the TCM statistics to itself);  eab_norm_stats_count / eab_norm_stats read them back:
+ *   weight_name = the layer's "....norm.weight" parameter, sums_host [C][2] = (sum, sum of squares) over `count` positions. */
+EAB_API int  eab_norm_stats_count(const eab_model* m);
+EAB_API int  eab_norm_stats(eab_model* m, int i, const char** weight_name, int* C, int64_t* count, double* sums_host, void* stream);
+
+
 /* ---------------------------------------------------------------------------------------------------------------
  * I/O edges of enhance.py: the wav container and the sample-rate conversion.
  *   eab_wav_info / eab_wav_decode   `noisy, sr = torchaudio.load(path)` (enhance.py:35) on the bytes of a RIFF/WAVE file held

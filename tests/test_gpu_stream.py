@@ -152,3 +152,49 @@ def test_stream_pcm16_hops(graph):
         b = q.step(hp)
         exp = (a.clamp(-1, 1) * 32767.0).to(torch.int16)
         assert b.dtype == torch.int16 and int((b.int() - exp.int()).abs().max()) <= 1, k
+
+
+def test_instancenorm_model_streams_through_batchnorm_calibration():
+    """to_batchnorm: the statistics the InstanceNorm layers saw on a calibration utterance become the BN buffers of the same
+    network.  (1) the resulting state_dict is a reference-loadable norm_type="BN" model: the oracle run with it equals the
+    oracle run of the IN model on that utterance; (2) our BN model equals our IN model there; (3) it streams."""
+    from eabnet_b200.model import EaBNetStream
+    cfg_in = O.make_cfg()
+    net, sd_in = _net(cfg_in, seed=4)
+    wave, _ = O.make_wave(1, 9, 160 * 40, seed=71)
+    spec = O.stft_compress(wave)
+    bn = net.to_batchnorm([spec.cuda()])
+    assert bn.norm_type == "BN" and net.norm_type == "IN"
+    sd_bn = {k: v.detach().cpu() for k, v in bn.state_dict().items()}
+    cfg_bn = O.make_cfg(norm_type="BN")
+    assert list(sd_bn) == list(O.param_shapes(cfg_bn))
+    ref_in = O.forward(sd_in, spec, cfg_in)
+    ref_bn = O.forward(sd_bn, spec, cfg_bn)
+    scale = max(1.0, float(ref_in.abs().max()))
+    assert (ref_bn - ref_in).abs().max() <= 2e-4 * scale          # (1): statistics measured on fp16-split tensor-core outputs
+    with torch.no_grad():
+        out_in = net(spec.cuda()).cpu()
+        out_bn = bn(spec.cuda()).cpu()
+    assert (out_bn - out_in).abs().max() <= 2e-4 * scale          # (2)
+    assert (out_bn - ref_bn).abs().max() <= 4e-4 * scale
+    # (3) hop by hop == offline enhance of the BN model
+    with torch.no_grad():
+        off = bn.enhance(wave.cuda()).cpu()
+    ses = EaBNetStream(bn, 1)
+    dw = wave.cuda()
+    hops = [ses.step(dw[:, :, 160 * k:160 * (k + 1)].contiguous()).cpu() for k in range(40)]
+    got = torch.cat(hops[1:], dim=1)                             # output delayed by one hop
+    assert (got - off[:, :got.shape[1]]).abs().max() <= 1e-4
+
+
+def test_to_batchnorm_pools_batches_and_rejects_bn_models():
+    cfg = O.make_cfg()
+    net, _ = _net(cfg, seed=5)
+    w1, _ = O.make_wave(2, 9, 4000, seed=1)
+    w2, _ = O.make_wave(1, 9, 6400, seed=2)
+    bn = net.to_batchnorm([O.stft_compress(w1).cuda(), O.stft_compress(w2).cuda()])
+    sd = bn.state_dict()
+    rv = [v for k, v in sd.items() if k.endswith("running_var")]
+    assert len(rv) > 60 and all(bool((v >= 0).all()) and bool(torch.isfinite(v).all()) for v in rv)
+    with pytest.raises(RuntimeError, match="static normalisation"):
+        bn.to_batchnorm([O.stft_compress(w2).cuda()])
