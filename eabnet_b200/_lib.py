@@ -60,6 +60,9 @@ SYMBOLS = {
     "eab_wav_encode": (C.c_int, [_F, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_size_t]),
     "eab_resample_length": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "eab_resample": (C.c_int, [_F, _F, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
+    "eab_gag_stream_step_spec": (C.c_int, [_P, _P, C.c_size_t, _F, _F, _F, C.c_int, _P]),
+    "eab_stream_step_postnet": (C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_size_t, C.c_int, _F, _F, C.c_int, _P]),
+    "eab_stream_step_postnet_pcm16": (C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_size_t, C.c_int, _P, _P, C.c_int, _P]),
     "eab_norm_stats_count": (C.c_int, [_P]),
     "eab_norm_stats": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int64), _P, _P]),
     "eab_last_launch_count": (C.c_int, [_P]),

@@ -445,6 +445,11 @@ struct GagPackArgs {
     float* x4;                   // [B][T][F][4]  channels (inpt_r, pre_r, inpt_i, pre_i)
     float* pre_row;              // [B][T][KP]    channel ri*F + f, zeros from 2F on
     int B, T, F, KP, KP2;        // KP2 = KP / 2
+    // streaming (T == 1): frame *step of every stream; inpt may be a ring of in_RT frames (slot stride in_slot floats: the
+    // spectrum ring of an EaBNet stream state), x4 is a ring of x_RT frames [S][x_RT][F][4]
+    const int* step;
+    int in_RT; long long in_slot;
+    int x_RT;
 };
 int launch_gag_pack(const GagPackArgs& a, cudaStream_t st);
 

@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(NCTRL + NEPI + NTW * 32, 1) conv_raw_kernel(co
                     for (int v = 0; v < a.nvar; ++v)
                         for (int ts = 0; ts < a.ntaps[v] * a.nslab; ++ts)
                             for (int hl = 0; hl < npb; ++hl) {               // W hi (passes 0 and 1), W lo (pass 2)
-                                RWAIT_IDLE(&b_empty[stage], sphase ^ 1);
+                                if (a.exp_flags & 64) RWAIT(&b_empty[stage], sphase ^ 1); else RWAIT_IDLE(&b_empty[stage], sphase ^ 1);
                                 if (lane == 0) {
                                     const float* img = (hl ? a.Wlo[v] : a.Whi[v]) + (size_t)ts * a.N * 32;
                                     if (a.exp_flags & 32) { mbar_arrive(&b_full[stage]); }
@@ -701,16 +701,20 @@ void set_group(RawConvArgs& a, int G, bool any_dual) {
 // before a weight ring; the group size (= ring stage size) is halved when that is what makes the second buffer fit.
 bool choose_plan(RawConvArgs& a, int G0, bool any_dual) {
     static const int force_nbuf = getenv("EAB_RAW_NBUF") ? atoi(getenv("EAB_RAW_NBUF")) : 0;      // diagnostics
+    static const int force_g = getenv("EAB_RAW_G") ? atoi(getenv("EAB_RAW_G")) : 0;               // 1: always the halved group
+    static const int force_ns = getenv("EAB_RAW_NS") ? atoi(getenv("EAB_RAW_NS")) : 0;            // raw ring depth of ring-weight layers
     for (int nbuf = 2; nbuf >= 1; --nbuf) {
         if (force_nbuf && nbuf != force_nbuf) continue;
         for (int resident = 1; resident >= 0; --resident) {
             for (int G = G0; G >= 32 && G * a.nplanes >= 64 && G >= G0 / 2; G >>= 1) {      // >= 2 chunks per transform thread
+                if (force_g && G == G0 && G0 / 2 >= 32 && (G0 / 2) * a.nplanes >= 64) continue;
                 set_group(a, G, any_dual);
                 a.resident = resident; a.nbuf = nbuf; a.nsb = 3; a.nstage = 0;
                 const int fixed = make_raw_plan(a).total;
                 if (fixed >= SMEM_LIMIT) continue;
-                const int ns = std::min(NSTAGE_MAX, (SMEM_LIMIT - fixed) / a.stage_bytes);
+                int ns = std::min(NSTAGE_MAX, (SMEM_LIMIT - fixed) / a.stage_bytes);
                 if (ns < 2) continue;
+                if (!resident && force_ns >= 2 && ns > force_ns) ns = force_ns;
                 a.nstage = ns;
                 if (!resident)                                   // leftover shared memory deepens the weight ring
                     for (int nsb = NSB_MAX; nsb > 3; --nsb) {

@@ -33,11 +33,17 @@ __global__ void __launch_bounds__(256) gag_pack_kernel(const GagPackArgs a) {
     const size_t p = (size_t)t * a.F + f;
     const float pr = __ldg(a.pre + ((size_t)b * 2 + 0) * TF + p);
     const float pi = __ldg(a.pre + ((size_t)b * 2 + 1) * TF + p);
-    const long long ib = (long long)b * a.sb + (long long)t * a.st + (long long)f * a.sf;
+    long long ib = (long long)b * a.sb + (long long)t * a.st + (long long)f * a.sf;
+    size_t xrow = bt;
+    if (a.step) {                                            // streaming: ring slots of the absolute frame index
+        const int n = *a.step;
+        ib += (long long)ring_slot(n, a.in_RT) * a.in_slot;
+        xrow = bt * a.x_RT + ring_slot(n, a.x_RT);
+    }
     const float xr = __ldg(a.inpt + ib), xi = __ldg(a.inpt + ib + a.sc);
     // memory channel order of the first conv: m*2 + ri with m = (inpt, pre_x)  <->  reference channel ri*2 + m after the
     // weight packer's permutation (see Builder::gated / Packer::conv perm_ri)
-    reinterpret_cast<float4*>(a.x4)[bt * a.F + f] = make_float4(xr, pr, xi, pi);
+    reinterpret_cast<float4*>(a.x4)[xrow * a.F + f] = make_float4(xr, pr, xi, pi);
     prow[f] = pr;
     prow[a.F + f] = pi;
 }
@@ -78,6 +84,7 @@ __global__ void __launch_bounds__(256) gag_crm_kernel(const GagCrmArgs a) {
 int launch_gag_pack(const GagPackArgs& a, cudaStream_t st) {
     if (a.B <= 0 || a.T <= 0) return 0;
     if (a.KP < 2 * a.F || (a.KP & 1) || a.KP2 * 2 != a.KP) return fail("gag_pack: bad row width");
+    if (a.step && (a.T != 1 || a.in_RT < 1 || a.x_RT < 1)) return fail("gag_pack: a streaming step is one frame per stream");
     const size_t n = (size_t)a.B * a.T * a.KP2;
     ProfScope ps("gag_elementwise", 0.0, 4.0 * a.B * a.T * (4.0 * a.F + 4.0 * a.F + a.KP), st);
     EAB_CUDA(launch_k(gag_pack_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, st, a));

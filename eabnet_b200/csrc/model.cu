@@ -1023,6 +1023,7 @@ struct Ctx {
     bool streaming = false;
     const int* step = nullptr;
     const int* start = nullptr;   // [streams] first absolute frame of each stream (eab_stream_reset_one)
+    int gag_in_RT = 1; long long gag_in_slot = 0;      // streaming GaGNet: ring geometry of the `inpt` frame source
     int next_RT = 0;          // ring size of the next allocation (0 = the default of 2: current + previous frame)
     int last_RT = 0;          // ring size of the last allocation (0 offline)
     bool tensor_ok() const { return m->opt_umma && !streaming; }
@@ -1771,7 +1772,29 @@ int run_gag_in(Ctx& cx, const GagIn& in, const Act& feat, const Act& pre, Act* o
     out->F = 1; out->C = c.d_feat; out->xf = xform_identity();
     out->data = cx.alloc_act((size_t)cx.B * cx.T * c.d_feat);
     out->RT = cx.last_RT;
-    if (!cx.tensor_ok()) return fail("GaGNet: the glance / gaze input convs run on the tcgen05 path only (option umma=0 is not supported)");
+    if (!cx.tensor_ok()) {
+        // CUDA-core path (streaming, option umma = 0): the dense [K][value | gate] matrix of every column split; the split's
+        // SW output channels are position `sp` of a [.., nsplit, SW] view of the d_feat-wide row
+        if (cx.dry) return 0;
+        for (int sp = 0; sp < in.nsplit; ++sp) {
+            if (!in.u[sp].ok) return fail("internal: GaGNet input conv bias images missing");
+            ConvArgs a;
+            memset(&a, 0, sizeof(a));
+            a.nsrc = 2;
+            const Act* srcs[2] = {&feat, &pre};
+            for (int i = 0; i < 2; ++i) { a.src[i].x = srcs[i]->data; a.src[i].C = srcs[i]->C; a.src[i].xf = srcs[i]->xf; a.src[i].RT = srcs[i]->RT; }
+            a.step = cx.step; a.start = cx.start; a.out_RT = out->RT;
+            a.B = cx.B; a.T = cx.T; a.Fin = 1; a.E = 1; a.Fout = in.nsplit;
+            a.in_stride = 1; a.out_stride = 1; a.out_off = sp;
+            a.ntaps = 1; a.dt[0] = 0; a.df[0] = 0;
+            a.W = cx.W(in.off_dense[sp]); a.bias = cx.W(in.u[sp].off_bias[0]);
+            a.Cout = in.SW; a.N = 2 * in.SW; a.gate_off = in.SW;
+            a.algo_frac = (float)(c.d_feat + 2 * c.n_freq) / (float)in.K;
+            a.out = out->data;
+            EAB_TRY(launch_conv(a, cx.st));
+        }
+        return 0;
+    }
     for (int sp = 0; sp < in.nsplit; ++sp) {
         if (!cx.dry && !in.u[sp].ok) return fail("internal: GaGNet input conv images missing");
         UmmaConvArgs u;
@@ -1893,16 +1916,20 @@ int run_gag_forward(Ctx& cx, const float* inpt, const long long* strides, const 
     const int F = c.n_freq, KP = ceil64(2 * F);
     Act x;
     x.F = F; x.C = 4; x.xf = xform_identity();
-    x.data = cx.alloc_act((size_t)cx.B * cx.T * F * 4);
+    x.data = cx.alloc_act((size_t)cx.B * cx.T * F * 4);          // streaming: a ring of 2 frames (the kt = 2 first conv)
+    x.RT = cx.last_RT;
     Act pre;
     pre.F = 1; pre.C = KP; pre.xf = xform_identity();
+    if (cx.streaming) cx.next_RT = 1;                            // read by 1x1 convs and the elementwise kernels only
     pre.data = cx.alloc_act((size_t)cx.B * cx.T * KP);
+    pre.RT = cx.last_RT;
     if (!cx.dry) {
         GagPackArgs a;
         memset(&a, 0, sizeof(a));
         a.inpt = inpt; a.sb = strides[0]; a.sc = strides[1]; a.st = strides[2]; a.sf = strides[3];
         a.pre = pre_in; a.x4 = x.data; a.pre_row = pre.data;
         a.B = cx.B; a.T = cx.T; a.F = F; a.KP = KP; a.KP2 = KP / 2;
+        if (cx.streaming) { a.step = cx.step; a.in_RT = cx.gag_in_RT; a.in_slot = cx.gag_in_slot; a.x_RT = x.RT; }
         EAB_TRY(launch_gag_pack(a, cx.st));
     }
     // ---------------- encoder (GaGNet.py:361-365 / :408-412): only the bottleneck is used
@@ -1935,7 +1962,9 @@ int run_gag_forward(Ctx& cx, const float* inpt, const long long* strides, const 
         const bool last = gi + 1 == m->gags.size();
         Act next;
         next.F = 1; next.C = KP; next.xf = xform_identity();
+        if (cx.streaming) cx.next_RT = 1;
         next.data = last ? nullptr : cx.alloc_act((size_t)cx.B * cx.T * KP);      // outlives the module's scratch
+        next.RT = cx.last_RT;
         const size_t scope = cx.mark();
         Act xg, xz;
         EAB_TRY(run_gag_in(cx, G.in_g, feat, pre, &xg));
@@ -1959,9 +1988,12 @@ int run_gag_forward(Ctx& cx, const float* inpt, const long long* strides, const 
         }
         tap(cx, ("g.tcn_g." + std::to_string(gi)).c_str(), xg);
         Act gain;
+        if (cx.streaming) cx.next_RT = 1;                        // (gag_crm_kernel reads plain rows)
         EAB_TRY(run_gag_lin(cx, G.lin_g, xg, &gain));
         Act rr, ri;
+        if (cx.streaming) cx.next_RT = 1;
         EAB_TRY(run_gag_lin(cx, G.lin_r, xr, &rr));
+        if (cx.streaming) cx.next_RT = 1;
         EAB_TRY(run_gag_lin(cx, G.lin_i, xi, &ri));
         tap(cx, ("g.gain." + std::to_string(gi)).c_str(), gain);
         tap(cx, ("g.res_r." + std::to_string(gi)).c_str(), rr);
@@ -2006,12 +2038,24 @@ inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
 int stream_layout(eab_model* m, int S, StreamLayout* L) {
     const eab_config& c = m->cfg;
-    if (m->kind != 0) return fail("streaming is implemented for EaBNet handles only");
     if (S < 1) return fail("stream: need at least one stream");
     if (c.norm_type != 1) return fail("streaming needs norm_type='BN': InstanceNorm statistics span the whole utterance (EaBNet.py:684-686)");
     if (!c.is_causal) return fail("streaming needs is_causal=True");
     size_t o = 256;
     L->off_start = o; o += up256((size_t)S * sizeof(int));
+    if (m->kind == 1) {
+        // GaGNet post-filter: [0,256) frame counter | start | estimates of the q modules [q][S][2][F] | activation rings
+        L->off_desc = L->off_prev = L->off_tail = L->off_spec = o;
+        L->off_out = o; o += up256(m->gags.size() * (size_t)S * 2 * c.n_freq * sizeof(float));
+        L->off_act = o;
+        Ctx cx;
+        cx.m = m; cx.dry = true; cx.base = nullptr; cx.B = S; cx.T = 1; cx.st = nullptr; cx.streaming = true;
+        const long long zero[4] = {0, 0, 0, 0};
+        EAB_TRY(run_gag_forward(cx, nullptr, zero, nullptr, nullptr));
+        if (cx.stats_off != 0) return fail("internal: streaming plan allocated statistics");
+        L->total = o + cx.act_peak;
+        return 0;
+    }
     L->off_desc = o; o += up256(m->tcms.size() * sizeof(TcmStreamDesc));
     L->off_prev = o; o += up256((size_t)S * c.M * 160 * sizeof(float));
     L->off_tail = o; o += up256((size_t)S * 160 * sizeof(float));
@@ -2036,6 +2080,19 @@ int stream_forward(eab_model* m, char* state, const StreamLayout& L, int S, cuda
     cx.start = reinterpret_cast<const int*>(state + L.off_start);
     cx.tcm_desc_dev = reinterpret_cast<const TcmStreamDesc*>(state + L.off_desc);
     return run_forward(cx, reinterpret_cast<const float*>(state + L.off_spec), reinterpret_cast<float*>(state + L.off_out));
+}
+
+// one frame of every stream through the post-filter: inpt element (s, ri, f) at inpt[s*strides[0] + ri*strides[1] + f*strides[3]
+// + slot*in_slot] (slot = *step % in_RT: the spectrum ring of an EaBNet stream state, or in_RT = 1 for a plain frame);
+// pre [S][2][F]; the q estimates go to the state's [q][S][2][F] block
+int gag_stream_forward(eab_model* m, char* state, const StreamLayout& L, const float* inpt, const long long* strides, int in_RT,
+                       long long in_slot, const float* pre, int S, cudaStream_t st) {
+    Ctx cx;
+    cx.m = m; cx.dry = false; cx.base = state + L.off_act; cx.B = S; cx.T = 1; cx.st = st;
+    cx.streaming = true; cx.step = reinterpret_cast<const int*>(state);
+    cx.start = reinterpret_cast<const int*>(state + L.off_start);
+    cx.gag_in_RT = in_RT; cx.gag_in_slot = in_slot;
+    return run_gag_forward(cx, inpt, strides, pre, reinterpret_cast<float*>(state + L.off_out));
 }
 
 int gag_forward(eab_model* m, const float* inpt, const long long* strides, const float* pre, float* out, int B, int T, void* ws,
@@ -2510,6 +2567,7 @@ int eab_stream_reset(eab_model* m, void* state, size_t state_bytes, int n_stream
 int eab_stream_step_spec(eab_model* m, void* state, size_t state_bytes, const float* frame, float* out_frame, int n_streams,
                          void* stream) {
     StreamLayout L;
+    if (m && m->kind != 0) return fail("eab_stream_step_spec needs an EaBNet handle (a GaGNet steps through eab_gag_stream_step_spec)");
     EAB_TRY(stream_check(m, state, state_bytes, n_streams, &L));
     if (!frame || !out_frame) return fail("eab_stream_step_spec: null argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -2534,14 +2592,21 @@ int eab_stream_step_spec(eab_model* m, void* state, size_t state_bytes, const fl
     return 0;
 }
 
-static int stream_step_any(eab_model* m, void* state, size_t state_bytes, const float* hop, const int16_t* hop16, float* enhanced_hop,
-                           int16_t* enhanced16, int n_streams, void* stream) {
-    StreamLayout L;
+static int stream_step_any(eab_model* m, void* state, size_t state_bytes, eab_model* gag, void* gstate, size_t gstate_bytes, int ref_mic,
+                           const float* hop, const int16_t* hop16, float* enhanced_hop, int16_t* enhanced16, int n_streams, void* stream) {
+    StreamLayout L, GL;
+    if (m && m->kind != 0) return fail("eab_stream_step needs an EaBNet handle");
     EAB_TRY(stream_check(m, state, state_bytes, n_streams, &L));
     if ((!hop && !hop16) || (!enhanced_hop && !enhanced16)) return fail("eab_stream_step: null argument");
     const eab_config& c = m->cfg;
     if (c.topo_type == 1) return fail("eab_stream_step: the 'miso' topology returns [B,2,T], which has no iSTFT");
     if (c.n_freq != 161) return fail("eab_stream_step: the 320-point STFT gives 161 bins");
+    if (gag) {
+        if (gag->kind != 1) return fail("eab_stream_step_postnet: the post-filter handle is not a GaGNet");
+        if (gag->cfg.n_freq != c.n_freq) return fail("eab_stream_step_postnet: EaBNet and GaGNet disagree on the number of bins");
+        if (ref_mic < 0 || ref_mic >= c.M) return fail("eab_stream_step_postnet: reference microphone out of range");
+        EAB_TRY(stream_check(gag, gstate, gstate_bytes, n_streams, &GL));
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* p = static_cast<char*>(state);
     int* step = reinterpret_cast<int*>(p);
@@ -2550,8 +2615,18 @@ static int stream_step_any(eab_model* m, void* state, size_t state_bytes, const 
     EAB_TRY(launch_stft_frame(hop, hop16, reinterpret_cast<float*>(p + L.off_prev), reinterpret_cast<float*>(p + L.off_spec), 2, step,
                               start, n_streams, c.M, st));
     EAB_TRY(stream_forward(m, p, L, n_streams, st));
-    EAB_TRY(launch_istft_frame(reinterpret_cast<const float*>(p + L.off_out), reinterpret_cast<float*>(p + L.off_tail),
-                               enhanced_hop, enhanced16, step, start, n_streams, st));
+    const float* est = reinterpret_cast<const float*>(p + L.off_out);
+    if (gag) {
+        // enhance.py:49-62 frame by frame: GaGNet on (reference microphone of the compressed spectrum - read in place from the
+        // spectrum ring's current slot -, EaBNet's estimate); the last module's estimate goes to the iSTFT
+        char* g = static_cast<char*>(gstate);
+        const long long FM2 = (long long)c.n_freq * c.M * 2;
+        const long long strides[4] = {2 * FM2, 1, 0, (long long)c.M * 2};
+        EAB_TRY(gag_stream_forward(gag, g, GL, reinterpret_cast<const float*>(p + L.off_spec) + ref_mic * 2, strides, 2, FM2, est, n_streams, st));
+        est = reinterpret_cast<const float*>(g + GL.off_out) + (gag->gags.size() - 1) * (size_t)n_streams * 2 * c.n_freq;
+        EAB_TRY(launch_step_advance(reinterpret_cast<int*>(g), st));
+    }
+    EAB_TRY(launch_istft_frame(est, reinterpret_cast<float*>(p + L.off_tail), enhanced_hop, enhanced16, step, start, n_streams, st));
     EAB_TRY(launch_step_advance(step, st));
     m->last_launches = launch_count();
     return 0;
@@ -2560,14 +2635,49 @@ static int stream_step_any(eab_model* m, void* state, size_t state_bytes, const 
 int eab_stream_step(eab_model* m, void* state, size_t state_bytes, const float* hop, float* enhanced_hop, int n_streams,
                     void* stream) {
     if (!hop || !enhanced_hop) return fail("eab_stream_step: null argument");
-    return stream_step_any(m, state, state_bytes, hop, nullptr, enhanced_hop, nullptr, n_streams, stream);
+    return stream_step_any(m, state, state_bytes, nullptr, nullptr, 0, 0, hop, nullptr, enhanced_hop, nullptr, n_streams, stream);
 }
 
 // the same step on the 16-bit PCM wire format: hop [S][M][160] int16 (sample / 32768), enhanced hop [S][160] int16
 int eab_stream_step_pcm16(eab_model* m, void* state, size_t state_bytes, const int16_t* hop, int16_t* enhanced_hop, int n_streams,
                           void* stream) {
     if (!hop || !enhanced_hop) return fail("eab_stream_step_pcm16: null argument");
-    return stream_step_any(m, state, state_bytes, nullptr, hop, nullptr, enhanced_hop, n_streams, stream);
+    return stream_step_any(m, state, state_bytes, nullptr, nullptr, 0, 0, nullptr, hop, nullptr, enhanced_hop, n_streams, stream);
+}
+
+// EaBNet + GaGNet post-filter, one hop per stream (enhance.py:49-62 as a causal stream).  Both states carry their own frame
+// counter: reset them together (eab_stream_reset / eab_stream_reset_one on each).
+int eab_stream_step_postnet(eab_model* eabnet, void* state, size_t state_bytes, eab_model* gagnet, void* gag_state, size_t gag_state_bytes,
+                            int ref_mic, const float* hop, float* enhanced_hop, int n_streams, void* stream) {
+    if (!hop || !enhanced_hop || !gagnet) return fail("eab_stream_step_postnet: null argument");
+    return stream_step_any(eabnet, state, state_bytes, gagnet, gag_state, gag_state_bytes, ref_mic, hop, nullptr, enhanced_hop, nullptr,
+                           n_streams, stream);
+}
+int eab_stream_step_postnet_pcm16(eab_model* eabnet, void* state, size_t state_bytes, eab_model* gagnet, void* gag_state,
+                                  size_t gag_state_bytes, int ref_mic, const int16_t* hop, int16_t* enhanced_hop, int n_streams, void* stream) {
+    if (!hop || !enhanced_hop || !gagnet) return fail("eab_stream_step_postnet_pcm16: null argument");
+    return stream_step_any(eabnet, state, state_bytes, gagnet, gag_state, gag_state_bytes, ref_mic, nullptr, hop, nullptr, enhanced_hop,
+                           n_streams, stream);
+}
+
+// GaGNet.forward one frame at a time: inpt_frame / pre_frame [S][2][F] -> the q modules' estimates [q][S][2][F]
+int eab_gag_stream_step_spec(eab_model* gagnet, void* gag_state, size_t gag_state_bytes, const float* inpt_frame, const float* pre_frame,
+                             float* out_frames, int n_streams, void* stream) {
+    if (!gagnet || gagnet->kind != 1) return fail("eab_gag_stream_step_spec: the handle is not a GaGNet");
+    if (!inpt_frame || !pre_frame || !out_frames) return fail("eab_gag_stream_step_spec: null argument");
+    StreamLayout GL;
+    EAB_TRY(stream_check(gagnet, gag_state, gag_state_bytes, n_streams, &GL));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* g = static_cast<char*>(gag_state);
+    const int F = gagnet->cfg.n_freq;
+    const long long strides[4] = {2LL * F, (long long)F, 0, 1};
+    reset_launch_count();
+    EAB_TRY(gag_stream_forward(gagnet, g, GL, inpt_frame, strides, 1, 0, pre_frame, n_streams, st));
+    EAB_CUDA(cudaMemcpyAsync(out_frames, g + GL.off_out, gagnet->gags.size() * (size_t)n_streams * 2 * F * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+    EAB_TRY(launch_step_advance(reinterpret_cast<int*>(g), st));
+    gagnet->last_launches = launch_count();
+    return 0;
 }
 
 // One stream leaves and a new one joins in its slot: from the next step on stream `idx` starts over (its frame 0), the other

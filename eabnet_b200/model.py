@@ -460,7 +460,9 @@ class EaBNetStream:
     With graph=True the whole step (stft frame, ~270 layer kernels, istft frame) is captured once into a CUDA graph
     and replayed: the frame counter lives in device memory, so the captured launches never change."""
 
-    def __init__(self, net: EaBNet, n_streams: int, device=None, graph: bool = False):
+    def __init__(self, net: EaBNet, n_streams: int, device=None, graph: bool = False, postnet=None, ref_mic: int = 0):
+        """`postnet`: a GaGNet (is_causal, norm_type "BN") run behind the beamformer on every hop (enhance.py:49-62 as a stream,
+        eab_stream_step_postnet); `ref_mic` is the microphone whose spectrum it filters (EaBNet.py:141)."""
         dev = torch.device(device) if device is not None else next(net.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("eabnet_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
@@ -472,29 +474,45 @@ class EaBNetStream:
         if nbytes == 0:
             _lib.check(1, "eab_stream_state_bytes")
         self.state = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.postnet, self.ref_mic, self.gstate = postnet, int(ref_mic), None
+        if postnet is not None:
+            gbytes = lib.eab_stream_state_bytes(postnet._native.h, self.S)
+            if gbytes == 0:
+                _lib.check(1, "eab_stream_state_bytes (post-filter)")
+            self.gstate = torch.empty(gbytes, dtype=torch.uint8, device=dev)
         self._graph = None
         self._hop_in = self._hop_out = None
         self.reset()
 
+    def _states(self):
+        yield self.net, self.state
+        if self.postnet is not None:
+            yield self.postnet, self.gstate
+
     def reset(self) -> None:
         with torch.cuda.device(self.dev):
-            self.net._sync_params(self.dev)
             st = torch.cuda.current_stream(self.dev).cuda_stream
-            _lib.check(self.net._native.lib.eab_stream_reset(self.net._native.h, _ptr(self.state), self.state.numel(),
-                                                             self.S, st), "eab_stream_reset")
+            for mod, state in self._states():
+                mod._sync_params(self.dev)
+                _lib.check(mod._native.lib.eab_stream_reset(mod._native.h, _ptr(state), state.numel(), self.S, st), "eab_stream_reset")
 
     def reset_stream(self, idx: int) -> None:
         """Stream `idx` leaves and a new one joins in its slot: it starts over at its frame 0 from the next step on, the other
         streams carry on bit-identically (eab_stream_reset_one; stream-ordered, valid between graph replays too)."""
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev).cuda_stream
-            _lib.check(self.net._native.lib.eab_stream_reset_one(self.net._native.h, _ptr(self.state), self.state.numel(),
-                                                                 self.S, int(idx), st), "eab_stream_reset_one")
+            for mod, state in self._states():
+                _lib.check(mod._native.lib.eab_stream_reset_one(mod._native.h, _ptr(state), state.numel(), self.S, int(idx), st),
+                           "eab_stream_reset_one")
 
     def _launch(self, hop: torch.Tensor, out: torch.Tensor) -> None:
         st = torch.cuda.current_stream(self.dev).cuda_stream
         lib, h = self.net._native.lib, self.net._native.h
-        if hop.dtype == torch.int16:
+        if self.postnet is not None:
+            fn = lib.eab_stream_step_postnet_pcm16 if hop.dtype == torch.int16 else lib.eab_stream_step_postnet
+            _lib.check(fn(h, _ptr(self.state), self.state.numel(), self.postnet._native.h, _ptr(self.gstate), self.gstate.numel(),
+                          self.ref_mic, _ptr(hop), _ptr(out), self.S, st), "eab_stream_step_postnet")
+        elif hop.dtype == torch.int16:
             _lib.check(lib.eab_stream_step_pcm16(h, _ptr(self.state), self.state.numel(), _ptr(hop), _ptr(out), self.S, st),
                        "eab_stream_step_pcm16")
         else:
@@ -520,11 +538,14 @@ class EaBNetStream:
                 self.net._sync_params(self.dev)
                 # one eager step first: first-use work of the library (constant tables, shared-memory attributes) is not
                 # capturable; the carried state it advanced is put back before the capture
-                snapshot = self.state.clone()
+                snapshot = [state.clone() for _, state in self._states()]
                 self._hop_in.zero_()
                 self._launch(self._hop_in, self._hop_out)
-                self.state.copy_(snapshot)
+                for (_, state), snap in zip(self._states(), snapshot):
+                    state.copy_(snap)
                 del snapshot
+                if self.postnet is not None:
+                    self.postnet._sync_params(self.dev)
                 torch.cuda.current_stream(self.dev).synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):

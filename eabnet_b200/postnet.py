@@ -83,6 +83,48 @@ class GaGNet(_NativeModule):
         out = self.forward_time_major(inpt, pre_x)
         return [out[i].transpose(-2, -1) for i in range(self.q)]
 
+    def stream(self, n_streams: int, device=None) -> "GaGNetStream":
+        return GaGNetStream(self, n_streams, device)
+
+
+class GaGNetStream:
+    """GaGNet.forward one frame at a time for S concurrent streams (is_causal, norm_type "BN"): eab_gag_stream_step_spec."""
+
+    def __init__(self, net: GaGNet, n_streams: int, device=None):
+        dev = torch.device(device) if device is not None else next(net.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("eabnet_b200 runs on CUDA (sm_100a) only - there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.net, self.S, self.dev = net, int(n_streams), dev
+        lib, h = net._native.lib, net._native.h
+        nbytes = lib.eab_stream_state_bytes(h, self.S)
+        if nbytes == 0:
+            _lib.check(1, "eab_stream_state_bytes")
+        self.state = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.reset()
+
+    def reset(self) -> None:
+        with torch.cuda.device(self.dev):
+            self.net._sync_params(self.dev)
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            _lib.check(self.net._native.lib.eab_stream_reset(self.net._native.h, _ptr(self.state), self.state.numel(), self.S, st),
+                       "eab_stream_reset")
+
+    def step_spec(self, inpt_frame: torch.Tensor, pre_frame: torch.Tensor) -> torch.Tensor:
+        """inpt_frame, pre_frame [S,2,F] -> the q modules' estimates of this frame [q,S,2,F]"""
+        Fq = self.net.fft_num // 2 + 1
+        for t in (inpt_frame, pre_frame):
+            if tuple(t.shape) != (self.S, 2, Fq) or t.dtype != torch.float32 or t.device != self.dev:
+                raise ValueError("expected float32 [%d,2,%d] tensors on %s" % (self.S, Fq, self.dev))
+        a, b = inpt_frame.contiguous(), pre_frame.contiguous()
+        out = torch.empty((self.net.q, self.S, 2, Fq), dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            _lib.check(self.net._native.lib.eab_gag_stream_step_spec(self.net._native.h, _ptr(self.state), self.state.numel(), _ptr(a),
+                                                                     _ptr(b), _ptr(out), self.S, st), "eab_gag_stream_step_spec")
+        return out
+
 
 def make_gag_net(args) -> GaGNet:
     """GaGNet.py:645-665 (minus the `.cuda()`: move the wrapper with `.to(device)` like enhance.py:22 does)."""
@@ -141,6 +183,12 @@ class EaBNetWithPostNet(nn.Module):
 
     def last_launch_count(self) -> int:
         return self.eabnet.last_launch_count()
+
+    def stream(self, n_streams: int, graph: bool = False):
+        """Causal hop-by-hop enhancement with the post-filter for `n_streams` concurrent streams (both networks is_causal and
+        norm_type "BN"): eab_stream_step_postnet."""
+        from .model import EaBNetStream
+        return EaBNetStream(self.eabnet, n_streams, graph=graph, postnet=self.postnet, ref_mic=self.ref_mic)
 
     def graphed_enhance(self, wave: torch.Tensor):
         """`enhance` on a fixed device buffer captured once into a CUDA graph (see EaBNet.graphed_enhance)."""

@@ -136,6 +136,24 @@ EAB_API int  eab_stream_step_pcm16(eab_model* m, void* state_dev, size_t state_b
                            int16_t* enhanced_hop_dev, int n_streams, void* stream);
 EAB_API int  eab_stream_reset_one(eab_model* m, void* state_dev, size_t state_bytes, int n_streams, int idx, void* stream);
 
+/* Post-filter streaming (enhance.py:49-62 as a causal stream; GaGNet.py:75-89 one frame at a time).  A GaGNet handle built with
+ * is_causal and norm_type "BN" takes the same state calls as an EaBNet handle: eab_stream_state_bytes / eab_stream_reset /
+ * eab_stream_reset_one (its state holds a frame counter, the per-stream start frames, the q estimates of the step and every
+ * activation ring).
+ *   eab_gag_stream_step_spec   GaGNet.forward(inpt, pre_x) for frame n of every stream: inpt_frame / pre_frame [S][2][F] ->
+ *                              out_frames [q][S][2][F] (every module's estimate of the frame)
+ *   eab_stream_step_postnet    one 10 ms hop through EaBNet AND the post-filter: STFT frame -> EaBNet step -> GaGNet step on
+ *                              (microphone ref_mic of the compressed spectrum, EaBNet's estimate) -> iSTFT of the last module's
+ *                              estimate.  Both states advance together; reset them together.  _pcm16: int16 hops in and out. */
+EAB_API int  eab_gag_stream_step_spec(eab_model* gagnet, void* gag_state_dev, size_t gag_state_bytes, const float* inpt_frame_dev,
+                              const float* pre_frame_dev, float* out_frames_dev, int n_streams, void* stream);
+EAB_API int  eab_stream_step_postnet(eab_model* eabnet, void* state_dev, size_t state_bytes, eab_model* gagnet, void* gag_state_dev,
+                             size_t gag_state_bytes, int ref_mic, const float* hop_dev, float* enhanced_hop_dev, int n_streams,
+                             void* stream);
+EAB_API int  eab_stream_step_postnet_pcm16(eab_model* eabnet, void* state_dev, size_t state_bytes, eab_model* gagnet,
+                                   void* gag_state_dev, size_t gag_state_bytes, int ref_mic, const int16_t* hop_dev,
+                                   int16_t* enhanced_hop_dev, int n_streams, void* stream);
+
 /* Streaming an InstanceNorm-trained model.  InstanceNorm statistics span the whole utterance (EaBNet.py:684-686), so an IN
  * model cannot be stepped causally; the reference's own note (EaBNet.py:45-48) points at accumulated statistics or another norm.
  * What this library offers is the second: the per-channel statistics every InstanceNorm layer saw on calibration audio become

@@ -213,3 +213,81 @@ def test_gag_other_kernel_sizes_and_widths(over):
         got = net.forward_time_major(x.cuda(), pre.cuda()).cpu()
     scale = max(1.0, float(ref.abs().max()))
     assert float((got - ref).abs().max()) <= TIGHT * scale
+
+
+# ------------------------------------------------------------------------------------------------ post-filter streaming
+@pytest.mark.parametrize("over", [{}, {"is_squeezed": True, "acti_type": "tanh"}, {"is_u2": False, "intra_connect": "add", "dilas": (1, 2, 4)}])
+def test_gag_stream_frames_match_offline_oracle(over):
+    """GaGNet.forward one frame at a time (eab_gag_stream_step_spec, carried state) == the oracle run OFFLINE on the whole
+    signal: causal + BatchNorm makes frame n a function of frames <= n"""
+    cfg = G.make_gag_cfg(norm_type="BN", **over)
+    net, sd = _gag(cfg, "B", seed=6)
+    S, T = 3, 60
+    g = torch.Generator().manual_seed(5)
+    x, pre = 0.5 * torch.randn(S, 2, T, 161, generator=g), 0.3 * torch.randn(S, 2, T, 161, generator=g)
+    ref = torch.stack(G.gag_forward(sd, x, pre, cfg)).transpose(-2, -1)          # [q,S,2,T,F]
+    ses = net.stream(S)
+    dx, dp = x.cuda(), pre.cuda()
+    worst = 0.0
+    for t in range(T):
+        got = ses.step_spec(dx[:, :, t].contiguous(), dp[:, :, t].contiguous()).cpu()      # [q,S,2,F]
+        worst = max(worst, float((got - ref[:, :, :, t]).abs().max()))
+    assert worst <= 5e-5 * max(1.0, float(ref.abs().max())), worst
+    assert net.last_launch_count() > 0
+    # reset: the same frames again give the same result
+    ses.reset()
+    again = ses.step_spec(dx[:, :, 0].contiguous(), dp[:, :, 0].contiguous()).cpu()
+    assert float((again - ref[:, :, :, 0]).abs().max()) <= 5e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_gag_stream_rejects_instance_norm_and_eabnet_entry_points():
+    cfg = G.make_gag_cfg()
+    net, _ = _gag(cfg, "B", seed=1)
+    with pytest.raises(RuntimeError, match="BN"):
+        net.stream(2)
+
+
+@pytest.mark.parametrize("graph,pcm", [(False, False), (True, False), (False, True)])
+def test_postnet_stream_hops_match_offline_enhance(graph, pcm):
+    """EaBNetWithPostNet hop by hop (eab_stream_step_postnet) == its offline wave -> wave call and the oracle; stream 1 is
+    restarted mid-run and reproduces a fresh run while stream 0 carries on"""
+    from eabnet_b200 import make_eabnet_with_postnet
+    from eabnet_b200.postnet import default_postnet_args
+    args = default_postnet_args(ref_mic=1, norm_type="BN", gagnet_norm_type="BN")
+    w = make_eabnet_with_postnet(args).eval()
+    cfg_e, cfg_g = O.make_cfg(norm_type="BN"), G.make_gag_cfg(norm_type="BN")
+    sd = G.make_postnet_weights(cfg_e, cfg_g, 2, "B")
+    w.load_state_dict(sd, strict=True)
+    w.cuda()
+    S, nh = 2, 26
+    wave, _ = O.make_wave(S, 9, 160 * nh, seed=91)
+    if pcm:
+        wave = (wave * 32768.0).round().clamp(-32768, 32767) / 32768.0
+    r = G.postnet_forward(sd, O.stft_compress(wave), cfg_e, cfg_g, ref_mic=1)
+    ref = O.istft(r["esti_stft"].contiguous())                                   # [S, 160*nh]
+    with torch.no_grad():
+        off = w.enhance(wave.cuda()).cpu()
+    ses = w.stream(S, graph=graph)
+    dw = wave.cuda()
+    if pcm:
+        dw = (dw * 32768.0).round().to(torch.int16)
+    hops = [ses.step(dw[:, :, 160 * k:160 * (k + 1)].contiguous()).clone() for k in range(nh)]
+    got = torch.cat(hops[1:], dim=1).cpu()                                       # delayed by one hop
+    n = got.shape[1]
+    if pcm:
+        exp = (ref[:, :n].clamp(-1, 1) * 32767.0).to(torch.int16)
+        assert int((got.int() - exp.int()).abs().max()) <= 2
+        return
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((got - ref[:, :n]).abs().max()) <= 2e-4 * scale
+    assert float((got - off[:, :n]).abs().max()) <= TOL * scale                 # offline path: tensor cores, fp16 splits
+    # stream 1 leaves, a new one joins
+    ses.reset_stream(1)
+    wave2, _ = O.make_wave(1, 9, 160 * 8, seed=92)
+    fresh = w.stream(1)
+    for k in range(8):
+        hop = dw[:, :, 160 * k:160 * (k + 1)].clone()
+        hop[1] = wave2[0, :, 160 * k:160 * (k + 1)].cuda()
+        a = ses.step(hop.contiguous())
+        b = fresh.step(wave2[:, :, 160 * k:160 * (k + 1)].cuda().contiguous())
+        assert float((a[1] - b[0]).abs().max()) <= 1e-6, k
