@@ -167,6 +167,30 @@ EAB_API int  eab_norm_stats(eab_model* m, int i, const char** weight_name, int* 
 
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * First slice of the training step (train_distributed.py:214-230, BASELINE configs[4]): the tail
+ * of the beamforming head and the loss, forward AND backward, as hand-written kernels (fp32 CUDA cores; no autograd graph, no
+ * library call).  Everything else of the backward pass is not built: the module still refuses autograd (model.py).
+ *   eab_head_forward    out [B,2,T,F] = sum_m w_m x_m with w = Linear(ReLU(Linear(h2)))   (LSTM_BF.w_dnn, EaBNet.py:593-597,
+ *                       612-613, and the filter-and-sum of EaBNet.forward, EaBNet.py:114-117).  W1 [64,64], b1 [64], W2 [2M,64],
+ *                       b2 [2M] in torch's layouts; h2 [B,T,F,64] (the second LSTM's output, channels last); spec [B,T,F,M,2].
+ *   eab_head_backward   given d_out [B,2,T,F]: d_h2 [B,T,F,64] and grads = [dW1 64x64 | db1 64 | dW2 2Mx64 | db2 2M]
+ *                       (summed in a fixed order: bit-identical from run to run); workspace of eab_head_backward_workspace_bytes.
+ *   eab_loss_com_mag_mse / _backward   com_mag_mse_loss(esti, label, frame_list) (EaBNet.py:627-640) and its gradient with
+ *                       respect to esti; frames_dev [B] (NULL = every utterance has T frames, train_distributed.py:221),
+ *                       frames_total = their sum; scratch16 = 16 bytes of device scratch; grad_loss_dev = upstream gradient of
+ *                       the scalar (NULL = 1). */
+EAB_API int    eab_head_forward(const float* W1_dev, const float* b1_dev, const float* W2_dev, const float* b2_dev, const float* h2_dev,
+                                const float* spec_dev, float* out_dev, int B, int T, int F, int M, void* stream);
+EAB_API size_t eab_head_backward_workspace_bytes(int M);
+EAB_API int    eab_head_backward(const float* W1_dev, const float* b1_dev, const float* W2_dev, const float* b2_dev,
+                                 const float* h2_dev, const float* spec_dev, const float* d_out_dev, float* d_h2_dev, float* grads_dev,
+                                 int B, int T, int F, int M, void* workspace_dev, size_t workspace_bytes, void* stream);
+EAB_API int    eab_loss_com_mag_mse(const float* esti_dev, const float* label_dev, const int* frames_dev, int64_t frames_total, int B,
+                                    int T, int F, float* loss_dev, void* scratch16_dev, void* stream);
+EAB_API int    eab_loss_com_mag_mse_backward(const float* esti_dev, const float* label_dev, const int* frames_dev, int64_t frames_total,
+                                             int B, int T, int F, const float* grad_loss_dev, float* d_esti_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * I/O edges of enhance.py: the wav container and the sample-rate conversion.
  *   eab_wav_info / eab_wav_decode   `noisy, sr = torchaudio.load(path)` (enhance.py:35) on the bytes of a RIFF/WAVE file held
  *                                   in HOST memory: planar float32 [channels][frames], integer PCM scaled like torchaudio
