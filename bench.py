@@ -339,6 +339,97 @@ def config4(args, dev, net, world, rank, ins2, outs2):
             "value": nb_total * args.batch * args.seconds / dt, "unit": UNIT}
 
 
+def config5_training(args, dev, world, rank, local):
+    """BASELINE configs[4]: the training step of train_distributed.py:214-230 (batch 16 x 4 s per GPU, data-parallel, NCCL gradient
+    allreduce).  The backward pass of the product is NOT built beyond its first slice, so this object reports (a) the stated
+    baseline: the oracle port of the whole step in torch eager on this GPU (cuDNN / cuBLAS autograd), wrapped in
+    DistributedDataParallel when launched under torchrun, with the 35.16 MB gradient allreduce timed on its own; (b) the slice of
+    the step the product's hand-written kernels cover today (head tail + loss, forward and backward) at the same shapes."""
+    import torch
+    import torch.distributed as dist
+    from oracle import eabnet_oracle as O          # baseline leg only
+    from oracle import train_oracle as TO
+    Bt, Lt = args.train_batch, int(4.0 * SR)
+    torch.manual_seed(7 + rank)
+    model = TO.TrainableEaBNetWithPostNet().to(dev)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=5e-4)
+    wave, clean = O.make_wave(Bt, 9, Lt, seed=500 + rank)
+    wave, clean = wave.to(dev), clean.to(dev)
+
+    def step():
+        opt.zero_grad()
+        noisy = O.stft_compress(wave)                                            # prepare_data, test.py:20-47
+        target = O.stft_compress(clean.unsqueeze(1))[..., 0, :].permute(0, 3, 1, 2).contiguous()
+        out = net(noisy)
+        l = TO.loss_fn(out, target, [noisy.shape[1]] * Bt)
+        l["final"].backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        return l["final"].detach(), noisy, target, out
+
+    loss, noisy, target, out = step()                                            # warm-up (cuDNN plans, allocator)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nst = 3
+    e0.record()
+    for _ in range(nst):
+        loss, noisy, target, out = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_step = e0.elapsed_time(e1) / nst
+    nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    res = {"workload": "train_distributed.py:214-230 training step, EaBNetWithPostNet, batch %d x 4 s per GPU, %d rank(s)%s (BASELINE configs[4])"
+                       % (Bt, world, ", DistributedDataParallel over NCCL" if world > 1 else ""),
+           "baseline": {"kind": "port", "what": "oracle port of the training step in torch eager on cuda (autograd, Adam, clip_grad_norm_)",
+                        "ms_per_step": ms_step, "audio_s_per_s": world * Bt * 4.0 / (ms_step * 1e-3), "steps": nst,
+                        "loss": float(loss), "grad_bytes": nparam * 4}}
+    if world > 1:
+        flat = torch.zeros(nparam, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(flat)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ar = e0.elapsed_time(e1) / 10
+        res["baseline"]["allreduce_ms"] = ar
+        res["baseline"]["allreduce_busbw_GBps"] = 2.0 * (world - 1) / world * nparam * 4 / (ar * 1e-3) / 1e9
+    if rank == 0:
+        # the product's slice at the same shapes: h2 = a stand-in for the second LSTM's output, the real spectrum and target
+        from eabnet_b200.train import com_mag_mse_loss, head_filter_sum
+        sdm = dict(zip(model.names, model.values))
+        Wn = ["eabnet.bf_map.w_dnn.0.weight", "eabnet.bf_map.w_dnn.0.bias", "eabnet.bf_map.w_dnn.2.weight", "eabnet.bf_map.w_dnn.2.bias"]
+        Ws = [sdm[k].detach().clone().requires_grad_(True) for k in Wn]
+        T = noisy.shape[1]
+        h2 = torch.tanh(torch.randn(Bt, T, 161, 64, device=dev)).requires_grad_(True)
+        spec = noisy.detach()
+
+        def slice_step():
+            o = head_filter_sum(h2, spec, *Ws)
+            lo = com_mag_mse_loss(o, target)
+            return torch.autograd.grad(lo, [h2] + Ws)
+        for _ in range(2):
+            slice_step()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(5):
+            slice_step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        res["product_slice"] = {"what": "hand-written kernels: w_dnn + filter-and-sum forward / backward (d h2, dW1, db1, dW2, db2) and "
+                                        "com_mag_mse_loss forward / backward (csrc/head_bwd.cu)", "ms": e0.elapsed_time(e1) / 5,
+                                "rows": Bt * T * 161, "note": "everything upstream of h2 (LSTM, decoder, TCMs, encoder, STFT) has no backward kernel yet"}
+    del model, net, opt
+    torch.cuda.empty_cache()
+    return res
+
+
 def build_roofline(prof, ms_step, frames, peaks):
     """Per-family and whole-step roofline fractions on SURVEY 8(d) algorithmic bytes; `prof` = one profiled step."""
     fam = {}
@@ -406,6 +497,8 @@ def main():
     ap.add_argument("--no-config4", action="store_true", help="skip the 2048-utterance dataset-scale measurement (BASELINE configs[3])")
     ap.add_argument("--no-single", action="store_true", help="skip the one-utterance latency measurement (BASELINE configs[0] shape)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager-on-GPU baseline (oracle port on cuda)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the training-step object (BASELINE configs[4])")
+    ap.add_argument("--train-batch", type=int, default=16, help="utterances (4 s) per GPU of the training-step object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
 
@@ -528,6 +621,9 @@ def main():
     eager = gpu_eager_baseline(args, dev) if (rank == 0 and world == 1 and not args.no_gpu_eager) else None
     latency = stream_latency(args, dev) if args.stream_steps > 0 else None
     postnet = postnet_throughput(args, dev, wave) if (rank == 0 and not args.no_postnet) else None
+    del graphs
+    torch.cuda.empty_cache()
+    c5 = config5_training(args, dev, world, rank, local) if not args.no_config5 else None
 
     from eabnet_b200.shard import max_over_ranks
     ms, ms_e2e = max_over_ranks([ms, ms_e2e], dev)
@@ -564,6 +660,8 @@ def main():
             line["latency"] = latency
         if postnet is not None:
             line["postnet"] = postnet
+        if c5 is not None:
+            line["config5"] = c5
         if world == 1 and not args.no_cpu_baseline:
             val, med, cores, sample = cpu_reference_throughput(args.ref_batch, args.seconds, 3, 1)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
