@@ -38,6 +38,35 @@ __device__ __forceinline__ float ex2(float x) {          // one SFU op, ~2 ulp
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// two fp32 operations per instruction (sm_100: FFMA2 / FMUL2 / FADD2); each lane rounds exactly like the scalar form
+struct F2 { float x, y; };
+__device__ __forceinline__ uint64_t pk(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ F2 upk(uint64_t r) { F2 o; asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r)); return o; }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)), "l"(pk(c.x, c.y)));
+    return upk(d);
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)));
+    return upk(d);
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)));
+    return upk(d);
+}
+__device__ __forceinline__ F2 sub2(F2 a, F2 b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)));
+    return upk(d);
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 #ifdef EAB_LSTM_EXPERIMENT
 #define EXP_FLAG(bit) ((a.exp_flags & (bit)) != 0)
 #else
@@ -165,29 +194,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                 tmem_wait_ld();
                 float hv[8];
                 const float* bi = sbias + u * 128 + qtr * 32;   // biases pre-scaled by -log2(e) (i,f,o) / -2 log2(e) (g)
+                // 7 SFU ops per unit instead of 10: the sigmoid / tanh quotients share their reciprocals
+                //   c' = sig(f) c + sig(i) tanh(g) = [c (1+Ei)(1+Eg) + (1-Eg)(1+Ef)] / [(1+Ei)(1+Ef)(1+Eg)]
+                //   h  = sig(o) tanh(c')          = (1-Ec) / [(1+Eo)(1+Ec)]
+                // with Ei = e^-i, Ef = e^-f, Eg = e^-2g, Ec = e^-2c', Eo = e^-o.  The exponents are clamped from above
+                // only (2^40: the functions are saturated to < 1e-12 there and the triple product stays < 2^127).
+                // Two hidden units per instruction wherever the ISA has a packed fp32 form (the busiest scheduler of this
+                // kernel issues on 80 % of its cycles - ncu, profiles/r02_v3_lstm_full.txt - so the cell phase is bound by
+                // instruction issue as much as by the SFU): 43 instructions per unit PAIR instead of 38 per unit.
+                const F2 one = {1.f, 1.f}, nl = {-L2E, -L2E}, nl2 = {-2.f * L2E, -2.f * L2E};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    // 7 SFU ops per unit instead of 10: the sigmoid / tanh quotients share their reciprocals
-                    //   c' = sig(f) c + sig(i) tanh(g) = [c (1+Ei)(1+Eg) + (1-Eg)(1+Ef)] / [(1+Ei)(1+Ef)(1+Eg)]
-                    //   h  = sig(o) tanh(c')          = (1-Ec) / [(1+Eo)(1+Ec)]
-                    // with Ei = e^-i, Ef = e^-f, Eg = e^-2g, Ec = e^-2c', Eo = e^-o.  The exponents are clamped from above
-                    // only (2^40: the functions are saturated to < 1e-12 there and the triple product stays < 2^127).
+                for (int e = 0; e < 8; e += 2) {
                     if (EXP_FLAG(2)) {          // experiment: no SFU work at all
-                        const float cn = fmaf(c[u * 8 + e], __uint_as_float(gf[e]), __uint_as_float(gi[e]) * __uint_as_float(gg[e])) * 0.25f;
-                        c[u * 8 + e] = cn;
-                        hv[e] = cn * __uint_as_float(go[e]) * 0.01f;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float cn = fmaf(c[u * 8 + e + q], __uint_as_float(gf[e + q]), __uint_as_float(gi[e + q]) * __uint_as_float(gg[e + q])) * 0.25f;
+                            c[u * 8 + e + q] = cn;
+                            hv[e + q] = cn * __uint_as_float(go[e + q]) * 0.01f;
+                        }
                         continue;
                     }
-                    const float Ei = ex2(fminf(fmaf(__uint_as_float(gi[e]), -L2E, bi[e]), 40.f));
-                    const float Ef = ex2(fminf(fmaf(__uint_as_float(gf[e]), -L2E, bi[8 + e]), 40.f));
-                    const float Eg = ex2(fminf(fmaf(__uint_as_float(gg[e]), -2.f * L2E, bi[16 + e]), 40.f));
-                    const float Eo = ex2(fminf(fmaf(__uint_as_float(go[e]), -L2E, bi[24 + e]), 40.f));
-                    const float A = 1.f + Ei, Bf = 1.f + Ef, G = 1.f + Eg;
-                    const float AG = A * G;
-                    const float cn = __fdividef(fmaf(c[u * 8 + e], AG, (1.f - Eg) * Bf), AG * Bf);
-                    c[u * 8 + e] = cn;
-                    const float Ec = ex2(fminf(cn * (-2.f * L2E), 40.f));
-                    hv[e] = __fdividef(1.f - Ec, (1.f + Eo) * (1.f + Ec));
+                    const F2 ti = fma2({__uint_as_float(gi[e]), __uint_as_float(gi[e + 1])}, nl, {bi[e], bi[e + 1]});
+                    const F2 tf = fma2({__uint_as_float(gf[e]), __uint_as_float(gf[e + 1])}, nl, {bi[8 + e], bi[8 + e + 1]});
+                    const F2 tg = fma2({__uint_as_float(gg[e]), __uint_as_float(gg[e + 1])}, nl2, {bi[16 + e], bi[16 + e + 1]});
+                    const F2 to = fma2({__uint_as_float(go[e]), __uint_as_float(go[e + 1])}, nl, {bi[24 + e], bi[24 + e + 1]});
+                    const F2 Ei = {ex2(fminf(ti.x, 40.f)), ex2(fminf(ti.y, 40.f))};
+                    const F2 Ef = {ex2(fminf(tf.x, 40.f)), ex2(fminf(tf.y, 40.f))};
+                    const F2 Eg = {ex2(fminf(tg.x, 40.f)), ex2(fminf(tg.y, 40.f))};
+                    const F2 Eo = {ex2(fminf(to.x, 40.f)), ex2(fminf(to.y, 40.f))};
+                    const F2 A = add2(one, Ei), Bf = add2(one, Ef), G = add2(one, Eg);
+                    const F2 AG = mul2(A, G);
+                    const F2 num = fma2({c[u * 8 + e], c[u * 8 + e + 1]}, AG, mul2(sub2(one, Eg), Bf));
+                    const F2 den = mul2(AG, Bf);
+                    const F2 cn = mul2(num, {rcp_approx(den.x), rcp_approx(den.y)});
+                    c[u * 8 + e] = cn.x; c[u * 8 + e + 1] = cn.y;
+                    const F2 tc = mul2(cn, nl2);
+                    const F2 Ec = {ex2(fminf(tc.x, 40.f)), ex2(fminf(tc.y, 40.f))};
+                    const F2 hden = mul2(add2(one, Eo), add2(one, Ec));
+                    const F2 h = mul2(sub2(one, Ec), {rcp_approx(hden.x), rcp_approx(hden.y)});
+                    hv[e] = h.x; hv[e + 1] = h.y;
                 }
                 {   // fp32 copy for HBM: chunk c of a row lives at (c ^ (row & 7)) * 16 (conflict-free both ways)
                     if (u == 0 && t > 0) MBW(hs_free, (uint32_t)((t - 1) & 1));    // h_{t-1} has left the staging tile
