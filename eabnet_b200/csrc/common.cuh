@@ -212,6 +212,11 @@ struct UmmaConvArgs {
     int tiles_per_b;             // ceil(T*E / 128)
     unsigned long long* dbg;     // optional [16] cycle counters of CTA 0 (diagnostics), else null
     int stats_ld, stats_coff;    // statistics arrays are [B][stats_ld][2], this launch owns channels stats_coff.. (0 = [B][Cout][2])
+    // streaming (one frame per stream and launch): B == 1 and T == number of STREAMS, so a GEMM row is (stream, e) and all
+    // streams share one row space; sources / out / resid are rings [stream][RT][F][C], frame n = *step in slot n % RT, a tap dt
+    // reads frame n - dt (zeros before the stream's start frame)
+    const int* step; const int* start;
+    int out_RT, resid_RT;
 };
 bool umma_conv_supported(const UmmaConvArgs& a);
 int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st);

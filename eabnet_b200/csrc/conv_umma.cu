@@ -20,6 +20,8 @@
 // (A_hi B_hi + A_lo B_hi + A_hi B_lo) for fp32-grade accuracy where single-pass TF32 is not enough.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -48,7 +50,7 @@ __host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef) {
     s.b_stage_bytes = N * 128;
     s.stg_ld = Cout + 4;
     const int stage = A_STAGE_BYTES + s.b_stage_bytes;
-    const int fixed = TM * s.stg_ld * 4 + TM * 8 + 3 * ncoef * 4 + N * 4 + 256 + 64;
+    const int fixed = TM * s.stg_ld * 4 + 2 * TM * 8 + 3 * ncoef * 4 + N * 4 + 256 + 64;
     int ns = (227 * 1024 - 1024 - fixed) / stage;
     if (ns > 6) ns = 6;
     s.nstages = ns;
@@ -56,7 +58,7 @@ __host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef) {
     s.b_off = ns * A_STAGE_BYTES;
     s.stg_off = s.b_off + ns * s.b_stage_bytes;
     s.rowoff_off = s.stg_off + TM * s.stg_ld * 4;
-    s.coef_off = s.rowoff_off + TM * 8;
+    s.coef_off = s.rowoff_off + 2 * TM * 8;         // row offsets into out, and into resid (a ring of its own when streaming)
     s.bias_off = (s.coef_off + 3 * ncoef * 4 + 15) / 16 * 16;
     s.bar_off = s.bias_off + N * 4;
     s.total = s.bar_off + 256 + 1024;          // + slack for the 1024-byte alignment of the base
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     uint8_t* Bs = smem + sp.b_off;
     float* stg = reinterpret_cast<float*>(smem + sp.stg_off);
     long long* rowoff = reinterpret_cast<long long*>(smem + sp.rowoff_off);
+    long long* rowoff_r = rowoff + TM;
     float* coef = reinterpret_cast<float*>(smem + sp.coef_off);
     float* sbias = reinterpret_cast<float*>(smem + sp.bias_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
@@ -106,6 +109,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     const long long tile_begin = ntiles * blockIdx.x / gridDim.x;
     const long long tile_end = ntiles * (blockIdx.x + 1) / gridDim.x;
     const int rows_per_b = a.T * a.E;
+    const bool streaming = a.step != nullptr;
+    const int nfr = streaming ? __ldg(a.step) : 0;             // absolute frame index of this step
     const int chunks_per_pass_unit = a.ntaps * a.nslab;       // (tap, slab) pairs
     const int nchunks = chunks_per_pass_unit * a.npass;
 
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         const float* xb0 = nullptr;
         const float* xb1 = nullptr;
         int rt[RPP], rf[RPP];                   // frame index and e * in_stride of this thread's rows (big negative if ragged)
+        int rs[RPP];                            // streaming: rt = the row's STREAM, rs = that stream's start frame
         auto decode_tile = [&](long long tile) {
             const int b = (int)(tile / a.tiles_per_b);
             const int row0 = (int)(tile - (long long)b * a.tiles_per_b) * TM;
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 const int t = r / a.E;
                 rt[i] = r < rows_per_b ? t : -(1 << 28);
                 rf[i] = (r - t * a.E) * a.in_stride;
+                rs[i] = (streaming && a.start && r < rows_per_b) ? __ldg(a.start + t) : 0;
             }
         };
         auto issue_loads = [&](float4 (&v)[2 * RPP], uint32_t& mask) {
@@ -153,9 +160,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             for (int i = 0; i < RPP; ++i) {
                 v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int tt = rt[i] - dtv;
+                int tt = rt[i] - dtv;
                 const int fi = rf[i] + dfv;
-                if ((unsigned)tt < (unsigned)a.T && (unsigned)fi < (unsigned)a.Fin) {
+                if (streaming) {                 // frame n - dt of stream rt[i]: its ring slot, or the zeros of the causal padding
+                    const int RT = second ? a.src[1].RT : a.src[0].RT;
+                    const int fr = nfr - dtv;
+                    tt = (rt[i] >= 0 && fr >= rs[i]) ? rt[i] * RT + ring_slot(fr, RT) : -1;
+                }
+                if ((streaming ? tt >= 0 : (unsigned)tt < (unsigned)a.T) && (unsigned)fi < (unsigned)a.Fin) {
                     const float* p = xb + (uint32_t)((tt * a.Fin + fi) * C + cc);
                     if (!WIDE) {
                         v[2 * i] = __ldg(reinterpret_cast<const float4*>(p));
@@ -347,11 +359,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             {
                 const int r = row0 + row;
                 long long off = -1;
+                long long off_r = -1;
                 if (r < rows_per_b) {
                     const int t = r / a.E, e = r - t * a.E;
-                    off = ((((long long)b * a.T + t) * a.Fout) + (e * a.out_stride + a.out_off)) * a.out_ld + a.out_coff;
+                    const long long fo = e * a.out_stride + a.out_off;
+                    if (streaming) {
+                        off = (((long long)t * a.out_RT + ring_slot(nfr, a.out_RT)) * a.Fout + fo) * a.out_ld + a.out_coff;
+                        off_r = (((long long)t * a.resid_RT + ring_slot(nfr, a.resid_RT)) * a.Fout + fo) * a.out_ld + a.out_coff;
+                    } else {
+                        off = ((((long long)b * a.T + t) * a.Fout) + fo) * a.out_ld + a.out_coff;
+                        off_r = off;
+                    }
                 }
                 rowoff[row] = off;
+                rowoff_r[row] = off_r;
             }
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
@@ -395,7 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 float4 o = *reinterpret_cast<const float4*>(stg + r * ld + cq);
                 const long long off = rowoff[r];
                 if (a.resid) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + off + cq));
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + rowoff_r[r] + cq));
                     o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
                     if (a.nstats) *reinterpret_cast<float4*>(stg + r * ld + cq) = o;
                 }
@@ -458,6 +479,14 @@ bool umma_conv_supported(const UmmaConvArgs& a) {
 int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
     if (!umma_conv_supported(a)) return fail("conv_umma: unsupported shape");
     if (a.B <= 0 || a.T <= 0 || a.E <= 0) return 0;
+    if (a.step) {
+        if (a.B != 1 || a.nstats != 0 || a.out_RT < 1 || (a.resid && a.resid_RT < 1)) return fail("conv_umma: bad streaming launch");
+        for (int i = 0; i < a.nsrc; ++i) {
+            int back = 0;
+            for (int k = 0; k < a.ntaps; ++k) back = std::max(back, a.dt[k]);
+            if (a.src[i].RT < back + 1) return fail("conv_umma: source ring shorter than the receptive field");
+        }
+    }
     const Smem sp = smem_plan(a.N, a.Cout, a.ncoef);
     if (sp.nstages < 2) return fail("conv_umma: not enough shared memory for two stages");
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<false>), sp.total));

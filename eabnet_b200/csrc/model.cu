@@ -272,6 +272,7 @@ struct eab_model {
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
+    int opt_stream_umma = 1;      // streaming: the per-layer convs on the tcgen05 gather kernel (rows = streams x F); 0 = CUDA cores
     int opt_tcm_chain = 1;        // TCM stacks as single launches (tcm_chain.cu): a GaGNet module's three stacks / an EaBNet group; 2: one chain per launch, 3: cooperative grid-barrier form
     int opt_norm_log = 0;         // record where every InstanceNorm's (sum, sum of squares) of a forward live (eab_norm_stats)
     struct NormLog { int gamma; const double* stats; int C, count, B; };
@@ -1027,6 +1028,7 @@ struct Ctx {
     int next_RT = 0;          // ring size of the next allocation (0 = the default of 2: current + previous frame)
     int last_RT = 0;          // ring size of the last allocation (0 offline)
     bool tensor_ok() const { return m->opt_umma && !streaming; }
+    bool stream_umma() const { return m->opt_umma && streaming && m->opt_stream_umma; }      // conv_umma with ring addressing
     std::vector<TcmStreamDesc>* tcm_desc = nullptr;     // planning pass of eab_stream_reset: receives the descriptors
     std::vector<std::pair<size_t, size_t>>* per_stream = nullptr;      // planning pass: carried per-stream state to zero on a restart
     const TcmStreamDesc* tcm_desc_dev = nullptr;        // step: the table inside the state blob
@@ -1117,6 +1119,22 @@ bool to_plane_args(const UmmaConvArgs& u, PlaneConvArgs* p, int force_P = 0) {
     p->tiles_per_b = (int)(((long long)u.T * p->P + 127) / 128);
     p->nbuf = 1;
     return plane_conv_supported(*p);
+}
+
+// streaming: the variants of one layer on the tcgen05 gather kernel - all streams share one row space (B = 1, "frames" = streams)
+int run_umma_stream(Ctx& cx, UmmaConvArgs* us, int n, int out_RT, int resid_RT) {
+    if (cx.dry) return 0;
+    for (int i = 0; i < n; ++i) {
+        UmmaConvArgs& u = us[i];
+        for (int k = 0; k < u.nsrc; ++k)
+            if (u.src[k].x2) return fail("internal: lazy residual sum in a streaming step");
+        u.B = 1; u.T = cx.B;
+        u.tiles_per_b = (int)(((long long)cx.B * u.E + 127) / 128);
+        u.step = cx.step; u.start = cx.start; u.out_RT = out_RT; u.resid_RT = resid_RT;
+        u.nstats = 0;
+        EAB_TRY(launch_conv_umma(u, cx.st));
+    }
+    return 0;
 }
 
 int launch_tensor_conv(eab_model* m, const UmmaConvArgs& u, cudaStream_t st) {
@@ -1282,7 +1300,7 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
             return launch_conv_staged(p, cx.st);
         }
     }
-    if (cx.tensor_ok() && L.umma_ok) {
+    if ((cx.tensor_ok() || cx.stream_umma()) && L.umma_ok) {
         UmmaConvArgs us[4];
         bool all_ok = true;
         int nus = 0;
@@ -1312,6 +1330,7 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
         if (all_ok) {
             allocate_out();
             for (int i = 0; i < nus; ++i) us[i].out = out->data;
+            if (cx.streaming) return run_umma_stream(cx, us, nus, out->RT, 0);
             return run_tensor_convs(cx, us, nus);
         }
     }
@@ -1441,7 +1460,7 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
 int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const float* bias, int Cout, int N, int gate_off,
                   int ntaps, const int* dt, int relu, const float* resid, int nstats, double** stats,
                   const float** stat_alpha, Act* out, const UmmaW* uw = nullptr, bool preallocated = false, int resid_RT = 0) {
-    const bool use_umma = uw && uw->ok && cx.tensor_ok() && (resid == nullptr || uw->ld == Cout);
+    const bool use_umma = uw && uw->ok && (cx.tensor_ok() || cx.stream_umma()) && (resid == nullptr || uw->ld == Cout);
     if (!preallocated) {
         out->F = srcs[0].F;
         out->C = use_umma ? uw->ld : Cout;      // the tcgen05 path may pad the channel count (e.g. 18 -> 32, zeros)
@@ -1474,6 +1493,7 @@ int run_pointwise(Ctx& cx, const Act* srcs, int nsrc, const float* W, const floa
             u.tiles_per_b = (cx.T * u.E + 127) / 128;
             if (!umma_conv_supported(u)) return fail("internal: pointwise layer rejected by the tcgen05 path");
         }
+        if (cx.streaming) return run_umma_stream(cx, us, uw->nsplit, out->RT, resid_RT);
         return run_tensor_convs(cx, us, uw->nsplit);
     }
     if (cx.dry) return 0;
@@ -1772,8 +1792,8 @@ int run_gag_in(Ctx& cx, const GagIn& in, const Act& feat, const Act& pre, Act* o
     out->F = 1; out->C = c.d_feat; out->xf = xform_identity();
     out->data = cx.alloc_act((size_t)cx.B * cx.T * c.d_feat);
     out->RT = cx.last_RT;
-    if (!cx.tensor_ok()) {
-        // CUDA-core path (streaming, option umma = 0): the dense [K][value | gate] matrix of every column split; the split's
+    if (!cx.tensor_ok() && !cx.stream_umma()) {
+        // CUDA-core path (streaming with stream_umma = 0, option umma = 0): the dense [K][value | gate] matrix of every column split; the split's
         // SW output channels are position `sp` of a [.., nsplit, SW] view of the d_feat-wide row
         if (cx.dry) return 0;
         for (int sp = 0; sp < in.nsplit; ++sp) {
@@ -1812,7 +1832,8 @@ int run_gag_in(Ctx& cx, const GagIn& in, const Act& feat, const Act& pre, Act* o
         u.out = out->data; u.out_ld = c.d_feat; u.out_coff = sp * in.SW;
         u.tiles_per_b = (cx.T + 127) / 128;
         if (feat.C + pre.C != in.K || !umma_conv_supported(u)) return fail("internal: GaGNet input conv rejected by the tcgen05 path");
-        EAB_TRY(run_tensor_convs(cx, &u, 1));
+        if (cx.streaming) EAB_TRY(run_umma_stream(cx, &u, 1, out->RT, 0));
+        else EAB_TRY(run_tensor_convs(cx, &u, 1));
     }
     return 0;
 }
@@ -2539,6 +2560,7 @@ int eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host,
 
 size_t eab_stream_state_bytes(const eab_model* m, int n_streams) {
     StreamLayout L;
+    if (m && m->dirty) { fail("eab_stream_state_bytes: commit the parameters first (the layout depends on which layers run on the tensor cores)"); return 0; }
     if (!m || stream_layout(const_cast<eab_model*>(m), n_streams, &L)) return 0;
     return L.total;
 }
@@ -2749,6 +2771,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "host_graph") m->opt_host_graph = value != 0;
     else if (n == "dual_stream") m->opt_dual_stream = value != 0;
     else if (n == "stream_tcm") m->opt_stream_tcm = value != 0;
+    else if (n == "stream_umma") m->opt_stream_umma = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "stft_tc") g_stft_tc = value != 0;
     else if (n == "fused_head") m->opt_fused_head = value != 0;

@@ -470,6 +470,10 @@ class EaBNetStream:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.net, self.S, self.dev, self.use_graph = net, int(n_streams), dev, graph
         lib, h = net._native.lib, net._native.h
+        with torch.cuda.device(dev):
+            net._sync_params(dev)                # the state layout depends on the committed weights (tensor-core images)
+            if postnet is not None:
+                postnet._sync_params(dev)
         nbytes = lib.eab_stream_state_bytes(h, self.S)
         if nbytes == 0:
             _lib.check(1, "eab_stream_state_bytes")

@@ -98,6 +98,8 @@ class GaGNetStream:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.net, self.S, self.dev = net, int(n_streams), dev
         lib, h = net._native.lib, net._native.h
+        with torch.cuda.device(dev):
+            net._sync_params(dev)
         nbytes = lib.eab_stream_state_bytes(h, self.S)
         if nbytes == 0:
             _lib.check(1, "eab_stream_state_bytes")
