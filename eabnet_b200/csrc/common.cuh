@@ -84,6 +84,24 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 #endif
 
 #ifdef __CUDACC__
+// Programmatic dependent launch, for the streaming step only (chains of ~90 launches of 5-20 us: the next kernel's launch latency
+// and prologue - barrier init, TMEM allocation, static weights - run under the tail of its predecessor).  The kernel must
+// execute pdl_wait() before it reads anything an earlier kernel of the stream wrote, and may call pdl_trigger() at any point.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
+#ifdef __CUDACC__
 // coefficients for channel c of batch b (called once per CTA per channel, not per element)
 __device__ __forceinline__ void xform_coeffs(const Xform& xf, int b, int C, int c, float& s, float& h, float& a) {
     s = 1.f; h = 0.f; a = 1.f;

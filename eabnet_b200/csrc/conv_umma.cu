@@ -103,6 +103,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (a.step) {                 // streaming launches are programmatic dependents (launch_k_pdl): everything above ran under the
+        pdl_trigger();            // predecessor's tail; nothing below may start before its results are visible
+        pdl_wait();
+    }
 
     // contiguous tile range of this CTA
     const long long ntiles = (long long)a.B * a.tiles_per_b;
@@ -259,7 +263,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 hi[i] = make_uint4(pack_h2(v[2 * i].x, v[2 * i].y), pack_h2(v[2 * i].z, v[2 * i].w),
                                    pack_h2(v[2 * i + 1].x, v[2 * i + 1].y), pack_h2(v[2 * i + 1].z, v[2 * i + 1].w));
             for (int pass = 0; pass < a.npass; ++pass) {
-                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_wait_backoff(&empty[stage], phase ^ 1, 20u);      // (polling: the suspend-hinted wait pays a wake-up latency per handshake,
+                                                                       //  15-20 us of a one-tile streaming launch)
                 uint8_t* A = As + stage * A_STAGE_BYTES + st_off;
                 if (pass == 1) {                 // residual of the fp16 rounding, itself rounded to fp16
 #pragma unroll
@@ -301,11 +306,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long tile = tile_begin; tile < tile_end; ++tile) {
-            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            mbar_wait_spin(&acc_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.N);
             for (int ch = 0; ch < nchunks; ++ch) {
-                mbar_wait(&full[stage], phase);
+                mbar_wait_spin(&full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_addr = smem_u32(As + stage * A_STAGE_BYTES);
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         for (long long tile = tile_begin; tile < tile_end; ++tile) {
             for (int unit = 0; unit < chunks_per_pass_unit; ++unit) {
                 for (int pass = 0; pass < a.npass; ++pass) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_wait_backoff(&empty[stage], phase ^ 1, 32u);
                     if (lane == 0) {
                         const float* img = (pass == 2 ? a.Wlo : a.Whi) + (size_t)unit * a.N * 32;     // N rows x 128 B
                         mbar_arrive_expect_tx(&full[stage], bytes);
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 rowoff[row] = off;
                 rowoff_r[row] = off_r;
             }
-            mbar_wait(&acc_full[acc], acc_phase);
+            mbar_wait_backoff(&acc_full[acc], acc_phase, 64u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.N);
             for (int c0 = 0; c0 < a.Cout; c0 += 16) {
@@ -503,7 +508,10 @@ int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
                  4.0 * (pos * a.in_stride * kreal / (a.out_stride > 1 ? 2.0 : 1.0) / (a.wide ? (double)a.kwidth / a.src[0].C / 2.0 : 1.0) +
                         pos * a.Cout * (a.resid ? 2 : 1) + (double)a.ntaps * kreal * a.N),
                  st);
-    if (a.wide) EAB_CUDA(launch_k(conv_umma_kernel<true>, dim3(grid), dim3(NTHREADS), (size_t)sp.total, st, a));
+    if (a.step) {
+        if (a.wide) EAB_CUDA(launch_k_pdl(conv_umma_kernel<true>, dim3(grid), dim3(NTHREADS), (size_t)sp.total, st, a));
+        else EAB_CUDA(launch_k_pdl(conv_umma_kernel<false>, dim3(grid), dim3(NTHREADS), (size_t)sp.total, st, a));
+    } else if (a.wide) EAB_CUDA(launch_k(conv_umma_kernel<true>, dim3(grid), dim3(NTHREADS), (size_t)sp.total, st, a));
     else EAB_CUDA(launch_k(conv_umma_kernel<false>, dim3(grid), dim3(NTHREADS), (size_t)sp.total, st, a));
     EAB_LAUNCH_CHECK("conv_umma_kernel");
     return 0;
