@@ -301,6 +301,8 @@ EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, in
  *   "host_graph" (1) / "dual_stream" (1)   eab_enhance_host_batches: replay each slot's step from a CUDA graph / alternate
  *                       batches on two compute streams
  *   "stream_tcm" (1)    streaming: the TCM stack as one launch
+ *   "stream_umma" (1)   streaming: the per-layer convs on the tcgen05 gather kernel (all streams in one GEMM row space); 0 = CUDA cores
+ *   "norm_log" (0)      record the InstanceNorm statistics of the next eab_forward for eab_norm_stats (BN calibration)
  *   "raw_grid" (0), "dbg_launch" (-1), "lstm_exp" (0)   diagnostics (grid cap of conv_raw so that small inputs walk many tiles per
  *                       CTA; which tensor-core conv launch fills eab_debug_counters; LSTM ablation switches of debug builds)
  * Changing an option invalidates the CUDA graphs eab_enhance_host_batches has captured (they are re-captured on next use). */
