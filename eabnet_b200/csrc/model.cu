@@ -2560,7 +2560,6 @@ int eab_enhance_host(eab_model* m, const float* wave_host, float* enhanced_host,
 
 size_t eab_stream_state_bytes(const eab_model* m, int n_streams) {
     StreamLayout L;
-    if (m && m->dirty) { fail("eab_stream_state_bytes: commit the parameters first (the layout depends on which layers run on the tensor cores)"); return 0; }
     if (!m || stream_layout(const_cast<eab_model*>(m), n_streams, &L)) return 0;
     return L.total;
 }
