@@ -548,7 +548,7 @@ def main():
             graphs, streams = [], [torch.cuda.current_stream(dev)]
             run_step = lambda i: net.enhance(wave)            # noqa: E731
         else:
-            ng = 1 if args.single_stream else 2
+            ng = 1 if args.single_stream else int(os.environ.get("EAB_BENCH_STREAMS", "2"))
             graphs = [net.graphed_enhance(wave, private_workspace=True) for _ in range(ng)]
             streams = [torch.cuda.Stream(dev) for _ in range(ng)]
 
