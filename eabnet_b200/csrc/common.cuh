@@ -374,6 +374,18 @@ struct LstmArgs {
     int exp_flags;               // diagnostics builds only
 };
 int launch_lstm(const LstmArgs& a, cudaStream_t st);
+
+// streaming LSTM step on the tensor cores: the two elementwise kernels around the gate GEMM (lstm.cu)
+struct LstmFrameArgs {
+    const float* x; int x_RT; Xform xf; int layer_norm; const float* ln_g; const float* ln_b;     // ln: source ring -> out [rows][64]
+    const float* gates; int gates_ld;                                                               // cell: [rows][gates_ld]
+    float* c_state; float* h_state;                                                                 // [rows][64]
+    float* out; int out_RT;                                                                         // ln: [rows][64]; cell: ring [S][out_RT][F][64]
+    const int* step;
+    int rows, F;                                                                                    // rows = streams x F
+};
+int launch_lstm_ln_frame(const LstmFrameArgs& a, cudaStream_t st);
+int launch_lstm_cell_frame(const LstmFrameArgs& a, cudaStream_t st);
 bool lstm_umma_supported(const LstmArgs& a);
 int launch_lstm_umma(const LstmArgs& a, cudaStream_t st);
 

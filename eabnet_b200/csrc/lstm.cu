@@ -265,7 +265,85 @@ int launch_e(const LstmArgs& a, cudaStream_t st) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming step on the tensor cores (one frame per stream): the gate pre-activations [x_t, h_{t-1}] [W_ih ; W_hh]^T + b are
+// one tcgen05 GEMM over all (stream, f) rows (conv_umma, two sources, K = 64 + 64, N = 256: run_pointwise in model_run.cu);
+// these two bandwidth-bound kernels do what surrounds it.
+//   lstm_ln_frame_kernel    x_t of every stream from its ring slot -> norm + PReLU (Xform) -> LayerNorm(64) -> [rows][64]
+//   lstm_cell_frame_kernel  gates [rows][256] (i | f | g | o, 64 each) + c_{t-1} -> c_t, h_t -> state and the output ring slot
+__global__ void __launch_bounds__(256) lstm_ln_frame_kernel(const LstmFrameArgs a) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);         // a warp per (stream, f) row, 2 channels per lane
+    if (row >= a.rows) return;
+    const int lane = threadIdx.x & 31;
+    const int s = row / a.F, f = row - s * a.F;
+    const int n = __ldg(a.step);
+    const float* xp = a.x + (((size_t)s * a.x_RT + ring_slot(n, a.x_RT)) * a.F + f) * 64 + lane * 2;
+    float2 v = *reinterpret_cast<const float2*>(xp);
+    float vv[2] = {v.x, v.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float cs, ch, ca;
+        xform_coeffs(a.xf, s, 64, lane * 2 + k, cs, ch, ca);
+        float z = vv[k];
+        if (a.xf.prelu == 1) { z = prelu_f(z, ca); z = fmaf(z, cs, ch); }
+        else { z = fmaf(z, cs, ch); if (a.xf.prelu == 2) z = prelu_f(z, ca); }
+        vv[k] = z;
+    }
+    if (a.layer_norm) {
+        float sum = vv[0] + vv[1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.f / 64.f);
+        const float d0 = vv[0] - mean, d1 = vv[1] - mean;
+        float sq = d0 * d0 + d1 * d1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq * (1.f / 64.f) + 1e-5f);
+        vv[0] = d0 * rstd * __ldg(a.ln_g + lane * 2) + __ldg(a.ln_b + lane * 2);
+        vv[1] = d1 * rstd * __ldg(a.ln_g + lane * 2 + 1) + __ldg(a.ln_b + lane * 2 + 1);
+    }
+    *reinterpret_cast<float2*>(a.out + (size_t)row * 64 + lane * 2) = make_float2(vv[0], vv[1]);
+}
+
+__global__ void __launch_bounds__(256) lstm_cell_frame_kernel(const LstmFrameArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (row, 4 hidden units)
+    if (i >= (long long)a.rows * 16) return;
+    const int row = (int)(i >> 4), j = (int)(i & 15) * 4;
+    const float* g = a.gates + (size_t)row * a.gates_ld;
+    const float4 gi = *reinterpret_cast<const float4*>(g + j), gf = *reinterpret_cast<const float4*>(g + 64 + j),
+                 gg = *reinterpret_cast<const float4*>(g + 128 + j), go = *reinterpret_cast<const float4*>(g + 192 + j);
+    float4 c = *reinterpret_cast<const float4*>(a.c_state + (size_t)row * 64 + j);
+    float4 h;
+    c.x = sigmoid_f(gf.x) * c.x + sigmoid_f(gi.x) * tanh_f(gg.x); h.x = sigmoid_f(go.x) * tanh_f(c.x);
+    c.y = sigmoid_f(gf.y) * c.y + sigmoid_f(gi.y) * tanh_f(gg.y); h.y = sigmoid_f(go.y) * tanh_f(c.y);
+    c.z = sigmoid_f(gf.z) * c.z + sigmoid_f(gi.z) * tanh_f(gg.z); h.z = sigmoid_f(go.z) * tanh_f(c.z);
+    c.w = sigmoid_f(gf.w) * c.w + sigmoid_f(gi.w) * tanh_f(gg.w); h.w = sigmoid_f(go.w) * tanh_f(c.w);
+    *reinterpret_cast<float4*>(a.c_state + (size_t)row * 64 + j) = c;
+    *reinterpret_cast<float4*>(a.h_state + (size_t)row * 64 + j) = h;
+    const int s = row / a.F, f = row - s * a.F;
+    const int n = __ldg(a.step);
+    *reinterpret_cast<float4*>(a.out + (((size_t)s * a.out_RT + ring_slot(n, a.out_RT)) * a.F + f) * 64 + j) = h;
+}
+
 }  // namespace
+
+int launch_lstm_ln_frame(const LstmFrameArgs& a, cudaStream_t st) {
+    if (a.rows <= 0) return 0;
+    if (!a.step || !a.x || !a.out || a.x_RT < 1) return fail("lstm_ln_frame: bad arguments");
+    ProfScope ps("lstm_frame", 0.0, 8.0 * a.rows * 64, st);
+    EAB_CUDA(launch_k(lstm_ln_frame_kernel, dim3((a.rows + 7) / 8), dim3(256), (size_t)0, st, a));
+    EAB_LAUNCH_CHECK("lstm_ln_frame_kernel");
+    return 0;
+}
+
+int launch_lstm_cell_frame(const LstmFrameArgs& a, cudaStream_t st) {
+    if (a.rows <= 0) return 0;
+    if (!a.step || !a.gates || !a.c_state || !a.h_state || !a.out || a.out_RT < 1 || a.gates_ld < 256) return fail("lstm_cell_frame: bad arguments");
+    ProfScope ps("lstm_frame", 0.0, 4.0 * a.rows * (256 + 4 * 64), st);
+    EAB_CUDA(launch_k(lstm_cell_frame_kernel, dim3((unsigned)(((long long)a.rows * 16 + 255) / 256)), dim3(256), (size_t)0, st, a));
+    EAB_LAUNCH_CHECK("lstm_cell_frame_kernel");
+    return 0;
+}
 
 int launch_lstm(const LstmArgs& a, cudaStream_t st) {
     if (a.F < 8) return fail("lstm: F < 8 is not supported");

@@ -172,6 +172,8 @@ struct eab_model {
     UmmaW u_dnn[2], u_cnn;
     size_t off_rnn_img[2] = {0, 0}, off_rnn_ubias[2] = {0, 0};
     bool rnn_umma_ok = false;
+    size_t off_rnn_step[2] = {0, 0}, off_rnn_step_b[2] = {0, 0};      // streaming gate GEMM: dense [x | h][256] + bias
+    UmmaW u_rnn_step[2];
 
     // device state
     float* blob = nullptr;
@@ -205,6 +207,7 @@ struct eab_model {
     int opt_head_w_tap = 0;       // also write the beam weights (debug tap "w") from the fused head kernel
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
+    int opt_stream_lstm = 1;      // streaming: the LSTM step as a tensor-core gate GEMM + cell kernel (needs stream_umma); 0 = CUDA-core lstm kernel
     int opt_stream_umma = 1;      // streaming: the per-layer convs on the tcgen05 gather kernel (rows = streams x F); 0 = CUDA cores
     int opt_tcm_chain = 1;        // TCM stacks as single launches (tcm_chain.cu): a GaGNet module's three stacks / an EaBNet group; 2: one chain per launch, 3: cooperative grid-barrier form
     int opt_norm_log = 0;         // record where every InstanceNorm's (sum, sum of squares) of a forward live (eab_norm_stats)

@@ -382,6 +382,24 @@ struct Packer {
                     }
                 }
             }
+            // streaming step on the tensor cores: the gate GEMM [x_t, h_{t-1}] (K = 64 + 64) x dense [128][256] (column = torch
+            // gate row g*64 + j), bias b_ih + b_hh
+            if (m->rnn_umma_ok) {
+                for (int r = 0; r < 2; ++r) {
+                    m->off_rnn_step[r] = alloc((size_t)128 * 256);
+                    std::vector<float> bsum(256);
+                    for (int n = 0; n < 256; ++n) {
+                        bsum[n] = P(m->rnn[r][2])[n] + P(m->rnn[r][3])[n];
+                        for (int k = 0; k < 64; ++k) {
+                            blob[m->off_rnn_step[r] + (size_t)k * 256 + n] = P(m->rnn[r][0])[(size_t)n * 64 + k];
+                            blob[m->off_rnn_step[r] + (size_t)(64 + k) * 256 + n] = P(m->rnn[r][1])[(size_t)n * 64 + k];
+                        }
+                    }
+                    m->off_rnn_step_b[r] = alloc(256);
+                    for (int n = 0; n < 256; ++n) blob[m->off_rnn_step_b[r] + n] = bsum[n];
+                    m->u_rnn_step[r] = umma_images(m->off_rnn_step[r], 1, 128, 256, 256, false, 0, bsum.data());
+                }
+            }
             m->off_dnn_w[0] = linear(m->dnn_w[0], m->dnn_b[0], H, H, &m->dnn_N[0], &m->off_dnn_b[0]);
             m->off_dnn_w[1] = linear(m->dnn_w[1], m->dnn_b[1], 2 * c.M, H, &m->dnn_N[1], &m->off_dnn_b[1]);
             {

@@ -734,7 +734,38 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
                         continue;
                     }
                 }
-                EAB_TRY(launch_lstm(a, cx.st));
+                if (!(cx.stream_umma() && m->rnn_umma_ok && m->u_rnn_step[l].ok && m->opt_stream_lstm)) EAB_TRY(launch_lstm(a, cx.st));
+            }
+            if (cx.stream_umma() && m->rnn_umma_ok && (cx.dry || m->u_rnn_step[l].ok) && m->opt_stream_lstm) {
+                // streaming step on the tensor cores: [LayerNorm kernel ->] gate GEMM over all (stream, f) rows -> cell kernel
+                const Act& src = l ? h[0] : emb;
+                Act xin = src;
+                if (l == 0) {
+                    xin.F = c.n_freq; xin.C = 64; xin.xf = xform_identity();
+                    cx.next_RT = 1; xin.data = cx.alloc_act((size_t)cx.B * c.n_freq * 64); xin.RT = 1;
+                    if (!cx.dry) {
+                        LstmFrameArgs f;
+                        memset(&f, 0, sizeof(f));
+                        f.x = src.data; f.x_RT = src.RT; f.xf = src.xf; f.layer_norm = 1;
+                        f.ln_g = cx.W(m->off_ln_g); f.ln_b = cx.W(m->off_ln_b);
+                        f.out = xin.data; f.step = cx.step; f.rows = cx.B * c.n_freq; f.F = c.n_freq;
+                        EAB_TRY(launch_lstm_ln_frame(f, cx.st));
+                    }
+                }
+                Act hprev;
+                hprev.F = c.n_freq; hprev.C = 64; hprev.xf = xform_identity(); hprev.data = hc_state[0]; hprev.RT = 1;
+                Act pair[2] = {xin, hprev};
+                Act gates;
+                cx.next_RT = 1;
+                EAB_TRY(run_pointwise(cx, pair, 2, cx.W(m->off_rnn_step[l]), cx.W(m->off_rnn_step_b[l]), 256, 256, 0, 1, nullptr, 0, nullptr, 0,
+                                      nullptr, nullptr, &gates, &m->u_rnn_step[l]));
+                if (!cx.dry) {
+                    LstmFrameArgs f;
+                    memset(&f, 0, sizeof(f));
+                    f.gates = gates.data; f.gates_ld = gates.C; f.c_state = hc_state[1]; f.h_state = hc_state[0];
+                    f.out = h[l].data; f.out_RT = h[l].RT; f.step = cx.step; f.rows = cx.B * c.n_freq; f.F = c.n_freq;
+                    EAB_TRY(launch_lstm_cell_frame(f, cx.st));
+                }
             }
             tap(cx, l ? "h2" : "h1", h[l]);
         }
