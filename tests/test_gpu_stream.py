@@ -19,10 +19,15 @@ def _net(cfg, variant="B", seed=0):
     return net.cuda(), sd
 
 
+@pytest.mark.parametrize("opts", [{}, {"stream_umma": 0}, {"stream_lstm": 0}, {"stream_tcm": 0}])
 @pytest.mark.parametrize("extra", [{}, {"is_u2": False, "bf_type": "cnn", "M": 4}, {"intra_connect": "add"}])
-def test_stream_spec_frames_match_offline_oracle(extra):
+def test_stream_spec_frames_match_offline_oracle(extra, opts):
+    """default: per-layer convs and the LSTM gate GEMM on the tensor cores (conv_umma with ring addressing), fused TCM kernel;
+    opts switch each of them back to the CUDA-core / per-layer form"""
     cfg = O.make_cfg(norm_type="BN", **extra)
     net, sd = _net(cfg, seed=3)
+    for k, v in opts.items():
+        net.set_option(k, v)
     S, T = 3, 70                                   # 70 frames: deeper than the largest TCM dilation ring (4*32+1 = 129? no: covers d<=16 fully, d=32 partially)
     wave, _ = O.make_wave(S, cfg["M"], 160 * (T - 1), seed=11)
     spec = O.stft_compress(wave)                   # [S,T,161,M,2]
