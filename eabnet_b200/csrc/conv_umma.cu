@@ -42,20 +42,33 @@ constexpr int A_STAGE_BYTES = TM * 128;
 struct Smem {
     // offsets (bytes) into the 1024-aligned dynamic shared memory
     int a_off, b_off, stg_off, rowoff_off, coef_off, bias_off, bar_off, total;
-    int nstages, b_stage_bytes, stg_ld;
+    int nstages, a_stage_bytes, b_stage_bytes, stg_ld;
+    int merged;                 // 3-pass layers: ONE ring stage per (tap, slab) holds A hi | A lo and W hi | W lo
 };
 
-__host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef) {
+// A 3-pass layer used to push three stages per (tap, slab) through the ring - A hi twice - each with its own wait, proxy fence
+// and arrive; a single-tile CTA (every launch of a streaming step) spent most of its ~14 us on those 27-54 handshakes.  Merged
+// stages hold both halves of the split once: one handshake and twelve MMAs per (tap, slab).  Falls back to per-pass stages when
+// two merged stages do not fit (N = 256).
+__host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef, int npass) {
     Smem s;
-    s.b_stage_bytes = N * 128;
     s.stg_ld = Cout + 4;
-    const int stage = A_STAGE_BYTES + s.b_stage_bytes;
     const int fixed = TM * s.stg_ld * 4 + 2 * TM * 8 + 3 * ncoef * 4 + N * 4 + 256 + 64;
-    int ns = (227 * 1024 - 1024 - fixed) / stage;
+    const int avail = 227 * 1024 - 1024 - fixed;
+    s.merged = 0;
+    s.a_stage_bytes = A_STAGE_BYTES;
+    s.b_stage_bytes = N * 128;
+    if (npass == 3 && avail / (2 * (A_STAGE_BYTES + N * 128)) >= 2) {
+        s.merged = 1;
+        s.a_stage_bytes = 2 * A_STAGE_BYTES;
+        s.b_stage_bytes = 2 * N * 128;
+    }
+    const int stage = s.a_stage_bytes + s.b_stage_bytes;
+    int ns = avail / stage;
     if (ns > 6) ns = 6;
     s.nstages = ns;
     s.a_off = 0;
-    s.b_off = ns * A_STAGE_BYTES;
+    s.b_off = ns * s.a_stage_bytes;
     s.stg_off = s.b_off + ns * s.b_stage_bytes;
     s.rowoff_off = s.stg_off + TM * s.stg_ld * 4;
     s.coef_off = s.rowoff_off + 2 * TM * 8;         // row offsets into out, and into resid (a ring of its own when streaming)
@@ -71,7 +84,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     // align to 1024 B (128B-swizzle atom) by OFFSETTING the __shared__ array: a round trip through uintptr_t would
     // demote every later access to generic ST.E / LD.E
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef);
+    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass);
     uint8_t* As = smem + sp.a_off;
     uint8_t* Bs = smem + sp.b_off;
     float* stg = reinterpret_cast<float*>(smem + sp.stg_off);
@@ -116,7 +129,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     const bool streaming = a.step != nullptr;
     const int nfr = streaming ? __ldg(a.step) : 0;             // absolute frame index of this step
     const int chunks_per_pass_unit = a.ntaps * a.nslab;       // (tap, slab) pairs
-    const int nchunks = chunks_per_pass_unit * a.npass;
+    const int nchunks = chunks_per_pass_unit * (sp.merged ? 1 : a.npass);      // ring stages per tile
 
     if (warp < NPROD / 32) {
         // =========================================================================== A producers
@@ -262,10 +275,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             for (int i = 0; i < RPP; ++i)
                 hi[i] = make_uint4(pack_h2(v[2 * i].x, v[2 * i].y), pack_h2(v[2 * i].z, v[2 * i].w),
                                    pack_h2(v[2 * i + 1].x, v[2 * i + 1].y), pack_h2(v[2 * i + 1].z, v[2 * i + 1].w));
+            if (sp.merged) {
+                mbar_wait_backoff(&empty[stage], phase ^ 1, 20u);
+                uint8_t* A = As + stage * sp.a_stage_bytes + st_off;
+#pragma unroll
+                for (int i = 0; i < RPP; ++i) {
+                    *reinterpret_cast<uint4*>(A + i * 4096) = hi[i];
+                    *reinterpret_cast<uint4*>(A + A_STAGE_BYTES + i * 4096) =
+                        make_uint4(pack_lo_h2(v[2 * i].x, v[2 * i].y, hi[i].x), pack_lo_h2(v[2 * i].z, v[2 * i].w, hi[i].y),
+                                   pack_lo_h2(v[2 * i + 1].x, v[2 * i + 1].y, hi[i].z), pack_lo_h2(v[2 * i + 1].z, v[2 * i + 1].w, hi[i].w));
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[stage]);
+                if (++stage == NS) { stage = 0; phase ^= 1; }
+            } else
             for (int pass = 0; pass < a.npass; ++pass) {
                 mbar_wait_backoff(&empty[stage], phase ^ 1, 20u);      // (polling: the suspend-hinted wait pays a wake-up latency per handshake,
                                                                        //  15-20 us of a one-tile streaming launch)
-                uint8_t* A = As + stage * A_STAGE_BYTES + st_off;
+                uint8_t* A = As + stage * sp.a_stage_bytes + st_off;
                 if (pass == 1) {                 // residual of the fp16 rounding, itself rounded to fp16
 #pragma unroll
                     for (int i = 0; i < RPP; ++i)
@@ -313,8 +340,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 mbar_wait_spin(&full[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(As + stage * A_STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(As + stage * sp.a_stage_bytes);
                     const uint32_t b_addr = smem_u32(Bs + stage * sp.b_stage_bytes);
+                    if (sp.merged) {            // A hi W hi + A lo W hi + A hi W lo from one stage
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) {
+                            const uint32_t aa = a_addr + (g == 1 ? A_STAGE_BYTES : 0);
+                            const uint32_t bb = b_addr + (g == 2 ? a.N * 128 : 0);
+#pragma unroll
+                            for (int k = 0; k < KC / 16; ++k)
+                                umma_f16(d_tmem, make_desc(aa + k * 32), make_desc(bb + k * 32), idesc, (ch | g | k) ? 1u : 0u);
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k) {
                         const uint64_t ad = make_desc(a_addr + k * 32);
@@ -333,9 +370,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         // =========================================================================== B (weight) loader
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t bytes = (uint32_t)sp.b_stage_bytes;
+        const uint32_t bytes = (uint32_t)(a.N * 128);                // one weight image: N rows x 128 B
         for (long long tile = tile_begin; tile < tile_end; ++tile) {
             for (int unit = 0; unit < chunks_per_pass_unit; ++unit) {
+                if (sp.merged) {
+                    mbar_wait_backoff(&empty[stage], phase ^ 1, 32u);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+                        bulk_copy_g2s(Bs + stage * sp.b_stage_bytes, a.Whi + (size_t)unit * a.N * 32, bytes, &full[stage]);
+                        bulk_copy_g2s(Bs + stage * sp.b_stage_bytes + bytes, a.Wlo + (size_t)unit * a.N * 32, bytes, &full[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 for (int pass = 0; pass < a.npass; ++pass) {
                     mbar_wait_backoff(&empty[stage], phase ^ 1, 32u);
                     if (lane == 0) {
@@ -492,7 +540,7 @@ int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
             if (a.src[i].RT < back + 1) return fail("conv_umma: source ring shorter than the receptive field");
         }
     }
-    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef);
+    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass);
     if (sp.nstages < 2) return fail("conv_umma: not enough shared memory for two stages");
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<false>), sp.total));
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<true>), sp.total));
