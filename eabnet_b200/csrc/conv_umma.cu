@@ -31,6 +31,12 @@ namespace {
 
 using namespace umma;
 
+#ifdef EAB_UMMA_DEBUG
+#define UDBG(i) do { if (a.dbg && blockIdx.x == 0) a.dbg[i] = clock64(); } while (0)
+#else
+#define UDBG(i) do { } while (0)
+#endif
+
 constexpr int TM = 128;             // rows per tile (UMMA M)
 constexpr int KC = 64;              // fp16 elements per K slab = one 128-byte swizzle row
 constexpr int NPROD = 256;          // producer threads (8 warps)
@@ -102,6 +108,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
+    if (tid == 0) UDBG(0);
     const int NS = sp.nstages;
     const uint32_t tmem_cols = a.N <= 64 ? 128u : (a.N <= 128 ? 256u : 512u);      // two accumulators
 
@@ -112,14 +119,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     }
     if (warp == NPROD / 32) tmem_alloc(tmem_slot, tmem_cols);
     for (int i = tid; i < a.N; i += NTHREADS) sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+    if (a.step) {
+        // streaming: one coefficient set for the whole launch (B == 1) and static normalisation (BatchNorm), i.e. weights only:
+        // computed here, under the predecessor's tail, instead of after the dependency wait (4.8 of a one-tile launch's 12 us)
+        const int C0s = a.src[0].C;
+        for (int i = tid; i < a.ncoef; i += NTHREADS) {
+            const int sidx = i < C0s ? 0 : 1;
+            const int c = sidx ? i - C0s : i;
+            float cs, ch, ca;
+            xform_coeffs(a.src[sidx].xf, 0, a.src[sidx].C, c, cs, ch, ca);
+            coef[i] = cs;
+            coef[a.ncoef + i] = ch;
+            coef[2 * a.ncoef + i] = a.src[sidx].xf.prelu ? ca : 1.f;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) UDBG(1);
     if (a.step) {                 // streaming launches are programmatic dependents (launch_k_pdl): everything above ran under the
         pdl_trigger();            // predecessor's tail; nothing below may start before its results are visible
         pdl_wait();
     }
+    if (tid == 0) UDBG(2);
 
     // contiguous tile range of this CTA
     const long long ntiles = (long long)a.B * a.tiles_per_b;
@@ -209,7 +232,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         };
 
         // ---- store-side state
-        int cur_b = -1;
+        int cur_b = streaming ? 0 : -1;          // streaming: the coefficients were set in the prologue
         int stage = 0;
         uint32_t phase = 0;
         int s_tap = 0, s_slab = 0;
@@ -232,6 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                     }
                     named_bar_sync(1, NPROD);
                     cur_b = b;
+                    if (tid == 0) UDBG(3);
                 }
             }
             const bool second = s_slab >= nslab0;
@@ -325,6 +349,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             if (issued < total_units) { issue_loads(v0, m0); ++issued; }
             consume(v1, m1);
         }
+        if (tid == 0) UDBG(4);
     } else if (warp == NPROD / 32) {
         // =========================================================================== MMA issuer
         const uint32_t idesc = make_idesc(a.N);
@@ -366,6 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) UDBG(5);
     } else if (warp == NPROD / 32 + 1) {
         // =========================================================================== B (weight) loader
         int stage = 0;
@@ -428,6 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 rowoff_r[row] = off_r;
             }
             mbar_wait_backoff(&acc_full[acc], acc_phase, 64u);
+            if (et == 0) UDBG(6);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * a.N);
             for (int c0 = 0; c0 < a.Cout; c0 += 16) {
@@ -500,6 +527,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                     }
                 }
             }
+            if (et == 0) UDBG(7);
             named_bar_sync(2, NEPI);            // staging free for the next tile
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -507,7 +535,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
 
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) UDBG(8);
     if (warp == NPROD / 32) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == NPROD / 32 && lane == 0) UDBG(9);
 }
 
 }  // namespace
@@ -535,6 +565,7 @@ int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
     if (a.step) {
         if (a.B != 1 || a.nstats != 0 || a.out_RT < 1 || (a.resid && a.resid_RT < 1)) return fail("conv_umma: bad streaming launch");
         for (int i = 0; i < a.nsrc; ++i) {
+            if (a.src[i].xf.affine == 1) return fail("conv_umma: a streaming launch needs static normalisation (its coefficients are set before the dependency wait)");
             int back = 0;
             for (int k = 0; k < a.ntaps; ++k) back = std::max(back, a.dt[k]);
             if (a.src[i].RT < back + 1) return fail("conv_umma: source ring shorter than the receptive field");

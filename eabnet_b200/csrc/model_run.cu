@@ -127,6 +127,7 @@ int run_umma_stream(Ctx& cx, UmmaConvArgs* us, int n, int out_RT, int resid_RT) 
         u.tiles_per_b = (int)(((long long)cx.B * u.E + 127) / 128);
         u.step = cx.step; u.start = cx.start; u.out_RT = out_RT; u.resid_RT = resid_RT;
         u.nstats = 0;
+        if (cx.m->opt_dbg_launch <= -300 && cx.m->umma_launch_idx++ == -300 - cx.m->opt_dbg_launch && cx.m->dbg_buf) u.dbg = cx.m->dbg_buf;
         EAB_TRY(launch_conv_umma(u, cx.st));
     }
     return 0;
@@ -1114,6 +1115,7 @@ int stream_layout(eab_model* m, int S, StreamLayout* L) {
 }
 
 int stream_forward(eab_model* m, char* state, const StreamLayout& L, int S, cudaStream_t st) {
+    m->umma_launch_idx = 0;
     if (m->dirty) return fail("parameters not committed: call eab_commit_params first");
     Ctx cx;
     cx.m = m; cx.dry = false; cx.base = state + L.off_act; cx.B = S; cx.T = 1; cx.st = st;
