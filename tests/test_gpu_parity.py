@@ -353,3 +353,20 @@ def test_two_private_graphs_on_two_streams():
     assert torch.equal(outs[-1], ref) and torch.equal(outs[-2], ref)
     with pytest.raises(ValueError), torch.no_grad():
         net.enhance(buf, workspace=torch.empty(16, dtype=torch.uint8, device="cuda"))
+
+
+def test_long_utterance_more_than_eight_tcm_tiles():
+    """T = 1101 frames (11 s): more than 8 frame tiles per utterance, i.e. past the thread-block-cluster limit of the TCM chain
+    kernel (it takes its cooperative grid-barrier form there), long rings of conv_raw tiles per batch item"""
+    cfg = O.make_cfg()
+    net, sd = _net(cfg, seed=21)
+    wave, _ = O.make_wave(1, 9, 160 * 1100, seed=8)
+    spec = O.stft_compress(wave)
+    ref = O.forward(sd, spec, cfg)
+    with torch.no_grad():
+        out = net(spec.cuda()).cpu()
+        wav = net.enhance(wave.cuda()).cpu()
+    scale = max(1.0, float(ref.abs().max()))
+    assert out.shape == ref.shape == (1, 2, 1101, 161)
+    assert float((out - ref).abs().max()) <= TIGHT * scale
+    assert float((wav - O.istft(ref)).abs().max()) <= TOL
