@@ -57,7 +57,7 @@ def test_head_and_loss_forward_backward_match_autograd(B, T, F, M):
     loss = com_mag_mse_loss(out, label.cuda(), frames)
     gg = torch.autograd.grad(3.0 * loss, pg)                    # an upstream factor exercises grad_loss_dev
     assert float((out.detach().cpu().double() - out64.detach()).abs().max()) <= 2e-5 * max(1.0, float(out64.abs().max()))
-    assert abs(float(loss) - float(loss64)) <= 1e-5 * max(1.0, abs(float(loss64)))
+    assert abs(float(loss.detach()) - float(loss64.detach())) <= 1e-5 * max(1.0, abs(float(loss64.detach())))
     for name, a, b in zip(("h2", "W1", "b1", "W2", "b2"), gg, g64):
         ref = 3.0 * b
         assert a.shape == ref.shape
@@ -77,7 +77,7 @@ def test_head_backward_is_deterministic_and_loss_default_mask():
     for a, b in zip(*runs):
         assert torch.equal(a, b)
     ref = ref_loss(ref_head(h2.double(), spec.double(), W1.double(), b1.double(), W2.double(), b2.double()), label.double(), [300, 300])
-    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert abs(float(loss.detach()) - float(ref)) <= 1e-5 * abs(float(ref))
 
 
 def test_train_slice_rejects_cpu_and_bad_shapes():
