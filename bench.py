@@ -628,14 +628,21 @@ def main():
         clocks = sampler.stop()
         assert torch.isfinite(y).all()
 
-    c4 = config4(args, dev, net, world, rank, [wave_host, wave_host2], [out_host, out_host2]) if not args.no_config4 else None
-    single = single_utterance(dev, net) if (rank == 0 and not args.no_single) else None
-    eager = gpu_eager_baseline(args, dev) if (rank == 0 and world == 1 and not args.no_gpu_eager) else None
-    latency = stream_latency(args, dev) if args.stream_steps > 0 else None
-    postnet = postnet_throughput(args, dev, wave) if (rank == 0 and not args.no_postnet) else None
+    def optional(fn, *a):
+        """the secondary objects must never cost the headline line: a failure is reported inside the object"""
+        try:
+            return fn(*a)
+        except Exception as e:                       # noqa: BLE001
+            return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+    c4 = optional(config4, args, dev, net, world, rank, [wave_host, wave_host2], [out_host, out_host2]) if not args.no_config4 else None
+    single = optional(single_utterance, dev, net) if (rank == 0 and not args.no_single) else None
+    eager = optional(gpu_eager_baseline, args, dev) if (rank == 0 and world == 1 and not args.no_gpu_eager) else None
+    latency = optional(stream_latency, args, dev) if args.stream_steps > 0 else None
+    postnet = optional(postnet_throughput, args, dev, wave) if (rank == 0 and not args.no_postnet) else None
     del graphs
     torch.cuda.empty_cache()
-    c5 = config5_training(args, dev, world, rank, local) if not args.no_config5 else None
+    c5 = optional(config5_training, args, dev, world, rank, local) if not args.no_config5 else None
 
     from eabnet_b200.shard import max_over_ranks
     ms, ms_e2e, ms_e2e16 = max_over_ranks([ms, ms_e2e, ms_e2e16], dev)
