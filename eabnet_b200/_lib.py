@@ -58,6 +58,8 @@ SYMBOLS = {
     "eab_head_backward": (C.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "eab_loss_com_mag_mse": (C.c_int, [_F, _F, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _F, _P, _P]),
     "eab_loss_com_mag_mse_backward": (C.c_int, [_F, _F, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _F, _F, _P]),
+    "eab_loss_com_mag_mse_fm": (C.c_int, [_F, _F, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _F, _P, _P]),
+    "eab_loss_com_mag_mse_fm_backward": (C.c_int, [_F, _F, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _F, _F, _P]),
     "eab_wav_info": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int),
                               C.POINTER(C.c_int)]),
     "eab_wav_decode": (C.c_int, [_P, C.c_size_t, _F, _P]),

@@ -280,6 +280,7 @@ struct LossArgs {
     const float* esti; const float* label;        // [B][2][T][F]
     const int* frames;                            // [B] valid frames per utterance (device) or null = T
     int B, T, F;
+    int freq_major;                               // 0: [B][2][T][F] (EaBNet's estimate) ; 1: [B][2][F][T] (GaGNet's stage estimates)
     double* sums;                                 // [2]: sum of masked (|e|-|l|)^2, sum of masked |e-l|^2
     const float* gscale;                          // backward: upstream gradient of the scalar loss (device) or null = 1
     float* d_esti;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const LossArgs a) {
     double s1 = 0.0, s2 = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long b = i / TF, p = i - b * TF;
-        const int t = (int)(p / a.F);
+        const int t = a.freq_major ? (int)(p % a.T) : (int)(p / a.F);
         if (a.frames && t >= __ldg(a.frames + b)) continue;
         const float er = __ldg(a.esti + (b * 2) * TF + p), ei = __ldg(a.esti + (b * 2 + 1) * TF + p);
         const float lr = __ldg(a.label + (b * 2) * TF + p), li = __ldg(a.label + (b * 2 + 1) * TF + p);
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const LossArgs a) {
     const float g = (a.gscale ? __ldg(a.gscale) : 1.f) / (float)a.n_mask;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long b = i / TF, p = i - b * TF;
-        const int t = (int)(p / a.F);
+        const int t = a.freq_major ? (int)(p % a.T) : (int)(p / a.F);
         float dr = 0.f, di = 0.f;
         if (!(a.frames && t >= __ldg(a.frames + b))) {
             const float er = __ldg(a.esti + (b * 2) * TF + p), ei = __ldg(a.esti + (b * 2 + 1) * TF + p);
@@ -406,13 +407,35 @@ int eab_head_backward(const float* W1, const float* b1, const float* W2, const f
     return 0;
 }
 
+static int loss_fwd(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F, int freq_major,
+                    float* loss, void* scratch16, void* stream);
+static int loss_bwd(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F, int freq_major,
+                    const float* grad_loss_dev, float* d_esti, void* stream);
 int eab_loss_com_mag_mse(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F,
                          float* loss, void* scratch16, void* stream) {
+    return loss_fwd(esti, label, frames_dev, frames_total, B, T, F, 0, loss, scratch16, stream);
+}
+int eab_loss_com_mag_mse_backward(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F,
+                                  const float* grad_loss_dev, float* d_esti, void* stream) {
+    return loss_bwd(esti, label, frames_dev, frames_total, B, T, F, 0, grad_loss_dev, d_esti, stream);
+}
+// the same loss on frequency-major tensors [B][2][F][T]: one stage of stagewise_com_mag_mse_loss (GaGNet.py:601-619)
+int eab_loss_com_mag_mse_fm(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F,
+                            float* loss, void* scratch16, void* stream) {
+    return loss_fwd(esti, label, frames_dev, frames_total, B, T, F, 1, loss, scratch16, stream);
+}
+int eab_loss_com_mag_mse_fm_backward(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F,
+                                     const float* grad_loss_dev, float* d_esti, void* stream) {
+    return loss_bwd(esti, label, frames_dev, frames_total, B, T, F, 1, grad_loss_dev, d_esti, stream);
+}
+
+static int loss_fwd(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F, int freq_major,
+                    float* loss, void* scratch16, void* stream) {
     if (!esti || !label || !loss || !scratch16) return fail("eab_loss_com_mag_mse: null argument");
     if (B < 1 || T < 1 || F < 1) return fail("eab_loss_com_mag_mse: bad shape");
     LossArgs a;
     memset(&a, 0, sizeof(a));
-    a.esti = esti; a.label = label; a.frames = frames_dev; a.B = B; a.T = T; a.F = F; a.loss = loss;
+    a.esti = esti; a.label = label; a.frames = frames_dev; a.B = B; a.T = T; a.F = F; a.loss = loss; a.freq_major = freq_major;
     a.sums = static_cast<double*>(scratch16);
     a.n_mask = (double)(frames_dev ? frames_total : (int64_t)B * T) * F;
     if (a.n_mask <= 0) return fail("eab_loss_com_mag_mse: empty mask");
@@ -427,13 +450,14 @@ int eab_loss_com_mag_mse(const float* esti, const float* label, const int* frame
     return 0;
 }
 
-int eab_loss_com_mag_mse_backward(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F,
-                                  const float* grad_loss_dev, float* d_esti, void* stream) {
+static int loss_bwd(const float* esti, const float* label, const int* frames_dev, int64_t frames_total, int B, int T, int F, int freq_major,
+                    const float* grad_loss_dev, float* d_esti, void* stream) {
     if (!esti || !label || !d_esti) return fail("eab_loss_com_mag_mse_backward: null argument");
     if (B < 1 || T < 1 || F < 1) return fail("eab_loss_com_mag_mse_backward: bad shape");
     LossArgs a;
     memset(&a, 0, sizeof(a));
     a.esti = esti; a.label = label; a.frames = frames_dev; a.B = B; a.T = T; a.F = F; a.d_esti = d_esti; a.gscale = grad_loss_dev;
+    a.freq_major = freq_major;
     a.n_mask = (double)(frames_dev ? frames_total : (int64_t)B * T) * F;
     if (a.n_mask <= 0) return fail("eab_loss_com_mag_mse_backward: empty mask");
     int sms = 0;

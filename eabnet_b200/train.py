@@ -66,12 +66,15 @@ def head_filter_sum(h2, spec, W1, b1, W2, b2):
 
 class _ComMagMse(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, esti, label, frames):
+    def forward(ctx, esti, label, frames, freq_major=False):
         _check(esti, "esti")
         _check(label, "label")
         if esti.ndim != 4 or esti.shape[1] != 2 or tuple(label.shape) != tuple(esti.shape):
             raise ValueError("com_mag_mse_loss: esti and label [B,2,T,F]")
-        B, _, T, Fq = esti.shape
+        if freq_major:
+            B, _, Fq, T = esti.shape
+        else:
+            B, _, T, Fq = esti.shape
         e, l = esti.contiguous(), label.contiguous()
         total = 0
         if frames is not None:
@@ -80,33 +83,58 @@ class _ComMagMse(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=esti.device)
         scratch = torch.empty(2, dtype=torch.float64, device=esti.device)
         with torch.cuda.device(esti.device):
-            _lib.check(_lib.load().eab_loss_com_mag_mse(e.data_ptr(), l.data_ptr(), frames.data_ptr() if frames is not None else None,
+            fn = _lib.load().eab_loss_com_mag_mse_fm if freq_major else _lib.load().eab_loss_com_mag_mse
+            _lib.check(fn(e.data_ptr(), l.data_ptr(), frames.data_ptr() if frames is not None else None,
                                                         total, B, T, Fq, loss.data_ptr(), scratch.data_ptr(), _st(esti.device)),
                        "eab_loss_com_mag_mse")
         ctx.save_for_backward(e, l)
-        ctx.frames, ctx.total = frames, total
+        ctx.frames, ctx.total, ctx.freq_major, ctx.dims = frames, total, bool(freq_major), (B, T, Fq)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         e, l = ctx.saved_tensors
-        B, _, T, Fq = e.shape
+        B, T, Fq = ctx.dims
         d = torch.empty_like(e)
         gc = g.contiguous().float()
         with torch.cuda.device(e.device):
-            _lib.check(_lib.load().eab_loss_com_mag_mse_backward(e.data_ptr(), l.data_ptr(),
+            fn = _lib.load().eab_loss_com_mag_mse_fm_backward if ctx.freq_major else _lib.load().eab_loss_com_mag_mse_backward
+            _lib.check(fn(e.data_ptr(), l.data_ptr(),
                                                                  ctx.frames.data_ptr() if ctx.frames is not None else None, ctx.total,
                                                                  B, T, Fq, gc.data_ptr(), d.data_ptr(), _st(e.device)),
                        "eab_loss_com_mag_mse_backward")
-        return d, None, None
+        return d, None, None, None
+
+
+def _frames(frame_list, B, T):
+    if frame_list is None:
+        return None
+    frames = torch.as_tensor(frame_list, dtype=torch.int64)
+    if frames.numel() != B or int(frames.max()) != T or int(frames.min()) < 1:
+        raise ValueError("frame_list: one entry per utterance, the longest equal to T (the reference pads to it)")
+    return frames
 
 
 def com_mag_mse_loss(esti, label, frame_list=None):
     """com_mag_mse_loss(esti, label, frame_list) of EaBNet.py:627-640 for esti / label [B,2,T,F]; frame_list: valid frames per
     utterance (a list or int tensor; None = all T frames, what train_distributed.py:221 passes).  Differentiable in esti."""
-    frames = None
-    if frame_list is not None:
-        frames = torch.as_tensor(frame_list, dtype=torch.int64)
-        if frames.numel() != esti.shape[0] or int(frames.max()) != esti.shape[2] or int(frames.min()) < 1:
-            raise ValueError("frame_list: one entry per utterance, the longest equal to T (the reference pads to it)")
-    return _ComMagMse.apply(esti, label, frames)
+    return _ComMagMse.apply(esti, label, _frames(frame_list, esti.shape[0], esti.shape[2]), False)
+
+
+def stagewise_com_mag_mse_loss(esti_list, label, frame_list=None):
+    """stagewise_com_mag_mse_loss (GaGNet.py:601-619): estimates and label [B,2,F,T]; every stage weighted 0.1, the last one 1."""
+    frames = _frames(frame_list, label.shape[0], label.shape[3])
+    alpha = [0.1] * len(esti_list)
+    alpha[-1] = 1.0
+    total = None
+    for a, e in zip(alpha, esti_list):
+        term = a * _ComMagMse.apply(e, label, frames, True)
+        total = term if total is None else total + term
+    return total
+
+
+def eabnet_with_postnet_loss(output, label, frame_list=None):
+    """eabnet_with_postnet_loss (EaBNet.py:642-650) on the wrapper's output dict; label [B,2,T,F]."""
+    loss0 = com_mag_mse_loss(output["esti0_stft"], label, frame_list)
+    loss1 = stagewise_com_mag_mse_loss(output["esti1_stft_list"], label.permute(0, 1, 3, 2), frame_list)
+    return {"eabnet": loss0, "postnet": loss1, "final": loss0 + loss1}

@@ -191,6 +191,14 @@ EAB_API int    eab_loss_com_mag_mse(const float* esti_dev, const float* label_de
                                     int T, int F, float* loss_dev, void* scratch16_dev, void* stream);
 EAB_API int    eab_loss_com_mag_mse_backward(const float* esti_dev, const float* label_dev, const int* frames_dev, int64_t frames_total,
                                              int B, int T, int F, const float* grad_loss_dev, float* d_esti_dev, void* stream);
+/* ... and on frequency-major tensors [B,2,F,T]: one stage of stagewise_com_mag_mse_loss (GaGNet.py:601-619; the stage weights
+ * 0.1 / 1 and the sum over stages are scalar arithmetic of the caller), i.e. eabnet_with_postnet_loss (EaBNet.py:642-650) is
+ * eab_loss_com_mag_mse(esti0) + sum_i alpha_i eab_loss_com_mag_mse_fm(esti1_list[i]). */
+EAB_API int    eab_loss_com_mag_mse_fm(const float* esti_dev, const float* label_dev, const int* frames_dev, int64_t frames_total, int B,
+                                       int T, int F, float* loss_dev, void* scratch16_dev, void* stream);
+EAB_API int    eab_loss_com_mag_mse_fm_backward(const float* esti_dev, const float* label_dev, const int* frames_dev,
+                                                int64_t frames_total, int B, int T, int F, const float* grad_loss_dev,
+                                                float* d_esti_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * I/O edges of enhance.py: the wav container and the sample-rate conversion.

@@ -89,3 +89,28 @@ def test_train_slice_rejects_cpu_and_bad_shapes():
         head_filter_sum(h2.cuda(), spec.cuda(), W1.cuda(), b1.cuda(), W2[:2].cuda(), b2.cuda())
     with pytest.raises(ValueError):
         com_mag_mse_loss(label.cuda(), label.cuda(), [2])     # longest entry must be T
+
+
+def test_wrapper_loss_matches_autograd_of_the_reference_formulas():
+    """eabnet_with_postnet_loss (EaBNet.py:642-650): plain loss on the beamformer estimate + stagewise loss on the q post-filter
+    estimates ([B,2,F,T], weights 0.1 / 1, GaGNet.py:601-619); forward value and gradients against float64 autograd"""
+    from eabnet_b200.train import eabnet_with_postnet_loss
+    from oracle import train_oracle as TO
+    g = torch.Generator().manual_seed(17)
+    B, T, F = 3, 37, 161
+    e0 = 0.5 * torch.randn(B, 2, T, F, generator=g)
+    e1 = [0.5 * torch.randn(B, 2, F, T, generator=g).contiguous() for _ in range(3)]
+    label = 0.5 * torch.randn(B, 2, T, F, generator=g)
+    frames = [T, 20, 31]
+    r0 = e0.double().requires_grad_(True)
+    r1 = [t.double().requires_grad_(True) for t in e1]
+    ref = TO.loss_fn({"esti0_stft": r0, "esti1_stft_list": r1}, label.double(), frames)
+    gref = torch.autograd.grad(ref["final"], [r0] + r1)
+    p0 = e0.cuda().requires_grad_(True)
+    p1 = [t.cuda().requires_grad_(True) for t in e1]
+    got = eabnet_with_postnet_loss({"esti0_stft": p0, "esti1_stft_list": p1}, label.cuda(), frames)
+    ggot = torch.autograd.grad(got["final"], [p0] + p1)
+    for k in ("eabnet", "postnet", "final"):
+        assert abs(float(got[k].detach()) - float(ref[k].detach())) <= 1e-5 * max(1.0, abs(float(ref[k].detach()))), k
+    for a, b in zip(ggot, gref):
+        assert float((a.cpu().double() - b).abs().max()) <= 3e-5 * max(1e-6, float(b.abs().max())) + 1e-10
