@@ -372,6 +372,7 @@ struct LstmArgs {
     float* h_state; float* c_state;
     int out_RT;
     int exp_flags;               // diagnostics builds only
+    int rows_per_cta;            // tcgen05 kernel, diagnostics: live rows per CTA (0 = 96)
 };
 int launch_lstm(const LstmArgs& a, cudaStream_t st);
 

@@ -16,6 +16,8 @@
 //                             PReLU and the head's LayerNorm (thread-local over the 64 channels), split to fp16 hi/lo,
 //                             store to the A operand once the input-projection MMAs have released it, arrive
 //   warp 20     MMA issuer  : h-part of step t (24 MMAs M128 x N128 x K16, two commits), then x-part of step t+1
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -112,7 +114,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int NQ = a.B * a.F;
-    const int q0 = blockIdx.x * RPC;
+    const int rows_act = a.rows_per_cta > 0 ? a.rows_per_cta : RPC;      // (experiment: fewer live rows per CTA, more CTAs)
+    const int q0 = blockIdx.x * rows_act;
     const int b0 = q0 / a.F;
 
     if (tid == 0) {
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         const int qtr = warp >> 2;              // which 16 hidden units
         const int row = quad * 32 + lane;
         const int q = q0 + row;
-        const bool valid = q < NQ;
+        const bool valid = q < NQ && row < rows_act;
         const int bq = valid ? q / a.F : 0;
         const int fq = valid ? q - bq * a.F : 0;
         uint8_t* hs_row = Hs + row * 256;
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
         const int row = pidx * 16 + (lane >> 1);
         const int half = lane & 1;                                   // channels half*32 .. +32
         const int q = q0 + row;
-        const bool valid = q < NQ;
+        const bool valid = q < NQ && row < rows_act;
         const int bq = valid ? q / a.F : 0;
         const int fq = valid ? q - bq * a.F : 0;
         const float* xp = a.src.x + (((size_t)bq * a.T) * a.F + fq) * H + half * 32;
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                 const int r = g >> 4, ch = g & 15;
                 const int qq = q0 + r;
                 const float4 v = *reinterpret_cast<const float4*>(Hs + r * 256 + ((ch ^ (r & 7)) << 4));
-                if (qq < NQ && !EXP_FLAG(1))
+                if (qq < NQ && r < rows_act && !EXP_FLAG(1))
                     *reinterpret_cast<float4*>(base + (long long)qq * H + ch * 4 + (qq >= q_next_b ? jump : 0)) = v;
             }
             mbar_arrive(hs_free);
@@ -423,7 +426,11 @@ int launch_lstm_umma(const LstmArgs& a, cudaStream_t st) {
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(lstm_umma_kernel), SMEM_BYTES));
     const int NQ = a.B * a.F;
     ProfScope ps("lstm_umma", 2.0 * NQ * a.T * (64 + H) * 4.0 * H, 4.0 * NQ * a.T * (64 + H), st);
-    EAB_CUDA(launch_k(lstm_umma_kernel, dim3((NQ + RPC - 1) / RPC), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a));
+    static const int rows_env = getenv("EAB_LSTM_ROWS") ? atoi(getenv("EAB_LSTM_ROWS")) : 0;      // diagnostics: 1..96 live rows per CTA
+    LstmArgs b = a;
+    b.rows_per_cta = (rows_env >= 1 && rows_env <= RPC) ? rows_env : 0;
+    const int rpc = b.rows_per_cta ? b.rows_per_cta : RPC;
+    EAB_CUDA(launch_k(lstm_umma_kernel, dim3((NQ + rpc - 1) / rpc), dim3(NTHREADS), (size_t)SMEM_BYTES, st, b));
     EAB_LAUNCH_CHECK("lstm_umma_kernel");
     return 0;
 }
