@@ -157,6 +157,7 @@ class _NativeModule(nn.Module):
     def set_option(self, name: str, value: int) -> None:
         """kernel-selection / precision knobs of the native path (see include/eabnet_b200.h: eab_set_option)"""
         _lib.check(self._native.lib.eab_set_option(self._native.h, name.encode(), int(value)), "eab_set_option")
+        self._opt_epoch = getattr(self, "_opt_epoch", 0) + 1          # streaming sessions re-plan their state after an option change
 
     def profile(self, on) -> None:
         """switch per-launch CUDA-event timing on/off for this thread's launches (2 = one entry per launch)"""
@@ -493,8 +494,30 @@ class EaBNetStream:
         if self.postnet is not None:
             yield self.postnet, self.gstate
 
+    def _epoch(self):
+        return (getattr(self.net, "_opt_epoch", 0), getattr(self.postnet, "_opt_epoch", 0) if self.postnet is not None else 0)
+
     def reset(self) -> None:
+        """All streams start over.  Also re-plans the state blobs: kernel-selection options (stream_umma, stream_lstm, ...) change
+        their layout, so an option set after the session was created takes effect here (a step in between raises)."""
         with torch.cuda.device(self.dev):
+            lib = self.net._native.lib
+            need = lib.eab_stream_state_bytes(self.net._native.h, self.S)
+            if need == 0:
+                _lib.check(1, "eab_stream_state_bytes")
+            if need != self.state.numel():
+                self.state = torch.empty(need, dtype=torch.uint8, device=self.dev)
+                self._graph = None
+            if self.postnet is not None:
+                gneed = lib.eab_stream_state_bytes(self.postnet._native.h, self.S)
+                if gneed == 0:
+                    _lib.check(1, "eab_stream_state_bytes (post-filter)")
+                if gneed != self.gstate.numel():
+                    self.gstate = torch.empty(gneed, dtype=torch.uint8, device=self.dev)
+                    self._graph = None
+            if getattr(self, "_planned", None) != self._epoch():
+                self._graph = None                    # a captured step bakes the old kernel selection in
+            self._planned = self._epoch()
             st = torch.cuda.current_stream(self.dev).cuda_stream
             for mod, state in self._states():
                 mod._sync_params(self.dev)
@@ -528,6 +551,8 @@ class EaBNetStream:
         int16 [S,M,160] -> int16 [S,160] (eab_stream_step_pcm16)."""
         if tuple(hop.shape) != (self.S, self.net.M, 160) or hop.dtype not in (torch.float32, torch.int16) or hop.device != self.dev:
             raise ValueError("expected a float32 or int16 [%d,%d,160] tensor on %s" % (self.S, self.net.M, self.dev))
+        if self._planned != self._epoch():
+            raise RuntimeError("kernel options changed since this streaming session was planned: call reset() first")
         hop = hop.contiguous()
         if out is None:
             out = torch.empty((self.S, 160), dtype=hop.dtype, device=self.dev)
@@ -566,6 +591,8 @@ class EaBNetStream:
             frame = frame.unsqueeze(-2)
         if tuple(frame.shape) != (self.S, N_FREQ, net.M, 2) or frame.dtype != torch.float32 or frame.device != self.dev:
             raise ValueError("expected a float32 [%d,%d,%d,2] tensor on %s" % (self.S, N_FREQ, net.M, self.dev))
+        if self._planned != self._epoch():
+            raise RuntimeError("kernel options changed since this streaming session was planned: call reset() first")
         frame = frame.contiguous()
         out = torch.empty((self.S, 2) if net.topo_type == "miso" else (self.S, 2, N_FREQ), dtype=torch.float32, device=self.dev)
         with torch.cuda.device(self.dev):

@@ -115,6 +115,8 @@ EAB_API int  eab_enhance_host_batches(eab_model* m, const float* const* waves_ho
  * The caller owns the state blob (device memory, 256-byte aligned, eab_stream_state_bytes(m, n_streams) bytes): conv
  * history rings, TCM dilation rings, LSTM (h, c), the previous hop and the overlap-add tail.  One step launches
  * kernels only (the frame counter lives in the state and is read on the device): it can be captured in a CUDA graph.
+ * Kernel-selection options ("umma", "stream_umma", "stream_lstm", "stream_tcm") change the layout too: set them before
+ * eab_stream_state_bytes / eab_stream_reset; after changing one, size and reset the blob again.
  * Size the blob AFTER eab_commit_params: which layers run on the tensor cores (padded channel counts of their outputs) is
  * known once the weights are packed; a blob sized before that is refused by reset / step with a message, never overrun.
  *   eab_stream_step      hop_dev [S][M][160] new samples -> enhanced_hop_dev [S][160], delayed by ONE hop (overlap-add

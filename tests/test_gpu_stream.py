@@ -203,3 +203,22 @@ def test_to_batchnorm_pools_batches_and_rejects_bn_models():
     assert len(rv) > 60 and all(bool((v >= 0).all()) and bool(torch.isfinite(v).all()) for v in rv)
     with pytest.raises(RuntimeError, match="static normalisation"):
         bn.to_batchnorm([O.stft_compress(w2).cuda()])
+
+
+def test_stream_session_replans_after_an_option_change():
+    """kernel-selection options change the state layout: a step after set_option raises until reset() re-plans the session"""
+    cfg = O.make_cfg(norm_type="BN")
+    net, sd = _net(cfg, seed=9)
+    S, T = 2, 12
+    wave, _ = O.make_wave(S, 9, 160 * (T - 1), seed=13)
+    spec = O.stft_compress(wave)
+    ref = O.forward(sd, spec, cfg)
+    ses = net.stream(S)
+    ses.step_spec(spec[:, 0].cuda().contiguous())
+    net.set_option("stream_umma", 0)
+    with pytest.raises(RuntimeError, match="reset"):
+        ses.step_spec(spec[:, 1].cuda().contiguous())
+    ses.reset()
+    for t in range(T):
+        got = ses.step_spec(spec[:, t].cuda().contiguous()).cpu()
+        assert float((got - ref[:, :, t]).abs().max()) <= EXACT * max(1.0, float(ref.abs().max()))
