@@ -299,6 +299,7 @@ bool staged_conv_fits(const PlaneConvArgs& a);          // shared-memory / unit-
 int launch_stage(const PlaneConvArgs& a, cudaStream_t st);
 int launch_conv_staged(PlaneConvArgs a, cudaStream_t st);
 extern bool g_stft_tc;           // STFT as a tcgen05 GEMM (default) / fp32 CUDA-core kernel
+extern bool g_istft_tc;          // iSTFT as a tcgen05 GEMM (option) / fused fp32 CUDA-core kernel (default)
 
 // ---------------------------------------------------------------------------------------------------
 // conv_raw.cu: the conv layer as ONE kernel, no staged planes in HBM.  The loader bulk-copies the RAW fp32 rows a

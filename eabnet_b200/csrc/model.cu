@@ -702,6 +702,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "stream_lstm") m->opt_stream_lstm = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "stft_tc") g_stft_tc = value != 0;
+    else if (n == "istft_tc") g_istft_tc = value != 0;
     else if (n == "fused_head") m->opt_fused_head = value != 0;
     else if (n == "head_w_tap") m->opt_head_w_tap = value != 0;
     else if (n == "enc_passes" && (value == 1 || value == 3)) { m->opt_enc_passes = value; m->opt_inner_passes = value; }

@@ -45,10 +45,17 @@ struct Tables {
     // column 2f = Re X[f], 2f+1 = Im X[f]
     void* dft_hi = nullptr;
     void* dft_lo = nullptr;
+    // tensor-core inverse transform (conv_umma weight images, [2 taps][6 K slabs][N rows][64 k], 128B-swizzled, fp16 hi / lo):
+    // row n = output sample of a hop, K = (Re X[0..160] | Im X[0..160] | zeros to 384) of frame t (tap 0: its first half lands
+    // in hop t - 1) and frame t - 1 (tap 1: its second half); synthesis window, 1 / 320, the half-spectrum weights and the
+    // window envelope folded in.  Column groups: samples 0..127 (N = 128) and 128..159 (N = 32).
+    void* idft_hi[2] = {nullptr, nullptr};
+    void* idft_lo[2] = {nullptr, nullptr};
     void* planes = nullptr;  // scratch: fp16 hi/lo hop planes of the waveforms (grow-only)
     size_t planes_bytes = 0;
 };
 constexpr int DFT_GROUPS = 3, DFT_SLABS = 3;
+constexpr int IDFT_SLABS = 6, IDFT_K = IDFT_SLABS * 64;      // 322 -> 384
 constexpr size_t DFT_GROUP_HALVES = (size_t)2 * DFT_SLABS * 128 * 64;
 Tables g_tab[64];
 std::mutex g_tab_mu;
@@ -117,6 +124,35 @@ int get_tables(Tables** out) {
         EAB_CUDA(cudaMalloc(&t.dft_lo, lo.size() * 2));
         EAB_CUDA(cudaMemcpy(t.dft_hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
         EAB_CUDA(cudaMemcpy(t.dft_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+        for (int g = 0; g < 2; ++g) {
+            const int N = g ? 32 : 128, n0 = g ? 128 : 0;
+            std::vector<__half> ih((size_t)2 * IDFT_SLABS * N * 64), il(ih.size());
+            for (int tap = 0; tap < 2; ++tap)
+                for (int sl = 0; sl < IDFT_SLABS; ++sl)
+                    for (int n = 0; n < N; ++n)
+                        for (int k = 0; k < 64; ++k) {
+                            const int kk = sl * 64 + k, smp = n0 + n;
+                            double wv = 0.0;
+                            if (kk < 2 * NF) {
+                                const int f = kk < NF ? kk : kk - NF;
+                                const int ns = smp + (tap ? HOP : 0);        // sample inside the frame
+                                const int kf = (ns * f) % NFFT;
+                                const double cf = (f == 0 || f == 160) ? 1.0 : 2.0;
+                                const double basis = kk < NF ? cos(th * kf) : -sin(th * kf);
+                                const double env = (double)win[smp] * win[smp] + (double)win[smp + HOP] * win[smp + HOP];
+                                wv = (double)win[ns] * cf * basis / NFFT / env;
+                            }
+                            const float wf = (float)wv;
+                            const __half h = __float2half_rn(wf);
+                            const size_t idx = ((size_t)(tap * IDFT_SLABS + sl) * N + n) * 64 + (size_t)((((k >> 3) ^ (n & 7)) << 3) | (k & 7));
+                            ih[idx] = h;
+                            il[idx] = __float2half_rn(wf - __half2float(h));
+                        }
+            EAB_CUDA(cudaMalloc(&t.idft_hi[g], ih.size() * 2));
+            EAB_CUDA(cudaMalloc(&t.idft_lo[g], il.size() * 2));
+            EAB_CUDA(cudaMemcpy(t.idft_hi[g], ih.data(), ih.size() * 2, cudaMemcpyHostToDevice));
+            EAB_CUDA(cudaMemcpy(t.idft_lo[g], il.data(), il.size() * 2, cudaMemcpyHostToDevice));
+        }
     }
     *out = &t;
     return 0;
@@ -590,10 +626,73 @@ int launch_step_advance(int* step, cudaStream_t st) {
     return 0;
 }
 
+bool g_istft_tc = false;         // iSTFT as a tcgen05 GEMM (option istft_tc; measured slower: 0.245 vs 0.209 ms) / fused fp32 CUDA-core kernel (default)
+
+namespace {
+
+// spec [B][2][T][161] -> rows [B][T][384] = (Re | Im | zeros): the A operand of the inverse-DFT GEMM
+__global__ void __launch_bounds__(256) istft_pack_kernel(const float* __restrict__ spec, float* __restrict__ rows, int B, int T) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)B * T * IDFT_K;
+    if (i >= n) return;
+    const size_t bt = i / IDFT_K;
+    const int kk = (int)(i - bt * IDFT_K);
+    const size_t b = bt / T, t = bt - b * T;
+    float v = 0.f;
+    if (kk < 2 * NF) {
+        const int ri = kk >= NF, f = kk - ri * NF;
+        v = __ldg(spec + ((b * 2 + ri) * T + t) * NF + f);
+    }
+    rows[i] = v;
+}
+
+// iSTFT as a two-tap tensor-core GEMM (north_star: "windowed DFT-as-GEMM on tensor cores with fused overlap-add"): output row t
+// = hop t - 1 = first half of frame t (tap 0) + second half of frame t - 1 (tap 1), K = 2 x 322, N = 160, 3-pass fp16 split;
+// window, 1/320, half-spectrum weights and the overlap-add envelope live in the weight images, so the GEMM's rows ARE the
+// output samples; a strided device copy drops the unused row 0 of every utterance.
+int launch_istft_tc(Tables* t, const float* spec, float* wave, int B, int T, cudaStream_t st) {
+    float* rows = nullptr;
+    float* tmp = nullptr;
+    const size_t nrows = (size_t)B * T;
+    EAB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&rows), nrows * IDFT_K * sizeof(float), st));
+    EAB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), nrows * HOP * sizeof(float), st));
+    auto done = [&](int rc) { cudaFreeAsync(rows, st); cudaFreeAsync(tmp, st); return rc; };
+    {
+        ProfScope ps("istft", 0.0, 4.0 * (double)B * 2 * T * NF, st, 4.0 * ((double)B * 2 * T * NF + (double)nrows * IDFT_K));
+        const size_t n = nrows * IDFT_K;
+        if (launch_k(istft_pack_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, st, spec, rows, B, T) != cudaSuccess)
+            return done(fail("istft_pack_kernel launch failed"));
+        count_launch();
+    }
+    for (int g = 0; g < 2; ++g) {
+        UmmaConvArgs u;
+        memset(&u, 0, sizeof(u));
+        u.nsrc = 1;
+        u.src[0].x = rows; u.src[0].C = IDFT_K; u.src[0].xf = xform_identity();
+        u.B = B; u.T = T; u.Fin = 1; u.E = 1; u.in_stride = 1; u.out_stride = 1; u.out_off = 0; u.Fout = 1;
+        u.ntaps = 2; u.dt[0] = 0; u.dt[1] = 1;
+        u.nslab = IDFT_SLABS; u.ncoef = IDFT_K; u.npass = 3;
+        u.Whi = static_cast<const float*>(t->idft_hi[g]); u.Wlo = static_cast<const float*>(t->idft_lo[g]);
+        u.Cout = g ? 32 : 128; u.N = u.Cout;
+        u.algo_frac = (float)(2 * NF) / (float)IDFT_K;
+        u.out = tmp; u.out_ld = HOP; u.out_coff = g ? 128 : 0;
+        u.tiles_per_b = (T + 127) / 128;
+        if (launch_conv_umma(u, st)) return done(1);
+    }
+    // hop h = row h + 1: wave [B][160 (T - 1)] <- tmp [B][T][160] without its first row
+    if (cudaMemcpy2DAsync(wave, (size_t)(T - 1) * HOP * sizeof(float), tmp + HOP, (size_t)T * HOP * sizeof(float),
+                          (size_t)(T - 1) * HOP * sizeof(float), (size_t)B, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return done(fail("istft: strided copy failed"));
+    return done(0);
+}
+
+}  // namespace
+
 int launch_istft(const float* spec, float* wave, int B, int T, cudaStream_t st, short* wave16) {
     if (T < 2) return fail("istft: need at least 2 frames");
     Tables* t;
     EAB_TRY(get_tables(&t));
+    if (g_istft_tc && !wave16) return launch_istft_tc(t, spec, wave, B, T, st);        // (the int16 writer stays with the fused kernel)
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(stft_kernel), (int)kSmemBytes));
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(istft_kernel), (int)kSmemBytes));
     ProfScope ps("istft", 2.0 * NF * NCOL * (double)B * T, 4.0 * ((double)B * 2 * T * NF + (double)B * HOP * (T - 1)), st);

@@ -310,6 +310,9 @@ EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, in
  *                       per TCM, 2 = one chain per launch, 3 = the cooperative grid-barrier form (also taken when T > 1024)
  *   "fused_head" (1)    w_dnn + filter-and-sum as one kernel     "head_w_tap" (0)  ... which also writes the beam weights (tap "w")
  *   "stft_tc" (1)       STFT as a tensor-core DFT-GEMM; 0 = fp32 CUDA-core kernel.  PROCESS-WIDE switch (eab_stft has no handle)
+ *   "istft_tc" (0)      iSTFT as a tensor-core two-tap DFT-GEMM (window, 1/320 and the overlap-add envelope folded into the weight
+ *                       images; 3-pass fp16 split, 2.6e-6) instead of the fused fp32 CUDA-core kernel (4e-8).  Measured slower (0.245
+ *                       vs 0.209 ms per 64 x 6 s), hence off.  PROCESS-WIDE like stft_tc
  *   "host_graph" (1) / "dual_stream" (1)   eab_enhance_host_batches: replay each slot's step from a CUDA graph / alternate
  *                       batches on two compute streams
  *   "stream_tcm" (1)    streaming: the TCM stack as one launch

@@ -63,6 +63,24 @@ def test_istft_matches_oracle(B, T):
     assert (got - ref).abs().max() <= 2e-6 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("B,T", [(1, 2), (3, 47), (2, 601)])
+def test_istft_tensor_core_option_matches_oracle(B, T):
+    """option istft_tc: the inverse DFT as a two-tap tcgen05 GEMM with the window / envelope folded into the weights (3-pass
+    fp16 split: 3e-6 instead of the fused fp32 kernel's 4e-8)"""
+    from eabnet_b200 import EaBNet, istft
+    net = EaBNet()                                   # any handle: the switch is process-wide
+    g = torch.Generator().manual_seed(1000 + T)
+    spec = torch.randn(B, 2, T, 161, generator=g)
+    ref = O.istft(spec)
+    try:
+        net.set_option("istft_tc", 1)
+        got = istft(spec.cuda()).cpu()
+    finally:
+        net.set_option("istft_tc", 0)
+    assert got.shape == ref.shape == (B, 160 * (T - 1))
+    assert float((got - ref).abs().max()) <= 5e-6 * max(1.0, float(ref.abs().max()))
+
+
 def test_stft_istft_round_trip_full_size():
     """size-independent property at the BASELINE config-2 length: without the compression the analysis /
     synthesis pair is the identity on the interior, so istft(stft) applied to z|z| must return the wave."""
