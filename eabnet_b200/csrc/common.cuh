@@ -289,6 +289,10 @@ struct PlaneConvArgs {
     // "wide" staging (first layer, 2M input channels): a plane row (t, e) is the whole kf x C tap window, wide_k contiguous
     // floats starting at column e*col_stride of frame t, zero-padded to nslab*64; the time taps are then plain row shifts
     int wide_k;
+    // wide_kt > 1: wide_kt frames stacked along K - K block j (wide_k floats) of row (t, e) is the window of frame
+    // t - (wide_kt - 1 - j) (zeros before the first frame): the time taps cost no MMAs of their own
+    int wide_kt;
+    int ksteps;                  // 16-column K steps of a slab that carry data (0 = all 4; 3 when wide_k <= 48: the rest is zero padding)
     float algo_in_share;         // profiling only: share of the layer's input bytes this launch accounts for (0 = all)
 };
 bool plane_conv_supported(const PlaneConvArgs& a);      // shape rules of the padded-pitch row space (pure check)

@@ -15,6 +15,7 @@
 // Since round 2 the 2-D conv layers with 64-channel sources run on conv_raw.cu (no stage pass, no planes in HBM); this pair
 // remains for what that kernel does not take: the first layer (2M input channels, frequency-pair rows), the STFT-as-GEMM,
 // pointwise / dilated GEMMs with a residual, ReLU, two statistics or wide sources (TCM layer path, w_dnn, GaGNet heads).
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -86,11 +87,17 @@ __global__ void __launch_bounds__(256) stage_kernel(const PlaneConvArgs a) {
             if (r >= 0 && r < a.T * a.P) {
                 const int t = (int)__umulhi((unsigned)r, a.p_magic);
                 const int col = r - t * a.P;
-                const int k0 = slab * KC + c8 * 8;
+                int k0 = slab * KC + c8 * 8;
+                int tt = t;
+                if (a.wide_kt > 1) {               // frames stacked along K (wide_k % 8 == 0: a chunk stays inside its frame)
+                    const int j = k0 / a.wide_k;
+                    k0 -= j * a.wide_k;
+                    tt = j < a.wide_kt ? t - (a.wide_kt - 1 - j) : -1;
+                }
                 // the window never leaves its frame: in the pair layout the last row's second position is past the last bin
                 const int wk = min(a.wide_k, (a.Fin - col * a.col_stride) * src.C);
-                if (col < a.plane_cols[0] && k0 < wk) {
-                    const float* p = src.x + (((size_t)b * a.T + t) * a.Fin + (size_t)col * a.col_stride) * src.C + k0;     // 8-byte aligned
+                if (col < a.plane_cols[0] && k0 < wk && tt >= 0) {
+                    const float* p = src.x + (((size_t)b * a.T + tt) * a.Fin + (size_t)col * a.col_stride) * src.C + k0;     // 8-byte aligned
                     float x[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -171,7 +178,8 @@ __host__ __device__ inline Plan make_plan(const PlaneConvArgs& a) {
     p.w_images = a.ntaps * a.nslab * npb;
     p.stg_ld = a.Cout + 4;
     p.b_off = a.nbuf * p.buf_bytes;
-    p.stg_off = p.b_off + (a.resident ? p.w_images : a.nsb) * p.b_stage_bytes;
+    // ring mode, 3 passes: a stage holds the W-hi AND the W-lo image of one (tap, slab) - one wait and one commit per three units
+    p.stg_off = p.b_off + (a.resident ? p.w_images : a.nsb * npb) * p.b_stage_bytes;
     p.rowoff_off = p.stg_off;
     p.bias_off = p.rowoff_off;
     p.utab_off = p.bias_off + a.N * 4;
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(NTHREADS_STAGED, 1) conv_tma_kernel(const Plan
 
         const uint32_t idesc = make_idesc(a.N);
         const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0;
-        long long t_wacc = 0, t_wplane = 0, t_wb = 0;
+        long long t_wacc = 0, t_wplane = 0, t_wb = 0, t_issue = 0, t_commit = 0;
         const long long t_start = dbg_on ? clock64() : 0;
         const uint32_t bs_lo = desc_lo(smem_u32(Bs));
         const uint32_t bstep = (uint32_t)pl.b_stage_bytes >> 4;
@@ -297,28 +305,38 @@ __global__ void __launch_bounds__(NTHREADS_STAGED, 1) conv_tma_kernel(const Plan
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.N);
             const uint32_t origin = (smem_u32(planes + buf * pl.buf_bytes) + (uint32_t)lead * 128u) >> 4;
+            int pass3 = 0;                                       // units run (tap, slab) major, pass minor
             for (int unit = 0; unit < units_per_tile; ++unit) {
                 uint32_t blo;
                 if (!a.resident) {                               // single issuer in ring mode: the ring position runs on
-                    const long long w2 = dbg_on ? clock64() : 0;
-                    mbar_wait(&b_full[stage], sphase);
-                    if (dbg_on) t_wb += clock64() - w2;
-                    tc_fence_after();
-                    blo = bs_lo + (uint32_t)stage * bstep;
+                    if (pass3 == 0) {
+                        const long long w2 = dbg_on ? clock64() : 0;
+                        mbar_wait(&b_full[stage], sphase);
+                        if (dbg_on) t_wb += clock64() - w2;
+                        tc_fence_after();
+                    }
+                    blo = bs_lo + (uint32_t)(stage * npb + (pass3 == 2 ? 1 : 0)) * bstep;
                 } else {
                     blo = bs_lo + (uint32_t)a.unit_b[unit] * bstep;
                 }
                 const uint32_t alo = ((origin + a.unit_a[unit]) & 0x3FFFu) | (1u << 16);
-                umma_f16_lo_elect_x4(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
-                if (!a.resident) {
-                    umma_commit_elect(&b_empty[stage]);
-                    if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
+                const long long w3 = dbg_on ? clock64() : 0;
+                if (a.ksteps == 3) umma_f16_lo_elect_x3(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
+                else umma_f16_lo_elect_x4(d_tmem, alo, blo, idesc, unit ? 1u : 0u);
+                const long long w4 = dbg_on ? clock64() : 0;
+                if (++pass3 == a.npass) {
+                    pass3 = 0;
+                    if (!a.resident) {
+                        umma_commit_elect(&b_empty[stage]);
+                        if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
+                    }
                 }
+                if (dbg_on) { t_issue += w4 - w3; t_commit += clock64() - w4; }
             }
             umma_commit_elect(&acc_full[acc]);
             umma_commit_elect(&plane_empty[buf]);
         }
-        if (dbg_on && lane == 0) { a.dbg[4] = clock64() - t_start; a.dbg[5] = t_wacc; a.dbg[6] = t_wplane; a.dbg[7] = t_wb; a.dbg[2] = tile_end - tile_begin; a.dbg[0] = clock64() - t_start; }
+        if (dbg_on && lane == 0) { a.dbg[4] = clock64() - t_start; a.dbg[5] = t_wacc; a.dbg[6] = t_wplane; a.dbg[7] = t_wb; a.dbg[2] = tile_end - tile_begin; a.dbg[0] = clock64() - t_start; a.dbg[1] = t_issue; a.dbg[3] = t_commit; a.dbg[13] = a.nsb; a.dbg[14] = a.nbuf; a.dbg[15] = a.resident; }
     } else if (warp == 2) {
         // =========================================================================== B (weight) loader
         int stage = 0;
@@ -335,16 +353,15 @@ __global__ void __launch_bounds__(NTHREADS_STAGED, 1) conv_tma_kernel(const Plan
         } else
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             for (int ts = 0; ts < a.ntaps * a.nslab; ++ts) {
-                for (int pass = 0; pass < a.npass; ++pass) {
-                    mbar_wait(&b_empty[stage], sphase ^ 1);
-                    if (lane == 0) {
-                        const float* img = (pass == 2 ? a.Wlo : a.Whi) + (size_t)ts * a.N * 32;
-                        mbar_arrive_expect_tx(&b_full[stage], bytes);
-                        bulk_copy_g2s(Bs + stage * pl.b_stage_bytes, img, bytes, &b_full[stage]);
-                    }
-                    __syncwarp();
-                    if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
+                mbar_wait(&b_empty[stage], sphase ^ 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&b_full[stage], bytes * (uint32_t)npb);
+                    uint8_t* dst = Bs + (size_t)stage * npb * pl.b_stage_bytes;
+                    bulk_copy_g2s(dst, a.Whi + (size_t)ts * a.N * 32, bytes, &b_full[stage]);
+                    if (npb == 2) bulk_copy_g2s(dst + pl.b_stage_bytes, a.Wlo + (size_t)ts * a.N * 32, bytes, &b_full[stage]);
                 }
+                __syncwarp();
+                if (++stage == a.nsb) { stage = 0; sphase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -554,7 +571,8 @@ int choose_nbuf(PlaneConvArgs& a) {
         if (make_plan(a).total <= 227 * 1024) return nb;
     }
     a.resident = 0;                                      // 2. weight ring: as many plane buffers as fit with a 3-stage ring
-    for (int nb = 3; nb >= 1; --nb) {                    //    (measured: 3 buffers + 3 stages beats 2 buffers + 6 stages), then
+    static const int nbuf_env = getenv("EAB_TMA_NBUF") ? atoi(getenv("EAB_TMA_NBUF")) : 3;     // diagnostics
+    for (int nb = nbuf_env >= 1 && nbuf_env <= 3 ? nbuf_env : 3; nb >= 1; --nb) {                    //    (measured: 3 buffers + 3 stages beats 2 buffers + 6 stages), then
         a.nbuf = nb;                                     //    deepen the ring into whatever shared memory is left
         a.nsb = 3;
         if (make_plan(a).total > 227 * 1024) continue;
@@ -629,6 +647,8 @@ int launch_stage(const PlaneConvArgs& a_in, cudaStream_t st) {
 int launch_conv_staged(PlaneConvArgs a, cudaStream_t st) {
     if (a.B <= 0 || a.T <= 0 || a.E <= 0) return 0;
     a.p_magic = a.P == 1 ? 0u : (unsigned)((1ull << 32) / (unsigned)a.P) + 1u;
+    static const int k3_env = getenv("EAB_TMA_K3") ? atoi(getenv("EAB_TMA_K3")) : 1;
+    if (!k3_env) a.ksteps = 0;
     if (!choose_nbuf(a)) return fail("conv_staged: shared-memory budget");
     const Plan pl = make_plan(a);
     {

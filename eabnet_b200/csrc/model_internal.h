@@ -69,6 +69,7 @@ struct ConvLayer {
     // output position reads ceil(kf / 2) consecutive rows, so taps = kt x ceil(kf / 2) row shifts (stride-2 conv only)
     bool pair_ok = false;
     int p_ntaps = 0, p_dt[kMaxTaps], p_ds[kMaxTaps];
+    int p_stack = 1;                     // kt when the time taps are stacked along K (kt * 2 cin <= 64): taps = frequency shifts only
     size_t off_phi = 0, off_plo = 0;
     NormAct na;
 };

@@ -162,23 +162,29 @@ struct Packer {
         L.umma_ok = true;
         if (L.wide && !L.deconv && 2 * L.cin <= 64 && L.kt * ((L.kf + 1) / 2) <= kMaxTaps) {
             const int ns = (L.kf + 1) / 2;
-            L.p_ntaps = L.kt * ns;
+            // kt * 2 cin <= 64 (and 8-float chunks that stay inside a frame): the kt frames of a pair are stacked along K,
+            // the row carries no zero padding and only the ns frequency shifts remain as taps (half the MMAs for kt = 2)
+            const bool stack = L.kt > 1 && L.kt * 2 * L.cin <= 64 && (2 * L.cin) % 8 == 0;
+            L.p_stack = stack ? L.kt : 1;
+            L.p_ntaps = stack ? ns : L.kt * ns;
             const size_t img = (size_t)L.p_ntaps * cout_t * 32;            // floats: one 64-wide slab per tap
             L.off_phi = alloc(img);
             L.off_plo = alloc(img);
             __half* phi = reinterpret_cast<__half*>(blob.data() + L.off_phi);
             __half* plo = reinterpret_cast<__half*>(blob.data() + L.off_plo);
             int q = 0;
-            for (int j = 0; j < L.kt; ++j)
+            for (int j0 = 0; j0 < (stack ? 1 : L.kt); ++j0)
                 for (int sft = 0; sft < ns; ++sft, ++q) {
-                    L.p_dt[q] = L.kt - 1 - j;
+                    L.p_dt[q] = stack ? 0 : L.kt - 1 - j0;
                     L.p_ds[q] = sft;
                     const size_t base = (size_t)q * cout_t * 64;
                     for (int n = 0; n < cout_t; ++n)
                         for (int k = 0; k < 64; ++k) {
-                            const int pos = k / L.cin, cm = k - pos * L.cin;       // position inside the pair, memory channel
+                            const int j = stack ? k / (2 * L.cin) : j0;           // kernel row (frame t - (kt - 1 - j))
+                            const int kk = stack ? k - j * 2 * L.cin : k;
+                            const int pos = kk / L.cin, cm = kk - pos * L.cin;    // position inside the pair, memory channel
                             float w = 0.f;
-                            if (pos < 2 && 2 * sft + pos < L.kf) {
+                            if (j < L.kt && pos < 2 && 2 * sft + pos < L.kf) {
                                 int ci = cm;                                      // memory channel -> reference channel
                                 if (L.perm_ri) { const int mic = cm / 2, ri = cm - 2 * mic; ci = ri * L.M + mic; }
                                 w = W[(((size_t)n * L.cin + ci) * L.kt + j) * L.kf + 2 * sft + pos];

@@ -259,8 +259,10 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
             }
             p.nslab = 1;
             p.Whi = cx.W(L.off_phi); p.Wlo = cx.W(L.off_plo);
-            p.algo_frac = (float)(L.kf * cin) / (float)(((L.kf + 1) / 2) * 64);
+            p.algo_frac = (float)(L.p_stack * L.kf * cin) / (float)(((L.kf + 1) / 2) * 64);
             p.wide_k = 2 * cin;
+            p.wide_kt = L.p_stack;
+            if (L.p_stack * 2 * cin <= 48 && L.p_stack * 2 * cin > 32) p.ksteps = 3;      // 36 of 64 columns (M = 9): the fourth K step is padding
         } else {
             p.P = Fout;
             p.plane_cols[0] = Fout;

@@ -200,6 +200,22 @@ __device__ __forceinline__ void umma_f16_lo_elect_x4(uint32_t tmem_d, uint32_t a
         "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate_first), "r"(DESC_HI)
         : "memory");
 }
+// three K steps: a slab whose last 16 columns are zero padding (first layer: 36 of 64)
+__device__ __forceinline__ void umma_f16_lo_elect_x3(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t"
+        "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t}" ::"r"(tmem_d),
+        "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate_first), "r"(DESC_HI)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
