@@ -394,6 +394,8 @@ int launch_lstm_ln_frame(const LstmFrameArgs& a, cudaStream_t st);
 int launch_lstm_cell_frame(const LstmFrameArgs& a, cudaStream_t st);
 bool lstm_umma_supported(const LstmArgs& a);
 int launch_lstm_umma(const LstmArgs& a, cudaStream_t st);
+bool lstm_pp_supported(const LstmArgs& a);      // lstm_pp.cu: 128 sequences per CTA as two interleaved sub-batches
+int launch_lstm_pp(const LstmArgs& a, cudaStream_t st);
 
 struct BeamArgs {
     const float* w;              // [B][T][F][w_ld]: first 2M (mimo) / 2 (miso) channels used, channel = m*2 + ri

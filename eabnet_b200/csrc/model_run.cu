@@ -731,6 +731,11 @@ int run_forward(Ctx& cx, const float* inpt, float* out_dev) {
                     u.exp_flags = m->opt_lstm_exp;
                     u.Wimg = cx.W(m->off_rnn_img[l]);
                     u.bias = cx.W(m->off_rnn_ubias[l]);
+                    if (m->opt_lstm_pp && lstm_pp_supported(u)) {
+                        EAB_TRY(launch_lstm_pp(u, cx.st));
+                        tap(cx, l ? "h2" : "h1", h[l]);
+                        continue;
+                    }
                     if (lstm_umma_supported(u)) {
                         EAB_TRY(launch_lstm_umma(u, cx.st));
                         tap(cx, l ? "h2" : "h1", h[l]);

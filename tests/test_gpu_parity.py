@@ -252,6 +252,28 @@ def test_full_size_config2_slice_against_oracle():
     assert (out[idx] - ref4).abs().max() <= 1e-4
 
 
+def test_interleaved_lstm_kernel_matches_oracle():
+    """option lstm_pp: the LSTM layers as two interleaved sub-batches per CTA (lstm_pp.cu) - same arithmetic as lstm_umma.cu,
+    other schedule and TMEM access shape; B x F = 483 sequences = three full CTAs and a ragged one that straddles batch items"""
+    cfg = O.make_cfg()
+    net, sd = _net(cfg, seed=12)
+    wave, _ = O.make_wave(3, 9, 6400, seed=44)
+    spec = O.stft_compress(wave)
+    ref = O.forward(sd, spec, cfg)
+    with torch.no_grad():
+        base = net(spec.cuda()).cpu()
+        net.set_option("lstm_pp", 1)
+        try:
+            net.set_option("head_w_tap", 1)
+            got = net(spec.cuda()).cpu()
+            h2 = net.debug_tap("h2", (3, spec.shape[1], 161, 64)).cpu()
+        finally:
+            net.set_option("lstm_pp", 0)
+    assert torch.isfinite(h2).all() and float(h2.abs().max()) > 0
+    assert (got - ref).abs().max() <= TIGHT * max(1.0, float(ref.abs().max()))
+    assert (got - base).abs().max() <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
 def test_many_tiles_per_cta_match_one_tile_per_cta():
     """conv_raw's grid capped to 3 CTAs (option raw_grid): every CTA walks dozens of tiles, so all of the kernel's mbarrier
     phase logic, ring wrap-arounds and batch-item changes run at a size the oracle checks in a second; BatchNorm models are
