@@ -69,6 +69,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// timing experiments (diagnostics builds, EAB_NVCC_EXTRA=-DEAB_LSTM_EXPERIMENT; option lstm_exp; wrong results): bit 1 no copy-out
+// stores, 2 no SFU work, 4 one bias load per half instead of 32 (measured: no effect), 8 no fp32 staging stores (-3 %)
 #ifdef EAB_LSTM_EXPERIMENT
 #define EXP_FLAG(bit) ((a.exp_flags & (bit)) != 0)
 #else
@@ -196,7 +198,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                 tmem_ld8_nowait(taddr + u * 128 + 24, go);
                 tmem_wait_ld();
                 float hv[8];
-                const float* bi = sbias + u * 128 + qtr * 32;   // biases pre-scaled by -log2(e) (i,f,o) / -2 log2(e) (g)
+                const float* bi = sbias + (EXP_FLAG(4) ? 0 : u * 128 + qtr * 32);   // biases pre-scaled by -log2(e) (i,f,o) / -2 log2(e) (g)
+                const float bconst = EXP_FLAG(4) ? bi[0] : 0.f;          // experiment: one bias load per half instead of 32
                 // 7 SFU ops per unit instead of 10: the sigmoid / tanh quotients share their reciprocals
                 //   c' = sig(f) c + sig(i) tanh(g) = [c (1+Ei)(1+Eg) + (1-Eg)(1+Ef)] / [(1+Ei)(1+Ef)(1+Eg)]
                 //   h  = sig(o) tanh(c')          = (1-Ec) / [(1+Eo)(1+Ec)]
@@ -217,10 +220,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                         }
                         continue;
                     }
-                    const F2 ti = fma2({__uint_as_float(gi[e]), __uint_as_float(gi[e + 1])}, nl, {bi[e], bi[e + 1]});
-                    const F2 tf = fma2({__uint_as_float(gf[e]), __uint_as_float(gf[e + 1])}, nl, {bi[8 + e], bi[8 + e + 1]});
-                    const F2 tg = fma2({__uint_as_float(gg[e]), __uint_as_float(gg[e + 1])}, nl2, {bi[16 + e], bi[16 + e + 1]});
-                    const F2 to = fma2({__uint_as_float(go[e]), __uint_as_float(go[e + 1])}, nl, {bi[24 + e], bi[24 + e + 1]});
+                    const F2 ti = fma2({__uint_as_float(gi[e]), __uint_as_float(gi[e + 1])}, nl, EXP_FLAG(4) ? F2{bconst, bconst} : F2{bi[e], bi[e + 1]});
+                    const F2 tf = fma2({__uint_as_float(gf[e]), __uint_as_float(gf[e + 1])}, nl, EXP_FLAG(4) ? F2{bconst, bconst} : F2{bi[8 + e], bi[8 + e + 1]});
+                    const F2 tg = fma2({__uint_as_float(gg[e]), __uint_as_float(gg[e + 1])}, nl2, EXP_FLAG(4) ? F2{bconst, bconst} : F2{bi[16 + e], bi[16 + e + 1]});
+                    const F2 to = fma2({__uint_as_float(go[e]), __uint_as_float(go[e + 1])}, nl, EXP_FLAG(4) ? F2{bconst, bconst} : F2{bi[24 + e], bi[24 + e + 1]});
                     const F2 Ei = {ex2(fminf(ti.x, 40.f)), ex2(fminf(ti.y, 40.f))};
                     const F2 Ef = {ex2(fminf(tf.x, 40.f)), ex2(fminf(tf.y, 40.f))};
                     const F2 Eg = {ex2(fminf(tg.x, 40.f)), ex2(fminf(tg.y, 40.f))};
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_umma_kernel(const LstmArgs a
                     const F2 h = mul2(sub2(one, Ec), {rcp_approx(hden.x), rcp_approx(hden.y)});
                     hv[e] = h.x; hv[e + 1] = h.y;
                 }
-                {   // fp32 copy for HBM: chunk c of a row lives at (c ^ (row & 7)) * 16 (conflict-free both ways)
+                if (!EXP_FLAG(8)) {   // fp32 copy for HBM: chunk c of a row lives at (c ^ (row & 7)) * 16 (conflict-free both ways)
                     if (u == 0 && t > 0) MBW(hs_free, (uint32_t)((t - 1) & 1));    // h_{t-1} has left the staging tile
                     const int c0 = qtr * 4 + u * 2;
                     *reinterpret_cast<float4*>(hs_row + (((c0 + 0) ^ (row & 7)) << 4)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
