@@ -159,22 +159,40 @@ int get_tables(Tables** out) {
 }
 
 // acc[r] = sum_k A[k][r] * tab[k][col]   (A in shared memory, 16-byte aligned rows of RB floats)
+// The table column is fetched KB values at a time, one block ahead of the arithmetic: with one load per k the loop runs at
+// the L2 latency of that load (a streaming frame kernel - few CTAs, the 207 KB table read by each - took 58 us for 161 steps).
+// R <= RB live rows (the rows of A keep their pitch of RB floats).
+constexpr int KB = 8;
+template <int R = RB>
 __device__ __forceinline__ void column_gemm(const float* __restrict__ A, const float* __restrict__ tab, int col,
-                                            float (&acc)[RB]) {
+                                            float (&acc)[R]) {
 #pragma unroll
-    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-#pragma unroll 2
-    for (int k = 0; k < NF; ++k) {
-        const float tv = __ldg(tab + (size_t)k * LDT + col);
-        const float4* a4 = reinterpret_cast<const float4*>(A + k * RB);
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    const float* tc = tab + col;
+    float cur[KB], nxt[KB];
 #pragma unroll
-        for (int u = 0; u < RB / 4; ++u) {
-            const float4 v = a4[u];
-            acc[4 * u + 0] = fmaf(v.x, tv, acc[4 * u + 0]);
-            acc[4 * u + 1] = fmaf(v.y, tv, acc[4 * u + 1]);
-            acc[4 * u + 2] = fmaf(v.z, tv, acc[4 * u + 2]);
-            acc[4 * u + 3] = fmaf(v.w, tv, acc[4 * u + 3]);
+    for (int j = 0; j < KB; ++j) cur[j] = __ldg(tc + (size_t)j * LDT);
+#pragma unroll 1
+    for (int k0 = 0; k0 < NF; k0 += KB) {
+#pragma unroll
+        for (int j = 0; j < KB; ++j) nxt[j] = k0 + KB + j < NF ? __ldg(tc + (size_t)(k0 + KB + j) * LDT) : 0.f;
+#pragma unroll
+        for (int j = 0; j < KB; ++j) {
+            if (k0 + j < NF) {
+                const float tv = cur[j];
+                const float4* a4 = reinterpret_cast<const float4*>(A + (k0 + j) * RB);
+#pragma unroll
+                for (int u = 0; u < R / 4; ++u) {
+                    const float4 v = a4[u];
+                    acc[4 * u + 0] = fmaf(v.x, tv, acc[4 * u + 0]);
+                    acc[4 * u + 1] = fmaf(v.y, tv, acc[4 * u + 1]);
+                    acc[4 * u + 2] = fmaf(v.z, tv, acc[4 * u + 2]);
+                    acc[4 * u + 3] = fmaf(v.w, tv, acc[4 * u + 3]);
+                }
+            }
         }
+#pragma unroll
+        for (int j = 0; j < KB; ++j) cur[j] = nxt[j];
     }
 }
 
@@ -387,9 +405,10 @@ __global__ void __launch_bounds__(THREADS) stft_frame_kernel(const float* __rest
 }
 
 // Spectrum frame n [S][2][161] -> windowed inverse DFT; output hop n-1 = (second half of frame n-1, carried in `tail`,
-// + first half of frame n) / envelope.  The first call (n == 0) emits zeros.  grid (ceil(S / RB)), rows = streams.
+// + first half of frame n) / envelope.  The first call (n == 0) emits zeros.  grid (ceil(S / RBF)), rows = streams.
 // hop_out16 != null: the hop leaves as int16(clip(y, -1, 1) * 32767); start: see stft_frame_kernel (a stream's first frame emits
 // zeros: its overlap-add partner does not exist yet).
+constexpr int RBF = 8;           // streams per CTA of the inverse frame kernel (one frame each: 256 streams = 32 CTAs, not 11)
 __global__ void __launch_bounds__(THREADS) istft_frame_kernel(const float* __restrict__ frame, float* __restrict__ tail,
                                                               float* __restrict__ hop_out, short* __restrict__ hop_out16,
                                                               const int* __restrict__ step_p, const int* __restrict__ start,
@@ -400,8 +419,8 @@ __global__ void __launch_bounds__(THREADS) istft_frame_kernel(const float* __res
     float* Aim = Are + NF * RB;
     float* PQ = Aim + NF * RB;
     const int step = *step_p;
-    const int s0 = blockIdx.x * RB;
-    for (int i = threadIdx.x; i < RB * NF; i += THREADS) {
+    const int s0 = blockIdx.x * RBF;
+    for (int i = threadIdx.x; i < RBF * NF; i += THREADS) {
         const int r = i / NF, f = i - r * NF;
         float re = 0.f, im = 0.f;
         if (s0 + r < S) {
@@ -414,13 +433,13 @@ __global__ void __launch_bounds__(THREADS) istft_frame_kernel(const float* __res
     __syncthreads();
     const int col = threadIdx.x;
     if (col < NCOL) {
-        float acc[RB];
-        column_gemm(col < NF ? Are : Aim, tab, col, acc);
+        float acc[RBF];
+        column_gemm<RBF>(col < NF ? Are : Aim, tab, col, acc);
 #pragma unroll
-        for (int r = 0; r < RB; ++r) PQ[r * NCOL + col] = acc[r];
+        for (int r = 0; r < RBF; ++r) PQ[r * NCOL + col] = acc[r];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < RB * HOP; i += THREADS) {
+    for (int i = threadIdx.x; i < RBF * HOP; i += THREADS) {
         const int r = i / HOP, n = i - r * HOP;
         if (s0 + r >= S) continue;
         const float* P = PQ + r * NCOL;
@@ -608,7 +627,7 @@ int launch_istft_frame(const float* frame, float* tail, float* hop_out, short* h
     EAB_TRY(get_tables(&t));
     EAB_TRY(configure_smem());
     ProfScope ps("istft_frame", 2.0 * NF * NCOL * (double)S, 4.0 * ((double)S * 2 * NF + (double)S * HOP * 3), st);
-    EAB_CUDA(launch_k(istft_frame_kernel, dim3((S + RB - 1) / RB), dim3(THREADS), kSmemBytes, st, frame, tail, hop_out, hop_out16, step, start,
+    EAB_CUDA(launch_k(istft_frame_kernel, dim3((S + RBF - 1) / RBF), dim3(THREADS), kSmemBytes, st, frame, tail, hop_out, hop_out16, step, start,
                       (const float*)t->inv, (const float*)t->win, (const float*)t->ienv, S));
     EAB_LAUNCH_CHECK("istft_frame_kernel");
     return 0;
