@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
 #pragma unroll
             for (int s = 0; s < SPC; ++s) p[s] = 0.f;
             const int j0 = kg * kper2, j1 = min(a.kd * CD, j0 + kper2);
-#pragma unroll 8
+#pragma unroll 20
             for (int j = j0; j < j1; ++j) {
                 const int tap = j / CD, c = j & (CD - 1);
                 const float wv = __ldg(a.blob + d.W_dil + ((size_t)tap * 2 * CD + br * CD + c) * (2 * CD) + col);
