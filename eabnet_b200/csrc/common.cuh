@@ -235,8 +235,13 @@ struct UmmaConvArgs {
     // reads frame n - dt (zeros before the stream's start frame)
     const int* step; const int* start;
     int out_RT, resid_RT;
+    // second variant of the same launch (launch_conv_umma_pair: both output parities of a streaming transposed conv): CTAs
+    // [0, grid0) run the fields above, the rest these; everything else is shared.  grid0 == 0: one variant
+    int grid0;
+    struct Var { int E, out_off, ntaps, tiles_per_b; int dt[kMaxTaps], df[kMaxTaps]; const float* Whi; const float* Wlo; } var1;
 };
 bool umma_conv_supported(const UmmaConvArgs& a);
+int launch_conv_umma_pair(const UmmaConvArgs& a0, const UmmaConvArgs& a1, cudaStream_t st);      // streaming only
 int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st);
 
 // "Stage once, shift by descriptor": GEMM rows are (t, e') with a padded pitch P >= E rows per frame; the transformed fp16

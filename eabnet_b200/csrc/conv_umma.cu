@@ -144,14 +144,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     }
     if (tid == 0) UDBG(2);
 
+    // Two variants in one grid (streaming: both output parities of a transposed conv - they read the same frames and differ in
+    // taps, weights and output columns): CTAs [0, grid0) run variant 0, the rest variant 1.  grid0 == 0: one variant.
+    const bool v1 = a.grid0 > 0 && (int)blockIdx.x >= a.grid0;
+    const int vE = v1 ? a.var1.E : a.E;
+    const int v_ntaps = v1 ? a.var1.ntaps : a.ntaps;
+    const int v_out_off = v1 ? a.var1.out_off : a.out_off;
+    const int v_tpb = v1 ? a.var1.tiles_per_b : a.tiles_per_b;
+    const float* vWhi = v1 ? a.var1.Whi : a.Whi;
+    const float* vWlo = v1 ? a.var1.Wlo : a.Wlo;
+    const unsigned bx = v1 ? blockIdx.x - (unsigned)a.grid0 : blockIdx.x;
+    const unsigned gx = a.grid0 > 0 ? (v1 ? gridDim.x - (unsigned)a.grid0 : (unsigned)a.grid0) : gridDim.x;
     // contiguous tile range of this CTA
-    const long long ntiles = (long long)a.B * a.tiles_per_b;
-    const long long tile_begin = ntiles * blockIdx.x / gridDim.x;
-    const long long tile_end = ntiles * (blockIdx.x + 1) / gridDim.x;
-    const int rows_per_b = a.T * a.E;
+    const long long ntiles = (long long)a.B * v_tpb;
+    const long long tile_begin = ntiles * bx / gx;
+    const long long tile_end = ntiles * (bx + 1) / gx;
+    const int rows_per_b = a.T * vE;
     const bool streaming = a.step != nullptr;
     const int nfr = streaming ? __ldg(a.step) : 0;             // absolute frame index of this step
-    const int chunks_per_pass_unit = a.ntaps * a.nslab;       // (tap, slab) pairs
+    const int chunks_per_pass_unit = v_ntaps * a.nslab;       // (tap, slab) pairs
     const int nchunks = chunks_per_pass_unit * (sp.merged ? 1 : a.npass);      // ring stages per tile
 
     if (warp < NPROD / 32) {
@@ -176,21 +187,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         int rt[RPP], rf[RPP];                   // frame index and e * in_stride of this thread's rows (big negative if ragged)
         int rs[RPP];                            // streaming: rt = the row's STREAM, rs = that stream's start frame
         auto decode_tile = [&](long long tile) {
-            const int b = (int)(tile / a.tiles_per_b);
-            const int row0 = (int)(tile - (long long)b * a.tiles_per_b) * TM;
+            const int b = (int)(tile / v_tpb);
+            const int row0 = (int)(tile - (long long)b * v_tpb) * TM;
             xb0 = a.src[0].x + (size_t)b * a.T * a.Fin * C0;
             xb1 = a.nsrc > 1 ? a.src[1].x + (size_t)b * a.T * a.Fin * C1 : nullptr;
 #pragma unroll
             for (int i = 0; i < RPP; ++i) {
                 const int r = row0 + rbase + 32 * i;
-                const int t = r / a.E;
+                const int t = r / vE;
                 rt[i] = r < rows_per_b ? t : -(1 << 28);
-                rf[i] = (r - t * a.E) * a.in_stride;
+                rf[i] = (r - t * vE) * a.in_stride;
                 rs[i] = (streaming && a.start && r < rows_per_b) ? __ldg(a.start + t) : 0;
             }
         };
         auto issue_loads = [&](float4 (&v)[2 * RPP], uint32_t& mask) {
-            const int dtv = a.dt[l_tap], dfv = a.df[l_tap];
+            const int dtv = v1 ? a.var1.dt[l_tap] : a.dt[l_tap], dfv = v1 ? a.var1.df[l_tap] : a.df[l_tap];
             const bool second = l_slab >= nslab0;
             const float* __restrict__ xb = second ? xb1 : xb0;
             const int C = second ? C1 : C0;
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             }
             if (++l_slab == a.nslab) {
                 l_slab = 0;
-                if (++l_tap == a.ntaps) {
+                if (++l_tap == v_ntaps) {
                     l_tap = 0;
                     if (++l_tile < tile_end) decode_tile(l_tile);
                 }
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         const int mode1 = a.nsrc > 1 ? (a.src[1].xf.affine == 0 && a.src[1].xf.prelu == 0 ? 0 : (a.src[1].xf.prelu == 1 ? 2 : 1)) : 0;
         auto consume = [&](float4 (&v)[2 * RPP], uint32_t mask) {
             if ((s_tap | s_slab) == 0) {
-                const int b = (int)(s_tile / a.tiles_per_b);
+                const int b = (int)(s_tile / v_tpb);
                 if (b != cur_b) {
                     named_bar_sync(1, NPROD);   // nobody still reads the previous coefficients
                     for (int i = tid; i < a.ncoef; i += NPROD) {
@@ -333,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             }
             if (++s_slab == a.nslab) {
                 s_slab = 0;
-                if (++s_tap == a.ntaps) { s_tap = 0; ++s_tile; }
+                if (++s_tap == v_ntaps) { s_tap = 0; ++s_tile; }
             }
         };
 
@@ -403,8 +414,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                     mbar_wait_backoff(&empty[stage], phase ^ 1, 32u);
                     if (lane == 0) {
                         mbar_arrive_expect_tx(&full[stage], 2 * bytes);
-                        bulk_copy_g2s(Bs + stage * sp.b_stage_bytes, a.Whi + (size_t)unit * a.N * 32, bytes, &full[stage]);
-                        bulk_copy_g2s(Bs + stage * sp.b_stage_bytes + bytes, a.Wlo + (size_t)unit * a.N * 32, bytes, &full[stage]);
+                        bulk_copy_g2s(Bs + stage * sp.b_stage_bytes, vWhi + (size_t)unit * a.N * 32, bytes, &full[stage]);
+                        bulk_copy_g2s(Bs + stage * sp.b_stage_bytes + bytes, vWlo + (size_t)unit * a.N * 32, bytes, &full[stage]);
                     }
                     __syncwarp();
                     if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -413,7 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
                 for (int pass = 0; pass < a.npass; ++pass) {
                     mbar_wait_backoff(&empty[stage], phase ^ 1, 32u);
                     if (lane == 0) {
-                        const float* img = (pass == 2 ? a.Wlo : a.Whi) + (size_t)unit * a.N * 32;     // N rows x 128 B
+                        const float* img = (pass == 2 ? vWlo : vWhi) + (size_t)unit * a.N * 32;     // N rows x 128 B
                         mbar_arrive_expect_tx(&full[stage], bytes);
                         bulk_copy_g2s(Bs + stage * sp.b_stage_bytes, img, bytes, &full[stage]);
                     }
@@ -432,16 +443,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long tile = tile_begin; tile < tile_end; ++tile) {
-            const int b = (int)(tile / a.tiles_per_b);
-            const int row0 = (int)(tile - (long long)b * a.tiles_per_b) * TM;
+            const int b = (int)(tile / v_tpb);
+            const int row0 = (int)(tile - (long long)b * v_tpb) * TM;
             const int nvalid = min(TM, rows_per_b - row0);
             {
                 const int r = row0 + row;
                 long long off = -1;
                 long long off_r = -1;
                 if (r < rows_per_b) {
-                    const int t = r / a.E, e = r - t * a.E;
-                    const long long fo = e * a.out_stride + a.out_off;
+                    const int t = r / vE, e = r - t * vE;
+                    const long long fo = e * a.out_stride + v_out_off;
                     if (streaming) {
                         off = (((long long)t * a.out_RT + ring_slot(nfr, a.out_RT)) * a.Fout + fo) * a.out_ld + a.out_coff;
                         off_r = (((long long)t * a.resid_RT + ring_slot(nfr, a.resid_RT)) * a.Fout + fo) * a.out_ld + a.out_coff;
@@ -557,6 +568,58 @@ bool umma_conv_supported(const UmmaConvArgs& a) {
     }
     if (a.out_ld % 4 != 0 || a.out_coff % 4 != 0) return false;
     return true;
+}
+
+// Both output parities of a streaming transposed conv as ONE launch (a streaming step is a chain of ~15 us launches whatever
+// their size: 25 of the 81 conv launches of a step disappear).  The variants must agree in everything but taps, weights, output
+// columns and row count.
+int launch_conv_umma_pair(const UmmaConvArgs& a0, const UmmaConvArgs& a1, cudaStream_t st) {
+    if (!a0.step || a0.wide || a1.wide || a0.grid0 || a1.grid0) return fail("conv_umma_pair: streaming, non-wide launches only");
+    if (!umma_conv_supported(a0) || !umma_conv_supported(a1)) return fail("conv_umma_pair: unsupported shape");
+#define EAB_PAIR_SAME(f) if (a0.f != a1.f) return fail("conv_umma_pair: the variants differ in " #f " (only taps, weights and output columns may differ)")
+    EAB_PAIR_SAME(nsrc); EAB_PAIR_SAME(B); EAB_PAIR_SAME(T); EAB_PAIR_SAME(Fin); EAB_PAIR_SAME(Fout); EAB_PAIR_SAME(in_stride);
+    EAB_PAIR_SAME(out_stride); EAB_PAIR_SAME(nslab); EAB_PAIR_SAME(npass); EAB_PAIR_SAME(N); EAB_PAIR_SAME(Cout); EAB_PAIR_SAME(gate_off);
+    EAB_PAIR_SAME(out); EAB_PAIR_SAME(bias); EAB_PAIR_SAME(resid); EAB_PAIR_SAME(out_RT); EAB_PAIR_SAME(resid_RT); EAB_PAIR_SAME(ncoef);
+    EAB_PAIR_SAME(relu); EAB_PAIR_SAME(out_ld); EAB_PAIR_SAME(out_coff);
+#undef EAB_PAIR_SAME
+    for (int i = 0; i < a0.nsrc; ++i)
+        if (a0.src[i].x != a1.src[i].x || a0.src[i].RT != a1.src[i].RT) return fail("conv_umma_pair: different sources");
+    if (a1.E <= 0) return launch_conv_umma(a0, st);
+    if (a0.E <= 0) return launch_conv_umma(a1, st);
+    UmmaConvArgs a = a0;
+    a.var1.E = a1.E; a.var1.out_off = a1.out_off; a.var1.ntaps = a1.ntaps; a.var1.tiles_per_b = a1.tiles_per_b;
+    for (int k = 0; k < kMaxTaps; ++k) { a.var1.dt[k] = a1.dt[k]; a.var1.df[k] = a1.df[k]; }
+    a.var1.Whi = a1.Whi; a.var1.Wlo = a1.Wlo;
+    if (a.B != 1 || a.nstats != 0 || a.out_RT < 1 || (a.resid && a.resid_RT < 1)) return fail("conv_umma: bad streaming launch");
+    for (int i = 0; i < a.nsrc; ++i) {
+        if (a.src[i].xf.affine == 1) return fail("conv_umma: a streaming launch needs static normalisation (its coefficients are set before the dependency wait)");
+        int back = 0;
+        for (int k = 0; k < a0.ntaps; ++k) back = std::max(back, a0.dt[k]);
+        for (int k = 0; k < a1.ntaps; ++k) back = std::max(back, a1.dt[k]);
+        if (a.src[i].RT < back + 1) return fail("conv_umma: source ring shorter than the receptive field");
+    }
+    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass);
+    if (sp.nstages < 2) return fail("conv_umma: not enough shared memory for two stages");
+    EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<false>), sp.total));
+    int sms = 0;
+    EAB_TRY(device_sm_count(&sms));
+    const long long nt0 = (long long)a.B * a0.tiles_per_b, nt1 = (long long)a.B * a1.tiles_per_b;
+    int g0 = (int)nt0, g1 = (int)nt1;
+    if (nt0 + nt1 > sms) {               // one CTA per SM: split the SMs by tile count
+        g0 = (int)std::max(1ll, std::min((long long)sms - 1, (sms * nt0 + (nt0 + nt1) / 2) / (nt0 + nt1)));
+        g1 = sms - g0;
+    }
+    a.grid0 = g0;
+    double kreal = 0;
+    for (int i = 0; i < a.nsrc; ++i) kreal += a.src[i].C;
+    const double pos0 = (double)a.B * a.T * a0.E, pos1 = (double)a.B * a.T * a1.E;
+    ProfScope ps("conv_umma", 2.0 * (pos0 * a0.ntaps + pos1 * a1.ntaps) * kreal * a.N * a.algo_frac,
+                 4.0 * ((pos0 + pos1) * a.in_stride * kreal / 2.0 + (pos0 + pos1) * a.Cout * (a.resid ? 2 : 1) +
+                        (double)(a0.ntaps + a1.ntaps) * kreal * a.N),
+                 st);
+    EAB_CUDA(launch_k_pdl(conv_umma_kernel<false>, dim3(g0 + g1), dim3(NTHREADS), (size_t)sp.total, st, a));
+    EAB_LAUNCH_CHECK("conv_umma_kernel");
+    return 0;
 }
 
 int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {

@@ -128,6 +128,11 @@ int run_umma_stream(Ctx& cx, UmmaConvArgs* us, int n, int out_RT, int resid_RT) 
         u.step = cx.step; u.start = cx.start; u.out_RT = out_RT; u.resid_RT = resid_RT;
         u.nstats = 0;
         if (cx.m->opt_dbg_launch <= -300 && cx.m->umma_launch_idx++ == -300 - cx.m->opt_dbg_launch && cx.m->dbg_buf) u.dbg = cx.m->dbg_buf;
+        if (n == 2 && cx.m->opt_stream_pair && !u.wide && us[0].out_stride == 2 && us[1].out_stride == 2 && us[0].bias == us[1].bias &&
+            us[0].out == us[1].out && us[0].N == us[1].N) {
+            if (i == 1) EAB_TRY(launch_conv_umma_pair(us[0], us[1], cx.st));     // both output parities of a transposed conv in one grid
+            continue;
+        }
         EAB_TRY(launch_conv_umma(u, cx.st));
     }
     return 0;
