@@ -237,6 +237,10 @@ struct UmmaConvArgs {
     int out_RT, resid_RT;
     // second variant of the same launch (launch_conv_umma_pair: both output parities of a streaming transposed conv): CTAs
     // [0, grid0) run the fields above, the rest these; everything else is shared.  grid0 == 0: one variant
+    // post != 0 (streaming, static normalisation): the epilogue applies post_xf to the layer's own result and adds resid_xf(resid)
+    // - the residual sum of a U-Net module (x0 + y, EaBNet.py:372-388) without a combine launch; the output then carries no transform
+    int post;
+    Xform post_xf, resid_xf;
     int grid0;
     struct Var { int E, out_off, ntaps, tiles_per_b; int dt[kMaxTaps], df[kMaxTaps]; const float* Whi; const float* Wlo; } var1;
 };

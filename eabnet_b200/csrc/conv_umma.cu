@@ -47,7 +47,7 @@ constexpr int A_STAGE_BYTES = TM * 128;
 
 struct Smem {
     // offsets (bytes) into the 1024-aligned dynamic shared memory
-    int a_off, b_off, stg_off, rowoff_off, coef_off, bias_off, bar_off, total;
+    int a_off, b_off, stg_off, rowoff_off, coef_off, bias_off, post_off, bar_off, total;
     int nstages, a_stage_bytes, b_stage_bytes, stg_ld;
     int merged;                 // 3-pass layers: ONE ring stage per (tap, slab) holds A hi | A lo and W hi | W lo
 };
@@ -56,10 +56,11 @@ struct Smem {
 // and arrive; a single-tile CTA (every launch of a streaming step) spent most of its ~14 us on those 27-54 handshakes.  Merged
 // stages hold both halves of the split once: one handshake and twelve MMAs per (tap, slab).  Falls back to per-pass stages when
 // two merged stages do not fit (N = 256).
-__host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef, int npass) {
+__host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef, int npass, int post = 0) {
     Smem s;
     s.stg_ld = Cout + 4;
-    const int fixed = TM * s.stg_ld * 4 + 2 * TM * 8 + 3 * ncoef * 4 + N * 4 + 256 + 64;
+    const int post_bytes = post ? 6 * Cout * 4 : 0;          // [2][3][Cout] coefficients of the fused residual sum
+    const int fixed = TM * s.stg_ld * 4 + 2 * TM * 8 + 3 * ncoef * 4 + N * 4 + post_bytes + 256 + 64;
     const int avail = 227 * 1024 - 1024 - fixed;
     s.merged = 0;
     s.a_stage_bytes = A_STAGE_BYTES;
@@ -79,7 +80,8 @@ __host__ __device__ inline Smem smem_plan(int N, int Cout, int ncoef, int npass)
     s.rowoff_off = s.stg_off + TM * s.stg_ld * 4;
     s.coef_off = s.rowoff_off + 2 * TM * 8;         // row offsets into out, and into resid (a ring of its own when streaming)
     s.bias_off = (s.coef_off + 3 * ncoef * 4 + 15) / 16 * 16;
-    s.bar_off = s.bias_off + N * 4;
+    s.post_off = s.bias_off + N * 4;
+    s.bar_off = (s.post_off + post_bytes + 15) / 16 * 16;
     s.total = s.bar_off + 256 + 1024;          // + slack for the 1024-byte alignment of the base
     return s;
 }
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     // align to 1024 B (128B-swizzle atom) by OFFSETTING the __shared__ array: a round trip through uintptr_t would
     // demote every later access to generic ST.E / LD.E
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass);
+    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass, a.post);
     uint8_t* As = smem + sp.a_off;
     uint8_t* Bs = smem + sp.b_off;
     float* stg = reinterpret_cast<float*>(smem + sp.stg_off);
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
     long long* rowoff_r = rowoff + TM;
     float* coef = reinterpret_cast<float*>(smem + sp.coef_off);
     float* sbias = reinterpret_cast<float*>(smem + sp.bias_off);
+    float* pcoef = reinterpret_cast<float*>(smem + sp.post_off);       // [post | resid][scale, shift, slope][Cout] (a.post)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
     uint64_t* full = bars;                      // [nstages]  A stored (128 arrivals) + B bytes landed
     uint64_t* empty = bars + 8;                 // [nstages]  MMAs that read the stage have completed
@@ -132,6 +135,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             coef[a.ncoef + i] = ch;
             coef[2 * a.ncoef + i] = a.src[sidx].xf.prelu ? ca : 1.f;
         }
+        if (a.post)
+            for (int i = tid; i < 2 * a.Cout; i += NTHREADS) {
+                const int sidx = i / a.Cout, c = i - sidx * a.Cout;
+                float cs, ch, ca;
+                xform_coeffs(sidx ? a.resid_xf : a.post_xf, 0, a.Cout, c, cs, ch, ca);
+                pcoef[(sidx * 3 + 0) * a.Cout + c] = cs;
+                pcoef[(sidx * 3 + 1) * a.Cout + c] = ch;
+                pcoef[(sidx * 3 + 2) * a.Cout + c] = ca;
+            }
     }
     tc_fence_before();
     __syncthreads();
@@ -506,7 +518,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UmmaConvAr
             for (int r = et / tpr; r < nvalid; r += rows_per_it) {
                 float4 o = *reinterpret_cast<const float4*>(stg + r * ld + cq);
                 const long long off = rowoff[r];
-                if (a.resid) {
+                if (a.post) {                   // module output = xform(this layer) + xform(module input conv): as combine_kernel computes it
+                    float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + rowoff_r[r] + cq));
+                    const float* p0 = pcoef + cq;
+                    const float* p1 = pcoef + 3 * a.Cout + cq;
+                    const int m0 = a.post_xf.prelu, m1 = a.resid_xf.prelu;
+                    q.x = xform_apply(q.x, p1[0], p1[a.Cout], p1[2 * a.Cout], m1) + xform_apply(o.x, p0[0], p0[a.Cout], p0[2 * a.Cout], m0);
+                    q.y = xform_apply(q.y, p1[1], p1[a.Cout + 1], p1[2 * a.Cout + 1], m1) + xform_apply(o.y, p0[1], p0[a.Cout + 1], p0[2 * a.Cout + 1], m0);
+                    q.z = xform_apply(q.z, p1[2], p1[a.Cout + 2], p1[2 * a.Cout + 2], m1) + xform_apply(o.z, p0[2], p0[a.Cout + 2], p0[2 * a.Cout + 2], m0);
+                    q.w = xform_apply(q.w, p1[3], p1[a.Cout + 3], p1[2 * a.Cout + 3], m1) + xform_apply(o.w, p0[3], p0[a.Cout + 3], p0[2 * a.Cout + 3], m0);
+                    o = q;
+                } else if (a.resid) {
                     const float4 q = __ldg(reinterpret_cast<const float4*>(a.resid + rowoff_r[r] + cq));
                     o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
                     if (a.nstats) *reinterpret_cast<float4*>(stg + r * ld + cq) = o;
@@ -580,7 +602,7 @@ int launch_conv_umma_pair(const UmmaConvArgs& a0, const UmmaConvArgs& a1, cudaSt
     EAB_PAIR_SAME(nsrc); EAB_PAIR_SAME(B); EAB_PAIR_SAME(T); EAB_PAIR_SAME(Fin); EAB_PAIR_SAME(Fout); EAB_PAIR_SAME(in_stride);
     EAB_PAIR_SAME(out_stride); EAB_PAIR_SAME(nslab); EAB_PAIR_SAME(npass); EAB_PAIR_SAME(N); EAB_PAIR_SAME(Cout); EAB_PAIR_SAME(gate_off);
     EAB_PAIR_SAME(out); EAB_PAIR_SAME(bias); EAB_PAIR_SAME(resid); EAB_PAIR_SAME(out_RT); EAB_PAIR_SAME(resid_RT); EAB_PAIR_SAME(ncoef);
-    EAB_PAIR_SAME(relu); EAB_PAIR_SAME(out_ld); EAB_PAIR_SAME(out_coff);
+    EAB_PAIR_SAME(relu); EAB_PAIR_SAME(out_ld); EAB_PAIR_SAME(out_coff); EAB_PAIR_SAME(post);
 #undef EAB_PAIR_SAME
     for (int i = 0; i < a0.nsrc; ++i)
         if (a0.src[i].x != a1.src[i].x || a0.src[i].RT != a1.src[i].RT) return fail("conv_umma_pair: different sources");
@@ -591,6 +613,7 @@ int launch_conv_umma_pair(const UmmaConvArgs& a0, const UmmaConvArgs& a1, cudaSt
     for (int k = 0; k < kMaxTaps; ++k) { a.var1.dt[k] = a1.dt[k]; a.var1.df[k] = a1.df[k]; }
     a.var1.Whi = a1.Whi; a.var1.Wlo = a1.Wlo;
     if (a.B != 1 || a.nstats != 0 || a.out_RT < 1 || (a.resid && a.resid_RT < 1)) return fail("conv_umma: bad streaming launch");
+    if (a.post && (!a.resid || a.post_xf.affine == 1 || a.resid_xf.affine == 1)) return fail("conv_umma: a fused residual sum needs a residual and static normalisation");
     for (int i = 0; i < a.nsrc; ++i) {
         if (a.src[i].xf.affine == 1) return fail("conv_umma: a streaming launch needs static normalisation (its coefficients are set before the dependency wait)");
         int back = 0;
@@ -598,7 +621,7 @@ int launch_conv_umma_pair(const UmmaConvArgs& a0, const UmmaConvArgs& a1, cudaSt
         for (int k = 0; k < a1.ntaps; ++k) back = std::max(back, a1.dt[k]);
         if (a.src[i].RT < back + 1) return fail("conv_umma: source ring shorter than the receptive field");
     }
-    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass);
+    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass, a.post);
     if (sp.nstages < 2) return fail("conv_umma: not enough shared memory for two stages");
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<false>), sp.total));
     int sms = 0;
@@ -625,8 +648,10 @@ int launch_conv_umma_pair(const UmmaConvArgs& a0, const UmmaConvArgs& a1, cudaSt
 int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
     if (!umma_conv_supported(a)) return fail("conv_umma: unsupported shape");
     if (a.B <= 0 || a.T <= 0 || a.E <= 0) return 0;
+    if (a.post && !a.step) return fail("conv_umma: the fused residual sum is a streaming feature");
     if (a.step) {
         if (a.B != 1 || a.nstats != 0 || a.out_RT < 1 || (a.resid && a.resid_RT < 1)) return fail("conv_umma: bad streaming launch");
+        if (a.post && (!a.resid || a.post_xf.affine == 1 || a.resid_xf.affine == 1)) return fail("conv_umma: a fused residual sum needs a residual and static normalisation");
         for (int i = 0; i < a.nsrc; ++i) {
             if (a.src[i].xf.affine == 1) return fail("conv_umma: a streaming launch needs static normalisation (its coefficients are set before the dependency wait)");
             int back = 0;
@@ -634,7 +659,7 @@ int launch_conv_umma(const UmmaConvArgs& a, cudaStream_t st) {
             if (a.src[i].RT < back + 1) return fail("conv_umma: source ring shorter than the receptive field");
         }
     }
-    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass);
+    const Smem sp = smem_plan(a.N, a.Cout, a.ncoef, a.npass, a.post);
     if (sp.nstages < 2) return fail("conv_umma: not enough shared memory for two stages");
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<false>), sp.total));
     EAB_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(conv_umma_kernel<true>), sp.total));

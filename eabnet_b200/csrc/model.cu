@@ -701,6 +701,7 @@ int eab_set_option(eab_model* m, const char* name, int value) {
     else if (n == "stream_umma") m->opt_stream_umma = value != 0;
     else if (n == "stream_lstm") m->opt_stream_lstm = value != 0;
     else if (n == "stream_pair") m->opt_stream_pair = value != 0;
+    else if (n == "stream_fuse") m->opt_stream_fuse = value != 0;
     else if (n == "lstm_pp") m->opt_lstm_pp = value != 0;
     else if (n == "lstm_exp") m->opt_lstm_exp = value;
     else if (n == "stft_tc") g_stft_tc = value != 0;

@@ -209,6 +209,7 @@ struct eab_model {
     int opt_lstm_exp = 0;         // diagnostics (EAB_LSTM_EXPERIMENT builds)
     int opt_stream_tcm = 1;       // streaming: the whole TCM stack as one launch (0 = per-layer kernels)
     int opt_lstm_pp = 0;          // LSTM layers on lstm_pp.cu (two interleaved sub-batches of 64 per CTA: measured slower, tensor-pipe bound); 0 = lstm_umma.cu
+    int opt_stream_fuse = 1;      // streaming: a U-Net module's residual sum in the last inner deconv's epilogue (no combine launch); changes the state layout
     int opt_stream_pair = 1;      // streaming: both output parities of a transposed conv as one launch (conv_umma second variant)
     int opt_stream_lstm = 1;      // streaming: the LSTM step as a tensor-core gate GEMM + cell kernel (needs stream_umma); 0 = CUDA-core lstm kernel
     int opt_stream_umma = 1;      // streaming: the per-layer convs on the tcgen05 gather kernel (rows = streams x F); 0 = CUDA cores

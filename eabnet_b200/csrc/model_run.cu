@@ -216,7 +216,10 @@ inline int zone_passes(const eab_model* m, int zone) {
 
 // one 2-D layer: conv/deconv (+gate) -> raw output + statistics; returns the Act a consumer should read
 int materialize(Ctx& cx, Act* a);
-int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* out, float* prealloc = nullptr) {
+// fuse_res / fuse_out (streaming on the tensor cores only, see fuse_ok in run_module): the launch writes xform(own result) +
+// xform(*fuse_res) straight into *fuse_out's buffer - the module's residual sum without a combine launch
+int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* out, float* prealloc = nullptr,
+               const Act* fuse_res = nullptr, const Act* fuse_out = nullptr) {
     Act srcs[2];
     for (int i = 0; i < nsrc; ++i) srcs[i] = srcs_in[i];
     if (!(cx.tensor_ok() && L.umma_ok && cx.m->opt_staged && !L.wide))
@@ -330,6 +333,17 @@ int run_conv2d(Ctx& cx, const ConvLayer& L, const Act* srcs_in, int nsrc, Act* o
                 all_ok = all_ok && umma_conv_supported(u);
             }
         }
+        if (all_ok && fuse_res) {
+            if (!cx.streaming) return fail("internal: fused residual sum outside a streaming step");
+            out->data = fuse_out->data; out->RT = fuse_out->RT;
+            for (int i = 0; i < nus; ++i) {
+                us[i].out = out->data;
+                us[i].post = 1; us[i].post_xf = out->xf; us[i].resid = fuse_res->data; us[i].resid_xf = fuse_res->xf;
+            }
+            out->xf = xform_identity();
+            return run_umma_stream(cx, us, nus, out->RT, fuse_res->RT);
+        }
+        if (fuse_res) return fail("internal: fused residual sum on a layer the tensor-core path does not take");
         if (all_ok) {
             allocate_out();
             for (int i = 0; i < nus; ++i) us[i].out = out->data;
@@ -431,15 +445,21 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
         keep.push_back(z);
         y = z;
     }
+    // streaming on the tensor cores (static normalisation): the last inner deconv's epilogue adds the transformed x0 and writes the
+    // module output itself - no combine launch (9 of a step's launches)
+    const bool fuse_ok = !lazy && cx.streaming && cx.stream_umma() && cx.m->opt_stream_fuse && !U.deco.empty() && U.deco.back().umma_ok &&
+                         !U.deco.back().wide && (U.deco.size() == 1 || cx.m->cfg.intra_connect == 0) && cx.m->cfg.norm_type != 0 &&
+                         U.deco.back().cout == out->C;
     for (size_t i = 0; i < U.deco.size(); ++i) {
         Act z;
         float* pre = (lazy && i + 1 == U.deco.size()) ? buf_y : nullptr;
+        const bool fuse = fuse_ok && i + 1 == U.deco.size();
         if (i == 0) {
-            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z, pre));
+            EAB_TRY(run_conv2d(cx, U.deco[i], &y, 1, &z, pre, fuse ? &x0 : nullptr, fuse ? out : nullptr));
         } else {
             Act pair[2] = {y, keep[keep.size() - 1 - i]};
             if (cx.m->cfg.intra_connect == 0) {
-                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z, pre));
+                EAB_TRY(run_conv2d(cx, U.deco[i], pair, 2, &z, pre, fuse ? &x0 : nullptr, fuse ? out : nullptr));
             } else {
                 Act sum;
                 EAB_TRY(run_combine(cx, pair, 2, &sum));
@@ -451,7 +471,7 @@ int run_module(Ctx& cx, const UnetModule& U, const Act* srcs, int nsrc, Act* out
     if (lazy) {
         out->data = x0.data; out->xf = x0.xf;
         out->data2 = y.data; out->xf2 = y.xf;
-    } else {
+    } else if (!fuse_ok) {
         Act pair[2] = {x0, y};
         EAB_TRY(run_combine_into(cx, pair, 2, out));
     }

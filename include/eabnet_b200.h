@@ -317,6 +317,8 @@ EAB_API int64_t eab_debug_tap(eab_model* m, const char* name, float* dst_dev, in
  *                       batches on two compute streams
  *   "stream_tcm" (1)    streaming: the TCM stack as one launch
  *   "stream_umma" (1)   streaming: the per-layer convs on the tcgen05 gather kernel (all streams in one GEMM row space); 0 = CUDA cores
+ *   "stream_fuse" (1)   streaming (BatchNorm models): the residual sum of a U-Net module in the epilogue of its last inner deconv instead
+ *                       of a launch of its own (9 per step); changes the state layout like the kernel-selection options
  *   "stream_pair" (1)   streaming: the two output parities of a transposed conv as ONE launch (25 of the 81 conv launches of a step)
  *   "lstm_pp" (0)       offline LSTM layers on lstm_pp.cu: 128 sequences per CTA as two interleaved sub-batches whose gate GEMMs run
  *                       under each other's cell phase (tcgen05.ld.16x256b keeps all four schedulers' SFUs busy).  Same results to
