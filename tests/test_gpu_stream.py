@@ -19,7 +19,8 @@ def _net(cfg, variant="B", seed=0):
     return net.cuda(), sd
 
 
-@pytest.mark.parametrize("opts", [{}, {"stream_umma": 0}, {"stream_lstm": 0}, {"stream_tcm": 0}])
+@pytest.mark.parametrize("opts", [{}, {"stream_umma": 0}, {"stream_lstm": 0}, {"stream_tcm": 0}, {"stream_pair": 0}, {"stream_fuse": 0},
+                                  {"stream_pair": 0, "stream_fuse": 0}])
 @pytest.mark.parametrize("extra", [{}, {"is_u2": False, "bf_type": "cnn", "M": 4}, {"intra_connect": "add"}])
 def test_stream_spec_frames_match_offline_oracle(extra, opts):
     """default: per-layer convs and the LSTM gate GEMM on the tensor cores (conv_umma with ring addressing), fused TCM kernel;
@@ -40,6 +41,26 @@ def test_stream_spec_frames_match_offline_oracle(extra, opts):
         worst = max(worst, float((got - ref[:, :, t]).abs().max()))
     assert worst <= EXACT * max(1.0, float(ref.abs().max())), worst
     assert net.last_launch_count() > 0
+
+
+def test_stream_launch_merging_is_bit_identical():
+    """stream_pair (both output parities of a transposed conv in one grid) and stream_fuse (a module's residual sum in the last inner
+    deconv's epilogue) change the launch list, not the arithmetic: same bits, fewer launches"""
+    cfg = O.make_cfg(norm_type="BN")
+    S, T = 5, 12
+    wave, _ = O.make_wave(S, 9, 160 * (T - 1), seed=31)
+    spec = O.stft_compress(wave).cuda()
+    outs, launches = [], []
+    for opts in ({}, {"stream_pair": 0}, {"stream_fuse": 0}, {"stream_pair": 0, "stream_fuse": 0}):
+        net, _ = _net(cfg, seed=7)
+        for k, v in opts.items():
+            net.set_option(k, v)
+        ses = net.stream(S)
+        outs.append(torch.stack([ses.step_spec(spec[:, t].contiguous()) for t in range(T)], 2).cpu())
+        launches.append(net.last_launch_count())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    assert launches[0] < launches[1] < launches[3] and launches[0] < launches[2] < launches[3], launches
 
 
 def test_stream_long_history_and_reset():
