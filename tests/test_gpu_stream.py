@@ -63,6 +63,21 @@ def test_stream_launch_merging_is_bit_identical():
     assert launches[0] < launches[1] < launches[3] and launches[0] < launches[2] < launches[3], launches
 
 
+def test_stream_many_streams_fill_the_gpu():
+    """128 streams: the merged two-parity launches of the wide layers have more tiles than SMs (the grid is split between the
+    variants by tile count, CTAs walk several tiles) - checked against the offline oracle"""
+    cfg = O.make_cfg(norm_type="BN")
+    net, sd = _net(cfg, seed=13)
+    S, T = 128, 4
+    wave, _ = O.make_wave(S, 9, 160 * (T - 1), seed=51)
+    spec = O.stft_compress(wave)
+    ref = O.forward(sd, spec, cfg)
+    ses = net.stream(S)
+    dspec = spec.cuda()
+    outs = torch.stack([ses.step_spec(dspec[:, t].contiguous()) for t in range(T)], 2).cpu()
+    assert (outs - ref).abs().max() <= EXACT * max(1.0, float(ref.abs().max()))
+
+
 def test_stream_long_history_and_reset():
     """more frames than the deepest dilation ring (4*32+1), then reset() and replay: identical results"""
     cfg = O.make_cfg(norm_type="BN")
