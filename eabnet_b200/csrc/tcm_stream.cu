@@ -45,6 +45,16 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
     }
     __syncthreads();
     const int kper2 = (a.kd * CD + KG2 - 1) / KG2;         // (tap, channel) pairs per K group of the dilated convs
+    // The weights do not depend on the activations: every phase fetches the NEXT phase's first PF weights of this thread before
+    // its own reduction and block barriers, so that phase starts on registers instead of an L2 round trip (54 dependent phases).
+    constexpr int PF = 16;
+    float pf[PF];
+    {
+        const int n = tid & (CD - 1), kg = tid / CD;
+        const float* w = a.blob + a.desc[0].W_in + (size_t)(kg * (DF / KG1)) * CD + n;
+#pragma unroll
+        for (int k = 0; k < PF; ++k) pf[k] = __ldg(w + (size_t)k * CD);
+    }
     for (int l = 0; l < a.ntcm; ++l) {
         const TcmStreamDesc& d = a.desc[l];
         // ---------------------------------------------------------------- squeeze 1x1: 64 outputs x 16 K groups
@@ -54,15 +64,25 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
             float p[SPC];
 #pragma unroll
             for (int s = 0; s < SPC; ++s) p[s] = 0.f;
-            const float* w = a.blob + d.W_in + (size_t)(kg * KPER) * CD + n;
+            static_assert(KPER == PF, "the squeeze weights of a thread are exactly the prefetch registers");
 #pragma unroll
             for (int k = 0; k < KPER; ++k) {
-                const float wv = __ldg(w + (size_t)k * CD);
+                const float wv = pf[k];
 #pragma unroll
                 for (int s = 0; s < SPC; ++s) p[s] = fmaf(xs[s][kg * KPER + k], wv, p[s]);
             }
 #pragma unroll
             for (int s = 0; s < SPC; ++s) red[(kg * SPC + s) * CD + n] = p[s];
+        }
+        {   // prefetch: the first PF (tap, channel) weights of this thread's dilated-conv column
+            const int col = tid & (2 * CD - 1), br = col / CD, kg = tid / (2 * CD);
+            const int j0 = kg * kper2;
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int j = min(j0 + k, a.kd * CD - 1);
+                const int tap = j / CD, c = j & (CD - 1);
+                pf[k] = __ldg(a.blob + d.W_dil + ((size_t)tap * 2 * CD + br * CD + c) * (2 * CD) + col);
+            }
         }
         __syncthreads();
         float* ring = a.act_base + d.ring_off;
@@ -100,8 +120,17 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
 #pragma unroll
             for (int s = 0; s < SPC; ++s) p[s] = 0.f;
             const int j0 = kg * kper2, j1 = min(a.kd * CD, j0 + kper2);
-#pragma unroll 20
-            for (int j = j0; j < j1; ++j) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int j = j0 + k;
+                if (j < j1) {
+                    const int tap = j / CD, c = j & (CD - 1);
+#pragma unroll
+                    for (int s = 0; s < SPC; ++s) p[s] = fmaf(u[br][tap][s][c], pf[k], p[s]);
+                }
+            }
+#pragma unroll 12
+            for (int j = j0 + PF; j < j1; ++j) {
                 const int tap = j / CD, c = j & (CD - 1);
                 const float wv = __ldg(a.blob + d.W_dil + ((size_t)tap * 2 * CD + br * CD + c) * (2 * CD) + col);
 #pragma unroll
@@ -109,6 +138,12 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
             }
 #pragma unroll
             for (int s = 0; s < SPC; ++s) red[(kg * SPC + s) * (2 * CD) + col] = p[s];
+        }
+        {   // prefetch: this thread's expand weights
+            const int j = tid & (DF - 1), kg = tid / DF;
+            const float* w = a.blob + d.W_out + (size_t)(kg * (CD / KG3)) * DF + j;
+#pragma unroll
+            for (int c = 0; c < PF; ++c) pf[c] = __ldg(w + (size_t)c * DF);
         }
         __syncthreads();
         if (tid < SPC * CD) {
@@ -130,15 +165,21 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
             float p[SPC];
 #pragma unroll
             for (int s = 0; s < SPC; ++s) p[s] = 0.f;
-            const float* w = a.blob + d.W_out + (size_t)(kg * KPER) * DF + j;
+            static_assert(KPER == PF, "the expand weights of a thread are exactly the prefetch registers");
 #pragma unroll
             for (int c = 0; c < KPER; ++c) {
-                const float wv = __ldg(w + (size_t)c * DF);
+                const float wv = pf[c];
 #pragma unroll
                 for (int s = 0; s < SPC; ++s) p[s] = fmaf(uo[s][kg * KPER + c], wv, p[s]);
             }
 #pragma unroll
             for (int s = 0; s < SPC; ++s) red[(kg * SPC + s) * DF + j] = p[s];
+        }
+        if (l + 1 < a.ntcm) {   // prefetch: the next TCM's squeeze weights
+            const int n = tid & (CD - 1), kg = tid / CD;
+            const float* w = a.blob + a.desc[l + 1].W_in + (size_t)(kg * (DF / KG1)) * CD + n;
+#pragma unroll
+            for (int k = 0; k < PF; ++k) pf[k] = __ldg(w + (size_t)k * CD);
         }
         __syncthreads();
         if (tid < SPC * DF) {
