@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(NT) tcm_stream_kernel(const TcmStreamArgs a) {
                     for (int s = 0; s < SPC; ++s) p[s] = fmaf(u[br][tap][s][c], pf[k], p[s]);
                 }
             }
-#pragma unroll 12
+#pragma unroll 24
             for (int j = j0 + PF; j < j1; ++j) {
                 const int tap = j / CD, c = j & (CD - 1);
                 const float wv = __ldg(a.blob + d.W_dil + ((size_t)tap * 2 * CD + br * CD + c) * (2 * CD) + col);
